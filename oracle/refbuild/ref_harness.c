@@ -1,0 +1,390 @@
+/* ref_harness.c - drives the UNMODIFIED reference hot path (gravity_tree, density,
+ * force_update_hmax, hydro_force, domain_Decomposition, force_treebuild) on a
+ * particle set read from a file and dumps every output the parity tests compare.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Compiled together with the reference's own sources
+ * where they lie under /root/reference (see Makefile in this directory); the
+ * binary goes to oracle/_ref/ and is never linked into, or called by, the product.
+ *
+ * The set-up sequence follows what the reference does at start-up
+ * (begrun.c:32-, init.c:36-, allocate.c:20, init.c:150-157, init.c:250-252) reduced
+ * to the fields the hot path reads.
+ *
+ * usage: ref_harness <in.glin> <out.glout> "<ops>"
+ *   ops is a blank-separated list, executed in order:
+ *     T  ngb_treebuild()                      (init.c:529)
+ *     S  initial Hsml guess                   (restates init.c:719-745)
+ *     D  density()                            (accel.c:84)
+ *     R  TreeReconstructFlag = 1              (what domain_Decomposition sets, domain.c:135)
+ *     G  gravity_tree()                       (accel.c:61)
+ *     U  force_update_hmax()                  (accel.c:96)
+ *     H  hydro_force()                        (accel.c:106)
+ *     N  dump the node table of the current tree
+ *     C  integer pair counts at the current Hsml via ngb_treefind_variable / _pairs
+ *     A  compute_accelerations-order block:  R G D U H   (accel.c:61-106 without sub-grid physics)
+ *   every op that computes dumps its outputs under the prefix "<k>_<op>_" with k the
+ *   position in the list.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <time.h>
+#include <mpi.h>
+
+#include "allvars.h"
+#include "proto.h"
+
+/* ---- symbols the 13 hot-path files leave undefined ---- */
+double get_drift_factor(int t0, int t1) { (void) t0; (void) t1; return 0; }
+double get_gravkick_factor(int t0, int t1) { (void) t0; (void) t1; return 0; }
+double get_hydrokick_factor(int t0, int t1) { (void) t0; (void) t1; return 0; }
+double hubble_function(double a) { (void) a; return 0; }
+size_t my_fwrite(void *ptr, size_t size, size_t nmemb, FILE * stream) { return fwrite(ptr, size, nmemb, stream); }
+void rearrange_particle_sequence(void) { /* no Mass==0 particles in harness inputs (sfr_eff.c:1018) */ }
+static unsigned long long lcg_state = 42;
+double gsl_rng_uniform(gsl_rng * r)
+{
+  (void) r;
+  lcg_state = lcg_state * 6364136223846793005ULL + 1442695040888963407ULL;
+  return (double) (lcg_state >> 11) / 9007199254740992.0;
+}
+
+/* ---- tiny tagged-array container: see oracle/glio.py for the reader ---- */
+static FILE *fout;
+static void put(const char *prefix, const char *name, char kind, long long n, int ncomp, const void *data)
+{
+  char tag[48];
+  int esz = (kind == 'd' || kind == 'q') ? 8 : 4;
+  memset(tag, 0, sizeof(tag));
+  snprintf(tag, sizeof(tag), "%s%s", prefix, name);
+  fwrite(tag, 1, 48, fout);
+  fwrite(&kind, 1, 1, fout);
+  fwrite(&ncomp, 4, 1, fout);
+  fwrite(&n, 8, 1, fout);
+  fwrite(data, esz, (size_t) n * ncomp, fout);
+}
+static double now(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+#define NPAR 32
+static double par[NPAR];
+enum { P_THETA, P_ERRTOLFORCEACC, P_OPENCRIT, P_DESNUMNGB, P_MAXNGBDEV, P_ARTVISC, P_G, P_SOFT0,
+  P_MINGASHSMLFRAC = P_SOFT0 + 6, P_TIMEBASE_INTERVAL, P_TI_CURRENT, P_BHNGBFACTOR, P_PARTALLOC
+};
+
+static void dump_particles_out(const char *prefix, int what)
+{
+  long long n = NumPart, i;
+  double *d3 = malloc(sizeof(double) * 3 * n), *d1 = malloc(sizeof(double) * n);
+  int *i1 = malloc(sizeof(int) * n);
+  for(i = 0; i < n; i++) i1[i] = (int) P[i].ID;
+  put(prefix, "id", 'i', n, 1, i1);
+  if(what == 'G')
+    {
+      for(i = 0; i < n; i++) { d3[3 * i] = P[i].g.GravAccel[0]; d3[3 * i + 1] = P[i].g.GravAccel[1]; d3[3 * i + 2] = P[i].g.GravAccel[2]; }
+      put(prefix, "GravAccel", 'd', n, 3, d3);
+      for(i = 0; i < n; i++) d1[i] = P[i].OldAcc;
+      put(prefix, "OldAcc", 'd', n, 1, d1);
+      for(i = 0; i < n; i++) d1[i] = P[i].GravCost;
+      put(prefix, "GravCost", 'd', n, 1, d1);
+    }
+  if(what == 'D' || what == 'S')
+    {
+      for(i = 0; i < n; i++) d1[i] = P[i].Hsml;
+      put(prefix, "Hsml", 'd', n, 1, d1);
+    }
+  if(what == 'D')
+    {
+      long long ng = N_gas;
+      for(i = 0; i < n; i++) d1[i] = P[i].n.NumNgb;
+      put(prefix, "NumNgb", 'd', n, 1, d1);
+      for(i = 0; i < ng; i++) d1[i] = SphP[i].d.Density;
+      put(prefix, "Density", 'd', ng, 1, d1);
+      for(i = 0; i < ng; i++) d1[i] = SphP[i].h.DhsmlDensityFactor;
+      put(prefix, "DhsmlDensityFactor", 'd', ng, 1, d1);
+      for(i = 0; i < ng; i++) d1[i] = SphP[i].v.DivVel;
+      put(prefix, "DivVel", 'd', ng, 1, d1);
+      for(i = 0; i < ng; i++) d1[i] = SphP[i].r.CurlVel;
+      put(prefix, "CurlVel", 'd', ng, 1, d1);
+      for(i = 0; i < ng; i++) d1[i] = SphP[i].Pressure;
+      put(prefix, "Pressure", 'd', ng, 1, d1);
+      /* sink (Type 5) / dust (Type 2) targets: density.c:944-988 */
+      for(i = 0; i < n; i++) d1[i] = (P[i].Type == 5) ? P[i].b1.BH_Density : (P[i].Type == 2 ? P[i].d1.DUST_Density : 0);
+      put(prefix, "SinkDensity", 'd', n, 1, d1);
+      for(i = 0; i < n; i++) d1[i] = (P[i].Type == 5) ? P[i].b2.BH_Entropy : (P[i].Type == 2 ? P[i].d2.DUST_Entropy : 0);
+      put(prefix, "SinkEntropy", 'd', n, 1, d1);
+      for(i = 0; i < n; i++)
+	{
+	  int k;
+	  for(k = 0; k < 3; k++)
+	    d3[3 * i + k] = (P[i].Type == 5) ? P[i].b3.BH_SurroundingGasVel[k] : (P[i].Type == 2 ? P[i].d3.DUST_SurroundingGasVel[k] : 0);
+	}
+      put(prefix, "SinkGasVel", 'd', n, 3, d3);
+    }
+  if(what == 'H')
+    {
+      long long ng = N_gas;
+      for(i = 0; i < ng; i++) { d3[3 * i] = SphP[i].a.HydroAccel[0]; d3[3 * i + 1] = SphP[i].a.HydroAccel[1]; d3[3 * i + 2] = SphP[i].a.HydroAccel[2]; }
+      put(prefix, "HydroAccel", 'd', ng, 3, d3);
+      for(i = 0; i < ng; i++) d1[i] = SphP[i].e.DtEntropy;
+      put(prefix, "DtEntropy", 'd', ng, 1, d1);
+      for(i = 0; i < ng; i++) d1[i] = SphP[i].MaxSignalVel;
+      put(prefix, "MaxSignalVel", 'd', ng, 1, d1);
+    }
+  free(d3); free(d1); free(i1);
+}
+
+static void dump_nodes(const char *prefix)
+{
+  long long nn = Numnodestree, k;
+  double *buf = malloc(sizeof(double) * 11 * nn);
+  int *fl = malloc(sizeof(int) * nn);
+  double dom[8];
+  for(k = 0; k < nn; k++)
+    {
+      int no = All.MaxPart + (int) k;
+      buf[11 * k + 0] = Nodes[no].len;
+      buf[11 * k + 1] = Nodes[no].center[0];
+      buf[11 * k + 2] = Nodes[no].center[1];
+      buf[11 * k + 3] = Nodes[no].center[2];
+      buf[11 * k + 4] = Nodes[no].u.d.mass;
+      buf[11 * k + 5] = Nodes[no].u.d.s[0];
+      buf[11 * k + 6] = Nodes[no].u.d.s[1];
+      buf[11 * k + 7] = Nodes[no].u.d.s[2];
+      buf[11 * k + 8] = Nodes[no].maxsoft;
+      buf[11 * k + 9] = Extnodes[no].hmax;
+      buf[11 * k + 10] = Extnodes[no].vmax;
+      fl[k] = Nodes[no].u.d.bitflags;
+    }
+  put(prefix, "nodes", 'd', nn, 11, buf);
+  put(prefix, "nodeflags", 'i', nn, 1, fl);
+  dom[0] = DomainLen; dom[1] = DomainFac;
+  dom[2] = DomainCorner[0]; dom[3] = DomainCorner[1]; dom[4] = DomainCorner[2];
+  dom[5] = DomainCenter[0]; dom[6] = DomainCenter[1]; dom[7] = DomainCenter[2];
+  put(prefix, "domain", 'd', 8, 1, dom);
+  free(buf); free(fl);
+}
+
+/* integer pair counts the reference never stores (density.c:858 is a dead local): re-evaluate the
+ * caller-side tests of density.c:835-856 and hydra.c:1236-1266 on the lists the reference's own
+ * neighbour searches return. */
+static void pair_counts(const char *prefix)
+{
+  long long n = NumPart, i;
+  int *cd = calloc(n, sizeof(int)), *ch = calloc(n, sizeof(int));
+  int dummy = 0, dummy2 = 0;
+  Ngblist = (int *) mymalloc(NumPart * sizeof(int));
+  for(i = 0; i < n; i++)
+    {
+      int startnode, nn, k;
+      double h = P[i].Hsml, h2 = h * h;
+      if(!(P[i].Type == 0 || P[i].Type == 5 || P[i].Type == 2))
+	continue;
+      startnode = All.MaxPart;
+      while(startnode >= 0)
+	{
+	  nn = ngb_treefind_variable(P[i].Pos, h, (int) i, &startnode, 0, &dummy, &dummy2);
+	  for(k = 0; k < nn; k++)
+	    {
+	      int j = Ngblist[k];
+	      double dx, dy, dz, r2;
+	      if(P[j].Mass == 0) continue;
+	      dx = P[i].Pos[0] - P[j].Pos[0]; dy = P[i].Pos[1] - P[j].Pos[1]; dz = P[i].Pos[2] - P[j].Pos[2];
+	      r2 = dx * dx + dy * dy + dz * dz;
+	      if(r2 < h2) cd[i]++;
+	    }
+	}
+      if(P[i].Type != 0)
+	continue;
+      startnode = All.MaxPart;
+      while(startnode >= 0)
+	{
+	  nn = ngb_treefind_pairs(P[i].Pos, h, (int) i, &startnode, 0, &dummy, &dummy2);
+	  for(k = 0; k < nn; k++)
+	    {
+	      int j = Ngblist[k];
+	      double dx, dy, dz, r2, hj;
+	      if(P[j].Mass == 0) continue;
+	      dx = P[i].Pos[0] - P[j].Pos[0]; dy = P[i].Pos[1] - P[j].Pos[1]; dz = P[i].Pos[2] - P[j].Pos[2];
+	      r2 = dx * dx + dy * dy + dz * dz;
+	      hj = P[j].Hsml;
+	      if((r2 < h2 || r2 < hj * hj) && sqrt(r2) > 0) ch[i]++;
+	    }
+	}
+    }
+  myfree(Ngblist);
+  {
+    int *ids = malloc(sizeof(int) * n);
+    for(i = 0; i < n; i++) ids[i] = (int) P[i].ID;
+    put(prefix, "id", 'i', n, 1, ids);
+    free(ids);
+  }
+  put(prefix, "DensPairs", 'i', n, 1, cd);
+  put(prefix, "HydroPairs", 'i', n, 1, ch);
+  free(cd); free(ch);
+}
+
+static void initial_hsml(void)
+{
+  /* restates init.c:719-745 (RestartFlag == 0) */
+  int i, no, p;
+  for(i = 0; i < N_gas; i++)
+    {
+      no = Father[i];
+      while(10 * All.DesNumNgb * P[i].Mass > Nodes[no].u.d.mass)
+	{
+	  p = Nodes[no].u.d.father;
+	  if(p < 0) break;
+	  no = p;
+	}
+      P[i].Hsml = pow(3.0 / (4 * M_PI) * All.DesNumNgb * P[i].Mass / Nodes[no].u.d.mass, 1.0 / 3) * Nodes[no].len;
+      if(P[i].Hsml > 10.0 * All.SofteningTable[0])
+	P[i].Hsml = All.SofteningTable[0];
+    }
+  for(i = 0; i < NumPart; i++)
+    {
+      if(P[i].Type == 5) P[i].Hsml = All.SofteningTable[5];
+      if(P[i].Type == 2) P[i].Hsml = All.SofteningTable[2];
+    }
+}
+
+int main(int argc, char **argv)
+{
+  FILE *fin;
+  char magic[4];
+  int version, i, k;
+  long long N, Ngas;
+  double *pos, *vel, *mass, *hsml, *oldacc, *entropy, *dtentropy;
+  int *type, *id, *timebin;
+  char *ops, *tok;
+  int opidx = 0;
+  double interactions;
+
+  if(argc < 4) { fprintf(stderr, "usage: %s in out \"ops\"\n", argv[0]); return 2; }
+  fin = fopen(argv[1], "rb");
+  if(!fin) { perror(argv[1]); return 2; }
+  if(fread(magic, 1, 4, fin) != 4 || memcmp(magic, "GLIN", 4)) { fprintf(stderr, "bad magic\n"); return 2; }
+  if(fread(&version, 4, 1, fin) != 1 || fread(&N, 8, 1, fin) != 1 || fread(&Ngas, 8, 1, fin) != 1) return 2;
+  if(fread(par, 8, NPAR, fin) != NPAR) return 2;
+#define RD(ptr, T, cnt) do { ptr = malloc(sizeof(T) * (size_t) (cnt) + 8); if(fread(ptr, sizeof(T), (size_t) (cnt), fin) != (size_t) (cnt)) { fprintf(stderr, "short read %s\n", #ptr); return 2; } } while(0)
+  RD(pos, double, 3 * N); RD(vel, double, 3 * N); RD(mass, double, N); RD(type, int, N);
+  RD(hsml, double, N); RD(id, int, N); RD(timebin, int, N); RD(oldacc, double, N);
+  RD(entropy, double, Ngas); RD(dtentropy, double, Ngas);
+  fclose(fin);
+  fout = fopen(argv[2], "wb");
+  if(!fout) { perror(argv[2]); return 2; }
+  fwrite("GLOU", 1, 4, fout);
+
+  MPI_Init(&argc, &argv);
+  ThisTask = 0; NTask = 1; PTask = 0;
+  mymalloc_init();
+  memset(&All, 0, sizeof(All));
+  All.PartAllocFactor = par[P_PARTALLOC] > 0 ? par[P_PARTALLOC] : 1.2;
+  All.TotNumPart = N; All.TotN_gas = Ngas;
+  All.MaxPart = (int) (All.PartAllocFactor * N) + 64;
+  All.MaxPartSph = (int) (All.PartAllocFactor * Ngas) + 64;
+  All.BufferSize = 200;
+  All.TopNodeAllocFactor = 0.02;	/* init.c:156 */
+  All.TreeAllocFactor = 2.0;		/* init.c:157 */
+  All.ErrTolTheta = par[P_THETA];
+  All.ErrTolForceAcc = par[P_ERRTOLFORCEACC];
+  All.TypeOfOpeningCriterion = (int) par[P_OPENCRIT];
+  All.DesNumNgb = (int) par[P_DESNUMNGB];
+  All.MaxNumNgbDeviation = par[P_MAXNGBDEV];
+  All.ArtBulkViscConst = par[P_ARTVISC];
+  All.G = par[P_G];
+  All.SofteningGas = par[P_SOFT0 + 0]; All.SofteningHalo = par[P_SOFT0 + 1]; All.SofteningDisk = par[P_SOFT0 + 2];
+  All.SofteningBulge = par[P_SOFT0 + 3]; All.SofteningStars = par[P_SOFT0 + 4]; All.SofteningBndry = par[P_SOFT0 + 5];
+  All.MinGasHsmlFractional = par[P_MINGASHSMLFRAC];
+  All.Timebase_interval = par[P_TIMEBASE_INTERVAL];
+  All.Ti_Current = (int) par[P_TI_CURRENT];
+  All.BlackHoleNgbFactor = par[P_BHNGBFACTOR];
+  All.TreeDomainUpdateFrequency = 0.1;
+  All.Cadj_Cost = 1.0e-30; All.Cadj_Cpu = 1.0e-3;
+  All.Time = All.TimeBegin = 0; All.TimeMax = 1;
+  All.ComovingIntegrationOn = 0;
+  All.NumForcesSinceLastDomainDecomp = (long long) (1 + All.TotNumPart * All.TreeDomainUpdateFrequency);
+  set_softenings();
+  allocate_memory();
+  set_random_numbers();
+  FdTimings = fopen("/dev/null", "w");
+  FdCPU = fopen("/dev/null", "w");
+
+  NumPart = (int) N; N_gas = (int) Ngas;
+  memset(P, 0, sizeof(struct particle_data) * (size_t) All.MaxPart);
+  memset(SphP, 0, sizeof(struct sph_particle_data) * (size_t) All.MaxPartSph);
+  for(i = 0; i < NumPart; i++)
+    {
+      for(k = 0; k < 3; k++) { P[i].Pos[k] = pos[3 * i + k]; P[i].Vel[k] = vel[3 * i + k]; }
+      P[i].Mass = mass[i]; P[i].Type = type[i]; P[i].ID = id[i]; P[i].Hsml = hsml[i];
+      P[i].TimeBin = timebin[i]; P[i].OldAcc = oldacc[i]; P[i].GravCost = 1;	/* init.c:250-252 */
+      P[i].Ti_current = All.Ti_Current; P[i].Ti_begstep = 0;
+      if(i < N_gas)
+	{
+	  if(type[i] != 0) { fprintf(stderr, "gas must come first\n"); return 2; }
+	  for(k = 0; k < 3; k++) SphP[i].VelPred[k] = vel[3 * i + k];
+	  SphP[i].Entropy = entropy[i]; SphP[i].e.DtEntropy = dtentropy[i]; SphP[i].d.Density = -1;
+	}
+    }
+  for(i = 0; i < TIMEBINS; i++) TimeBinActive[i] = 1;
+  reconstruct_timebins();
+  TreeReconstructFlag = 1;
+  {
+    double t0 = now(), t1;
+    domain_Decomposition();	/* also peano_hilbert_order() and force_treeallocate() */
+    t1 = now() - t0;
+    put("", "time_domain", 'd', 1, 1, &t1);
+  }
+
+  ops = strdup(argv[3]);
+  for(tok = strtok(ops, " "); tok; tok = strtok(NULL, " "), opidx++)
+    {
+      char prefix[32];
+      double t0, dt;
+      const char *seq = tok;
+      if(tok[0] == 'A') seq = "RGDUH";
+      for(; *seq; seq++)
+	{
+	  char op = *seq;
+	  snprintf(prefix, sizeof(prefix), "%d_%c_", opidx, op);
+	  t0 = now();
+	  switch (op)
+	    {
+	    case 'T': ngb_treebuild(); TreeReconstructFlag = 0; break;
+	    case 'S': initial_hsml(); break;
+	    case 'D': density(); break;
+	    case 'R': TreeReconstructFlag = 1; break;
+	    case 'G': gravity_tree(); break;
+	    case 'U': force_update_hmax(); break;
+	    case 'H': hydro_force(); break;
+	    case 'N': dump_nodes(prefix); break;
+	    case 'C': pair_counts(prefix); break;
+	    default: fprintf(stderr, "unknown op %c\n", op); return 2;
+	    }
+	  dt = now() - t0;
+	  if(strchr("TDGUH", op)) put(prefix, "time", 'd', 1, 1, &dt);
+	  if(strchr("GDHS", op)) dump_particles_out(prefix, op);
+	  if(op == 'G')
+	    {
+	      interactions = 0;
+	      for(i = 0; i < NumPart; i++) interactions += P[i].GravCost;
+	      put(prefix, "interactions", 'd', 1, 1, &interactions);
+	      put(prefix, "theta_after", 'd', 1, 1, &All.ErrTolTheta);
+	    }
+	  if(op == 'T' || op == 'G')
+	    {
+	      int nn = Numnodestree;
+	      put(prefix, "numnodes", 'i', 1, 1, &nn);
+	    }
+	}
+    }
+  /* reference time buckets (allvars.h:205-238) */
+  put("", "CPU_Step", 'd', CPU_PARTS, 1, CPU_Step);
+  fclose(fout);
+  return 0;
+}

@@ -1,0 +1,1 @@
+/* empty GSL stand-in: the hot-path sources only need the include to resolve */
