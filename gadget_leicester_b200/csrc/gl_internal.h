@@ -1,0 +1,183 @@
+// gl_internal.h - shared declarations of libgl_b200 (not part of the public ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/gl_b200.h"
+
+#define GL_BITS 21			// BITS_PER_DIMENSION, allvars.h:58
+#define GL_MAXITER 150			// MAXITER, allvars.h:139
+#define GL_WARPS_PER_BLOCK 4
+#define GL_BLOCK (32 * GL_WARPS_PER_BLOCK)
+
+struct gl_error_t { int code; };
+
+#define GL_CUDA(ctx, call)                                                                       \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if(e__ != cudaSuccess) {                                                                     \
+      (ctx)->fail(std::string(#call) + ": " + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
+                  std::to_string(__LINE__));                                                     \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while(0)
+
+// growable device buffer
+template <class T> struct DBuf
+{
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n)
+  {
+    if(n <= cap) return cudaSuccess;
+    if(p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 16 + 64;
+    cudaError_t e = cudaMalloc((void **) &p, want * sizeof(T));
+    if(e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release()
+  {
+    if(p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// domain cube, exactly the quantities of domain.c:2004-2013
+struct gl_domain
+{
+  double len, fac;
+  double corner[3], center[3];
+};
+
+// device-side parameter block (copied by value into kernels)
+struct gl_dparams
+{
+  double theta, errtolforceacc;
+  double soft[6];		// ForceSoftening
+  double G, lambda_fac;
+  double desnumngb, maxdev, bhfac, mingashsml;
+  double artvisc, timebase_interval;
+  int ti_current;
+};
+
+struct gl_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  gl_params par{};
+  bool have_par = false;
+  long long max_part = 0;
+  long long n = 0;		// loaded particles
+  bool tree_flag = true;	// TreeReconstructFlag
+  bool tree_valid = false;
+  bool have_domain = false, domain_imposed = false;
+  gl_domain dom{};
+  long long kernel_launches = 0;
+  gl_stats st{};
+
+  // ---- input-order particle state (index = P[] index) ----
+  DBuf<double> in_pos, in_vel, in_mass, in_hsml, in_oldacc, in_entropy, in_dtentropy;
+  DBuf<int> in_type, in_timebin, in_tibegstep;
+  // ---- keys / sort ----
+  DBuf<unsigned long long> key_m, key_m_sorted, key_ph;
+  DBuf<int> idx, perm;		// perm[sorted] = input index
+  DBuf<int> inv;		// inv[input] = sorted index
+  DBuf<int> ph_order;		// ph_order[k] = tree (Morton) index of the k-th particle along the Peano-Hilbert curve
+  DBuf<unsigned char> cub_tmp;
+  DBuf<double> dom_dev;		// 8 doubles + scratch for the extent reduction
+  // ---- sorted particle state (tree order = Morton order) ----
+  DBuf<double4> s_pm;		// x,y,z,mass
+  DBuf<double4> s_vh;		// vx,vy,vz,hsml
+  DBuf<int> s_type;
+  // ---- tree ----
+  DBuf<signed char> lev_c;	// c[i] common level of sorted keys i-1,i ; c[0]=c[n]=-1
+  DBuf<int> ncnt, noff;		// nodes starting at particle a, exclusive scan
+  long long nnodes = 0, nentries = 0;
+  DBuf<int> n_first, n_end, n_parent;
+  DBuf<signed char> n_level;
+  DBuf<int> lev_list;		// node ids grouped by level
+  int lev_start[GL_BITS + 2]{};
+  DBuf<double4> n_sm;		// s[3], mass
+  DBuf<double4> n_cl;		// center[3], len
+  DBuf<double4> n_aux;		// maxsoft, hmax, vmax, divVmax
+  DBuf<int> p_father;		// Father[] analogue: node id containing sorted particle directly
+  DBuf<int> scan_tmp_i;
+  // ---- walk entries (DFS order, nodes and particle leaves interleaved) ----
+  DBuf<int> e_next;		// node: skip entry; particle: -1-(p*8+type)
+  DBuf<double4> e_A;		// node: s,mass ; particle: pos,mass
+  DBuf<double4> e_B;		// node: center,len ; particle: soft,0,0,-1
+  DBuf<double2> e_C;		// node: maxsoft, mass*len*len ; particle: unused
+  DBuf<double> e_hmax;		// node: hmax (for the symmetric search)
+  // ---- targets ----
+  DBuf<int> tgt_in;		// user-supplied P[] indices (or empty = all)
+  long long n_tgt_in = -1;
+  DBuf<int> tgt_sorted;		// sorted-order indices of the gravity targets
+  DBuf<int> tgt_sph;		// sorted-order indices of SPH targets (gas/sink/dust)
+  DBuf<int> tgt_flag;
+  long long n_tgt = 0, n_tgt_sph = 0, n_tgt_gas = 0;
+  bool tgt_dirty = true;
+  DBuf<int> tgt_gas;
+  // ---- outputs, input order ----
+  DBuf<double> o_acc, o_oldacc, o_numngb, o_density, o_dhsml, o_divvel, o_curlvel, o_pressure, o_sinkrho,
+    o_sinkentr, o_sinkvel, o_hacc, o_dtentr, o_maxsig;
+  DBuf<float> o_gravcost;
+  DBuf<int> o_denspairs, o_hydropairs;
+  DBuf<unsigned long long> d_counter;	// [0] interactions, [1] max passes, [2] error flag
+  // ---- hydro source records (sorted order) ----
+  DBuf<double4> h_q;		// rho, P/rho^2, P/rho^2*Omega, soundspeed
+  DBuf<double2> h_r;		// f (Balsara), timestep
+  // ---- gadget AoS layer ----
+  gl_gadget_layout lay{};
+  bool have_lay = false;
+  long long g_numpart = 0, g_ngas = 0;
+  void *pin = nullptr;
+  size_t pin_cap = 0;
+
+  cudaEvent_t ev[16]{};
+
+  int fail(const std::string &m)
+  {
+    err = m;
+    return 1;
+  }
+};
+
+// gl_keys.cu
+int glk_find_extent(gl_ctx *c);
+int glk_keys_and_sort(gl_ctx *c);
+int glk_export_keys(gl_ctx *c, gl_peanokey *ph, gl_peanokey *mo, int where);
+int glk_ph_order(gl_ctx *c, long long n_gas, int *order, int where);
+// gl_tree.cu
+int glt_build(gl_ctx *c);
+int glt_update_hmax(gl_ctx *c);
+int glt_get_nodes(gl_ctx *c, double *table, long long cap);
+// gl_gravity.cu
+int glg_gravity(gl_ctx *c);
+// gl_sph.cu
+int gls_density(gl_ctx *c);
+int gls_hydro(gl_ctx *c);
+// gl_api.cu
+int gl_prepare_targets(gl_ctx *c);
+
+#define GL_LAUNCH_COUNT(c) ((c)->kernel_launches++)
+
+static inline int gl_grid(long long n, int block) { return (int) ((n + block - 1) / block); }
+
+#ifdef __CUDACC__
+// read-only 32-byte record load as two 16-byte LDG.NC
+__device__ __forceinline__ double4 gl_ld4(const double4 *p)
+{
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+#endif

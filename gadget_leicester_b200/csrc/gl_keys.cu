@@ -1,0 +1,435 @@
+// gl_keys.cu - K1 domain extent, K2 Peano-Hilbert + Morton keys, K3 radix sort + SoA permutation.
+//
+// Reference behaviour reproduced (nothing is copied; the reference is CPU C):
+//   domain_findExtent        domain.c:1972-2014   cube = 1.001 * max extent, fac = 2^21/len
+//   peano_hilbert_key        peano.c:300-316      63-bit key, pix = x->4 | y->2 | z->1 per level
+//   morton_key               peano.c:320-332      z->4, y->2, x->1 per level
+//   peano_hilbert_order      peano.c:25-92        gas block and the rest sorted separately, stable
+//
+// The reference drives its Hilbert key from two 48x8 lookup tables.  Here the same curve is
+// *generated*: the curve is defined by the order in which the 8 octants of a cell are visited
+// (a Gray-code path) and, for every octant, the axis permutation + reflection that maps the
+// parent's frame onto the child's.  Closing that definition under composition yields a 24-state
+// automaton whose keys are identical to the reference's (checked bit-for-bit in tests/).
+#include "gl_internal.h"
+#include <cub/cub.cuh>
+
+// ---------------------------------------------------------------- Hilbert automaton ----
+namespace
+{
+struct Affine3
+{				// T(p) = mask ^ XOR_b (bit b of p ? col[b] : 0), p a 3-bit octant code
+  unsigned char col[3], mask;
+};
+inline unsigned apply(const Affine3 &T, unsigned p)
+{
+  unsigned v = T.mask;
+  for(int b = 0; b < 3; b++)
+    if((p >> b) & 1) v ^= T.col[b];
+  return v;
+}
+inline Affine3 compose(const Affine3 &A, const Affine3 &B)	// A after B
+{
+  Affine3 R;
+  for(int b = 0; b < 3; b++) R.col[b] = (unsigned char) (apply(A, B.col[b]) ^ A.mask);
+  R.mask = (unsigned char) apply(A, B.mask);
+  return R;
+}
+inline bool same(const Affine3 &A, const Affine3 &B)
+{
+  return A.col[0] == B.col[0] && A.col[1] == B.col[1] && A.col[2] == B.col[2] && A.mask == B.mask;
+}
+
+struct HilbertTables
+{
+  unsigned char sub[24][8];	// key digit emitted for octant code pix in state s
+  unsigned char next[24][8];	// successor state
+  int nstates;
+};
+
+// octant code = (x?4)|(y?2)|(z?1).  Visit order of the base cell (position along the curve):
+//   (0,0,0) (0,1,0) (1,1,0) (1,0,0) (1,0,1) (1,1,1) (0,1,1) (0,0,1)
+// rank_of[pix] is the curve position of octant pix.
+const unsigned char kRankOf[8] = { 0, 7, 1, 6, 3, 4, 2, 5 };
+// frame change applied when descending into the octant with (frame-local) code q:
+// {image of bit0(z), bit1(y), bit2(x)}, reflection mask
+const Affine3 kChild[8] = {
+  {{2, 1, 4}, 0}, {{2, 1, 4}, 3}, {{4, 2, 1}, 0}, {{4, 2, 1}, 5},
+  {{1, 2, 4}, 6}, {{1, 2, 4}, 6}, {{4, 2, 1}, 0}, {{4, 2, 1}, 5}
+};
+
+const HilbertTables &hilbert_tables()
+{
+  static HilbertTables T;
+  static bool done = false;
+  if(done) return T;
+  Affine3 states[64];
+  int ns = 1;
+  states[0] = Affine3{{1, 2, 4}, 0};
+  for(int s = 0; s < ns; s++)
+    for(unsigned pix = 0; pix < 8; pix++)
+      {
+	unsigned q = apply(states[s], pix);
+	Affine3 nx = compose(kChild[q], states[s]);
+	int id = -1;
+	for(int k = 0; k < ns; k++)
+	  if(same(states[k], nx)) id = k;
+	if(id < 0)
+	  {
+	    id = ns;
+	    states[ns++] = nx;
+	  }
+	T.sub[s][pix] = kRankOf[q];
+	T.next[s][pix] = (unsigned char) id;
+      }
+  T.nstates = ns;		// 24 for this curve
+  done = true;
+  return T;
+}
+}				// namespace
+
+extern "C" gl_peanokey gl_peano_hilbert_key(int x, int y, int z, int bits)
+{
+  const HilbertTables &T = hilbert_tables();
+  unsigned s = 0;
+  gl_peanokey key = 0;
+  for(int i = bits - 1; i >= 0; i--)
+    {
+      unsigned pix = (((x >> i) & 1) << 2) | (((y >> i) & 1) << 1) | ((z >> i) & 1);
+      key = (key << 3) | T.sub[s][pix];
+      s = T.next[s][pix];
+    }
+  return key;
+}
+
+extern "C" gl_peanokey gl_morton_key(int x, int y, int z, int bits)
+{
+  gl_peanokey m = 0;
+  for(int i = bits - 1; i >= 0; i--)
+    m = (m << 3) | ((((z >> i) & 1) << 2) | (((y >> i) & 1) << 1) | ((x >> i) & 1));
+  return m;
+}
+
+__constant__ unsigned char c_hsub[24 * 8];
+__constant__ unsigned char c_hnext[24 * 8];
+
+static int upload_tables(gl_ctx *c)
+{
+  static bool up = false;
+  if(up) return 0;
+  const HilbertTables &T = hilbert_tables();
+  if(T.nstates != 24) return c->fail("hilbert automaton closure != 24 states");
+  GL_CUDA(c, cudaMemcpyToSymbol(c_hsub, T.sub, 24 * 8));
+  GL_CUDA(c, cudaMemcpyToSymbol(c_hnext, T.next, 24 * 8));
+  up = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------- K1 extent ----
+__global__ void k_extent_partial(const double *__restrict__ pos, long long n, double *__restrict__ part)
+{
+  double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+  for(long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x)
+    {
+#pragma unroll
+      for(int k = 0; k < 3; k++)
+	{
+	  double v = pos[3 * i + k];
+	  lo[k] = fmin(lo[k], v);
+	  hi[k] = fmax(hi[k], v);
+	}
+    }
+  __shared__ double sh[GL_BLOCK / 32][6];
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+    for(int o = 16; o > 0; o >>= 1)
+      {
+	lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+	hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+      }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if(l == 0)
+    for(int k = 0; k < 3; k++)
+      {
+	sh[w][k] = lo[k];
+	sh[w][3 + k] = hi[k];
+      }
+  __syncthreads();
+  if(threadIdx.x == 0)
+    {
+      for(int ww = 1; ww < blockDim.x / 32; ww++)
+	for(int k = 0; k < 3; k++)
+	  {
+	    sh[0][k] = fmin(sh[0][k], sh[ww][k]);
+	    sh[0][3 + k] = fmax(sh[0][3 + k], sh[ww][3 + k]);
+	  }
+      for(int k = 0; k < 6; k++) part[blockIdx.x * 6 + k] = sh[0][k];
+    }
+}
+
+__global__ void k_extent_final(const double *__restrict__ part, int nblocks, double *__restrict__ out6)
+{
+  // single warp
+  double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+  for(int b = threadIdx.x; b < nblocks; b += 32)
+    for(int k = 0; k < 3; k++)
+      {
+	lo[k] = fmin(lo[k], part[b * 6 + k]);
+	hi[k] = fmax(hi[k], part[b * 6 + 3 + k]);
+      }
+  for(int k = 0; k < 3; k++)
+    for(int o = 16; o > 0; o >>= 1)
+      {
+	lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+	hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+      }
+  if(threadIdx.x == 0)
+    for(int k = 0; k < 3; k++)
+      {
+	out6[k] = lo[k];
+	out6[3 + k] = hi[k];
+      }
+}
+
+static void domain_from_minmax(gl_domain &d, const double lo[3], const double hi[3])
+{
+  // domain.c:1999-2013, same operation order
+  double len = 0;
+  for(int j = 0; j < 3; j++)
+    if(hi[j] - lo[j] > len) len = hi[j] - lo[j];
+  len *= 1.001;
+  for(int j = 0; j < 3; j++)
+    {
+      d.center[j] = 0.5 * (lo[j] + hi[j]);
+      d.corner[j] = 0.5 * (lo[j] + hi[j]) - 0.5 * len;
+    }
+  d.len = len;
+  d.fac = 1.0 / len * (double) (1ull << GL_BITS);
+}
+
+int glk_find_extent(gl_ctx *c)
+{
+  if(c->domain_imposed)
+    {
+      c->have_domain = true;
+      return 0;
+    }
+  const int nb = 148 * 4;
+  GL_CUDA(c, c->dom_dev.ensure((size_t) nb * 6 + 16));
+  k_extent_partial<<<nb, GL_BLOCK, 0, c->stream>>>(c->in_pos.p, c->n, c->dom_dev.p + 16);
+  GL_LAUNCH_COUNT(c);
+  k_extent_final<<<1, 32, 0, c->stream>>>(c->dom_dev.p + 16, nb, c->dom_dev.p);
+  GL_LAUNCH_COUNT(c);
+  double mm[6];
+  GL_CUDA(c, cudaMemcpyAsync(mm, c->dom_dev.p, sizeof(mm), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  domain_from_minmax(c->dom, mm, mm + 3);
+  c->have_domain = true;
+  return 0;
+}
+
+extern "C" int gl_domain_set_extent(gl_ctx *c, const double xmin[3], const double xmax[3])
+{
+  domain_from_minmax(c->dom, xmin, xmax);
+  c->have_domain = true;
+  c->domain_imposed = true;
+  c->tree_valid = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------- K2 keys ----
+__device__ __forceinline__ unsigned long long spread3(unsigned v)	// 21 bits -> every 3rd bit
+{
+  unsigned long long x = v & 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__device__ __forceinline__ void grid_coords(const double *__restrict__ pos, long long i, const gl_domain &d, int &ix,
+					     int &iy, int &iz)
+{
+  // (int) ((P[i].Pos[k] - DomainCorner[k]) * DomainFac), forcetree.c:181-183 / domain.c - no FMA contraction
+  ix = (int) __dmul_rn(__dsub_rn(pos[3 * i + 0], d.corner[0]), d.fac);
+  iy = (int) __dmul_rn(__dsub_rn(pos[3 * i + 1], d.corner[1]), d.fac);
+  iz = (int) __dmul_rn(__dsub_rn(pos[3 * i + 2], d.corner[2]), d.fac);
+}
+
+template <bool WITH_PH>
+__global__ void k_keys(const double *__restrict__ pos, long long n, gl_domain d, unsigned long long *__restrict__ mkey,
+		       unsigned long long *__restrict__ phkey, int *__restrict__ idx)
+{
+  __shared__ unsigned char s_sub[192], s_next[192];
+  if(WITH_PH)
+    {
+      for(int t = threadIdx.x; t < 192; t += blockDim.x)
+	{
+	  s_sub[t] = c_hsub[t];
+	  s_next[t] = c_hnext[t];
+	}
+      __syncthreads();
+    }
+  long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  int ix, iy, iz;
+  grid_coords(pos, i, d, ix, iy, iz);
+  mkey[i] = spread3((unsigned) ix) | (spread3((unsigned) iy) << 1) | (spread3((unsigned) iz) << 2);
+  if(idx) idx[i] = (int) i;
+  if(WITH_PH)
+    {
+      unsigned s = 0;
+      unsigned long long key = 0;
+#pragma unroll 1
+      for(int b = GL_BITS - 1; b >= 0; b--)
+	{
+	  unsigned pix = (((ix >> b) & 1) << 2) | (((iy >> b) & 1) << 1) | ((iz >> b) & 1);
+	  unsigned t = s * 8 + pix;
+	  key = (key << 3) | s_sub[t];
+	  s = s_next[t];
+	}
+      phkey[i] = key;
+    }
+}
+
+// PH key from a Morton key: the Morton digit holds (z,y,x) where the Hilbert automaton wants (x,y,z)
+__global__ void k_ph_from_morton(const unsigned long long *__restrict__ mkey, long long n,
+				 unsigned long long *__restrict__ phkey, int *__restrict__ idx)
+{
+  __shared__ unsigned char s_sub[192], s_next[192];
+  for(int t = threadIdx.x; t < 192; t += blockDim.x)
+    {
+      s_sub[t] = c_hsub[t];
+      s_next[t] = c_hnext[t];
+    }
+  __syncthreads();
+  long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const unsigned long long m = mkey[i];
+  unsigned s = 0;
+  unsigned long long key = 0;
+#pragma unroll 1
+  for(int b = GL_BITS - 1; b >= 0; b--)
+    {
+      const unsigned d = (unsigned) (m >> (3 * b)) & 7u;
+      const unsigned pix = ((d & 1u) << 2) | (d & 2u) | (d >> 2);
+      const unsigned t = s * 8 + pix;
+      key = (key << 3) | s_sub[t];
+      s = s_next[t];
+    }
+  phkey[i] = key;
+  idx[i] = (int) i;
+}
+
+// ---------------------------------------------------------------- K3 sort + gather ----
+__global__ void k_gather_sorted(long long n, const int *__restrict__ perm, const double *__restrict__ pos,
+				const double *__restrict__ vel, const double *__restrict__ mass,
+				const double *__restrict__ hsml, const int *__restrict__ type,
+				double4 *__restrict__ s_pm, double4 *__restrict__ s_vh, int *__restrict__ s_type,
+				int *__restrict__ inv)
+{
+  long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  int j = perm[i];
+  s_pm[i] = make_double4(pos[3ll * j], pos[3ll * j + 1], pos[3ll * j + 2], mass[j]);
+  s_vh[i] = make_double4(vel[3ll * j], vel[3ll * j + 1], vel[3ll * j + 2], hsml[j]);
+  s_type[i] = type[j];
+  inv[j] = (int) i;
+}
+
+static int sort_pairs(gl_ctx *c, const unsigned long long *kin, unsigned long long *kout, const int *vin, int *vout,
+		      long long n)
+{
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, (int) n, 0, 63, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, kin, kout, vin, vout, (int) n, 0, 63, c->stream));
+  c->kernel_launches += 5;	// onesweep: histogram + exclusive sum + ~3 digit passes (library-issued)
+  return 0;
+}
+
+int glk_keys_and_sort(gl_ctx *c)
+{
+  long long n = c->n;
+  if(upload_tables(c)) return 1;
+  if(!c->have_domain)
+    if(glk_find_extent(c)) return 1;
+  GL_CUDA(c, c->key_m.ensure(n));
+  GL_CUDA(c, c->key_m_sorted.ensure(n));
+  GL_CUDA(c, c->idx.ensure(n));
+  GL_CUDA(c, c->perm.ensure(n));
+  GL_CUDA(c, c->inv.ensure(n));
+  GL_CUDA(c, c->s_pm.ensure(n + 1));
+  GL_CUDA(c, c->s_vh.ensure(n + 1));
+  GL_CUDA(c, c->s_type.ensure(n + 1));
+  k_keys<false><<<gl_grid(n, 256), 256, 0, c->stream>>>(c->in_pos.p, n, c->dom, c->key_m.p, nullptr, c->idx.p);
+  GL_LAUNCH_COUNT(c);
+  if(sort_pairs(c, c->key_m.p, c->key_m_sorted.p, c->idx.p, c->perm.p, n)) return 1;
+  k_gather_sorted<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->perm.p, c->in_pos.p, c->in_vel.p, c->in_mass.p,
+							  c->in_hsml.p, c->in_type.p, c->s_pm.p, c->s_vh.p,
+							  c->s_type.p, c->inv.p);
+  GL_LAUNCH_COUNT(c);
+  // Peano-Hilbert sequence of the tree-ordered particles: target groups (one warp = 32 consecutive
+  // targets) are formed along the Hilbert curve, which never jumps, so a group's bounding box stays
+  // compact; along the Morton curve the groups that straddle an octant boundary span the whole cell.
+  GL_CUDA(c, c->key_ph.ensure(n));
+  GL_CUDA(c, c->ph_order.ensure(n + 1));
+  k_ph_from_morton<<<gl_grid(n, 256), 256, 0, c->stream>>>(c->key_m_sorted.p, n, c->key_ph.p, c->idx.p);
+  GL_LAUNCH_COUNT(c);
+  if(sort_pairs(c, c->key_ph.p, c->key_m.p, c->idx.p, c->ph_order.p, n)) return 1;
+  GL_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int glk_export_keys(gl_ctx *c, gl_peanokey *ph, gl_peanokey *mo, int where)
+{
+  long long n = c->n;
+  if(upload_tables(c)) return 1;
+  if(!c->have_domain)
+    if(glk_find_extent(c)) return 1;
+  GL_CUDA(c, c->key_m.ensure(n));
+  GL_CUDA(c, c->key_ph.ensure(n));
+  k_keys<true><<<gl_grid(n, 256), 256, 0, c->stream>>>(c->in_pos.p, n, c->dom, c->key_m.p, c->key_ph.p, nullptr);
+  GL_LAUNCH_COUNT(c);
+  cudaMemcpyKind kind = where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if(ph) GL_CUDA(c, cudaMemcpyAsync(ph, c->key_ph.p, n * sizeof(gl_peanokey), kind, c->stream));
+  if(mo) GL_CUDA(c, cudaMemcpyAsync(mo, c->key_m.p, n * sizeof(gl_peanokey), kind, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->tree_valid = false;	// key_m scratch is shared with the tree build
+  return 0;
+}
+
+__global__ void k_iota(int *p, long long n, int base)
+{
+  long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i < n) p[i] = base + (int) i;
+}
+
+int glk_ph_order(gl_ctx *c, long long n_gas, int *order, int where)
+{
+  long long n = c->n;
+  if(n_gas < 0 || n_gas > n) return c->fail("gl_peano_hilbert_order: bad n_gas");
+  if(upload_tables(c)) return 1;
+  if(!c->have_domain)
+    if(glk_find_extent(c)) return 1;
+  GL_CUDA(c, c->key_m.ensure(n));
+  GL_CUDA(c, c->key_ph.ensure(n));
+  GL_CUDA(c, c->key_m_sorted.ensure(n));
+  GL_CUDA(c, c->idx.ensure(n));
+  GL_CUDA(c, c->perm.ensure(n));
+  k_keys<true><<<gl_grid(n, 256), 256, 0, c->stream>>>(c->in_pos.p, n, c->dom, c->key_m.p, c->key_ph.p, c->idx.p);
+  GL_LAUNCH_COUNT(c);
+  // peano.c:37-62 gas block, :64-88 the rest; mysort_peano is a stable merge sort, radix sort is stable too
+  if(n_gas > 0)
+    if(sort_pairs(c, c->key_ph.p, c->key_m_sorted.p, c->idx.p, c->perm.p, n_gas)) return 1;
+  if(n - n_gas > 0)
+    if(sort_pairs(c, c->key_ph.p + n_gas, c->key_m_sorted.p + n_gas, c->idx.p + n_gas, c->perm.p + n_gas, n - n_gas))
+      return 1;
+  cudaMemcpyKind kind = where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  GL_CUDA(c, cudaMemcpyAsync(order, c->perm.p, n * sizeof(int), kind, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->tree_valid = false;
+  return 0;
+}

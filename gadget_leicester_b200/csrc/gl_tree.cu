@@ -1,0 +1,463 @@
+// gl_tree.cu - K4 bottom-up oct-tree from sorted Morton keys, K5 node moments, K9 hmax refresh.
+//
+// What the reference does (forcetree.c): force_treebuild_single (:125-373) inserts particles one by
+// one into a top-down oct-tree on the 21-bit domain grid; force_update_node_recursive (:468-872)
+// then computes, post-order and in child-slot order 0..7 (x->bit0, y->bit1, z->bit2), the FP64
+// moments mass, s, hmax, vmax, maxsoft, and threads the tree (nextnode / sibling) for a stackless
+// walk.  The set of nodes that can ever take part in an interaction is exactly "every oct-tree cell
+// that holds >= 2 particles"; empty cells and single-particle cells of its always-complete top tree
+// are opened without an interaction (forcetree.c:1996-2004) or carry zero mass.
+//
+// B200 design: particles are radix-sorted by Morton key (child-slot order == key order), so
+//   c[i]  = number of oct-tree levels the keys i-1 and i share (c[0] = c[n] = -1)
+// fully determines the tree.  A cell at level L whose first particle is a exists iff
+// c[a] < L <= c[a+1]; so particle a opens max(0, c[a+1]-c[a]) nodes, one exclusive scan numbers all
+// nodes, and that numbering IS the DFS pre-order the reference threads with nextnode/sibling:
+//   node id = noff[a] + (L - c[a] - 1),  DFS entry index of the node = a + id,
+//   DFS entry index of particle p = p + noff[p+1],  "sibling" of a node = entry index of its end.
+// Moments are then evaluated level by level from the leaves up, each node summing its children in
+// key order - the same FP64 operation order as the reference, hence bit-identical mass/s.
+#include "gl_internal.h"
+#include <cub/cub.cuh>
+
+__device__ __forceinline__ int common_level(unsigned long long a, unsigned long long b)
+{
+  unsigned long long x = a ^ b;
+  if(x == 0) return GL_BITS;
+  int p = 63 - __clzll((long long) x);	// highest differing bit, 0..62
+  return (62 - p) / 3;
+}
+
+__global__ void k_levels(const unsigned long long *__restrict__ key, long long n, signed char *__restrict__ c)
+{
+  long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i > n) return;
+  if(i == 0 || i == n)
+    c[i] = -1;
+  else
+    c[i] = (signed char) common_level(key[i - 1], key[i]);
+}
+
+__global__ void k_count(const signed char *__restrict__ c, long long n, int *__restrict__ cnt)
+{
+  long long a = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(a > n) return;
+  int v = 0;
+  if(a < n)
+    {
+      v = (int) c[a + 1] - (int) c[a];
+      if(v < 0) v = 0;
+    }
+  cnt[a] = v;
+}
+
+__global__ void k_make_nodes(const signed char *__restrict__ c, const int *__restrict__ noff, long long n,
+			     int *__restrict__ n_first, signed char *__restrict__ n_level, int *__restrict__ levcount)
+{
+  __shared__ int sh[GL_BITS + 1];
+  if(threadIdx.x <= GL_BITS) sh[threadIdx.x] = 0;
+  __syncthreads();
+  long long a = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(a < n)
+    {
+      int c0 = c[a], c1 = c[a + 1];
+      int base = noff[a];
+      for(int L = c0 + 1; L <= c1; L++)
+	{
+	  int id = base + (L - c0 - 1);
+	  n_first[id] = (int) a;
+	  n_level[id] = (signed char) L;
+	  atomicAdd(&sh[L], 1);
+	}
+    }
+  __syncthreads();
+  if(threadIdx.x <= GL_BITS && sh[threadIdx.x]) atomicAdd(&levcount[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void k_fill_levels(const signed char *__restrict__ n_level, long long m, int *__restrict__ cursor,
+			      int *__restrict__ lev_list)
+{
+  long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  bool ok = id < m;
+  int L = ok ? n_level[id] : 31;
+  unsigned peers = __match_any_sync(0xffffffffu, L);
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(peers) - 1;
+  int rank = __popc(peers & ((1u << lane) - 1));
+  int base = 0;
+  if(ok && lane == leader) base = atomicAdd(&cursor[L], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if(ok) lev_list[base + rank] = (int) id;
+}
+
+// first index j in (lo, hi] such that (key[j] >> sh) != pref, or hi if none; galloping then bisection
+__device__ __forceinline__ int range_end(const unsigned long long *__restrict__ key, int lo, int hi, int sh,
+					 unsigned long long pref)
+{
+  int step = 1, good = lo;	// key[good] matches
+  int bad = hi;			// first known non-match (or hi)
+  while(true)
+    {
+      long long probe = (long long) good + step;
+      if(probe >= hi) break;
+      if((key[probe] >> sh) == pref)
+	{
+	  good = (int) probe;
+	  step <<= 1;
+	}
+      else
+	{
+	  bad = (int) probe;
+	  break;
+	}
+    }
+  while(bad - good > 1)
+    {
+      int mid = good + (bad - good) / 2;
+      if((key[mid] >> sh) == pref)
+	good = mid;
+      else
+	bad = mid;
+    }
+  return bad;
+}
+
+__global__ void k_moments(int L, const int *__restrict__ lev_list, int count, const unsigned long long *__restrict__ key,
+			  long long n, const signed char *__restrict__ c, const int *__restrict__ noff,
+			  const int *__restrict__ n_first, int *__restrict__ n_end, int *__restrict__ n_parent,
+			  int *__restrict__ p_father, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
+			  const int *__restrict__ s_type, double4 *__restrict__ n_sm, double4 *__restrict__ n_cl,
+			  double4 *__restrict__ n_aux, gl_domain dom, gl_dparams par)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= count) return;
+  int id = lev_list[t];
+  int a = n_first[id];
+  unsigned long long ka = key[a];
+  int b;
+  if(L == 0)
+    b = (int) n;
+  else
+    {
+      int sh = 3 * (GL_BITS - L);
+      b = range_end(key, a, (int) n, sh, ka >> sh);
+    }
+  n_end[id] = b;
+  if(L == 0) n_parent[id] = -1;
+
+  // geometric centre and side length: root = domain cube, then the +-len/4 steps of forcetree.c:259-277 / :404-411
+  double len = dom.len, cx = dom.center[0], cy = dom.center[1], cz = dom.center[2];
+  for(int lev = 1; lev <= L; lev++)
+    {
+      int d = (int) ((ka >> (3 * (GL_BITS - lev))) & 7);
+      double lenhalf = __dmul_rn(0.25, len);
+      cx = (d & 1) ? __dadd_rn(cx, lenhalf) : __dsub_rn(cx, lenhalf);
+      cy = (d & 2) ? __dadd_rn(cy, lenhalf) : __dsub_rn(cy, lenhalf);
+      cz = (d & 4) ? __dadd_rn(cz, lenhalf) : __dsub_rn(cz, lenhalf);
+      len = __dmul_rn(0.5, len);
+    }
+
+  // children in slot order (forcetree.c:543-729)
+  double mass = 0, s0 = 0, s1 = 0, s2 = 0, hmax = 0, vmax = 0, maxsoft = 0;
+  int p = a;
+  int sh2 = 3 * (GL_BITS - 1 - L);
+  while(p < b)
+    {
+      int q = p + 1;
+      if(L < GL_BITS && q < b) q = range_end(key, p, b, sh2, key[p] >> sh2);
+      if(q - p == 1 || L >= GL_BITS)
+	{
+	  // particle leaf (for L == GL_BITS every particle of the finest cell hangs directly below)
+	  q = p + 1;
+	  double4 pm = s_pm[p];
+	  double4 vh = s_vh[p];
+	  int ty = s_type[p];
+	  mass = __dadd_rn(mass, pm.w);
+	  s0 = __dadd_rn(s0, __dmul_rn(pm.w, pm.x));
+	  s1 = __dadd_rn(s1, __dmul_rn(pm.w, pm.y));
+	  s2 = __dadd_rn(s2, __dmul_rn(pm.w, pm.z));
+	  if(ty == 0)
+	    {
+	      if(vh.w > hmax) hmax = vh.w;
+	      if(vh.w > maxsoft) maxsoft = vh.w;
+	    }
+	  else if(par.soft[ty] > maxsoft)
+	    maxsoft = par.soft[ty];
+	  vmax = fmax(vmax, fmax(fabs(vh.x), fmax(fabs(vh.y), fabs(vh.z))));
+	  p_father[p] = id;
+	}
+      else
+	{
+	  int child = noff[p] + (L - (int) c[p]);
+	  double4 cs = n_sm[child];
+	  double4 ca = n_aux[child];
+	  mass = __dadd_rn(mass, cs.w);
+	  s0 = __dadd_rn(s0, __dmul_rn(cs.w, cs.x));
+	  s1 = __dadd_rn(s1, __dmul_rn(cs.w, cs.y));
+	  s2 = __dadd_rn(s2, __dmul_rn(cs.w, cs.z));
+	  if(ca.y > hmax) hmax = ca.y;
+	  if(ca.z > vmax) vmax = ca.z;
+	  if(ca.x > maxsoft) maxsoft = ca.x;
+	  n_parent[child] = id;
+	}
+      p = q;
+    }
+  if(mass != 0)
+    {
+      s0 = __ddiv_rn(s0, mass);
+      s1 = __ddiv_rn(s1, mass);
+      s2 = __ddiv_rn(s2, mass);
+    }
+  else
+    {
+      s0 = cx;
+      s1 = cy;
+      s2 = cz;
+    }
+  n_sm[id] = make_double4(s0, s1, s2, mass);
+  n_cl[id] = make_double4(cx, cy, cz, len);
+  n_aux[id] = make_double4(maxsoft, hmax, vmax, 0.0);
+}
+
+__global__ void k_entries_particles(long long n, const int *__restrict__ noff, const double4 *__restrict__ s_pm,
+				    const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
+				    int *__restrict__ e_next, double4 *__restrict__ e_A, double4 *__restrict__ e_B,
+				    double2 *__restrict__ e_C, double *__restrict__ e_hmax, gl_dparams par)
+{
+  long long p = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(p >= n) return;
+  long long e = p + noff[p + 1];
+  int ty = s_type[p];
+  double soft = (ty == 0) ? s_vh[p].w : par.soft[ty];
+  e_next[e] = -1 - (int) (p * 8 + ty);
+  e_A[e] = s_pm[p];
+  e_B[e] = make_double4(soft, 0.0, 0.0, -1.0);
+  e_C[e] = make_double2(0.0, 0.0);
+  e_hmax[e] = 0.0;
+}
+
+__global__ void k_entries_nodes(long long m, long long n, const int *__restrict__ noff, const int *__restrict__ n_first,
+				const int *__restrict__ n_end, const double4 *__restrict__ n_sm,
+				const double4 *__restrict__ n_cl, const double4 *__restrict__ n_aux,
+				int *__restrict__ e_next, double4 *__restrict__ e_A, double4 *__restrict__ e_B,
+				double2 *__restrict__ e_C, double *__restrict__ e_hmax)
+{
+  long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(id >= m) return;
+  long long e = (long long) n_first[id] + id;
+  int b = n_end[id];
+  e_next[e] = b + noff[b];	// "sibling": first DFS entry behind this subtree
+  double4 sm = n_sm[id];
+  double4 cl = n_cl[id];
+  double4 ax = n_aux[id];
+  e_A[e] = sm;
+  e_B[e] = cl;
+  // mass * nop->len * nop->len, evaluated left to right as in forcetree.c:2085
+  e_C[e] = make_double2(ax.x, __dmul_rn(__dmul_rn(sm.w, cl.w), cl.w));
+  e_hmax[e] = ax.y;
+}
+
+static int scan_exclusive(gl_ctx *c, const int *in, int *out, long long n)
+{
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int) n, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, in, out, (int) n, c->stream));
+  c->kernel_launches += 2;
+  return 0;
+}
+
+gl_dparams gl_make_dparams(const gl_ctx *c)
+{
+  gl_dparams d{};
+  d.theta = c->par.ErrTolTheta;
+  d.errtolforceacc = c->par.ErrTolForceAcc;
+  for(int i = 0; i < 6; i++) d.soft[i] = c->par.ForceSoftening[i];
+  d.G = c->par.G;
+  d.lambda_fac = c->par.OmegaLambdaHubble2;
+  d.desnumngb = c->par.DesNumNgb;
+  d.maxdev = c->par.MaxNumNgbDeviation;
+  d.bhfac = c->par.BlackHoleNgbFactor;
+  d.mingashsml = c->par.MinGasHsml;
+  d.artvisc = c->par.ArtBulkViscConst;
+  d.timebase_interval = c->par.Timebase_interval;
+  d.ti_current = c->par.Ti_Current;
+  return d;
+}
+
+int glt_build(gl_ctx *c)
+{
+  long long n = c->n;
+  if(n <= 0) return c->fail("force_treebuild: no particles loaded");
+  if(!c->have_par) return c->fail("force_treebuild: gl_set_params not called");
+  cudaEventRecord(c->ev[0], c->stream);
+  if(glk_keys_and_sort(c)) return 1;
+  cudaEventRecord(c->ev[1], c->stream);
+  const unsigned long long *key = c->key_m_sorted.p;
+  GL_CUDA(c, c->lev_c.ensure(n + 2));
+  GL_CUDA(c, c->ncnt.ensure(n + 2));
+  GL_CUDA(c, c->noff.ensure(n + 2));
+  GL_CUDA(c, c->scan_tmp_i.ensure(64));
+  k_levels<<<gl_grid(n + 1, 256), 256, 0, c->stream>>>(key, n, c->lev_c.p);
+  k_count<<<gl_grid(n + 1, 256), 256, 0, c->stream>>>(c->lev_c.p, n, c->ncnt.p);
+  c->kernel_launches += 2;
+  if(scan_exclusive(c, c->ncnt.p, c->noff.p, n + 1)) return 1;
+  int m = 0;
+  GL_CUDA(c, cudaMemcpyAsync(&m, c->noff.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->nnodes = m;
+  c->nentries = n + m;
+  if(c->nentries >= (1ll << 28)) return c->fail("force_treebuild: more than 2^28 tree entries (index encoding limit)");
+  size_t mm = (size_t) m + 1;
+  GL_CUDA(c, c->n_first.ensure(mm));
+  GL_CUDA(c, c->n_end.ensure(mm));
+  GL_CUDA(c, c->n_parent.ensure(mm));
+  GL_CUDA(c, c->n_level.ensure(mm));
+  GL_CUDA(c, c->lev_list.ensure(mm));
+  GL_CUDA(c, c->n_sm.ensure(mm));
+  GL_CUDA(c, c->n_cl.ensure(mm));
+  GL_CUDA(c, c->n_aux.ensure(mm));
+  GL_CUDA(c, c->p_father.ensure(n + 1));
+  int *levcount = c->scan_tmp_i.p;	// [0..21] counts, [32..53] cursors
+  GL_CUDA(c, cudaMemsetAsync(levcount, 0, 64 * sizeof(int), c->stream));
+  GL_CUDA(c, cudaMemsetAsync(c->p_father.p, 0xff, (n + 1) * sizeof(int), c->stream));
+  int hcount[GL_BITS + 1];
+  if(m > 0)
+    {
+      k_make_nodes<<<gl_grid(n, 256), 256, 0, c->stream>>>(c->lev_c.p, c->noff.p, n, c->n_first.p, c->n_level.p,
+							  levcount);
+      GL_LAUNCH_COUNT(c);
+      GL_CUDA(c, cudaMemcpyAsync(hcount, levcount, sizeof(hcount), cudaMemcpyDeviceToHost, c->stream));
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      int start = 0, hcur[GL_BITS + 1];
+      for(int L = 0; L <= GL_BITS; L++)
+	{
+	  c->lev_start[L] = start;
+	  hcur[L] = start;
+	  start += hcount[L];
+	}
+      c->lev_start[GL_BITS + 1] = start;
+      if(start != m) return c->fail("force_treebuild: level histogram does not add up");
+      GL_CUDA(c, cudaMemcpyAsync(levcount + 32, hcur, sizeof(hcur), cudaMemcpyHostToDevice, c->stream));
+      k_fill_levels<<<gl_grid(m, 256), 256, 0, c->stream>>>(c->n_level.p, m, levcount + 32, c->lev_list.p);
+      GL_LAUNCH_COUNT(c);
+    }
+  cudaEventRecord(c->ev[2], c->stream);
+  gl_dparams dp = gl_make_dparams(c);
+  if(m > 0)
+    for(int L = GL_BITS; L >= 0; L--)
+      {
+	int cnt = c->lev_start[L + 1] - c->lev_start[L];
+	if(cnt <= 0) continue;
+	k_moments<<<gl_grid(cnt, 128), 128, 0, c->stream>>>(L, c->lev_list.p + c->lev_start[L], cnt, key, n, c->lev_c.p,
+							   c->noff.p, c->n_first.p, c->n_end.p, c->n_parent.p,
+							   c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->n_sm.p,
+							   c->n_cl.p, c->n_aux.p, c->dom, dp);
+	GL_LAUNCH_COUNT(c);
+      }
+  size_t ne = (size_t) c->nentries + 1;
+  GL_CUDA(c, c->e_next.ensure(ne));
+  GL_CUDA(c, c->e_A.ensure(ne));
+  GL_CUDA(c, c->e_B.ensure(ne));
+  GL_CUDA(c, c->e_C.ensure(ne));
+  GL_CUDA(c, c->e_hmax.ensure(ne));
+  k_entries_particles<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->noff.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
+							      c->e_next.p, c->e_A.p, c->e_B.p, c->e_C.p, c->e_hmax.p, dp);
+  GL_LAUNCH_COUNT(c);
+  if(m > 0)
+    {
+      k_entries_nodes<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, n, c->noff.p, c->n_first.p, c->n_end.p, c->n_sm.p,
+							       c->n_cl.p, c->n_aux.p, c->e_next.p, c->e_A.p, c->e_B.p,
+							       c->e_C.p, c->e_hmax.p);
+      GL_LAUNCH_COUNT(c);
+    }
+  cudaEventRecord(c->ev[3], c->stream);
+  GL_CUDA(c, cudaGetLastError());
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->st.ms_keys_sort = ms;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+  c->st.ms_treebuild = ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+  c->st.ms_moments = ms;
+  c->st.numnodes = m;
+  c->st.numentries = c->nentries;
+  c->tree_valid = true;
+  c->tree_flag = false;
+  c->tgt_dirty = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------- K9 hmax refresh ----
+// forcetree.c:1661-1705: from every active gas particle climb the father chain while the particle's
+// Hsml raises the node's hmax.  Positive doubles order like their bit patterns, so an unsigned
+// 64-bit atomicMax implements "if(h > hmax) hmax = h" without a lock.
+__global__ void k_update_hmax(const int *__restrict__ tgt, long long nt, const double4 *__restrict__ s_vh,
+			      const int *__restrict__ p_father, const int *__restrict__ n_parent,
+			      const int *__restrict__ n_first, double *__restrict__ e_hmax)
+{
+  long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(t >= nt) return;
+  int p = tgt[t];
+  double h = s_vh[p].w;
+  unsigned long long hb = (unsigned long long) __double_as_longlong(h);
+  int no = p_father[p];
+  while(no >= 0)
+    {
+      unsigned long long *addr = (unsigned long long *) &e_hmax[(long long) n_first[no] + no];
+      unsigned long long old = atomicMax(addr, hb);
+      if(old >= hb) break;
+      no = n_parent[no];
+    }
+}
+
+int glt_update_hmax(gl_ctx *c)
+{
+  if(!c->tree_valid) return c->fail("force_update_hmax: no tree");
+  if(gl_prepare_targets(c)) return 1;
+  cudaEventRecord(c->ev[0], c->stream);
+  if(c->n_tgt_gas > 0)
+    {
+      k_update_hmax<<<gl_grid(c->n_tgt_gas, 256), 256, 0, c->stream>>>(c->tgt_gas.p, c->n_tgt_gas, c->s_vh.p,
+								       c->p_father.p, c->n_parent.p, c->n_first.p,
+								       c->e_hmax.p);
+      GL_LAUNCH_COUNT(c);
+    }
+  cudaEventRecord(c->ev[1], c->stream);
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->st.ms_hmax = ms;
+  return 0;
+}
+
+__global__ void k_node_table(long long m, const int *__restrict__ n_first, const signed char *__restrict__ n_level,
+			     const double4 *__restrict__ n_sm, const double4 *__restrict__ n_cl,
+			     const double4 *__restrict__ n_aux, const double *__restrict__ e_hmax, double *__restrict__ out)
+{
+  long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(id >= m) return;
+  double4 sm = n_sm[id], cl = n_cl[id], ax = n_aux[id];
+  double *o = out + 12 * id;
+  o[0] = cl.w; o[1] = cl.x; o[2] = cl.y; o[3] = cl.z;
+  o[4] = sm.w; o[5] = sm.x; o[6] = sm.y; o[7] = sm.z;
+  o[8] = ax.x; o[9] = e_hmax[(long long) n_first[id] + id]; o[10] = ax.z; o[11] = (double) n_level[id];
+}
+
+int glt_get_nodes(gl_ctx *c, double *table, long long cap)
+{
+  if(!c->tree_valid) return c->fail("gl_get_nodes: no tree");
+  long long m = c->nnodes;
+  if(cap < m) return c->fail("gl_get_nodes: buffer too small");
+  if(m == 0) return 0;
+  DBuf<double> tmp;
+  GL_CUDA(c, tmp.ensure((size_t) m * 12));
+  k_node_table<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->n_first.p, c->n_level.p, c->n_sm.p, c->n_cl.p, c->n_aux.p,
+							c->e_hmax.p, tmp.p);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaMemcpyAsync(table, tmp.p, (size_t) m * 12 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  tmp.release();
+  return 0;
+}

@@ -1,0 +1,182 @@
+"""Host-side mirror of the reference's operator interface for the force path.
+
+The reference exposes global C symbols acting on global arrays (proto.h:281,295,331,332;
+forcetree.h:48,67,86).  `ForcePath` keeps the same entry-point names, argument meaning and
+side effects, but on an explicit object: `P` is a dict of numpy arrays laid out like P[]/SphP[]
+(see ics.py), and every method calls straight into libgl_b200.so (the CUDA path).  Errors from
+the library raise GLError - the analogue of endrun(code) (endrun.c:23).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as L
+
+
+class ForcePath:
+    def __init__(self, params, device=0, max_part=0):
+        self._lib = L.load_library()
+        self._ctx = C.c_void_p()
+        if self._lib.gl_create(C.byref(self._ctx), int(device), int(max_part)) != 0:
+            raise L.GLError("gl_create failed: no usable CUDA device (libgl_b200 has no CPU fallback)")
+        self.params = dict(params)
+        self._gp = L.make_params(self.params)
+        self._chk(self._lib.gl_set_params(self._ctx, C.byref(self._gp)))
+        self.N = 0
+        self.P = None
+
+    # -- plumbing ------------------------------------------------------------------------
+    def _chk(self, rc):
+        if rc != 0:
+            raise L.GLError(self._lib.gl_last_error(self._ctx).decode())
+
+    def close(self):
+        if self._ctx:
+            self._lib.gl_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ctx(self):
+        return self._ctx
+
+    def set_ErrTolTheta(self, theta):
+        """All.ErrTolTheta (gravtree.c:396-397 sets it to 0 after the first call)."""
+        self._gp.ErrTolTheta = theta
+        self._chk(self._lib.gl_set_params(self._ctx, C.byref(self._gp)))
+
+    def set_params(self, **kw):
+        self.params.update(kw)
+        self._gp = L.make_params(self.params)
+        self._chk(self._lib.gl_set_params(self._ctx, C.byref(self._gp)))
+
+    # -- particle state ------------------------------------------------------------------
+    def load(self, P):
+        """Upload P[]/SphP[] (host numpy arrays, gas first).  The analogue of the state the
+        reference's entry points find in its globals when they are called."""
+        self.P = P
+        n = P["pos"].shape[0]
+        self.N = n
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        self._keep = [f64(P["pos"]), f64(P["vel"]), f64(P["mass"]), i32(P["type"]), f64(P["hsml"]), f64(P["oldacc"]),
+                      i32(P["timebin"]), i32(P.get("ti_begstep", np.zeros(n, np.int32))), f64(P["entropy"]),
+                      f64(P["dtentropy"])]
+        self._chk(self._lib.gl_load_particles(self._ctx, n, *[L._ptr(a) for a in self._keep], 0))
+
+    def load_device(self, n, ptrs):
+        """Same as load() but from device pointers (ints), in gl_load_particles order; 0 = absent."""
+        self.N = int(n)
+        self._chk(self._lib.gl_load_particles(self._ctx, int(n), *[C.c_void_p(p) if p else None for p in ptrs], 1))
+
+    def set_targets(self, index=None):
+        """Active list (FirstActiveParticle/NextActiveParticle) or a GPU's Peano-Hilbert segment."""
+        if index is None:
+            self._chk(self._lib.gl_set_targets(self._ctx, None, -1, 0))
+        else:
+            idx = np.ascontiguousarray(index, dtype=np.int32)
+            self._chk(self._lib.gl_set_targets(self._ctx, L._ptr(idx), idx.size, 0))
+
+    # -- domain / keys -------------------------------------------------------------------
+    def domain_findExtent(self):
+        out = np.zeros(8)
+        self._chk(self._lib.gl_domain_find_extent(self._ctx, out.ctypes.data_as(L.c_double_p)))
+        return dict(DomainLen=out[0], DomainFac=out[1], DomainCorner=out[2:5].copy(), DomainCenter=out[5:8].copy())
+
+    def domain_setExtent(self, xmin, xmax):
+        a = np.ascontiguousarray(xmin, dtype=np.float64)
+        b = np.ascontiguousarray(xmax, dtype=np.float64)
+        self._chk(self._lib.gl_domain_set_extent(self._ctx, a.ctypes.data_as(L.c_double_p),
+                                                 b.ctypes.data_as(L.c_double_p)))
+
+    def peano_and_morton_keys(self):
+        ph = np.zeros(self.N, dtype=np.uint64)
+        mo = np.zeros(self.N, dtype=np.uint64)
+        self._chk(self._lib.gl_peano_keys(self._ctx, L._ptr(ph), L._ptr(mo), 0))
+        return ph, mo
+
+    def peano_hilbert_order(self, n_gas):
+        order = np.zeros(self.N, dtype=np.int32)
+        self._chk(self._lib.gl_peano_hilbert_order(self._ctx, int(n_gas), L._ptr(order), 0))
+        return order
+
+    # -- tree ----------------------------------------------------------------------------
+    def force_treebuild(self):
+        nn = C.c_longlong(0)
+        self._chk(self._lib.gl_force_treebuild(self._ctx, C.byref(nn)))
+        return nn.value
+
+    ngb_treebuild = force_treebuild  # ngb.c:315: the neighbour tree IS the gravity tree
+
+    def set_TreeReconstructFlag(self, flag=1):
+        self._lib.gl_set_tree_reconstruct_flag(self._ctx, int(flag))
+
+    def nodes(self):
+        st = self.stats()
+        tab = np.zeros((st["numnodes"], 12))
+        if st["numnodes"]:
+            self._chk(self._lib.gl_get_nodes(self._ctx, tab.ctypes.data_as(L.c_double_p), st["numnodes"]))
+        return tab
+
+    # -- the force entry points ------------------------------------------------------------
+    def gravity_tree(self):
+        self._chk(self._lib.gl_gravity_tree(self._ctx))
+        acc = np.zeros((self.N, 3))
+        old = np.zeros(self.N)
+        cost = np.zeros(self.N, dtype=np.float32)
+        self._chk(self._lib.gl_get_gravity(self._ctx, L._ptr(acc), L._ptr(old), L._ptr(cost), 0))
+        return dict(GravAccel=acc, OldAcc=old, GravCost=cost)
+
+    def density(self):
+        self._chk(self._lib.gl_density(self._ctx))
+        n = self.N
+        names = ["Hsml", "NumNgb", "Density", "DhsmlDensityFactor", "DivVel", "CurlVel", "Pressure", "SinkDensity",
+                 "SinkEntropy"]
+        out = {k: np.zeros(n) for k in names}
+        out["SinkGasVel"] = np.zeros((n, 3))
+        self._chk(self._lib.gl_get_density(self._ctx, *[L._ptr(out[k]) for k in names], L._ptr(out["SinkGasVel"]), 0))
+        dp = np.zeros(n, dtype=np.int32)
+        self._chk(self._lib.gl_get_pair_counts(self._ctx, L._ptr(dp), None, 0))
+        out["DensPairs"] = dp
+        return out
+
+    def force_update_hmax(self):
+        self._chk(self._lib.gl_force_update_hmax(self._ctx))
+
+    def hydro_force(self):
+        self._chk(self._lib.gl_hydro_force(self._ctx))
+        n = self.N
+        out = dict(HydroAccel=np.zeros((n, 3)), DtEntropy=np.zeros(n), MaxSignalVel=np.zeros(n))
+        self._chk(self._lib.gl_get_hydro(self._ctx, L._ptr(out["HydroAccel"]), L._ptr(out["DtEntropy"]),
+                                         L._ptr(out["MaxSignalVel"]), 0))
+        hp = np.zeros(n, dtype=np.int32)
+        self._chk(self._lib.gl_get_pair_counts(self._ctx, None, L._ptr(hp), 0))
+        out["HydroPairs"] = hp
+        return out
+
+    def compute_accelerations(self, mode=0):
+        """accel.c:27 (force part): gravity (twice at Ti_Current==0), density, hmax, hydro."""
+        self._chk(self._lib.gl_compute_accelerations(self._ctx, int(mode)))
+
+    # device-resident variants used by bench.py's `value` leg (no result download)
+    def gravity_tree_nocopy(self):
+        self._chk(self._lib.gl_gravity_tree(self._ctx))
+
+    def density_nocopy(self):
+        self._chk(self._lib.gl_density(self._ctx))
+
+    def hydro_force_nocopy(self):
+        self._chk(self._lib.gl_hydro_force(self._ctx))
+
+    def stats(self):
+        s = L.GLStats()
+        self._chk(self._lib.gl_get_stats(self._ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in L.GLStats._fields_}
+
+    def reset_launch_count(self):
+        self._lib.gl_reset_launch_count(self._ctx)

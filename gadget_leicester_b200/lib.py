@@ -1,0 +1,146 @@
+"""ctypes binding of libgl_b200.so (the C ABI declared in include/gl_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or no GPU is visible the
+constructor raises.  Nothing under oracle/ is imported here.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgl_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_float_p = C.POINTER(C.c_float)
+c_u64_p = C.POINTER(C.c_ulonglong)
+
+
+class GLParams(C.Structure):
+    _fields_ = [
+        ("ErrTolTheta", C.c_double),
+        ("ErrTolForceAcc", C.c_double),
+        ("TypeOfOpeningCriterion", C.c_int),
+        ("DesNumNgb", C.c_int),
+        ("MaxNumNgbDeviation", C.c_double),
+        ("BlackHoleNgbFactor", C.c_double),
+        ("ArtBulkViscConst", C.c_double),
+        ("G", C.c_double),
+        ("ForceSoftening", C.c_double * 6),
+        ("MinGasHsml", C.c_double),
+        ("Timebase_interval", C.c_double),
+        ("Ti_Current", C.c_int),
+        ("ComovingIntegrationOn", C.c_int),
+        ("OmegaLambdaHubble2", C.c_double),
+    ]
+
+
+class GLStats(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "ms_keys_sort", "ms_treebuild", "ms_moments", "ms_gravity_walk", "ms_density", "ms_hmax", "ms_hydro",
+        "ms_h2d", "ms_d2h")] + [(k, C.c_longlong) for k in (
+            "interactions", "density_targets", "density_passes_max", "hydro_targets", "numnodes", "numentries",
+            "kernel_launches")]
+
+
+class GLGadgetLayout(C.Structure):
+    _fields_ = [("p_stride", C.c_longlong), ("sph_stride", C.c_longlong)] + [(k, C.c_int) for k in (
+        "p_Pos", "p_Vel", "p_Mass", "p_GravAccel", "p_OldAcc", "p_Hsml", "p_NumNgb", "p_GravCost", "p_Ti_begstep",
+        "p_Type", "p_TimeBin", "p_SinkDensity", "p_SinkEntropy", "p_SinkGasVel", "p_DustDensity", "p_DustEntropy",
+        "p_DustGasVel", "p_SwallowID", "s_Entropy", "s_Pressure", "s_VelPred", "s_MaxSignalVel", "s_Density",
+        "s_DtEntropy", "s_HydroAccel", "s_DhsmlDensityFactor", "s_DivVel", "s_CurlVel")]
+
+
+# every symbol include/gl_b200.h declares (tests check that the .so exports all of them)
+EXPORTS = [
+    "gl_create", "gl_destroy", "gl_last_error", "gl_set_params", "gl_stream", "gl_load_particles", "gl_set_oldacc",
+    "gl_set_hsml", "gl_domain_find_extent", "gl_domain_set_extent", "gl_peano_keys", "gl_peano_hilbert_order",
+    "gl_peano_hilbert_key", "gl_morton_key", "gl_force_treebuild", "gl_get_nodes", "gl_set_targets",
+    "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations",
+    "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
+    "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libgl_b200.so is missing (%s): build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C gadget_leicester_b200/csrc` - there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.gl_create.argtypes = [C.POINTER(vp), C.c_int, C.c_longlong]
+    lib.gl_destroy.argtypes = [vp]
+    lib.gl_destroy.restype = None
+    lib.gl_last_error.argtypes = [vp]
+    lib.gl_last_error.restype = C.c_char_p
+    lib.gl_stream.argtypes = [vp]
+    lib.gl_stream.restype = vp
+    lib.gl_set_params.argtypes = [vp, C.POINTER(GLParams)]
+    lib.gl_load_particles.argtypes = [vp, C.c_longlong] + [vp] * 10 + [C.c_int]
+    lib.gl_set_oldacc.argtypes = [vp, vp, C.c_int]
+    lib.gl_set_hsml.argtypes = [vp, vp, C.c_int]
+    lib.gl_domain_find_extent.argtypes = [vp, c_double_p]
+    lib.gl_domain_set_extent.argtypes = [vp, c_double_p, c_double_p]
+    lib.gl_peano_keys.argtypes = [vp, vp, vp, C.c_int]
+    lib.gl_peano_hilbert_order.argtypes = [vp, C.c_longlong, vp, C.c_int]
+    lib.gl_peano_hilbert_key.argtypes = [C.c_int] * 4
+    lib.gl_peano_hilbert_key.restype = C.c_ulonglong
+    lib.gl_morton_key.argtypes = [C.c_int] * 4
+    lib.gl_morton_key.restype = C.c_ulonglong
+    lib.gl_force_treebuild.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.gl_get_nodes.argtypes = [vp, c_double_p, C.c_longlong]
+    lib.gl_set_targets.argtypes = [vp, vp, C.c_longlong, C.c_int]
+    for f in ("gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force"):
+        getattr(lib, f).argtypes = [vp]
+    lib.gl_compute_accelerations.argtypes = [vp, C.c_int]
+    lib.gl_set_tree_reconstruct_flag.argtypes = [vp, C.c_int]
+    lib.gl_set_tree_reconstruct_flag.restype = None
+    lib.gl_get_gravity.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.gl_get_density.argtypes = [vp] + [vp] * 10 + [C.c_int]
+    lib.gl_get_hydro.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.gl_get_pair_counts.argtypes = [vp, vp, vp, C.c_int]
+    lib.gl_get_stats.argtypes = [vp, C.POINTER(GLStats)]
+    lib.gl_reset_launch_count.argtypes = [vp]
+    lib.gl_reset_launch_count.restype = None
+    lib.gl_gadget_bind.argtypes = [vp, C.POINTER(GLGadgetLayout)]
+    lib.gl_gadget_pull.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong]
+    lib.gl_gadget_push.argtypes = [vp, vp, vp, C.c_int]
+    _lib = lib
+    return lib
+
+
+def make_params(p):
+    """dict (ics.default_params) -> GLParams, applying set_softenings (gravtree.c:835-885)."""
+    g = GLParams()
+    g.ErrTolTheta = p["ErrTolTheta"]
+    g.ErrTolForceAcc = p["ErrTolForceAcc"]
+    g.TypeOfOpeningCriterion = int(p["TypeOfOpeningCriterion"])
+    g.DesNumNgb = int(p["DesNumNgb"])
+    g.MaxNumNgbDeviation = p["MaxNumNgbDeviation"]
+    g.BlackHoleNgbFactor = p["BlackHoleNgbFactor"]
+    g.ArtBulkViscConst = p["ArtBulkViscConst"]
+    g.G = p["G"]
+    for i in range(6):
+        g.ForceSoftening[i] = 2.8 * p["Softening"][i]        # gravtree.c:881-882
+    g.MinGasHsml = p["MinGasHsmlFractional"] * g.ForceSoftening[0]  # gravtree.c:884
+    g.Timebase_interval = p["Timebase_interval"]
+    g.Ti_Current = int(p["Ti_Current"])
+    g.ComovingIntegrationOn = 0
+    g.OmegaLambdaHubble2 = 0.0
+    return g
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GLError(RuntimeError):
+    pass

@@ -1,0 +1,152 @@
+/* gl_b200.h - C ABI of libgl_b200.so: the B200-native (sm_100a) force path of the
+ * Leicester GADGET-3 fork.  Plain pointers and sizes only; no torch types.
+ *
+ * Each entry point names the reference interface it replaces (file:line into the
+ * reference tree).  The reference has no plugin API: its boundary is a set of global C
+ * symbols operating on the global arrays P[] / SphP[] (proto.h:281,295,331,332;
+ * forcetree.h:48,67,86).  The functions below are what those symbols bind to; the glue
+ * a maintainer adds on the reference side (which owns allvars.h and therefore the struct
+ * layout) is shown in INTEGRATION.md and shipped as integration/gl_gadget_glue.c.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error
+ * (gl_last_error() gives the text).  The reference's own convention for unrecoverable
+ * errors is endrun(code) (endrun.c:23); the glue maps non-zero returns onto it.
+ * One gl_ctx <-> one GPU <-> one reference MPI rank.  Calls are synchronous: results
+ * are complete in the caller's memory on return.
+ */
+#ifndef GL_B200_H
+#define GL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gl_ctx gl_ctx;
+typedef unsigned long long gl_peanokey;	/* peanokey, allvars.h:144 (63 bits used) */
+
+/* Run-time parameters the path reads out of the reference's global `All`
+ * (SURVEY.md 8(b) "Inputs read").  Field names follow struct global_data_all_processes. */
+typedef struct gl_params
+{
+  double ErrTolTheta;		/* All.ErrTolTheta, forcetree.c:2074-2076 (0 selects the relative criterion) */
+  double ErrTolForceAcc;	/* All.ErrTolForceAcc, forcetree.c:1850 */
+  int TypeOfOpeningCriterion;	/* gravtree.c:396-397 */
+  int DesNumNgb;		/* density.c:158 */
+  double MaxNumNgbDeviation;	/* density.c:559 */
+  double BlackHoleNgbFactor;	/* density.c:551 */
+  double ArtBulkViscConst;	/* hydra.c:1538 */
+  double G;			/* gravtree.c:403 */
+  double ForceSoftening[6];	/* All.ForceSoftening[] = 2.8 * SofteningTable[], gravtree.c:881-882 */
+  double MinGasHsml;		/* gravtree.c:884 */
+  double Timebase_interval;	/* density.c:491, hydra.c:1583 */
+  int Ti_Current;		/* All.Ti_Current */
+  int ComovingIntegrationOn;	/* must be 0: the comoving factors of hydra.c:196-206 are not implemented */
+  double OmegaLambdaHubble2;	/* All.OmegaLambda*All.Hubble^2, gravtree.c:405-411 (0 for the shipped run) */
+} gl_params;
+
+/* ---- life cycle ---------------------------------------------------------------- */
+/* max_part plays the role of All.MaxPart (allocate.c:56): device buffers are sized once. */
+int gl_create(gl_ctx ** ctx, int device, long long max_part);
+void gl_destroy(gl_ctx * ctx);
+const char *gl_last_error(const gl_ctx * ctx);
+int gl_set_params(gl_ctx * ctx, const gl_params * p);
+/* stream the library launches on (a cudaStream_t); lets a caller time it with its own events */
+void *gl_stream(gl_ctx * ctx);
+
+/* ---- particle state, SoA form ---------------------------------------------------- */
+/* Loads the fields of P[]/SphP[] the path reads (allvars.h:1131-1377, :1384-1639).  All arrays
+ * have n elements and are indexed like P[]; the SphP fields are only read where type==0.
+ * `where`: 0 = host pointers, 1 = device pointers (same device as the ctx).
+ *   pos[3n] P.Pos, vel[3n] SphP.VelPred for gas else P.Vel, mass P.Mass, type P.Type,
+ *   hsml P.Hsml, oldacc P.OldAcc, timebin P.TimeBin, ti_begstep P.Ti_begstep,
+ *   entropy SphP.Entropy, dtentropy SphP.e.DtEntropy, divvel SphP.v.DivVel (may be NULL = 0). */
+int gl_load_particles(gl_ctx * ctx, long long n, const double *pos, const double *vel, const double *mass,
+		      const int *type, const double *hsml, const double *oldacc, const int *timebin,
+		      const int *ti_begstep, const double *entropy, const double *dtentropy, int where);
+/* update only P.OldAcc / P.Hsml between calls (used when chaining calls like accel.c:61-67 does) */
+int gl_set_oldacc(gl_ctx * ctx, const double *oldacc, int where);
+int gl_set_hsml(gl_ctx * ctx, const double *hsml, int where);
+
+/* ---- domain / keys: domain.c:1972 domain_findExtent, peano.c:300,320,335 ------------------ */
+/* computes DomainCorner/Center/Len/Fac from the loaded positions; out[8] = len, fac, corner[3], center[3] */
+int gl_domain_find_extent(gl_ctx * ctx, double *out8);
+/* multi-GPU: impose the global extent (the ncclAllReduce min/max result, domain.c:1996-1997) */
+int gl_domain_set_extent(gl_ctx * ctx, const double xmin[3], const double xmax[3]);
+/* peano_and_morton_key for every loaded particle on the BITS_PER_DIMENSION=21 grid */
+int gl_peano_keys(gl_ctx * ctx, gl_peanokey * ph_keys, gl_peanokey * morton_keys, int where);
+/* peano_hilbert_order (peano.c:25): order[] such that new P[i] = old P[order[i]]; the gas block
+ * [0,n_gas) and the rest are ordered separately as the reference does (peano.c:37-88). */
+int gl_peano_hilbert_order(gl_ctx * ctx, long long n_gas, int *order, int where);
+/* scalar (host) versions of peano.c:300 / :320, exported for the key parity tests */
+gl_peanokey gl_peano_hilbert_key(int x, int y, int z, int bits);
+gl_peanokey gl_morton_key(int x, int y, int z, int bits);
+
+/* ---- tree: forcetree.c:67 force_treebuild (+ :468 force_update_node_recursive) ------------- */
+/* returns 0 and stores the node count (Numnodestree analogue) in *numnodes */
+int gl_force_treebuild(gl_ctx * ctx, long long *numnodes);
+/* node table for parity tests: per node 12 doubles
+ * {len, center[3], mass, s[3], maxsoft, hmax, vmax, level}; host buffer of 12*numnodes doubles */
+int gl_get_nodes(gl_ctx * ctx, double *table, long long cap_nodes);
+
+/* ---- targets ---------------------------------------------------------------------------------- */
+/* Restrict the next force calls to a subset of P[] indices (the active list
+ * FirstActiveParticle/NextActiveParticle, or a GPU's Peano-Hilbert segment).  n<0 = all. */
+int gl_set_targets(gl_ctx * ctx, const int *index, long long n, int where);
+
+/* ---- the four force entry points -------------------------------------------------------------- */
+int gl_gravity_tree(gl_ctx * ctx);	/* gravtree.c:27  (includes the tree build when flagged) */
+int gl_density(gl_ctx * ctx);		/* density.c:89   (with the Hsml iteration) */
+int gl_force_update_hmax(gl_ctx * ctx);	/* forcetree.c:1661 */
+int gl_hydro_force(gl_ctx * ctx);	/* hydra.c:145 */
+int gl_compute_accelerations(gl_ctx * ctx, int mode);	/* accel.c:27, force part (:61-106) */
+void gl_set_tree_reconstruct_flag(gl_ctx * ctx, int flag);	/* TreeReconstructFlag, domain.c:135 */
+
+/* ---- results (arrays indexed like P[], n elements; NULL pointers are skipped) ------------------- */
+/* gravity: P.g.GravAccel (already x G), P.OldAcc, P.GravCost (gravtree.c:392-403, forcetree.c:2282) */
+int gl_get_gravity(gl_ctx * ctx, double *gravaccel3, double *oldacc, float *gravcost, int where);
+/* density: P.Hsml, P.n.NumNgb, SphP.d.Density, .h.DhsmlDensityFactor, .v.DivVel, .r.CurlVel, .Pressure;
+ * sink/dust targets: b1/d1 density, b2/d2 entropy, b3/d3 gas velocity (density.c:944-988, :520-546) */
+int gl_get_density(gl_ctx * ctx, double *hsml, double *numngb, double *density, double *dhsml, double *divvel,
+		   double *curlvel, double *pressure, double *sink_density, double *sink_entropy,
+		   double *sink_gasvel3, int where);
+/* hydro: SphP.a.HydroAccel, .e.DtEntropy (converted, hydra.c:583), .MaxSignalVel */
+int gl_get_hydro(gl_ctx * ctx, double *hydroaccel3, double *dtentropy, double *maxsignalvel, int where);
+/* integer pair counts (not stored by the reference, density.c:858 is a dead local): number of j with
+ * Mass_j != 0 and r2 < h_i^2 (density) / (r2 < h_i^2 or r2 < h_j^2) and r > 0 (hydro) */
+int gl_get_pair_counts(gl_ctx * ctx, int *dens_pairs, int *hydro_pairs, int where);
+
+/* ---- statistics --------------------------------------------------------------------------------- */
+typedef struct gl_stats
+{
+  double ms_keys_sort, ms_treebuild, ms_moments, ms_gravity_walk, ms_density, ms_hmax, ms_hydro, ms_h2d, ms_d2h;
+  long long interactions;	/* sum of P.GravCost over targets of the last gl_gravity_tree */
+  long long density_targets, density_passes_max, hydro_targets;
+  long long numnodes, numentries;
+  long long kernel_launches;	/* kernels launched by this library since gl_create / last reset */
+} gl_stats;
+int gl_get_stats(gl_ctx * ctx, gl_stats * out);
+void gl_reset_launch_count(gl_ctx * ctx);
+
+/* ---- drop-in layer for the reference's AoS arrays ------------------------------------------------- */
+/* Byte offsets inside struct particle_data / struct sph_particle_data; the glue fills them with
+ * offsetof() so the library never needs allvars.h (SURVEY.md 8(b) "ABI caveat"). */
+typedef struct gl_gadget_layout
+{
+  long long p_stride, sph_stride;
+  int p_Pos, p_Vel, p_Mass, p_GravAccel, p_OldAcc, p_Hsml, p_NumNgb, p_GravCost, p_Ti_begstep, p_Type, p_TimeBin;
+  int p_SinkDensity, p_SinkEntropy, p_SinkGasVel;	/* b1/b2/b3 (Type 5) */
+  int p_DustDensity, p_DustEntropy, p_DustGasVel;	/* d1/d2/d3 (Type 2) */
+  int p_SwallowID;
+  int s_Entropy, s_Pressure, s_VelPred, s_MaxSignalVel, s_Density, s_DtEntropy, s_HydroAccel,
+    s_DhsmlDensityFactor, s_DivVel, s_CurlVel;
+} gl_gadget_layout;
+int gl_gadget_bind(gl_ctx * ctx, const gl_gadget_layout * lay);
+/* pack P[0..NumPart) / SphP[0..N_gas) into the device SoA (host threads + pinned staging) */
+int gl_gadget_pull(gl_ctx * ctx, const void *P, const void *SphP, long long NumPart, long long N_gas);
+/* scatter results back in place; what = bit mask: 1 gravity, 2 density, 4 hydro */
+int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
