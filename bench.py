@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py - one JSON line per run (contract in the task prompt; tier section (4)).
+
+A "step" is one full force evaluation (accel.c:61-106): tree rebuild (keys, sort, build, moments) +
+gravity walk with the relative criterion + density (converged-Hsml pass) + hmax refresh + hydro, on the
+configuration BASELINE.json's target is quoted on: config 0, the 1.6M-gas protoplanetary disc + 2 sinks.
+With --gpus N (torchrun) the disc is scaled to N x 1.6M gas particles (BASELINE config 2's "scaled disc",
+weak scaling): each rank owns one Peano-Hilbert segment of targets and the sources are replicated by NCCL
+all-gathers (gadget_leicester_b200/multigpu.py).
+
+  value  = gravity particle-node interactions per second of whole-step time, inputs resident in HBM
+  e2e    = the same metric through the drop-in boundary with HOST P[]/SphP[] buffers
+           (gl_gadget_pull -> gl_compute_accelerations -> gl_gadget_push), wall clock
+  --impl reference : the reference's own CPU code (oracle/_ref/ref_harness when it was compiled, else the
+           C restatement oracle/gl_oracle) on the host cores, one single-rank instance per core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gravity particle-node interactions/s per full force step (gravity+density+hydro)"
+UNIT = "interactions/s"
+N_GAS_PER_GPU = 1600000
+CPU_SAMPLE_NGAS = 200000
+FLOP_PER_INTERACTION = 25.0
+DENS_BYTES_PER_UPDATE = 84.0    # SURVEY.md 8(d), compulsory HBM bytes per update per pass
+HYDRO_BYTES_PER_UPDATE = 96.0
+
+
+def peaks():
+    p = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+    except Exception:
+        pass
+    return dict(hbm_gbs=p.get("hbm_gbs", 6650.0), sm_max_mhz=p.get("sm_max_mhz", 1965.0),
+                source="MEASURED_PEAKS.json" if p else "fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        import numpy as np
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ----------------------------------------------------------------------------------------- reference arm ----
+def oracle_binary():
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if os.path.exists(ref):
+        return ref, "reference"
+    import __graft_entry__ as ge
+    ge.build_oracle()
+    return os.path.join(ROOT, "oracle", "gl_oracle"), "port"
+
+
+def run_cpu_instances(ninst, nsteps, ngas, seed0=42):
+    """ninst concurrent single-rank instances; returns (interactions per step per instance, per-step seconds)."""
+    import numpy as np
+    import tempfile
+    from gadget_leicester_b200 import ics
+    from oracle import glio
+    binary, kind = oracle_binary()
+    td = tempfile.mkdtemp(prefix="glbench_")
+    par = ics.default_params()
+    procs = []
+    ops = "T S D R G G D U H" + " A" * nsteps      # settle (cold start), then nsteps timed force evaluations
+    for k in range(ninst):
+        ps = ics.disc(ngas, seed=seed0 + k)
+        fin, fout = os.path.join(td, "in%d.glin" % k), os.path.join(td, "out%d.glou" % k)
+        glio.write_glin(fin, ps, par)
+        procs.append((subprocess.Popen([binary, fin, fout, ops], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), fout))
+    inter, secs = [], []
+    for p, fout in procs:
+        if p.wait() != 0:
+            raise RuntimeError("CPU reference instance failed")
+        o = glio.read_glou(fout)
+        for s in range(nsteps):
+            pre = "%d_" % (9 + s)
+            t = sum(float(o[pre + op + "_time"][0]) for op in "GDUH")
+            inter.append(float(o[pre + "G_interactions"][0]))
+            secs.append(t)
+    inter = np.array(inter).reshape(ninst, nsteps)
+    secs = np.array(secs).reshape(ninst, nsteps)
+    return inter, secs, kind
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    nwarm, nsteps = min(args.warmup, 1), max(1, min(args.steps, 3))
+    inter, secs, kind = run_cpu_instances(cores, nwarm + nsteps, CPU_SAMPLE_NGAS)
+    inter, secs = inter[:, nwarm:], secs[:, nwarm:]
+    step_s = float(secs.max(axis=0).mean())          # slowest instance per step
+    value = float(inter.sum(axis=0).mean() / step_s)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=nsteps, warmup=nwarm, ms_per_step=step_s * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload="config 0 disc generator at %d gas + 2 sinks per instance (bounded sample of the 1.6M disc)"
+                            % CPU_SAMPLE_NGAS, instances=cores),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind,
+                                  sample="%d concurrent single-rank instances (no MPI in the image) of the %d-gas disc; "
+                                         "step = gravity_tree+density+force_update_hmax+hydro_force after a settled start"
+                                         % (cores, CPU_SAMPLE_NGAS)),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                sph_updates_per_s=float(cores * CPU_SAMPLE_NGAS / step_s), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm ----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ngas", type=int, default=0, help="override gas particles per GPU (default 1.6M)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    from gadget_leicester_b200 import ics
+    from gadget_leicester_b200.multigpu import DistributedForcePath
+    from gadget_leicester_b200.gadget import ForcePath
+    from gadget_leicester_b200 import aos
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warm = max(3, args.warmup)
+    ngas = (args.ngas or N_GAS_PER_GPU) * world
+    par = ics.default_params()
+    ps = ics.disc(ngas, seed=42)
+    ps["hsml"] = ics.guess_hsml(ps, par["DesNumNgb"])
+    ps["hsml"][ps["type"] == 5] = par["Softening"][5]
+    n = ps["pos"].shape[0]
+
+    dfp = DistributedForcePath(par, rank=rank, world=world, device=local)
+    dfp.decompose(ps)
+    # settle: Barnes-Hut pass (OldAcc=0) then cold-start density; afterwards every step is a steady-state step
+    dfp.compute_accelerations()
+    cold_passes = dfp.fp.stats()["density_passes_max"]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def one_step():
+        dfp.fp.set_TreeReconstructFlag(1)
+        dfp.compute_accelerations()
+
+    for _ in range(warm):
+        one_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    dfp.fp.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot_ms, acc = 0.0, dict(ms_keys_sort=0, ms_treebuild=0, ms_moments=0, ms_gravity_walk=0, ms_density=0, ms_hmax=0, ms_hydro=0)
+    inter = 0
+    passes = []
+    for _ in range(args.steps):
+        flush.fill_(1)                         # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        e0.record(torch.cuda.current_stream())
+        one_step()
+        torch.cuda.synchronize()
+        e1.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        tot_ms += e0.elapsed_time(e1)
+        st = dfp.fp.stats()
+        for k in acc:
+            acc[k] += st[k]
+        inter += st["interactions"]
+        passes.append(st["density_passes_max"])
+    launches = dfp.fp.stats()["kernel_launches"]
+    clocks = sampler.stop()
+    t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+    it = torch.tensor([float(inter)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t.item()) / args.steps
+    inter_per_step = float(it.item()) / args.steps
+    value = inter_per_step / (ms_per_step * 1e-3)
+    phase = {k: v / args.steps for k, v in acc.items()}
+
+    # ---- roofline of the dominant kernel (per-launch durations from the library's CUDA events) ----
+    pk = peaks()
+    own_targets = dfp.hi - dfp.lo
+    own_gas = int((ps["type"][dfp.order[dfp.lo:dfp.hi]] == 0).sum())
+    cand = dict(gravity_walk=phase["ms_gravity_walk"], density=phase["ms_density"], hydro=phase["ms_hydro"])
+    dom = max(cand, key=cand.get)
+    if dom == "gravity_walk":
+        nsm = torch.cuda.get_device_properties(local).multi_processor_count
+        peak = nsm * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        ach = FLOP_PER_INTERACTION * (inter / args.steps) / (cand[dom] * 1e-3) / 1e12
+        roof = dict(kernel="k_gravity_walk", bound="fp32", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                    note="25 flop/interaction (SURVEY 8(d)); peak = SMs*128*2*sm_max_mhz from " + pk["source"])
+    else:
+        per = DENS_BYTES_PER_UPDATE if dom == "density" else HYDRO_BYTES_PER_UPDATE
+        units = own_gas * (max(1, int(np.mean(passes))) if dom == "density" else 1)
+        ach = per * units / (cand[dom] * 1e-3) / 1e9
+        roof = dict(kernel="k_" + dom, bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                    traffic=None, note="%g B/update (SURVEY 8(d)); peak from %s" % (per, pk["source"]))
+
+    # ---- e2e: the same step through the drop-in boundary with host P[]/SphP[] (rank-local set) ----
+    e2e = None
+    if not args.no_e2e and world == 1:
+        res_h = dfp.res["hsml"].cpu().numpy()
+        res_o = dfp.res["oldacc"].cpu().numpy()
+        ps2 = {k: (v[dfp.order] if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+        ps2["hsml"], ps2["oldacc"] = res_h, res_o
+        dfp.close()
+        del dfp
+        torch.cuda.empty_cache()
+        fp = ForcePath(dict(par, ErrTolTheta=0.0))       # steady state: relative criterion (gravtree.c:396-397)
+        arr = aos.GadgetArrays(ps2, pinned=True)
+        drop = aos.GadgetDropIn(fp, arr)
+        for _ in range(2):
+            fp.set_TreeReconstructFlag(1)
+            drop.compute_accelerations()
+        torch.cuda.synchronize()
+        ksteps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        ie = 0
+        for _ in range(ksteps):
+            fp.set_TreeReconstructFlag(1)
+            drop.compute_accelerations()
+            ie += fp.stats()["interactions"]
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ksteps
+        h2d, d2h = drop.bytes_per_step()
+        e2e = dict(value=(ie / ksteps) / dt, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=dt * 1e3,
+                   steps=ksteps, api="gl_gadget_pull + gl_compute_accelerations + gl_gadget_push on pinned host P[]/SphP[]")
+        fp.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ci, cs, kind = run_cpu_instances(1, 2, CPU_SAMPLE_NGAS)
+            cpu_base = dict(value=float(ci[0, 1] / cs[0, 1]), unit=UNIT, cores=1, kind=kind,
+                            sample="1 single-rank instance, %d-gas disc + 2 sinks (same generator, bounded sample), "
+                                   "one settled force step: %.2f s" % (CPU_SAMPLE_NGAS, cs[0, 1]),
+                            sph_updates_per_s=float(CPU_SAMPLE_NGAS / cs[0, 1]))
+        except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
+            cpu_base = dict(value=None, unit=UNIT, cores=1, kind="unavailable", sample=str(ex)[:200])
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms_per_step,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 predicates + f32 force magnitude (gravity), f64 (SPH)",
+                data="synthetic",
+                config=dict(workload="BASELINE config 0: Pd_N16e5 protoplanetary disc, %d gas + 2 sinks%s" %
+                            (ngas, "" if world == 1 else " (scaled disc, %d per GPU)" % (ngas // world)),
+                            particles=n, parallelism="ph-segments x%d" % world, l2="256 MiB flush between timed steps",
+                            step="tree rebuild + gravity (relative criterion) + density + hmax + hydro"),
+                interactions_per_step=inter_per_step, sph_updates_per_s=(ngas / (ms_per_step * 1e-3)),
+                force_eval_ms=ms_per_step, phase_ms=phase, density_passes=dict(cold_start=cold_passes, steady=passes),
+                gpu_launches=int(launches), clocks=clocks, roofline=roof)
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,20 @@ extern "C" int gl_set_hsml(gl_ctx *c, const double *hsml, int where)
   return 0;
 }
 
+extern "C" int gl_set_sph_state(gl_ctx *c, const double *density, const double *pressure, const double *dhsml,
+				const double *divvel, const double *curlvel, int where)
+{
+  cudaSetDevice(c->device);
+  if(c->n <= 0) return c->fail("gl_set_sph_state: no particles");
+  const size_t n = (size_t) c->n;
+  if(density && put(c, c->o_density, density, n, where, 0.0)) return 1;
+  if(pressure && put(c, c->o_pressure, pressure, n, where, 0.0)) return 1;
+  if(dhsml && put(c, c->o_dhsml, dhsml, n, where, 0.0)) return 1;
+  if(divvel && put(c, c->o_divvel, divvel, n, where, 0.0)) return 1;
+  if(curlvel && put(c, c->o_curlvel, curlvel, n, where, 0.0)) return 1;
+  return 0;
+}
+
 extern "C" int gl_domain_find_extent(gl_ctx *c, double *out8)
 {
   cudaSetDevice(c->device);

@@ -393,13 +393,17 @@ int glt_build(gl_ctx *c)
 // forcetree.c:1661-1705: from every active gas particle climb the father chain while the particle's
 // Hsml raises the node's hmax.  Positive doubles order like their bit patterns, so an unsigned
 // 64-bit atomicMax implements "if(h > hmax) hmax = h" without a lock.
-__global__ void k_update_hmax(const int *__restrict__ tgt, long long nt, const double4 *__restrict__ s_vh,
+__global__ void k_update_hmax(long long n, const int *__restrict__ s_type, const double4 *__restrict__ s_vh,
 			      const int *__restrict__ p_father, const int *__restrict__ n_parent,
 			      const int *__restrict__ n_first, double *__restrict__ e_hmax)
 {
-  long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(t >= nt) return;
-  int p = tgt[t];
+  // every gas particle of the tree, not only this call's targets: particles whose Hsml did not change
+  // stop at their father (old >= h), and after a multi-GPU allgather of Hsml the particles owned by
+  // other GPUs must raise hmax here as well (the reference exchanges the raised top-leaf values,
+  // forcetree.c:1722-1747)
+  long long p = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(p >= n) return;
+  if(s_type[p] != 0) return;
   double h = s_vh[p].w;
   unsigned long long hb = (unsigned long long) __double_as_longlong(h);
   int no = p_father[p];
@@ -415,15 +419,10 @@ __global__ void k_update_hmax(const int *__restrict__ tgt, long long nt, const d
 int glt_update_hmax(gl_ctx *c)
 {
   if(!c->tree_valid) return c->fail("force_update_hmax: no tree");
-  if(gl_prepare_targets(c)) return 1;
   cudaEventRecord(c->ev[0], c->stream);
-  if(c->n_tgt_gas > 0)
-    {
-      k_update_hmax<<<gl_grid(c->n_tgt_gas, 256), 256, 0, c->stream>>>(c->tgt_gas.p, c->n_tgt_gas, c->s_vh.p,
-								       c->p_father.p, c->n_parent.p, c->n_first.p,
-								       c->e_hmax.p);
-      GL_LAUNCH_COUNT(c);
-    }
+  k_update_hmax<<<gl_grid(c->n, 256), 256, 0, c->stream>>>(c->n, c->s_type.p, c->s_vh.p, c->p_father.p, c->n_parent.p,
+							    c->n_first.p, c->e_hmax.p);
+  GL_LAUNCH_COUNT(c);
   cudaEventRecord(c->ev[1], c->stream);
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   float ms;

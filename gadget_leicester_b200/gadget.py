@@ -74,6 +74,18 @@ class ForcePath:
         self.N = int(n)
         self._chk(self._lib.gl_load_particles(self._ctx, int(n), *[C.c_void_p(p) if p else None for p in ptrs], 1))
 
+    def set_OldAcc(self, oldacc):
+        """Overwrite P[].OldAcc (input of the relative opening criterion, forcetree.c:1850)."""
+        a = np.ascontiguousarray(oldacc, dtype=np.float64)
+        assert a.size == self.N
+        self._chk(self._lib.gl_set_oldacc(self._ctx, L._ptr(a), 0))
+
+    def set_Hsml(self, hsml):
+        """Overwrite P[].Hsml."""
+        a = np.ascontiguousarray(hsml, dtype=np.float64)
+        assert a.size == self.N
+        self._chk(self._lib.gl_set_hsml(self._ctx, L._ptr(a), 0))
+
     def set_targets(self, index=None):
         """Active list (FirstActiveParticle/NextActiveParticle) or a GPU's Peano-Hilbert segment."""
         if index is None:

@@ -29,7 +29,7 @@ def default_params(**over):
         Timebase_interval=100.0 / (1 << 29),  # (TimeMax-TimeBegin)/TIMEBASE, begrun.c
         Ti_Current=0,
         BlackHoleNgbFactor=4.0,       # .txt
-        PartAllocFactor=1.2,
+        PartAllocFactor=2.5,
     )
     p.update(over)
     return p

@@ -55,7 +55,7 @@ class GLGadgetLayout(C.Structure):
 # every symbol include/gl_b200.h declares (tests check that the .so exports all of them)
 EXPORTS = [
     "gl_create", "gl_destroy", "gl_last_error", "gl_set_params", "gl_stream", "gl_load_particles", "gl_set_oldacc",
-    "gl_set_hsml", "gl_domain_find_extent", "gl_domain_set_extent", "gl_peano_keys", "gl_peano_hilbert_order",
+    "gl_set_hsml", "gl_set_sph_state", "gl_domain_find_extent", "gl_domain_set_extent", "gl_peano_keys", "gl_peano_hilbert_order",
     "gl_peano_hilbert_key", "gl_morton_key", "gl_force_treebuild", "gl_get_nodes", "gl_set_targets",
     "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations",
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
@@ -87,6 +87,7 @@ def load_library():
     lib.gl_load_particles.argtypes = [vp, C.c_longlong] + [vp] * 10 + [C.c_int]
     lib.gl_set_oldacc.argtypes = [vp, vp, C.c_int]
     lib.gl_set_hsml.argtypes = [vp, vp, C.c_int]
+    lib.gl_set_sph_state.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int]
     lib.gl_domain_find_extent.argtypes = [vp, c_double_p]
     lib.gl_domain_set_extent.argtypes = [vp, c_double_p, c_double_p]
     lib.gl_peano_keys.argtypes = [vp, vp, vp, C.c_int]

@@ -1,0 +1,163 @@
+"""One-process-per-GPU sharding of the force path.
+
+The reference partitions TARGETS by contiguous Peano-Hilbert key segments (domain.c:1075-1113) and, per
+force phase, ships every target that touches a foreign top-tree leaf to the owner and the partial sums
+back (gravtree.c:246/:307, density.c:258/:305, hydra.c:412/:463).  Inside one NVSwitch box the pattern is
+inverted: SOURCES are replicated with one NCCL all-gather per phase, every GPU builds the identical
+global tree, and walks only its own Peano-Hilbert segment of targets.  No result reduction exists
+because every target is computed entirely by its owner, and because tree and per-target arithmetic are
+the same on every GPU the results are bit-identical for any GPU count.
+
+Exchange steps per force evaluation (the only collectives on the data path):
+  1. all-gather of the owned particle state (pos, vel, mass, type, Hsml, OldAcc, time bins, entropy);
+  2. after density: all-gather of Hsml and the SphP fields hydro reads from neighbours
+     (Density, Pressure, DhsmlDensityFactor, DivVel, CurlVel) - replaces hydra.c:412 and the hmax
+     exchange of forcetree.c:1722-1747.
+
+torch / torch.distributed are used for device memory, streams and the NCCL plumbing only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .gadget import ForcePath
+
+try:
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    dist = None
+
+
+def partition_range(n, world, rank):
+    """Contiguous equal-count segments of the Peano-Hilbert ordered particle list.  All segments have
+    m = ceil(n/world) particles except the last ones, which may be shorter (or empty)."""
+    m = -(-n // world)
+    lo = min(n, rank * m)
+    hi = min(n, lo + m)
+    return lo, hi, m
+
+
+def gather_padded(own, n, m, group=None):
+    """all-gather segments of m rows (the last one zero-padded) and return the first n rows.
+    own: [<=m, ...] tensor of this rank's segment.  Works with NCCL (cuda) and gloo (cpu)."""
+    world = dist.get_world_size(group) if (dist is not None and dist.is_initialized()) else 1
+    if world == 1:
+        return own[:n]
+    shape = (m,) + tuple(own.shape[1:])
+    send = own
+    if own.shape[0] != m:
+        send = torch.zeros(shape, dtype=own.dtype, device=own.device)
+        send[: own.shape[0]] = own
+    full = torch.empty((world * m,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+    dist.all_gather_into_tensor(full, send.contiguous(), group=group)
+    return full[:n]
+
+
+STATE_FIELDS = ("pos", "vel", "mass", "type", "hsml", "oldacc", "timebin", "ti_begstep", "entropy", "dtentropy")
+SPH_FIELDS = ("hsml", "density", "pressure", "dhsml", "divvel", "curlvel")
+
+
+class DistributedForcePath:
+    """Owns this rank's Peano-Hilbert segment on the GPU and evaluates forces for it."""
+
+    def __init__(self, params, rank=0, world=1, device=0, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device("cuda", device)
+        self.fp = ForcePath(params, device=device)
+        self.params = params
+        self.n = 0
+        self.own = {}
+        self.full = {}
+
+    # -- set-up: the analogue of domain_Decomposition + peano_hilbert_order (domain.c:100, peano.c:25) --------
+    def decompose(self, ps):
+        """ps: the FULL particle set as host numpy arrays (every rank passes the same set).  Orders it along the
+        Peano-Hilbert curve (gas block first, like the reference) and keeps this rank's segment on the GPU."""
+        n = ps["pos"].shape[0]
+        ngas = int((ps["type"] == 0).sum())
+        self.fp.load(ps)
+        order = self.fp.peano_hilbert_order(ngas)
+        self.n, self.ngas = n, ngas
+        lo, hi, m = partition_range(n, self.world, self.rank)
+        self.lo, self.hi, self.m = lo, hi, m
+        seg = order[lo:hi]
+        dev = self.device
+        tb = ps.get("ti_begstep", np.zeros(n, np.int32))
+        self.own = dict(
+            pos=torch.from_numpy(ps["pos"][seg]).to(dev), vel=torch.from_numpy(ps["vel"][seg]).to(dev),
+            mass=torch.from_numpy(ps["mass"][seg]).to(dev), type=torch.from_numpy(ps["type"][seg].astype(np.int32)).to(dev),
+            hsml=torch.from_numpy(ps["hsml"][seg]).to(dev), oldacc=torch.from_numpy(ps["oldacc"][seg]).to(dev),
+            timebin=torch.from_numpy(ps["timebin"][seg].astype(np.int32)).to(dev),
+            ti_begstep=torch.from_numpy(tb[seg].astype(np.int32)).to(dev),
+            entropy=torch.from_numpy(ps["entropy"][seg]).to(dev), dtentropy=torch.from_numpy(ps["dtentropy"][seg]).to(dev))
+        self.targets = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+        self.order = order
+        # result buffers (full length, only [lo,hi) is meaningful on this rank)
+        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
+        self.res = dict(acc=f64(n, 3), oldacc=f64(n), gravcost=torch.zeros(n, dtype=torch.float32, device=dev),
+                        hsml=f64(n), numngb=f64(n), density=f64(n), dhsml=f64(n), divvel=f64(n), curlvel=f64(n),
+                        pressure=f64(n), hacc=f64(n, 3), dtentr=f64(n), maxsig=f64(n))
+        return order
+
+    def _sync_lib(self):
+        # the library runs on its own stream and synchronises before returning; make torch's stream wait for
+        # nothing further (results are complete), and make sure torch work is done before the library reads
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # -- one force evaluation ------------------------------------------------------------------------------
+    def exchange_state(self):
+        """Exchange step 1: replicate the sources (NCCL all-gather over NVLink)."""
+        for k in STATE_FIELDS:
+            self.full[k] = gather_padded(self.own[k], self.n, self.m, self.group).contiguous()
+        self._sync_lib()
+        f = self.full
+        ptrs = [f[k].data_ptr() for k in STATE_FIELDS]
+        self.fp.load_device(self.n, ptrs)
+        lib, ctx = self.fp._lib, self.fp.ctx
+        self.fp._chk(lib.gl_set_targets(ctx, C.c_void_p(self.targets.data_ptr()), self.targets.numel(), 1))
+
+    def gravity(self):
+        self.fp.gravity_tree_nocopy()
+        r = self.res
+        lib, ctx = self.fp._lib, self.fp.ctx
+        self.fp._chk(lib.gl_get_gravity(ctx, C.c_void_p(r["acc"].data_ptr()), C.c_void_p(r["oldacc"].data_ptr()),
+                                        C.c_void_p(r["gravcost"].data_ptr()), 1))
+        self.own["oldacc"] = r["oldacc"][self.lo:self.hi].clone()
+
+    def density_and_exchange(self):
+        """density() for the owned targets, then exchange step 2."""
+        self.fp.density_nocopy()
+        r = self.res
+        lib, ctx = self.fp._lib, self.fp.ctx
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self.fp._chk(lib.gl_get_density(ctx, p(r["hsml"]), p(r["numngb"]), p(r["density"]), p(r["dhsml"]), p(r["divvel"]),
+                                        p(r["curlvel"]), p(r["pressure"]), None, None, None, 1))
+        self.own["hsml"] = r["hsml"][self.lo:self.hi].clone()
+        if self.world > 1:
+            g = {k: gather_padded(r[k][self.lo:self.hi], self.n, self.m, self.group).contiguous() for k in SPH_FIELDS}
+            self._sync_lib()
+            self.fp._chk(lib.gl_set_hsml(ctx, p(g["hsml"]), 1))
+            self.fp._chk(lib.gl_set_sph_state(ctx, p(g["density"]), p(g["pressure"]), p(g["dhsml"]), p(g["divvel"]),
+                                              p(g["curlvel"]), 1))
+            self._keep = g
+
+    def hydro(self):
+        self.fp.force_update_hmax()
+        self.fp.hydro_force_nocopy()
+        r = self.res
+        lib, ctx = self.fp._lib, self.fp.ctx
+        self.fp._chk(lib.gl_get_hydro(ctx, C.c_void_p(r["hacc"].data_ptr()), C.c_void_p(r["dtentr"].data_ptr()),
+                                      C.c_void_p(r["maxsig"].data_ptr()), 1))
+
+    def compute_accelerations(self, sph=True):
+        """accel.c:27 force part for this rank's segment, with the two exchange steps."""
+        self.exchange_state()
+        self.gravity()
+        if sph and self.ngas > 0:
+            self.density_and_exchange()
+            self.hydro()
+
+    def close(self):
+        self.fp.close()

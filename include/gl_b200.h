@@ -67,6 +67,12 @@ int gl_load_particles(gl_ctx * ctx, long long n, const double *pos, const double
 int gl_set_oldacc(gl_ctx * ctx, const double *oldacc, int where);
 int gl_set_hsml(gl_ctx * ctx, const double *hsml, int where);
 
+/* SphP state of particles that are NOT density targets of this rank/step (inactive particles, or particles
+ * owned by another GPU after the allgather that replaces the hydro export loop, hydra.c:412): SphP.d.Density,
+ * .Pressure, .h.DhsmlDensityFactor, .v.DivVel, .r.CurlVel; n elements each, indexed like P[]. */
+int gl_set_sph_state(gl_ctx * ctx, const double *density, const double *pressure, const double *dhsml,
+		     const double *divvel, const double *curlvel, int where);
+
 /* ---- domain / keys: domain.c:1972 domain_findExtent, peano.c:300,320,335 ------------------ */
 /* computes DomainCorner/Center/Len/Fac from the loaded positions; out[8] = len, fac, corner[3], center[3] */
 int gl_domain_find_extent(gl_ctx * ctx, double *out8);

@@ -1,0 +1,26 @@
+/* layout_probe.c - prints the byte offsets of the P[] / SphP[] fields the force path touches, as the
+ * reference's allvars.h defines them under the shipped Makefile's -D list (SURVEY.md 8(b) "ABI caveat").
+ * Build-container tool: `make layout` writes gadget_leicester_b200/gadget_layout.json. */
+#include <stdio.h>
+#include <stddef.h>
+#include <mpi.h>
+#include "allvars.h"
+
+#define PO(name, field) printf("  \"%s\": %zu,\n", name, offsetof(struct particle_data, field))
+#define SO(name, field) printf("  \"%s\": %zu,\n", name, offsetof(struct sph_particle_data, field))
+int main(void)
+{
+  printf("{\n");
+  printf("  \"p_stride\": %zu,\n  \"sph_stride\": %zu,\n", sizeof(struct particle_data), sizeof(struct sph_particle_data));
+  PO("p_Pos", Pos); PO("p_Vel", Vel); PO("p_Mass", Mass); PO("p_GravAccel", g.GravAccel); PO("p_OldAcc", OldAcc);
+  PO("p_Hsml", Hsml); PO("p_NumNgb", n.NumNgb); PO("p_GravCost", GravCost); PO("p_Ti_begstep", Ti_begstep);
+  PO("p_Type", Type); PO("p_TimeBin", TimeBin);
+  PO("p_SinkDensity", b1.BH_Density); PO("p_SinkEntropy", b2.BH_Entropy); PO("p_SinkGasVel", b3.BH_SurroundingGasVel);
+  PO("p_DustDensity", d1.DUST_Density); PO("p_DustEntropy", d2.DUST_Entropy); PO("p_DustGasVel", d3.DUST_SurroundingGasVel);
+  PO("p_SwallowID", SwallowID); PO("p_ID", ID);
+  SO("s_Entropy", Entropy); SO("s_Pressure", Pressure); SO("s_VelPred", VelPred); SO("s_MaxSignalVel", MaxSignalVel);
+  SO("s_Density", d.Density); SO("s_DtEntropy", e.DtEntropy); SO("s_HydroAccel", a.HydroAccel);
+  SO("s_DhsmlDensityFactor", h.DhsmlDensityFactor); SO("s_DivVel", v.DivVel); SO("s_CurlVel", r.CurlVel);
+  printf("  \"sizeof_NODE\": %zu,\n  \"sizeof_extNODE\": %zu\n}\n", sizeof(struct NODE), sizeof(struct extNODE));
+  return 0;
+}

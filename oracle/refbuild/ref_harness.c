@@ -21,6 +21,7 @@
  *     H  hydro_force()                        (accel.c:106)
  *     N  dump the node table of the current tree
  *     C  integer pair counts at the current Hsml via ngb_treefind_variable / _pairs
+ *     K  Peano-Hilbert and Morton key of every particle (peano_and_morton_key, peano.c:335)
  *     A  compute_accelerations-order block:  R G D U H   (accel.c:61-106 without sub-grid physics)
  *   every op that computes dumps its outputs under the prefix "<k>_<op>_" with k the
  *   position in the list.
@@ -229,6 +230,27 @@ static void pair_counts(const char *prefix)
   free(cd); free(ch);
 }
 
+/* keys of every particle from the reference's own peano_and_morton_key (peano.c:335) */
+static void dump_keys(const char *prefix)
+{
+  long long n = NumPart, i;
+  long long *ph = malloc(8 * n), *mo = malloc(8 * n);
+  int *ids = malloc(4 * n);
+  for(i = 0; i < n; i++)
+    {
+      peanokey m;
+      ph[i] = (long long) peano_and_morton_key((int) ((P[i].Pos[0] - DomainCorner[0]) * DomainFac),
+						(int) ((P[i].Pos[1] - DomainCorner[1]) * DomainFac),
+						(int) ((P[i].Pos[2] - DomainCorner[2]) * DomainFac), BITS_PER_DIMENSION, &m);
+      mo[i] = (long long) m;
+      ids[i] = (int) P[i].ID;
+    }
+  put(prefix, "id", 'i', n, 1, ids);
+  put(prefix, "phkey", 'q', n, 1, ph);
+  put(prefix, "mortonkey", 'q', n, 1, mo);
+  free(ph); free(mo); free(ids);
+}
+
 static void initial_hsml(void)
 {
   /* restates init.c:719-745 (RestartFlag == 0) */
@@ -364,6 +386,7 @@ int main(int argc, char **argv)
 	    case 'H': hydro_force(); break;
 	    case 'N': dump_nodes(prefix); break;
 	    case 'C': pair_counts(prefix); break;
+	    case 'K': dump_keys(prefix); break;
 	    default: fprintf(stderr, "unknown op %c\n", op); return 2;
 	    }
 	  dt = now() - t0;

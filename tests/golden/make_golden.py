@@ -1,0 +1,85 @@
+"""Generates the committed golden fixtures by running the UNMODIFIED reference (oracle/_ref/ref_harness,
+built by oracle/refbuild from /root/reference) in the build container.
+
+    python tests/golden/make_golden.py
+
+Each fixture is one .npz holding the input particle set, the parameters and every array the reference
+produced for the op sequence below, re-ordered to input order (the reference permutes P[] into
+Peano-Hilbert order; ids make that reversible).  /root/reference is NOT needed to USE the fixtures.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from gadget_leicester_b200 import ics  # noqa: E402
+import util  # noqa: E402
+
+OPS = "K T S D R G G D U H N C"
+# stage prefixes of OPS (position_op_)
+STAGES = dict(keys="0_K_", tree0="1_T_", hsml0="2_S_", dens1="3_D_", grav1="5_G_", grav2="6_G_", dens2="7_D_",
+              hydro="9_H_", nodes="10_N_", pairs="11_C_")
+
+CASES = {
+    "cube_2k": lambda: (ics.cube(2000, seed=11), ics.default_params()),
+    "disc_3k_sinks": lambda: (ics.disc(3000, seed=12), ics.default_params()),
+    "evrard_2k": lambda: (ics.evrard(2000, seed=13), ics.default_params()),
+    "plummer_2k": lambda: (ics.plummer(2000, seed=14),
+                           ics.default_params(Softening=[1e-5, ics.plummer_softening(2000), 5e-5, 1e-7, 0.01, 5e-5])),
+    # ragged: 333 gas + one particle each of types 1 (halo), 2 (dust target), 5 (sink target)
+    "mixed_336": lambda: (_mixed(), ics.default_params()),
+}
+
+
+def _mixed():
+    ps = ics.cube(333, seed=15)
+    g = np.random.Generator(np.random.Philox(key=16))
+    extra = 3
+    out = {}
+    n = 333 + extra
+    out["pos"] = np.vstack([ps["pos"], g.random((extra, 3))])
+    out["vel"] = np.vstack([ps["vel"], np.zeros((extra, 3))])
+    out["mass"] = np.concatenate([ps["mass"], [0.05, 0.02, 0.01]])
+    out["type"] = np.concatenate([ps["type"], [1, 2, 5]]).astype(np.int32)
+    out["hsml"] = np.zeros(n)
+    out["id"] = np.arange(1, n + 1, dtype=np.int32)
+    out["timebin"] = np.zeros(n, dtype=np.int32)
+    out["oldacc"] = np.zeros(n)
+    out["entropy"] = np.concatenate([ps["entropy"], np.zeros(extra)])
+    out["dtentropy"] = np.zeros(n)
+    return out
+
+
+def main():
+    if not util.have_ref():
+        raise SystemExit("oracle/_ref/ref_harness missing: run `make -C oracle/refbuild` (needs /root/reference)")
+    for name, mk in CASES.items():
+        ps, par = mk()
+        # the shipped run uses 10 (.txt PartAllocFactor); a tiny MaxPart trips a heap bug in the reference's top-node retry path
+        par["PartAllocFactor"] = max(10.0, 40000.0 / ps["pos"].shape[0])
+        n = ps["pos"].shape[0]
+        ngas = int((ps["type"] == 0).sum())
+        ref = util.run_oracle(util.REF_HARNESS, ps, par, OPS)
+        out = {"in_" + k: v for k, v in ps.items()}
+        out["params_json"] = np.frombuffer(json.dumps(par).encode(), dtype=np.uint8)
+        for stage, pre in STAGES.items():
+            for k, v in ref.items():
+                if not k.startswith(pre) or k.endswith("_id") or k.endswith("_time"):
+                    continue
+                field = k[len(pre):]
+                if (pre + "id") in ref and v.shape[0] in (n, ngas) and field not in ("nodes", "nodeflags", "domain"):
+                    v = util.by_id(ref, pre, field, v.shape[0])
+                out[stage + "__" + field] = v
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, n, "particles ->", os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

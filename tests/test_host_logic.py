@@ -1,0 +1,103 @@
+"""CPU suite: host-side logic - IC generators, the GLIN/GLOU containers, the AoS layout, and the N>1
+partition + all-gather plumbing on the gloo backend (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gadget_leicester_b200 import ics, aos
+from gadget_leicester_b200.multigpu import partition_range, gather_padded
+from oracle import glio
+
+
+def test_generators_are_deterministic_and_gas_first():
+    for gen, n in ((ics.disc, 500), (ics.evrard, 300), (ics.cube, 300), (ics.plummer, 300)):
+        a, b = gen(n, seed=9), gen(n, seed=9)
+        assert (a["pos"] == b["pos"]).all() and (a["vel"] == b["vel"]).all()
+        ng = int((a["type"] == 0).sum())
+        assert (a["type"][:ng] == 0).all() and (a["type"][ng:] != 0).all()
+        assert len(set(map(tuple, a["pos"]))) == a["pos"].shape[0]  # no coincident points (forcetree.c:208-232)
+    d = ics.disc(500)
+    assert d["pos"].shape[0] == 502 and (d["type"][-2:] == 5).all()
+
+
+def test_glin_roundtrip(tmp_path):
+    ps, par = ics.disc(100, seed=2), ics.default_params()
+    p = tmp_path / "x.glin"
+    glio.write_glin(str(p), ps, par)
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"GLIN"
+    n = int(np.frombuffer(raw[8:16], dtype=np.int64)[0])
+    assert n == 102
+    parr = np.frombuffer(raw[24:24 + 8 * glio.NPAR], dtype=np.float64)
+    assert parr[glio.P_DESNUMNGB] == 40 and parr[glio.P_SOFT0 + 5] == 5e-5
+    pos = np.frombuffer(raw[24 + 8 * glio.NPAR:24 + 8 * glio.NPAR + 24 * n], dtype=np.float64).reshape(n, 3)
+    assert (pos == ps["pos"]).all()
+
+
+def test_aos_layout_matches_reference_struct_sizes():
+    lay = aos.layout()
+    assert lay["p_stride"] == 536 and lay["sph_stride"] == 264
+    assert lay["p_GravCost"] == 520 and lay["p_Type"] == 532 and lay["s_HydroAccel"] == 96
+    ps = ics.disc(64, seed=3)
+    ps["hsml"][:] = 0.1
+    arr = aos.GadgetArrays(ps, pinned=False)
+    assert (arr.pview("p_Pos", np.float64, 3) == ps["pos"]).all()
+    assert (arr.pview("p_Type", np.int16) == ps["type"]).all()
+    assert (arr.sview("s_VelPred", np.float64, 3) == ps["vel"][:64]).all()
+    r = arr.results()
+    assert r["Hsml"][0] == 0.1 and r["Density"][0] == -1.0
+
+
+def test_partition_covers_everything():
+    for n in (1, 7, 64, 1000003):
+        for world in (1, 2, 3, 8):
+            segs = [partition_range(n, world, r) for r in range(world)]
+            assert segs[0][0] == 0 and segs[-1][1] == n
+            for a, b in zip(segs, segs[1:]):
+                assert a[1] == b[0]
+            assert all(hi - lo <= m for lo, hi, m in segs)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi, m = partition_range(n, world, rank)
+    full = torch.arange(n * 3, dtype=torch.float64).reshape(n, 3)
+    got = gather_padded(full[lo:hi].clone(), n, m)
+    ids = gather_padded(torch.arange(lo, hi, dtype=torch.int32), n, m)
+    ok = bool((got == full).all()) and bool((ids == torch.arange(n, dtype=torch.int32)).all())
+    # the "unconverged targets remaining" reduction of density.c:656 in NCCL/gloo form
+    left = torch.tensor([rank + 1], dtype=torch.int64)
+    dist.all_reduce(left)
+    ok = ok and int(left.item()) == world * (world + 1) // 2
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 11, 1001])
+def test_allgather_plumbing_gloo_world2(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
