@@ -48,6 +48,8 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->o_pressure.release(); c->o_sinkrho.release(); c->o_sinkentr.release(); c->o_sinkvel.release(); c->o_hacc.release();
   c->o_dtentr.release(); c->o_maxsig.release(); c->o_gravcost.release(); c->o_denspairs.release();
   c->o_hydropairs.release(); c->d_counter.release(); c->h_q.release(); c->h_r.release();
+  c->e_rng.release(); c->n_child.release(); c->fat_p.release(); c->fat_i.release(); c->fat_state.release();
+  c->fat_rec.release(); c->fat_tgt.release();
   if(c->pin) cudaFreeHost(c->pin);
   for(int i = 0; i < 16; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);

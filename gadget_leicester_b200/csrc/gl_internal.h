@@ -109,6 +109,7 @@ struct gl_ctx
   DBuf<double4> n_sm;		// s[3], mass
   DBuf<double4> n_cl;		// center[3], len
   DBuf<double4> n_aux;		// maxsoft, hmax, vmax, divVmax
+  DBuf<int> n_child;		// 8 child codes per node (see k_moments)
   DBuf<int> p_father;		// Father[] analogue: node id containing sorted particle directly
   DBuf<int> scan_tmp_i;
   // ---- walk entries (DFS order, nodes and particle leaves interleaved) ----
@@ -117,6 +118,7 @@ struct gl_ctx
   DBuf<double4> e_B;		// node: center,len ; particle: soft,0,0,-1
   DBuf<double2> e_C;		// node: maxsoft, mass*len*len ; particle: unused
   DBuf<double> e_hmax;		// node: hmax (for the symmetric search)
+  DBuf<int2> e_rng;		// node: [first,end) range of tree-ordered particles below it
   // ---- targets ----
   DBuf<int> tgt_in;		// user-supplied P[] indices (or empty = all)
   long long n_tgt_in = -1;
@@ -135,6 +137,10 @@ struct gl_ctx
   // ---- hydro source records (sorted order) ----
   DBuf<double4> h_q;		// rho, P/rho^2, P/rho^2*Omega, soundspeed
   DBuf<double2> h_r;		// f (Balsara), timestep
+  // ---- fat density targets (block-per-target path) ----
+  DBuf<int> fat_p, fat_i;
+  DBuf<double4> fat_state, fat_rec;
+  DBuf<double> fat_tgt;
   // ---- gadget AoS layer ----
   gl_gadget_layout lay{};
   bool have_lay = false;

@@ -6,15 +6,26 @@
 // (ngb.c:169-297) and forms 11 sums; hydro_force/hydro_evaluate (hydra.c:145-813, :822-1995) do the
 // same with the symmetric search ngb_treefind_pairs (ngb.c:32-160).
 //
-// B200 design: the Hsml sequence of a target depends on that target alone (the one-sided search
-// only uses h_i), so the whole iteration runs inside one kernel: a warp owns 32 consecutive SPH
-// targets of the Morton order, marches once per round through the DFS entry array pruning with the
-// bounding box of its still-unconverged lanes, and every lane tests each surviving gas particle
-// with the reference's FP64 predicate r2 < h_i^2.  Neighbours are met in the reference's own order
-// (DFS = child-slot order), sums are FP64 without FMA contraction, so Density/NumNgb agree with
-// the oracle to the last bits and the Hsml iteration follows the reference's path exactly.
-// Rounds continue until all lanes of the warp are done - no host round trips, no relaunch.
+// B200 design.  One warp owns 32 consecutive SPH targets of the Peano-Hilbert order (a compact
+// clump).  The Hsml sequence of a target depends on that target alone (the one-sided search only
+// uses h_i), so the whole iteration runs inside ONE kernel launch, round by round, until every
+// lane of the warp has converged - no host round trips, no relaunch, no MPI_Allreduce of
+// "particles left" (density.c:656).  Each round has three phases:
+//   1. collect  - the warp marches through the DFS entry array; a node is entered only if the
+//                 search sphere of at least one still-active lane touches its cube (per-lane
+//                 test + vote, so one far-out lane does not inflate everybody's search); a cell
+//                 with <= 32 particles is swallowed in one coalesced load.  Gas candidates
+//                 (position, mass, h) are STAGED IN SHARED MEMORY, 256 at a time.
+//   2. test     - for every active target the 32 lanes test 32 staged candidates per step with
+//                 the reference's FP64 predicate r2 < h^2 (same operation order, no FMA);
+//                 hits are compacted with ballot/popc into a dense hit list.
+//   3. sum      - full warps of hits evaluate the kernel and its derivative (all lanes busy)
+//                 and the per-lane partial sums are combined with WARP SHUFFLES.
+// The neighbour SETS (hence the integer pair counts) are exactly the reference's; the FP64 sums are
+// formed in a different order (32 partial sums + butterfly), i.e. they agree to ~1e-15 relative.
 #include "gl_internal.h"
+#include <climits>
+#include <algorithm>
 
 gl_dparams gl_make_dparams(const gl_ctx *c);
 
@@ -28,16 +39,208 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define GL_GAMMA (7. / 5.)	// allvars.h:64
 #define GL_GAMMA_MINUS1 (GL_GAMMA - 1)
 #define BOX_SLACK 1.0000000001
+#define CAND_CAP 256		// staged candidates per warp
+#define SPH_WARPS 4
+#define STK_CAP 1024
+#define FAT_THRESH 4096	// neighbours above which a target leaves the warp path
+#define FAT_MAX 64
+#define STK_RESERVE 160	// 7 pushes per level x 21 levels: pure depth-first continuation never overflows
+#define SPH_BLOCK (32 * SPH_WARPS)
+#define FULL 0xffffffffu
 
-__device__ __forceinline__ double warp_min_d(double v, unsigned mask = 0xffffffffu)
+__device__ __forceinline__ double warp_sum_d(double v)
 {
-  for(int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, o));
+  for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
-__device__ __forceinline__ double warp_max_d(double v, unsigned mask = 0xffffffffu)
+__device__ __forceinline__ double warp_max_d(double v)
 {
-  for(int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o));
+  for(int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
   return v;
+}
+__device__ __forceinline__ double warp_min_d(double v)
+{
+  for(int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// squared distance from point p to the cube (centre B.xyz, half side `half`)
+__device__ __forceinline__ double dist2_to_cube(double px, double py, double pz, const double4 &B, double half)
+{
+  const double dx = fmax(0.0, fabs(B.x - px) - half);
+  const double dy = fmax(0.0, fabs(B.y - py) - half);
+  const double dz = fmax(0.0, fabs(B.z - pz) - half);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+struct WarpStage
+{
+  double x[CAND_CAP], y[CAND_CAP], z[CAND_CAP], m[CAND_CAP], h[CAND_CAP];	// position, mass, Hsml of the candidate
+  int j[CAND_CAP];
+  int hit[64];
+  int stk[STK_CAP];		// tree cells still to be examined (DFS entry index, or -(p+2) for a lone particle)
+  int2 rng[32];			// particle ranges swallowed in the current step
+};
+
+// append the gas particles of the tree range [a,b) (b-a <= 32) to the staged list; returns the new count
+__device__ __forceinline__ int stage_range(WarpStage &S, int ncand, int a, int b, int lane, const double4 *__restrict__ s_pm,
+					    const double4 *__restrict__ s_vh, const int *__restrict__ s_type)
+{
+  const int j = a + lane;
+  bool ok = j < b;
+  double4 pm = make_double4(0, 0, 0, 0);
+  if(ok)
+    {
+      ok = (s_type[j] == 0);	// ngb.c:54 / :191: only gas particles are neighbours
+      if(ok)
+	{
+	  pm = gl_ld4(&s_pm[j]);
+	  ok = (pm.w != 0);	// density.c:832 / hydra.c:1236: skip Mass == 0
+	}
+    }
+  const unsigned ball = __ballot_sync(FULL, ok);
+  if(ok)
+    {
+      const int pos = ncand + __popc(ball & ((1u << lane) - 1));
+      S.x[pos] = pm.x;
+      S.y[pos] = pm.y;
+      S.z[pos] = pm.z;
+      S.m[pos] = pm.w;
+      S.h[pos] = s_vh[j].w;
+      S.j[pos] = j;
+    }
+  return ncand + __popc(ball);
+}
+
+// after a batch of `take` hits has been consumed, move the remaining hit-list entries to the front
+__device__ __forceinline__ void hits_shift(WarpStage &S, int nh, int lane)
+{
+  __syncwarp();
+  if(nh > 32)
+    {
+      const int mv = S.hit[32 + lane];
+      __syncwarp();
+      if(lane < nh - 32) S.hit[lane] = mv;
+      __syncwarp();
+    }
+}
+
+// Phase 1, warp-parallel.  The warp keeps a stack of tree cells still to be examined.  Every step the lanes
+// pop up to 32 cells, fetch their cubes with INDEPENDENT loads (one memory latency per step instead of one
+// per cell), test each cube against the search spheres of the still-active targets (ngb.c:270-289 /
+// :136-152), and either swallow the cell (<= 32 particles: its tree range is staged with one coalesced
+// load) or push its children (child table written by k_moments).  flush(ncand) runs phases 2+3.
+template <bool USE_HMAX, class Flush>
+__device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries, const int *__restrict__ e_next,
+					    const double4 *__restrict__ e_B, const double *__restrict__ e_hmax,
+					    const int2 *__restrict__ e_rng, const int *__restrict__ n_child,
+					    const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
+					    const int *__restrict__ s_type, unsigned active, double px, double py, double pz,
+					    double radius, unsigned &visits, unsigned &staged, Flush flush)
+{
+  if(nentries <= 0 || active == 0) return;
+  int ncand = 0;
+  if(lane == 0) S.stk[0] = (__ldg(&e_next[0]) >= 0) ? 0 : -2;
+  __syncwarp();
+  int sp = 1;
+  const unsigned lt = (1u << lane) - 1;
+  while(sp > 0)
+    {
+      int k = sp < 32 ? sp : 32;
+      int room = (STK_CAP - STK_RESERVE - sp) / 7;
+      if(room < 1) room = 1;
+      if(k > room) k = room;
+      const int my = (lane < k) ? S.stk[sp - 1 - lane] : -1;
+      sp -= k;
+      __syncwarp();
+      visits += k;
+      const bool isnode = my >= 0;
+      const bool ispart = my < -1;
+      double4 B = make_double4(0, 0, 0, 0);
+      int2 rg = make_int2(0, 0);
+      double hm = 0, half = 0;
+      if(isnode)
+	{
+	  B = gl_ld4(&e_B[my]);
+	  rg = __ldg(&e_rng[my]);
+	  if(USE_HMAX) hm = __ldg(&e_hmax[my]);
+	  half = 0.5 * B.w;
+	}
+      bool acc = false;
+      unsigned need = __ballot_sync(FULL, isnode);
+      for(unsigned rest = active; rest && need; rest &= rest - 1)
+	{
+	  const int t = __ffs(rest) - 1;
+	  const double tx = __shfl_sync(FULL, px, t), ty = __shfl_sync(FULL, py, t), tz = __shfl_sync(FULL, pz, t);
+	  const double tr = __shfl_sync(FULL, radius, t);
+	  if(isnode && !acc)
+	    {
+	      const double R = (USE_HMAX ? fmax(tr, hm) : tr) * BOX_SLACK;
+	      acc = dist2_to_cube(tx, ty, tz, B, half) < R * R;
+	    }
+	  need = __ballot_sync(FULL, isnode && !acc);
+	}
+      const bool small = acc && (rg.y - rg.x <= 32);
+      bool big = acc && !small;
+      bool bucket = false;
+      // push the children of the large cells
+      int4 c0 = make_int4(-1, -1, -1, -1), c1 = c0;
+      if(big)
+	{
+	  const int4 *ct = reinterpret_cast<const int4 *>(n_child + 8ll * (my - rg.x));
+	  c0 = __ldg(ct);
+	  c1 = __ldg(ct + 1);
+	  if(c0.x == INT_MIN)
+	    {
+	      bucket = true;	// finest-level cell holding coincident keys: no child table, staged piecewise below
+	      big = false;
+	    }
+	}
+      const int cc[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+#pragma unroll
+      for(int i = 0; i < 8; i++)
+	{
+	  const bool has = big && cc[i] != -1;
+	  const unsigned ball = __ballot_sync(FULL, has);
+	  if(has) S.stk[sp + __popc(ball & lt)] = cc[i];
+	  sp += __popc(ball);
+	}
+      // swallow the small cells and the lone particles
+      const bool isrange = small || ispart;
+      if(ispart) rg = make_int2(-(my + 2), -(my + 2) + 1);
+      const unsigned rball = __ballot_sync(FULL, isrange);
+      if(isrange) S.rng[__popc(rball & lt)] = rg;
+      const int nr = __popc(rball);
+      __syncwarp();
+      for(int i = 0; i < nr; i++)
+	{
+	  const int2 r = S.rng[i];
+	  if(ncand + 32 > CAND_CAP)
+	    {
+	      flush(ncand);
+	      ncand = 0;
+	    }
+	  ncand = stage_range(S, ncand, r.x, r.y, lane, s_pm, s_vh, s_type);
+	  staged += r.y - r.x;
+	}
+      for(unsigned bm = __ballot_sync(FULL, bucket); bm; bm &= bm - 1)
+	{
+	  const int b = __ffs(bm) - 1;
+	  const int ra = __shfl_sync(FULL, rg.x, b), rb = __shfl_sync(FULL, rg.y, b);
+	  for(int a = ra; a < rb; a += 32)
+	    {
+	      if(ncand + 32 > CAND_CAP)
+		{
+		  flush(ncand);
+		  ncand = 0;
+		}
+	      ncand = stage_range(S, ncand, a, (a + 32 < rb) ? a + 32 : rb, lane, s_pm, s_vh, s_type);
+	    }
+	  staged += rb - ra;
+	}
+      __syncwarp();
+    }
+  if(ncand > 0) flush(ncand);
 }
 
 struct DensOut
@@ -46,14 +249,258 @@ struct DensOut
   int *pairs;
 };
 
-__global__ void __launch_bounds__(GL_BLOCK)
+struct DensAcc
+{
+  double rho, wngb, dhsmlrho, divv, rot0, rot1, rot2, sentr, gv0, gv1, gv2;
+  int numngb;
+  __device__ void zero() { rho = wngb = dhsmlrho = divv = rot0 = rot1 = rot2 = sentr = gv0 = gv1 = gv2 = 0; numngb = 0; }
+};
+
+// density.c:548-646 for one target: is the neighbour number inside the window?  If not, move the bracket and
+// Hsml exactly as the reference does.  Returns true when the target has to be evaluated again.
+__device__ __forceinline__ bool hsml_step(double wngb, double rho, double dhsmlrho, int ptype, double desnumngb,
+					  const gl_dparams &par, double &h, double &left, double &right,
+					  unsigned long long *counter)
+{
+  bool redo = (wngb < (desnumngb - par.maxdev)) || (wngb > (desnumngb + par.maxdev) && h > (1.01 * par.mingashsml));
+  if(redo && left > 0 && right > 0 && (right - left) < 1.0e-3 * left) redo = false;	// density.c:566-573
+  if(!redo) return false;
+  double dfac = 1.0;
+  if(ptype == 0 && rho > 0)
+    {
+      dfac = dhsmlrho * (h / (3 * rho));	// density.c:442
+      dfac = (dfac > -0.9) ? 1 / (1 + dfac) : 1;
+    }
+  if(wngb < (desnumngb - par.maxdev))
+    left = fmax(h, left);
+  else
+    {
+      if(right != 0)
+	{
+	  if(h < right) right = h;
+	}
+      else
+	right = h;
+    }
+  if(right > 0 && left > 0)
+    h = pow(0.5 * (pow(left, 3.0) + pow(right, 3.0)), 1.0 / 3);
+  else
+    {
+      if(right == 0 && left == 0) atomicMax(&counter[2], 8188ull);	// endrun(8188), density.c:608
+      if(right == 0 && left > 0)
+	{
+	  if(ptype == 0 && fabs(wngb - desnumngb) < 0.5 * desnumngb)
+	    {
+	      const double fac = 1 - (wngb - desnumngb) / (3 * wngb) * dfac;
+	      h *= (fac < 1.26) ? fac : 1.26;
+	    }
+	  else
+	    h *= 1.26;
+	}
+      if(right > 0 && left == 0)
+	{
+	  if(ptype == 0 && fabs(wngb - desnumngb) < 0.5 * desnumngb)
+	    {
+	      const double fac = 1 - (wngb - desnumngb) / (3 * wngb) * dfac;
+	      if(fac > 1 / 1.26)
+		h *= fac;
+	      else
+		h /= 1.26;
+	    }
+	  else
+	    h /= 1.26;
+	}
+    }
+  if(h < par.mingashsml) h = par.mingashsml;
+  return true;
+}
+
+struct DensIn
+{
+  const int *noff;
+  const double *in_entropy, *in_dtentropy;
+  const int *in_timebin, *in_tibegstep;
+};
+
+// final store of one converged target: density.c:434-546 post-processing + the P[]/SphP[] fields
+__device__ __forceinline__ void density_store(const DensAcc &A, double h, int p, int pin, int ptype, const DensOut &out,
+					      const DensIn &in, double4 *__restrict__ s_vh, double4 *__restrict__ e_B,
+					      const gl_dparams &par)
+{
+  const double rho = A.rho;
+  out.hsml_in[pin] = h;
+  s_vh[p].w = h;
+  out.numngb[pin] = A.wngb;
+  out.pairs[pin] = A.numngb;
+  if(ptype == 0)
+    {
+      e_B[(long long) p + in.noff[p + 1]].x = h;	// live Hsml for the gravity softening, forcetree.c:2046-2054
+      double dfac = A.dhsmlrho, curl = 0, dv = A.divv;
+      if(rho > 0)
+	{
+	  dfac *= h / (3 * rho);
+	  dfac = (dfac > -0.9) ? 1 / (1 + dfac) : 1;
+	  curl = sqrt(A.rot0 * A.rot0 + A.rot1 * A.rot1 + A.rot2 * A.rot2) / rho;
+	  dv = A.divv / rho;
+	}
+      const int tb = in.in_timebin[pin];
+      const int dt_step = tb ? (1 << tb) : 0;
+      const double dt_entr = (par.ti_current - (in.in_tibegstep[pin] + dt_step / 2)) * par.timebase_interval;
+      out.density[pin] = rho;
+      out.dhsml[pin] = dfac;
+      out.divvel[pin] = dv;
+      out.curlvel[pin] = curl;
+      out.pressure[pin] = (in.in_entropy[pin] + in.in_dtentropy[pin] * dt_entr) * pow(rho, GL_GAMMA);
+    }
+  else
+    {				// density.c:520-546 sink (Type 5) / dust (Type 2) post-processing
+      double se = A.sentr, g0 = A.gv0, g1 = A.gv1, g2 = A.gv2;
+      if(rho > 0)
+	{
+	  se /= rho; g0 /= rho; g1 /= rho; g2 /= rho;
+	}
+      out.sinkrho[pin] = rho;
+      out.sinkentr[pin] = se;
+      out.sinkvel[3ll * pin] = g0;
+      out.sinkvel[3ll * pin + 1] = g1;
+      out.sinkvel[3ll * pin + 2] = g2;
+    }
+}
+
+// kernel value + derivative and the density.c:862-913 sums for one neighbour
+__device__ __forceinline__ void density_pair(DensAcc &P, int ttype, double dx, double dy, double dz, double r2, double mass_j,
+					     double hinv, double hinv3, double hinv4, double tvx, double tvy, double tvz,
+					     const double4 &vj, double entr_j)
+{
+  P.numngb++;
+  const double r = sqrt(r2);
+  const double u = r * hinv;
+  double wk, dwk;
+  if(u < 0.5)
+    {
+      wk = hinv3 * (KERNEL_COEFF_1 + KERNEL_COEFF_2 * (u - 1) * u * u);
+      dwk = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
+    }
+  else
+    {
+      wk = hinv3 * KERNEL_COEFF_5 * (1.0 - u) * (1.0 - u) * (1.0 - u);
+      dwk = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+    }
+  P.rho += mass_j * wk;
+  P.wngb += NORM_COEFF * wk / hinv3;
+  P.dhsmlrho += -mass_j * (3 * hinv * wk + u * dwk);
+  if(ttype != 0)
+    {				// only sink / dust targets keep these (density.c:944-988)
+      P.gv0 += mass_j * wk * vj.x;
+      P.gv1 += mass_j * wk * vj.y;
+      P.gv2 += mass_j * wk * vj.z;
+      P.sentr += mass_j * wk * entr_j;
+    }
+  else if(r > 0)
+    {
+      const double fac = mass_j * dwk / r;
+      const double dvx = tvx - vj.x, dvy = tvy - vj.y, dvz = tvz - vj.z;
+      P.divv += -fac * (dx * dvx + dy * dvy + dz * dvz);
+      P.rot0 += fac * (dz * dvy - dy * dvz);
+      P.rot1 += fac * (dx * dvz - dz * dvx);
+      P.rot2 += fac * (dy * dvx - dx * dvy);
+    }
+}
+
+// phases 2+3 for one staged chunk: every active target against all staged candidates
+__device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, unsigned todo_mask, int lane, double px, double py,
+					      double pz, double vx, double vy, double vz, double h, int ptype, DensAcc &A,
+					      const double4 *__restrict__ s_vh, const double *__restrict__ s_entropy)
+{
+  __syncwarp();
+  for(unsigned rest = todo_mask; rest; rest &= rest - 1)
+    {
+      const int t = __ffs(rest) - 1;
+      const double tx = __shfl_sync(FULL, px, t), ty = __shfl_sync(FULL, py, t), tz = __shfl_sync(FULL, pz, t);
+      const double th = __shfl_sync(FULL, h, t);
+      const double tvx = __shfl_sync(FULL, vx, t), tvy = __shfl_sync(FULL, vy, t), tvz = __shfl_sync(FULL, vz, t);
+      const int ttype = __shfl_sync(FULL, ptype, t);
+      const double h2 = th * th;
+      const double hinv = 1.0 / th;
+      const double hinv3 = hinv * hinv * hinv;
+      const double hinv4 = hinv3 * hinv;
+      DensAcc P;
+      P.zero();
+      int nh = 0;
+      for(int base = 0;; base += 32)
+	{
+	  if(base < ncand)
+	    {
+	      const int c = base + lane;
+	      bool hit = false;
+	      if(c < ncand)
+		{
+		  // density.c:835-856: dx = pos_i - pos_j, r2 = dx*dx + dy*dy + dz*dz, r2 < h2
+		  const double dx = tx - S.x[c], dy = ty - S.y[c], dz = tz - S.z[c];
+		  hit = (dx * dx + dy * dy + dz * dz) < h2;
+		}
+	      const unsigned ball = __ballot_sync(FULL, hit);
+	      if(hit) S.hit[nh + __popc(ball & ((1u << lane) - 1))] = c;
+	      nh += __popc(ball);
+	      __syncwarp();
+	      if(nh < 32 && base + 32 < ncand) continue;	// keep filling until a full warp of hits is available
+	    }
+	  if(nh == 0) break;
+	  // phase 3: one hit per lane
+	  const int take = nh < 32 ? nh : 32;
+	  if(lane < take)
+	    {
+	      const int c = S.hit[lane];
+	      const int j = S.j[c];
+	      const double dx = tx - S.x[c], dy = ty - S.y[c], dz = tz - S.z[c];
+	      const double r2 = dx * dx + dy * dy + dz * dz;
+	      const double4 vj = gl_ld4(&s_vh[j]);
+	      density_pair(P, ttype, dx, dy, dz, r2, S.m[c], hinv, hinv3, hinv4, tvx, tvy, tvz, vj,
+			   (ttype != 0) ? __ldg(&s_entropy[j]) : 0.0);
+	    }
+	  hits_shift(S, nh, lane);
+	  nh -= take;
+	  if(base + 32 >= ncand && nh == 0) break;
+	}
+      // warp-shuffle reduction of the partial sums into the owner lane
+      const int tot = __reduce_add_sync(FULL, P.numngb);
+      if(tot == 0) continue;
+      const double r_rho = warp_sum_d(P.rho), r_w = warp_sum_d(P.wngb), r_d = warp_sum_d(P.dhsmlrho);
+      double r4, r5, r6, r7;
+      if(ttype != 0)
+	{
+	  r4 = warp_sum_d(P.gv0); r5 = warp_sum_d(P.gv1); r6 = warp_sum_d(P.gv2); r7 = warp_sum_d(P.sentr);
+	}
+      else
+	{
+	  r4 = warp_sum_d(P.divv); r5 = warp_sum_d(P.rot0); r6 = warp_sum_d(P.rot1); r7 = warp_sum_d(P.rot2);
+	}
+      if(lane == t)
+	{
+	  A.rho += r_rho; A.wngb += r_w; A.dhsmlrho += r_d; A.numngb += tot;
+	  if(ttype != 0)
+	    {
+	      A.gv0 += r4; A.gv1 += r5; A.gv2 += r6; A.sentr += r7;
+	    }
+	  else
+	    {
+	      A.divv += r4; A.rot0 += r5; A.rot1 += r6; A.rot2 += r7;
+	    }
+	}
+    }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(SPH_BLOCK)
 k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
-	  double4 *__restrict__ e_B, const double4 *__restrict__ s_pm, double4 *__restrict__ s_vh,
-	  const int *__restrict__ s_type, const double *__restrict__ s_entropy, const int *__restrict__ noff,
-	  const int *__restrict__ perm, const double *__restrict__ in_entropy, const double *__restrict__ in_dtentropy,
-	  const int *__restrict__ in_timebin, const int *__restrict__ in_tibegstep, DensOut out,
+	  double4 *__restrict__ e_B, const int2 *__restrict__ e_rng, const int *__restrict__ n_child,
+	  const double4 *__restrict__ s_pm, double4 *__restrict__ s_vh, const int *__restrict__ s_type, const double *__restrict__ s_entropy,
+	  const int *__restrict__ perm, DensIn in, DensOut out, int *__restrict__ fat_p, double4 *__restrict__ fat_state,
 	  unsigned long long *__restrict__ counter, gl_dparams par)
 {
+  extern __shared__ __align__(16) unsigned char gl_smem_raw[];
+  WarpStage *stage = reinterpret_cast<WarpStage *>(gl_smem_raw);
+  WarpStage &S = stage[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long) blockDim.x + threadIdx.x) >> 5;
   const long long t = warp * 32 + lane;
@@ -63,8 +510,8 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
   if(live)
     {
       p = tgt[t];
-      double4 pm = s_pm[p];
-      double4 vh = s_vh[p];
+      const double4 pm = s_pm[p];
+      const double4 vh = s_vh[p];
       px = pm.x; py = pm.y; pz = pm.z;
       ptype = s_type[p];
       pin = perm[p];
@@ -75,150 +522,62 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
 	}
     }
   const double desnumngb = (ptype == 5) ? par.desnumngb * par.bhfac : par.desnumngb;	// density.c:548-557
+  const long long clk0 = clock64();
+  unsigned visits = 0, staged = 0;
   double left = 0, right = 0;
   bool todo = live;
   int iter = 0;
-  double rho = 0, wngb = 0, dhsmlrho = 0, divv = 0, rot0 = 0, rot1 = 0, rot2 = 0, sentr = 0, gv0 = 0, gv1 = 0, gv2 = 0;
-  int numngb = 0;
-
-  while(__any_sync(0xffffffffu, todo))
+  DensAcc A;
+  A.zero();
+  // the pair count of the previous call tells which targets are "fat" before any work is spent on them
+  bool defer = live && (out.pairs[pin] > FAT_THRESH), deferred = false;
+  if(__any_sync(FULL, defer))
     {
-      // bounding box of the search spheres of the lanes still iterating
-      const double hb = h * BOX_SLACK;
-      const double bxlo = warp_min_d(todo ? px - hb : 1e300), bxhi = warp_max_d(todo ? px + hb : -1e300);
-      const double bylo = warp_min_d(todo ? py - hb : 1e300), byhi = warp_max_d(todo ? py + hb : -1e300);
-      const double bzlo = warp_min_d(todo ? pz - hb : 1e300), bzhi = warp_max_d(todo ? pz + hb : -1e300);
-      const double h2 = h * h;
-      const double hinv = 1.0 / h;
-      const double hinv3 = hinv * hinv * hinv;
-      const double hinv4 = hinv3 * hinv;
-      if(todo)
-	{			// lanes that already converged keep the sums of their final round
-	  rho = wngb = dhsmlrho = divv = rot0 = rot1 = rot2 = sentr = gv0 = gv1 = gv2 = 0;
-	  numngb = 0;
-	}
-      int e = 0;
-      while(e < nentries)
+      if(defer)
 	{
-	  const int nx = __ldg(&e_next[e]);
-	  if(nx >= 0)
+	  const int slot = (int) atomicAdd(&counter[8], 1ull);
+	  if(slot < FAT_MAX)
 	    {
-	      // node: prune against the group box (ngb.c:270-289 does it per target with h + len/2)
-	      const double4 B = e_B[e];
-	      const double half = 0.5 * B.w;
-	      const bool out_of_box = (B.x + half < bxlo) || (B.x - half > bxhi) || (B.y + half < bylo) ||
-		(B.y - half > byhi) || (B.z + half < bzlo) || (B.z - half > bzhi);
-	      e = out_of_box ? nx : e + 1;
-	      continue;
-	    }
-	  const int code = -1 - nx;
-	  e++;
-	  if((code & 7) != 0) continue;	// ngb.c:191: only gas particles are neighbours
-	  const int j = code >> 3;
-	  const double4 pj = gl_ld4(&s_pm[j]);
-	  if(pj.w == 0) continue;	// density.c:832
-	  // density.c:835-856
-	  const double dx = px - pj.x, dy = py - pj.y, dz = pz - pj.z;
-	  const double r2 = dx * dx + dy * dy + dz * dz;
-	  const bool hit = todo && (r2 < h2);
-	  if(!__any_sync(0xffffffffu, hit)) continue;
-	  const double4 vj = gl_ld4(&s_vh[j]);
-	  const double entr_j = __ldg(&s_entropy[j]);
-	  if(hit)
-	    {
-	      numngb++;
-	      const double r = sqrt(r2);
-	      const double u = r * hinv;
-	      double wk, dwk;
-	      if(u < 0.5)
-		{
-		  wk = hinv3 * (KERNEL_COEFF_1 + KERNEL_COEFF_2 * (u - 1) * u * u);
-		  dwk = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
-		}
-	      else
-		{
-		  wk = hinv3 * KERNEL_COEFF_5 * (1.0 - u) * (1.0 - u) * (1.0 - u);
-		  dwk = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-		}
-	      const double mass_j = pj.w;
-	      rho += mass_j * wk;
-	      wngb += NORM_COEFF * wk / hinv3;
-	      dhsmlrho += -mass_j * (3 * hinv * wk + u * dwk);
-	      gv0 += mass_j * wk * vj.x;
-	      gv1 += mass_j * wk * vj.y;
-	      gv2 += mass_j * wk * vj.z;
-	      sentr += mass_j * wk * entr_j;
-	      if(r > 0)
-		{
-		  const double fac = mass_j * dwk / r;
-		  const double dvx = vx - vj.x, dvy = vy - vj.y, dvz = vz - vj.z;
-		  divv += -fac * (dx * dvx + dy * dvy + dz * dvz);
-		  rot0 += fac * (dz * dvy - dy * dvz);
-		  rot1 += fac * (dx * dvz - dz * dvx);
-		  rot2 += fac * (dy * dvx - dx * dvy);
-		}
+	      fat_p[slot] = p;
+	      fat_state[slot] = make_double4(h, 0.0, 0.0, 0.0);
+	      todo = false;
+	      deferred = true;
 	    }
 	}
+      defer = false;
+    }
+
+  while(true)
+    {
+      const unsigned todo_mask = __ballot_sync(FULL, todo);
+      if(todo_mask == 0) break;
+      if(todo) A.zero();	// lanes that already converged keep the sums of their final round
+      sph_collect<false>(S, lane, nentries, e_next, e_B, nullptr, e_rng, n_child, s_pm, s_vh, s_type, todo_mask, px, py, pz, h,
+			 visits, staged, [&](int ncand) {
+			   density_chunk(S, ncand, todo_mask, lane, px, py, pz, vx, vy, vz, h, ptype, A, s_vh, s_entropy);
+			 });
 
       // ---- post-processing and Hsml update, density.c:434-652 (one lane = one target) ----
       if(todo)
 	{
-	  bool redo = (wngb < (desnumngb - par.maxdev)) || (wngb > (desnumngb + par.maxdev) && h > (1.01 * par.mingashsml));
-	  if(redo && left > 0 && right > 0 && (right - left) < 1.0e-3 * left) redo = false;	// density.c:566-573
-	  if(redo)
-	    {
-	      double dfac = 1.0;
-	      if(ptype == 0 && rho > 0)
-		{
-		  dfac = dhsmlrho * (h / (3 * rho));	// density.c:442
-		  dfac = (dfac > -0.9) ? 1 / (1 + dfac) : 1;
-		}
-	      if(wngb < (desnumngb - par.maxdev))
-		left = fmax(h, left);
-	      else
-		{
-		  if(right != 0)
-		    {
-		      if(h < right) right = h;
-		    }
-		  else
-		    right = h;
-		}
-	      if(right > 0 && left > 0)
-		h = pow(0.5 * (pow(left, 3.0) + pow(right, 3.0)), 1.0 / 3);
-	      else
-		{
-		  if(right == 0 && left == 0) atomicMax(&counter[2], 8188ull);	// endrun(8188), density.c:608
-		  if(right == 0 && left > 0)
-		    {
-		      if(ptype == 0 && fabs(wngb - desnumngb) < 0.5 * desnumngb)
-			{
-			  double fac = 1 - (wngb - desnumngb) / (3 * wngb) * dfac;
-			  h *= (fac < 1.26) ? fac : 1.26;
-			}
-		      else
-			h *= 1.26;
-		    }
-		  if(right > 0 && left == 0)
-		    {
-		      if(ptype == 0 && fabs(wngb - desnumngb) < 0.5 * desnumngb)
-			{
-			  double fac = 1 - (wngb - desnumngb) / (3 * wngb) * dfac;
-			  if(fac > 1 / 1.26)
-			    h *= fac;
-			  else
-			    h /= 1.26;
-			}
-		      else
-			h /= 1.26;
-		    }
-		}
-	      if(h < par.mingashsml) h = par.mingashsml;
-	    }
-	  else
-	    todo = false;
+	  todo = hsml_step(A.wngb, A.rho, A.dhsmlrho, ptype, desnumngb, par, h, left, right, counter);
+	  if(todo && A.numngb > FAT_THRESH) defer = true;
 	}
       iter++;
+      if(defer && todo)
+	{
+	  // a target with thousands of neighbours (a sink in a disc hole) would keep this warp busy for the rest of
+	  // the launch: hand it to the block-per-target path, which continues its iteration where it stands
+	  const int slot = (int) atomicAdd(&counter[8], 1ull);
+	  if(slot < FAT_MAX)
+	    {
+	      fat_p[slot] = p;
+	      fat_state[slot] = make_double4(h, left, right, (double) iter);
+	      todo = false;
+	      deferred = true;
+	    }
+	  defer = false;
+	}
       if(iter > GL_MAXITER)
 	{			// density.c:669-674 endrun(1155)
 	  if(todo) atomicMax(&counter[2], 1155ull);
@@ -226,54 +585,244 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
 	}
     }
 
-  if(live)
+  if(live && !deferred) density_store(A, h, p, pin, ptype, out, in, s_vh, e_B, par);
+  const unsigned maxit = __reduce_max_sync(FULL, (unsigned) iter);
+  if(lane == 0)
     {
-      out.hsml_in[pin] = h;
-      s_vh[p].w = h;
-      out.numngb[pin] = wngb;
-      out.pairs[pin] = numngb;
-      if(ptype == 0)
-	{
-	  e_B[(long long) p + noff[p + 1]].x = h;	// live Hsml for the gravity softening, forcetree.c:2046-2054
-	  double dfac = dhsmlrho, curl = 0, dv = divv;
-	  if(rho > 0)
-	    {
-	      dfac *= h / (3 * rho);
-	      dfac = (dfac > -0.9) ? 1 / (1 + dfac) : 1;
-	      curl = sqrt(rot0 * rot0 + rot1 * rot1 + rot2 * rot2) / rho;
-	      dv = divv / rho;
-	    }
-	  const int tb = in_timebin[pin];
-	  const int dt_step = tb ? (1 << tb) : 0;
-	  const double dt_entr = (par.ti_current - (in_tibegstep[pin] + dt_step / 2)) * par.timebase_interval;
-	  out.density[pin] = rho;
-	  out.dhsml[pin] = dfac;
-	  out.divvel[pin] = dv;
-	  out.curlvel[pin] = curl;
-	  out.pressure[pin] = (in_entropy[pin] + in_dtentropy[pin] * dt_entr) * pow(rho, GL_GAMMA);
-	}
-      else
-	{			// density.c:520-546 sink (Type 5) / dust (Type 2) post-processing
-	  double se = sentr, g0 = gv0, g1 = gv1, g2 = gv2;
-	  if(rho > 0)
-	    {
-	      se /= rho; g0 /= rho; g1 /= rho; g2 /= rho;
-	    }
-	  out.sinkrho[pin] = rho;
-	  out.sinkentr[pin] = se;
-	  out.sinkvel[3ll * pin] = g0;
-	  out.sinkvel[3ll * pin + 1] = g1;
-	  out.sinkvel[3ll * pin + 2] = g2;
-	}
+      // load-balance diagnostics (the analogue of the reference's work-load balance line, gravtree.c:812)
+      const unsigned long long cyc = (unsigned long long) (clock64() - clk0);
+      atomicMax(&counter[1], (unsigned long long) maxit);
+      atomicMax(&counter[3], cyc);
+      atomicAdd(&counter[4], cyc);
+      atomicMax(&counter[5], (unsigned long long) staged);
+      atomicAdd(&counter[6], (unsigned long long) staged);
+      atomicMax(&counter[7], (unsigned long long) visits);
     }
-  const unsigned maxit = __reduce_max_sync(0xffffffffu, (unsigned) iter);
-  if(lane == 0) atomicMax(&counter[1], (unsigned long long) maxit);
 }
 
 __global__ void k_gather_d(long long n, const int *__restrict__ perm, const double *__restrict__ in, double *__restrict__ out)
 {
   long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(i < n) out[i] = in[perm[i]];
+}
+
+// ---------------------------------------------------------------- fat targets ----
+// A target with thousands of neighbours (e.g. the central sink, whose 160 kernel-weighted neighbours
+// sit at the rim of a ~22k-particle sphere) is a long serial tail for one warp.  It is handed to this
+// path instead: (1) ALL SMs brute-force the gas particles once and append those inside a guard radius
+// Rc to a compact candidate list, (2) one 1024-thread block per target runs the reference's Hsml
+// iteration over that list.  If Hsml leaves the guard radius the host enlarges Rc and repeats.
+struct FatTarget
+{
+  double x, y, z, rc;
+};
+
+__global__ void k_fat_scan(long long n, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
+			   const int *__restrict__ s_type, const double *__restrict__ s_entropy, int nf,
+			   const FatTarget *__restrict__ ft, int *__restrict__ cnt, const int *__restrict__ off,
+			   double4 *__restrict__ rec)
+{
+  __shared__ FatTarget sh[8];
+  if(threadIdx.x < nf) sh[threadIdx.x] = ft[threadIdx.x];
+  __syncthreads();
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  if(s_type[i] != 0) return;
+  const double4 pm = s_pm[i];
+  if(pm.w == 0) return;
+  for(int f = 0; f < nf; f++)
+    {
+      const double dx = sh[f].x - pm.x, dy = sh[f].y - pm.y, dz = sh[f].z - pm.z;
+      if(dx * dx + dy * dy + dz * dz < sh[f].rc * sh[f].rc)
+	{
+	  const int k = atomicAdd(&cnt[f], 1);
+	  if(rec)
+	    {
+	      const double4 vh = s_vh[i];
+	      rec[2ll * (off[f] + k)] = pm;
+	      rec[2ll * (off[f] + k) + 1] = make_double4(vh.x, vh.y, vh.z, s_entropy[i]);
+	    }
+	}
+    }
+}
+
+#define FAT_THREADS 1024
+__global__ void __launch_bounds__(FAT_THREADS)
+k_fat_rounds(int nf, const int *__restrict__ fat_p, double4 *__restrict__ fat_state, int *__restrict__ fat_flag,
+	     const FatTarget *__restrict__ ft, const int *__restrict__ cnt, const int *__restrict__ off,
+	     const double4 *__restrict__ rec, const double4 *__restrict__ s_pm, double4 *__restrict__ s_vh,
+	     const int *__restrict__ s_type, const int *__restrict__ perm, double4 *__restrict__ e_B, DensIn in, DensOut out,
+	     unsigned long long *__restrict__ counter, gl_dparams par)
+{
+  __shared__ double red[FAT_THREADS / 32][8];
+  __shared__ int redn[FAT_THREADS / 32];
+  __shared__ double sh_h;
+  __shared__ int sh_go;
+  const int f = blockIdx.x;
+  if(f >= nf) return;
+  if(fat_flag[f] == 1) return;	// already converged in an earlier sweep
+  const int p = fat_p[f];
+  const int ptype = s_type[p], pin = perm[p];
+  const double4 pm = s_pm[p];
+  const double4 vh = s_vh[p];
+  const double px = pm.x, py = pm.y, pz = pm.z;
+  const double vx = (ptype == 0) ? vh.x : 0, vy = (ptype == 0) ? vh.y : 0, vz = (ptype == 0) ? vh.z : 0;
+  const double desnumngb = (ptype == 5) ? par.desnumngb * par.bhfac : par.desnumngb;
+  const double rc = ft[f].rc;
+  const int nrec = cnt[f];
+  const double4 *my = rec + 2ll * off[f];
+  double4 st = fat_state[f];
+  double h = st.x, left = st.y, right = st.z;
+  int iter = (int) st.w;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  while(true)
+    {
+      const double h2 = h * h, hinv = 1.0 / h, hinv3 = hinv * hinv * hinv, hinv4 = hinv3 * hinv;
+      DensAcc P;
+      P.zero();
+      for(int k = threadIdx.x; k < nrec; k += FAT_THREADS)
+	{
+	  const double4 a = my[2ll * k];
+	  const double dx = px - a.x, dy = py - a.y, dz = pz - a.z;
+	  const double r2 = dx * dx + dy * dy + dz * dz;
+	  if(r2 < h2)
+	    {
+	      const double4 b = my[2ll * k + 1];
+	      density_pair(P, ptype, dx, dy, dz, r2, a.w, hinv, hinv3, hinv4, vx, vy, vz, b, b.w);
+	    }
+	}
+      double v[8] = { P.rho, P.wngb, P.dhsmlrho, (ptype != 0) ? P.gv0 : P.divv, (ptype != 0) ? P.gv1 : P.rot0,
+	(ptype != 0) ? P.gv2 : P.rot1, (ptype != 0) ? P.sentr : P.rot2, 0.0 };
+      for(int q = 0; q < 7; q++) v[q] = warp_sum_d(v[q]);
+      const int cn = __reduce_add_sync(FULL, P.numngb);
+      if(lane == 0)
+	{
+	  for(int q = 0; q < 7; q++) red[w][q] = v[q];
+	  redn[w] = cn;
+	}
+      __syncthreads();
+      if(threadIdx.x == 0)
+	{
+	  DensAcc A;
+	  A.zero();
+	  for(int ww = 0; ww < FAT_THREADS / 32; ww++)
+	    {
+	      A.rho += red[ww][0]; A.wngb += red[ww][1]; A.dhsmlrho += red[ww][2];
+	      if(ptype != 0)
+		{
+		  A.gv0 += red[ww][3]; A.gv1 += red[ww][4]; A.gv2 += red[ww][5]; A.sentr += red[ww][6];
+		}
+	      else
+		{
+		  A.divv += red[ww][3]; A.rot0 += red[ww][4]; A.rot1 += red[ww][5]; A.rot2 += red[ww][6];
+		}
+	      A.numngb += redn[ww];
+	    }
+	  const double h_eval = h;
+	  const bool redo = hsml_step(A.wngb, A.rho, A.dhsmlrho, ptype, desnumngb, par, h, left, right, counter);
+	  iter++;
+	  int go = 1;
+	  if(!redo)
+	    {
+	      density_store(A, h_eval, p, pin, ptype, out, in, s_vh, e_B, par);
+	      fat_flag[f] = 1;
+	      go = 0;
+	    }
+	  else if(iter > GL_MAXITER)
+	    {
+	      atomicMax(&counter[2], 1155ull);
+	      fat_flag[f] = 1;
+	      go = 0;
+	    }
+	  else if(h * BOX_SLACK >= rc)
+	    {
+	      fat_flag[f] = 2;	// Hsml left the guard radius: the host rebuilds the candidate list
+	      go = 0;
+	    }
+	  fat_state[f] = make_double4(h, left, right, (double) iter);
+	  atomicMax(&counter[1], (unsigned long long) iter);
+	  sh_h = h;
+	  sh_go = go;
+	}
+      __syncthreads();
+      h = sh_h;
+      if(!sh_go) break;
+    }
+}
+
+static int density_fat_path(gl_ctx *c, int nfat, const DensIn &in, const DensOut &out, const double *s_entropy,
+			    const gl_dparams &dp)
+{
+  long long n = c->n;
+  std::vector<int> hp(nfat), hflag(nfat, 0);
+  std::vector<double4> hst(nfat);
+  GL_CUDA(c, cudaMemcpyAsync(hp.data(), c->fat_p.p, nfat * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaMemcpyAsync(hst.data(), c->fat_state.p, nfat * sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<double4> hpos(nfat);
+  for(int f = 0; f < nfat; f++)
+    GL_CUDA(c, cudaMemcpyAsync(&hpos[f], c->s_pm.p + hp[f], sizeof(double4), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, c->fat_tgt.ensure(8 * 4));
+  GL_CUDA(c, c->fat_i.ensure(64));
+  for(int b0 = 0; b0 < nfat; b0 += 8)
+    {
+      const int nb = std::min(8, nfat - b0);
+      std::vector<double> guard(nb, 1.3);
+      for(int sweep = 0; sweep < 64; sweep++)
+	{
+	  FatTarget ht[8];
+	  bool any = false;
+	  for(int f = 0; f < nb; f++)
+	    {
+	      const double hh = std::max(hst[b0 + f].x, std::max(hst[b0 + f].y, hst[b0 + f].z));
+	      ht[f] = FatTarget{hpos[b0 + f].x, hpos[b0 + f].y, hpos[b0 + f].z, hflag[b0 + f] == 1 ? 0.0 : guard[f] * hh};
+	      any = any || hflag[b0 + f] != 1;
+	    }
+	  if(!any) break;
+	  int hz[24] = { 0 };
+	  GL_CUDA(c, cudaMemcpyAsync(c->fat_tgt.p, ht, sizeof(FatTarget) * nb, cudaMemcpyHostToDevice, c->stream));
+	  GL_CUDA(c, cudaMemcpyAsync(c->fat_i.p, hz, sizeof(hz), cudaMemcpyHostToDevice, c->stream));
+	  int *cnt = c->fat_i.p, *off = c->fat_i.p + 8, *flag = c->fat_i.p + 16;
+	  k_fat_scan<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->s_pm.p, c->s_vh.p, c->s_type.p, s_entropy, nb,
+							    (const FatTarget *) c->fat_tgt.p, cnt, off, nullptr);
+	  GL_LAUNCH_COUNT(c);
+	  int hc[8];
+	  GL_CUDA(c, cudaMemcpyAsync(hc, cnt, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
+	  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+	  int ho[8], tot = 0;
+	  for(int f = 0; f < nb; f++)
+	    {
+	      ho[f] = tot;
+	      tot += hc[f];
+	    }
+	  GL_CUDA(c, c->fat_rec.ensure(2 * (size_t) tot + 2));
+	  int hfl[8];
+	  for(int f = 0; f < nb; f++) hfl[f] = hflag[b0 + f] == 1 ? 1 : 0;
+	  GL_CUDA(c, cudaMemsetAsync(cnt, 0, 8 * sizeof(int), c->stream));
+	  GL_CUDA(c, cudaMemcpyAsync(off, ho, sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
+	  GL_CUDA(c, cudaMemcpyAsync(flag, hfl, sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
+	  k_fat_scan<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->s_pm.p, c->s_vh.p, c->s_type.p, s_entropy, nb,
+							    (const FatTarget *) c->fat_tgt.p, cnt, off, c->fat_rec.p);
+	  GL_LAUNCH_COUNT(c);
+	  k_fat_rounds<<<nb, FAT_THREADS, 0, c->stream>>>(nb, c->fat_p.p + b0, c->fat_state.p + b0, flag,
+							  (const FatTarget *) c->fat_tgt.p, cnt, off, c->fat_rec.p, c->s_pm.p,
+							  c->s_vh.p, c->s_type.p, c->perm.p, c->e_B.p, in, out, c->d_counter.p, dp);
+	  GL_LAUNCH_COUNT(c);
+	  GL_CUDA(c, cudaMemcpyAsync(hfl, flag, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
+	  GL_CUDA(c, cudaMemcpyAsync(&hst[b0], c->fat_state.p + b0, sizeof(double4) * nb, cudaMemcpyDeviceToHost, c->stream));
+	  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+	  GL_CUDA(c, cudaGetLastError());
+	  for(int f = 0; f < nb; f++)
+	    {
+	      if(hfl[f] == 2) guard[f] = 1.6;	// Hsml ran out of the guard sphere: take a wider one around the new value
+	      hflag[b0 + f] = hfl[f] == 1 ? 1 : 0;
+	    }
+	}
+      for(int f = 0; f < nb; f++)
+	if(hflag[b0 + f] != 1) return c->fail("density: fat-target path did not converge");
+    }
+  return 0;
 }
 
 int gls_density(gl_ctx *c)
@@ -291,28 +840,47 @@ int gls_density(gl_ctx *c)
   GL_CUDA(c, c->o_sinkrho.ensure(n));
   GL_CUDA(c, c->o_sinkentr.ensure(n));
   GL_CUDA(c, c->o_sinkvel.ensure(3 * n));
-  GL_CUDA(c, c->o_denspairs.ensure(n));
-  GL_CUDA(c, c->d_counter.ensure(8));
-  GL_CUDA(c, c->h_q.ensure(n + 1));	// scratch: sorted entropy lives in h_r until hydro overwrites it
-  GL_CUDA(c, c->h_r.ensure(n + 1));
+  if(c->o_denspairs.cap < (size_t) n)
+    {
+      GL_CUDA(c, c->o_denspairs.ensure(n));
+      GL_CUDA(c, cudaMemsetAsync(c->o_denspairs.p, 0, c->o_denspairs.cap * sizeof(int), c->stream));	// no history: nobody is fat yet
+    }
+  GL_CUDA(c, c->d_counter.ensure(16));
+  GL_CUDA(c, c->h_q.ensure(n + 1));
+  GL_CUDA(c, c->h_r.ensure(n + 1));	// scratch: the tree-ordered entropy lives here until hydro overwrites it
   double *s_entropy = (double *) c->h_r.p;
-  GL_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 8 * sizeof(unsigned long long), c->stream));
+  GL_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16 * sizeof(unsigned long long), c->stream));
   cudaEventRecord(c->ev[0], c->stream);
   k_gather_d<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->perm.p, c->in_entropy.p, s_entropy);
   GL_LAUNCH_COUNT(c);
   DensOut out{c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p, c->o_pressure.p,
 	      c->o_sinkrho.p, c->o_sinkentr.p, c->o_sinkvel.p, c->o_denspairs.p};
+  DensIn in{c->noff.p, c->in_entropy.p, c->in_dtentropy.p, c->in_timebin.p, c->in_tibegstep.p};
   gl_dparams dp = gl_make_dparams(c);
+  GL_CUDA(c, c->fat_p.ensure(FAT_MAX));
+  GL_CUDA(c, c->fat_state.ensure(FAT_MAX));
   if(nt > 0)
     {
-      k_density<<<gl_grid(nt, GL_BLOCK), GL_BLOCK, 0, c->stream>>>(c->tgt_sph.p, nt, (int) c->nentries, c->e_next.p, c->e_B.p,
-								  c->s_pm.p, c->s_vh.p, c->s_type.p, s_entropy, c->noff.p,
-								  c->perm.p, c->in_entropy.p, c->in_dtentropy.p,
-								  c->in_timebin.p, c->in_tibegstep.p, out, c->d_counter.p, dp);
+      static bool attr_done = false;
+      if(!attr_done)
+	{
+	  GL_CUDA(c, cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (SPH_WARPS * sizeof(WarpStage))));
+	  attr_done = true;
+	}
+      k_density<<<gl_grid(nt, SPH_BLOCK), SPH_BLOCK, SPH_WARPS * sizeof(WarpStage), c->stream>>>(
+	c->tgt_sph.p, nt, (int) c->nentries, c->e_next.p, c->e_B.p, c->e_rng.p, c->n_child.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
+	s_entropy, c->perm.p, in, out, c->fat_p.p, c->fat_state.p, c->d_counter.p, dp);
       GL_LAUNCH_COUNT(c);
+      unsigned long long nfat = 0;
+      GL_CUDA(c, cudaMemcpyAsync(&nfat, c->d_counter.p + 8, sizeof(nfat), cudaMemcpyDeviceToHost, c->stream));
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      GL_CUDA(c, cudaGetLastError());
+      if(nfat > 0)
+	if(density_fat_path(c, (int) std::min<unsigned long long>(nfat, FAT_MAX), in, out, s_entropy, dp)) return 1;
+      c->st.density_fat_targets = (long long) nfat;
     }
   cudaEventRecord(c->ev[1], c->stream);
-  unsigned long long cnt[4];
+  unsigned long long cnt[8];
   GL_CUDA(c, cudaMemcpyAsync(cnt, c->d_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   GL_CUDA(c, cudaGetLastError());
@@ -321,6 +889,9 @@ int gls_density(gl_ctx *c)
   c->st.ms_density = ms;
   c->st.density_targets = nt;
   c->st.density_passes_max = (long long) cnt[1];
+  if(getenv("GL_DEBUG_SPH"))
+    fprintf(stderr, "[gl] density: %lld warps, cycles max %.3g avg %.3g | staged max %llu avg %.1f | entry visits max %llu | rounds max %llu | %.2f ms\n",
+	    (nt + 31) / 32, (double) cnt[3], (double) cnt[4] / ((nt + 31) / 32), cnt[5], (double) cnt[6] / ((nt + 31) / 32), cnt[7], cnt[1], ms);
   if(cnt[2] == 1155) return c->fail("density: failed to converge in neighbour iteration (endrun(1155), density.c:669)");
   if(cnt[2] == 8188) return c->fail("density: Left == Right == 0 (endrun(8188), density.c:608)");
   return 0;
@@ -354,145 +925,202 @@ __global__ void k_hydro_prep(long long n, const int *__restrict__ perm, const in
   h_r[i] = make_double2(f, (double) (tb ? (1 << tb) : 0));
 }
 
-__global__ void __launch_bounds__(GL_BLOCK)
-k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
-	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const double4 *__restrict__ s_pm,
-	const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q, const double2 *__restrict__ h_r,
-	const int *__restrict__ perm, const double *__restrict__ pressure, const double *__restrict__ dhsml,
-	const double *__restrict__ divvel, const double *__restrict__ curlvel, double *__restrict__ o_hacc,
-	double *__restrict__ o_dtentr, double *__restrict__ o_maxsig, int *__restrict__ o_pairs, gl_dparams par)
+struct HydroAcc
 {
+  double a0, a1, a2, dtE, maxsig;
+  int npairs;
+  __device__ void zero() { a0 = a1 = a2 = dtE = maxsig = 0; npairs = 0; }
+};
+
+struct HydroTarget
+{
+  double px, py, pz, vx, vy, vz, h_i, mass, rho, f1, cs_i, p_over_rho2_i;
+  int timestep;
+};
+
+__device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, unsigned live_mask, int lane, const HydroTarget &T,
+					    HydroAcc &A, const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
+					    const double2 *__restrict__ h_r, double artvisc, double timebase_interval)
+{
+  __syncwarp();
+  for(unsigned rest = live_mask; rest; rest &= rest - 1)
+    {
+      const int t = __ffs(rest) - 1;
+#define BC(v) __shfl_sync(FULL, (v), t)
+      const double tx = BC(T.px), ty = BC(T.py), tz = BC(T.pz), tvx = BC(T.vx), tvy = BC(T.vy), tvz = BC(T.vz);
+      const double h_i = BC(T.h_i), mass = BC(T.mass), rho = BC(T.rho), f1 = BC(T.f1), cs_i = BC(T.cs_i);
+      const double p_over_rho2_i = BC(T.p_over_rho2_i);
+      const int timestep = BC(T.timestep);
+#undef BC
+      const double h_i2 = h_i * h_i;
+      HydroAcc P;
+      P.zero();
+      int nh = 0;
+      for(int base = 0;; base += 32)
+	{
+	  if(base < ncand)
+	    {
+	      const int c = base + lane;
+	      bool hit = false;
+	      if(c < ncand)
+		{
+		  // hydra.c:1250-1266: r2 < h_i^2 || r2 < h_j^2
+		  const double dx = tx - S.x[c], dy = ty - S.y[c], dz = tz - S.z[c];
+		  const double r2 = dx * dx + dy * dy + dz * dz;
+		  const double h_j = S.h[c];
+		  hit = (r2 < h_i2 || r2 < h_j * h_j);
+		}
+	      const unsigned ball = __ballot_sync(FULL, hit);
+	      if(hit) S.hit[nh + __popc(ball & ((1u << lane) - 1))] = c;
+	      nh += __popc(ball);
+	      __syncwarp();
+	      if(nh < 32 && base + 32 < ncand) continue;
+	    }
+	  if(nh == 0) break;
+	  const int take = nh < 32 ? nh : 32;
+	  if(lane < take)
+	    {
+	      const int c = S.hit[lane];
+	      const int j = S.j[c];
+	      const double dx = tx - S.x[c], dy = ty - S.y[c], dz = tz - S.z[c];
+	      const double r2 = dx * dx + dy * dy + dz * dz;
+	      const double h_j = S.h[c];
+	      const double mass_j = S.m[c];
+	      const double r = sqrt(r2);
+	      if(r > 0)
+		{
+		  const double4 vj = gl_ld4(&s_vh[j]);
+		  const double4 q = gl_ld4(&h_q[j]);
+		  const double2 rr = __ldg(&h_r[j]);
+		  P.npairs++;
+		  const double rho_j = q.x;
+		  const double soundspeed_j = q.w;
+		  const double dvx = tvx - vj.x, dvy = tvy - vj.y, dvz = tvz - vj.z;
+		  const double vdotr = dx * dvx + dy * dvy + dz * dvz;
+		  const double vdotr2 = vdotr;	// non-comoving, hydra.c:1279-1282
+		  double dwk_i = 0, dwk_j = 0;
+		  if(r2 < h_i2)
+		    {
+		      const double hinv = 1.0 / h_i;
+		      const double hinv4 = hinv * hinv * hinv * hinv;
+		      const double u = r * hinv;
+		      if(u < 0.5)
+			dwk_i = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
+		      else
+			dwk_i = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+		    }
+		  if(r2 < h_j * h_j)
+		    {
+		      const double hinv = 1.0 / h_j;
+		      const double hinv4 = hinv * hinv * hinv * hinv;
+		      const double u = r * hinv;
+		      if(u < 0.5)
+			dwk_j = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
+		      else
+			dwk_j = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+		    }
+		  double vsig = cs_i + soundspeed_j;	// hydra.c:1502
+		  if(vsig > P.maxsig) P.maxsig = vsig;
+		  double visc = 0;
+		  if(vdotr2 < 0)
+		    {
+		      const double mu_ij = 1.0 * vdotr2 / r;	// fac_mu = 1
+		      vsig -= 3 * mu_ij;
+		      if(vsig > P.maxsig) P.maxsig = vsig;
+		      const double rho_ij = 0.5 * (rho + rho_j);
+		      const double f2 = rr.x;
+		      visc = 0.25 * artvisc * vsig * (-mu_ij) / rho_ij * (f1 + f2);
+		      // hydra.c:1583-1597 viscosity limiter
+		      const int ts_j = (int) rr.y;
+		      const double dt = 2 * ((timestep > ts_j) ? timestep : ts_j) * timebase_interval;
+		      if(dt > 0 && (dwk_i + dwk_j) < 0)
+			{
+			  const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (mass + mass_j) * (dwk_i + dwk_j) * r * dt);
+			  visc = (visc < lim) ? visc : lim;
+			}
+		    }
+		  const double p_over_rho2_j = q.z;	// already x DhsmlDensityFactor_j (hydra.c:1600)
+		  const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) / r;
+		  const double hfc = hfc_visc + mass_j * (p_over_rho2_i * dwk_i + p_over_rho2_j * dwk_j) / r;
+		  P.a0 += (-hfc * dx);
+		  P.a1 += (-hfc * dy);
+		  P.a2 += (-hfc * dz);
+		  P.dtE += (0.5 * hfc_visc * vdotr2);
+		}
+	    }
+	  hits_shift(S, nh, lane);
+	  nh -= take;
+	  if(base + 32 >= ncand && nh == 0) break;
+	}
+      const int tot = __reduce_add_sync(FULL, P.npairs);
+      if(tot == 0) continue;
+      const double r0 = warp_sum_d(P.a0), r1 = warp_sum_d(P.a1), r2s = warp_sum_d(P.a2), r3 = warp_sum_d(P.dtE);
+      const double r4 = warp_max_d(P.maxsig);
+      if(lane == t)
+	{
+	  A.a0 += r0; A.a1 += r1; A.a2 += r2s; A.dtE += r3;
+	  if(r4 > A.maxsig) A.maxsig = r4;
+	  A.npairs += tot;
+	}
+    }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
+	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const int2 *__restrict__ e_rng,
+	const int *__restrict__ n_child, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
+	const double4 *__restrict__ h_q, const double2 *__restrict__ h_r, const int *__restrict__ perm,
+	const double *__restrict__ pressure, const double *__restrict__ dhsml, const double *__restrict__ divvel,
+	const double *__restrict__ curlvel, double *__restrict__ o_hacc, double *__restrict__ o_dtentr,
+	double *__restrict__ o_maxsig, int *__restrict__ o_pairs, gl_dparams par)
+{
+  extern __shared__ __align__(16) unsigned char gl_smem_raw[];
+  WarpStage *stage = reinterpret_cast<WarpStage *>(gl_smem_raw);
+  WarpStage &S = stage[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long) blockDim.x + threadIdx.x) >> 5;
   const long long t = warp * 32 + lane;
   const bool live = t < nt;
   int p = 0, pin = 0;
-  double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, h_i = 0, mass = 0, rho = 1, f1 = 0, cs_i = 0, p_over_rho2_i = 0;
-  int timestep = 0;
+  HydroTarget T;
+  T.px = T.py = T.pz = T.vx = T.vy = T.vz = T.h_i = T.mass = T.f1 = T.cs_i = T.p_over_rho2_i = 0;
+  T.rho = 1;
+  T.timestep = 0;
   if(live)
     {
       // hydra.c:958-979 target load
       p = tgt[t];
       pin = perm[p];
       const double4 pm = s_pm[p], vh = s_vh[p];
-      px = pm.x; py = pm.y; pz = pm.z; mass = pm.w;
-      vx = vh.x; vy = vh.y; vz = vh.z; h_i = vh.w;
-      rho = h_q[p].x;
+      T.px = pm.x; T.py = pm.y; T.pz = pm.z; T.mass = pm.w;
+      T.vx = vh.x; T.vy = vh.y; T.vz = vh.z; T.h_i = vh.w;
+      T.rho = h_q[p].x;
       const double P = pressure[pin];
-      timestep = (int) h_r[p].y;
-      cs_i = sqrt(GL_GAMMA * P / rho);
+      T.timestep = (int) h_r[p].y;
+      T.cs_i = sqrt(GL_GAMMA * P / T.rho);
       const double adv = fabs(divvel[pin]);
-      f1 = adv / (adv + curlvel[pin] + 0.0001 * cs_i / h_i / 1.0);
-      p_over_rho2_i = P / (rho * rho);	// hydra.c:1154-1155
-      p_over_rho2_i *= dhsml[pin];
+      T.f1 = adv / (adv + curlvel[pin] + 0.0001 * T.cs_i / T.h_i / 1.0);
+      T.p_over_rho2_i = P / (T.rho * T.rho);	// hydra.c:1154-1155
+      T.p_over_rho2_i *= dhsml[pin];
     }
-  const double h_i2 = h_i * h_i;
-  const double bxlo = warp_min_d(live ? px : 1e300), bxhi = warp_max_d(live ? px : -1e300);
-  const double bylo = warp_min_d(live ? py : 1e300), byhi = warp_max_d(live ? py : -1e300);
-  const double bzlo = warp_min_d(live ? pz : 1e300), bzhi = warp_max_d(live ? pz : -1e300);
-  const double hgrp = warp_max_d(live ? h_i : 0.0);
-  double a0 = 0, a1 = 0, a2 = 0, dtE = 0, maxsig = 0;
-  int npairs = 0;
-  int e = 0;
-  while(e < nentries)
-    {
-      const int nx = __ldg(&e_next[e]);
-      if(nx >= 0)
-	{
-	  // ngb.c:136-152: search radius max(hmax_node, h_i); here max over the warp's targets
-	  const double4 B = gl_ld4(&e_B[e]);
-	  const double reach = fmax(__ldg(&e_hmax[e]), hgrp) * BOX_SLACK + 0.5 * B.w;
-	  const bool out_of_box = (B.x + reach < bxlo) || (B.x - reach > bxhi) || (B.y + reach < bylo) ||
-	    (B.y - reach > byhi) || (B.z + reach < bzlo) || (B.z - reach > bzhi);
-	  e = out_of_box ? nx : e + 1;
-	  continue;
-	}
-      const int code = -1 - nx;
-      e++;
-      if((code & 7) != 0) continue;	// ngb.c:54
-      const int j = code >> 3;
-      const double4 pj = gl_ld4(&s_pm[j]);
-      if(pj.w == 0) continue;	// hydra.c:1236
-      const double4 vj = gl_ld4(&s_vh[j]);
-      const double dx = px - pj.x, dy = py - pj.y, dz = pz - pj.z;
-      const double r2 = dx * dx + dy * dy + dz * dz;
-      const double h_j = vj.w;
-      const bool hit = live && (r2 < h_i2 || r2 < h_j * h_j);	// hydra.c:1266
-      if(!__any_sync(0xffffffffu, hit)) continue;
-      const double4 q = gl_ld4(&h_q[j]);
-      const double2 rr = __ldg(&h_r[j]);
-      if(hit)
-	{
-	  const double r = sqrt(r2);
-	  if(r > 0)
-	    {
-	      npairs++;
-	      const double rho_j = q.x;
-	      double p_over_rho2_j = q.y;
-	      const double soundspeed_j = q.w;
-	      const double dvx = vx - vj.x, dvy = vy - vj.y, dvz = vz - vj.z;
-	      const double vdotr = dx * dvx + dy * dvy + dz * dvz;
-	      const double vdotr2 = vdotr;	// non-comoving, hydra.c:1279-1282
-	      double dwk_i = 0, dwk_j = 0;
-	      if(r2 < h_i2)
-		{
-		  const double hinv = 1.0 / h_i;
-		  const double hinv4 = hinv * hinv * hinv * hinv;
-		  const double u = r * hinv;
-		  if(u < 0.5)
-		    dwk_i = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
-		  else
-		    dwk_i = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-		}
-	      if(r2 < h_j * h_j)
-		{
-		  const double hinv = 1.0 / h_j;
-		  const double hinv4 = hinv * hinv * hinv * hinv;
-		  const double u = r * hinv;
-		  if(u < 0.5)
-		    dwk_j = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
-		  else
-		    dwk_j = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-		}
-	      double vsig = cs_i + soundspeed_j;	// hydra.c:1502
-	      if(vsig > maxsig) maxsig = vsig;
-	      double visc = 0;
-	      if(vdotr2 < 0)
-		{
-		  const double mu_ij = 1.0 * vdotr2 / r;	// fac_mu = 1
-		  vsig -= 3 * mu_ij;
-		  if(vsig > maxsig) maxsig = vsig;
-		  const double rho_ij = 0.5 * (rho + rho_j);
-		  const double f2 = rr.x;
-		  visc = 0.25 * par.artvisc * vsig * (-mu_ij) / rho_ij * (f1 + f2);
-		  // hydra.c:1583-1597 viscosity limiter
-		  const int ts_j = (int) rr.y;
-		  const double dt = 2 * ((timestep > ts_j) ? timestep : ts_j) * par.timebase_interval;
-		  if(dt > 0 && (dwk_i + dwk_j) < 0)
-		    {
-		      const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (mass + pj.w) * (dwk_i + dwk_j) * r * dt);
-		      visc = (visc < lim) ? visc : lim;
-		    }
-		}
-	      p_over_rho2_j = q.z;	// already x DhsmlDensityFactor_j
-	      const double hfc_visc = 0.5 * pj.w * visc * (dwk_i + dwk_j) / r;
-	      const double hfc = hfc_visc + pj.w * (p_over_rho2_i * dwk_i + p_over_rho2_j * dwk_j) / r;
-	      a0 += (-hfc * dx);
-	      a1 += (-hfc * dy);
-	      a2 += (-hfc * dz);
-	      dtE += (0.5 * hfc_visc * vdotr2);
-	    }
-	}
-    }
+  const unsigned live_mask = __ballot_sync(FULL, live);
+  HydroAcc A;
+  A.zero();
+  unsigned visits = 0, staged = 0;
+  sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, T.px, T.py, T.pz, T.h_i,
+		    visits, staged, [&](int ncand) {
+		      hydro_chunk(S, ncand, live_mask, lane, T, A, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
+		    });
   if(live)
     {
-      o_hacc[3ll * pin] = a0;
-      o_hacc[3ll * pin + 1] = a1;
-      o_hacc[3ll * pin + 2] = a2;
+      o_hacc[3ll * pin] = A.a0;
+      o_hacc[3ll * pin + 1] = A.a1;
+      o_hacc[3ll * pin + 2] = A.a2;
       // hydra.c:583: DtEntropy *= GAMMA_MINUS1 / (hubble_a2 * rho^GAMMA_MINUS1)
-      o_dtentr[pin] = dtE * (GL_GAMMA_MINUS1 / (1.0 * pow(rho, GL_GAMMA_MINUS1)));
-      o_maxsig[pin] = maxsig;
-      o_pairs[pin] = npairs;
+      o_dtentr[pin] = A.dtE * (GL_GAMMA_MINUS1 / (1.0 * pow(T.rho, GL_GAMMA_MINUS1)));
+      o_maxsig[pin] = A.maxsig;
+      o_pairs[pin] = A.npairs;
     }
 }
 
@@ -517,10 +1145,17 @@ int gls_hydro(gl_ctx *c)
   GL_LAUNCH_COUNT(c);
   if(nt > 0)
     {
-      k_hydro<<<gl_grid(nt, GL_BLOCK), GL_BLOCK, 0, c->stream>>>(c->tgt_gas.p, nt, (int) c->nentries, c->e_next.p, c->e_B.p,
-								c->e_hmax.p, c->s_pm.p, c->s_vh.p, c->h_q.p, c->h_r.p, c->perm.p,
-								c->o_pressure.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p,
-								c->o_hacc.p, c->o_dtentr.p, c->o_maxsig.p, c->o_hydropairs.p, dp);
+      static bool attr_done = false;
+      if(!attr_done)
+	{
+	  GL_CUDA(c, cudaFuncSetAttribute(k_hydro, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (SPH_WARPS * sizeof(WarpStage))));
+	  attr_done = true;
+	}
+      k_hydro<<<gl_grid(nt, SPH_BLOCK), SPH_BLOCK, SPH_WARPS * sizeof(WarpStage), c->stream>>>(c->tgt_gas.p, nt, (int) c->nentries, c->e_next.p, c->e_B.p,
+								  c->e_hmax.p, c->e_rng.p, c->n_child.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
+								  c->h_q.p, c->h_r.p, c->perm.p, c->o_pressure.p, c->o_dhsml.p,
+								  c->o_divvel.p, c->o_curlvel.p, c->o_hacc.p, c->o_dtentr.p,
+								  c->o_maxsig.p, c->o_hydropairs.p, dp);
       GL_LAUNCH_COUNT(c);
     }
   cudaEventRecord(c->ev[1], c->stream);

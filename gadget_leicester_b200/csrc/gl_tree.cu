@@ -19,6 +19,7 @@
 // key order - the same FP64 operation order as the reference, hence bit-identical mass/s.
 #include "gl_internal.h"
 #include <cub/cub.cuh>
+#include <climits>
 
 __device__ __forceinline__ int common_level(unsigned long long a, unsigned long long b)
 {
@@ -127,11 +128,15 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
 			  const int *__restrict__ n_first, int *__restrict__ n_end, int *__restrict__ n_parent,
 			  int *__restrict__ p_father, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
 			  const int *__restrict__ s_type, double4 *__restrict__ n_sm, double4 *__restrict__ n_cl,
-			  double4 *__restrict__ n_aux, gl_domain dom, gl_dparams par)
+			  double4 *__restrict__ n_aux, int *__restrict__ n_child, gl_domain dom, gl_dparams par)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if(t >= count) return;
   int id = lev_list[t];
+  // child table for the parallel SPH walks: DFS entry index of a child node, -(p+2) for a particle leaf p,
+  // -1 = no further child; a finest-level bucket (coincident keys) is flagged by n_child[0] = INT_MIN
+  int nch = 0;
+  int *child_tab = n_child + 8ll * id;
   int a = n_first[id];
   unsigned long long ka = key[a];
   int b;
@@ -185,6 +190,8 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
 	    maxsoft = par.soft[ty];
 	  vmax = fmax(vmax, fmax(fabs(vh.x), fmax(fabs(vh.y), fabs(vh.z))));
 	  p_father[p] = id;
+	  if(nch < 8) child_tab[nch] = -(p + 2);
+	  nch++;
 	}
       else
 	{
@@ -199,6 +206,8 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
 	  if(ca.z > vmax) vmax = ca.z;
 	  if(ca.x > maxsoft) maxsoft = ca.x;
 	  n_parent[child] = id;
+	  if(nch < 8) child_tab[nch] = p + child;	// DFS entry index of node (p, L+1): first particle + node id
+	  nch++;
 	}
       p = q;
     }
@@ -217,6 +226,8 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
   n_sm[id] = make_double4(s0, s1, s2, mass);
   n_cl[id] = make_double4(cx, cy, cz, len);
   n_aux[id] = make_double4(maxsoft, hmax, vmax, 0.0);
+  for(int k = nch; k < 8; k++) child_tab[k] = -1;
+  if(nch > 8) child_tab[0] = INT_MIN;
 }
 
 __global__ void k_entries_particles(long long n, const int *__restrict__ noff, const double4 *__restrict__ s_pm,
@@ -255,6 +266,15 @@ __global__ void k_entries_nodes(long long m, long long n, const int *__restrict_
   // mass * nop->len * nop->len, evaluated left to right as in forcetree.c:2085
   e_C[e] = make_double2(ax.x, __dmul_rn(__dmul_rn(sm.w, cl.w), cl.w));
   e_hmax[e] = ax.y;
+}
+
+// particle range [a,b) below every node entry: lets the SPH walks swallow a small cell in one coalesced step
+__global__ void k_entries_range(long long m, const int *__restrict__ n_first, const int *__restrict__ n_end,
+				int2 *__restrict__ e_rng)
+{
+  long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(id >= m) return;
+  e_rng[(long long) n_first[id] + id] = make_int2(n_first[id], n_end[id]);	// node id = entry index - first
 }
 
 static int scan_exclusive(gl_ctx *c, const int *in, int *out, long long n)
@@ -317,6 +337,7 @@ int glt_build(gl_ctx *c)
   GL_CUDA(c, c->n_sm.ensure(mm));
   GL_CUDA(c, c->n_cl.ensure(mm));
   GL_CUDA(c, c->n_aux.ensure(mm));
+  GL_CUDA(c, c->n_child.ensure(8 * mm));
   GL_CUDA(c, c->p_father.ensure(n + 1));
   int *levcount = c->scan_tmp_i.p;	// [0..21] counts, [32..53] cursors
   GL_CUDA(c, cudaMemsetAsync(levcount, 0, 64 * sizeof(int), c->stream));
@@ -352,7 +373,7 @@ int glt_build(gl_ctx *c)
 	k_moments<<<gl_grid(cnt, 128), 128, 0, c->stream>>>(L, c->lev_list.p + c->lev_start[L], cnt, key, n, c->lev_c.p,
 							   c->noff.p, c->n_first.p, c->n_end.p, c->n_parent.p,
 							   c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->n_sm.p,
-							   c->n_cl.p, c->n_aux.p, c->dom, dp);
+							   c->n_cl.p, c->n_aux.p, c->n_child.p, c->dom, dp);
 	GL_LAUNCH_COUNT(c);
       }
   size_t ne = (size_t) c->nentries + 1;
@@ -369,6 +390,9 @@ int glt_build(gl_ctx *c)
       k_entries_nodes<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, n, c->noff.p, c->n_first.p, c->n_end.p, c->n_sm.p,
 							       c->n_cl.p, c->n_aux.p, c->e_next.p, c->e_A.p, c->e_B.p,
 							       c->e_C.p, c->e_hmax.p);
+      GL_LAUNCH_COUNT(c);
+      GL_CUDA(c, c->e_rng.ensure(ne));
+      k_entries_range<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->n_first.p, c->n_end.p, c->e_rng.p);
       GL_LAUNCH_COUNT(c);
     }
   cudaEventRecord(c->ev[3], c->stream);

@@ -41,7 +41,7 @@ class GLStats(C.Structure):
         "ms_keys_sort", "ms_treebuild", "ms_moments", "ms_gravity_walk", "ms_density", "ms_hmax", "ms_hydro",
         "ms_h2d", "ms_d2h")] + [(k, C.c_longlong) for k in (
             "interactions", "density_targets", "density_passes_max", "hydro_targets", "numnodes", "numentries",
-            "kernel_launches")]
+            "density_fat_targets", "kernel_launches")]
 
 
 class GLGadgetLayout(C.Structure):

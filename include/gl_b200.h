@@ -128,6 +128,7 @@ typedef struct gl_stats
   long long interactions;	/* sum of P.GravCost over targets of the last gl_gravity_tree */
   long long density_targets, density_passes_max, hydro_targets;
   long long numnodes, numentries;
+  long long density_fat_targets;	/* targets handed to the block-per-target density path */
   long long kernel_launches;	/* kernels launched by this library since gl_create / last reset */
 } gl_stats;
 int gl_get_stats(gl_ctx * ctx, gl_stats * out);

@@ -120,7 +120,7 @@ def _check_sequence(FP, ps, par, R, label):
             e = util.rel_err_vec(d2[k][:ngas], R["dens2__" + k])
             scale = 1.0
             if k in ("DivVel", "CurlVel"):  # differences of nearly equal velocities: compare to the velocity scale / h
-                e = np.abs(d2[k][:ngas] - R["dens2__" + k]) / (np.abs(R["dens2__" + k]) + np.abs(ps["vel"][:ngas]).max() / R["dens2__Hsml"][:ngas])
+                e = np.abs(d2[k][:ngas] - R["dens2__" + k]) / (np.abs(R["dens2__" + k]) + np.abs(ps["vel"][:ngas]).max() / R["dens2__Hsml"][:ngas] + 1e-300)
             assert e.max() <= TOL_SPH * scale, label + ": " + util.summarize(k, e)
         e = util.rel_err_vec(d2["NumNgb"][sph], R["dens2__NumNgb"][sph])
         assert e.max() <= TOL_SPH
@@ -253,8 +253,12 @@ def test_ragged_warp_and_target_subset(FP, port_bin):
     assert (g["GravCost"][sub] == full_g["GravCost"][sub]).all()
     assert fp2.stats()["interactions"] == int(full_g["GravCost"][sub].sum())
     gas_sub = sub[ps["type"][sub] == 0]
-    assert (d["Density"][gas_sub] == full_d["Density"][gas_sub]).all()
-    assert (d["NumNgb"][sub] == full_d["NumNgb"][sub]).all()
+    # SPH sums are 32 partial sums + a shuffle butterfly whose grouping depends on the warp's composition:
+    # identical neighbour sets (pair counts), values equal to FP64 round-off
+    assert (d["DensPairs"][sub] == full_d["DensPairs"][sub]).all()
+    assert util.rel_err_vec(d["Density"][gas_sub], full_d["Density"][gas_sub]).max() <= 1e-13
+    sph_sub = sub[np.isin(ps["type"][sub], (0, 2, 5))]
+    assert util.rel_err_vec(d["NumNgb"][sph_sub], full_d["NumNgb"][sph_sub]).max() <= 1e-13
     fp.close()
     fp2.close()
 
