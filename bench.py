@@ -278,7 +278,7 @@ def main():
         dt = (time.perf_counter() - t0) / ksteps
         h2d, d2h = drop.bytes_per_step()
         e2e = dict(value=(ie / ksteps) / dt, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=dt * 1e3,
-                   steps=ksteps, api="gl_gadget_pull + gl_compute_accelerations + gl_gadget_push on pinned host P[]/SphP[]")
+                   steps=ksteps, api="gl_gadget_compute_accelerations on pinned host P[]/SphP[] (pack + H2D, force path, pipelined D2H + scatter)")
         fp.close()
 
     if rank != 0:

@@ -112,13 +112,12 @@ class GadgetDropIn:
     def bytes_per_step(self):
         n = self.a.NumPart
         h2d = n * (11 * 8 + 3 * 4)
-        d2h = n * ((3 + 1) * 8 + 4) + n * (10 + 3) * 8 + n * 5 * 8
+        other = 5 * 8 if n > self.a.N_gas else 0      # sink / dust columns only travel when such targets exist
+        d2h = n * ((3 + 1) * 8 + 4) + n * (7 * 8 + other) + n * 5 * 8
         return h2d, d2h
 
     def compute_accelerations(self, mode=0):
         fp, a = self.fp, self.a
         lib = fp._lib
-        fp._chk(lib.gl_gadget_pull(fp.ctx, L._ptr(a.P), L._ptr(a.SphP), a.NumPart, a.N_gas))
         fp.N = a.NumPart
-        fp._chk(lib.gl_compute_accelerations(fp.ctx, int(mode)))
-        fp._chk(lib.gl_gadget_push(fp.ctx, L._ptr(a.P), L._ptr(a.SphP), 7 if a.N_gas else 1))
+        fp._chk(lib.gl_gadget_compute_accelerations(fp.ctx, L._ptr(a.P), L._ptr(a.SphP), a.NumPart, a.N_gas, int(mode)))

@@ -51,6 +51,9 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->e_rng.release(); c->n_child.release(); c->fat_p.release(); c->fat_i.release(); c->fat_state.release();
   c->fat_rec.release(); c->fat_tgt.release();
   if(c->pin) cudaFreeHost(c->pin);
+  if(c->pin2) cudaFreeHost(c->pin2);
+  for(int k = 0; k < 2; k++)
+    if(c->copy_stream[k]) cudaStreamDestroy(c->copy_stream[k]);
   for(int i = 0; i < 16; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -433,6 +436,9 @@ static int ensure_pinned(gl_ctx *c, size_t bytes)
 {
   if(bytes <= c->pin_cap) return 0;
   if(c->pin) cudaFreeHost(c->pin);
+  if(c->pin2) cudaFreeHost(c->pin2);
+  for(int k = 0; k < 2; k++)
+    if(c->copy_stream[k]) cudaStreamDestroy(c->copy_stream[k]);
   c->pin = nullptr;
   c->pin_cap = 0;
   GL_CUDA(c, cudaMallocHost(&c->pin, bytes + bytes / 8));
@@ -510,89 +516,170 @@ extern "C" int gl_gadget_pull(gl_ctx *c, const void *Pv, const void *SphPv, long
   return gl_load_particles(c, n, pos, vel, mass, type, hsml, oldacc, timebin, tibeg, entropy, dtentropy, 0);
 }
 
+// ---- result scatter: D2H of compact SoA results on `st`, then a multi-threaded scatter into P[] / SphP[] ----
+static int push_gravity_on(gl_ctx *c, cudaStream_t st, double *stage, char *P)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n;
+  const gl_gadget_layout L = c->lay;
+  double *acc = stage, *old = acc + 3 * n;
+  float *cost = (float *) (old + n);
+  GL_CUDA(c, cudaMemcpyAsync(acc, c->o_acc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(c, cudaMemcpyAsync(old, c->o_oldacc.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(c, cudaMemcpyAsync(cost, c->o_gravcost.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(c, cudaStreamSynchronize(st));
+  parallel_for(n, [=](long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	char *pi = P + i * L.p_stride;
+	double *g = (double *) (pi + L.p_GravAccel);
+	g[0] = acc[3 * i]; g[1] = acc[3 * i + 1]; g[2] = acc[3 * i + 2];
+	*(double *) (pi + L.p_OldAcc) = old[i];
+	*(float *) (pi + L.p_GravCost) = cost[i];
+      }
+  });
+  return 0;
+}
+
+static int push_density_on(gl_ctx *c, cudaStream_t st, double *stage, char *P, char *S)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n, N_gas = c->g_ngas;
+  const gl_gadget_layout L = c->lay;
+  double *hs = stage, *nn = hs + n, *de = nn + n, *dh = de + n, *dv = dh + n, *cu = dv + n, *pr = cu + n, *sr = pr + n,
+    *se = sr + n, *sv = se + n;
+  const double *src[9] = { c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p,
+    c->o_pressure.p, c->o_sinkrho.p, c->o_sinkentr.p };
+  double *dst[9] = { hs, nn, de, dh, dv, cu, pr, sr, se };
+  const bool have_other = (n > N_gas);	// sink / dust fields only exist for non-gas targets
+  for(int k = 0; k < (have_other ? 9 : 7); k++)
+    GL_CUDA(c, cudaMemcpyAsync(dst[k], src[k], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if(have_other) GL_CUDA(c, cudaMemcpyAsync(sv, c->o_sinkvel.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(c, cudaStreamSynchronize(st));
+  parallel_for(n, [=](long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	char *pi = P + i * L.p_stride;
+	const int ty = *(const short *) (pi + L.p_Type);
+	if(!(ty == 0 || ty == 5 || ty == 2)) continue;
+	*(double *) (pi + L.p_Hsml) = hs[i];
+	*(double *) (pi + L.p_NumNgb) = nn[i];
+	*(unsigned int *) (pi + L.p_SwallowID) = 0;	// density.c:130
+	if(ty == 0 && i < N_gas)
+	  {
+	    char *si = S + i * L.sph_stride;
+	    *(double *) (si + L.s_Density) = de[i];
+	    *(double *) (si + L.s_DhsmlDensityFactor) = dh[i];
+	    *(double *) (si + L.s_DivVel) = dv[i];
+	    *(double *) (si + L.s_CurlVel) = cu[i];
+	    *(double *) (si + L.s_Pressure) = pr[i];
+	  }
+	else if(ty == 5)
+	  {
+	    *(double *) (pi + L.p_SinkDensity) = sr[i];
+	    *(double *) (pi + L.p_SinkEntropy) = se[i];
+	    double *g = (double *) (pi + L.p_SinkGasVel);
+	    g[0] = sv[3 * i]; g[1] = sv[3 * i + 1]; g[2] = sv[3 * i + 2];
+	  }
+	else if(ty == 2)
+	  {
+	    *(double *) (pi + L.p_DustDensity) = sr[i];
+	    *(double *) (pi + L.p_DustEntropy) = se[i];
+	    double *g = (double *) (pi + L.p_DustGasVel);
+	    g[0] = sv[3 * i]; g[1] = sv[3 * i + 1]; g[2] = sv[3 * i + 2];
+	  }
+      }
+  });
+  return 0;
+}
+
+static int push_hydro_on(gl_ctx *c, cudaStream_t st, double *stage, char *P, char *S)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n, N_gas = c->g_ngas;
+  const gl_gadget_layout L = c->lay;
+  double *ha = stage, *dt = ha + 3 * n, *ms = dt + n;
+  GL_CUDA(c, cudaMemcpyAsync(ha, c->o_hacc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(c, cudaMemcpyAsync(dt, c->o_dtentr.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(c, cudaMemcpyAsync(ms, c->o_maxsig.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GL_CUDA(c, cudaStreamSynchronize(st));
+  parallel_for(std::min(n, N_gas), [=](long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	const char *pi = P + i * L.p_stride;
+	if(*(const short *) (pi + L.p_Type) != 0) continue;
+	char *si = S + i * L.sph_stride;
+	double *g = (double *) (si + L.s_HydroAccel);
+	g[0] = ha[3 * i]; g[1] = ha[3 * i + 1]; g[2] = ha[3 * i + 2];
+	*(double *) (si + L.s_DtEntropy) = dt[i];
+	*(double *) (si + L.s_MaxSignalVel) = ms[i];
+      }
+  });
+  return 0;
+}
+
+static int ensure_pinned2(gl_ctx *c, size_t bytes)
+{
+  if(bytes <= c->pin2_cap) return 0;
+  if(c->pin2) cudaFreeHost(c->pin2);
+  c->pin2 = nullptr;
+  c->pin2_cap = 0;
+  GL_CUDA(c, cudaMallocHost(&c->pin2, bytes + bytes / 8));
+  c->pin2_cap = bytes + bytes / 8;
+  return 0;
+}
+
 extern "C" int gl_gadget_push(gl_ctx *c, void *Pv, void *SphPv, int what)
 {
   cudaSetDevice(c->device);
   if(!c->have_lay) return c->fail("gl_gadget_push: gl_gadget_bind not called");
   const long long n = c->n;
-  const gl_gadget_layout L = c->lay;
+  if(ensure_pinned2(c, (size_t) n * 24 * sizeof(double))) return 1;
+  double *stage = (double *) c->pin2;
+  if((what & 1) && push_gravity_on(c, c->stream, stage, (char *) Pv)) return 1;
+  if((what & 2) && push_density_on(c, c->stream, stage, (char *) Pv, (char *) SphPv)) return 1;
+  if((what & 4) && push_hydro_on(c, c->stream, stage, (char *) Pv, (char *) SphPv)) return 1;
+  return 0;
+}
+
+// The drop-in compute_accelerations (accel.c:27) on the reference's host arrays, software-pipelined:
+// while the GPU runs density, a host thread pulls the gravity results over PCIe on a copy stream and
+// scatters them into P[]; while hmax+hydro run, another thread does the same for the density results.
+extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv, long long NumPart, long long N_gas, int mode)
+{
+  (void) mode;
+  cudaSetDevice(c->device);
+  if(!c->have_lay) return c->fail("gl_gadget_compute_accelerations: gl_gadget_bind not called");
+  if(gl_gadget_pull(c, Pv, SphPv, NumPart, N_gas)) return 1;
+  const long long n = c->n;
+  if(ensure_pinned2(c, (size_t) n * 24 * sizeof(double))) return 1;
+  if(!c->copy_stream[0])
+    for(int k = 0; k < 2; k++) GL_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream[k], cudaStreamNonBlocking));
+  double *stA = (double *) c->pin2, *stB = stA + 5 * n, *stC = stB + 13 * n;	// 5n | 13n | 5n doubles
   char *P = (char *) Pv, *S = (char *) SphPv;
-  const long long N_gas = c->g_ngas;
-  const size_t bytes = (size_t) n * (20 * sizeof(double));
-  if(ensure_pinned(c, bytes)) return 1;
-  double *b0 = (double *) c->pin;
-  if(what & 1)
+  const bool first = (c->par.TypeOfOpeningCriterion == 1 && c->par.Ti_Current == 0 && c->par.ErrTolTheta != 0);
+  if(gl_gravity_tree(c)) return 1;	// accel.c:61
+  if(first)
+    if(gl_gravity_tree(c)) return 1;	// accel.c:63-67
+  int rcA = 0, rcB = 0;
+  std::thread tA([&]() { rcA = push_gravity_on(c, c->copy_stream[0], stA, P); });
+  std::thread tB;
+  int rc = 0;
+  if(gl_prepare_targets(c)) rc = 1;
+  const bool sph = (rc == 0) && c->n_tgt_sph > 0;
+  if(sph)
     {
-      double *acc = b0, *old = acc + 3 * n;
-      float *cost = (float *) (old + n);
-      if(gl_get_gravity(c, acc, old, cost, 0)) return 1;
-      parallel_for(n, [=](long long a, long long b) {
-	for(long long i = a; i < b; i++)
-	  {
-	    char *pi = P + i * L.p_stride;
-	    double *g = (double *) (pi + L.p_GravAccel);
-	    g[0] = acc[3 * i]; g[1] = acc[3 * i + 1]; g[2] = acc[3 * i + 2];
-	    *(double *) (pi + L.p_OldAcc) = old[i];
-	    *(float *) (pi + L.p_GravCost) = cost[i];
-	  }
-      });
+      rc = gl_density(c);	// accel.c:84
+      if(rc == 0)
+	{
+	  tB = std::thread([&]() { rcB = push_density_on(c, c->copy_stream[1], stB, P, S); });
+	  rc = gl_force_update_hmax(c);	// accel.c:96
+	  if(rc == 0) rc = gl_hydro_force(c);	// accel.c:106
+	}
     }
-  if(what & 2)
-    {
-      double *hs = b0, *nn = hs + n, *de = nn + n, *dh = de + n, *dv = dh + n, *cu = dv + n, *pr = cu + n, *sr = pr + n,
-	*se = sr + n, *sv = se + n;
-      if(gl_get_density(c, hs, nn, de, dh, dv, cu, pr, sr, se, sv, 0)) return 1;
-      parallel_for(n, [=](long long a, long long b) {
-	for(long long i = a; i < b; i++)
-	  {
-	    char *pi = P + i * L.p_stride;
-	    const int ty = *(const short *) (pi + L.p_Type);
-	    if(!(ty == 0 || ty == 5 || ty == 2)) continue;
-	    *(double *) (pi + L.p_Hsml) = hs[i];
-	    *(double *) (pi + L.p_NumNgb) = nn[i];
-	    *(unsigned int *) (pi + L.p_SwallowID) = 0;	// density.c:130
-	    if(ty == 0 && i < N_gas)
-	      {
-		char *si = S + i * L.sph_stride;
-		*(double *) (si + L.s_Density) = de[i];
-		*(double *) (si + L.s_DhsmlDensityFactor) = dh[i];
-		*(double *) (si + L.s_DivVel) = dv[i];
-		*(double *) (si + L.s_CurlVel) = cu[i];
-		*(double *) (si + L.s_Pressure) = pr[i];
-	      }
-	    else if(ty == 5)
-	      {
-		*(double *) (pi + L.p_SinkDensity) = sr[i];
-		*(double *) (pi + L.p_SinkEntropy) = se[i];
-		double *g = (double *) (pi + L.p_SinkGasVel);
-		g[0] = sv[3 * i]; g[1] = sv[3 * i + 1]; g[2] = sv[3 * i + 2];
-	      }
-	    else if(ty == 2)
-	      {
-		*(double *) (pi + L.p_DustDensity) = sr[i];
-		*(double *) (pi + L.p_DustEntropy) = se[i];
-		double *g = (double *) (pi + L.p_DustGasVel);
-		g[0] = sv[3 * i]; g[1] = sv[3 * i + 1]; g[2] = sv[3 * i + 2];
-	      }
-	  }
-      });
-    }
-  if(what & 4)
-    {
-      double *ha = b0, *dt = ha + 3 * n, *ms = dt + n;
-      if(gl_get_hydro(c, ha, dt, ms, 0)) return 1;
-      parallel_for(std::min(n, N_gas), [=](long long a, long long b) {
-	for(long long i = a; i < b; i++)
-	  {
-	    const char *pi = P + i * L.p_stride;
-	    if(*(const short *) (pi + L.p_Type) != 0) continue;
-	    char *si = S + i * L.sph_stride;
-	    double *g = (double *) (si + L.s_HydroAccel);
-	    g[0] = ha[3 * i]; g[1] = ha[3 * i + 1]; g[2] = ha[3 * i + 2];
-	    *(double *) (si + L.s_DtEntropy) = dt[i];
-	    *(double *) (si + L.s_MaxSignalVel) = ms[i];
-	  }
-      });
-    }
+  tA.join();
+  if(tB.joinable()) tB.join();
+  if(rc || rcA || rcB) return 1;
+  if(sph && push_hydro_on(c, c->stream, stC, P, S)) return 1;
   return 0;
 }

@@ -145,8 +145,9 @@ struct gl_ctx
   gl_gadget_layout lay{};
   bool have_lay = false;
   long long g_numpart = 0, g_ngas = 0;
-  void *pin = nullptr;
-  size_t pin_cap = 0;
+  void *pin = nullptr, *pin2 = nullptr;
+  size_t pin_cap = 0, pin2_cap = 0;
+  cudaStream_t copy_stream[2] = { nullptr, nullptr };
 
   cudaEvent_t ev[16]{};
 

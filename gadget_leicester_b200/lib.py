@@ -59,7 +59,7 @@ EXPORTS = [
     "gl_peano_hilbert_key", "gl_morton_key", "gl_force_treebuild", "gl_get_nodes", "gl_set_targets",
     "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations",
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
-    "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push",
+    "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
 ]
 
 _lib = None
@@ -114,6 +114,7 @@ def load_library():
     lib.gl_gadget_bind.argtypes = [vp, C.POINTER(GLGadgetLayout)]
     lib.gl_gadget_pull.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong]
     lib.gl_gadget_push.argtypes = [vp, vp, vp, C.c_int]
+    lib.gl_gadget_compute_accelerations.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, C.c_int]
     _lib = lib
     return lib
 

@@ -150,6 +150,9 @@ typedef struct gl_gadget_layout
 int gl_gadget_bind(gl_ctx * ctx, const gl_gadget_layout * lay);
 /* pack P[0..NumPart) / SphP[0..N_gas) into the device SoA (host threads + pinned staging) */
 int gl_gadget_pull(gl_ctx * ctx, const void *P, const void *SphP, long long NumPart, long long N_gas);
+/* compute_accelerations(mode) of accel.c:27 on the reference's own arrays in one call: pull, the force path,
+ * and a software-pipelined push (results of one phase cross PCIe and are scattered while the next phase runs) */
+int gl_gadget_compute_accelerations(gl_ctx * ctx, void *P, void *SphP, long long NumPart, long long N_gas, int mode);
 /* scatter results back in place; what = bit mask: 1 gravity, 2 density, 4 hydro */
 int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
 

@@ -1,0 +1,193 @@
+/* gl_gadget_glue.c - the reference-side binding of libgl_b200.so.
+ *
+ * This file is what a maintainer of the reference ADDS to its tree (it is compiled with the reference's own
+ * allvars.h/proto.h and -D list, so every offsetof() below is exact for that build) and then REMOVES
+ * gravtree.o density.o hydra.o from OBJS (Makefile:845-856), linking with -lgl_b200 -lcudart instead.
+ * It defines the reference's own global entry points for the force path
+ *     void gravity_tree(void)            proto.h / gravtree.c:27
+ *     void density(void)                 proto.h / density.c:89
+ *     void force_update_hmax(void)       forcetree.h / forcetree.c:1661   (only when GL_TAKE_OVER_HMAX is set)
+ *     void hydro_force(void)             proto.h / hydra.c:145
+ *     void compute_accelerations(int)    proto.h / accel.c:27             (only when GL_TAKE_OVER_ACCEL is set)
+ * on top of the C ABI of include/gl_b200.h, keeps the reference's side effects (All.ErrTolTheta = 0 after the
+ * first call, TreeReconstructFlag = 0, All.TotNumOfForces, CPU_Step[] buckets), leaves the mymalloc stack
+ * untouched (mymalloc.c:159-164) and maps any library error onto endrun() (endrun.c:23).
+ *
+ * It is compiled in the build container by oracle/refbuild (target `dropin`) into oracle/_ref/ref_dropin,
+ * where the reference's own harness runs with THESE symbols instead of gravtree.c/density.c/hydra.c.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <stddef.h>
+#include <mpi.h>
+#include "allvars.h"
+#include "proto.h"
+#include "gl_b200.h"
+
+static gl_ctx *GL;
+
+static void gl_fail(const char *where)
+{
+  printf("libgl_b200: %s failed: %s\n", where, GL ? gl_last_error(GL) : "no context");
+  fflush(stdout);
+  endrun(8800);
+}
+
+static void gl_sync_params(void)
+{
+  gl_params p;
+  int i;
+  p.ErrTolTheta = All.ErrTolTheta;
+  p.ErrTolForceAcc = All.ErrTolForceAcc;
+  p.TypeOfOpeningCriterion = All.TypeOfOpeningCriterion;
+  p.DesNumNgb = All.DesNumNgb;
+  p.MaxNumNgbDeviation = All.MaxNumNgbDeviation;
+  p.BlackHoleNgbFactor = All.BlackHoleNgbFactor;
+  p.ArtBulkViscConst = All.ArtBulkViscConst;
+  p.G = All.G;
+  for(i = 0; i < 6; i++) p.ForceSoftening[i] = All.ForceSoftening[i];
+  p.MinGasHsml = All.MinGasHsml;
+  p.Timebase_interval = All.Timebase_interval;
+  p.Ti_Current = All.Ti_Current;
+  p.ComovingIntegrationOn = All.ComovingIntegrationOn;
+  p.OmegaLambdaHubble2 = All.OmegaLambda * All.Hubble * All.Hubble;
+  if(gl_set_params(GL, &p)) gl_fail("gl_set_params");
+}
+
+static void gl_attach(void)
+{
+  gl_gadget_layout L;
+  if(GL) return;
+  /* one rank <-> one GPU of the node */
+  if(gl_create(&GL, ThisTask % 8, All.MaxPart)) gl_fail("gl_create");
+  L.p_stride = sizeof(struct particle_data);
+  L.sph_stride = sizeof(struct sph_particle_data);
+  L.p_Pos = offsetof(struct particle_data, Pos);
+  L.p_Vel = offsetof(struct particle_data, Vel);
+  L.p_Mass = offsetof(struct particle_data, Mass);
+  L.p_GravAccel = offsetof(struct particle_data, g.GravAccel);
+  L.p_OldAcc = offsetof(struct particle_data, OldAcc);
+  L.p_Hsml = offsetof(struct particle_data, Hsml);
+  L.p_NumNgb = offsetof(struct particle_data, n.NumNgb);
+  L.p_GravCost = offsetof(struct particle_data, GravCost);
+  L.p_Ti_begstep = offsetof(struct particle_data, Ti_begstep);
+  L.p_Type = offsetof(struct particle_data, Type);
+  L.p_TimeBin = offsetof(struct particle_data, TimeBin);
+  L.p_SinkDensity = offsetof(struct particle_data, b1.BH_Density);
+  L.p_SinkEntropy = offsetof(struct particle_data, b2.BH_Entropy);
+  L.p_SinkGasVel = offsetof(struct particle_data, b3.BH_SurroundingGasVel);
+  L.p_DustDensity = offsetof(struct particle_data, d1.DUST_Density);
+  L.p_DustEntropy = offsetof(struct particle_data, d2.DUST_Entropy);
+  L.p_DustGasVel = offsetof(struct particle_data, d3.DUST_SurroundingGasVel);
+  L.p_SwallowID = offsetof(struct particle_data, SwallowID);
+  L.s_Entropy = offsetof(struct sph_particle_data, Entropy);
+  L.s_Pressure = offsetof(struct sph_particle_data, Pressure);
+  L.s_VelPred = offsetof(struct sph_particle_data, VelPred);
+  L.s_MaxSignalVel = offsetof(struct sph_particle_data, MaxSignalVel);
+  L.s_Density = offsetof(struct sph_particle_data, d.Density);
+  L.s_DtEntropy = offsetof(struct sph_particle_data, e.DtEntropy);
+  L.s_HydroAccel = offsetof(struct sph_particle_data, a.HydroAccel);
+  L.s_DhsmlDensityFactor = offsetof(struct sph_particle_data, h.DhsmlDensityFactor);
+  L.s_DivVel = offsetof(struct sph_particle_data, v.DivVel);
+  L.s_CurlVel = offsetof(struct sph_particle_data, r.CurlVel);
+  if(gl_gadget_bind(GL, &L)) gl_fail("gl_gadget_bind");
+}
+
+/* the library evaluates the particles it is told to; the reference's active list is
+ * FirstActiveParticle / NextActiveParticle[] (run.c:190-343) */
+static int gl_send_active_list(void)
+{
+  int i, n = 0, all, *idx;
+  for(i = FirstActiveParticle; i >= 0; i = NextActiveParticle[i]) n++;
+  all = (n == NumPart);
+  if(all)
+    {
+      if(gl_set_targets(GL, NULL, -1, 0)) gl_fail("gl_set_targets");
+      return n;
+    }
+  idx = (int *) malloc(sizeof(int) * (n > 0 ? n : 1));	/* private scratch: the mymalloc stack stays as found */
+  for(i = FirstActiveParticle, n = 0; i >= 0; i = NextActiveParticle[i]) idx[n++] = i;
+  if(gl_set_targets(GL, idx, n, 0)) gl_fail("gl_set_targets");
+  free(idx);
+  return n;
+}
+
+static void gl_pull(void)
+{
+  int i;
+  gl_attach();
+  gl_sync_params();
+  /* sources must be current: the reference drifts lazily inside its walks (forcetree.c:1911, ngb.c:57) */
+  for(i = 0; i < NumPart; i++)
+    if(P[i].Ti_current != All.Ti_Current) drift_particle(i, All.Ti_Current);
+  if(gl_gadget_pull(GL, P, SphP, NumPart, N_gas)) gl_fail("gl_gadget_pull");
+  gl_set_tree_reconstruct_flag(GL, 1);
+}
+
+static int gl_loaded_for = -1;	/* All.NumCurrentTiStep the device copy belongs to */
+
+static void gl_ensure_loaded(void)
+{
+  if(gl_loaded_for != All.NumCurrentTiStep || TreeReconstructFlag)
+    {
+      gl_pull();
+      gl_loaded_for = All.NumCurrentTiStep;
+    }
+  gl_send_active_list();
+}
+
+void gravity_tree(void)
+{
+  double t0 = second();
+  int nactive;
+  gl_ensure_loaded();
+  nactive = gl_send_active_list();
+  gl_sync_params();
+  if(gl_gravity_tree(GL)) gl_fail("gl_gravity_tree");
+  if(gl_gadget_push(GL, P, SphP, 1)) gl_fail("gl_gadget_push");
+#ifdef GL_KEEP_CPU_TREE
+  /* The reference's sub-grid physics (blackhole.c:1351, dust.c:1235), setup_smoothinglengths (init.c:719) and its own
+   * force_update_hmax still walk the CPU Nodes[] tree.  Until those loops are ported too a host
+   * that needs them keeps building it here - at ~0.4 us/particle this dominates the step, so leave it off when only
+   * the force path is used. */
+  if(TreeReconstructFlag) force_treebuild(NumPart, NULL);
+#endif
+  if(All.TypeOfOpeningCriterion == 1) All.ErrTolTheta = 0;	/* gravtree.c:396-397 */
+  TreeReconstructFlag = 0;
+  All.TotNumOfForces += nactive;	/* gravtree.c:788 (GlobNumForceUpdate) */
+  CPU_Step[CPU_TREEWALK1] += timediff(t0, second());
+}
+
+void density(void)
+{
+  double t0 = second();
+  gl_ensure_loaded();
+  if(gl_density(GL)) gl_fail("gl_density");
+  if(gl_gadget_push(GL, P, SphP, 2)) gl_fail("gl_gadget_push");
+  CPU_Step[CPU_DENSCOMPUTE] += timediff(t0, second());
+}
+
+void hydro_force(void)
+{
+  double t0 = second();
+  gl_ensure_loaded();
+  if(gl_force_update_hmax(GL)) gl_fail("gl_force_update_hmax");
+  if(gl_hydro_force(GL)) gl_fail("gl_hydro_force");
+  if(gl_gadget_push(GL, P, SphP, 4)) gl_fail("gl_gadget_push");
+  CPU_Step[CPU_HYDCOMPUTE] += timediff(t0, second());
+}
+
+#ifdef GL_TAKE_OVER_ACCEL
+/* the whole force part of accel.c:27-106 in one pipelined call; the sub-grid physics that follows in the
+ * reference (accel.c:176-256) still runs on the host and still finds its inputs in P[]/SphP[] */
+void gl_compute_force_path(int mode)
+{
+  gl_attach();
+  gl_sync_params();
+  gl_send_active_list();
+  gl_set_tree_reconstruct_flag(GL, 1);
+  if(gl_gadget_compute_accelerations(GL, P, SphP, NumPart, N_gas, mode)) gl_fail("gl_gadget_compute_accelerations");
+  if(All.TypeOfOpeningCriterion == 1) All.ErrTolTheta = 0;
+  TreeReconstructFlag = 0;
+}
+#endif
