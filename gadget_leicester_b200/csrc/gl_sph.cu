@@ -46,6 +46,9 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define FAT_MAX 64
 #define STK_RESERVE 160	// 7 pushes per level x 21 levels: pure depth-first continuation never overflows
 #define SPH_BLOCK (32 * SPH_WARPS)
+#ifndef SPH_MIN_BLOCKS
+#define SPH_MIN_BLOCKS 3
+#endif
 #define FULL 0xffffffffu
 
 __device__ __forceinline__ double warp_sum_d(double v)
@@ -73,18 +76,43 @@ __device__ __forceinline__ double dist2_to_cube(double px, double py, double pz,
   return dx * dx + dy * dy + dz * dz;
 }
 
+// Per-warp shared-memory stage.  Candidates are kept as FP32 coordinates RELATIVE TO THE GROUP CENTRE: they only feed
+// a conservative pre-filter (see cand_threshold); every accept/reject decision that counts is re-taken in FP64 from
+// the FP64 particle records.
 struct WarpStage
 {
-  double x[CAND_CAP], y[CAND_CAP], z[CAND_CAP], m[CAND_CAP], h[CAND_CAP];	// position, mass, Hsml of the candidate
-  int j[CAND_CAP];
-  int hit[64];
+  float fx[CAND_CAP], fy[CAND_CAP], fz[CAND_CAP], fh[CAND_CAP];	// candidate position - group centre, candidate Hsml
+  int j[CAND_CAP];		// tree index of the candidate
+  int hit[64];			// compacted "maybe" list of the current target
   int stk[STK_CAP];		// tree cells still to be examined (DFS entry index, or -(p+2) for a lone particle)
   int2 rng[32];			// particle ranges swallowed in the current step
+  float4 cell[32];		// cubes popped in the current step: centre - group centre, half side
+  float cellh[32];		// their hmax (symmetric search only)
 };
 
+// FP32 view of the warp's targets for the two conservative filters
+struct GroupF
+{
+  double gcx, gcy, gcz;		// group centre (FP64)
+  float ax, ay, az;		// this lane's target position - group centre
+  float r;			// this lane's search radius (Hsml), 0 when the lane is idle
+  float amax;			// max |a| component over the warp
+};
+
+// Conservative FP32 bound for "r2 < h*h".  With a, b the FP64 offsets of target and candidate from the group centre
+// and L >= every |component| involved, each component of (af - bf) is off by at most 3*2^-24*L, so
+// |r2f - r2| <= 2*sqrt(3)*|d|*1.8e-7*L + 3*(1.8e-7*L)^2 + 2e-7*r2.  Near the boundary |d| ~ h; the threshold below
+// exceeds that bound more than tenfold, so a true neighbour can never be filtered out (the pair counts stay exact).
+__device__ __forceinline__ float cand_threshold(float h, float L)
+{
+  return h * h * 1.00002f + (8.0e-6f * h + 1.0e-11f * L) * L;
+}
+
 // append the gas particles of the tree range [a,b) (b-a <= 32) to the staged list; returns the new count
-__device__ __forceinline__ int stage_range(WarpStage &S, int ncand, int a, int b, int lane, const double4 *__restrict__ s_pm,
-					    const double4 *__restrict__ s_vh, const int *__restrict__ s_type)
+template <bool WANT_H>
+__device__ __forceinline__ int stage_range(WarpStage &S, int ncand, int a, int b, int lane, const GroupF &G, float &lmax,
+					    const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
+					    const int *__restrict__ s_type)
 {
   const int j = a + lane;
   bool ok = j < b;
@@ -102,12 +130,13 @@ __device__ __forceinline__ int stage_range(WarpStage &S, int ncand, int a, int b
   if(ok)
     {
       const int pos = ncand + __popc(ball & ((1u << lane) - 1));
-      S.x[pos] = pm.x;
-      S.y[pos] = pm.y;
-      S.z[pos] = pm.z;
-      S.m[pos] = pm.w;
-      S.h[pos] = s_vh[j].w;
+      const float bx = (float) (pm.x - G.gcx), by = (float) (pm.y - G.gcy), bz = (float) (pm.z - G.gcz);
+      S.fx[pos] = bx;
+      S.fy[pos] = by;
+      S.fz[pos] = bz;
+      if(WANT_H) S.fh[pos] = (float) s_vh[j].w;
       S.j[pos] = j;
+      lmax = fmaxf(lmax, fmaxf(fabsf(bx), fmaxf(fabsf(by), fabsf(bz))));
     }
   return ncand + __popc(ball);
 }
@@ -126,24 +155,27 @@ __device__ __forceinline__ void hits_shift(WarpStage &S, int nh, int lane)
 }
 
 // Phase 1, warp-parallel.  The warp keeps a stack of tree cells still to be examined.  Every step the lanes
-// pop up to 32 cells, fetch their cubes with INDEPENDENT loads (one memory latency per step instead of one
-// per cell), test each cube against the search spheres of the still-active targets (ngb.c:270-289 /
-// :136-152), and either swallow the cell (<= 32 particles: its tree range is staged with one coalesced
-// load) or push its children (child table written by k_moments).  flush(ncand) runs phases 2+3.
+// pop up to 32 cells and fetch their cubes with INDEPENDENT loads (one memory latency per step instead of one
+// per cell); the cubes are parked in shared memory and every lane tests ITS OWN search sphere against each of them
+// (ngb.c:270-289 / :136-152, here in FP32 with a conservative margin - this test only prunes).  A touched cell
+// is swallowed (<= 32 particles: its tree range is staged with one coalesced load) or its children are pushed
+// (child table written by k_moments).  flush(ncand, lmax) runs phases 2+3.
 template <bool USE_HMAX, class Flush>
 __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries, const int *__restrict__ e_next,
 					    const double4 *__restrict__ e_B, const double *__restrict__ e_hmax,
 					    const int2 *__restrict__ e_rng, const int *__restrict__ n_child,
 					    const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
-					    const int *__restrict__ s_type, unsigned active, double px, double py, double pz,
-					    double radius, unsigned &visits, unsigned &staged, Flush flush)
+					    const int *__restrict__ s_type, unsigned active, const GroupF &G,
+					    unsigned &visits, unsigned &staged, Flush flush)
 {
   if(nentries <= 0 || active == 0) return;
   int ncand = 0;
+  float lmax = 0.f;
   if(lane == 0) S.stk[0] = (__ldg(&e_next[0]) >= 0) ? 0 : -2;
   __syncwarp();
   int sp = 1;
   const unsigned lt = (1u << lane) - 1;
+  const bool mine = (active >> lane) & 1;
   while(sp > 0)
     {
       int k = sp < 32 ? sp : 32;
@@ -152,34 +184,37 @@ __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries
       if(k > room) k = room;
       const int my = (lane < k) ? S.stk[sp - 1 - lane] : -1;
       sp -= k;
-      __syncwarp();
       visits += k;
       const bool isnode = my >= 0;
       const bool ispart = my < -1;
-      double4 B = make_double4(0, 0, 0, 0);
       int2 rg = make_int2(0, 0);
-      double hm = 0, half = 0;
+      float4 cf = make_float4(0.f, 0.f, 0.f, -1.f);	// half < 0 marks "not a cube"
+      float hm = 0.f;
       if(isnode)
 	{
-	  B = gl_ld4(&e_B[my]);
+	  const double4 B = gl_ld4(&e_B[my]);
 	  rg = __ldg(&e_rng[my]);
-	  if(USE_HMAX) hm = __ldg(&e_hmax[my]);
-	  half = 0.5 * B.w;
+	  if(USE_HMAX) hm = (float) __ldg(&e_hmax[my]) * 1.000001f;
+	  cf = make_float4((float) (B.x - G.gcx), (float) (B.y - G.gcy), (float) (B.z - G.gcz), (float) (0.5 * B.w) * 1.000001f);
 	}
-      bool acc = false;
-      unsigned need = __ballot_sync(FULL, isnode);
-      for(unsigned rest = active; rest && need; rest &= rest - 1)
+      S.cell[lane] = cf;
+      if(USE_HMAX) S.cellh[lane] = hm;
+      __syncwarp();
+      // lane = target: which of the k cubes does my sphere touch?
+      unsigned touched = 0;
+      for(int i = 0; i < k; i++)
 	{
-	  const int t = __ffs(rest) - 1;
-	  const double tx = __shfl_sync(FULL, px, t), ty = __shfl_sync(FULL, py, t), tz = __shfl_sync(FULL, pz, t);
-	  const double tr = __shfl_sync(FULL, radius, t);
-	  if(isnode && !acc)
-	    {
-	      const double R = (USE_HMAX ? fmax(tr, hm) : tr) * BOX_SLACK;
-	      acc = dist2_to_cube(tx, ty, tz, B, half) < R * R;
-	    }
-	  need = __ballot_sync(FULL, isnode && !acc);
+	  const float4 c = S.cell[i];
+	  if(c.w < 0.f) continue;
+	  const float dx = fmaxf(0.f, fabsf(c.x - G.ax) - c.w), dy = fmaxf(0.f, fabsf(c.y - G.ay) - c.w),
+	    dz = fmaxf(0.f, fabsf(c.z - G.az) - c.w);
+	  float R = USE_HMAX ? fmaxf(G.r, S.cellh[i]) : G.r;
+	  // FP32 slack: relative on the radius, absolute on the coordinates that entered the subtractions
+	  R = R * 1.001f + 1.0e-6f * (fabsf(c.x) + fabsf(c.y) + fabsf(c.z) + c.w + G.amax);
+	  const bool touch = mine && (dx * dx + dy * dy + dz * dz < R * R);
+	  if(__any_sync(FULL, touch)) touched |= 1u << i;
 	}
+      const bool acc = isnode && ((touched >> lane) & 1);
       const bool small = acc && (rg.y - rg.x <= 32);
       bool big = acc && !small;
       bool bucket = false;
@@ -217,10 +252,11 @@ __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries
 	  const int2 r = S.rng[i];
 	  if(ncand + 32 > CAND_CAP)
 	    {
-	      flush(ncand);
+	      flush(ncand, lmax);
 	      ncand = 0;
+	      lmax = 0.f;
 	    }
-	  ncand = stage_range(S, ncand, r.x, r.y, lane, s_pm, s_vh, s_type);
+	  ncand = stage_range<USE_HMAX>(S, ncand, r.x, r.y, lane, G, lmax, s_pm, s_vh, s_type);
 	  staged += r.y - r.x;
 	}
       for(unsigned bm = __ballot_sync(FULL, bucket); bm; bm &= bm - 1)
@@ -231,16 +267,37 @@ __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries
 	    {
 	      if(ncand + 32 > CAND_CAP)
 		{
-		  flush(ncand);
+		  flush(ncand, lmax);
 		  ncand = 0;
+		  lmax = 0.f;
 		}
-	      ncand = stage_range(S, ncand, a, (a + 32 < rb) ? a + 32 : rb, lane, s_pm, s_vh, s_type);
+	      ncand = stage_range<USE_HMAX>(S, ncand, a, (a + 32 < rb) ? a + 32 : rb, lane, G, lmax, s_pm, s_vh, s_type);
 	    }
 	  staged += rb - ra;
 	}
       __syncwarp();
     }
-  if(ncand > 0) flush(ncand);
+  if(ncand > 0) flush(ncand, lmax);
+}
+
+// group centre + FP32 target offsets for one round
+__device__ __forceinline__ GroupF make_group(bool act, double px, double py, double pz, double radius)
+{
+  GroupF G;
+  const double xlo = warp_min_d(act ? px : 1e300), xhi = warp_max_d(act ? px : -1e300);
+  const double ylo = warp_min_d(act ? py : 1e300), yhi = warp_max_d(act ? py : -1e300);
+  const double zlo = warp_min_d(act ? pz : 1e300), zhi = warp_max_d(act ? pz : -1e300);
+  G.gcx = 0.5 * (xlo + xhi);
+  G.gcy = 0.5 * (ylo + yhi);
+  G.gcz = 0.5 * (zlo + zhi);
+  G.ax = act ? (float) (px - G.gcx) : 0.f;
+  G.ay = act ? (float) (py - G.gcy) : 0.f;
+  G.az = act ? (float) (pz - G.gcz) : 0.f;
+  G.r = act ? (float) radius * 1.000001f : 0.f;
+  float am = fmaxf(fabsf(G.ax), fmaxf(fabsf(G.ay), fabsf(G.az)));
+  for(int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(FULL, am, o));
+  G.amax = am;
+  return G;
 }
 
 struct DensOut
@@ -408,25 +465,28 @@ __device__ __forceinline__ void density_pair(DensAcc &P, int ttype, double dx, d
 }
 
 // phases 2+3 for one staged chunk: every active target against all staged candidates
-__device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, unsigned todo_mask, int lane, double px, double py,
-					      double pz, double vx, double vy, double vz, double h, int ptype, DensAcc &A,
+__device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, float lmax, unsigned todo_mask, int lane, const GroupF &G,
+					      double px, double py, double pz, double vx, double vy, double vz, double h,
+					      int ptype, DensAcc &A, const double4 *__restrict__ s_pm,
 					      const double4 *__restrict__ s_vh, const double *__restrict__ s_entropy)
 {
   __syncwarp();
+  float L = lmax;
+  for(int o = 16; o > 0; o >>= 1) L = fmaxf(L, __shfl_xor_sync(FULL, L, o));
+  L = fmaxf(L, G.amax);
+  const float mythr = cand_threshold(G.r, L);
   for(unsigned rest = todo_mask; rest; rest &= rest - 1)
     {
       const int t = __ffs(rest) - 1;
-      const double tx = __shfl_sync(FULL, px, t), ty = __shfl_sync(FULL, py, t), tz = __shfl_sync(FULL, pz, t);
-      const double th = __shfl_sync(FULL, h, t);
-      const double tvx = __shfl_sync(FULL, vx, t), tvy = __shfl_sync(FULL, vy, t), tvz = __shfl_sync(FULL, vz, t);
-      const int ttype = __shfl_sync(FULL, ptype, t);
-      const double h2 = th * th;
-      const double hinv = 1.0 / th;
-      const double hinv3 = hinv * hinv * hinv;
-      const double hinv4 = hinv3 * hinv;
+      const float tax = __shfl_sync(FULL, G.ax, t), tay = __shfl_sync(FULL, G.ay, t), taz = __shfl_sync(FULL, G.az, t);
+      const float thr = __shfl_sync(FULL, mythr, t);
+      // phase 2 (FP32, conservative): compact the candidates that MAY be neighbours of target t
+      int nh = 0;
       DensAcc P;
       P.zero();
-      int nh = 0;
+      bool loaded = false;
+      double tx = 0, ty = 0, tz = 0, tvx = 0, tvy = 0, tvz = 0, h2 = 0, hinv = 0, hinv3 = 0, hinv4 = 0;
+      int ttype = 0;
       for(int base = 0;; base += 32)
 	{
 	  if(base < ncand)
@@ -435,9 +495,8 @@ __device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, unsigned 
 	      bool hit = false;
 	      if(c < ncand)
 		{
-		  // density.c:835-856: dx = pos_i - pos_j, r2 = dx*dx + dy*dy + dz*dz, r2 < h2
-		  const double dx = tx - S.x[c], dy = ty - S.y[c], dz = tz - S.z[c];
-		  hit = (dx * dx + dy * dy + dz * dz) < h2;
+		  const float dx = tax - S.fx[c], dy = tay - S.fy[c], dz = taz - S.fz[c];
+		  hit = (dx * dx + dy * dy + dz * dz) <= thr;
 		}
 	      const unsigned ball = __ballot_sync(FULL, hit);
 	      if(hit) S.hit[nh + __popc(ball & ((1u << lane) - 1))] = c;
@@ -446,17 +505,33 @@ __device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, unsigned 
 	      if(nh < 32 && base + 32 < ncand) continue;	// keep filling until a full warp of hits is available
 	    }
 	  if(nh == 0) break;
-	  // phase 3: one hit per lane
+	  if(!loaded)
+	    {
+	      tx = __shfl_sync(FULL, px, t); ty = __shfl_sync(FULL, py, t); tz = __shfl_sync(FULL, pz, t);
+	      tvx = __shfl_sync(FULL, vx, t); tvy = __shfl_sync(FULL, vy, t); tvz = __shfl_sync(FULL, vz, t);
+	      const double th = __shfl_sync(FULL, h, t);
+	      ttype = __shfl_sync(FULL, ptype, t);
+	      h2 = th * th;
+	      hinv = 1.0 / th;
+	      hinv3 = hinv * hinv * hinv;
+	      hinv4 = hinv3 * hinv;
+	      loaded = true;
+	    }
+	  // phase 3: one candidate per lane, the reference's FP64 test and sums
 	  const int take = nh < 32 ? nh : 32;
 	  if(lane < take)
 	    {
-	      const int c = S.hit[lane];
-	      const int j = S.j[c];
-	      const double dx = tx - S.x[c], dy = ty - S.y[c], dz = tz - S.z[c];
+	      const int j = S.j[S.hit[lane]];
+	      const double4 pj = gl_ld4(&s_pm[j]);
+	      // density.c:835-856: dx = pos_i - pos_j, r2 = dx*dx + dy*dy + dz*dz, r2 < h2
+	      const double dx = tx - pj.x, dy = ty - pj.y, dz = tz - pj.z;
 	      const double r2 = dx * dx + dy * dy + dz * dz;
-	      const double4 vj = gl_ld4(&s_vh[j]);
-	      density_pair(P, ttype, dx, dy, dz, r2, S.m[c], hinv, hinv3, hinv4, tvx, tvy, tvz, vj,
-			   (ttype != 0) ? __ldg(&s_entropy[j]) : 0.0);
+	      if(r2 < h2)
+		{
+		  const double4 vj = gl_ld4(&s_vh[j]);
+		  density_pair(P, ttype, dx, dy, dz, r2, pj.w, hinv, hinv3, hinv4, tvx, tvy, tvz, vj,
+			       (ttype != 0) ? __ldg(&s_entropy[j]) : 0.0);
+		}
 	    }
 	  hits_shift(S, nh, lane);
 	  nh -= take;
@@ -491,7 +566,7 @@ __device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, unsigned 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(SPH_BLOCK)
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MIN_BLOCKS)
 k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	  double4 *__restrict__ e_B, const int2 *__restrict__ e_rng, const int *__restrict__ n_child,
 	  const double4 *__restrict__ s_pm, double4 *__restrict__ s_vh, const int *__restrict__ s_type, const double *__restrict__ s_entropy,
@@ -552,9 +627,10 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
       const unsigned todo_mask = __ballot_sync(FULL, todo);
       if(todo_mask == 0) break;
       if(todo) A.zero();	// lanes that already converged keep the sums of their final round
-      sph_collect<false>(S, lane, nentries, e_next, e_B, nullptr, e_rng, n_child, s_pm, s_vh, s_type, todo_mask, px, py, pz, h,
-			 visits, staged, [&](int ncand) {
-			   density_chunk(S, ncand, todo_mask, lane, px, py, pz, vx, vy, vz, h, ptype, A, s_vh, s_entropy);
+      const GroupF G = make_group(todo, px, py, pz, h);
+      sph_collect<false>(S, lane, nentries, e_next, e_B, nullptr, e_rng, n_child, s_pm, s_vh, s_type, todo_mask, G, visits, staged,
+			 [&](int ncand, float lmax) {
+			   density_chunk(S, ncand, lmax, todo_mask, lane, G, px, py, pz, vx, vy, vz, h, ptype, A, s_pm, s_vh, s_entropy);
 			 });
 
       // ---- post-processing and Hsml update, density.c:434-652 (one lane = one target) ----
@@ -827,7 +903,8 @@ static int density_fat_path(gl_ctx *c, int nfat, const DensIn &in, const DensOut
 
 int gls_density(gl_ctx *c)
 {
-  if(!c->tree_valid) return c->fail("density: no tree (call gl_force_treebuild / gl_gravity_tree first, init.c:529)");
+  if(!c->tree_valid)		// the reference builds it beforehand (ngb_treebuild, init.c:529); a fresh load has none yet
+    if(glt_build(c)) return 1;
   if(c->par.ComovingIntegrationOn) return c->fail("density: ComovingIntegrationOn != 0 is not implemented");
   if(gl_prepare_targets(c)) return 1;
   long long n = c->n, nt = c->n_tgt_sph;
@@ -938,24 +1015,28 @@ struct HydroTarget
   int timestep;
 };
 
-__device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, unsigned live_mask, int lane, const HydroTarget &T,
-					    HydroAcc &A, const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
+__device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax, unsigned live_mask, int lane, const GroupF &G,
+					    const HydroTarget &T, HydroAcc &A, const double4 *__restrict__ s_pm,
+					    const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
 					    const double2 *__restrict__ h_r, double artvisc, double timebase_interval)
 {
   __syncwarp();
+  float L = lmax;
+  for(int o = 16; o > 0; o >>= 1) L = fmaxf(L, __shfl_xor_sync(FULL, L, o));
+  L = fmaxf(L, G.amax);
+  const float mythr = cand_threshold(G.r, L);
   for(unsigned rest = live_mask; rest; rest &= rest - 1)
     {
       const int t = __ffs(rest) - 1;
-#define BC(v) __shfl_sync(FULL, (v), t)
-      const double tx = BC(T.px), ty = BC(T.py), tz = BC(T.pz), tvx = BC(T.vx), tvy = BC(T.vy), tvz = BC(T.vz);
-      const double h_i = BC(T.h_i), mass = BC(T.mass), rho = BC(T.rho), f1 = BC(T.f1), cs_i = BC(T.cs_i);
-      const double p_over_rho2_i = BC(T.p_over_rho2_i);
-      const int timestep = BC(T.timestep);
-#undef BC
-      const double h_i2 = h_i * h_i;
+      const float tax = __shfl_sync(FULL, G.ax, t), tay = __shfl_sync(FULL, G.ay, t), taz = __shfl_sync(FULL, G.az, t);
+      const float thr = __shfl_sync(FULL, mythr, t);
       HydroAcc P;
       P.zero();
       int nh = 0;
+      bool loaded = false;
+      double tx = 0, ty = 0, tz = 0, tvx = 0, tvy = 0, tvz = 0, h_i = 0, mass = 0, rho = 0, f1 = 0, cs_i = 0, p_over_rho2_i = 0,
+	h_i2 = 0, hinv_i = 0, hinv4_i = 0;
+      int timestep = 0;
       for(int base = 0;; base += 32)
 	{
 	  if(base < ncand)
@@ -964,11 +1045,10 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, unsigned li
 	      bool hit = false;
 	      if(c < ncand)
 		{
-		  // hydra.c:1250-1266: r2 < h_i^2 || r2 < h_j^2
-		  const double dx = tx - S.x[c], dy = ty - S.y[c], dz = tz - S.z[c];
-		  const double r2 = dx * dx + dy * dy + dz * dz;
-		  const double h_j = S.h[c];
-		  hit = (r2 < h_i2 || r2 < h_j * h_j);
+		  // conservative FP32 version of hydra.c:1266 (r2 < h_i^2 || r2 < h_j^2)
+		  const float dx = tax - S.fx[c], dy = tay - S.fy[c], dz = taz - S.fz[c];
+		  const float r2 = dx * dx + dy * dy + dz * dz;
+		  hit = (r2 <= thr) || (r2 <= cand_threshold(S.fh[c], L));
 		}
 	      const unsigned ball = __ballot_sync(FULL, hit);
 	      if(hit) S.hit[nh + __popc(ball & ((1u << lane) - 1))] = c;
@@ -977,75 +1057,90 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, unsigned li
 	      if(nh < 32 && base + 32 < ncand) continue;
 	    }
 	  if(nh == 0) break;
+	  if(!loaded)
+	    {
+#define BC(v) __shfl_sync(FULL, (v), t)
+	      tx = BC(T.px); ty = BC(T.py); tz = BC(T.pz); tvx = BC(T.vx); tvy = BC(T.vy); tvz = BC(T.vz);
+	      h_i = BC(T.h_i); mass = BC(T.mass); rho = BC(T.rho); f1 = BC(T.f1); cs_i = BC(T.cs_i);
+	      p_over_rho2_i = BC(T.p_over_rho2_i);
+	      timestep = BC(T.timestep);
+#undef BC
+	      h_i2 = h_i * h_i;
+	      hinv_i = 1.0 / h_i;
+	      hinv4_i = hinv_i * hinv_i * hinv_i * hinv_i;
+	      loaded = true;
+	    }
 	  const int take = nh < 32 ? nh : 32;
 	  if(lane < take)
 	    {
-	      const int c = S.hit[lane];
-	      const int j = S.j[c];
-	      const double dx = tx - S.x[c], dy = ty - S.y[c], dz = tz - S.z[c];
+	      const int j = S.j[S.hit[lane]];
+	      const double4 pj = gl_ld4(&s_pm[j]);
+	      const double4 vj = gl_ld4(&s_vh[j]);
+	      const double dx = tx - pj.x, dy = ty - pj.y, dz = tz - pj.z;
 	      const double r2 = dx * dx + dy * dy + dz * dz;
-	      const double h_j = S.h[c];
-	      const double mass_j = S.m[c];
-	      const double r = sqrt(r2);
-	      if(r > 0)
+	      const double h_j = vj.w;
+	      const double mass_j = pj.w;
+	      const double h_j2 = h_j * h_j;
+	      if(r2 < h_i2 || r2 < h_j2)	// hydra.c:1266, the reference's FP64 predicate
 		{
-		  const double4 vj = gl_ld4(&s_vh[j]);
-		  const double4 q = gl_ld4(&h_q[j]);
-		  const double2 rr = __ldg(&h_r[j]);
-		  P.npairs++;
-		  const double rho_j = q.x;
-		  const double soundspeed_j = q.w;
-		  const double dvx = tvx - vj.x, dvy = tvy - vj.y, dvz = tvz - vj.z;
-		  const double vdotr = dx * dvx + dy * dvy + dz * dvz;
-		  const double vdotr2 = vdotr;	// non-comoving, hydra.c:1279-1282
-		  double dwk_i = 0, dwk_j = 0;
-		  if(r2 < h_i2)
+		  const double r = sqrt(r2);
+		  if(r > 0)
 		    {
-		      const double hinv = 1.0 / h_i;
-		      const double hinv4 = hinv * hinv * hinv * hinv;
-		      const double u = r * hinv;
-		      if(u < 0.5)
-			dwk_i = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
-		      else
-			dwk_i = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-		    }
-		  if(r2 < h_j * h_j)
-		    {
-		      const double hinv = 1.0 / h_j;
-		      const double hinv4 = hinv * hinv * hinv * hinv;
-		      const double u = r * hinv;
-		      if(u < 0.5)
-			dwk_j = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
-		      else
-			dwk_j = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-		    }
-		  double vsig = cs_i + soundspeed_j;	// hydra.c:1502
-		  if(vsig > P.maxsig) P.maxsig = vsig;
-		  double visc = 0;
-		  if(vdotr2 < 0)
-		    {
-		      const double mu_ij = 1.0 * vdotr2 / r;	// fac_mu = 1
-		      vsig -= 3 * mu_ij;
-		      if(vsig > P.maxsig) P.maxsig = vsig;
-		      const double rho_ij = 0.5 * (rho + rho_j);
-		      const double f2 = rr.x;
-		      visc = 0.25 * artvisc * vsig * (-mu_ij) / rho_ij * (f1 + f2);
-		      // hydra.c:1583-1597 viscosity limiter
-		      const int ts_j = (int) rr.y;
-		      const double dt = 2 * ((timestep > ts_j) ? timestep : ts_j) * timebase_interval;
-		      if(dt > 0 && (dwk_i + dwk_j) < 0)
+		      const double4 q = gl_ld4(&h_q[j]);
+		      const double2 rr = __ldg(&h_r[j]);
+		      P.npairs++;
+		      const double rho_j = q.x;
+		      const double soundspeed_j = q.w;
+		      const double dvx = tvx - vj.x, dvy = tvy - vj.y, dvz = tvz - vj.z;
+		      const double vdotr = dx * dvx + dy * dvy + dz * dvz;
+		      const double vdotr2 = vdotr;	// non-comoving, hydra.c:1279-1282
+		      double dwk_i = 0, dwk_j = 0;
+		      if(r2 < h_i2)
 			{
-			  const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (mass + mass_j) * (dwk_i + dwk_j) * r * dt);
-			  visc = (visc < lim) ? visc : lim;
+			  const double u = r * hinv_i;
+			  if(u < 0.5)
+			    dwk_i = hinv4_i * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
+			  else
+			    dwk_i = hinv4_i * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
 			}
+		      if(r2 < h_j2)
+			{
+			  const double hinv = 1.0 / h_j;
+			  const double hinv4 = hinv * hinv * hinv * hinv;
+			  const double u = r * hinv;
+			  if(u < 0.5)
+			    dwk_j = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
+			  else
+			    dwk_j = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+			}
+		      double vsig = cs_i + soundspeed_j;	// hydra.c:1502
+		      if(vsig > P.maxsig) P.maxsig = vsig;
+		      double visc = 0;
+		      if(vdotr2 < 0)
+			{
+			  const double mu_ij = 1.0 * vdotr2 / r;	// fac_mu = 1
+			  vsig -= 3 * mu_ij;
+			  if(vsig > P.maxsig) P.maxsig = vsig;
+			  const double rho_ij = 0.5 * (rho + rho_j);
+			  const double f2 = rr.x;
+			  visc = 0.25 * artvisc * vsig * (-mu_ij) / rho_ij * (f1 + f2);
+			  // hydra.c:1583-1597 viscosity limiter
+			  const int ts_j = (int) rr.y;
+			  const double dt = 2 * ((timestep > ts_j) ? timestep : ts_j) * timebase_interval;
+			  if(dt > 0 && (dwk_i + dwk_j) < 0)
+			    {
+			      const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (mass + mass_j) * (dwk_i + dwk_j) * r * dt);
+			      visc = (visc < lim) ? visc : lim;
+			    }
+			}
+		      const double p_over_rho2_j = q.z;	// already x DhsmlDensityFactor_j (hydra.c:1600)
+		      const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) / r;
+		      const double hfc = hfc_visc + mass_j * (p_over_rho2_i * dwk_i + p_over_rho2_j * dwk_j) / r;
+		      P.a0 += (-hfc * dx);
+		      P.a1 += (-hfc * dy);
+		      P.a2 += (-hfc * dz);
+		      P.dtE += (0.5 * hfc_visc * vdotr2);
 		    }
-		  const double p_over_rho2_j = q.z;	// already x DhsmlDensityFactor_j (hydra.c:1600)
-		  const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) / r;
-		  const double hfc = hfc_visc + mass_j * (p_over_rho2_i * dwk_i + p_over_rho2_j * dwk_j) / r;
-		  P.a0 += (-hfc * dx);
-		  P.a1 += (-hfc * dy);
-		  P.a2 += (-hfc * dz);
-		  P.dtE += (0.5 * hfc_visc * vdotr2);
 		}
 	    }
 	  hits_shift(S, nh, lane);
@@ -1066,7 +1161,7 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, unsigned li
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(SPH_BLOCK)
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MIN_BLOCKS)
 k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const int2 *__restrict__ e_rng,
 	const int *__restrict__ n_child, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
@@ -1108,9 +1203,10 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
   HydroAcc A;
   A.zero();
   unsigned visits = 0, staged = 0;
-  sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, T.px, T.py, T.pz, T.h_i,
-		    visits, staged, [&](int ncand) {
-		      hydro_chunk(S, ncand, live_mask, lane, T, A, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
+  const GroupF G = make_group(live, T.px, T.py, T.pz, T.h_i);
+  sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, G, visits, staged,
+		    [&](int ncand, float lmax) {
+		      hydro_chunk(S, ncand, lmax, live_mask, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
 		    });
   if(live)
     {
@@ -1126,7 +1222,8 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
 
 int gls_hydro(gl_ctx *c)
 {
-  if(!c->tree_valid) return c->fail("hydro_force: no tree");
+  if(!c->tree_valid)
+    if(glt_build(c)) return 1;
   if(c->par.ComovingIntegrationOn) return c->fail("hydro_force: ComovingIntegrationOn != 0 is not implemented");
   if(c->o_density.cap < (size_t) c->n) return c->fail("hydro_force: density() has not been run (SphP.Density unknown)");
   if(gl_prepare_targets(c)) return 1;
