@@ -142,6 +142,107 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------ the 2^27-particle configs ----
+def big_config(args):
+    """BASELINE configs 3 (collisionless Plummer sphere, gravity walk only) and 4 (uniform random gas cube,
+    density + hydro only), strong scaling: the SAME N-particle set for any GPU count, generated on the device."""
+    import numpy as np
+    import torch
+    from gadget_leicester_b200 import ics
+    from gadget_leicester_b200.multigpu import DistributedForcePath
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.n or (1 << 27)
+    dev = torch.device("cuda", local)
+    warm = max(3, args.warmup)
+    if args.config == 3:
+        par = ics.default_params(Softening=[1e-5, ics.plummer_softening(n), 5e-5, 1e-7, 0.01, 5e-5])
+        ps = ics.plummer_torch(n, dev, seed=42)
+        kw = dict(sph=False, gravity=True)
+        metric, unit = "gravity particle-node interactions/s (tree rebuild + walk, relative criterion)", "interactions/s"
+        work = "BASELINE config 3: collisionless Plummer sphere, %d particles, gravity tree walk only" % n
+    else:
+        par = ics.default_params(DesNumNgb=64, MaxNumNgbDeviation=0.5)
+        ps = ics.cube_torch(n, dev, seed=42)
+        ps["hsml"].fill_((3.0 * 64 / (4 * np.pi * n)) ** (1.0 / 3.0) * 1.3)
+        kw = dict(sph=True, gravity=False)
+        metric, unit = "SPH particle updates/s (tree rebuild + density + hydro)", "updates/s"
+        work = "BASELINE config 4: uniform random SPH cube, %d gas particles, Ngb=64, density+hydro only" % n
+    dfp = DistributedForcePath(par, rank=rank, world=world, device=local)
+    dfp.decompose_device(ps)
+    del ps
+    torch.cuda.empty_cache()
+    dfp.compute_accelerations(**kw)          # settle: Barnes-Hut pass / cold-start density
+    cold_passes = dfp.fp.stats()["density_passes_max"]
+
+    def one_step():
+        dfp.fp.set_TreeReconstructFlag(1)
+        dfp.compute_accelerations(**kw)
+
+    for _ in range(warm):
+        one_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    dfp.fp.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot_ms, inter, phase = 0.0, 0, {}
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        e0.record(torch.cuda.current_stream())
+        one_step()
+        torch.cuda.synchronize()
+        e1.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        tot_ms += e0.elapsed_time(e1)
+        st = dfp.fp.stats()
+        inter += st["interactions"] if args.config == 3 else 0
+        for k in ("ms_keys_sort", "ms_treebuild", "ms_moments", "ms_gravity_walk", "ms_density", "ms_hmax", "ms_hydro"):
+            phase[k] = phase.get(k, 0.0) + st[k] / args.steps
+    launches = dfp.fp.stats()["kernel_launches"]
+    clocks = sampler.stop()
+    t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+    it = torch.tensor([float(inter)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t.item()) / args.steps
+    units = (float(it.item()) / args.steps) if args.config == 3 else float(n)
+    pk = peaks()
+    if args.config == 3:
+        nsm = torch.cuda.get_device_properties(local).multi_processor_count
+        peak = nsm * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        ach = FLOP_PER_INTERACTION * (inter / args.steps) / (phase["ms_gravity_walk"] * 1e-3) / 1e12
+        roof = dict(kernel="k_gravity_walk", bound="fp32", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                    note="25 flop/interaction; this rank's launch; peak = SMs*128*2*sm_max_mhz (" + pk["source"] + ")")
+    else:
+        own = dfp.hi - dfp.lo
+        dom = "hydro" if phase["ms_hydro"] >= phase["ms_density"] else "density"
+        per = HYDRO_BYTES_PER_UPDATE if dom == "hydro" else DENS_BYTES_PER_UPDATE
+        ach = per * own / (phase["ms_" + dom] * 1e-3) / 1e9
+        roof = dict(kernel="k_" + dom, bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                    traffic=None, note="%g B/update; this rank's launch; peak from %s" % (per, pk["source"]))
+    if rank == 0:
+        print(json.dumps(dict(metric=metric, value=units / (ms_per_step * 1e-3), unit=unit, n_gpus=world, steps=args.steps, warmup=warm,
+                              ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None,
+                              dtype="f64 predicates + f32 force magnitude" if args.config == 3 else "f64", data="synthetic",
+                              config=dict(workload=work, particles=n, parallelism="ph-segments x%d" % world,
+                                          l2="inputs larger than L2 (%.1f GB of tree records)" % (n * 150e-9)),
+                              phase_ms=phase, density_passes=dict(cold_start=cold_passes), gpu_launches=int(launches), clocks=clocks,
+                              roofline=roof, e2e=None, interactions_per_step=(units if args.config == 3 else None))))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------- our arm ----
 def main():
     ap = argparse.ArgumentParser()
@@ -150,11 +251,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ngas", type=int, default=0, help="override gas particles per GPU (default 1.6M)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 3, 4],
+                    help="0: disc (default, headline); 3: Plummer sphere, gravity only; 4: uniform gas cube, density+hydro only")
+    ap.add_argument("--n", type=int, default=0, help="total particles for --config 3/4 (default 2^27)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config in (3, 4):
+        return big_config(args)
 
     import numpy as np
     import torch

@@ -79,8 +79,20 @@ __device__ __forceinline__ double dist2_to_cube(double px, double py, double pz,
 // Per-warp shared-memory stage.  Candidates are kept as FP32 coordinates RELATIVE TO THE GROUP CENTRE: they only feed
 // a conservative pre-filter (see cand_threshold); every accept/reject decision that counts is re-taken in FP64 from
 // the FP64 particle records.
+#ifdef GL_PHASE_PROF
+__device__ unsigned long long g_phase[8];
+#define PH_T(v) const long long v = clock64()
+#define PH_ADD(S, idx, v) do { if((threadIdx.x & 31) == 0) (S).ph[idx] += (unsigned long long) (clock64() - (v)); } while(0)
+#else
+#define PH_T(v)
+#define PH_ADD(S, idx, v)
+#endif
+
 struct WarpStage
 {
+#ifdef GL_PHASE_PROF
+  unsigned long long ph[8];
+#endif
   float fx[CAND_CAP], fy[CAND_CAP], fz[CAND_CAP], fh[CAND_CAP];	// candidate position - group centre, candidate Hsml
   int j[CAND_CAP];		// tree index of the candidate
   int hit[64];			// compacted "maybe" list of the current target
@@ -182,6 +194,7 @@ __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries
       int room = (STK_CAP - STK_RESERVE - sp) / 7;
       if(room < 1) room = 1;
       if(k > room) k = room;
+      PH_T(tc0);
       const int my = (lane < k) ? S.stk[sp - 1 - lane] : -1;
       sp -= k;
       visits += k;
@@ -240,6 +253,7 @@ __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries
 	  if(has) S.stk[sp + __popc(ball & lt)] = cc[i];
 	  sp += __popc(ball);
 	}
+      PH_ADD(S, 0, tc0);
       // swallow the small cells and the lone particles
       const bool isrange = small || ispart;
       if(ispart) rg = make_int2(-(my + 2), -(my + 2) + 1);
@@ -256,7 +270,9 @@ __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries
 	      ncand = 0;
 	      lmax = 0.f;
 	    }
+	  PH_T(ts0);
 	  ncand = stage_range<USE_HMAX>(S, ncand, r.x, r.y, lane, G, lmax, s_pm, s_vh, s_type);
+	  PH_ADD(S, 1, ts0);
 	  staged += r.y - r.x;
 	}
       for(unsigned bm = __ballot_sync(FULL, bucket); bm; bm &= bm - 1)
@@ -430,7 +446,9 @@ __device__ __forceinline__ void density_pair(DensAcc &P, int ttype, double dx, d
 					     const double4 &vj, double entr_j)
 {
   P.numngb++;
-  const double r = sqrt(r2);
+  // r and 1/r from one reciprocal square root (r2 == 0 is the target itself: r = 0, no velocity terms)
+  const double rinv = (r2 > 0) ? rsqrt(r2) : 0.0;
+  const double r = r2 * rinv;
   const double u = r * hinv;
   double wk, dwk;
   if(u < 0.5)
@@ -455,7 +473,7 @@ __device__ __forceinline__ void density_pair(DensAcc &P, int ttype, double dx, d
     }
   else if(r > 0)
     {
-      const double fac = mass_j * dwk / r;
+      const double fac = mass_j * dwk * rinv;
       const double dvx = tvx - vj.x, dvy = tvy - vj.y, dvz = tvz - vj.z;
       P.divv += -fac * (dx * dvx + dy * dvy + dz * dvz);
       P.rot0 += fac * (dz * dvy - dy * dvz);
@@ -1039,6 +1057,7 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
       int timestep = 0;
       for(int base = 0;; base += 32)
 	{
+	  PH_T(tt0);
 	  if(base < ncand)
 	    {
 	      const int c = base + lane;
@@ -1054,9 +1073,11 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 	      if(hit) S.hit[nh + __popc(ball & ((1u << lane) - 1))] = c;
 	      nh += __popc(ball);
 	      __syncwarp();
+	      PH_ADD(S, 2, tt0);
 	      if(nh < 32 && base + 32 < ncand) continue;
 	    }
 	  if(nh == 0) break;
+	  PH_T(th0);
 	  if(!loaded)
 	    {
 #define BC(v) __shfl_sync(FULL, (v), t)
@@ -1083,12 +1104,15 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 	      const double h_j2 = h_j * h_j;
 	      if(r2 < h_i2 || r2 < h_j2)	// hydra.c:1266, the reference's FP64 predicate
 		{
-		  const double r = sqrt(r2);
-		  if(r > 0)
+		  if(r2 > 0)
 		    {
 		      const double4 q = gl_ld4(&h_q[j]);
 		      const double2 rr = __ldg(&h_r[j]);
 		      P.npairs++;
+		      // r and 1/r from one reciprocal square root; the reference divides by r three times
+		      // (hydra.c:1511, 1602, 1606), here these are multiplications by rinv (1 ulp apart)
+		      const double rinv = rsqrt(r2);
+		      const double r = r2 * rinv;
 		      const double rho_j = q.x;
 		      const double soundspeed_j = q.w;
 		      const double dvx = tvx - vj.x, dvy = tvy - vj.y, dvz = tvz - vj.z;
@@ -1118,7 +1142,7 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 		      double visc = 0;
 		      if(vdotr2 < 0)
 			{
-			  const double mu_ij = 1.0 * vdotr2 / r;	// fac_mu = 1
+			  const double mu_ij = vdotr2 * rinv;	// fac_mu = 1
 			  vsig -= 3 * mu_ij;
 			  if(vsig > P.maxsig) P.maxsig = vsig;
 			  const double rho_ij = 0.5 * (rho + rho_j);
@@ -1134,8 +1158,8 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 			    }
 			}
 		      const double p_over_rho2_j = q.z;	// already x DhsmlDensityFactor_j (hydra.c:1600)
-		      const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) / r;
-		      const double hfc = hfc_visc + mass_j * (p_over_rho2_i * dwk_i + p_over_rho2_j * dwk_j) / r;
+		      const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) * rinv;
+		      const double hfc = hfc_visc + mass_j * (p_over_rho2_i * dwk_i + p_over_rho2_j * dwk_j) * rinv;
 		      P.a0 += (-hfc * dx);
 		      P.a1 += (-hfc * dy);
 		      P.a2 += (-hfc * dz);
@@ -1144,9 +1168,11 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 		}
 	    }
 	  hits_shift(S, nh, lane);
+	  PH_ADD(S, 3, th0);
 	  nh -= take;
 	  if(base + 32 >= ncand && nh == 0) break;
 	}
+      PH_T(tr0);
       const int tot = __reduce_add_sync(FULL, P.npairs);
       if(tot == 0) continue;
       const double r0 = warp_sum_d(P.a0), r1 = warp_sum_d(P.a1), r2s = warp_sum_d(P.a2), r3 = warp_sum_d(P.dtE);
@@ -1157,6 +1183,7 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 	  if(r4 > A.maxsig) A.maxsig = r4;
 	  A.npairs += tot;
 	}
+      PH_ADD(S, 4, tr0);
     }
   __syncwarp();
 }
@@ -1203,11 +1230,21 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
   HydroAcc A;
   A.zero();
   unsigned visits = 0, staged = 0;
+#ifdef GL_PHASE_PROF
+  if(lane == 0) for(int q = 0; q < 8; q++) S.ph[q] = 0;
+  __syncwarp();
+#endif
+  PH_T(tk0);
   const GroupF G = make_group(live, T.px, T.py, T.pz, T.h_i);
   sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, G, visits, staged,
 		    [&](int ncand, float lmax) {
 		      hydro_chunk(S, ncand, lmax, live_mask, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
 		    });
+#ifdef GL_PHASE_PROF
+  PH_ADD(S, 5, tk0);
+  __syncwarp();
+  if(lane < 6) atomicAdd(&g_phase[lane], S.ph[lane]);
+#endif
   if(live)
     {
       o_hacc[3ll * pin] = A.a0;
@@ -1261,6 +1298,14 @@ int gls_hydro(gl_ctx *c)
   float ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->st.ms_hydro = ms;
+#ifdef GL_PHASE_PROF
+  {
+    unsigned long long ph[8];
+    cudaMemcpyFromSymbol(ph, g_phase, sizeof(ph));
+    fprintf(stderr, "[gl] hydro phase cycles (sum over warps, cumulative): collect %.3g stage %.3g test %.3g heavy %.3g reduce %.3g total %.3g\n",
+	    (double) ph[0], (double) ph[1], (double) ph[2], (double) ph[3], (double) ph[4], (double) ph[5]);
+  }
+#endif
   c->st.hydro_targets = nt;
   return 0;
 }

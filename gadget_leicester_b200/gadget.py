@@ -117,6 +117,10 @@ class ForcePath:
         self._chk(self._lib.gl_peano_hilbert_order(self._ctx, int(n_gas), L._ptr(order), 0))
         return order
 
+    def peano_hilbert_order_device(self, n_gas, out_ptr):
+        """peano_hilbert_order into a device int32 buffer (pointer as int)."""
+        self._chk(self._lib.gl_peano_hilbert_order(self._ctx, int(n_gas), C.c_void_p(out_ptr), 1))
+
     # -- tree ----------------------------------------------------------------------------
     def force_treebuild(self):
         nn = C.c_longlong(0)

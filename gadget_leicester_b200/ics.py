@@ -157,3 +157,44 @@ def guess_hsml(ps, des_num_ngb):
     out = np.zeros(pos.shape[0])
     out[gas] = h
     return out
+
+
+# ---- device-side generators for the 2^27 configs (host numpy would need > 100 GB across 8 ranks) ----------------
+def plummer_torch(n, device, seed=42, a=1.0, rmax=10.0):
+    """Config 3 on the GPU: same distribution as plummer(), torch Philox stream."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    x = torch.rand(n, generator=g, device=device, dtype=torch.float64).clamp_(1e-12, 1 - 1e-12)
+    # truncate at rmax by rescaling the mass fraction: M(<r)/M = r^3 / (r^2 + a^2)^1.5
+    fmax = (rmax ** 3) / (rmax * rmax + 1.0) ** 1.5
+    x = x * fmax
+    r = a / torch.sqrt(x ** (-2.0 / 3.0) - 1.0)
+    ct = 2 * torch.rand(n, generator=g, device=device, dtype=torch.float64) - 1
+    st = torch.sqrt(1 - ct * ct)
+    phi = 2 * np.pi * torch.rand(n, generator=g, device=device, dtype=torch.float64)
+    pos = torch.stack([r * st * torch.cos(phi), r * st * torch.sin(phi), r * ct], dim=1).contiguous()
+    sig = torch.sqrt(1.0 / (6.0 * torch.sqrt(r * r + a * a)))
+    vel = (torch.randn(n, 3, generator=g, device=device, dtype=torch.float64) * sig[:, None]).contiguous()
+    return _finish_torch(pos, vel, torch.full((n,), 1.0 / n, device=device, dtype=torch.float64),
+                         torch.ones(n, device=device, dtype=torch.int32), torch.zeros(n, device=device, dtype=torch.float64))
+
+
+def cube_torch(n, device, seed=42, vamp=0.05):
+    """Config 4 on the GPU: uniform random gas cube."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    pos = torch.rand(n, 3, generator=g, device=device, dtype=torch.float64)
+    vel = (2 * torch.rand(n, 3, generator=g, device=device, dtype=torch.float64) - 1) * vamp
+    return _finish_torch(pos, vel, torch.full((n,), 1.0 / n, device=device, dtype=torch.float64),
+                         torch.zeros(n, device=device, dtype=torch.int32), torch.ones(n, device=device, dtype=torch.float64))
+
+
+def _finish_torch(pos, vel, mass, ptype, entropy):
+    import torch
+    n = pos.shape[0]
+    dev = pos.device
+    z = lambda dt: torch.zeros(n, device=dev, dtype=dt)
+    return dict(pos=pos, vel=vel, mass=mass, type=ptype, hsml=z(torch.float64), oldacc=z(torch.float64), timebin=z(torch.int32),
+                ti_begstep=z(torch.int32), entropy=entropy, dtentropy=z(torch.float64))

@@ -101,6 +101,31 @@ class DistributedForcePath:
                         pressure=f64(n), hacc=f64(n, 3), dtentr=f64(n), maxsig=f64(n))
         return order
 
+    def decompose_device(self, ps):
+        """Same as decompose() for a particle set that already lives on this GPU as torch tensors (every rank
+        generated the same set): nothing of size N ever touches the host."""
+        n = ps["pos"].shape[0]
+        ngas = int((ps["type"] == 0).sum().item())
+        assert bool((ps["type"][:ngas] == 0).all().item()), "gas must come first"
+        dev = self.device
+        self.n, self.ngas = n, ngas
+        torch.cuda.current_stream(dev).synchronize()
+        self.fp.load_device(n, [ps[k].data_ptr() for k in STATE_FIELDS])
+        order = torch.empty(n, dtype=torch.int32, device=dev)
+        self.fp.peano_hilbert_order_device(ngas, order.data_ptr())
+        lo, hi, m = partition_range(n, self.world, self.rank)
+        self.lo, self.hi, self.m = lo, hi, m
+        seg = order[lo:hi].long()
+        self.own = {k: ps[k].index_select(0, seg).contiguous() for k in STATE_FIELDS}
+        self.targets = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+        self.order = order
+        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
+        self.res = dict(acc=f64(n, 3), oldacc=f64(n), gravcost=torch.zeros(n, dtype=torch.float32, device=dev))
+        if ngas > 0:
+            self.res.update(hsml=f64(n), numngb=f64(n), density=f64(n), dhsml=f64(n), divvel=f64(n), curlvel=f64(n),
+                            pressure=f64(n), hacc=f64(n, 3), dtentr=f64(n), maxsig=f64(n))
+        return order
+
     def _sync_lib(self):
         # the library runs on its own stream and synchronises before returning; make torch's stream wait for
         # nothing further (results are complete), and make sure torch work is done before the library reads
@@ -151,10 +176,13 @@ class DistributedForcePath:
         self.fp._chk(lib.gl_get_hydro(ctx, C.c_void_p(r["hacc"].data_ptr()), C.c_void_p(r["dtentr"].data_ptr()),
                                       C.c_void_p(r["maxsig"].data_ptr()), 1))
 
-    def compute_accelerations(self, sph=True):
+    def compute_accelerations(self, sph=True, gravity=True):
         """accel.c:27 force part for this rank's segment, with the two exchange steps."""
         self.exchange_state()
-        self.gravity()
+        if gravity:
+            self.gravity()
+        else:
+            self.fp.force_treebuild()
         if sph and self.ngas > 0:
             self.density_and_exchange()
             self.hydro()
