@@ -5,6 +5,8 @@
 #include <algorithm>
 
 gl_dparams gl_make_dparams(const gl_ctx *c);
+template <class T> static int get(gl_ctx *c, T *dst, const DBuf<T> &src, size_t cnt, int where, const char *what);
+static int finish_get(gl_ctx *c, int evslot);
 
 extern "C" int gl_create(gl_ctx **out, int device, long long max_part)
 {
@@ -46,6 +48,7 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->tgt_sph.release(); c->tgt_flag.release(); c->tgt_gas.release(); c->o_acc.release(); c->o_oldacc.release();
   c->o_numngb.release(); c->o_density.release(); c->o_dhsml.release(); c->o_divvel.release(); c->o_curlvel.release();
   c->o_pressure.release(); c->o_sinkrho.release(); c->o_sinkentr.release(); c->o_sinkvel.release(); c->o_hacc.release();
+  c->o_pot.release();
   c->o_dtentr.release(); c->o_maxsig.release(); c->o_gravcost.release(); c->o_denspairs.release();
   c->o_hydropairs.release(); c->d_counter.release(); c->h_q.release(); c->h_r.release();
   c->e_rng.release(); c->n_child.release(); c->fat_p.release(); c->fat_i.release(); c->fat_state.release();
@@ -296,6 +299,20 @@ extern "C" int gl_gravity_tree(gl_ctx *c)
   bool rebuilt = c->tree_flag || !c->tree_valid;
   if(rebuilt) c->tgt_dirty = true;
   return glg_gravity(c);
+}
+
+extern "C" int gl_compute_potential(gl_ctx *c)
+{
+  cudaSetDevice(c->device);
+  return glg_potential(c);
+}
+
+extern "C" int gl_get_potential(gl_ctx *c, double *potential, int where)
+{
+  cudaSetDevice(c->device);
+  cudaEventRecord(c->ev[10], c->stream);
+  if(get(c, potential, c->o_pot, (size_t) c->n, where, "Potential")) return 1;
+  return finish_get(c, 10);
 }
 
 extern "C" int gl_density(gl_ctx *c)

@@ -22,14 +22,14 @@ struct GravTarget
   double x, y, z, aold, soft;
 };
 
-template <bool BH>
+template <bool BH, bool POT>
 __global__ void __launch_bounds__(GL_BLOCK)
 k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	       const double4 *__restrict__ e_A, const double4 *__restrict__ e_B, const double2 *__restrict__ e_C,
 	       const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
 	       const int *__restrict__ perm, const double *__restrict__ in_oldacc, double *__restrict__ o_acc,
-	       double *__restrict__ o_oldacc, float *__restrict__ o_gravcost, unsigned long long *__restrict__ counter,
-	       gl_dparams par)
+	       double *__restrict__ o_oldacc, float *__restrict__ o_gravcost, double *__restrict__ o_pot,
+	       unsigned long long *__restrict__ counter, gl_dparams par)
 {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long) blockDim.x + threadIdx.x) >> 5;
@@ -117,7 +117,25 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 	  const float rinv = rsqrtf(r2f);
 	  const float r = (r2f > 0.f) ? r2f * rinv : 0.f;
 	  float fac;
-	  if(r >= hf)
+	  if(POT)
+	    {
+	      // forcetree.c:3497-3511: -m/r outside the softening length, spline potential wp inside
+	      if(r >= hf)
+		fac = -mf * rinv;
+	      else
+		{
+		  const float hinv = 1.0f / hf;
+		  const float u = r * hinv;
+		  float wp;
+		  if(u < 0.5f)
+		    wp = -2.8f + u * u * (5.333333333333f + u * u * (6.4f * u - 9.6f));
+		  else
+		    wp = -3.2f + 0.066666666667f / u + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u)));
+		  fac = mf * hinv * wp;
+		}
+	      ax += (double) fac;
+	    }
+	  else if(r >= hf)
 	    fac = mf * rinv * rinv * rinv;
 	  else
 	    {
@@ -130,14 +148,23 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 		fac = mf * h3inv * (21.333333333333f - 48.0f * u + 38.4f * u * u - 10.666666666667f * u * u * u -
 				    0.066666666667f / (u * u * u));
 	    }
-	  const double fd = (double) fac;
-	  ax = fma(dx, fd, ax);
-	  ay = fma(dy, fd, ay);
-	  az = fma(dz, fd, az);
+	  if(!POT)
+	    {
+	      const double fd = (double) fac;
+	      ax = fma(dx, fd, ax);
+	      ay = fma(dy, fd, ay);
+	      az = fma(dz, fd, az);
+	    }
 	  if(A.w > 0) ninter++;	// forcetree.c:2214
 	}
     }
-  if(live)
+  if(live && POT)
+    {
+      // potential.c:169-184: remove the self term with All.SofteningTable, then x G (the Lambda term of :235 is 0 here)
+      const double m_i = s_pm[p].w;
+      o_pot[pin] = __dmul_rn(__dadd_rn(ax, __ddiv_rn(m_i, par.softtab[ptype])), par.G);
+    }
+  if(live && !POT)
     {
       // gravtree.c:388-403: OldAcc from the un-scaled acceleration, then x G (+ the Lambda term, :405-411)
       const double old = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
@@ -149,7 +176,7 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
     }
   // interaction total (timings.txt "ia/part", gravtree.c:822)
   unsigned long long tot = (unsigned long long) __reduce_add_sync(0xffffffffu, live ? ninter : 0);
-  if(lane == 0 && tot) atomicAdd(&counter[0], tot);
+  if(lane == 0 && tot && !POT) atomicAdd(&counter[0], tot);
 }
 
 int glg_gravity(gl_ctx *c)
@@ -173,15 +200,15 @@ int glg_gravity(gl_ctx *c)
     {
       int grid = gl_grid(nt, GL_BLOCK);
       if(c->par.ErrTolTheta != 0)
-	k_gravity_walk<true><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p,
+	k_gravity_walk<true, false><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p,
 							      c->e_B.p, c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
 							      c->perm.p, c->in_oldacc.p, c->o_acc.p, c->o_oldacc.p,
-							      c->o_gravcost.p, c->d_counter.p, dp);
+							      c->o_gravcost.p, nullptr, c->d_counter.p, dp);
       else
-	k_gravity_walk<false><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p,
+	k_gravity_walk<false, false><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p,
 							       c->e_B.p, c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
 							       c->perm.p, c->in_oldacc.p, c->o_acc.p, c->o_oldacc.p,
-							       c->o_gravcost.p, c->d_counter.p, dp);
+							       c->o_gravcost.p, nullptr, c->d_counter.p, dp);
       GL_LAUNCH_COUNT(c);
     }
   cudaEventRecord(c->ev[1], c->stream);
@@ -197,5 +224,44 @@ int glg_gravity(gl_ctx *c)
   GL_CUDA(c, cudaMemcpyAsync(c->in_oldacc.p, c->o_oldacc.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   // gravtree.c:396-397: switch to the relative criterion for all following force computations
   if(c->par.TypeOfOpeningCriterion == 1) c->par.ErrTolTheta = 0;
+  return 0;
+}
+
+// compute_potential (potential.c:22): the same walk and opening decisions, accumulating -m/r (or the spline
+// potential) for ALL particles; the self term is removed with All.SofteningTable as potential.c:176 does.
+int glg_potential(gl_ctx *c)
+{
+  if(!c->have_par) return c->fail("compute_potential: gl_set_params not called");
+  if(c->n <= 0) return c->fail("compute_potential: no particles loaded");
+  if(c->tree_flag || !c->tree_valid)	// potential.c:40-52
+    if(glt_build(c)) return 1;
+  // potential.c:54 loops over all particles, not the active list
+  const long long keep = c->n_tgt_in;
+  c->n_tgt_in = -1;
+  c->tgt_dirty = true;
+  if(gl_prepare_targets(c)) return 1;
+  long long n = c->n, nt = c->n_tgt;
+  GL_CUDA(c, c->o_pot.ensure(n));
+  GL_CUDA(c, c->d_counter.ensure(16));
+  gl_dparams dp = gl_make_dparams(c);
+  cudaEventRecord(c->ev[0], c->stream);
+  int grid = gl_grid(nt, GL_BLOCK);
+  if(c->par.ErrTolTheta != 0)
+    k_gravity_walk<true, true><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p, c->e_B.p,
+								c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->perm.p, c->in_oldacc.p,
+								nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp);
+  else
+    k_gravity_walk<false, true><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p, c->e_B.p,
+								 c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->perm.p, c->in_oldacc.p,
+								 nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp);
+  GL_LAUNCH_COUNT(c);
+  cudaEventRecord(c->ev[1], c->stream);
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, cudaGetLastError());
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->st.ms_potential = ms;
+  c->n_tgt_in = keep;
+  c->tgt_dirty = true;
   return 0;
 }

@@ -62,6 +62,7 @@ struct gl_dparams
 {
   double theta, errtolforceacc;
   double soft[6];		// ForceSoftening
+  double softtab[6];		// SofteningTable
   double G, lambda_fac;
   double desnumngb, maxdev, bhfac, mingashsml;
   double artvisc, timebase_interval;
@@ -132,6 +133,7 @@ struct gl_ctx
   DBuf<double> o_acc, o_oldacc, o_numngb, o_density, o_dhsml, o_divvel, o_curlvel, o_pressure, o_sinkrho,
     o_sinkentr, o_sinkvel, o_hacc, o_dtentr, o_maxsig;
   DBuf<float> o_gravcost;
+  DBuf<double> o_pot;
   DBuf<int> o_denspairs, o_hydropairs;
   DBuf<unsigned long long> d_counter;	// [0] interactions, [1] max passes, [2] error flag
   // ---- hydro source records (sorted order) ----
@@ -169,6 +171,7 @@ int glt_update_hmax(gl_ctx *c);
 int glt_get_nodes(gl_ctx *c, double *table, long long cap);
 // gl_gravity.cu
 int glg_gravity(gl_ctx *c);
+int glg_potential(gl_ctx *c);
 // gl_sph.cu
 int gls_density(gl_ctx *c);
 int gls_hydro(gl_ctx *c);

@@ -293,6 +293,7 @@ gl_dparams gl_make_dparams(const gl_ctx *c)
   d.theta = c->par.ErrTolTheta;
   d.errtolforceacc = c->par.ErrTolForceAcc;
   for(int i = 0; i < 6; i++) d.soft[i] = c->par.ForceSoftening[i];
+  for(int i = 0; i < 6; i++) d.softtab[i] = c->par.SofteningTable[i];
   d.G = c->par.G;
   d.lambda_fac = c->par.OmegaLambdaHubble2;
   d.desnumngb = c->par.DesNumNgb;

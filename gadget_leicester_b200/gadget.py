@@ -179,6 +179,13 @@ class ForcePath:
         """accel.c:27 (force part): gravity (twice at Ti_Current==0), density, hmax, hydro."""
         self._chk(self._lib.gl_compute_accelerations(self._ctx, int(mode)))
 
+    def compute_potential(self):
+        """potential.c:22: P[].p.Potential for all particles with the current tree / OldAcc / criterion."""
+        self._chk(self._lib.gl_compute_potential(self._ctx))
+        pot = np.zeros(self.N)
+        self._chk(self._lib.gl_get_potential(self._ctx, L._ptr(pot), 0))
+        return pot
+
     # device-resident variants used by bench.py's `value` leg (no result download)
     def gravity_tree_nocopy(self):
         self._chk(self._lib.gl_gravity_tree(self._ctx))

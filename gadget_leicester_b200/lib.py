@@ -33,13 +33,14 @@ class GLParams(C.Structure):
         ("Ti_Current", C.c_int),
         ("ComovingIntegrationOn", C.c_int),
         ("OmegaLambdaHubble2", C.c_double),
+        ("SofteningTable", C.c_double * 6),
     ]
 
 
 class GLStats(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "ms_keys_sort", "ms_treebuild", "ms_moments", "ms_gravity_walk", "ms_density", "ms_hmax", "ms_hydro",
-        "ms_h2d", "ms_d2h")] + [(k, C.c_longlong) for k in (
+        "ms_h2d", "ms_d2h", "ms_potential")] + [(k, C.c_longlong) for k in (
             "interactions", "density_targets", "density_passes_max", "hydro_targets", "numnodes", "numentries",
             "density_fat_targets", "kernel_launches")]
 
@@ -57,7 +58,7 @@ EXPORTS = [
     "gl_create", "gl_destroy", "gl_last_error", "gl_set_params", "gl_stream", "gl_load_particles", "gl_set_oldacc",
     "gl_set_hsml", "gl_set_sph_state", "gl_domain_find_extent", "gl_domain_set_extent", "gl_peano_keys", "gl_peano_hilbert_order",
     "gl_peano_hilbert_key", "gl_morton_key", "gl_force_treebuild", "gl_get_nodes", "gl_set_targets",
-    "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations",
+    "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations", "gl_compute_potential", "gl_get_potential",
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
 ]
@@ -99,7 +100,8 @@ def load_library():
     lib.gl_force_treebuild.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.gl_get_nodes.argtypes = [vp, c_double_p, C.c_longlong]
     lib.gl_set_targets.argtypes = [vp, vp, C.c_longlong, C.c_int]
-    for f in ("gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force"):
+    lib.gl_get_potential.argtypes = [vp, vp, C.c_int]
+    for f in ("gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_potential"):
         getattr(lib, f).argtypes = [vp]
     lib.gl_compute_accelerations.argtypes = [vp, C.c_int]
     lib.gl_set_tree_reconstruct_flag.argtypes = [vp, C.c_int]
@@ -132,6 +134,7 @@ def make_params(p):
     g.G = p["G"]
     for i in range(6):
         g.ForceSoftening[i] = 2.8 * p["Softening"][i]        # gravtree.c:881-882
+        g.SofteningTable[i] = p["Softening"][i]
     g.MinGasHsml = p["MinGasHsmlFractional"] * g.ForceSoftening[0]  # gravtree.c:884
     g.Timebase_interval = p["Timebase_interval"]
     g.Ti_Current = int(p["Ti_Current"])

@@ -42,6 +42,7 @@ typedef struct gl_params
   int Ti_Current;		/* All.Ti_Current */
   int ComovingIntegrationOn;	/* must be 0: the comoving factors of hydra.c:196-206 are not implemented */
   double OmegaLambdaHubble2;	/* All.OmegaLambda*All.Hubble^2, gravtree.c:405-411 (0 for the shipped run) */
+  double SofteningTable[6];	/* All.SofteningTable[], only for the self-potential term of potential.c:176 */
 } gl_params;
 
 /* ---- life cycle ---------------------------------------------------------------- */
@@ -105,11 +106,14 @@ int gl_density(gl_ctx * ctx);		/* density.c:89   (with the Hsml iteration) */
 int gl_force_update_hmax(gl_ctx * ctx);	/* forcetree.c:1661 */
 int gl_hydro_force(gl_ctx * ctx);	/* hydra.c:145 */
 int gl_compute_accelerations(gl_ctx * ctx, int mode);	/* accel.c:27, force part (:61-106) */
+int gl_compute_potential(gl_ctx * ctx);	/* potential.c:22 (all particles) */
 void gl_set_tree_reconstruct_flag(gl_ctx * ctx, int flag);	/* TreeReconstructFlag, domain.c:135 */
 
 /* ---- results (arrays indexed like P[], n elements; NULL pointers are skipped) ------------------- */
 /* gravity: P.g.GravAccel (already x G), P.OldAcc, P.GravCost (gravtree.c:392-403, forcetree.c:2282) */
 int gl_get_gravity(gl_ctx * ctx, double *gravaccel3, double *oldacc, float *gravcost, int where);
+/* P.p.Potential (already x G, self term removed as potential.c:176 does) */
+int gl_get_potential(gl_ctx * ctx, double *potential, int where);
 /* density: P.Hsml, P.n.NumNgb, SphP.d.Density, .h.DhsmlDensityFactor, .v.DivVel, .r.CurlVel, .Pressure;
  * sink/dust targets: b1/d1 density, b2/d2 entropy, b3/d3 gas velocity (density.c:944-988, :520-546) */
 int gl_get_density(gl_ctx * ctx, double *hsml, double *numngb, double *density, double *dhsml, double *divvel,
@@ -124,7 +128,7 @@ int gl_get_pair_counts(gl_ctx * ctx, int *dens_pairs, int *hydro_pairs, int wher
 /* ---- statistics --------------------------------------------------------------------------------- */
 typedef struct gl_stats
 {
-  double ms_keys_sort, ms_treebuild, ms_moments, ms_gravity_walk, ms_density, ms_hmax, ms_hydro, ms_h2d, ms_d2h;
+  double ms_keys_sort, ms_treebuild, ms_moments, ms_gravity_walk, ms_density, ms_hmax, ms_hydro, ms_h2d, ms_d2h, ms_potential;
   long long interactions;	/* sum of P.GravCost over targets of the last gl_gravity_tree */
   long long density_targets, density_passes_max, hydro_targets;
   long long numnodes, numentries;

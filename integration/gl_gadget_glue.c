@@ -51,6 +51,7 @@ static void gl_sync_params(void)
   p.Ti_Current = All.Ti_Current;
   p.ComovingIntegrationOn = All.ComovingIntegrationOn;
   p.OmegaLambdaHubble2 = All.OmegaLambda * All.Hubble * All.Hubble;
+  for(i = 0; i < 6; i++) p.SofteningTable[i] = All.SofteningTable[i];
   if(gl_set_params(GL, &p)) gl_fail("gl_set_params");
 }
 

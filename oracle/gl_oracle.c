@@ -14,7 +14,7 @@
  * (baseline x86-64, no FMA) - the same FP64 rounding as the reference build of SURVEY.md 8(c).
  *
  * usage: gl_oracle <in.glin> <out.glou> "<ops>"   (same container formats and op letters as
- *        oracle/refbuild/ref_harness.c: T S D R G U H N C A)
+ *        oracle/refbuild/ref_harness.c: T S D R G U H N C K P A)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -49,6 +49,7 @@ static int TypeOfOpeningCriterion, DesNumNgb, Ti_Current;
 static int N, Ngas;
 static double *Pos, *Vel, *Mass, *Hsml, *OldAcc, *Entropy, *DtEntropyIn;
 static int *Type, *ID, *TimeBin;
+static double *Potential;
 static double *GravAccel, *GravCost, *NumNgb, *Density, *DhsmlDensityFactor, *DivVel, *CurlVel, *Pressure, *SinkDensity,
   *SinkEntropy, *SinkGasVel, *HydroAccel, *DtEntropy, *MaxSignalVel;
 
@@ -417,6 +418,111 @@ static void gravity_tree(void)	/* gravtree.c:27-828 */
   if(TypeOfOpeningCriterion == 1) ErrTolTheta = 0;	/* :396-397 */
   for(i = 0; i < N; i++)
     for(j = 0; j < 3; j++) GravAccel[3 * i + j] *= G;	/* :400-403 */
+}
+
+/* ---------------------------------------------------------------- potential ---- */
+static void force_treeevaluate_potential(int target)	/* forcetree.c:3217-3543, mode 0 */
+{
+  int no, ptype = Type[target];
+  double r2, dx, dy, dz, mass, r, u, h = 0, h_inv, wp, pot = 0;
+  double pos_x = Pos[3 * target], pos_y = Pos[3 * target + 1], pos_z = Pos[3 * target + 2];
+  double aold = ErrTolForceAcc * OldAcc[target], soft = Hsml[target];
+  struct node *nop = 0;
+  no = N;
+  while(no >= 0)
+    {
+      if(no < N)
+	{
+	  dx = Pos[3 * no] - pos_x; dy = Pos[3 * no + 1] - pos_y; dz = Pos[3 * no + 2] - pos_z;
+	  mass = Mass[no];
+	}
+      else
+	{
+	  nop = &Nodes[no - N];
+	  mass = nop->mass;
+	  if(!nop->multiple && mass)
+	    {
+	      no = nop->nextnode;
+	      continue;
+	    }
+	  dx = nop->s[0] - pos_x; dy = nop->s[1] - pos_y; dz = nop->s[2] - pos_z;
+	}
+      r2 = dx * dx + dy * dy + dz * dz;
+      if(no < N)
+	{
+	  h = (ptype == 0) ? soft : ForceSoftening[ptype];
+	  if(Type[no] == 0)
+	    {
+	      if(h < Hsml[no]) h = Hsml[no];
+	    }
+	  else if(h < ForceSoftening[Type[no]])
+	    h = ForceSoftening[Type[no]];
+	  no = Nextnode[no];
+	}
+      else
+	{
+	  if(ErrTolTheta)
+	    {
+	      if(nop->len * nop->len > r2 * ErrTolTheta * ErrTolTheta)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	    }
+	  else
+	    {
+	      if(mass * nop->len * nop->len > r2 * r2 * aold)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	      if(fabs(nop->center[0] - pos_x) < 0.60 * nop->len)
+		if(fabs(nop->center[1] - pos_y) < 0.60 * nop->len)
+		  if(fabs(nop->center[2] - pos_z) < 0.60 * nop->len)
+		    {
+		      no = nop->nextnode;
+		      continue;
+		    }
+	    }
+	  h = (ptype == 0) ? soft : ForceSoftening[ptype];
+	  if(h < nop->maxsoft)
+	    {
+	      h = nop->maxsoft;
+	      if(r2 < h * h)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	    }
+	  no = nop->sibling;
+	}
+      r = sqrt(r2);
+      if(r >= h)
+	pot += (-mass / r);
+      else
+	{
+	  h_inv = 1.0 / h;
+	  u = r * h_inv;
+	  if(u < 0.5)
+	    wp = -2.8 + u * u * (5.333333333333 + u * u * (6.4 * u - 9.6));
+	  else
+	    wp = -3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)));
+	  pot += (mass * h_inv * wp);
+	}
+    }
+  Potential[target] = pot;
+}
+
+static void compute_potential(void)	/* potential.c:22-250 */
+{
+  int i;
+  if(TreeReconstructFlag) force_treebuild();
+  for(i = 0; i < N; i++) force_treeevaluate_potential(i);
+  for(i = 0; i < N; i++)
+    {
+      Potential[i] += Mass[i] / SofteningTable[Type[i]];	/* remove self-potential, potential.c:176 */
+      Potential[i] *= G;	/* :184 */
+    }
 }
 
 /* ---------------------------------------------------------------- neighbour search ---- */
@@ -914,6 +1020,7 @@ int main(int argc, char **argv)
   MinGasHsml = par[P_MINGASHSMLFRAC] * ForceSoftening[0];	/* gravtree.c:884 */
   Timebase_interval = par[P_TIMEBASE_INTERVAL]; Ti_Current = (int) par[P_TI_CURRENT]; BlackHoleNgbFactor = par[P_BHNGBFACTOR];
 #define AL(ptr, cnt) ptr = calloc((size_t) (cnt) + 1, sizeof(*ptr))
+  AL(Potential, N);
   AL(GravAccel, 3 * (size_t) N); AL(GravCost, N); AL(NumNgb, N); AL(Density, N); AL(DhsmlDensityFactor, N); AL(DivVel, N);
   AL(CurlVel, N); AL(Pressure, N); AL(SinkDensity, N); AL(SinkEntropy, N); AL(SinkGasVel, 3 * (size_t) N); AL(HydroAccel, 3 * (size_t) N);
   AL(DtEntropy, N); AL(MaxSignalVel, N); AL(Nextnode, N); AL(Father, N); AL(MortonKey, N); AL(Ngblist, N); AL(DensPairs, N);
@@ -950,10 +1057,16 @@ int main(int argc, char **argv)
 	    case 'N': dump_nodes(prefix); break;
 	    case 'C': pair_counts(prefix); break;
 	    case 'K': dump_keys(prefix); break;
+	    case 'P': compute_potential(); break;
 	    default: fprintf(stderr, "unknown op %c\n", op); return 2;
 	    }
 	  dt = now() - t0;
-	  if(strchr("TDGUH", op)) put(prefix, "time", 'd', 1, 1, &dt);
+	  if(strchr("TDGUHP", op)) put(prefix, "time", 'd', 1, 1, &dt);
+	  if(op == 'P')
+	    {
+	      put(prefix, "id", 'i', N, 1, ID);
+	      put(prefix, "Potential", 'd', N, 1, Potential);
+	    }
 	  if(strchr("GDHS", op)) dump(prefix, op);
 	  if(op == 'D') { double pp = density_passes; put(prefix, "passes", 'd', 1, 1, &pp); }
 	  if(op == 'G')

@@ -21,6 +21,7 @@
  *     H  hydro_force()                        (accel.c:106)
  *     N  dump the node table of the current tree
  *     C  integer pair counts at the current Hsml via ngb_treefind_variable / _pairs
+ *     P  compute_potential()                  (potential.c:22; run.c:74 at statistics times)
  *     K  Peano-Hilbert and Morton key of every particle (peano_and_morton_key, peano.c:335)
  *     A  compute_accelerations-order block:  R G D U H   (accel.c:61-106 without sub-grid physics)
  *   every op that computes dumps its outputs under the prefix "<k>_<op>_" with k the
@@ -387,10 +388,21 @@ int main(int argc, char **argv)
 	    case 'N': dump_nodes(prefix); break;
 	    case 'C': pair_counts(prefix); break;
 	    case 'K': dump_keys(prefix); break;
+	    case 'P': compute_potential(); break;
 	    default: fprintf(stderr, "unknown op %c\n", op); return 2;
 	    }
 	  dt = now() - t0;
-	  if(strchr("TDGUH", op)) put(prefix, "time", 'd', 1, 1, &dt);
+	  if(strchr("TDGUHP", op)) put(prefix, "time", 'd', 1, 1, &dt);
+	  if(op == 'P')
+	    {
+	      long long q;
+	      double *pt = malloc(sizeof(double) * NumPart);
+	      int *ids = malloc(sizeof(int) * NumPart);
+	      for(q = 0; q < NumPart; q++) { pt[q] = P[q].p.Potential; ids[q] = (int) P[q].ID; }
+	      put(prefix, "id", 'i', NumPart, 1, ids);
+	      put(prefix, "Potential", 'd', NumPart, 1, pt);
+	      free(pt); free(ids);
+	    }
 	  if(strchr("GDHS", op)) dump_particles_out(prefix, op);
 	  if(op == 'G')
 	    {

@@ -21,10 +21,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from gadget_leicester_b200 import ics  # noqa: E402
 import util  # noqa: E402
 
-OPS = "K T S D R G G D U H N C"
+OPS = "K T S D R G G D U H N C P"
 # stage prefixes of OPS (position_op_)
 STAGES = dict(keys="0_K_", tree0="1_T_", hsml0="2_S_", dens1="3_D_", grav1="5_G_", grav2="6_G_", dens2="7_D_",
-              hydro="9_H_", nodes="10_N_", pairs="11_C_")
+              hydro="9_H_", nodes="10_N_", pairs="11_C_", pot="12_P_")
 
 CASES = {
     "cube_2k": lambda: (ics.cube(2000, seed=11), ics.default_params()),

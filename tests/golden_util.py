@@ -6,9 +6,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN_DIR = os.path.join(HERE, "golden")
-OPS = "K T S D R G G D U H N C"
+OPS = "K T S D R G G D U H N C P"
 STAGES = dict(keys="0_K_", tree0="1_T_", hsml0="2_S_", dens1="3_D_", grav1="5_G_", grav2="6_G_", dens2="7_D_",
-              hydro="9_H_", nodes="10_N_", pairs="11_C_")
+              hydro="9_H_", nodes="10_N_", pairs="11_C_", pot="12_P_")
 
 
 def golden_names():

@@ -141,6 +141,13 @@ def _check_sequence(FP, ps, par, R, label):
                 e = util.rel_err_vec(h[k][:ngas], ref)
             report.append(util.summarize(label + " " + k, e))
             assert e.max() <= 1e-7, report[-1]
+    # ---- compute_potential (potential.c:22): same walk, same decisions, -m/r sums ----
+    if "pot__Potential" in R:
+        fp.set_OldAcc(R["grav2__OldAcc"])
+        pot = fp.compute_potential()
+        e = util.rel_err_vec(pot, R["pot__Potential"])
+        report.append(util.summarize(label + " Potential", e))
+        assert np.percentile(e, 99) <= TOL_ACC_P99 and np.median(e) <= TOL_ACC_MEDIAN, report[-1]
     fp.close()
     print("\n".join(report))
 
