@@ -39,6 +39,42 @@ def partition_range(n, world, rank):
     return lo, hi, m
 
 
+def work_balanced_ranges(cost, world):
+    """domain_findSplit_work_balanced (domain.c:1075-1113) for one contiguous segment per GPU: cut the
+    Peano-Hilbert ordered list where the running cost crosses k/world of the total.  `cost` is the reference's
+    per-particle weight (1 + GravCost) / 2^TimeBin (domain.c:378-384), in Peano-Hilbert order (numpy array).
+    Returns a list of (lo, hi)."""
+    c = np.cumsum(np.asarray(cost, dtype=np.float64))
+    n = c.size
+    tot = c[-1] if n else 0.0
+    cuts = [0]
+    for k in range(1, world):
+        cuts.append(int(np.searchsorted(c, tot * k / world * (1 + 1e-12), side="right")) if n else 0)
+    cuts.append(n)
+    for k in range(1, len(cuts)):
+        cuts[k] = max(cuts[k], cuts[k - 1])
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
+
+
+def gather_ragged(own, ranges, group=None):
+    """all-gather segments of different lengths: pad every segment to the longest one, gather, then drop the
+    padding.  ranges: list of (lo, hi) for all ranks."""
+    world = len(ranges)
+    if world == 1:
+        return own
+    mmax = max(hi - lo for lo, hi in ranges)
+    n = ranges[-1][1]
+    send = own
+    if own.shape[0] != mmax:
+        send = torch.zeros((mmax,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+        send[: own.shape[0]] = own
+    full = torch.empty((world * mmax,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+    dist.all_gather_into_tensor(full, send.contiguous(), group=group)
+    if all(hi - lo == mmax for lo, hi in ranges[:-1]):
+        return full[:n]            # only the last segment is short: the padding sits at the very end
+    return torch.cat([full[r * mmax: r * mmax + (hi - lo)] for r, (lo, hi) in enumerate(ranges)], dim=0)
+
+
 def gather_padded(own, n, m, group=None):
     """all-gather segments of m rows (the last one zero-padded) and return the first n rows.
     own: [<=m, ...] tensor of this rank's segment.  Works with NCCL (cuda) and gloo (cpu)."""
@@ -72,15 +108,22 @@ class DistributedForcePath:
         self.full = {}
 
     # -- set-up: the analogue of domain_Decomposition + peano_hilbert_order (domain.c:100, peano.c:25) --------
-    def decompose(self, ps):
+    def decompose(self, ps, cost=None):
         """ps: the FULL particle set as host numpy arrays (every rank passes the same set).  Orders it along the
-        Peano-Hilbert curve (gas block first, like the reference) and keeps this rank's segment on the GPU."""
+        Peano-Hilbert curve (gas block first, like the reference) and keeps this rank's segment on the GPU.
+        cost: optional per-particle work weight in input order, (1 + GravCost) / 2^TimeBin as domain.c:378-384;
+        None = equal counts (what the reference gets on its first step, GravCost = 1 for everybody)."""
         n = ps["pos"].shape[0]
         ngas = int((ps["type"] == 0).sum())
         self.fp.load(ps)
         order = self.fp.peano_hilbert_order(ngas)
         self.n, self.ngas = n, ngas
-        lo, hi, m = partition_range(n, self.world, self.rank)
+        if cost is None:
+            self.ranges = [partition_range(n, self.world, r)[:2] for r in range(self.world)]
+        else:
+            self.ranges = work_balanced_ranges(np.asarray(cost)[order], self.world)
+        lo, hi = self.ranges[self.rank]
+        m = max(b - a for a, b in self.ranges)
         self.lo, self.hi, self.m = lo, hi, m
         seg = order[lo:hi]
         dev = self.device
@@ -113,6 +156,7 @@ class DistributedForcePath:
         self.fp.load_device(n, [ps[k].data_ptr() for k in STATE_FIELDS])
         order = torch.empty(n, dtype=torch.int32, device=dev)
         self.fp.peano_hilbert_order_device(ngas, order.data_ptr())
+        self.ranges = [partition_range(n, self.world, r)[:2] for r in range(self.world)]
         lo, hi, m = partition_range(n, self.world, self.rank)
         self.lo, self.hi, self.m = lo, hi, m
         seg = order[lo:hi].long()
@@ -135,7 +179,7 @@ class DistributedForcePath:
     def exchange_state(self):
         """Exchange step 1: replicate the sources (NCCL all-gather over NVLink)."""
         for k in STATE_FIELDS:
-            self.full[k] = gather_padded(self.own[k], self.n, self.m, self.group).contiguous()
+            self.full[k] = gather_ragged(self.own[k], self.ranges, self.group).contiguous()
         self._sync_lib()
         f = self.full
         ptrs = [f[k].data_ptr() for k in STATE_FIELDS]
@@ -161,7 +205,7 @@ class DistributedForcePath:
                                         p(r["curlvel"]), p(r["pressure"]), None, None, None, 1))
         self.own["hsml"] = r["hsml"][self.lo:self.hi].clone()
         if self.world > 1:
-            g = {k: gather_padded(r[k][self.lo:self.hi], self.n, self.m, self.group).contiguous() for k in SPH_FIELDS}
+            g = {k: gather_ragged(r[k][self.lo:self.hi], self.ranges, self.group).contiguous() for k in SPH_FIELDS}
             self._sync_lib()
             self.fp._chk(lib.gl_set_hsml(ctx, p(g["hsml"]), 1))
             self.fp._chk(lib.gl_set_sph_state(ctx, p(g["density"]), p(g["pressure"]), p(g["dhsml"]), p(g["divvel"]),

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from gadget_leicester_b200 import ics, aos
-from gadget_leicester_b200.multigpu import partition_range, gather_padded
+from gadget_leicester_b200.multigpu import partition_range, gather_padded, gather_ragged, work_balanced_ranges
 from oracle import glio
 
 
@@ -63,6 +63,22 @@ def test_partition_covers_everything():
             assert all(hi - lo <= m for lo, hi, m in segs)
 
 
+def test_work_balanced_split_equalises_cost():
+    """domain_findSplit_work_balanced (domain.c:1075): contiguous segments of (nearly) equal summed cost."""
+    rng = np.random.default_rng(4)
+    gravcost = rng.integers(50, 4000, size=100003).astype(np.float64)
+    timebin = rng.integers(0, 3, size=gravcost.size)
+    cost = (1 + gravcost) / 2.0 ** timebin            # domain.c:378-384
+    for world in (1, 2, 3, 8):
+        rg = work_balanced_ranges(cost, world)
+        assert rg[0][0] == 0 and rg[-1][1] == cost.size and all(a[1] == b[0] for a, b in zip(rg, rg[1:]))
+        seg = np.array([cost[a:b].sum() for a, b in rg])
+        assert seg.max() - seg.min() <= 2 * cost.max()
+    # equal weights reproduce the equal-count split of the first step (GravCost = 1, init.c:252)
+    rg = work_balanced_ranges(np.ones(1000), 4)
+    assert [b - a for a, b in rg] == [250, 250, 250, 250]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -80,6 +96,12 @@ def _worker(rank, world, port, n, q):
     got = gather_padded(full[lo:hi].clone(), n, m)
     ids = gather_padded(torch.arange(lo, hi, dtype=torch.int32), n, m)
     ok = bool((got == full).all()) and bool((ids == torch.arange(n, dtype=torch.int32)).all())
+    # ragged (work-balanced) segments
+    cut = max(1, n // 3)
+    ranges = [(0, cut), (cut, n)]
+    a, b = ranges[rank]
+    got2 = gather_ragged(full[a:b].clone(), ranges)
+    ok = ok and bool((got2 == full).all())
     # the "unconverged targets remaining" reduction of density.c:656 in NCCL/gloo form
     left = torch.tensor([rank + 1], dtype=torch.int64)
     dist.all_reduce(left)
