@@ -41,7 +41,8 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define BOX_SLACK 1.0000000001
 #define CAND_CAP 256		// staged candidates per warp
 #define SPH_WARPS 4
-#define STK_CAP 1024
+#define STK_CAP 512
+#define LT_MIN_ACTIVE 12	// with at least this many active targets a warp runs lane = target (see density_chunk_lt)
 #define FAT_THRESH 4096	// neighbours above which a target leaves the warp path
 #define FAT_MAX 64
 #define STK_RESERVE 160	// 7 pushes per level x 21 levels: pure depth-first continuation never overflows
@@ -93,7 +94,8 @@ struct WarpStage
 #ifdef GL_PHASE_PROF
   unsigned long long ph[8];
 #endif
-  float fx[CAND_CAP], fy[CAND_CAP], fz[CAND_CAP], fh[CAND_CAP];	// candidate position - group centre, candidate Hsml
+  float4 cand[CAND_CAP];	// candidate position - group centre (x,y,z) and candidate Hsml (w)
+  unsigned char hl[CAND_CAP * 32];	// lane = target mode: hl[k*32 + lane] = k-th candidate that lane's target may touch
   int j[CAND_CAP];		// tree index of the candidate
   int hit[64];			// compacted "maybe" list of the current target
   int stk[STK_CAP];		// tree cells still to be examined (DFS entry index, or -(p+2) for a lone particle)
@@ -143,10 +145,7 @@ __device__ __forceinline__ int stage_range(WarpStage &S, int ncand, int a, int b
     {
       const int pos = ncand + __popc(ball & ((1u << lane) - 1));
       const float bx = (float) (pm.x - G.gcx), by = (float) (pm.y - G.gcy), bz = (float) (pm.z - G.gcz);
-      S.fx[pos] = bx;
-      S.fy[pos] = by;
-      S.fz[pos] = bz;
-      if(WANT_H) S.fh[pos] = (float) s_vh[j].w;
+      S.cand[pos] = make_float4(bx, by, bz, WANT_H ? (float) s_vh[j].w : 0.f);
       S.j[pos] = j;
       lmax = fmaxf(lmax, fmaxf(fabsf(bx), fmaxf(fabsf(by), fabsf(bz))));
     }
@@ -513,7 +512,8 @@ __device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, float lma
 	      bool hit = false;
 	      if(c < ncand)
 		{
-		  const float dx = tax - S.fx[c], dy = tay - S.fy[c], dz = taz - S.fz[c];
+		  const float4 cd = S.cand[c];
+		  const float dx = tax - cd.x, dy = tay - cd.y, dz = taz - cd.z;
 		  hit = (dx * dx + dy * dy + dz * dz) <= thr;
 		}
 	      const unsigned ball = __ballot_sync(FULL, hit);
@@ -584,6 +584,55 @@ __device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, float lma
   __syncwarp();
 }
 
+
+// Phases 2+3, lane = target.  Used while most of the warp is still active: every lane scans the staged candidates
+// (one broadcast shared-memory read per candidate, FP32 conservative filter) and notes the ones its own target may
+// touch in a private byte list; then every lane walks ITS list and adds the reference's FP64 terms straight into its
+// own accumulators - no broadcasts, no cross-lane reduction, and the neighbours arrive in tree order, i.e. in the
+// reference's own summation order.  (When few targets are left, density_chunk's target-major scheme is cheaper.)
+__device__ __forceinline__ void density_chunk_lt(WarpStage &S, int ncand, float lmax, bool todo, int lane, const GroupF &G,
+						 double px, double py, double pz, double vx, double vy, double vz, double h,
+						 int ptype, DensAcc &A, const double4 *__restrict__ s_pm,
+						 const double4 *__restrict__ s_vh, const double *__restrict__ s_entropy)
+{
+  __syncwarp();
+  float L = lmax;
+  for(int o = 16; o > 0; o >>= 1) L = fmaxf(L, __shfl_xor_sync(FULL, L, o));
+  L = fmaxf(L, G.amax);
+  const float thr = todo ? cand_threshold(G.r, L) : -1.f;
+  int nmine = 0;
+#pragma unroll 4
+  for(int c = 0; c < ncand; c++)
+    {
+      const float4 cd = S.cand[c];
+      const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
+      if(dx * dx + dy * dy + dz * dz <= thr)
+	{
+	  S.hl[nmine * 32 + lane] = (unsigned char) c;
+	  nmine++;
+	}
+    }
+  const double h2 = h * h, hinv = 1.0 / h, hinv3 = hinv * hinv * hinv, hinv4 = hinv3 * hinv;
+  const int kmax = __reduce_max_sync(FULL, nmine);
+  for(int k = 0; k < kmax; k++)
+    {
+      if(k < nmine)
+	{
+	  const int j = S.j[S.hl[k * 32 + lane]];
+	  const double4 pj = gl_ld4(&s_pm[j]);
+	  // density.c:835-856: dx = pos_i - pos_j, r2 = dx*dx + dy*dy + dz*dz, r2 < h2
+	  const double dx = px - pj.x, dy = py - pj.y, dz = pz - pj.z;
+	  const double r2 = dx * dx + dy * dy + dz * dz;
+	  if(r2 < h2)
+	    {
+	      const double4 vj = gl_ld4(&s_vh[j]);
+	      density_pair(A, ptype, dx, dy, dz, r2, pj.w, hinv, hinv3, hinv4, vx, vy, vz, vj, (ptype != 0) ? __ldg(&s_entropy[j]) : 0.0);
+	    }
+	}
+    }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MIN_BLOCKS)
 k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	  double4 *__restrict__ e_B, const int2 *__restrict__ e_rng, const int *__restrict__ n_child,
@@ -648,7 +697,10 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
       const GroupF G = make_group(todo, px, py, pz, h);
       sph_collect<false>(S, lane, nentries, e_next, e_B, nullptr, e_rng, n_child, s_pm, s_vh, s_type, todo_mask, G, visits, staged,
 			 [&](int ncand, float lmax) {
-			   density_chunk(S, ncand, lmax, todo_mask, lane, G, px, py, pz, vx, vy, vz, h, ptype, A, s_pm, s_vh, s_entropy);
+			   if(__popc(todo_mask) >= LT_MIN_ACTIVE)
+			     density_chunk_lt(S, ncand, lmax, todo, lane, G, px, py, pz, vx, vy, vz, h, ptype, A, s_pm, s_vh, s_entropy);
+			   else
+			     density_chunk(S, ncand, lmax, todo_mask, lane, G, px, py, pz, vx, vy, vz, h, ptype, A, s_pm, s_vh, s_entropy);
 			 });
 
       // ---- post-processing and Hsml update, density.c:434-652 (one lane = one target) ----
@@ -1065,9 +1117,10 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 	      if(c < ncand)
 		{
 		  // conservative FP32 version of hydra.c:1266 (r2 < h_i^2 || r2 < h_j^2)
-		  const float dx = tax - S.fx[c], dy = tay - S.fy[c], dz = taz - S.fz[c];
+		  const float4 cd = S.cand[c];
+		  const float dx = tax - cd.x, dy = tay - cd.y, dz = taz - cd.z;
 		  const float r2 = dx * dx + dy * dy + dz * dz;
-		  hit = (r2 <= thr) || (r2 <= cand_threshold(S.fh[c], L));
+		  hit = (r2 <= thr) || (r2 <= cand_threshold(cd.w, L));
 		}
 	      const unsigned ball = __ballot_sync(FULL, hit);
 	      if(hit) S.hit[nh + __popc(ball & ((1u << lane) - 1))] = c;
@@ -1188,6 +1241,98 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
   __syncwarp();
 }
 
+
+// lane = target version of hydro_chunk (see density_chunk_lt)
+__device__ __forceinline__ void hydro_chunk_lt(WarpStage &S, int ncand, float lmax, bool live, int lane, const GroupF &G,
+					       const HydroTarget &T, HydroAcc &A, const double4 *__restrict__ s_pm,
+					       const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
+					       const double2 *__restrict__ h_r, double artvisc, double timebase_interval)
+{
+  __syncwarp();
+  float L = lmax;
+  for(int o = 16; o > 0; o >>= 1) L = fmaxf(L, __shfl_xor_sync(FULL, L, o));
+  L = fmaxf(L, G.amax);
+  const float thr = live ? cand_threshold(G.r, L) : -1.f;
+  int nmine = 0;
+#pragma unroll 4
+  for(int c = 0; c < ncand; c++)
+    {
+      const float4 cd = S.cand[c];
+      const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
+      const float r2 = dx * dx + dy * dy + dz * dz;
+      // conservative FP32 version of hydra.c:1266 (r2 < h_i^2 || r2 < h_j^2)
+      if(live && (r2 <= thr || r2 <= cand_threshold(cd.w, L)))
+	{
+	  S.hl[nmine * 32 + lane] = (unsigned char) c;
+	  nmine++;
+	}
+    }
+  const double h_i = T.h_i, h_i2 = h_i * h_i, hinv_i = 1.0 / h_i, hinv4_i = hinv_i * hinv_i * hinv_i * hinv_i;
+  const int kmax = __reduce_max_sync(FULL, nmine);
+  for(int k = 0; k < kmax; k++)
+    {
+      if(k < nmine)
+	{
+	  const int j = S.j[S.hl[k * 32 + lane]];
+	  const double4 pj = gl_ld4(&s_pm[j]);
+	  const double4 vj = gl_ld4(&s_vh[j]);
+	  const double dx = T.px - pj.x, dy = T.py - pj.y, dz = T.pz - pj.z;
+	  const double r2 = dx * dx + dy * dy + dz * dz;
+	  const double h_j = vj.w, mass_j = pj.w, h_j2 = h_j * h_j;
+	  if((r2 < h_i2 || r2 < h_j2) && r2 > 0)	// hydra.c:1266, :1270
+	    {
+	      const double4 q = gl_ld4(&h_q[j]);
+	      const double2 rr = __ldg(&h_r[j]);
+	      A.npairs++;
+	      const double rinv = rsqrt(r2);
+	      const double r = r2 * rinv;
+	      const double rho_j = q.x, soundspeed_j = q.w;
+	      const double dvx = T.vx - vj.x, dvy = T.vy - vj.y, dvz = T.vz - vj.z;
+	      const double vdotr2 = dx * dvx + dy * dvy + dz * dvz;	// non-comoving, hydra.c:1279-1282
+	      double dwk_i = 0, dwk_j = 0;
+	      if(r2 < h_i2)
+		{
+		  const double u = r * hinv_i;
+		  dwk_i = (u < 0.5) ? hinv4_i * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : hinv4_i * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+		}
+	      if(r2 < h_j2)
+		{
+		  const double hinv = 1.0 / h_j;
+		  const double hinv4 = hinv * hinv * hinv * hinv;
+		  const double u = r * hinv;
+		  dwk_j = (u < 0.5) ? hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+		}
+	      double vsig = T.cs_i + soundspeed_j;	// hydra.c:1502
+	      if(vsig > A.maxsig) A.maxsig = vsig;
+	      double visc = 0;
+	      if(vdotr2 < 0)
+		{
+		  const double mu_ij = vdotr2 * rinv;	// fac_mu = 1
+		  vsig -= 3 * mu_ij;
+		  if(vsig > A.maxsig) A.maxsig = vsig;
+		  const double rho_ij = 0.5 * (T.rho + rho_j);
+		  visc = 0.25 * artvisc * vsig * (-mu_ij) / rho_ij * (T.f1 + rr.x);
+		  // hydra.c:1583-1597 viscosity limiter
+		  const int ts_j = (int) rr.y;
+		  const double dt = 2 * ((T.timestep > ts_j) ? T.timestep : ts_j) * timebase_interval;
+		  if(dt > 0 && (dwk_i + dwk_j) < 0)
+		    {
+		      const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (T.mass + mass_j) * (dwk_i + dwk_j) * r * dt);
+		      visc = (visc < lim) ? visc : lim;
+		    }
+		}
+	      const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) * rinv;
+	      const double hfc = hfc_visc + mass_j * (T.p_over_rho2_i * dwk_i + q.z * dwk_j) * rinv;	// q.z = P_j/rho_j^2 x Omega_j
+	      A.a0 += (-hfc * dx);
+	      A.a1 += (-hfc * dy);
+	      A.a2 += (-hfc * dz);
+	      A.dtE += (0.5 * hfc_visc * vdotr2);
+	    }
+	}
+    }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MIN_BLOCKS)
 k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const int2 *__restrict__ e_rng,
@@ -1238,7 +1383,10 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
   const GroupF G = make_group(live, T.px, T.py, T.pz, T.h_i);
   sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, G, visits, staged,
 		    [&](int ncand, float lmax) {
-		      hydro_chunk(S, ncand, lmax, live_mask, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
+		      if(__popc(live_mask) >= LT_MIN_ACTIVE)
+			hydro_chunk_lt(S, ncand, lmax, live, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
+		      else
+			hydro_chunk(S, ncand, lmax, live_mask, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
 		    });
 #ifdef GL_PHASE_PROF
   PH_ADD(S, 5, tk0);
