@@ -39,7 +39,7 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define GL_GAMMA (7. / 5.)	// allvars.h:64
 #define GL_GAMMA_MINUS1 (GL_GAMMA - 1)
 #define BOX_SLACK 1.0000000001
-#define CAND_CAP 256		// staged candidates per warp
+#define CAND_CAP 192		// staged candidates per warp (192: four 4-warp blocks of k_hydro fit one SM's shared memory)
 #define SPH_WARPS 4
 #define STK_CAP 512
 #define LT_MIN_ACTIVE 12	// with at least this many active targets a warp runs lane = target (see density_chunk_lt)
@@ -1333,7 +1333,7 @@ __device__ __forceinline__ void hydro_chunk_lt(WarpStage &S, int ncand, float lm
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(SPH_BLOCK, SPH_MIN_BLOCKS)
+__global__ void __launch_bounds__(SPH_BLOCK, 4)
 k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const int2 *__restrict__ e_rng,
 	const int *__restrict__ n_child, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
@@ -1383,10 +1383,8 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
   const GroupF G = make_group(live, T.px, T.py, T.pz, T.h_i);
   sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, G, visits, staged,
 		    [&](int ncand, float lmax) {
-		      if(__popc(live_mask) >= LT_MIN_ACTIVE)
-			hydro_chunk_lt(S, ncand, lmax, live, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
-		      else
-			hydro_chunk(S, ncand, lmax, live_mask, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
+		      // hydro has no iteration: every warp but the last one is full, so lane = target always
+		      hydro_chunk_lt(S, ncand, lmax, live, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
 		    });
 #ifdef GL_PHASE_PROF
   PH_ADD(S, 5, tk0);
