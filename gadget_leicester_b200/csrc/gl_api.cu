@@ -2,6 +2,7 @@
 #include "gl_internal.h"
 #include <cub/cub.cuh>
 #include <thread>
+#include <chrono>
 #include <algorithm>
 
 gl_dparams gl_make_dparams(const gl_ctx *c);
@@ -659,15 +660,91 @@ extern "C" int gl_gadget_push(gl_ctx *c, void *Pv, void *SphPv, int what)
   return 0;
 }
 
+// ---- fused scatters of the pipelined drop-in call: each struct array is touched exactly once ----
+// P[]: gravity results + the P-side density results, in one pass (struct lines 1, 2 and 8 of 9)
+static void scatter_P_fused(gl_ctx *c, char *P, const double *stA, const double *stB, bool sph)
+{
+  const long long n = c->n, N_gas = c->g_ngas;
+  const gl_gadget_layout L = c->lay;
+  const double *acc = stA, *old = acc + 3 * n;
+  const float *cost = (const float *) (old + n);
+  const double *hs = stB, *nn = hs + n, *sr = nn + 6 * n, *se = sr + n, *sv = se + n;
+  const int *type = (const int *) ((const double *) c->pin + 11 * n);	// Type column of the pull staging (still valid)
+  const bool have_other = (n > N_gas);
+  parallel_for(n, [=](long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	char *pi = P + i * L.p_stride;
+	double *g = (double *) (pi + L.p_GravAccel);
+	g[0] = acc[3 * i]; g[1] = acc[3 * i + 1]; g[2] = acc[3 * i + 2];
+	*(double *) (pi + L.p_OldAcc) = old[i];
+	*(float *) (pi + L.p_GravCost) = cost[i];
+	if(!sph) continue;
+	const int ty = type[i];
+	if(!(ty == 0 || ty == 5 || ty == 2)) continue;
+	*(double *) (pi + L.p_Hsml) = hs[i];
+	*(double *) (pi + L.p_NumNgb) = nn[i];
+	*(unsigned int *) (pi + L.p_SwallowID) = 0;	// density.c:130
+	if(ty == 5 && have_other)
+	  {
+	    *(double *) (pi + L.p_SinkDensity) = sr[i];
+	    *(double *) (pi + L.p_SinkEntropy) = se[i];
+	    double *v = (double *) (pi + L.p_SinkGasVel);
+	    v[0] = sv[3 * i]; v[1] = sv[3 * i + 1]; v[2] = sv[3 * i + 2];
+	  }
+	else if(ty == 2 && have_other)
+	  {
+	    *(double *) (pi + L.p_DustDensity) = sr[i];
+	    *(double *) (pi + L.p_DustEntropy) = se[i];
+	    double *v = (double *) (pi + L.p_DustGasVel);
+	    v[0] = sv[3 * i]; v[1] = sv[3 * i + 1]; v[2] = sv[3 * i + 2];
+	  }
+      }
+  });
+}
+
+// SphP[]: density + hydro results in one pass (struct lines 0, 1, 2 of 5)
+static void scatter_SphP_fused(gl_ctx *c, char *S, const double *stB, const double *stC)
+{
+  const long long n = c->n, N_gas = c->g_ngas;
+  const gl_gadget_layout L = c->lay;
+  const double *de = stB + 2 * n, *dh = de + n, *dv = dh + n, *cu = dv + n, *pr = cu + n;
+  const double *ha = stC, *dt = ha + 3 * n, *ms = dt + n;
+  const int *type = (const int *) ((const double *) c->pin + 11 * n);
+  parallel_for(std::min(n, N_gas), [=](long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	if(type[i] != 0) continue;
+	char *si = S + i * L.sph_stride;
+	*(double *) (si + L.s_Pressure) = pr[i];
+	*(double *) (si + L.s_MaxSignalVel) = ms[i];
+	*(double *) (si + L.s_Density) = de[i];
+	*(double *) (si + L.s_DtEntropy) = dt[i];
+	double *g = (double *) (si + L.s_HydroAccel);
+	g[0] = ha[3 * i]; g[1] = ha[3 * i + 1]; g[2] = ha[3 * i + 2];
+	*(double *) (si + L.s_DhsmlDensityFactor) = dh[i];
+	*(double *) (si + L.s_DivVel) = dv[i];
+	*(double *) (si + L.s_CurlVel) = cu[i];
+      }
+  });
+}
+
 // The drop-in compute_accelerations (accel.c:27) on the reference's host arrays, software-pipelined:
-// while the GPU runs density, a host thread pulls the gravity results over PCIe on a copy stream and
-// scatters them into P[]; while hmax+hydro run, another thread does the same for the density results.
+//   GPU:   gravity | density            | hmax + hydro        |
+//   PCIe:          | D2H gravity results| D2H density results | D2H hydro results
+//   host:                               | scatter into P[]    | scatter into SphP[]
+// Every struct array is read once (pull) and written once; the P[] scatter hides behind the hydro kernel.
 extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv, long long NumPart, long long N_gas, int mode)
 {
   (void) mode;
   cudaSetDevice(c->device);
   if(!c->have_lay) return c->fail("gl_gadget_compute_accelerations: gl_gadget_bind not called");
+  const bool trace = getenv("GL_DEBUG_E2E") != nullptr;
+  auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now_ms();
+  double t_pull = 0, t_grav = 0, t_dens = 0, t_hyd = 0, t_pP = 0;
   if(gl_gadget_pull(c, Pv, SphPv, NumPart, N_gas)) return 1;
+  t_pull = now_ms();
   const long long n = c->n;
   if(ensure_pinned2(c, (size_t) n * 24 * sizeof(double))) return 1;
   if(!c->copy_stream[0])
@@ -678,25 +755,57 @@ extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv,
   if(gl_gravity_tree(c)) return 1;	// accel.c:61
   if(first)
     if(gl_gravity_tree(c)) return 1;	// accel.c:63-67
-  int rcA = 0, rcB = 0;
-  std::thread tA([&]() { rcA = push_gravity_on(c, c->copy_stream[0], stA, P); });
-  std::thread tB;
+  t_grav = now_ms();
+  // gravity results start crossing PCIe while density runs
+  cudaStream_t cs0 = c->copy_stream[0], cs1 = c->copy_stream[1];
+  GL_CUDA(c, cudaMemcpyAsync(stA, c->o_acc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, cs0));
+  GL_CUDA(c, cudaMemcpyAsync(stA + 3 * n, c->o_oldacc.p, n * sizeof(double), cudaMemcpyDeviceToHost, cs0));
+  GL_CUDA(c, cudaMemcpyAsync(stA + 4 * n, c->o_gravcost.p, n * sizeof(float), cudaMemcpyDeviceToHost, cs0));
+  if(gl_prepare_targets(c)) return 1;
+  const bool sph = c->n_tgt_sph > 0;
   int rc = 0;
-  if(gl_prepare_targets(c)) rc = 1;
-  const bool sph = (rc == 0) && c->n_tgt_sph > 0;
+  std::thread tP;
   if(sph)
     {
       rc = gl_density(c);	// accel.c:84
+      t_dens = now_ms();
       if(rc == 0)
 	{
-	  tB = std::thread([&]() { rcB = push_density_on(c, c->copy_stream[1], stB, P, S); });
+	  const double *src[9] = { c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p,
+	    c->o_pressure.p, c->o_sinkrho.p, c->o_sinkentr.p };
+	  const bool have_other = (n > N_gas);
+	  for(int k = 0; k < (have_other ? 9 : 7); k++)
+	    GL_CUDA(c, cudaMemcpyAsync(stB + k * n, src[k], n * sizeof(double), cudaMemcpyDeviceToHost, cs1));
+	  if(have_other) GL_CUDA(c, cudaMemcpyAsync(stB + 9 * n, c->o_sinkvel.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, cs1));
+	  tP = std::thread([&]() {
+	    cudaSetDevice(c->device);
+	    cudaStreamSynchronize(cs0);
+	    cudaStreamSynchronize(cs1);
+	    scatter_P_fused(c, P, stA, stB, true);
+	    t_pP = now_ms();
+	  });
 	  rc = gl_force_update_hmax(c);	// accel.c:96
 	  if(rc == 0) rc = gl_hydro_force(c);	// accel.c:106
+	  t_hyd = now_ms();
+	  if(rc == 0)
+	    {
+	      GL_CUDA(c, cudaMemcpyAsync(stC, c->o_hacc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	      GL_CUDA(c, cudaMemcpyAsync(stC + 3 * n, c->o_dtentr.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	      GL_CUDA(c, cudaMemcpyAsync(stC + 4 * n, c->o_maxsig.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+	      GL_CUDA(c, cudaStreamSynchronize(cs1));
+	      scatter_SphP_fused(c, S, stB, stC);
+	    }
 	}
     }
-  tA.join();
-  if(tB.joinable()) tB.join();
-  if(rc || rcA || rcB) return 1;
-  if(sph && push_hydro_on(c, c->stream, stC, P, S)) return 1;
-  return 0;
+  else
+    {
+      GL_CUDA(c, cudaStreamSynchronize(cs0));
+      scatter_P_fused(c, P, stA, stB, false);
+    }
+  if(tP.joinable()) tP.join();
+  if(trace)
+    fprintf(stderr, "[gl] e2e ms since entry: pull %.1f | gravity done %.1f | density done %.1f | hydro done %.1f | P[] scatter done %.1f | exit %.1f\n",
+	    t_pull - t_start, t_grav - t_start, t_dens - t_start, t_hyd - t_start, t_pP - t_start, now_ms() - t_start);
+  return rc;
 }

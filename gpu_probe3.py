@@ -13,6 +13,8 @@ import ctypes as C
 from gadget_leicester_b200 import lib as L
 lib = fp._lib
 for it in range(4):
+    fp.set_TreeReconstructFlag(1); t0 = time.perf_counter(); drop.compute_accelerations(); print('pipelined %.1f ms' % ((time.perf_counter()-t0)*1e3))
+for it in range(0):
     fp.set_TreeReconstructFlag(1)
     t0 = time.perf_counter(); fp._chk(lib.gl_gadget_pull(fp.ctx, L._ptr(arr.P), L._ptr(arr.SphP), arr.NumPart, arr.N_gas))
     t1 = time.perf_counter(); fp._chk(lib.gl_compute_accelerations(fp.ctx, 0))
