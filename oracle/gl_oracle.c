@@ -1048,7 +1048,15 @@ int main(int argc, char **argv)
 	  switch (op)
 	    {
 	    case 'T': force_treebuild(); break;
-	    case 'S': initial_hsml(); break;
+	    case 'S':
+	      initial_hsml();
+	      for(i = 0; i < N; i++)	/* same input convention as ref_harness.c: OldAcc < 0 = swallowed after this step */
+		if(OldAcc[i] < 0)
+		  {
+		    Mass[i] = 0;
+		    OldAcc[i] = 0;
+		  }
+	      break;
 	    case 'D': density(); break;
 	    case 'R': TreeReconstructFlag = 1; break;
 	    case 'G': gravity_tree(); break;

@@ -379,7 +379,17 @@ int main(int argc, char **argv)
 	  switch (op)
 	    {
 	    case 'T': ngb_treebuild(); TreeReconstructFlag = 0; break;
-	    case 'S': initial_hsml(); break;
+	    case 'S':
+	      initial_hsml();
+	      /* input convention: OldAcc < 0 marks a gas particle that is swallowed (Mass = 0, sfr/blackhole code) after
+	         the initial-Hsml step but is still in the tree - the state density.c:832 / hydra.c:1236 guard against */
+	      for(i = 0; i < NumPart; i++)
+		if(P[i].OldAcc < 0)
+		  {
+		    P[i].Mass = 0;
+		    P[i].OldAcc = 0;
+		  }
+	      break;
 	    case 'D': density(); break;
 	    case 'R': TreeReconstructFlag = 1; break;
 	    case 'G': gravity_tree(); break;

@@ -34,6 +34,12 @@ CASES = {
                            ics.default_params(Softening=[1e-5, ics.plummer_softening(2000), 5e-5, 1e-7, 0.01, 5e-5])),
     # ragged: 333 gas + one particle each of types 1 (halo), 2 (dust target), 5 (sink target)
     "mixed_336": lambda: (_mixed(), ics.default_params()),
+    # individual time bins + entropy rates: exercises the viscosity limiter (hydra.c:1583-1597) and the pressure
+    # prediction (density.c:490-496), both of which vanish for TimeBin == 0
+    "cube_timebins_2k": lambda: (_timebins(), ics.default_params(Ti_Current=16)),
+    # swallowed (Mass == 0) gas particles still sitting in the tree between two domain decompositions
+    # (density.c:832, hydra.c:1236, forcetree.c:2214)
+    "cube_zero_mass_2k": lambda: (_zero_mass(), ics.default_params()),
 }
 
 
@@ -54,6 +60,22 @@ def _mixed():
     out["entropy"] = np.concatenate([ps["entropy"], np.zeros(extra)])
     out["dtentropy"] = np.zeros(n)
     return out
+
+
+def _timebins():
+    ps = ics.cube(2000, seed=21)
+    g = np.random.Generator(np.random.Philox(key=22))
+    ps["timebin"] = g.integers(0, 7, size=2000).astype(np.int32)
+    ps["dtentropy"] = (g.random(2000) - 0.5) * 2.0e3
+    ps["vel"] *= 20.0           # strong compression/shear so that the viscosity and its limiter are active
+    return ps
+
+
+def _zero_mass():
+    ps = ics.cube(2000, seed=23)
+    g = np.random.Generator(np.random.Philox(key=24))
+    ps["oldacc"][g.choice(2000, 100, replace=False)] = -1.0   # swallowed after the initial-Hsml step (see ref_harness.c op S)
+    return ps
 
 
 def main():

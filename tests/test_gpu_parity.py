@@ -48,6 +48,11 @@ def _check_sequence(FP, ps, par, R, label):
     ngas = int(gas.sum())
     ps = dict(ps)
     ps["hsml"] = R["hsml0__Hsml"].copy()
+    swallowed = ps["oldacc"] < 0      # harness convention (ref_harness.c op S): Mass := 0 after the initial-Hsml step
+    if swallowed.any():
+        ps["mass"], ps["oldacc"] = ps["mass"].copy(), ps["oldacc"].copy()
+        ps["mass"][swallowed] = 0.0
+        ps["oldacc"][swallowed] = 0.0
     fp = FP(par)
     fp.load(ps)
     report = []
