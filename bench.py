@@ -45,6 +45,21 @@ def peaks():
                 source="MEASURED_PEAKS.json" if p else "fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full capture (profiles/*_traffic.json,
+    written by scripts/ncu_summaries.py from the 1.6M-disc step); None when no capture names the kernel."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+        try:
+            t = json.load(open(f)).get("bytes_per_launch", {})
+            if kernel in t:
+                best = float(t[kernel])
+        except Exception:
+            pass
+    return best
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
@@ -347,14 +362,18 @@ def main():
         nsm = torch.cuda.get_device_properties(local).multi_processor_count
         peak = nsm * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
         ach = FLOP_PER_INTERACTION * (inter / args.steps) / (cand[dom] * 1e-3) / 1e12
-        roof = dict(kernel="k_gravity_walk", bound="fp32", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+        roof = dict(kernel="k_gravity_walk", bound="fp32", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                    traffic=(ncu_traffic("k_gravity_walk") if world == 1 and not args.ngas else None),
                     note="25 flop/interaction (SURVEY 8(d)); peak = SMs*128*2*sm_max_mhz from " + pk["source"])
     else:
         per = DENS_BYTES_PER_UPDATE if dom == "density" else HYDRO_BYTES_PER_UPDATE
         units = own_gas * (max(1, int(np.mean(passes))) if dom == "density" else 1)
         ach = per * units / (cand[dom] * 1e-3) / 1e9
         roof = dict(kernel="k_" + dom, bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
-                    traffic=None, note="%g B/update (SURVEY 8(d)); peak from %s" % (per, pk["source"]))
+                    traffic=(ncu_traffic("k_" + dom) if world == 1 and not args.ngas else None),
+                    algorithmic_bytes=per * units,
+                    note="%g B/update x %d updates (SURVEY 8(d)); peak from %s; traffic = ncu dram bytes per launch of the same "
+                         "workload (profiles/)" % (per, units, pk["source"]))
 
     # ---- e2e: the same step through the drop-in boundary with host P[]/SphP[] (rank-local set) ----
     e2e = None

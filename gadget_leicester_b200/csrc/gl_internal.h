@@ -138,7 +138,7 @@ struct gl_ctx
   DBuf<unsigned long long> d_counter;	// [0] interactions, [1] max passes, [2] error flag
   // ---- hydro source records (sorted order) ----
   DBuf<double4> h_q;		// rho, P/rho^2, P/rho^2*Omega, soundspeed
-  DBuf<double2> h_r;		// f (Balsara), timestep
+  DBuf<double4> h_r;		// f (Balsara), timestep, 1/h, 1/h^4
   // ---- fat density targets (block-per-target path) ----
   DBuf<int> fat_p, fat_i;
   DBuf<double4> fat_state, fat_rec;

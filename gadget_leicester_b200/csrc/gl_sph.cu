@@ -606,11 +606,9 @@ __device__ __forceinline__ void density_chunk_lt(WarpStage &S, int ncand, float 
     {
       const float4 cd = S.cand[c];
       const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
-      if(dx * dx + dy * dy + dz * dz <= thr)
-	{
-	  S.hl[nmine * 32 + lane] = (unsigned char) c;
-	  nmine++;
-	}
+      // branch-free append: the slot is overwritten by the next candidate unless this one is kept
+      S.hl[nmine * 32 + lane] = (unsigned char) c;
+      nmine += (dx * dx + dy * dy + dz * dz <= thr) ? 1 : 0;
     }
   const double h2 = h * h, hinv = 1.0 / h, hinv3 = hinv * hinv * hinv, hinv4 = hinv3 * hinv;
   const int kmax = __reduce_max_sync(FULL, nmine);
@@ -1049,14 +1047,14 @@ __global__ void k_hydro_prep(long long n, const int *__restrict__ perm, const in
 			     const double4 *__restrict__ s_vh, const double *__restrict__ density,
 			     const double *__restrict__ pressure, const double *__restrict__ dhsml,
 			     const double *__restrict__ divvel, const double *__restrict__ curlvel,
-			     const int *__restrict__ in_timebin, double4 *__restrict__ h_q, double2 *__restrict__ h_r)
+			     const int *__restrict__ in_timebin, double4 *__restrict__ h_q, double4 *__restrict__ h_r)
 {
   long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(i >= n) return;
   if(s_type[i] != 0)
     {
       h_q[i] = make_double4(0, 0, 0, 0);
-      h_r[i] = make_double2(0, 0);
+      h_r[i] = make_double4(0, 0, 0, 0);
       return;
     }
   const int j = perm[i];
@@ -1069,7 +1067,9 @@ __global__ void k_hydro_prep(long long n, const int *__restrict__ perm, const in
   const double f = adv / (adv + curlvel[j] + 0.0001 * cs / 1.0 / s_vh[i].w);
   const int tb = in_timebin[j];
   h_q[i] = make_double4(rho, porho2, porho2 * dhsml[j], cs);	// hydra.c:1600: p_over_rho2_j *= DhsmlDensityFactor
-  h_r[i] = make_double2(f, (double) (tb ? (1 << tb) : 0));
+  // 1/h_j and 1/h_j^4 exactly as hydra.c:1311-1312 forms them, once per source instead of once per pair
+  const double hinv = 1.0 / s_vh[i].w;
+  h_r[i] = make_double4(f, (double) (tb ? (1 << tb) : 0), hinv, hinv * hinv * hinv * hinv);
 }
 
 struct HydroAcc
@@ -1088,7 +1088,7 @@ struct HydroTarget
 __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax, unsigned live_mask, int lane, const GroupF &G,
 					    const HydroTarget &T, HydroAcc &A, const double4 *__restrict__ s_pm,
 					    const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
-					    const double2 *__restrict__ h_r, double artvisc, double timebase_interval)
+					    const double4 *__restrict__ h_r, double artvisc, double timebase_interval)
 {
   __syncwarp();
   float L = lmax;
@@ -1160,7 +1160,7 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 		  if(r2 > 0)
 		    {
 		      const double4 q = gl_ld4(&h_q[j]);
-		      const double2 rr = __ldg(&h_r[j]);
+		      const double4 rr = gl_ld4(&h_r[j]);
 		      P.npairs++;
 		      // r and 1/r from one reciprocal square root; the reference divides by r three times
 		      // (hydra.c:1511, 1602, 1606), here these are multiplications by rinv (1 ulp apart)
@@ -1246,7 +1246,7 @@ __device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax,
 __device__ __forceinline__ void hydro_chunk_lt(WarpStage &S, int ncand, float lmax, bool live, int lane, const GroupF &G,
 					       const HydroTarget &T, HydroAcc &A, const double4 *__restrict__ s_pm,
 					       const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
-					       const double2 *__restrict__ h_r, double artvisc, double timebase_interval)
+					       const double4 *__restrict__ h_r, double artvisc, double timebase_interval)
 {
   __syncwarp();
   float L = lmax;
@@ -1261,11 +1261,8 @@ __device__ __forceinline__ void hydro_chunk_lt(WarpStage &S, int ncand, float lm
       const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
       const float r2 = dx * dx + dy * dy + dz * dz;
       // conservative FP32 version of hydra.c:1266 (r2 < h_i^2 || r2 < h_j^2)
-      if(live && (r2 <= thr || r2 <= cand_threshold(cd.w, L)))
-	{
-	  S.hl[nmine * 32 + lane] = (unsigned char) c;
-	  nmine++;
-	}
+      S.hl[nmine * 32 + lane] = (unsigned char) c;	// branch-free append (see density_chunk_lt)
+      nmine += (live && (r2 <= thr || r2 <= cand_threshold(cd.w, L))) ? 1 : 0;
     }
   const double h_i = T.h_i, h_i2 = h_i * h_i, hinv_i = 1.0 / h_i, hinv4_i = hinv_i * hinv_i * hinv_i * hinv_i;
   const int kmax = __reduce_max_sync(FULL, nmine);
@@ -1282,7 +1279,7 @@ __device__ __forceinline__ void hydro_chunk_lt(WarpStage &S, int ncand, float lm
 	  if((r2 < h_i2 || r2 < h_j2) && r2 > 0)	// hydra.c:1266, :1270
 	    {
 	      const double4 q = gl_ld4(&h_q[j]);
-	      const double2 rr = __ldg(&h_r[j]);
+	      const double4 rr = gl_ld4(&h_r[j]);
 	      A.npairs++;
 	      const double rinv = rsqrt(r2);
 	      const double r = r2 * rinv;
@@ -1297,10 +1294,8 @@ __device__ __forceinline__ void hydro_chunk_lt(WarpStage &S, int ncand, float lm
 		}
 	      if(r2 < h_j2)
 		{
-		  const double hinv = 1.0 / h_j;
-		  const double hinv4 = hinv * hinv * hinv * hinv;
-		  const double u = r * hinv;
-		  dwk_j = (u < 0.5) ? hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+		  const double u = r * rr.z;
+		  dwk_j = (u < 0.5) ? rr.w * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : rr.w * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
 		}
 	      double vsig = T.cs_i + soundspeed_j;	// hydra.c:1502
 	      if(vsig > A.maxsig) A.maxsig = vsig;
@@ -1337,7 +1332,7 @@ __global__ void __launch_bounds__(SPH_BLOCK, 4)
 k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const int2 *__restrict__ e_rng,
 	const int *__restrict__ n_child, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
-	const double4 *__restrict__ h_q, const double2 *__restrict__ h_r, const int *__restrict__ perm,
+	const double4 *__restrict__ h_q, const double4 *__restrict__ h_r, const int *__restrict__ perm,
 	const double *__restrict__ pressure, const double *__restrict__ dhsml, const double *__restrict__ divvel,
 	const double *__restrict__ curlvel, double *__restrict__ o_hacc, double *__restrict__ o_dtentr,
 	double *__restrict__ o_maxsig, int *__restrict__ o_pairs, gl_dparams par)
