@@ -173,7 +173,7 @@ def big_config(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n = args.n or (1 << 27)
+    n = args.nparts or (1 << 27)
     dev = torch.device("cuda", local)
     warm = max(3, args.warmup)
     if args.config == 3:
@@ -268,7 +268,7 @@ def main():
     ap.add_argument("--ngas", type=int, default=0, help="override gas particles per GPU (default 1.6M)")
     ap.add_argument("--config", type=int, default=0, choices=[0, 3, 4],
                     help="0: disc (default, headline); 3: Plummer sphere, gravity only; 4: uniform gas cube, density+hydro only")
-    ap.add_argument("--n", type=int, default=0, help="total particles for --config 3/4 (default 2^27)")
+    ap.add_argument("--nparts", type=int, default=0, help="total particles for --config 3/4 (default 2^27)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

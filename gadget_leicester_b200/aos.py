@@ -111,7 +111,9 @@ class GadgetDropIn:
 
     def bytes_per_step(self):
         n = self.a.NumPart
-        h2d = n * (11 * 8 + 3 * 4)
+        # pack A (from P[]): pos, vel 24 + 24, mass, hsml, oldacc 8 each, type, timebin, ti_begstep 4 each;
+        # pack B (from SphP[], gas only): velpred 24, entropy, dtentropy 8 each
+        h2d = n * 84 + self.a.N_gas * 40
         other = 5 * 8 if n > self.a.N_gas else 0      # sink / dust columns only travel when such targets exist
         d2h = n * ((3 + 1) * 8 + 4) + n * (7 * 8 + other) + n * 5 * 8
         return h2d, d2h

@@ -29,6 +29,8 @@ extern "C" int gl_create(gl_ctx **out, int device, long long max_part)
       return 1;
     }
   for(int i = 0; i < 16; i++) cudaEventCreate(&c->ev[i]);
+  cudaEventCreateWithFlags(&c->ev_blk, cudaEventBlockingSync | cudaEventDisableTiming);
+  for(int i = 0; i < 4; i++) cudaEventCreateWithFlags(&c->ev_res[i], cudaEventBlockingSync | cudaEventDisableTiming);
   *out = c;
   return 0;
 }
@@ -38,6 +40,10 @@ extern "C" void gl_destroy(gl_ctx *c)
   if(!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  c->in_velpred.release();
+  if(c->ev_blk) cudaEventDestroy(c->ev_blk);
+  for(int i = 0; i < 4; i++)
+    if(c->ev_res[i]) cudaEventDestroy(c->ev_res[i]);
   c->in_pos.release(); c->in_vel.release(); c->in_mass.release(); c->in_hsml.release(); c->in_oldacc.release();
   c->in_entropy.release(); c->in_dtentropy.release(); c->in_type.release(); c->in_timebin.release();
   c->in_tibegstep.release(); c->key_m.release(); c->key_m_sorted.release(); c->key_ph.release(); c->idx.release();
@@ -52,6 +58,7 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->o_pot.release();
   c->o_dtentr.release(); c->o_maxsig.release(); c->o_gravcost.release(); c->o_denspairs.release();
   c->o_hydropairs.release(); c->d_counter.release(); c->h_q.release(); c->h_r.release();
+  c->tgt_gas_part.release(); c->tgt_part_flag.release();
   c->e_rng.release(); c->n_child.release(); c->fat_p.release(); c->fat_i.release(); c->fat_state.release();
   c->fat_rec.release(); c->fat_tgt.release();
   if(c->pin) cudaFreeHost(c->pin);
@@ -113,6 +120,7 @@ extern "C" int gl_load_particles(gl_ctx *c, long long n, const double *pos, cons
   c->tree_valid = false;
   c->tree_flag = true;
   c->tgt_dirty = true;
+  c->have_velpred = false;
   if(!c->domain_imposed) c->have_domain = false;
   return 0;
 }
@@ -209,6 +217,7 @@ extern "C" int gl_set_targets(gl_ctx *c, const int *index, long long n, int wher
 {
   cudaSetDevice(c->device);
   c->tgt_dirty = true;
+  c->tgt_host.clear();
   if(n < 0 || !index)
     {
       c->n_tgt_in = -1;
@@ -219,6 +228,7 @@ extern "C" int gl_set_targets(gl_ctx *c, const int *index, long long n, int wher
     GL_CUDA(c, cudaMemcpyAsync(c->tgt_in.p, index, n * sizeof(int), where ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
 			       c->stream));
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if(!where && n > 0 && c->have_lay) c->tgt_host.assign(index, index + n);	// only the drop-in layer scatters on the host
   c->n_tgt_in = n;
   return 0;
 }
@@ -290,6 +300,39 @@ int gl_prepare_targets(gl_ctx *c)
   if(select_flagged(c, f1, c->tgt_sph.p, n, &c->n_tgt_sph)) return 1;
   if(select_flagged(c, f2, c->tgt_gas.p, n, &c->n_tgt_gas)) return 1;
   c->tgt_dirty = false;
+  return 0;
+}
+
+// Drop-in pipeline: reorder the gas target list into [targets with P[] index < split | the others] so hydro can run
+// as two launches whose results are contiguous index ranges of the output arrays.  Both parts keep their
+// Peano-Hilbert sequence (the second one reversed - DevicePartition writes rejected items back to front), so a
+// warp's 32 targets stay a compact clump.
+__global__ void k_part_flag(long long nt, const int *__restrict__ tgt, const int *__restrict__ perm, int split, int *__restrict__ flag)
+{
+  long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(k < nt) flag[k] = perm[tgt[k]] < split;
+}
+
+int gl_split_gas_targets(gl_ctx *c, long long split, long long *n_lo)
+{
+  const long long nt = c->n_tgt_gas;
+  *n_lo = 0;
+  if(nt <= 0) return 0;
+  GL_CUDA(c, c->tgt_gas_part.ensure((size_t) nt + 1));
+  GL_CUDA(c, c->tgt_part_flag.ensure((size_t) nt + 1));
+  GL_CUDA(c, c->scan_tmp_i.ensure(64));
+  k_part_flag<<<gl_grid(nt, 256), 256, 0, c->stream>>>(nt, c->tgt_gas.p, c->perm.p, (int) split, c->tgt_part_flag.p);
+  GL_LAUNCH_COUNT(c);
+  size_t tmp = 0;
+  int *dcount = c->scan_tmp_i.p + 61;
+  cub::DevicePartition::Flagged(nullptr, tmp, c->tgt_gas.p, c->tgt_part_flag.p, c->tgt_gas_part.p, dcount, (int) nt, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DevicePartition::Flagged(c->cub_tmp.p, tmp, c->tgt_gas.p, c->tgt_part_flag.p, c->tgt_gas_part.p, dcount, (int) nt, c->stream));
+  c->kernel_launches += 2;
+  int h = 0;
+  GL_CUDA(c, cudaMemcpyAsync(&h, dcount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_lo = h;
   return 0;
 }
 
@@ -441,371 +484,3 @@ extern "C" void gl_reset_launch_count(gl_ctx *c)
   c->st.ms_d2h = 0;
 }
 
-// ---------------------------------------------------------------- gadget AoS layer ----
-extern "C" int gl_gadget_bind(gl_ctx *c, const gl_gadget_layout *lay)
-{
-  if(lay->p_stride <= 0 || lay->sph_stride <= 0) return c->fail("gl_gadget_bind: bad strides");
-  c->lay = *lay;
-  c->have_lay = true;
-  return 0;
-}
-
-static int ensure_pinned(gl_ctx *c, size_t bytes)
-{
-  if(bytes <= c->pin_cap) return 0;
-  if(c->pin) cudaFreeHost(c->pin);
-  if(c->pin2) cudaFreeHost(c->pin2);
-  for(int k = 0; k < 2; k++)
-    if(c->copy_stream[k]) cudaStreamDestroy(c->copy_stream[k]);
-  c->pin = nullptr;
-  c->pin_cap = 0;
-  GL_CUDA(c, cudaMallocHost(&c->pin, bytes + bytes / 8));
-  c->pin_cap = bytes + bytes / 8;
-  return 0;
-}
-
-template <class F> static void parallel_for(long long n, F f)
-{
-  unsigned hw = std::thread::hardware_concurrency();
-  int nth = (int) std::min<long long>(std::max(1u, std::min(hw, 32u)), (n + 65535) / 65536);
-  if(nth <= 1)
-    {
-      f(0, n);
-      return;
-    }
-  std::vector<std::thread> th;
-  long long chunk = (n + nth - 1) / nth;
-  for(int t = 0; t < nth; t++)
-    {
-      long long a = t * chunk, b = std::min(n, a + chunk);
-      if(a >= b) break;
-      th.emplace_back([=]() { f(a, b); });
-    }
-  for(auto &x : th) x.join();
-}
-
-// Staging layout (all in one pinned block, SoA): pos 3n | vel 3n | mass n | hsml n | oldacc n | entropy n |
-// dtentropy n | type n(int) | timebin n(int) | tibegstep n(int)
-extern "C" int gl_gadget_pull(gl_ctx *c, const void *Pv, const void *SphPv, long long NumPart, long long N_gas)
-{
-  cudaSetDevice(c->device);
-  if(!c->have_lay) return c->fail("gl_gadget_pull: gl_gadget_bind not called");
-  const long long n = NumPart;
-  if(n <= 0) return c->fail("gl_gadget_pull: NumPart <= 0");
-  const size_t bytes = (size_t) n * (11 * sizeof(double) + 3 * sizeof(int));
-  if(ensure_pinned(c, bytes)) return 1;
-  double *pos = (double *) c->pin, *vel = pos + 3 * n, *mass = vel + 3 * n, *hsml = mass + n, *oldacc = hsml + n,
-    *entropy = oldacc + n, *dtentropy = entropy + n;
-  int *type = (int *) (dtentropy + n), *timebin = type + n, *tibeg = timebin + n;
-  const gl_gadget_layout L = c->lay;
-  const char *P = (const char *) Pv, *S = (const char *) SphPv;
-  parallel_for(n, [=](long long a, long long b) {
-    for(long long i = a; i < b; i++)
-      {
-	const char *pi = P + i * L.p_stride;
-	const double *x = (const double *) (pi + L.p_Pos);
-	pos[3 * i] = x[0]; pos[3 * i + 1] = x[1]; pos[3 * i + 2] = x[2];
-	mass[i] = *(const double *) (pi + L.p_Mass);
-	hsml[i] = *(const double *) (pi + L.p_Hsml);
-	oldacc[i] = *(const double *) (pi + L.p_OldAcc);
-	const int ty = *(const short *) (pi + L.p_Type);
-	type[i] = ty;
-	timebin[i] = *(const short *) (pi + L.p_TimeBin);
-	tibeg[i] = *(const int *) (pi + L.p_Ti_begstep);
-	if(ty == 0 && i < N_gas)
-	  {
-	    const char *si = S + i * L.sph_stride;
-	    const double *v = (const double *) (si + L.s_VelPred);
-	    vel[3 * i] = v[0]; vel[3 * i + 1] = v[1]; vel[3 * i + 2] = v[2];
-	    entropy[i] = *(const double *) (si + L.s_Entropy);
-	    dtentropy[i] = *(const double *) (si + L.s_DtEntropy);
-	  }
-	else
-	  {
-	    const double *v = (const double *) (pi + L.p_Vel);
-	    vel[3 * i] = v[0]; vel[3 * i + 1] = v[1]; vel[3 * i + 2] = v[2];
-	    entropy[i] = 0;
-	    dtentropy[i] = 0;
-	  }
-      }
-  });
-  c->g_numpart = NumPart;
-  c->g_ngas = N_gas;
-  return gl_load_particles(c, n, pos, vel, mass, type, hsml, oldacc, timebin, tibeg, entropy, dtentropy, 0);
-}
-
-// ---- result scatter: D2H of compact SoA results on `st`, then a multi-threaded scatter into P[] / SphP[] ----
-static int push_gravity_on(gl_ctx *c, cudaStream_t st, double *stage, char *P)
-{
-  cudaSetDevice(c->device);
-  const long long n = c->n;
-  const gl_gadget_layout L = c->lay;
-  double *acc = stage, *old = acc + 3 * n;
-  float *cost = (float *) (old + n);
-  GL_CUDA(c, cudaMemcpyAsync(acc, c->o_acc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  GL_CUDA(c, cudaMemcpyAsync(old, c->o_oldacc.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  GL_CUDA(c, cudaMemcpyAsync(cost, c->o_gravcost.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  GL_CUDA(c, cudaStreamSynchronize(st));
-  parallel_for(n, [=](long long a, long long b) {
-    for(long long i = a; i < b; i++)
-      {
-	char *pi = P + i * L.p_stride;
-	double *g = (double *) (pi + L.p_GravAccel);
-	g[0] = acc[3 * i]; g[1] = acc[3 * i + 1]; g[2] = acc[3 * i + 2];
-	*(double *) (pi + L.p_OldAcc) = old[i];
-	*(float *) (pi + L.p_GravCost) = cost[i];
-      }
-  });
-  return 0;
-}
-
-static int push_density_on(gl_ctx *c, cudaStream_t st, double *stage, char *P, char *S)
-{
-  cudaSetDevice(c->device);
-  const long long n = c->n, N_gas = c->g_ngas;
-  const gl_gadget_layout L = c->lay;
-  double *hs = stage, *nn = hs + n, *de = nn + n, *dh = de + n, *dv = dh + n, *cu = dv + n, *pr = cu + n, *sr = pr + n,
-    *se = sr + n, *sv = se + n;
-  const double *src[9] = { c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p,
-    c->o_pressure.p, c->o_sinkrho.p, c->o_sinkentr.p };
-  double *dst[9] = { hs, nn, de, dh, dv, cu, pr, sr, se };
-  const bool have_other = (n > N_gas);	// sink / dust fields only exist for non-gas targets
-  for(int k = 0; k < (have_other ? 9 : 7); k++)
-    GL_CUDA(c, cudaMemcpyAsync(dst[k], src[k], n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if(have_other) GL_CUDA(c, cudaMemcpyAsync(sv, c->o_sinkvel.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  GL_CUDA(c, cudaStreamSynchronize(st));
-  parallel_for(n, [=](long long a, long long b) {
-    for(long long i = a; i < b; i++)
-      {
-	char *pi = P + i * L.p_stride;
-	const int ty = *(const short *) (pi + L.p_Type);
-	if(!(ty == 0 || ty == 5 || ty == 2)) continue;
-	*(double *) (pi + L.p_Hsml) = hs[i];
-	*(double *) (pi + L.p_NumNgb) = nn[i];
-	*(unsigned int *) (pi + L.p_SwallowID) = 0;	// density.c:130
-	if(ty == 0 && i < N_gas)
-	  {
-	    char *si = S + i * L.sph_stride;
-	    *(double *) (si + L.s_Density) = de[i];
-	    *(double *) (si + L.s_DhsmlDensityFactor) = dh[i];
-	    *(double *) (si + L.s_DivVel) = dv[i];
-	    *(double *) (si + L.s_CurlVel) = cu[i];
-	    *(double *) (si + L.s_Pressure) = pr[i];
-	  }
-	else if(ty == 5)
-	  {
-	    *(double *) (pi + L.p_SinkDensity) = sr[i];
-	    *(double *) (pi + L.p_SinkEntropy) = se[i];
-	    double *g = (double *) (pi + L.p_SinkGasVel);
-	    g[0] = sv[3 * i]; g[1] = sv[3 * i + 1]; g[2] = sv[3 * i + 2];
-	  }
-	else if(ty == 2)
-	  {
-	    *(double *) (pi + L.p_DustDensity) = sr[i];
-	    *(double *) (pi + L.p_DustEntropy) = se[i];
-	    double *g = (double *) (pi + L.p_DustGasVel);
-	    g[0] = sv[3 * i]; g[1] = sv[3 * i + 1]; g[2] = sv[3 * i + 2];
-	  }
-      }
-  });
-  return 0;
-}
-
-static int push_hydro_on(gl_ctx *c, cudaStream_t st, double *stage, char *P, char *S)
-{
-  cudaSetDevice(c->device);
-  const long long n = c->n, N_gas = c->g_ngas;
-  const gl_gadget_layout L = c->lay;
-  double *ha = stage, *dt = ha + 3 * n, *ms = dt + n;
-  GL_CUDA(c, cudaMemcpyAsync(ha, c->o_hacc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  GL_CUDA(c, cudaMemcpyAsync(dt, c->o_dtentr.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  GL_CUDA(c, cudaMemcpyAsync(ms, c->o_maxsig.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  GL_CUDA(c, cudaStreamSynchronize(st));
-  parallel_for(std::min(n, N_gas), [=](long long a, long long b) {
-    for(long long i = a; i < b; i++)
-      {
-	const char *pi = P + i * L.p_stride;
-	if(*(const short *) (pi + L.p_Type) != 0) continue;
-	char *si = S + i * L.sph_stride;
-	double *g = (double *) (si + L.s_HydroAccel);
-	g[0] = ha[3 * i]; g[1] = ha[3 * i + 1]; g[2] = ha[3 * i + 2];
-	*(double *) (si + L.s_DtEntropy) = dt[i];
-	*(double *) (si + L.s_MaxSignalVel) = ms[i];
-      }
-  });
-  return 0;
-}
-
-static int ensure_pinned2(gl_ctx *c, size_t bytes)
-{
-  if(bytes <= c->pin2_cap) return 0;
-  if(c->pin2) cudaFreeHost(c->pin2);
-  c->pin2 = nullptr;
-  c->pin2_cap = 0;
-  GL_CUDA(c, cudaMallocHost(&c->pin2, bytes + bytes / 8));
-  c->pin2_cap = bytes + bytes / 8;
-  return 0;
-}
-
-extern "C" int gl_gadget_push(gl_ctx *c, void *Pv, void *SphPv, int what)
-{
-  cudaSetDevice(c->device);
-  if(!c->have_lay) return c->fail("gl_gadget_push: gl_gadget_bind not called");
-  const long long n = c->n;
-  if(ensure_pinned2(c, (size_t) n * 24 * sizeof(double))) return 1;
-  double *stage = (double *) c->pin2;
-  if((what & 1) && push_gravity_on(c, c->stream, stage, (char *) Pv)) return 1;
-  if((what & 2) && push_density_on(c, c->stream, stage, (char *) Pv, (char *) SphPv)) return 1;
-  if((what & 4) && push_hydro_on(c, c->stream, stage, (char *) Pv, (char *) SphPv)) return 1;
-  return 0;
-}
-
-// ---- fused scatters of the pipelined drop-in call: each struct array is touched exactly once ----
-// P[]: gravity results + the P-side density results, in one pass (struct lines 1, 2 and 8 of 9)
-static void scatter_P_fused(gl_ctx *c, char *P, const double *stA, const double *stB, bool sph)
-{
-  const long long n = c->n, N_gas = c->g_ngas;
-  const gl_gadget_layout L = c->lay;
-  const double *acc = stA, *old = acc + 3 * n;
-  const float *cost = (const float *) (old + n);
-  const double *hs = stB, *nn = hs + n, *sr = nn + 6 * n, *se = sr + n, *sv = se + n;
-  const int *type = (const int *) ((const double *) c->pin + 11 * n);	// Type column of the pull staging (still valid)
-  const bool have_other = (n > N_gas);
-  parallel_for(n, [=](long long a, long long b) {
-    for(long long i = a; i < b; i++)
-      {
-	char *pi = P + i * L.p_stride;
-	double *g = (double *) (pi + L.p_GravAccel);
-	g[0] = acc[3 * i]; g[1] = acc[3 * i + 1]; g[2] = acc[3 * i + 2];
-	*(double *) (pi + L.p_OldAcc) = old[i];
-	*(float *) (pi + L.p_GravCost) = cost[i];
-	if(!sph) continue;
-	const int ty = type[i];
-	if(!(ty == 0 || ty == 5 || ty == 2)) continue;
-	*(double *) (pi + L.p_Hsml) = hs[i];
-	*(double *) (pi + L.p_NumNgb) = nn[i];
-	*(unsigned int *) (pi + L.p_SwallowID) = 0;	// density.c:130
-	if(ty == 5 && have_other)
-	  {
-	    *(double *) (pi + L.p_SinkDensity) = sr[i];
-	    *(double *) (pi + L.p_SinkEntropy) = se[i];
-	    double *v = (double *) (pi + L.p_SinkGasVel);
-	    v[0] = sv[3 * i]; v[1] = sv[3 * i + 1]; v[2] = sv[3 * i + 2];
-	  }
-	else if(ty == 2 && have_other)
-	  {
-	    *(double *) (pi + L.p_DustDensity) = sr[i];
-	    *(double *) (pi + L.p_DustEntropy) = se[i];
-	    double *v = (double *) (pi + L.p_DustGasVel);
-	    v[0] = sv[3 * i]; v[1] = sv[3 * i + 1]; v[2] = sv[3 * i + 2];
-	  }
-      }
-  });
-}
-
-// SphP[]: density + hydro results in one pass (struct lines 0, 1, 2 of 5)
-static void scatter_SphP_fused(gl_ctx *c, char *S, const double *stB, const double *stC)
-{
-  const long long n = c->n, N_gas = c->g_ngas;
-  const gl_gadget_layout L = c->lay;
-  const double *de = stB + 2 * n, *dh = de + n, *dv = dh + n, *cu = dv + n, *pr = cu + n;
-  const double *ha = stC, *dt = ha + 3 * n, *ms = dt + n;
-  const int *type = (const int *) ((const double *) c->pin + 11 * n);
-  parallel_for(std::min(n, N_gas), [=](long long a, long long b) {
-    for(long long i = a; i < b; i++)
-      {
-	if(type[i] != 0) continue;
-	char *si = S + i * L.sph_stride;
-	*(double *) (si + L.s_Pressure) = pr[i];
-	*(double *) (si + L.s_MaxSignalVel) = ms[i];
-	*(double *) (si + L.s_Density) = de[i];
-	*(double *) (si + L.s_DtEntropy) = dt[i];
-	double *g = (double *) (si + L.s_HydroAccel);
-	g[0] = ha[3 * i]; g[1] = ha[3 * i + 1]; g[2] = ha[3 * i + 2];
-	*(double *) (si + L.s_DhsmlDensityFactor) = dh[i];
-	*(double *) (si + L.s_DivVel) = dv[i];
-	*(double *) (si + L.s_CurlVel) = cu[i];
-      }
-  });
-}
-
-// The drop-in compute_accelerations (accel.c:27) on the reference's host arrays, software-pipelined:
-//   GPU:   gravity | density            | hmax + hydro        |
-//   PCIe:          | D2H gravity results| D2H density results | D2H hydro results
-//   host:                               | scatter into P[]    | scatter into SphP[]
-// Every struct array is read once (pull) and written once; the P[] scatter hides behind the hydro kernel.
-extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv, long long NumPart, long long N_gas, int mode)
-{
-  (void) mode;
-  cudaSetDevice(c->device);
-  if(!c->have_lay) return c->fail("gl_gadget_compute_accelerations: gl_gadget_bind not called");
-  const bool trace = getenv("GL_DEBUG_E2E") != nullptr;
-  auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t_start = now_ms();
-  double t_pull = 0, t_grav = 0, t_dens = 0, t_hyd = 0, t_pP = 0;
-  if(gl_gadget_pull(c, Pv, SphPv, NumPart, N_gas)) return 1;
-  t_pull = now_ms();
-  const long long n = c->n;
-  if(ensure_pinned2(c, (size_t) n * 24 * sizeof(double))) return 1;
-  if(!c->copy_stream[0])
-    for(int k = 0; k < 2; k++) GL_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream[k], cudaStreamNonBlocking));
-  double *stA = (double *) c->pin2, *stB = stA + 5 * n, *stC = stB + 13 * n;	// 5n | 13n | 5n doubles
-  char *P = (char *) Pv, *S = (char *) SphPv;
-  const bool first = (c->par.TypeOfOpeningCriterion == 1 && c->par.Ti_Current == 0 && c->par.ErrTolTheta != 0);
-  if(gl_gravity_tree(c)) return 1;	// accel.c:61
-  if(first)
-    if(gl_gravity_tree(c)) return 1;	// accel.c:63-67
-  t_grav = now_ms();
-  // gravity results start crossing PCIe while density runs
-  cudaStream_t cs0 = c->copy_stream[0], cs1 = c->copy_stream[1];
-  GL_CUDA(c, cudaMemcpyAsync(stA, c->o_acc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, cs0));
-  GL_CUDA(c, cudaMemcpyAsync(stA + 3 * n, c->o_oldacc.p, n * sizeof(double), cudaMemcpyDeviceToHost, cs0));
-  GL_CUDA(c, cudaMemcpyAsync(stA + 4 * n, c->o_gravcost.p, n * sizeof(float), cudaMemcpyDeviceToHost, cs0));
-  if(gl_prepare_targets(c)) return 1;
-  const bool sph = c->n_tgt_sph > 0;
-  int rc = 0;
-  std::thread tP;
-  if(sph)
-    {
-      rc = gl_density(c);	// accel.c:84
-      t_dens = now_ms();
-      if(rc == 0)
-	{
-	  const double *src[9] = { c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p,
-	    c->o_pressure.p, c->o_sinkrho.p, c->o_sinkentr.p };
-	  const bool have_other = (n > N_gas);
-	  for(int k = 0; k < (have_other ? 9 : 7); k++)
-	    GL_CUDA(c, cudaMemcpyAsync(stB + k * n, src[k], n * sizeof(double), cudaMemcpyDeviceToHost, cs1));
-	  if(have_other) GL_CUDA(c, cudaMemcpyAsync(stB + 9 * n, c->o_sinkvel.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, cs1));
-	  tP = std::thread([&]() {
-	    cudaSetDevice(c->device);
-	    cudaStreamSynchronize(cs0);
-	    cudaStreamSynchronize(cs1);
-	    scatter_P_fused(c, P, stA, stB, true);
-	    t_pP = now_ms();
-	  });
-	  rc = gl_force_update_hmax(c);	// accel.c:96
-	  if(rc == 0) rc = gl_hydro_force(c);	// accel.c:106
-	  t_hyd = now_ms();
-	  if(rc == 0)
-	    {
-	      GL_CUDA(c, cudaMemcpyAsync(stC, c->o_hacc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-	      GL_CUDA(c, cudaMemcpyAsync(stC + 3 * n, c->o_dtentr.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-	      GL_CUDA(c, cudaMemcpyAsync(stC + 4 * n, c->o_maxsig.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-	      GL_CUDA(c, cudaStreamSynchronize(c->stream));
-	      GL_CUDA(c, cudaStreamSynchronize(cs1));
-	      scatter_SphP_fused(c, S, stB, stC);
-	    }
-	}
-    }
-  else
-    {
-      GL_CUDA(c, cudaStreamSynchronize(cs0));
-      scatter_P_fused(c, P, stA, stB, false);
-    }
-  if(tP.joinable()) tP.join();
-  if(trace)
-    fprintf(stderr, "[gl] e2e ms since entry: pull %.1f | gravity done %.1f | density done %.1f | hydro done %.1f | P[] scatter done %.1f | exit %.1f\n",
-	    t_pull - t_start, t_grav - t_start, t_dens - t_start, t_hyd - t_start, t_pP - t_start, now_ms() - t_start);
-  return rc;
-}

@@ -1,0 +1,724 @@
+// gl_gadget.cu - drop-in layer for the reference's AoS arrays: struct particle_data P[] (allvars.h:1131) and
+// struct sph_particle_data SphP[] (allvars.h:1384), addressed through the offsetof() table the reference side
+// supplies (integration/gl_gadget_glue.c), so the library never needs allvars.h.
+//
+// The force path itself takes ~18 ms for the 1.6M-particle disc; moving 1.6M x 800 B structs through the host
+// caches costs about as much, so this layer is built like a pipeline, not like a wrapper:
+//
+//   host pool :  pack P[] ->|  pack SphP[]   |  scatter gravity -> P[]  |  scatter density -> P[], SphP[] | scatter hydro
+//   PCIe      :   H2D (by super-chunk, behind the pack) ...   D2H gravity |        D2H density            |  D2H hydro
+//   GPU       :             |  keys, sort, tree, walk         |  density                  |  hmax, hydro     |
+//
+// * pack A reads only what tree build + gravity need and all of it comes from P[] (Pos, Vel, Mass, Hsml, OldAcc,
+//   Type, TimeBin, Ti_begstep); each 256k-particle super-chunk is sent as soon as its last chunk is packed, so
+//   the H2D time hides behind the packing.  The SphP[] fields (VelPred, Entropy, DtEntropy) are packed while
+//   the GPU builds the tree and walks it, and reach the device before density needs them.
+// * every result block crosses PCIe on a copy stream while the next phase computes, and is scattered by the
+//   host pool (all cores but one, dynamic chunks, software prefetch) as soon as it has landed.
+// * the only serial tail is "D2H of the hydro results + their scatter into SphP[]".
+#include "gl_internal.h"
+#include "gl_host.h"
+#include <chrono>
+#include <algorithm>
+
+#define PACK_CHUNK 8192		// particles per work item of the host pool
+#define SUPER_CHUNKS 32		// work items per H2D super-chunk (256k particles, 21 MB)
+#define BAD_TYPE_MSG "P[i].Type != 0 inside the gas block [0,N_gas): the reference keeps gas first (SphP[i] belongs to P[i])"
+#define PF_DIST 8		// software prefetch distance in structs (measured on the B200 box's Xeon: -25% time)
+
+extern "C" int gl_gadget_bind(gl_ctx *c, const gl_gadget_layout *lay)
+{
+  if(lay->p_stride <= 0 || lay->sph_stride <= 0) return c->fail("gl_gadget_bind: bad strides");
+  c->lay = *lay;
+  c->have_lay = true;
+  return 0;
+}
+
+static int ensure_pinned(gl_ctx *c, void **p, size_t *cap, size_t bytes)
+{
+  if(bytes <= *cap) return 0;
+  if(*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  GL_CUDA(c, cudaMallocHost(p, bytes + bytes / 8));
+  *cap = bytes + bytes / 8;
+  return 0;
+}
+
+// Pull staging (one pinned block, SoA): pos 3n | vel 3n | mass n | hsml n | oldacc n | entropy n | dtentropy n |
+// velpred 3n | type n (int) | timebin n (int) | tibegstep n (int)
+struct PullStage
+{
+  double *pos, *vel, *mass, *hsml, *oldacc, *entropy, *dtentropy, *velpred;
+  int *type, *timebin, *tibeg;
+  static size_t bytes(long long n) { return (size_t) n * (14 * sizeof(double) + 3 * sizeof(int)); }
+  PullStage(void *base, long long n)
+  {
+    pos = (double *) base; vel = pos + 3 * n; mass = vel + 3 * n; hsml = mass + n; oldacc = hsml + n;
+    entropy = oldacc + n; dtentropy = entropy + n; velpred = dtentropy + n;
+    type = (int *) (velpred + 3 * n); timebin = type + n; tibeg = timebin + n;
+  }
+};
+
+static int ensure_input_buffers(gl_ctx *c, long long n, long long ngas)
+{
+  GL_CUDA(c, c->in_pos.ensure(3 * (size_t) n));
+  GL_CUDA(c, c->in_vel.ensure(3 * (size_t) n));
+  GL_CUDA(c, c->in_mass.ensure((size_t) n));
+  GL_CUDA(c, c->in_type.ensure((size_t) n));
+  GL_CUDA(c, c->in_hsml.ensure((size_t) n));
+  GL_CUDA(c, c->in_oldacc.ensure((size_t) n));
+  GL_CUDA(c, c->in_timebin.ensure((size_t) n));
+  GL_CUDA(c, c->in_tibegstep.ensure((size_t) n));
+  GL_CUDA(c, c->in_entropy.ensure((size_t) n));
+  GL_CUDA(c, c->in_dtentropy.ensure((size_t) n));
+  GL_CUDA(c, c->in_velpred.ensure(3 * (size_t) std::max<long long>(ngas, 1)));
+  return 0;
+}
+
+// ---- pack A: everything the tree build and the gravity walk read, all of it from P[] ----
+// Inside the gas block [0,N_gas) Type is 0 by the reference's layout (SphP[i] belongs to P[i], allvars.h:1384; every
+// reference loop relies on it), so only the first two cache lines of the struct are touched there (Pos, Vel, Mass,
+// OldAcc, Hsml); TimeBin / Ti_begstep, which sit 460 bytes further on, are fetched by pack B, which also verifies
+// the Type assumption.  The H2D copies of a super-chunk are enqueued on c->stream by the worker that packs its
+// last chunk.
+static std::shared_ptr<HostJob> submit_pack_A(gl_ctx *c, const char *P, long long n, long long ngas, PullStage st,
+					      std::atomic<int> *sc_left, std::atomic<int> *cuda_err)
+{
+  const gl_gadget_layout L = c->lay;
+  const long long nchunks = (n + PACK_CHUNK - 1) / PACK_CHUNK;
+  const long long nsuper = (nchunks + SUPER_CHUNKS - 1) / SUPER_CHUNKS;
+  for(long long s = 0; s < nsuper; s++)
+    sc_left[s].store((int) std::min<long long>(SUPER_CHUNKS, nchunks - s * SUPER_CHUNKS));
+  return HostPool::get().submit(n, PACK_CHUNK, [=](long long k, long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	const char *pi = P + i * L.p_stride;
+	const bool gas = i < ngas;
+	if(i + PF_DIST < b)
+	  {
+	    const char *pf = pi + PF_DIST * L.p_stride;
+	    __builtin_prefetch(pf + L.p_Pos);
+	    __builtin_prefetch(pf + L.p_OldAcc);
+	    if(!gas) __builtin_prefetch(pf + L.p_Ti_begstep);
+	  }
+	const double *x = (const double *) (pi + L.p_Pos);
+	st.pos[3 * i] = x[0]; st.pos[3 * i + 1] = x[1]; st.pos[3 * i + 2] = x[2];
+	const double *v = (const double *) (pi + L.p_Vel);
+	st.vel[3 * i] = v[0]; st.vel[3 * i + 1] = v[1]; st.vel[3 * i + 2] = v[2];
+	st.mass[i] = *(const double *) (pi + L.p_Mass);
+	st.hsml[i] = *(const double *) (pi + L.p_Hsml);
+	st.oldacc[i] = *(const double *) (pi + L.p_OldAcc);
+	if(gas)
+	  st.type[i] = 0;
+	else
+	  {
+	    st.type[i] = *(const short *) (pi + L.p_Type);
+	    st.timebin[i] = *(const short *) (pi + L.p_TimeBin);
+	    st.tibeg[i] = *(const int *) (pi + L.p_Ti_begstep);
+	  }
+      }
+    const long long s = k / SUPER_CHUNKS;
+    if(sc_left[s].fetch_sub(1) == 1)
+      {
+	// last chunk of this super-chunk: send it
+	const long long a0 = s * SUPER_CHUNKS * (long long) PACK_CHUNK, b0 = std::min(n, a0 + SUPER_CHUNKS * (long long) PACK_CHUNK), m = b0 - a0;
+	cudaSetDevice(c->device);
+	cudaError_t e = cudaSuccess;
+	auto up = [&](void *dst, const void *src, size_t bytes) {
+	  cudaError_t r = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+	  if(r != cudaSuccess) e = r;
+	};
+	up(c->in_pos.p + 3 * a0, st.pos + 3 * a0, 3 * m * sizeof(double));
+	up(c->in_vel.p + 3 * a0, st.vel + 3 * a0, 3 * m * sizeof(double));
+	up(c->in_mass.p + a0, st.mass + a0, m * sizeof(double));
+	up(c->in_hsml.p + a0, st.hsml + a0, m * sizeof(double));
+	up(c->in_oldacc.p + a0, st.oldacc + a0, m * sizeof(double));
+	up(c->in_type.p + a0, st.type + a0, m * sizeof(int));
+	const long long a1 = std::max(a0, ngas);	// the gas block's time bins come with pack B
+	if(a1 < b0)
+	  {
+	    up(c->in_timebin.p + a1, st.timebin + a1, (b0 - a1) * sizeof(int));
+	    up(c->in_tibegstep.p + a1, st.tibeg + a1, (b0 - a1) * sizeof(int));
+	  }
+	if(e != cudaSuccess) cuda_err->store((int) e);
+      }
+  });
+}
+
+// ---- pack B: the SphP[] fields of the gas block (VelPred, Entropy, DtEntropy) and its TimeBin / Ti_begstep from
+// P[]; checks Type == 0 there (bad_type counts violations).  Copies go out on `cs`. ----
+static std::shared_ptr<HostJob> submit_pack_B(gl_ctx *c, const char *P, const char *S, long long ngas, PullStage st,
+					      std::atomic<int> *left, cudaStream_t cs, cudaEvent_t done_ev,
+					      std::atomic<int> *cuda_err, std::atomic<long long> *bad_type)
+{
+  const gl_gadget_layout L = c->lay;
+  const long long nchunks = (ngas + PACK_CHUNK - 1) / PACK_CHUNK;
+  left->store((int) nchunks);
+  return HostPool::get().submit(ngas, PACK_CHUNK, [=](long long, long long a, long long b) {
+    long long bad = 0;
+    for(long long i = a; i < b; i++)
+      {
+	const char *si = S + i * L.sph_stride;
+	const char *pi = P + i * L.p_stride;
+	if(i + PF_DIST < b)
+	  {
+	    const char *pf = si + PF_DIST * L.sph_stride;
+	    __builtin_prefetch(pf + L.s_Entropy);
+	    __builtin_prefetch(pf + L.s_DtEntropy);
+	    __builtin_prefetch(pi + PF_DIST * L.p_stride + L.p_Ti_begstep);
+	  }
+	const double *v = (const double *) (si + L.s_VelPred);
+	st.velpred[3 * i] = v[0]; st.velpred[3 * i + 1] = v[1]; st.velpred[3 * i + 2] = v[2];
+	st.entropy[i] = *(const double *) (si + L.s_Entropy);
+	st.dtentropy[i] = *(const double *) (si + L.s_DtEntropy);
+	bad += (*(const short *) (pi + L.p_Type) != 0);
+	st.timebin[i] = *(const short *) (pi + L.p_TimeBin);
+	st.tibeg[i] = *(const int *) (pi + L.p_Ti_begstep);
+      }
+    if(bad) bad_type->fetch_add(bad);
+    if(left->fetch_sub(1) == 1)
+      {
+	cudaSetDevice(c->device);
+	cudaError_t e = cudaMemcpyAsync(c->in_velpred.p, st.velpred, 3 * ngas * sizeof(double), cudaMemcpyHostToDevice, cs);
+	if(e == cudaSuccess) e = cudaMemcpyAsync(c->in_entropy.p, st.entropy, ngas * sizeof(double), cudaMemcpyHostToDevice, cs);
+	if(e == cudaSuccess) e = cudaMemcpyAsync(c->in_dtentropy.p, st.dtentropy, ngas * sizeof(double), cudaMemcpyHostToDevice, cs);
+	if(e == cudaSuccess) e = cudaMemcpyAsync(c->in_timebin.p, st.timebin, ngas * sizeof(int), cudaMemcpyHostToDevice, cs);
+	if(e == cudaSuccess) e = cudaMemcpyAsync(c->in_tibegstep.p, st.tibeg, ngas * sizeof(int), cudaMemcpyHostToDevice, cs);
+	if(e == cudaSuccess) e = cudaEventRecord(done_ev, cs);
+	if(e != cudaSuccess) cuda_err->store((int) e);
+      }
+  });
+}
+
+static int ensure_copy_streams(gl_ctx *c)
+{
+  if(!c->copy_stream[0])
+    for(int k = 0; k < 2; k++) GL_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream[k], cudaStreamNonBlocking));
+  return 0;
+}
+
+static void mark_loaded(gl_ctx *c, long long n, long long ngas)
+{
+  c->n = n;
+  c->g_numpart = n;
+  c->g_ngas = ngas;
+  c->tree_valid = false;
+  c->tree_flag = true;
+  c->tgt_dirty = true;
+  if(!c->domain_imposed) c->have_domain = false;
+}
+
+// the SphP part of the state has reached the device on `cs` (event ev): make c->stream see it and publish VelPred
+static int finish_pack_B(gl_ctx *c, long long n, long long ngas, cudaEvent_t ev)
+{
+  GL_CUDA(c, cudaStreamWaitEvent(c->stream, ev, 0));
+  if(n > ngas)
+    {				// non-gas particles carry no entropy
+      GL_CUDA(c, cudaMemsetAsync(c->in_entropy.p + ngas, 0, (n - ngas) * sizeof(double), c->stream));
+      GL_CUDA(c, cudaMemsetAsync(c->in_dtentropy.p + ngas, 0, (n - ngas) * sizeof(double), c->stream));
+    }
+  c->n_velpred = ngas;
+  c->have_velpred = ngas > 0;
+  c->tgt_dirty = true;		// the SPH target list depends on the gas block's TimeBin (density_isactive, density.c:1035)
+  if(c->tree_valid)
+    if(glk_apply_velpred(c)) return 1;
+  return 0;
+}
+
+extern "C" int gl_gadget_pull(gl_ctx *c, const void *Pv, const void *SphPv, long long NumPart, long long N_gas)
+{
+  cudaSetDevice(c->device);
+  if(!c->have_lay) return c->fail("gl_gadget_pull: gl_gadget_bind not called");
+  const long long n = NumPart, ngas = std::min(N_gas, NumPart);
+  if(n <= 0) return c->fail("gl_gadget_pull: NumPart <= 0");
+  if(n >= (1ll << 27) + (1ll << 24)) return c->fail("gl_gadget_pull: n exceeds the 2^27 design limit of the index encoding");
+  if(ensure_pinned(c, &c->pin, &c->pin_cap, PullStage::bytes(n))) return 1;
+  if(ensure_input_buffers(c, n, ngas)) return 1;
+  if(ensure_copy_streams(c)) return 1;
+  PullStage st(c->pin, n);
+  const long long nsuper = ((n + PACK_CHUNK - 1) / PACK_CHUNK + SUPER_CHUNKS - 1) / SUPER_CHUNKS;
+  std::vector<std::atomic<int>> sc_left(nsuper);
+  std::atomic<int> b_left{0}, cuda_err{0};
+  std::atomic<long long> bad_type{0};
+  cudaEventRecord(c->ev[8], c->stream);
+  auto ja = submit_pack_A(c, (const char *) Pv, n, ngas, st, sc_left.data(), &cuda_err);
+  auto jb = submit_pack_B(c, (const char *) Pv, (const char *) SphPv, ngas, st, &b_left, c->copy_stream[0], c->ev[12], &cuda_err, &bad_type);
+  ja->wait();
+  jb->wait();
+  if(cuda_err.load()) return c->fail(std::string("gl_gadget_pull: ") + cudaGetErrorString((cudaError_t) cuda_err.load()));
+  if(bad_type.load()) return c->fail(BAD_TYPE_MSG);
+  c->have_velpred = false;
+  mark_loaded(c, n, ngas);
+  if(ngas > 0)
+    {
+      if(finish_pack_B(c, n, ngas, c->ev[12])) return 1;
+    }
+  else
+    {
+      GL_CUDA(c, cudaMemsetAsync(c->in_entropy.p, 0, n * sizeof(double), c->stream));
+      GL_CUDA(c, cudaMemsetAsync(c->in_dtentropy.p, 0, n * sizeof(double), c->stream));
+    }
+  cudaEventRecord(c->ev[9], c->stream);
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]);
+  c->st.ms_h2d = ms;
+  return 0;
+}
+
+// ---------------------------------------------------------------- result scatter ----
+// Result staging (pinned): A = gravity (acc 3n | oldacc n | gravcost n floats), B = density (hsml | numngb | density |
+// dhsml | divvel | curlvel | pressure | sinkrho | sinkentr | sinkvel 3n), C = hydro (hacc 3n | dtentr n | maxsig n)
+struct PushStage
+{
+  double *A, *B, *C;
+  static size_t bytes(long long n) { return (size_t) n * 24 * sizeof(double); }
+  PushStage(void *base, long long n)
+  {
+    A = (double *) base;
+    B = A + 5 * n;
+    C = B + 13 * n;
+  }
+};
+
+// the scatter only touches the particles that were evaluated: the active list when one was set (gl_set_targets)
+static int target_list(gl_ctx *c, const int **idx, long long *cnt)
+{
+  if(c->n_tgt_in < 0)
+    {
+      *idx = nullptr;
+      *cnt = c->n;
+      return 0;
+    }
+  if((long long) c->tgt_host.size() != c->n_tgt_in)
+    {
+      c->tgt_host.resize((size_t) c->n_tgt_in);
+      if(c->n_tgt_in > 0)
+	{
+	  GL_CUDA(c, cudaMemcpyAsync(c->tgt_host.data(), c->tgt_in.p, c->n_tgt_in * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+    }
+  *idx = c->tgt_host.data();
+  *cnt = c->n_tgt_in;
+  return 0;
+}
+
+static int d2h_gravity(gl_ctx *c, cudaStream_t s, double *A)
+{
+  const long long n = c->n;
+  GL_CUDA(c, cudaMemcpyAsync(A, c->o_acc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(A + 3 * n, c->o_oldacc.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(A + 4 * n, c->o_gravcost.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+static int d2h_density(gl_ctx *c, cudaStream_t s, double *B)
+{
+  const long long n = c->n;
+  const double *src[9] = { c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p,
+    c->o_pressure.p, c->o_sinkrho.p, c->o_sinkentr.p };
+  const bool have_other = (n > c->g_ngas);	// sink / dust fields only exist for non-gas targets
+  for(int k = 0; k < (have_other ? 9 : 7); k++)
+    GL_CUDA(c, cudaMemcpyAsync(B + k * n, src[k], n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if(have_other) GL_CUDA(c, cudaMemcpyAsync(B + 9 * n, c->o_sinkvel.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// hydro results of the P[] index range [a,b)
+static int d2h_hydro(gl_ctx *c, cudaStream_t s, double *C, long long a, long long b)
+{
+  const long long n = c->n, m = b - a;
+  if(m <= 0) return 0;
+  GL_CUDA(c, cudaMemcpyAsync(C + 3 * a, c->o_hacc.p + 3 * a, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(C + 3 * n + a, c->o_dtentr.p + a, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(C + 4 * n + a, c->o_maxsig.p + a, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// P[]: GravAccel, OldAcc, GravCost (gravtree.c:381-403, forcetree.c:2282)
+// reset_swallow: also do density()'s P[i].SwallowID = 0 (density.c:130) here - the field sits right behind
+// GravAccel/OldAcc/Hsml/NumNgb, i.e. in a cache line this loop owns anyway, and nothing reads it in between.
+static void scatter_gravity(gl_ctx *c, char *P, const double *A, const int *idx, long long cnt, bool reset_swallow)
+{
+  const long long n = c->n;
+  const gl_gadget_layout L = c->lay;
+  const double *acc = A, *old = A + 3 * n;
+  const float *cost = (const float *) (A + 4 * n);
+  const int *type = PullStage(c->pin, n).type;
+  HostPool::get().run(cnt, PACK_CHUNK, [=](long long, long long a, long long b) {
+    for(long long k = a; k < b; k++)
+      {
+	const long long i = idx ? idx[k] : k;
+	char *pi = P + i * L.p_stride;
+	if(k + PF_DIST < b)
+	  {
+	    char *pf = P + (idx ? idx[k + PF_DIST] : k + PF_DIST) * L.p_stride;
+	    __builtin_prefetch(pf + L.p_GravAccel, 1);
+	    __builtin_prefetch(pf + L.p_GravCost, 1);
+	  }
+	double *g = (double *) (pi + L.p_GravAccel);
+	g[0] = acc[3 * i]; g[1] = acc[3 * i + 1]; g[2] = acc[3 * i + 2];
+	*(double *) (pi + L.p_OldAcc) = old[i];
+	*(float *) (pi + L.p_GravCost) = cost[i];
+	if(reset_swallow)
+	  {
+	    const int ty = type[i];
+	    if(ty == 0 || ty == 5 || ty == 2) *(unsigned int *) (pi + L.p_SwallowID) = 0;
+	  }
+      }
+  });
+}
+
+// density results: P[].Hsml, .n.NumNgb, .SwallowID = 0 (density.c:130), sink / dust fields; SphP[].d.Density,
+// .h.DhsmlDensityFactor, .v.DivVel, .r.CurlVel, .Pressure (density.c:434-546, :944-988).
+// with_rho_p = false leaves SphP[].d.Density / .Pressure to scatter_hydro, which touches their cache lines anyway.
+static void scatter_density(gl_ctx *c, char *P, char *S, const double *B, const int *idx, long long cnt, bool with_rho_p, bool reset_swallow)
+{
+  const long long n = c->n, N_gas = c->g_ngas;
+  const gl_gadget_layout L = c->lay;
+  const double *hs = B, *nn = hs + n, *de = nn + n, *dh = de + n, *dv = dh + n, *cu = dv + n, *pr = cu + n, *sr = pr + n,
+    *se = sr + n, *sv = se + n;
+  const int *type = PullStage(c->pin, n).type;	// Type column of the pull staging (still valid)
+  const bool have_other = (n > N_gas);
+  HostPool::get().run(cnt, PACK_CHUNK, [=](long long, long long a, long long b) {
+    for(long long k = a; k < b; k++)
+      {
+	const long long i = idx ? idx[k] : k;
+	if(k + PF_DIST < b)
+	  {
+	    const long long ip = idx ? idx[k + PF_DIST] : k + PF_DIST;
+	    char *pf = P + ip * L.p_stride;
+	    __builtin_prefetch(pf + L.p_Hsml, 1);
+	    if(reset_swallow) __builtin_prefetch(pf + L.p_SwallowID, 1);
+	    if(ip < N_gas)
+	      {
+		char *sf = S + ip * L.sph_stride;
+		__builtin_prefetch(sf + L.s_DivVel, 1);
+		if(with_rho_p)
+		  {
+		    __builtin_prefetch(sf + L.s_Pressure, 1);
+		    __builtin_prefetch(sf + L.s_Density, 1);
+		  }
+	      }
+	  }
+	const int ty = type[i];
+	if(!(ty == 0 || ty == 5 || ty == 2)) continue;
+	char *pi = P + i * L.p_stride;
+	*(double *) (pi + L.p_Hsml) = hs[i];
+	*(double *) (pi + L.p_NumNgb) = nn[i];
+	if(reset_swallow) *(unsigned int *) (pi + L.p_SwallowID) = 0;
+	if(ty == 0 && i < N_gas)
+	  {
+	    char *si = S + i * L.sph_stride;
+	    if(with_rho_p)
+	      {
+		*(double *) (si + L.s_Pressure) = pr[i];
+		*(double *) (si + L.s_Density) = de[i];
+	      }
+	    *(double *) (si + L.s_DhsmlDensityFactor) = dh[i];
+	    *(double *) (si + L.s_DivVel) = dv[i];
+	    *(double *) (si + L.s_CurlVel) = cu[i];
+	  }
+	else if(ty == 5 && have_other)
+	  {
+	    *(double *) (pi + L.p_SinkDensity) = sr[i];
+	    *(double *) (pi + L.p_SinkEntropy) = se[i];
+	    double *v = (double *) (pi + L.p_SinkGasVel);
+	    v[0] = sv[3 * i]; v[1] = sv[3 * i + 1]; v[2] = sv[3 * i + 2];
+	  }
+	else if(ty == 2 && have_other)
+	  {
+	    *(double *) (pi + L.p_DustDensity) = sr[i];
+	    *(double *) (pi + L.p_DustEntropy) = se[i];
+	    double *v = (double *) (pi + L.p_DustGasVel);
+	    v[0] = sv[3 * i]; v[1] = sv[3 * i + 1]; v[2] = sv[3 * i + 2];
+	  }
+      }
+  });
+}
+
+// SphP[].a.HydroAccel, .e.DtEntropy, .MaxSignalVel (hydra.c:1931-1940, :583) for list entries [k0,k1); with B != NULL
+// also the SphP[].d.Density / .Pressure that scatter_density left behind (same cache lines).
+static void scatter_hydro(gl_ctx *c, char *S, const double *C, const double *B, const int *idx, long long k0, long long k1)
+{
+  const long long n = c->n, N_gas = c->g_ngas;
+  const gl_gadget_layout L = c->lay;
+  const double *ha = C, *dt = ha + 3 * n, *ms = dt + n;
+  const double *de = B ? B + 2 * n : nullptr, *pr = B ? B + 6 * n : nullptr;
+  const int *type = PullStage(c->pin, n).type;
+  HostPool::get().run(k1 - k0, PACK_CHUNK, [=](long long, long long a, long long b) {
+    a += k0;
+    b += k0;
+    for(long long k = a; k < b; k++)
+      {
+	const long long i = idx ? idx[k] : k;
+	if(k + PF_DIST < b)
+	  {
+	    const long long ip = idx ? idx[k + PF_DIST] : k + PF_DIST;
+	    if(ip < N_gas)
+	      {
+		char *sf = S + ip * L.sph_stride;
+		__builtin_prefetch(sf + L.s_MaxSignalVel, 1);
+		__builtin_prefetch(sf + L.s_HydroAccel, 1);
+	      }
+	  }
+	if(i >= N_gas || type[i] != 0) continue;
+	char *si = S + i * L.sph_stride;
+	if(pr)
+	  {
+	    *(double *) (si + L.s_Pressure) = pr[i];
+	    *(double *) (si + L.s_Density) = de[i];
+	  }
+	*(double *) (si + L.s_MaxSignalVel) = ms[i];
+	*(double *) (si + L.s_DtEntropy) = dt[i];
+	double *g = (double *) (si + L.s_HydroAccel);
+	g[0] = ha[3 * i]; g[1] = ha[3 * i + 1]; g[2] = ha[3 * i + 2];
+      }
+  });
+}
+
+extern "C" int gl_gadget_push(gl_ctx *c, void *Pv, void *SphPv, int what)
+{
+  cudaSetDevice(c->device);
+  if(!c->have_lay) return c->fail("gl_gadget_push: gl_gadget_bind not called");
+  const long long n = c->n;
+  if(c->pin_cap < PullStage::bytes(n)) return c->fail("gl_gadget_push: gl_gadget_pull has not been called for this particle set");
+  if(ensure_pinned(c, &c->pin2, &c->pin2_cap, PushStage::bytes(n))) return 1;
+  PushStage st(c->pin2, n);
+  const int *idx;
+  long long cnt;
+  if(target_list(c, &idx, &cnt)) return 1;
+  if(what & 1)
+    {
+      if(d2h_gravity(c, c->stream, st.A)) return 1;
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      scatter_gravity(c, (char *) Pv, st.A, idx, cnt, false);
+    }
+  if(what & 2)
+    {
+      if(d2h_density(c, c->stream, st.B)) return 1;
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      scatter_density(c, (char *) Pv, (char *) SphPv, st.B, idx, cnt, true, true);
+    }
+  if(what & 4)
+    {
+      if(d2h_hydro(c, c->stream, st.C, 0, n)) return 1;
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      scatter_hydro(c, (char *) SphPv, st.C, nullptr, idx, 0, cnt);
+    }
+  return 0;
+}
+
+// ---------------------------------------------------------------- the pipelined drop-in call ----
+namespace
+{
+// Wait for a copy to land WITHOUT parking inside the CUDA runtime: a thread blocked in cudaEventSynchronize was
+// measured to stall cudaStreamSynchronize calls of the GPU-driving thread until the event fired (2.7 ms per
+// step); polling with short sleeps costs no core and holds no driver lock.
+inline cudaError_t wait_event_polling(cudaEvent_t ev)
+{
+  cudaError_t e;
+  while((e = cudaEventQuery(ev)) == cudaErrorNotReady) std::this_thread::sleep_for(std::chrono::microseconds(40));
+  return e;
+}
+
+// hand-over between the thread that drives the GPU and the thread that scatters results
+struct Stages
+{
+  std::mutex m;
+  std::condition_variable cv;
+  int posted = 0;		// number of result blocks whose D2H has been enqueued (1 gravity, 2 density, 3 hydro)
+  bool abort = false;
+  void post(int k)
+  {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      posted = k;
+    }
+    cv.notify_all();
+  }
+  void stop()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      abort = true;
+    }
+    cv.notify_all();
+  }
+  bool wait_for(int k)
+  {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return abort || posted >= k; });
+    return posted >= k;
+  }
+};
+}
+
+// compute_accelerations (accel.c:27, force part :61-106) on the reference's host arrays.
+extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv, long long NumPart, long long N_gas, int mode)
+{
+  (void) mode;
+  cudaSetDevice(c->device);
+  if(!c->have_lay) return c->fail("gl_gadget_compute_accelerations: gl_gadget_bind not called");
+  const bool trace = getenv("GL_DEBUG_E2E") != nullptr;
+  auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now_ms();
+  double t_packA = 0, t_grav = 0, t_dens = 0, t_hyd = 0, t_sg = 0, t_sd = 0;
+  const long long n = NumPart, ngas = std::min(N_gas, NumPart);
+  if(n <= 0) return c->fail("gl_gadget_compute_accelerations: NumPart <= 0");
+  if(n >= (1ll << 27) + (1ll << 24)) return c->fail("gl_gadget_compute_accelerations: n exceeds the 2^27 design limit");
+  if(ensure_pinned(c, &c->pin, &c->pin_cap, PullStage::bytes(n))) return 1;
+  if(ensure_pinned(c, &c->pin2, &c->pin2_cap, PushStage::bytes(n))) return 1;
+  if(ensure_input_buffers(c, n, ngas)) return 1;
+  if(ensure_copy_streams(c)) return 1;
+  cudaStream_t cs0 = c->copy_stream[0], cs1 = c->copy_stream[1];
+  PullStage in(c->pin, n);
+  PushStage out(c->pin2, n);
+  char *P = (char *) Pv, *S = (char *) SphPv;
+
+  // ---- pull: pack A (H2D behind it on c->stream), then pack B in the background ----
+  const long long nsuper = ((n + PACK_CHUNK - 1) / PACK_CHUNK + SUPER_CHUNKS - 1) / SUPER_CHUNKS;
+  std::vector<std::atomic<int>> sc_left(nsuper);
+  std::atomic<int> b_left{0}, cuda_err{0};
+  std::atomic<long long> bad_type{0};
+  auto ja = submit_pack_A(c, P, n, ngas, in, sc_left.data(), &cuda_err);
+  auto jb = submit_pack_B(c, P, S, ngas, in, &b_left, cs0, c->ev[12], &cuda_err, &bad_type);
+  ja->wait();
+  t_packA = now_ms();
+  c->have_velpred = false;
+  mark_loaded(c, n, ngas);
+
+  const int *idx;
+  long long cnt;
+  int rc = 0;
+  Stages stages;
+  std::thread scatterer;
+  const bool saved_blocking = c->blocking_sync;
+  c->blocking_sync = true;
+  auto bail = [&](int code) {
+    c->post_launch = nullptr;
+    stages.stop();
+    jb->wait();
+    if(scatterer.joinable()) scatterer.join();
+    c->blocking_sync = saved_blocking;
+    return code;
+  };
+#define GLG_CUDA(call)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t e__ = (call);                                                                                  \
+    if(e__ != cudaSuccess) return bail(c->fail(std::string(#call) + ": " + cudaGetErrorString(e__)));         \
+  } while(0)
+  if(cuda_err.load()) return bail(c->fail(std::string("pack/H2D: ") + cudaGetErrorString((cudaError_t) cuda_err.load())));
+  if(target_list(c, &idx, &cnt)) return bail(1);
+  if(ngas == 0)
+    {
+      GLG_CUDA(cudaMemsetAsync(c->in_entropy.p, 0, n * sizeof(double), c->stream));
+      GLG_CUDA(cudaMemsetAsync(c->in_dtentropy.p, 0, n * sizeof(double), c->stream));
+    }
+
+  // ---- the scatter thread: waits for each result block to land, then runs the host pool on it ----
+  // blocks: 1 gravity, 2 density, 3 hydro of P[] indices [0,split), 4 hydro of [split,n)
+  cudaEvent_t evG = c->ev_res[0], evD = c->ev_res[1], evH1 = c->ev_res[2], evH2 = c->ev_res[3];
+  const long long split = idx ? cnt : ngas / 2;	// an explicit active list is not split
+  scatterer = std::thread([&]() {
+    cudaSetDevice(c->device);
+    jb->wait();			// FIFO pool: the SphP pack is ahead of every scatter anyway
+    if(!stages.wait_for(1)) return;
+    wait_event_polling(evG);
+    scatter_gravity(c, P, out.A, idx, cnt, true);
+    t_sg = now_ms();
+    if(!stages.wait_for(2)) return;
+    wait_event_polling(evD);
+    scatter_density(c, P, S, out.B, idx, cnt, false, false);
+    t_sd = now_ms();
+    if(!stages.wait_for(3)) return;
+    wait_event_polling(evH1);
+    scatter_hydro(c, S, out.C, out.B, idx, 0, split);
+    if(!stages.wait_for(4)) return;
+    wait_event_polling(evH2);
+    scatter_hydro(c, S, out.C, out.B, idx, split, cnt);
+  });
+  int hook_rc = 0;
+
+  // ---- GPU: gravity (tree build inside) ----
+  const bool first = (c->par.TypeOfOpeningCriterion == 1 && c->par.Ti_Current == 0 && c->par.ErrTolTheta != 0);
+  c->tgt_dirty = true;
+  if(glg_gravity(c)) return bail(1);	// accel.c:61
+  if(first)
+    if(glg_gravity(c)) return bail(1);	// accel.c:63-67
+  t_grav = now_ms();
+  GLG_CUDA(cudaEventRecord(c->ev[11], c->stream));
+  // the gravity block goes out once the density kernel has been launched (see gl_ctx::post_launch)
+  c->post_launch = [&]() {
+    if(cudaStreamWaitEvent(cs1, c->ev[11], 0) != cudaSuccess || d2h_gravity(c, cs1, out.A) || cudaEventRecord(evG, cs1) != cudaSuccess)
+      hook_rc = 1;
+    stages.post(1);
+  };
+
+  // ---- the SphP part of the state must be on the device now ----
+  jb->wait();
+  if(cuda_err.load()) return bail(c->fail(std::string("pack/H2D: ") + cudaGetErrorString((cudaError_t) cuda_err.load())));
+  if(bad_type.load()) return bail(c->fail(BAD_TYPE_MSG));
+  if(ngas > 0)
+    if(finish_pack_B(c, n, ngas, c->ev[12])) return bail(1);
+
+  if(gl_prepare_targets(c)) return bail(1);
+  const bool sph = c->n_tgt_sph > 0;
+  if(sph)
+    {
+      rc = gls_density(c);	// accel.c:84 (fires the gravity hook behind its kernel launch)
+      t_dens = now_ms();
+      if(rc || hook_rc) return bail(1);
+      GLG_CUDA(cudaEventRecord(c->ev[13], c->stream));
+      rc = glt_update_hmax(c);	// accel.c:96
+      if(rc) return bail(rc);
+      // accel.c:106 as two launches: [0,split) first, so its results travel and are scattered while the rest runs
+      long long n_lo = c->n_tgt_gas;
+      const int *tg = c->tgt_gas.p;
+      if(gls_hydro_begin(c)) return bail(1);
+      if(!idx && c->n_tgt_gas > 0)
+	{
+	  if(gl_split_gas_targets(c, split, &n_lo)) return bail(1);
+	  tg = c->tgt_gas_part.p;
+	}
+      if(gls_hydro_launch(c, tg, n_lo)) return bail(1);
+      GLG_CUDA(cudaEventRecord(c->ev[14], c->stream));
+      if(gls_hydro_launch(c, tg + n_lo, c->n_tgt_gas - n_lo)) return bail(1);
+      c->post_launch = [&]() {
+	if(cudaStreamWaitEvent(cs0, c->ev[13], 0) != cudaSuccess || d2h_density(c, cs0, out.B) || cudaEventRecord(evD, cs0) != cudaSuccess)
+	  hook_rc = 1;
+	stages.post(2);
+	if(cudaStreamWaitEvent(cs1, c->ev[14], 0) != cudaSuccess || d2h_hydro(c, cs1, out.C, 0, idx ? n : split) ||
+	   cudaEventRecord(evH1, cs1) != cudaSuccess)
+	  hook_rc = 1;
+	stages.post(3);
+      };
+      rc = gls_hydro_end(c);	// fires the hook, then waits for both launches
+      t_hyd = now_ms();
+      if(rc || hook_rc) return bail(1);
+      if(!idx)
+	if(d2h_hydro(c, c->stream, out.C, split, n)) return bail(1);
+      GLG_CUDA(cudaEventRecord(evH2, c->stream));
+      stages.post(4);
+    }
+  else
+    {
+      c->fire_post_launch();	// gravity-only particle set: the scatter thread ends after the gravity block
+      if(hook_rc) return bail(1);
+      stages.stop();
+    }
+  scatterer.join();
+  c->blocking_sync = saved_blocking;
+  if(trace)
+    fprintf(stderr, "[gl] e2e ms since entry: pack A %.1f | gravity done %.1f | gravity scattered %.1f | density done %.1f | "
+	    "density scattered %.1f | hydro done %.1f | exit %.1f  (%d pool threads)\n",
+	    t_packA - t_start, t_grav - t_start, t_sg - t_start, t_dens - t_start, t_sd - t_start, t_hyd - t_start,
+	    now_ms() - t_start, HostPool::get().threads());
+  if(trace)
+    fprintf(stderr, "[gl]     kernel events ms: keys+sort %.2f build %.2f moments %.2f walk %.2f density %.2f hmax %.2f hydro %.2f\n",
+	    c->st.ms_keys_sort, c->st.ms_treebuild, c->st.ms_moments, c->st.ms_gravity_walk, c->st.ms_density, c->st.ms_hmax, c->st.ms_hydro);
+  return rc;
+#undef GLG_CUDA
+}

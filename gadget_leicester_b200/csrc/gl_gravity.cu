@@ -214,7 +214,7 @@ int glg_gravity(gl_ctx *c)
   cudaEventRecord(c->ev[1], c->stream);
   unsigned long long tot = 0;
   GL_CUDA(c, cudaMemcpyAsync(&tot, c->d_counter.p, sizeof(tot), cudaMemcpyDeviceToHost, c->stream));
-  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, c->wait_stream());
   GL_CUDA(c, cudaGetLastError());
   float ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);

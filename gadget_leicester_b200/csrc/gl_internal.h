@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#include <functional>
 #include "../../include/gl_b200.h"
 
 #define GL_BITS 21			// BITS_PER_DIMENSION, allvars.h:58
@@ -87,6 +88,11 @@ struct gl_ctx
 
   // ---- input-order particle state (index = P[] index) ----
   DBuf<double> in_pos, in_vel, in_mass, in_hsml, in_oldacc, in_entropy, in_dtentropy;
+  // drop-in layer only: SphP[].VelPred of the gas block, kept apart from P[].Vel (node vmax uses P.Vel,
+  // forcetree.c:684; the SPH sums use VelPred, density.c:772 / hydra.c:962).  Applied to s_vh after every build.
+  DBuf<double> in_velpred;
+  long long n_velpred = 0;
+  bool have_velpred = false;
   DBuf<int> in_type, in_timebin, in_tibegstep;
   // ---- keys / sort ----
   DBuf<unsigned long long> key_m, key_m_sorted, key_ph;
@@ -122,6 +128,7 @@ struct gl_ctx
   DBuf<int2> e_rng;		// node: [first,end) range of tree-ordered particles below it
   // ---- targets ----
   DBuf<int> tgt_in;		// user-supplied P[] indices (or empty = all)
+  std::vector<int> tgt_host;	// host copy of the same list (the drop-in scatter only touches targets)
   long long n_tgt_in = -1;
   DBuf<int> tgt_sorted;		// sorted-order indices of the gravity targets
   DBuf<int> tgt_sph;		// sorted-order indices of SPH targets (gas/sink/dust)
@@ -152,6 +159,33 @@ struct gl_ctx
   cudaStream_t copy_stream[2] = { nullptr, nullptr };
 
   cudaEvent_t ev[16]{};
+  // the drop-in call keeps every host core but one busy with pack/scatter work: its long waits must sleep, not spin
+  // drop-in pipeline: called once, right after the next phase's main kernel has been launched.  Result copies are
+  // enqueued from here because a kernel submitted BEHIND a batch of D2H copies was measured to start only when
+  // the copies had finished (2.9 ms per step), although they run on another stream.
+  std::function<void()> post_launch;
+  void fire_post_launch()
+  {
+    if(post_launch)
+      {
+	std::function<void()> f = std::move(post_launch);
+	post_launch = nullptr;
+	f();
+      }
+  }
+  // hydro targets split by P[] index (drop-in pipeline: results of the first part cross PCIe while the second runs)
+  DBuf<int> tgt_gas_part;
+  DBuf<int> tgt_part_flag;
+  cudaEvent_t ev_blk = nullptr;
+  cudaEvent_t ev_res[4] = { nullptr, nullptr, nullptr, nullptr };	// "result block has landed in host memory" (blocking-sync events)
+  bool blocking_sync = false;
+  cudaError_t wait_stream()
+  {
+    if(!blocking_sync || !ev_blk) return cudaStreamSynchronize(stream);
+    cudaError_t e = cudaEventRecord(ev_blk, stream);
+    if(e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev_blk);
+  }
 
   int fail(const std::string &m)
   {
@@ -165,6 +199,7 @@ int glk_find_extent(gl_ctx *c);
 int glk_keys_and_sort(gl_ctx *c);
 int glk_export_keys(gl_ctx *c, gl_peanokey *ph, gl_peanokey *mo, int where);
 int glk_ph_order(gl_ctx *c, long long n_gas, int *order, int where);
+int glk_apply_velpred(gl_ctx *c);
 // gl_tree.cu
 int glt_build(gl_ctx *c);
 int glt_update_hmax(gl_ctx *c);
@@ -175,6 +210,10 @@ int glg_potential(gl_ctx *c);
 // gl_sph.cu
 int gls_density(gl_ctx *c);
 int gls_hydro(gl_ctx *c);
+int gls_hydro_begin(gl_ctx *c);
+int gls_hydro_launch(gl_ctx *c, const int *tgt, long long nt);
+int gls_hydro_end(gl_ctx *c);
+int gl_split_gas_targets(gl_ctx *c, long long split, long long *n_lo);
 // gl_api.cu
 int gl_prepare_targets(gl_ctx *c);
 

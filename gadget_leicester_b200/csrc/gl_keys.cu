@@ -339,6 +339,27 @@ __global__ void k_gather_sorted(long long n, const int *__restrict__ perm, const
   inv[j] = (int) i;
 }
 
+// drop-in layer: gas velocities of the SPH sums are SphP[].VelPred (see gl_internal.h in_velpred)
+__global__ void k_apply_velpred(long long ngas, const int *__restrict__ inv, const int *__restrict__ s_type,
+				const double *__restrict__ velpred, double4 *__restrict__ s_vh)
+{
+  long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= ngas) return;
+  const int p = inv[i];
+  if(s_type[p] != 0) return;
+  s_vh[p].x = velpred[3 * i];
+  s_vh[p].y = velpred[3 * i + 1];
+  s_vh[p].z = velpred[3 * i + 2];
+}
+
+int glk_apply_velpred(gl_ctx *c)
+{
+  if(!c->have_velpred || c->n_velpred <= 0) return 0;
+  k_apply_velpred<<<gl_grid(c->n_velpred, 256), 256, 0, c->stream>>>(c->n_velpred, c->inv.p, c->s_type.p, c->in_velpred.p, c->s_vh.p);
+  GL_LAUNCH_COUNT(c);
+  return 0;
+}
+
 static int sort_pairs(gl_ctx *c, const unsigned long long *kin, unsigned long long *kout, const int *vin, int *vout,
 		      long long n)
 {

@@ -1016,9 +1016,10 @@ int gls_density(gl_ctx *c)
 	c->tgt_sph.p, nt, (int) c->nentries, c->e_next.p, c->e_B.p, c->e_rng.p, c->n_child.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
 	s_entropy, c->perm.p, in, out, c->fat_p.p, c->fat_state.p, c->d_counter.p, dp);
       GL_LAUNCH_COUNT(c);
+      c->fire_post_launch();
       unsigned long long nfat = 0;
       GL_CUDA(c, cudaMemcpyAsync(&nfat, c->d_counter.p + 8, sizeof(nfat), cudaMemcpyDeviceToHost, c->stream));
-      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      GL_CUDA(c, c->wait_stream());
       GL_CUDA(c, cudaGetLastError());
       if(nfat > 0)
 	if(density_fat_path(c, (int) std::min<unsigned long long>(nfat, FAT_MAX), in, out, s_entropy, dp)) return 1;
@@ -1398,43 +1399,53 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
     }
 }
 
-int gls_hydro(gl_ctx *c)
+int gls_hydro_begin(gl_ctx *c)
 {
   if(!c->tree_valid)
     if(glt_build(c)) return 1;
   if(c->par.ComovingIntegrationOn) return c->fail("hydro_force: ComovingIntegrationOn != 0 is not implemented");
   if(c->o_density.cap < (size_t) c->n) return c->fail("hydro_force: density() has not been run (SphP.Density unknown)");
   if(gl_prepare_targets(c)) return 1;
-  long long n = c->n, nt = c->n_tgt_gas;
+  long long n = c->n;
   GL_CUDA(c, c->o_hacc.ensure(3 * n));
   GL_CUDA(c, c->o_dtentr.ensure(n));
   GL_CUDA(c, c->o_maxsig.ensure(n));
   GL_CUDA(c, c->o_hydropairs.ensure(n));
   GL_CUDA(c, c->h_q.ensure(n + 1));
   GL_CUDA(c, c->h_r.ensure(n + 1));
-  gl_dparams dp = gl_make_dparams(c);
   cudaEventRecord(c->ev[0], c->stream);
   k_hydro_prep<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->perm.p, c->s_type.p, c->s_vh.p, c->o_density.p, c->o_pressure.p,
 							c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p, c->in_timebin.p, c->h_q.p,
 							c->h_r.p);
   GL_LAUNCH_COUNT(c);
-  if(nt > 0)
+  return 0;
+}
+
+// one launch over a list of gas targets (tree indices, Peano-Hilbert ordered)
+int gls_hydro_launch(gl_ctx *c, const int *tgt, long long nt)
+{
+  if(nt <= 0) return 0;
+  static bool attr_done = false;
+  if(!attr_done)
     {
-      static bool attr_done = false;
-      if(!attr_done)
-	{
-	  GL_CUDA(c, cudaFuncSetAttribute(k_hydro, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (SPH_WARPS * sizeof(WarpStage))));
-	  attr_done = true;
-	}
-      k_hydro<<<gl_grid(nt, SPH_BLOCK), SPH_BLOCK, SPH_WARPS * sizeof(WarpStage), c->stream>>>(c->tgt_gas.p, nt, (int) c->nentries, c->e_next.p, c->e_B.p,
-								  c->e_hmax.p, c->e_rng.p, c->n_child.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
-								  c->h_q.p, c->h_r.p, c->perm.p, c->o_pressure.p, c->o_dhsml.p,
-								  c->o_divvel.p, c->o_curlvel.p, c->o_hacc.p, c->o_dtentr.p,
-								  c->o_maxsig.p, c->o_hydropairs.p, dp);
-      GL_LAUNCH_COUNT(c);
+      GL_CUDA(c, cudaFuncSetAttribute(k_hydro, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (SPH_WARPS * sizeof(WarpStage))));
+      attr_done = true;
     }
+  gl_dparams dp = gl_make_dparams(c);
+  k_hydro<<<gl_grid(nt, SPH_BLOCK), SPH_BLOCK, SPH_WARPS * sizeof(WarpStage), c->stream>>>(tgt, nt, (int) c->nentries, c->e_next.p, c->e_B.p,
+							  c->e_hmax.p, c->e_rng.p, c->n_child.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
+							  c->h_q.p, c->h_r.p, c->perm.p, c->o_pressure.p, c->o_dhsml.p,
+							  c->o_divvel.p, c->o_curlvel.p, c->o_hacc.p, c->o_dtentr.p,
+							  c->o_maxsig.p, c->o_hydropairs.p, dp);
+  GL_LAUNCH_COUNT(c);
+  return 0;
+}
+
+int gls_hydro_end(gl_ctx *c)
+{
   cudaEventRecord(c->ev[1], c->stream);
-  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->fire_post_launch();
+  GL_CUDA(c, c->wait_stream());
   GL_CUDA(c, cudaGetLastError());
   float ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
@@ -1447,6 +1458,13 @@ int gls_hydro(gl_ctx *c)
 	    (double) ph[0], (double) ph[1], (double) ph[2], (double) ph[3], (double) ph[4], (double) ph[5]);
   }
 #endif
-  c->st.hydro_targets = nt;
+  c->st.hydro_targets = c->n_tgt_gas;
   return 0;
+}
+
+int gls_hydro(gl_ctx *c)
+{
+  if(gls_hydro_begin(c)) return 1;
+  if(gls_hydro_launch(c, c->tgt_gas.p, c->n_tgt_gas)) return 1;
+  return gls_hydro_end(c);
 }

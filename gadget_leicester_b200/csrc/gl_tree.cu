@@ -396,6 +396,7 @@ int glt_build(gl_ctx *c)
       k_entries_range<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->n_first.p, c->n_end.p, c->e_rng.p);
       GL_LAUNCH_COUNT(c);
     }
+  if(glk_apply_velpred(c)) return 1;	// after the moments: node vmax is built from P[].Vel (forcetree.c:684)
   cudaEventRecord(c->ev[3], c->stream);
   GL_CUDA(c, cudaGetLastError());
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
