@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"      # VERSION and WARN print NCCL's banner on stdout; rank 0 prints ONE JSON line
 
 METRIC = "gravity particle-node interactions/s per full force step (gravity+density+hydro)"
 UNIT = "interactions/s"
@@ -195,6 +197,10 @@ def big_config(args):
     torch.cuda.empty_cache()
     dfp.compute_accelerations(**kw)          # settle: Barnes-Hut pass / cold-start density
     cold_passes = dfp.fp.stats()["density_passes_max"]
+    if world > 1 and args.config == 3 and not args.no_rebalance:
+        # domain.c:1075: the next decomposition balances the measured work (GravCost), not the particle count
+        dfp.rebalance()
+        dfp.compute_accelerations(**kw)
 
     def one_step():
         dfp.fp.set_TreeReconstructFlag(1)
@@ -269,6 +275,9 @@ def main():
     ap.add_argument("--config", type=int, default=0, choices=[0, 3, 4],
                     help="0: disc (default, headline); 3: Plummer sphere, gravity only; 4: uniform gas cube, density+hydro only")
     ap.add_argument("--nparts", type=int, default=0, help="total particles for --config 3/4 (default 2^27)")
+    ap.add_argument("--rebalance", action="store_true", help="config 0: re-split the Peano-Hilbert segments by the settle step's GravCost")
+    ap.add_argument("--no-rebalance", action="store_true", help="keep the equal-count Peano-Hilbert split (default: work-balanced "
+                    "split from the settle step's GravCost, domain.c:1075)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -307,6 +316,11 @@ def main():
     # settle: Barnes-Hut pass (OldAcc=0) then cold-start density; afterwards every step is a steady-state step
     dfp.compute_accelerations()
     cold_passes = dfp.fp.stats()["density_passes_max"]
+    if world > 1 and args.rebalance:
+        # domain.c:1075 balances the measured GRAVITY work; two thirds of this step is SPH work, which equal counts
+        # balance better on the disc (measured at N=2: 18.3 ms equal counts, 18.7 ms GravCost-balanced) - so off by default
+        dfp.rebalance()
+        dfp.compute_accelerations()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -326,6 +340,7 @@ def main():
     tot_ms, acc = 0.0, dict(ms_keys_sort=0, ms_treebuild=0, ms_moments=0, ms_gravity_walk=0, ms_density=0, ms_hmax=0, ms_hydro=0)
     inter = 0
     passes = []
+    wall = {}
     for _ in range(args.steps):
         flush.fill_(1)                         # L2 flush between timed iterations (untimed)
         torch.cuda.synchronize()
@@ -340,6 +355,8 @@ def main():
             acc[k] += st[k]
         inter += st["interactions"]
         passes.append(st["density_passes_max"])
+        for k, v in dfp.t.items():
+            wall[k] = wall.get(k, 0.0) + v * 1e3 / args.steps
     launches = dfp.fp.stats()["kernel_launches"]
     clocks = sampler.stop()
     t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
@@ -377,6 +394,39 @@ def main():
 
     # ---- e2e: the same step through the drop-in boundary with host P[]/SphP[] (rank-local set) ----
     e2e = None
+    if not args.no_e2e and world > 1:
+        # every rank owns the host P[]/SphP[] of its Peano-Hilbert segment, like every MPI rank of the reference
+        from gadget_leicester_b200.multigpu import DistributedDropIn
+        seg = dfp.order[dfp.lo:dfp.hi]
+        ps_seg = {k: (v[seg] if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+        ps_seg["hsml"] = dfp.res["hsml"][dfp.lo:dfp.hi].cpu().numpy()
+        ps_seg["oldacc"] = dfp.res["oldacc"][dfp.lo:dfp.hi].cpu().numpy()
+        dfp.fp.set_params(ErrTolTheta=0.0)
+        arr = aos.GadgetArrays(ps_seg, pinned=True)
+        drop = DistributedDropIn(dfp, arr)
+        for _ in range(2):
+            dfp.fp.set_TreeReconstructFlag(1)
+            drop.compute_accelerations()
+        ksteps = max(2, min(args.steps, 5))
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        ie = 0
+        for _ in range(ksteps):
+            dfp.fp.set_TreeReconstructFlag(1)
+            drop.compute_accelerations()
+            ie += dfp.fp.stats()["interactions"]
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ksteps
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        ii = torch.tensor([float(ie) / ksteps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ii, op=dist.ReduceOp.SUM)
+        h2d, d2h = drop.bytes_per_step()
+        e2e = dict(value=float(ii.item()) / float(tt.item()), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
+                   ms_per_step=float(tt.item()) * 1e3, steps=ksteps,
+                   api="DistributedDropIn.compute_accelerations: every rank's own pinned host P[]/SphP[] segment "
+                       "(gl_gadget_pack_segment + H2D, all-gathers, force path, async D2H + scatter); max over ranks")
     if not args.no_e2e and world == 1:
         res_h = dfp.res["hsml"].cpu().numpy()
         res_o = dfp.res["oldacc"].cpu().numpy()
@@ -432,7 +482,8 @@ def main():
                             step="tree rebuild + gravity (relative criterion) + density + hmax + hydro"),
                 interactions_per_step=inter_per_step, sph_updates_per_s=(ngas / (ms_per_step * 1e-3)),
                 force_eval_ms=ms_per_step, phase_ms=phase, density_passes=dict(cold_start=cold_passes, steady=passes),
-                gpu_launches=int(launches), clocks=clocks, roofline=roof)
+                gpu_launches=int(launches), clocks=clocks, roofline=roof,
+                wall_phase_ms={k: round(v, 3) for k, v in wall.items()})
     if e2e is not None:
         line["e2e"] = e2e
     if cpu_base is not None:

@@ -39,6 +39,9 @@ extern "C" void gl_destroy(gl_ctx *c)
 {
   if(!c) return;
   cudaSetDevice(c->device);
+  c->fire_post_launch();
+  for(auto &t : c->push_threads)
+    if(t.joinable()) t.join();
   cudaStreamSynchronize(c->stream);
   c->in_velpred.release();
   if(c->ev_blk) cudaEventDestroy(c->ev_blk);
@@ -163,6 +166,143 @@ extern "C" int gl_set_sph_state(gl_ctx *c, const double *density, const double *
   return 0;
 }
 
+// ---------------------------------------------------------------- multi-GPU: load from all-gather buffers ----
+#define GL_MAX_RANKS 16
+struct gl_segments
+{
+  long long start[GL_MAX_RANKS + 1];
+  int world;
+};
+
+__device__ __forceinline__ int seg_of(const gl_segments &sg, long long g)
+{
+  int r = 0;
+  while(r + 1 < sg.world && g >= sg.start[r + 1]) r++;
+  return r;
+}
+
+// Block layout (per rank, m = padded segment length), gravity-essential rows first so a gravity-only exchange can
+// send a prefix: doubles [pos 3m | mass m | hsml m | oldacc m || vel 3m | entropy m | dtentropy m], ints [type m ||
+// timebin m | ti_begstep m].  full = 0: only the part before "||" is present (rows_f = 6, rows_i = 1).
+__global__ void k_unpack_state(long long n, gl_segments sg, long long m, int full, const double *__restrict__ fb, const int *__restrict__ ib,
+			       double *__restrict__ pos, double *__restrict__ vel, double *__restrict__ mass,
+			       double *__restrict__ hsml, double *__restrict__ oldacc, double *__restrict__ entropy,
+			       double *__restrict__ dtentropy, int *__restrict__ type, int *__restrict__ timebin,
+			       int *__restrict__ tibeg)
+{
+  const long long g = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(g >= n) return;
+  const int r = seg_of(sg, g);
+  const long long j = g - sg.start[r];
+  const double *f = fb + (long long) r * (full ? 11 : 6) * m;
+  const int *q = ib + (long long) r * (full ? 3 : 1) * m;
+  pos[3 * g] = f[3 * j]; pos[3 * g + 1] = f[3 * j + 1]; pos[3 * g + 2] = f[3 * j + 2];
+  mass[g] = f[3 * m + j];
+  hsml[g] = f[4 * m + j];
+  oldacc[g] = f[5 * m + j];
+  type[g] = q[j];
+  if(full)
+    {
+      vel[3 * g] = f[6 * m + 3 * j]; vel[3 * g + 1] = f[6 * m + 3 * j + 1]; vel[3 * g + 2] = f[6 * m + 3 * j + 2];
+      entropy[g] = f[9 * m + j];
+      dtentropy[g] = f[10 * m + j];
+      timebin[g] = q[m + j];
+      tibeg[g] = q[2 * m + j];
+    }
+}
+
+static int make_segments(gl_ctx *c, gl_segments &sg, int world, const long long *seg_start, long long n, long long m)
+{
+  if(world < 1 || world > GL_MAX_RANKS) return c->fail("gathered load: world size out of range (1..16)");
+  sg.world = world;
+  for(int r = 0; r <= world; r++) sg.start[r] = seg_start[r];
+  if(sg.start[0] != 0 || sg.start[world] != n) return c->fail("gathered load: segments do not cover [0,n)");
+  for(int r = 0; r < world; r++)
+    if(sg.start[r + 1] < sg.start[r] || sg.start[r + 1] - sg.start[r] > m) return c->fail("gathered load: bad segment");
+  return 0;
+}
+
+extern "C" int gl_load_particles_gathered(gl_ctx *c, long long n, int world, long long m, const long long *seg_start,
+					   const double *f64buf, const int *i32buf, int full)
+{
+  cudaSetDevice(c->device);
+  if(n <= 0) return c->fail("gl_load_particles_gathered: n <= 0");
+  if(n >= (1ll << 27) + (1ll << 24)) return c->fail("gl_load_particles_gathered: n exceeds the 2^27 design limit of the index encoding");
+  gl_segments sg;
+  if(make_segments(c, sg, world, seg_start, n, m)) return 1;
+  GL_CUDA(c, c->in_pos.ensure(3 * (size_t) n));
+  GL_CUDA(c, c->in_vel.ensure(3 * (size_t) n));
+  GL_CUDA(c, c->in_mass.ensure((size_t) n));
+  GL_CUDA(c, c->in_type.ensure((size_t) n));
+  GL_CUDA(c, c->in_hsml.ensure((size_t) n));
+  GL_CUDA(c, c->in_oldacc.ensure((size_t) n));
+  GL_CUDA(c, c->in_timebin.ensure((size_t) n));
+  GL_CUDA(c, c->in_tibegstep.ensure((size_t) n));
+  GL_CUDA(c, c->in_entropy.ensure((size_t) n));
+  GL_CUDA(c, c->in_dtentropy.ensure((size_t) n));
+  if(!full)
+    {				// gravity-only exchange: the SPH-side inputs are not sent; keep them defined
+      GL_CUDA(c, cudaMemsetAsync(c->in_vel.p, 0, 3 * n * sizeof(double), c->stream));
+      GL_CUDA(c, cudaMemsetAsync(c->in_entropy.p, 0, n * sizeof(double), c->stream));
+      GL_CUDA(c, cudaMemsetAsync(c->in_dtentropy.p, 0, n * sizeof(double), c->stream));
+      GL_CUDA(c, cudaMemsetAsync(c->in_timebin.p, 0, n * sizeof(int), c->stream));
+      GL_CUDA(c, cudaMemsetAsync(c->in_tibegstep.p, 0, n * sizeof(int), c->stream));
+    }
+  k_unpack_state<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, sg, m, full, f64buf, i32buf, c->in_pos.p, c->in_vel.p, c->in_mass.p, c->in_hsml.p,
+							  c->in_oldacc.p, c->in_entropy.p, c->in_dtentropy.p, c->in_type.p,
+							  c->in_timebin.p, c->in_tibegstep.p);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, cudaGetLastError());
+  c->n = n;
+  c->tree_valid = false;
+  c->tree_flag = true;
+  c->tgt_dirty = true;
+  c->have_velpred = false;
+  if(!c->domain_imposed) c->have_domain = false;
+  return 0;
+}
+
+__global__ void k_unpack_sph(long long n, gl_segments sg, long long m, const double *__restrict__ fb, const int *__restrict__ inv,
+			     double4 *__restrict__ s_vh, double *__restrict__ hsml, double *__restrict__ density,
+			     double *__restrict__ pressure, double *__restrict__ dhsml, double *__restrict__ divvel,
+			     double *__restrict__ curlvel)
+{
+  const long long g = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(g >= n) return;
+  const int r = seg_of(sg, g);
+  const long long j = g - sg.start[r];
+  const double *f = fb + (long long) r * 6 * m;
+  const double h = f[j];
+  hsml[g] = h;
+  if(inv) s_vh[inv[g]].w = h;
+  density[g] = f[m + j];
+  pressure[g] = f[2 * m + j];
+  dhsml[g] = f[3 * m + j];
+  divvel[g] = f[4 * m + j];
+  curlvel[g] = f[5 * m + j];
+}
+
+extern "C" int gl_set_sph_state_gathered(gl_ctx *c, int world, long long m, const long long *seg_start, const double *buf)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n;
+  if(n <= 0) return c->fail("gl_set_sph_state_gathered: no particles");
+  gl_segments sg;
+  if(make_segments(c, sg, world, seg_start, n, m)) return 1;
+  GL_CUDA(c, c->o_density.ensure((size_t) n));
+  GL_CUDA(c, c->o_pressure.ensure((size_t) n));
+  GL_CUDA(c, c->o_dhsml.ensure((size_t) n));
+  GL_CUDA(c, c->o_divvel.ensure((size_t) n));
+  GL_CUDA(c, c->o_curlvel.ensure((size_t) n));
+  k_unpack_sph<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, sg, m, buf, c->tree_valid ? c->inv.p : nullptr, c->s_vh.p, c->in_hsml.p,
+							c->o_density.p, c->o_pressure.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 extern "C" int gl_domain_find_extent(gl_ctx *c, double *out8)
 {
   cudaSetDevice(c->device);
@@ -213,10 +353,18 @@ extern "C" int gl_get_nodes(gl_ctx *c, double *table, long long cap)
 extern "C" void gl_set_tree_reconstruct_flag(gl_ctx *c, int flag) { c->tree_flag = flag != 0; }
 
 // ---------------------------------------------------------------- targets ----
+extern "C" int gl_set_targets_ordered(gl_ctx *c, const int *index, long long n, int where)
+{
+  if(gl_set_targets(c, index, n, where)) return 1;
+  c->tgt_ordered = (c->n_tgt_in >= 0);
+  return 0;
+}
+
 extern "C" int gl_set_targets(gl_ctx *c, const int *index, long long n, int where)
 {
   cudaSetDevice(c->device);
   c->tgt_dirty = true;
+  c->tgt_ordered = false;
   c->tgt_host.clear();
   if(n < 0 || !index)
     {
@@ -240,15 +388,16 @@ __global__ void k_mark(long long nt, const int *__restrict__ tin, const int *__r
 }
 
 // flags: bit0 target, bit1 SPH target (density_isactive, density.c:1035-1057), bit2 gas target
-// thread k handles the k-th particle along the Peano-Hilbert curve, so the selected lists come out in PH order
-__global__ void k_classify(long long n, const int *__restrict__ ph_order, const int *__restrict__ s_type,
+// thread k handles the k-th candidate: the k-th particle along the Peano-Hilbert curve (cand = ph_order), or the
+// k-th entry of an ordered target list (cand built by k_list_candidates), so the selected lists keep that order
+__global__ void k_classify(long long n, const int *__restrict__ cand, const int *__restrict__ s_type,
 			   const int *__restrict__ in_timebin, const int *__restrict__ perm, int all,
 			   const int *__restrict__ mark, int *__restrict__ flag, int *__restrict__ f_sph,
 			   int *__restrict__ f_gas)
 {
   long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(k >= n) return;
-  const int i = ph_order[k];
+  const int i = cand[k];
   int f = all ? 1 : mark[i];
   int ty = s_type[i];
   flag[k] = f;
@@ -256,14 +405,19 @@ __global__ void k_classify(long long n, const int *__restrict__ ph_order, const 
   f_gas[k] = f && ty == 0;
 }
 
-static int select_flagged(gl_ctx *c, const int *flags, int *out, long long n, long long *count)
+__global__ void k_list_candidates(long long nt, const int *__restrict__ tin, const int *__restrict__ inv, int *__restrict__ cand)
 {
-  const int *it = c->ph_order.p;
+  long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(k < nt) cand[k] = inv[tin[k]];
+}
+
+static int select_flagged(gl_ctx *c, const int *items, const int *flags, int *out, long long n, long long *count)
+{
   size_t tmp = 0;
   int *dcount = c->scan_tmp_i.p + 60;
-  cub::DeviceSelect::Flagged(nullptr, tmp, it, flags, out, dcount, (int) n, c->stream);
+  cub::DeviceSelect::Flagged(nullptr, tmp, items, flags, out, dcount, (int) n, c->stream);
   GL_CUDA(c, c->cub_tmp.ensure(tmp));
-  GL_CUDA(c, cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, it, flags, out, dcount, (int) n, c->stream));
+  GL_CUDA(c, cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, items, flags, out, dcount, (int) n, c->stream));
   c->kernel_launches += 2;
   int h = 0;
   GL_CUDA(c, cudaMemcpyAsync(&h, dcount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -284,21 +438,44 @@ int gl_prepare_targets(gl_ctx *c)
   GL_CUDA(c, c->scan_tmp_i.ensure(64));
   int *f0 = c->tgt_flag.p, *f1 = f0 + n, *f2 = f1 + n, *mark = f2 + n;
   int all = c->n_tgt_in < 0;
-  if(!all)
+  const int *cand;
+  long long ncand = n;
+  if(!all && c->tgt_ordered)
     {
-      GL_CUDA(c, cudaMemsetAsync(mark, 0, n * sizeof(int), c->stream));
-      if(c->n_tgt_in > 0)
+      // the caller's list order is kept: candidates = the list itself, every one of them a target
+      ncand = c->n_tgt_in;
+      if(ncand > n) return c->fail("targets: ordered list longer than the particle set");
+      if(ncand > 0)
 	{
-	  k_mark<<<gl_grid(c->n_tgt_in, 256), 256, 0, c->stream>>>(c->n_tgt_in, c->tgt_in.p, c->inv.p, mark);
+	  k_list_candidates<<<gl_grid(ncand, 256), 256, 0, c->stream>>>(ncand, c->tgt_in.p, c->inv.p, mark);
 	  GL_LAUNCH_COUNT(c);
 	}
+      cand = mark;
+      all = 1;
     }
-  k_classify<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->ph_order.p, c->s_type.p, c->in_timebin.p, c->perm.p, all, mark,
-						      f0, f1, f2);
-  GL_LAUNCH_COUNT(c);
-  if(select_flagged(c, f0, c->tgt_sorted.p, n, &c->n_tgt)) return 1;
-  if(select_flagged(c, f1, c->tgt_sph.p, n, &c->n_tgt_sph)) return 1;
-  if(select_flagged(c, f2, c->tgt_gas.p, n, &c->n_tgt_gas)) return 1;
+  else
+    {
+      if(glk_ph_sequence(c)) return 1;	// the tree may have been built while an ordered list was set
+      cand = c->ph_order.p;
+      if(!all)
+	{
+	  GL_CUDA(c, cudaMemsetAsync(mark, 0, n * sizeof(int), c->stream));
+	  if(c->n_tgt_in > 0)
+	    {
+	      k_mark<<<gl_grid(c->n_tgt_in, 256), 256, 0, c->stream>>>(c->n_tgt_in, c->tgt_in.p, c->inv.p, mark);
+	      GL_LAUNCH_COUNT(c);
+	    }
+	}
+    }
+  c->n_tgt = c->n_tgt_sph = c->n_tgt_gas = 0;
+  if(ncand > 0)
+    {
+      k_classify<<<gl_grid(ncand, 256), 256, 0, c->stream>>>(ncand, cand, c->s_type.p, c->in_timebin.p, c->perm.p, all, mark, f0, f1, f2);
+      GL_LAUNCH_COUNT(c);
+      if(select_flagged(c, cand, f0, c->tgt_sorted.p, ncand, &c->n_tgt)) return 1;
+      if(select_flagged(c, cand, f1, c->tgt_sph.p, ncand, &c->n_tgt_sph)) return 1;
+      if(select_flagged(c, cand, f2, c->tgt_gas.p, ncand, &c->n_tgt_gas)) return 1;
+    }
   c->tgt_dirty = false;
   return 0;
 }
@@ -400,12 +577,36 @@ extern "C" int gl_compute_accelerations(gl_ctx *c, int mode)
 }
 
 // ---------------------------------------------------------------- results ----
+// cnt = elements for the whole particle set; with a result range set (gl_set_result_range) only the elements of
+// particles [first, first+count) are copied, to the same positions of dst
 template <class T> static int get(gl_ctx *c, T *dst, const DBuf<T> &src, size_t cnt, int where, const char *what)
 {
   if(!dst) return 0;
   if(src.cap < cnt) return c->fail(std::string("result not available: ") + what);
-  GL_CUDA(c, cudaMemcpyAsync(dst, src.p, cnt * sizeof(T), where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+  size_t off = 0;
+  if(c->res_count >= 0 && c->n > 0)
+    {
+      const size_t w = cnt / (size_t) c->n;	// 1 or 3 values per particle
+      off = (size_t) c->res_first * w;
+      cnt = (size_t) c->res_count * w;
+    }
+  if(cnt == 0) return 0;
+  GL_CUDA(c, cudaMemcpyAsync(dst + off, src.p + off, cnt * sizeof(T), where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
 			     c->stream));
+  return 0;
+}
+
+extern "C" int gl_set_result_range(gl_ctx *c, long long first, long long count)
+{
+  if(count < 0)
+    {
+      c->res_first = 0;
+      c->res_count = -1;
+      return 0;
+    }
+  if(first < 0 || first + count > c->n) return c->fail("gl_set_result_range: range outside the particle set");
+  c->res_first = first;
+  c->res_count = count;
   return 0;
 }
 

@@ -203,6 +203,8 @@ static void mark_loaded(gl_ctx *c, long long n, long long ngas)
   c->n = n;
   c->g_numpart = n;
   c->g_ngas = ngas;
+  c->g_off = 0;
+  c->g_type = PullStage(c->pin, n).type;
   c->tree_valid = false;
   c->tree_flag = true;
   c->tgt_dirty = true;
@@ -288,7 +290,7 @@ static int target_list(gl_ctx *c, const int **idx, long long *cnt)
   if(c->n_tgt_in < 0)
     {
       *idx = nullptr;
-      *cnt = c->n;
+      *cnt = c->g_numpart;
       return 0;
     }
   if((long long) c->tgt_host.size() != c->n_tgt_in)
@@ -305,48 +307,48 @@ static int target_list(gl_ctx *c, const int **idx, long long *cnt)
   return 0;
 }
 
+// Results are indexed like the global particle list; the host arrays hold [g_off, g_off + g_numpart) of it.
 static int d2h_gravity(gl_ctx *c, cudaStream_t s, double *A)
 {
-  const long long n = c->n;
-  GL_CUDA(c, cudaMemcpyAsync(A, c->o_acc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  GL_CUDA(c, cudaMemcpyAsync(A + 3 * n, c->o_oldacc.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  GL_CUDA(c, cudaMemcpyAsync(A + 4 * n, c->o_gravcost.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  const long long n = c->g_numpart, o = c->g_off;
+  GL_CUDA(c, cudaMemcpyAsync(A, c->o_acc.p + 3 * o, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(A + 3 * n, c->o_oldacc.p + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(A + 4 * n, c->o_gravcost.p + o, n * sizeof(float), cudaMemcpyDeviceToHost, s));
   return 0;
 }
 
 static int d2h_density(gl_ctx *c, cudaStream_t s, double *B)
 {
-  const long long n = c->n;
+  const long long n = c->g_numpart, o = c->g_off;
   const double *src[9] = { c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p,
     c->o_pressure.p, c->o_sinkrho.p, c->o_sinkentr.p };
   const bool have_other = (n > c->g_ngas);	// sink / dust fields only exist for non-gas targets
   for(int k = 0; k < (have_other ? 9 : 7); k++)
-    GL_CUDA(c, cudaMemcpyAsync(B + k * n, src[k], n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if(have_other) GL_CUDA(c, cudaMemcpyAsync(B + 9 * n, c->o_sinkvel.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GL_CUDA(c, cudaMemcpyAsync(B + k * n, src[k] + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if(have_other) GL_CUDA(c, cudaMemcpyAsync(B + 9 * n, c->o_sinkvel.p + 3 * o, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
   return 0;
 }
 
-// hydro results of the P[] index range [a,b)
+// hydro results of the local index range [a,b)
 static int d2h_hydro(gl_ctx *c, cudaStream_t s, double *C, long long a, long long b)
 {
-  const long long n = c->n, m = b - a;
+  const long long n = c->g_numpart, o = c->g_off, m = b - a;
   if(m <= 0) return 0;
-  GL_CUDA(c, cudaMemcpyAsync(C + 3 * a, c->o_hacc.p + 3 * a, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, s));
-  GL_CUDA(c, cudaMemcpyAsync(C + 3 * n + a, c->o_dtentr.p + a, m * sizeof(double), cudaMemcpyDeviceToHost, s));
-  GL_CUDA(c, cudaMemcpyAsync(C + 4 * n + a, c->o_maxsig.p + a, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(C + 3 * a, c->o_hacc.p + 3 * (o + a), 3 * m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(C + 3 * n + a, c->o_dtentr.p + o + a, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(C + 4 * n + a, c->o_maxsig.p + o + a, m * sizeof(double), cudaMemcpyDeviceToHost, s));
   return 0;
 }
 
-// P[]: GravAccel, OldAcc, GravCost (gravtree.c:381-403, forcetree.c:2282)
 // reset_swallow: also do density()'s P[i].SwallowID = 0 (density.c:130) here - the field sits right behind
 // GravAccel/OldAcc/Hsml/NumNgb, i.e. in a cache line this loop owns anyway, and nothing reads it in between.
 static void scatter_gravity(gl_ctx *c, char *P, const double *A, const int *idx, long long cnt, bool reset_swallow)
 {
-  const long long n = c->n;
+  const long long n = c->g_numpart;
   const gl_gadget_layout L = c->lay;
   const double *acc = A, *old = A + 3 * n;
   const float *cost = (const float *) (A + 4 * n);
-  const int *type = PullStage(c->pin, n).type;
+  const int *type = c->g_type;
   HostPool::get().run(cnt, PACK_CHUNK, [=](long long, long long a, long long b) {
     for(long long k = a; k < b; k++)
       {
@@ -376,11 +378,11 @@ static void scatter_gravity(gl_ctx *c, char *P, const double *A, const int *idx,
 // with_rho_p = false leaves SphP[].d.Density / .Pressure to scatter_hydro, which touches their cache lines anyway.
 static void scatter_density(gl_ctx *c, char *P, char *S, const double *B, const int *idx, long long cnt, bool with_rho_p, bool reset_swallow)
 {
-  const long long n = c->n, N_gas = c->g_ngas;
+  const long long n = c->g_numpart, N_gas = c->g_ngas;
   const gl_gadget_layout L = c->lay;
   const double *hs = B, *nn = hs + n, *de = nn + n, *dh = de + n, *dv = dh + n, *cu = dv + n, *pr = cu + n, *sr = pr + n,
     *se = sr + n, *sv = se + n;
-  const int *type = PullStage(c->pin, n).type;	// Type column of the pull staging (still valid)
+  const int *type = c->g_type;	// Type column of the pack staging (still valid)
   const bool have_other = (n > N_gas);
   HostPool::get().run(cnt, PACK_CHUNK, [=](long long, long long a, long long b) {
     for(long long k = a; k < b; k++)
@@ -443,11 +445,11 @@ static void scatter_density(gl_ctx *c, char *P, char *S, const double *B, const 
 // also the SphP[].d.Density / .Pressure that scatter_density left behind (same cache lines).
 static void scatter_hydro(gl_ctx *c, char *S, const double *C, const double *B, const int *idx, long long k0, long long k1)
 {
-  const long long n = c->n, N_gas = c->g_ngas;
+  const long long n = c->g_numpart, N_gas = c->g_ngas;
   const gl_gadget_layout L = c->lay;
   const double *ha = C, *dt = ha + 3 * n, *ms = dt + n;
   const double *de = B ? B + 2 * n : nullptr, *pr = B ? B + 6 * n : nullptr;
-  const int *type = PullStage(c->pin, n).type;
+  const int *type = c->g_type;
   HostPool::get().run(k1 - k0, PACK_CHUNK, [=](long long, long long a, long long b) {
     a += k0;
     b += k0;
@@ -483,8 +485,8 @@ extern "C" int gl_gadget_push(gl_ctx *c, void *Pv, void *SphPv, int what)
 {
   cudaSetDevice(c->device);
   if(!c->have_lay) return c->fail("gl_gadget_push: gl_gadget_bind not called");
-  const long long n = c->n;
-  if(c->pin_cap < PullStage::bytes(n)) return c->fail("gl_gadget_push: gl_gadget_pull has not been called for this particle set");
+  const long long n = c->g_numpart;
+  if(!c->g_type || n <= 0) return c->fail("gl_gadget_push: gl_gadget_pull has not been called for this particle set");
   if(ensure_pinned(c, &c->pin2, &c->pin2_cap, PushStage::bytes(n))) return 1;
   PushStage st(c->pin2, n);
   const int *idx;
@@ -721,4 +723,139 @@ extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv,
 	    c->st.ms_keys_sort, c->st.ms_treebuild, c->st.ms_moments, c->st.ms_gravity_walk, c->st.ms_density, c->st.ms_hmax, c->st.ms_hydro);
   return rc;
 #undef GLG_CUDA
+}
+
+// ---------------------------------------------------------------- multi-GPU: one rank's P[] / SphP[] ----
+// With the sources replicated by all-gathers (gl_load_particles_gathered) every rank still owns its own host arrays,
+// like every MPI rank of the reference does.  pack_segment turns them into this rank's all-gather block;
+// push_segment_async returns the rank's slice of a result block to them while the next phase computes.
+extern "C" int gl_gadget_pack_segment(gl_ctx *c, const void *Pv, const void *SphPv, long long NumPart, long long N_gas, long long m,
+				       long long global_offset, double *f64_dev, int *i32_dev)
+{
+  cudaSetDevice(c->device);
+  if(!c->have_lay) return c->fail("gl_gadget_pack_segment: gl_gadget_bind not called");
+  const long long n = NumPart, ngas = std::min(N_gas, NumPart);
+  if(n < 0 || n > m) return c->fail("gl_gadget_pack_segment: segment longer than the block (m)");
+  const size_t fbytes = (size_t) m * 11 * sizeof(double), ibytes = (size_t) m * 3 * sizeof(int);
+  if(ensure_pinned(c, &c->pin, &c->pin_cap, fbytes + ibytes)) return 1;
+  double *f = (double *) c->pin;
+  int *q = (int *) (f + 11 * m);
+  const gl_gadget_layout L = c->lay;
+  const char *P = (const char *) Pv, *S = (const char *) SphPv;
+  HostPool::get().run(n, PACK_CHUNK, [=](long long, long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	const char *pi = P + i * L.p_stride;
+	const bool gas = i < ngas;
+	const char *si = S + i * L.sph_stride;
+	if(i + PF_DIST < b)
+	  {
+	    const char *pf = pi + PF_DIST * L.p_stride;
+	    __builtin_prefetch(pf + L.p_Pos);
+	    __builtin_prefetch(pf + L.p_OldAcc);
+	    __builtin_prefetch(pf + L.p_Ti_begstep);
+	    if(gas)
+	      {
+		__builtin_prefetch(si + PF_DIST * L.sph_stride + L.s_Entropy);
+		__builtin_prefetch(si + PF_DIST * L.sph_stride + L.s_DtEntropy);
+	      }
+	  }
+	const double *x = (const double *) (pi + L.p_Pos);
+	f[3 * i] = x[0]; f[3 * i + 1] = x[1]; f[3 * i + 2] = x[2];
+	f[3 * m + i] = *(const double *) (pi + L.p_Mass);
+	f[4 * m + i] = *(const double *) (pi + L.p_Hsml);
+	f[5 * m + i] = *(const double *) (pi + L.p_OldAcc);
+	const double *v = gas ? (const double *) (si + L.s_VelPred) : (const double *) (pi + L.p_Vel);
+	f[6 * m + 3 * i] = v[0]; f[6 * m + 3 * i + 1] = v[1]; f[6 * m + 3 * i + 2] = v[2];
+	f[9 * m + i] = gas ? *(const double *) (si + L.s_Entropy) : 0.0;
+	f[10 * m + i] = gas ? *(const double *) (si + L.s_DtEntropy) : 0.0;
+	q[i] = *(const short *) (pi + L.p_Type);
+	q[m + i] = *(const short *) (pi + L.p_TimeBin);
+	q[2 * m + i] = *(const int *) (pi + L.p_Ti_begstep);
+      }
+  });
+  GL_CUDA(c, cudaMemcpyAsync(f64_dev, f, fbytes, cudaMemcpyHostToDevice, c->stream));
+  GL_CUDA(c, cudaMemcpyAsync(i32_dev, q, ibytes, cudaMemcpyHostToDevice, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->g_numpart = n;
+  c->g_ngas = ngas;
+  c->g_off = global_offset;
+  c->g_type = q;
+  return 0;
+}
+
+namespace
+{
+struct AsyncPush
+{
+  std::mutex m;
+  std::condition_variable cv;
+  bool enqueued = false, failed = false;
+};
+}
+
+// what = 1 gravity, 2 density or 4 hydro (one block per call).  The D2H of the block is enqueued behind the next
+// phase's kernel launch (gl_ctx::post_launch), a thread scatters it when it has landed; gl_gadget_push_wait joins.
+extern "C" int gl_gadget_push_segment_async(gl_ctx *c, void *Pv, void *SphPv, int what)
+{
+  cudaSetDevice(c->device);
+  if(!c->have_lay) return c->fail("gl_gadget_push_segment_async: gl_gadget_bind not called");
+  if(what != 1 && what != 2 && what != 4) return c->fail("gl_gadget_push_segment_async: what must be 1, 2 or 4");
+  const long long n = c->g_numpart;
+  if(!c->g_type || n <= 0) return c->fail("gl_gadget_push_segment_async: no host arrays packed");
+  if(ensure_pinned(c, &c->pin2, &c->pin2_cap, PushStage::bytes(n))) return 1;
+  if(ensure_copy_streams(c)) return 1;
+  const int slot = what == 1 ? 0 : (what == 2 ? 1 : 2);
+  PushStage st(c->pin2, n);
+  cudaEvent_t ready = c->ev[11 + slot], landed = c->ev_res[slot];
+  cudaStream_t cs = c->copy_stream[slot & 1];
+  c->fire_post_launch();	// a block still waiting for "the next launch" goes out now
+  GL_CUDA(c, cudaEventRecord(ready, c->stream));
+  auto ap = std::make_shared<AsyncPush>();
+  char *P = (char *) Pv, *S = (char *) SphPv;
+  c->post_launch = [=]() {
+    bool bad = cudaStreamWaitEvent(cs, ready, 0) != cudaSuccess;
+    if(!bad) bad = (what == 1) ? d2h_gravity(c, cs, st.A) : (what == 2) ? d2h_density(c, cs, st.B) : d2h_hydro(c, cs, st.C, 0, n);
+    if(!bad) bad = cudaEventRecord(landed, cs) != cudaSuccess;
+    {
+      std::lock_guard<std::mutex> lk(ap->m);
+      ap->enqueued = true;
+      ap->failed = bad;
+    }
+    ap->cv.notify_all();
+  };
+  c->push_threads.emplace_back([=]() {
+    cudaSetDevice(c->device);
+    {
+      std::unique_lock<std::mutex> lk(ap->m);
+      ap->cv.wait(lk, [&] { return ap->enqueued; });
+    }
+    if(ap->failed || wait_event_polling(landed) != cudaSuccess)
+      {
+	c->push_failed = 1;
+	return;
+      }
+    if(what == 1)
+      scatter_gravity(c, P, st.A, nullptr, n, false);
+    else if(what == 2)
+      scatter_density(c, P, S, st.B, nullptr, n, true, true);
+    else
+      scatter_hydro(c, S, st.C, nullptr, nullptr, 0, n);
+  });
+  return 0;
+}
+
+extern "C" int gl_gadget_push_wait(gl_ctx *c)
+{
+  cudaSetDevice(c->device);
+  c->fire_post_launch();
+  for(auto &t : c->push_threads)
+    if(t.joinable()) t.join();
+  c->push_threads.clear();
+  if(c->push_failed)
+    {
+      c->push_failed = 0;
+      return c->fail("gl_gadget_push_segment_async: a result block could not be copied back");
+    }
+  return 0;
 }

@@ -29,12 +29,17 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 	       const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
 	       const int *__restrict__ perm, const double *__restrict__ in_oldacc, double *__restrict__ o_acc,
 	       double *__restrict__ o_oldacc, float *__restrict__ o_gravcost, double *__restrict__ o_pot,
-	       unsigned long long *__restrict__ counter, gl_dparams par)
+	       unsigned long long *__restrict__ counter, gl_dparams par, int last_first)
 {
   const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long) blockDim.x + threadIdx.x) >> 5;
+  long long warp = (blockIdx.x * (long long) blockDim.x + threadIdx.x) >> 5;
+  // A caller-ordered list (a Peano-Hilbert segment) ends with the few non-gas particles (the gas block comes
+  // first, peano.c:37-88): the warp that mixes them with far-away gas particles marches through two unrelated
+  // parts of the tree and takes about twice as long as the others.  Started last it was a 0.7 ms tail of the
+  // 1.6M disc's walk; started first it disappears behind the rest.
+  if(last_first) warp = ((nt + 31) >> 5) - 1 - warp;
   const long long t = warp * 32 + lane;
-  const bool live = t < nt;
+  const bool live = t >= 0 && t < nt;
   int p = 0, ptype = 0, pin = 0;
   double px = 0, py = 0, pz = 0, aold = 0, hi = 0;
   if(live)
@@ -199,19 +204,21 @@ int glg_gravity(gl_ctx *c)
   if(nt > 0)
     {
       int grid = gl_grid(nt, GL_BLOCK);
+      const int lf = (c->n_tgt_in >= 0 && c->tgt_ordered) ? 1 : 0;
       if(c->par.ErrTolTheta != 0)
 	k_gravity_walk<true, false><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p,
 							      c->e_B.p, c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
 							      c->perm.p, c->in_oldacc.p, c->o_acc.p, c->o_oldacc.p,
-							      c->o_gravcost.p, nullptr, c->d_counter.p, dp);
+							      c->o_gravcost.p, nullptr, c->d_counter.p, dp, lf);
       else
 	k_gravity_walk<false, false><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p,
 							       c->e_B.p, c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
 							       c->perm.p, c->in_oldacc.p, c->o_acc.p, c->o_oldacc.p,
-							       c->o_gravcost.p, nullptr, c->d_counter.p, dp);
+							       c->o_gravcost.p, nullptr, c->d_counter.p, dp, lf);
       GL_LAUNCH_COUNT(c);
     }
   cudaEventRecord(c->ev[1], c->stream);
+  c->fire_post_launch();
   unsigned long long tot = 0;
   GL_CUDA(c, cudaMemcpyAsync(&tot, c->d_counter.p, sizeof(tot), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, c->wait_stream());
@@ -249,11 +256,11 @@ int glg_potential(gl_ctx *c)
   if(c->par.ErrTolTheta != 0)
     k_gravity_walk<true, true><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p, c->e_B.p,
 								c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->perm.p, c->in_oldacc.p,
-								nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp);
+								nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp, 0);
   else
     k_gravity_walk<false, true><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p, c->e_B.p,
 								 c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->perm.p, c->in_oldacc.p,
-								 nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp);
+								 nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp, 0);
   GL_LAUNCH_COUNT(c);
   cudaEventRecord(c->ev[1], c->stream);
   GL_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <functional>
+#include <thread>
 #include "../../include/gl_b200.h"
 
 #define GL_BITS 21			// BITS_PER_DIMENSION, allvars.h:58
@@ -130,6 +131,9 @@ struct gl_ctx
   DBuf<int> tgt_in;		// user-supplied P[] indices (or empty = all)
   std::vector<int> tgt_host;	// host copy of the same list (the drop-in scatter only touches targets)
   long long n_tgt_in = -1;
+  long long res_first = 0, res_count = -1;	// gl_set_result_range: gl_get_* copy only this particle range (-1 = all)
+  bool tgt_ordered = false;	// the list is already in a spatially coherent order (gl_set_targets_ordered): no PH sort
+  bool have_ph_order = false;
   DBuf<int> tgt_sorted;		// sorted-order indices of the gravity targets
   DBuf<int> tgt_sph;		// sorted-order indices of SPH targets (gas/sink/dust)
   DBuf<int> tgt_flag;
@@ -153,7 +157,9 @@ struct gl_ctx
   // ---- gadget AoS layer ----
   gl_gadget_layout lay{};
   bool have_lay = false;
-  long long g_numpart = 0, g_ngas = 0;
+  long long g_numpart = 0, g_ngas = 0;	// particles of the host arrays bound to this context (one rank's P[] / SphP[])
+  long long g_off = 0;		// their first global index: 0 on one GPU, the segment start when the sources were all-gathered
+  const int *g_type = nullptr;	// host copy of P[].Type for them (a column of the pack staging)
   void *pin = nullptr, *pin2 = nullptr;
   size_t pin_cap = 0, pin2_cap = 0;
   cudaStream_t copy_stream[2] = { nullptr, nullptr };
@@ -164,6 +170,8 @@ struct gl_ctx
   // enqueued from here because a kernel submitted BEHIND a batch of D2H copies was measured to start only when
   // the copies had finished (2.9 ms per step), although they run on another stream.
   std::function<void()> post_launch;
+  std::vector<std::thread> push_threads;	// gl_gadget_push_segment_async scatter threads, joined by gl_gadget_push_wait
+  int push_failed = 0;
   void fire_post_launch()
   {
     if(post_launch)
@@ -200,6 +208,7 @@ int glk_keys_and_sort(gl_ctx *c);
 int glk_export_keys(gl_ctx *c, gl_peanokey *ph, gl_peanokey *mo, int where);
 int glk_ph_order(gl_ctx *c, long long n_gas, int *order, int where);
 int glk_apply_velpred(gl_ctx *c);
+int glk_ph_sequence(gl_ctx *c);
 // gl_tree.cu
 int glt_build(gl_ctx *c);
 int glt_update_hmax(gl_ctx *c);

@@ -392,15 +392,28 @@ int glk_keys_and_sort(gl_ctx *c)
 							  c->in_hsml.p, c->in_type.p, c->s_pm.p, c->s_vh.p,
 							  c->s_type.p, c->inv.p);
   GL_LAUNCH_COUNT(c);
-  // Peano-Hilbert sequence of the tree-ordered particles: target groups (one warp = 32 consecutive
-  // targets) are formed along the Hilbert curve, which never jumps, so a group's bounding box stays
-  // compact; along the Morton curve the groups that straddle an octant boundary span the whole cell.
+  c->have_ph_order = false;
+  // a caller that hands over its targets already ordered along the curve (a GPU's Peano-Hilbert segment, or the
+  // reference's own P[] after peano_hilbert_order) does not need the second sort
+  if(!(c->n_tgt_in >= 0 && c->tgt_ordered))
+    if(glk_ph_sequence(c)) return 1;
+  GL_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+// Peano-Hilbert sequence of the tree-ordered particles: target groups (one warp = 32 consecutive
+// targets) are formed along the Hilbert curve, which never jumps, so a group's bounding box stays
+// compact; along the Morton curve the groups that straddle an octant boundary span the whole cell.
+int glk_ph_sequence(gl_ctx *c)
+{
+  if(c->have_ph_order) return 0;
+  long long n = c->n;
   GL_CUDA(c, c->key_ph.ensure(n));
   GL_CUDA(c, c->ph_order.ensure(n + 1));
   k_ph_from_morton<<<gl_grid(n, 256), 256, 0, c->stream>>>(c->key_m_sorted.p, n, c->key_ph.p, c->idx.p);
   GL_LAUNCH_COUNT(c);
   if(sort_pairs(c, c->key_ph.p, c->key_m.p, c->idx.p, c->ph_order.p, n)) return 1;
-  GL_CUDA(c, cudaGetLastError());
+  c->have_ph_order = true;
   return 0;
 }
 

@@ -93,10 +93,56 @@ def gather_padded(own, n, m, group=None):
 
 STATE_FIELDS = ("pos", "vel", "mass", "type", "hsml", "oldacc", "timebin", "ti_begstep", "entropy", "dtentropy")
 SPH_FIELDS = ("hsml", "density", "pressure", "dhsml", "divvel", "curlvel")
+# layout of one rank's all-gather block (include/gl_b200.h gl_load_particles_gathered): offsets in units of m
+# (what the tree build and the gravity walk read comes first, so a gravity-only exchange sends a prefix)
+F64_LAYOUT = (("pos", 0, 3), ("mass", 3, 1), ("hsml", 4, 1), ("oldacc", 5, 1), ("vel", 6, 3), ("entropy", 9, 1),
+              ("dtentropy", 10, 1))
+I32_LAYOUT = (("type", 0, 1), ("timebin", 1, 1), ("ti_begstep", 2, 1))
+F64_ROWS, I32_ROWS = 11, 3
+F64_ROWS_GRAV, I32_ROWS_GRAV = 6, 1
+
+
+def packed_views(f64, i32, m):
+    """Named views into one rank's send block: pos/vel as [m,3], the rest as [m]."""
+    v = {}
+    for name, off, w in F64_LAYOUT:
+        t = f64[off * m:(off + w) * m]
+        v[name] = t.view(m, 3) if w == 3 else t
+    for name, off, w in I32_LAYOUT:
+        v[name] = i32[off * m:(off + w) * m]
+    return v
+
+
+def unpack_gathered(full_f64, full_i32, ranges, m):
+    """Pure-torch statement of what gl_load_particles_gathered does with the all-gather receive buffers
+    (used by the CPU tests to pin the layout): returns the global arrays as a dict."""
+    out = {}
+    for name, off, w in F64_LAYOUT:
+        parts = []
+        for r, (lo, hi) in enumerate(ranges):
+            blk = full_f64[r * F64_ROWS * m:(r + 1) * F64_ROWS * m][off * m:(off + w) * m]
+            parts.append((blk.view(m, 3) if w == 3 else blk)[: hi - lo])
+        out[name] = torch.cat(parts, dim=0)
+    for name, off, w in I32_LAYOUT:
+        out[name] = torch.cat([full_i32[r * I32_ROWS * m:(r + 1) * I32_ROWS * m][off * m:(off + w) * m][: hi - lo]
+                               for r, (lo, hi) in enumerate(ranges)], dim=0)
+    return out
+
+
+def allgather_block(own, world, group=None):
+    """One collective for a whole block: own [k] -> [world*k]."""
+    if world == 1:
+        return own
+    full = torch.empty(world * own.numel(), dtype=own.dtype, device=own.device)
+    dist.all_gather_into_tensor(full, own, group=group)
+    return full
 
 
 class DistributedForcePath:
-    """Owns this rank's Peano-Hilbert segment on the GPU and evaluates forces for it."""
+    """Owns this rank's Peano-Hilbert segment on the GPU and evaluates forces for it.
+
+    Per force evaluation the data path has exactly three collectives (NCCL all-gathers over NVLink): the packed
+    float64 state block, the packed int32 state block, and - after density - the packed SphP block."""
 
     def __init__(self, params, rank=0, world=1, device=0, group=None):
         self.rank, self.world, self.group = rank, world, group
@@ -105,9 +151,32 @@ class DistributedForcePath:
         self.params = params
         self.n = 0
         self.own = {}
-        self.full = {}
+        self.t = {}          # wall-clock seconds per sub-phase of the last compute_accelerations (diagnostics)
 
     # -- set-up: the analogue of domain_Decomposition + peano_hilbert_order (domain.c:100, peano.c:25) --------
+    def _adopt(self, n, ngas, order, ranges, take):
+        """take(name, lo, hi) -> this rank's rows of a state field as a device tensor, in Peano-Hilbert order."""
+        dev = self.device
+        self.n, self.ngas, self.order, self.ranges = n, ngas, order, ranges
+        lo, hi = ranges[self.rank]
+        m = max(b - a for a, b in ranges)
+        self.lo, self.hi, self.m = lo, hi, m
+        self.seg_start = (C.c_longlong * (self.world + 1))(*([a for a, _ in ranges] + [n]))
+        self.own_f64 = torch.zeros(F64_ROWS * m, dtype=torch.float64, device=dev)
+        self.own_i32 = torch.zeros(I32_ROWS * m, dtype=torch.int32, device=dev)
+        self.own = packed_views(self.own_f64, self.own_i32, m)
+        for k in STATE_FIELDS:
+            self.own[k][: hi - lo] = take(k, lo, hi)
+        self.sph_send = torch.zeros(len(SPH_FIELDS) * m, dtype=torch.float64, device=dev)
+        self.targets = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
+        # result buffers (full length, only [lo,hi) is meaningful on this rank)
+        self.res = dict(acc=f64(n, 3), oldacc=f64(n), gravcost=torch.zeros(n, dtype=torch.float32, device=dev))
+        if ngas > 0:
+            self.res.update(hsml=f64(n), numngb=f64(n), density=f64(n), dhsml=f64(n), divvel=f64(n), curlvel=f64(n),
+                            pressure=f64(n), hacc=f64(n, 3), dtentr=f64(n), maxsig=f64(n))
+        return order
+
     def decompose(self, ps, cost=None):
         """ps: the FULL particle set as host numpy arrays (every rank passes the same set).  Orders it along the
         Peano-Hilbert curve (gas block first, like the reference) and keeps this rank's segment on the GPU.
@@ -117,32 +186,18 @@ class DistributedForcePath:
         ngas = int((ps["type"] == 0).sum())
         self.fp.load(ps)
         order = self.fp.peano_hilbert_order(ngas)
-        self.n, self.ngas = n, ngas
         if cost is None:
-            self.ranges = [partition_range(n, self.world, r)[:2] for r in range(self.world)]
+            ranges = [partition_range(n, self.world, r)[:2] for r in range(self.world)]
         else:
-            self.ranges = work_balanced_ranges(np.asarray(cost)[order], self.world)
-        lo, hi = self.ranges[self.rank]
-        m = max(b - a for a, b in self.ranges)
-        self.lo, self.hi, self.m = lo, hi, m
-        seg = order[lo:hi]
-        dev = self.device
+            ranges = work_balanced_ranges(np.asarray(cost)[order], self.world)
         tb = ps.get("ti_begstep", np.zeros(n, np.int32))
-        self.own = dict(
-            pos=torch.from_numpy(ps["pos"][seg]).to(dev), vel=torch.from_numpy(ps["vel"][seg]).to(dev),
-            mass=torch.from_numpy(ps["mass"][seg]).to(dev), type=torch.from_numpy(ps["type"][seg].astype(np.int32)).to(dev),
-            hsml=torch.from_numpy(ps["hsml"][seg]).to(dev), oldacc=torch.from_numpy(ps["oldacc"][seg]).to(dev),
-            timebin=torch.from_numpy(ps["timebin"][seg].astype(np.int32)).to(dev),
-            ti_begstep=torch.from_numpy(tb[seg].astype(np.int32)).to(dev),
-            entropy=torch.from_numpy(ps["entropy"][seg]).to(dev), dtentropy=torch.from_numpy(ps["dtentropy"][seg]).to(dev))
-        self.targets = torch.arange(lo, hi, dtype=torch.int32, device=dev)
-        self.order = order
-        # result buffers (full length, only [lo,hi) is meaningful on this rank)
-        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
-        self.res = dict(acc=f64(n, 3), oldacc=f64(n), gravcost=torch.zeros(n, dtype=torch.float32, device=dev),
-                        hsml=f64(n), numngb=f64(n), density=f64(n), dhsml=f64(n), divvel=f64(n), curlvel=f64(n),
-                        pressure=f64(n), hacc=f64(n, 3), dtentr=f64(n), maxsig=f64(n))
-        return order
+        src = dict(ps, ti_begstep=tb)
+        i32 = ("type", "timebin", "ti_begstep")
+
+        def take(k, lo, hi):
+            a = np.asarray(src[k])[order[lo:hi]]
+            return torch.from_numpy(np.ascontiguousarray(a.astype(np.int32) if k in i32 else a.astype(np.float64))).to(self.device)
+        return self._adopt(n, ngas, order, ranges, take)
 
     def decompose_device(self, ps):
         """Same as decompose() for a particle set that already lives on this GPU as torch tensors (every rank
@@ -150,79 +205,106 @@ class DistributedForcePath:
         n = ps["pos"].shape[0]
         ngas = int((ps["type"] == 0).sum().item())
         assert bool((ps["type"][:ngas] == 0).all().item()), "gas must come first"
-        dev = self.device
-        self.n, self.ngas = n, ngas
-        torch.cuda.current_stream(dev).synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
         self.fp.load_device(n, [ps[k].data_ptr() for k in STATE_FIELDS])
-        order = torch.empty(n, dtype=torch.int32, device=dev)
+        order = torch.empty(n, dtype=torch.int32, device=self.device)
         self.fp.peano_hilbert_order_device(ngas, order.data_ptr())
-        self.ranges = [partition_range(n, self.world, r)[:2] for r in range(self.world)]
-        lo, hi, m = partition_range(n, self.world, self.rank)
-        self.lo, self.hi, self.m = lo, hi, m
-        seg = order[lo:hi].long()
-        self.own = {k: ps[k].index_select(0, seg).contiguous() for k in STATE_FIELDS}
-        self.targets = torch.arange(lo, hi, dtype=torch.int32, device=dev)
-        self.order = order
-        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
-        self.res = dict(acc=f64(n, 3), oldacc=f64(n), gravcost=torch.zeros(n, dtype=torch.float32, device=dev))
-        if ngas > 0:
-            self.res.update(hsml=f64(n), numngb=f64(n), density=f64(n), dhsml=f64(n), divvel=f64(n), curlvel=f64(n),
-                            pressure=f64(n), hacc=f64(n, 3), dtentr=f64(n), maxsig=f64(n))
-        return order
+        ranges = [partition_range(n, self.world, r)[:2] for r in range(self.world)]
+        return self._adopt(n, ngas, order, ranges, lambda k, lo, hi: ps[k].index_select(0, order[lo:hi].long()))
 
     def _sync_lib(self):
-        # the library runs on its own stream and synchronises before returning; make torch's stream wait for
-        # nothing further (results are complete), and make sure torch work is done before the library reads
+        # the library runs on its own stream and synchronises before returning; make sure torch / NCCL work is
+        # done before the library reads it
         torch.cuda.current_stream(self.device).synchronize()
 
-    # -- one force evaluation ------------------------------------------------------------------------------
-    def exchange_state(self):
-        """Exchange step 1: replicate the sources (NCCL all-gather over NVLink)."""
-        for k in STATE_FIELDS:
-            self.full[k] = gather_ragged(self.own[k], self.ranges, self.group).contiguous()
-        self._sync_lib()
-        f = self.full
-        ptrs = [f[k].data_ptr() for k in STATE_FIELDS]
-        self.fp.load_device(self.n, ptrs)
-        lib, ctx = self.fp._lib, self.fp.ctx
-        self.fp._chk(lib.gl_set_targets(ctx, C.c_void_p(self.targets.data_ptr()), self.targets.numel(), 1))
+    def _tick(self, key, t0):
+        import time
+        t1 = time.perf_counter()
+        self.t[key] = self.t.get(key, 0.0) + (t1 - t0)
+        return t1
 
-    def gravity(self):
+    # -- one force evaluation ------------------------------------------------------------------------------
+    def exchange_state(self, full=True):
+        """Exchange step 1: replicate the sources (two NCCL all-gathers over NVLink: the float64 and the int32
+        block), unpacked into the library's input arrays by one kernel.  full=False (gravity only): just the
+        prefix of the blocks the tree build and the walk read (44 instead of 100 bytes per particle)."""
+        import time
+        t0 = time.perf_counter()
+        m = self.m
+        nf, ni = (F64_ROWS, I32_ROWS) if full else (F64_ROWS_GRAV, I32_ROWS_GRAV)
+        self.full_f64 = allgather_block(self.own_f64[: nf * m], self.world, self.group)
+        self.full_i32 = allgather_block(self.own_i32[: ni * m], self.world, self.group)
+        self._sync_lib()
+        t0 = self._tick("allgather_state", t0)
+        lib, ctx = self.fp._lib, self.fp.ctx
+        self.fp._chk(lib.gl_load_particles_gathered(ctx, self.n, self.world, m, self.seg_start,
+                                                    C.c_void_p(self.full_f64.data_ptr()), C.c_void_p(self.full_i32.data_ptr()),
+                                                    1 if full else 0))
+        self.fp._chk(lib.gl_set_result_range(ctx, self.lo, self.hi - self.lo))   # this rank only ever reads its own results
+        self.fp.N = self.n
+        # the segment is consecutive along the Peano-Hilbert curve already: the library keeps the order
+        import os
+        setter = lib.gl_set_targets if os.environ.get("GL_NO_ORDERED") else lib.gl_set_targets_ordered
+        self.fp._chk(setter(ctx, C.c_void_p(self.targets.data_ptr()), self.targets.numel(), 1))
+        self._tick("load_state", t0)
+
+    def gravity(self, fetch=True):
+        import time
+        t0 = time.perf_counter()
         self.fp.gravity_tree_nocopy()
+        t0 = self._tick("gravity_tree", t0)
+        if not fetch:
+            return
         r = self.res
         lib, ctx = self.fp._lib, self.fp.ctx
         self.fp._chk(lib.gl_get_gravity(ctx, C.c_void_p(r["acc"].data_ptr()), C.c_void_p(r["oldacc"].data_ptr()),
                                         C.c_void_p(r["gravcost"].data_ptr()), 1))
-        self.own["oldacc"] = r["oldacc"][self.lo:self.hi].clone()
+        self.own["oldacc"][: self.hi - self.lo] = r["oldacc"][self.lo:self.hi]
+        self._sync_lib()
+        self._tick("get_gravity", t0)
 
     def density_and_exchange(self):
-        """density() for the owned targets, then exchange step 2."""
+        """density() for the owned targets, then exchange step 2 (one all-gather of the packed SphP block)."""
+        import time
+        t0 = time.perf_counter()
         self.fp.density_nocopy()
+        t0 = self._tick("density", t0)
         r = self.res
         lib, ctx = self.fp._lib, self.fp.ctx
         p = lambda t: C.c_void_p(t.data_ptr())
         self.fp._chk(lib.gl_get_density(ctx, p(r["hsml"]), p(r["numngb"]), p(r["density"]), p(r["dhsml"]), p(r["divvel"]),
                                         p(r["curlvel"]), p(r["pressure"]), None, None, None, 1))
-        self.own["hsml"] = r["hsml"][self.lo:self.hi].clone()
+        k = self.hi - self.lo
+        self.own["hsml"][:k] = r["hsml"][self.lo:self.hi]
+        t0 = self._tick("get_density", t0)
         if self.world > 1:
-            g = {k: gather_ragged(r[k][self.lo:self.hi], self.ranges, self.group).contiguous() for k in SPH_FIELDS}
+            m = self.m
+            for j, f in enumerate(SPH_FIELDS):
+                self.sph_send[j * m: j * m + k] = r[f][self.lo:self.hi]
+            self.full_sph = allgather_block(self.sph_send, self.world, self.group)
             self._sync_lib()
-            self.fp._chk(lib.gl_set_hsml(ctx, p(g["hsml"]), 1))
-            self.fp._chk(lib.gl_set_sph_state(ctx, p(g["density"]), p(g["pressure"]), p(g["dhsml"]), p(g["divvel"]),
-                                              p(g["curlvel"]), 1))
-            self._keep = g
+            t0 = self._tick("allgather_sph", t0)
+            self.fp._chk(lib.gl_set_sph_state_gathered(ctx, self.world, m, self.seg_start, p(self.full_sph)))
+            self._tick("load_sph", t0)
+        else:
+            self._sync_lib()
 
     def hydro(self):
+        import time
+        t0 = time.perf_counter()
         self.fp.force_update_hmax()
         self.fp.hydro_force_nocopy()
+        t0 = self._tick("hydro", t0)
         r = self.res
         lib, ctx = self.fp._lib, self.fp.ctx
         self.fp._chk(lib.gl_get_hydro(ctx, C.c_void_p(r["hacc"].data_ptr()), C.c_void_p(r["dtentr"].data_ptr()),
                                       C.c_void_p(r["maxsig"].data_ptr()), 1))
+        self._tick("get_hydro", t0)
 
     def compute_accelerations(self, sph=True, gravity=True):
         """accel.c:27 force part for this rank's segment, with the two exchange steps."""
-        self.exchange_state()
+        self.t = {}
+        self.exchange_state(full=bool(sph and self.ngas > 0))
         if gravity:
             self.gravity()
         else:
@@ -231,5 +313,74 @@ class DistributedForcePath:
             self.density_and_exchange()
             self.hydro()
 
+    def rebalance(self):
+        """domain_findSplit_work_balanced (domain.c:1075-1113) with the measured cost of the last gravity call:
+        weight (1 + GravCost) / 2^TimeBin (domain.c:378-384), one contiguous Peano-Hilbert segment per GPU.
+        Three all-gathers (cost, and the current float64 / int32 state blocks); every rank then cuts its new
+        segment out of the replicated state locally - the analogue of domain_exchange (domain.c:596)."""
+        dev, m, k = self.device, self.m, self.hi - self.lo
+        send = torch.zeros(m, dtype=torch.float64, device=dev)
+        send[:k] = 1.0 + self.res["gravcost"][self.lo:self.hi].double()
+        send[:k] /= torch.pow(2.0, self.own["timebin"][:k].clamp(min=0).double())
+        full = allgather_block(send, self.world, self.group).view(self.world, m)
+        cost = torch.cat([full[r, : hi - lo] for r, (lo, hi) in enumerate(self.ranges)])
+        csum = torch.cumsum(cost, 0)
+        tot = float(csum[-1].item())
+        cuts = [0]
+        for r in range(1, self.world):
+            goal = torch.tensor([tot * r / self.world * (1 + 1e-12)], dtype=torch.float64, device=dev)
+            cuts.append(int(torch.searchsorted(csum, goal, right=True).item()))
+        cuts.append(self.n)
+        for r in range(1, len(cuts)):
+            cuts[r] = max(cuts[r], cuts[r - 1])
+        new_ranges = [(cuts[r], cuts[r + 1]) for r in range(self.world)]
+        del full, cost, csum
+        glob = unpack_gathered(allgather_block(self.own_f64, self.world, self.group),
+                               allgather_block(self.own_i32, self.world, self.group), self.ranges, m)
+        self.full_f64 = self.full_i32 = None
+        self._adopt(self.n, self.ngas, self.order, new_ranges, lambda name, lo, hi: glob[name][lo:hi])
+        return new_ranges
+
     def close(self):
         self.fp.close()
+
+
+class DistributedDropIn:
+    """compute_accelerations() (accel.c:27, force part) on THIS RANK'S OWN host P[] / SphP[] - its Peano-Hilbert
+    segment, the way every MPI rank of the reference holds its local particles - at any GPU count:
+    pack + H2D of the segment, the all-gathers, the force path, and the rank's slice of every result block copied
+    back and scattered while the next phase computes (gl_gadget_pack_segment / gl_gadget_push_segment_async)."""
+
+    def __init__(self, dfp, arrays):
+        from . import aos
+        self.d, self.a = dfp, arrays
+        self._lay = aos.layout_struct()
+        fp = dfp.fp
+        fp._chk(fp._lib.gl_gadget_bind(fp.ctx, C.byref(self._lay)))
+        assert arrays.NumPart == dfp.hi - dfp.lo
+
+    def bytes_per_step(self):
+        n, ng = self.a.NumPart, self.a.N_gas
+        h2d = self.d.m * (11 * 8 + 3 * 4)
+        other = 5 * 8 if n > ng else 0
+        d2h = n * ((3 + 1) * 8 + 4) + n * (7 * 8 + other) + n * 5 * 8
+        return h2d, d2h
+
+    def compute_accelerations(self):
+        d, a = self.d, self.a
+        fp = d.fp
+        lib, ctx = fp._lib, fp.ctx
+        P, S = L._ptr(a.P), L._ptr(a.SphP)
+        fp._chk(lib.gl_gadget_pack_segment(ctx, P, S, a.NumPart, a.N_gas, d.m, d.lo, C.c_void_p(d.own_f64.data_ptr()),
+                                           C.c_void_p(d.own_i32.data_ptr())))
+        d.t = {}
+        d.exchange_state()
+        d.gravity(fetch=False)
+        fp._chk(lib.gl_gadget_push_segment_async(ctx, P, S, 1))
+        if d.ngas > 0:
+            d.density_and_exchange()
+            fp._chk(lib.gl_gadget_push_segment_async(ctx, P, S, 2))
+            d.fp.force_update_hmax()
+            d.fp.hydro_force_nocopy()
+            fp._chk(lib.gl_gadget_push_segment_async(ctx, P, S, 4))
+        fp._chk(lib.gl_gadget_push_wait(ctx))

@@ -74,6 +74,19 @@ int gl_set_hsml(gl_ctx * ctx, const double *hsml, int where);
 int gl_set_sph_state(gl_ctx * ctx, const double *density, const double *pressure, const double *dhsml,
 		     const double *divvel, const double *curlvel, int where);
 
+/* ---- multi-GPU: the same two loads straight out of the NCCL all-gather receive buffers ---------------------
+ * These replace the import side of the reference's export/import loops (gravtree.c:246-366, density.c:258-342,
+ * hydra.c:412-520).  Every rank sends one block of doubles and one of ints for its Peano-Hilbert segment, padded to
+ * m particles; rank r's block sits at f64buf + r*11*m = [pos 3m | mass | hsml | oldacc | vel 3m | entropy |
+ * dtentropy] and i32buf + r*3*m = [type | timebin | ti_begstep].  full = 0: a gravity-only exchange sent just the
+ * prefix the tree build and the walk read - blocks of 6*m doubles [pos | mass | hsml | oldacc] and m ints [type].
+ * seg_start[world+1]: global index of each rank's first particle (seg_start[world] = n).  Device pointers. */
+int gl_load_particles_gathered(gl_ctx * ctx, long long n, int world, long long m, const long long *seg_start,
+			       const double *f64buf, const int *i32buf, int full);
+/* after density (replaces hydra.c:412 and the hmax exchange forcetree.c:1722-1747): rank r's block at
+ * buf + r*6*m = [hsml | density | pressure | dhsml | divvel | curlvel] */
+int gl_set_sph_state_gathered(gl_ctx * ctx, int world, long long m, const long long *seg_start, const double *buf);
+
 /* ---- domain / keys: domain.c:1972 domain_findExtent, peano.c:300,320,335 ------------------ */
 /* computes DomainCorner/Center/Len/Fac from the loaded positions; out[8] = len, fac, corner[3], center[3] */
 int gl_domain_find_extent(gl_ctx * ctx, double *out8);
@@ -99,6 +112,10 @@ int gl_get_nodes(gl_ctx * ctx, double *table, long long cap_nodes);
 /* Restrict the next force calls to a subset of P[] indices (the active list
  * FirstActiveParticle/NextActiveParticle, or a GPU's Peano-Hilbert segment).  n<0 = all. */
 int gl_set_targets(gl_ctx * ctx, const int *index, long long n, int where);
+/* Same, for a list that is already ordered along the space-filling curve (a GPU's Peano-Hilbert segment after
+ * domain.c:1075, or the reference's P[] after peano_hilbert_order, peano.c:25): warps take 32 consecutive list
+ * entries as they come and the library skips its own Peano-Hilbert sort.  Results do not depend on the order. */
+int gl_set_targets_ordered(gl_ctx * ctx, const int *index, long long n, int where);
 
 /* ---- the four force entry points -------------------------------------------------------------- */
 int gl_gravity_tree(gl_ctx * ctx);	/* gravtree.c:27  (includes the tree build when flagged) */
@@ -121,6 +138,10 @@ int gl_get_density(gl_ctx * ctx, double *hsml, double *numngb, double *density, 
 		   double *sink_gasvel3, int where);
 /* hydro: SphP.a.HydroAccel, .e.DtEntropy (converted, hydra.c:583), .MaxSignalVel */
 int gl_get_hydro(gl_ctx * ctx, double *hydroaccel3, double *dtentropy, double *maxsignalvel, int where);
+/* restrict the gl_get_* calls (device or host destination) to the particles [first, first+count): a GPU that only
+ * evaluated its own segment copies only that; count < 0 = all again.  Values land at the same indices of the
+ * destination arrays. */
+int gl_set_result_range(gl_ctx * ctx, long long first, long long count);
 /* integer pair counts (not stored by the reference, density.c:858 is a dead local): number of j with
  * Mass_j != 0 and r2 < h_i^2 (density) / (r2 < h_i^2 or r2 < h_j^2) and r > 0 (hydro) */
 int gl_get_pair_counts(gl_ctx * ctx, int *dens_pairs, int *hydro_pairs, int where);
@@ -159,6 +180,17 @@ int gl_gadget_pull(gl_ctx * ctx, const void *P, const void *SphP, long long NumP
 int gl_gadget_compute_accelerations(gl_ctx * ctx, void *P, void *SphP, long long NumPart, long long N_gas, int mode);
 /* scatter results back in place; what = bit mask: 1 gravity, 2 density, 4 hydro */
 int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
+
+/* ---- multi-GPU drop-in: every rank keeps its own P[] / SphP[] (its Peano-Hilbert segment), as every MPI rank of the
+ * reference does; the sources are replicated with gl_load_particles_gathered --------------------------------------- */
+/* pack this rank's arrays into its all-gather block (layout of gl_load_particles_gathered, padded to m particles) and
+ * send it to the device buffers f64_dev[11*m], i32_dev[3*m]; global_offset = index of the rank's first particle */
+int gl_gadget_pack_segment(gl_ctx * ctx, const void *P, const void *SphP, long long NumPart, long long N_gas, long long m,
+			   long long global_offset, double *f64_dev, int *i32_dev);
+/* return one result block (what = 1 gravity, 2 density, 4 hydro) of the rank's own particles to its arrays while the
+ * next phase computes; gl_gadget_push_wait() blocks until every pending block has been scattered */
+int gl_gadget_push_segment_async(gl_ctx * ctx, void *P, void *SphP, int what);
+int gl_gadget_push_wait(gl_ctx * ctx);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ n = ps["pos"].shape[0]
 d = DistributedForcePath(par, rank=rank, world=world, device=local)
 order = d.decompose(ps)
 d.compute_accelerations()      # BH pass + cold-start density + hydro
+res0 = {k: v[d.lo:d.hi].clone().cpu().numpy() for k, v in d.res.items()}
 d.fp.set_TreeReconstructFlag(1)
 d.compute_accelerations()      # relative criterion, steady density
 torch.cuda.synchronize()
@@ -64,6 +65,33 @@ if True:
     ok = all(checks.values())
     print("rank %d/%d segment [%d,%d): %s" % (rank, world, d.lo, d.hi, checks), flush=True)
     fp.close()
+# the same first evaluation through the rank-local drop-in boundary: host P[]/SphP[] of this rank's segment
+from gadget_leicester_b200 import aos  # noqa: E402
+from gadget_leicester_b200.multigpu import DistributedDropIn  # noqa: E402
+d2 = DistributedForcePath(par, rank=rank, world=world, device=local)
+order2 = d2.decompose(ps)
+seg = order2[d2.lo:d2.hi]
+ps_seg = {k: (v[seg] if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+arr = aos.GadgetArrays(ps_seg, pinned=True)
+DistributedDropIn(d2, arr).compute_accelerations()
+r = arr.results()
+ng = arr.N_gas
+checks2 = {
+    "dropin GravCost identical": bool((r["GravCost"] == res0["gravcost"]).all()),
+    "dropin GravAccel identical": bool((r["GravAccel"] == res0["acc"]).all()),
+    "dropin OldAcc identical": bool((r["OldAcc"] == res0["oldacc"]).all()),
+}
+if ng:
+    sphsel = np.isin(ps_seg["type"], (0, 2, 5))
+    checks2["dropin Hsml rel<=1e-12"] = bool(np.abs(r["Hsml"][sphsel] / res0["hsml"][sphsel] - 1).max() <= 1e-12)
+    checks2["dropin Density rel<=1e-11"] = bool(np.abs(r["Density"] / res0["density"][:ng] - 1).max() <= 1e-11)
+    checks2["dropin HydroAccel rel<=1e-8"] = bool((np.linalg.norm(r["HydroAccel"] - res0["hacc"][:ng], axis=1) /
+                                                   np.linalg.norm(res0["hacc"][:ng], axis=1)).max() <= 1e-8)
+    checks2["dropin DtEntropy/MaxSignalVel"] = bool(np.allclose(r["DtEntropy"], res0["dtentr"][:ng], rtol=1e-8, atol=0) and
+                                                    np.allclose(r["MaxSignalVel"], res0["maxsig"][:ng], rtol=1e-12, atol=0))
+ok = ok and all(checks2.values())
+print("rank %d/%d drop-in segment: %s" % (rank, world, checks2), flush=True)
+d2.close()
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -275,6 +275,83 @@ def test_ragged_warp_and_target_subset(FP, port_bin):
     fp2.close()
 
 
+def test_gathered_load_and_ordered_targets_match_plain_api(FP):
+    """The multi-GPU entry points on one GPU: gl_load_particles_gathered reading three ragged rank blocks laid out
+    like the NCCL all-gather receive buffers, and gl_set_targets_ordered (no Peano-Hilbert sort inside the library),
+    give what gl_load_particles + gl_set_targets give: gravity bit for bit, SPH to FP64 round-off."""
+    import ctypes as C
+    import torch
+    import gadget_leicester_b200.lib as L
+    from gadget_leicester_b200.multigpu import packed_views, F64_ROWS, I32_ROWS, STATE_FIELDS
+    ps = ics.disc(6000, seed=12)
+    par = ics.default_params()
+    ps["hsml"] = ics.guess_hsml(ps, par["DesNumNgb"])
+    ps["hsml"][ps["type"] == 5] = par["Softening"][5]
+    n = ps["pos"].shape[0]
+    a = FP(par)
+    a.load(ps)
+    order = a.peano_hilbert_order(6000)
+    ph = {k: (np.ascontiguousarray(v[order]) if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+    lo, hi = 1500, 4200            # "this rank's" segment of the Peano-Hilbert ordered list
+    tg = np.arange(lo, hi, dtype=np.int32)
+    a.load(ph)
+    a.set_targets(tg)
+    ga, da = a.gravity_tree(), a.density()
+    a.set_targets(None)            # hydro reads SphP of neighbours outside the segment (the other ranks' results)
+    a.density()
+    a.set_targets(tg)
+    a.force_update_hmax()
+    ha = a.hydro_force()
+    a.close()
+
+    ranges = [(0, 1000), (1000, 4200), (4200, n)]
+    m = max(y - x for x, y in ranges)
+    dev = torch.device("cuda", 0)
+    full_f = torch.zeros(3 * F64_ROWS * m, dtype=torch.float64, device=dev)
+    full_i = torch.zeros(3 * I32_ROWS * m, dtype=torch.int32, device=dev)
+    src = dict(ph, ti_begstep=ph.get("ti_begstep", np.zeros(n, np.int32)))
+    for r, (x, y) in enumerate(ranges):
+        v = packed_views(full_f[r * F64_ROWS * m:(r + 1) * F64_ROWS * m], full_i[r * I32_ROWS * m:(r + 1) * I32_ROWS * m], m)
+        for k in STATE_FIELDS:
+            arr = np.asarray(src[k])[x:y]
+            v[k][: y - x] = torch.from_numpy(np.ascontiguousarray(arr.astype(np.int32) if v[k].dtype == torch.int32 else arr.astype(np.float64))).to(dev)
+    torch.cuda.synchronize()
+    b = FP(par)
+    seg = (C.c_longlong * 4)(0, 1000, 4200, n)
+    b._chk(b._lib.gl_load_particles_gathered(b.ctx, n, 3, m, seg, C.c_void_p(full_f.data_ptr()), C.c_void_p(full_i.data_ptr()), 1))
+    b.N = n
+    tgt = torch.from_numpy(tg).to(dev)
+    b._chk(b._lib.gl_set_targets_ordered(b.ctx, C.c_void_p(tgt.data_ptr()), tgt.numel(), 1))
+    gb, db = b.gravity_tree(), b.density()
+    b.set_targets(None)
+    b.density()
+    b._chk(b._lib.gl_set_targets_ordered(b.ctx, C.c_void_p(tgt.data_ptr()), tgt.numel(), 1))
+    b.force_update_hmax()
+    hb = b.hydro_force()
+    b.close()
+    sl = slice(lo, hi)
+    gas = ph["type"][sl] == 0
+    # gravity-only exchange: only the prefix of every block (pos, mass, hsml, oldacc | type) was sent
+    from gadget_leicester_b200.multigpu import F64_ROWS_GRAV, I32_ROWS_GRAV
+    pre_f = torch.cat([full_f[r * F64_ROWS * m: r * F64_ROWS * m + F64_ROWS_GRAV * m] for r in range(3)]).contiguous()
+    pre_i = torch.cat([full_i[r * I32_ROWS * m: r * I32_ROWS * m + I32_ROWS_GRAV * m] for r in range(3)]).contiguous()
+    torch.cuda.synchronize()
+    g3 = FP(par)
+    g3._chk(g3._lib.gl_load_particles_gathered(g3.ctx, n, 3, m, seg, C.c_void_p(pre_f.data_ptr()), C.c_void_p(pre_i.data_ptr()), 0))
+    g3.N = n
+    g3._chk(g3._lib.gl_set_targets_ordered(g3.ctx, C.c_void_p(tgt.data_ptr()), tgt.numel(), 1))
+    g3._chk(g3._lib.gl_set_result_range(g3.ctx, lo, hi - lo))
+    gc = g3.gravity_tree()
+    g3.close()
+    assert (gc["GravCost"][sl] == ga["GravCost"][sl]).all() and (gc["GravAccel"][sl] == ga["GravAccel"][sl]).all()
+    assert (gc["GravAccel"][:lo] == 0).all() and (gc["GravAccel"][hi:] == 0).all()     # result range: nothing else was copied
+    assert (ga["GravCost"][sl] == gb["GravCost"][sl]).all() and (ga["GravAccel"][sl] == gb["GravAccel"][sl]).all()
+    assert (da["DensPairs"][sl] == db["DensPairs"][sl]).all() and (ha["HydroPairs"][sl] == hb["HydroPairs"][sl]).all()
+    assert util.rel_err_vec(db["Hsml"][sl], da["Hsml"][sl]).max() <= 1e-13
+    assert util.rel_err_vec(db["Density"][sl][gas], da["Density"][sl][gas]).max() <= 1e-12
+    assert util.rel_err_vec(hb["HydroAccel"][sl][gas], ha["HydroAccel"][sl][gas]).max() <= 1e-9
+
+
 def test_dropin_aos_boundary_matches_soa_api(FP):
     """compute_accelerations on the reference's own P[]/SphP[] byte layout (536 B / 264 B structs, offsets from
     allvars.h) gives the same numbers as the SoA entry points, and leaves untouched fields untouched."""

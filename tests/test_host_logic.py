@@ -10,7 +10,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from gadget_leicester_b200 import ics, aos
-from gadget_leicester_b200.multigpu import partition_range, gather_padded, gather_ragged, work_balanced_ranges
+from gadget_leicester_b200.multigpu import (partition_range, gather_padded, gather_ragged, work_balanced_ranges, packed_views,
+                                            unpack_gathered, allgather_block, F64_ROWS, I32_ROWS)
 from oracle import glio
 
 
@@ -102,6 +103,23 @@ def _worker(rank, world, port, n, q):
     a, b = ranges[rank]
     got2 = gather_ragged(full[a:b].clone(), ranges)
     ok = ok and bool((got2 == full).all())
+    # the packed state blocks of DistributedForcePath.exchange_state: one collective per dtype, ragged segments
+    mm = max(b2 - a2 for a2, b2 in ranges)
+    f64 = torch.zeros(F64_ROWS * mm, dtype=torch.float64)
+    i32 = torch.zeros(I32_ROWS * mm, dtype=torch.int32)
+    v = packed_views(f64, i32, mm)
+    g = torch.arange(a, b, dtype=torch.float64)
+    v["pos"][: b - a] = full[a:b]
+    v["vel"][: b - a] = -full[a:b]
+    for k, name in enumerate(("mass", "hsml", "oldacc", "entropy", "dtentropy")):
+        v[name][: b - a] = g * 10 + k
+    for k, name in enumerate(("type", "timebin", "ti_begstep")):
+        v[name][: b - a] = (g * 4 + k).to(torch.int32)
+    out = unpack_gathered(allgather_block(f64, world), allgather_block(i32, world), ranges, mm)
+    gg = torch.arange(n, dtype=torch.float64)
+    ok = ok and bool((out["pos"] == full).all()) and bool((out["vel"] == -full).all())
+    ok = ok and all(bool((out[name] == gg * 10 + k).all()) for k, name in enumerate(("mass", "hsml", "oldacc", "entropy", "dtentropy")))
+    ok = ok and all(bool((out[name] == (gg * 4 + k).to(torch.int32)).all()) for k, name in enumerate(("type", "timebin", "ti_begstep")))
     # the "unconverged targets remaining" reduction of density.c:656 in NCCL/gloo form
     left = torch.tensor([rank + 1], dtype=torch.int64)
     dist.all_reduce(left)
