@@ -40,6 +40,7 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define GL_GAMMA_MINUS1 (GL_GAMMA - 1)
 #define BOX_SLACK 1.0000000001
 #define CAND_CAP 192		// staged candidates per warp (192: four 4-warp blocks of k_hydro fit one SM's shared memory)
+#define QCAP 32			// lane = target mode: entries of every lane's private hit queue (power of two)
 #define SPH_WARPS 4
 #define STK_CAP 512
 #define LT_MIN_ACTIVE 12	// with at least this many active targets a warp runs lane = target (see density_chunk_lt)
@@ -94,23 +95,24 @@ struct WarpStage
 #ifdef GL_PHASE_PROF
   unsigned long long ph[8];
 #endif
-  float4 cand[CAND_CAP];	// candidate position - group centre (x,y,z) and candidate Hsml (w)
-  unsigned char hl[CAND_CAP * 32];	// lane = target mode: hl[k*32 + lane] = k-th candidate that lane's target may touch
+  float4 cand[CAND_CAP];	// candidate position - group centre (x,y,z); w = the candidate's own FP32 threshold (symmetric search)
   int j[CAND_CAP];		// tree index of the candidate
-  int hit[64];			// compacted "maybe" list of the current target
+  int q[QCAP * 32];		// lane = target mode: q[slot * 32 + lane] = ring of tree indices whose FP32 pre-test passed for that lane
+  int hit[64];			// target-major mode: compacted "maybe" list of the current target
   int stk[STK_CAP];		// tree cells still to be examined (DFS entry index, or -(p+2) for a lone particle)
   int2 rng[32];			// particle ranges swallowed in the current step
-  float4 cell[32];		// cubes popped in the current step: centre - group centre, half side
-  float cellh[32];		// their hmax (symmetric search only)
+  float4 cell[32];		// cubes popped in the current step: centre - group centre, padded half side (< 0: not a cube)
+  float cellh[32];		// their padded hmax (symmetric search only)
 };
 
 // FP32 view of the warp's targets for the two conservative filters
 struct GroupF
 {
   double gcx, gcy, gcz;		// group centre (FP64)
-  float ax, ay, az;		// this lane's target position - group centre
+  float ax, ay, az;		// this lane's target position - group centre (idle lanes: 1e18, out of everybody's reach)
   float r;			// this lane's search radius (Hsml), 0 when the lane is idle
-  float amax;			// max |a| component over the warp
+  float rpad, r2pad;		// radius padded for the FP32 cube tests of the collect phase, and its square
+  float amax;			// max |a| component over the active lanes of the warp
 };
 
 // Conservative FP32 bound for "r2 < h*h".  With a, b the FP64 offsets of target and candidate from the group centre
@@ -122,32 +124,37 @@ __device__ __forceinline__ float cand_threshold(float h, float L)
   return h * h * 1.00002f + (8.0e-6f * h + 1.0e-11f * L) * L;
 }
 
-// append the gas particles of the tree range [a,b) (b-a <= 32) to the staged list; returns the new count
+// append the gas particles of the tree range [a,b) (b-a <= 32) to the staged list; returns the new count.
+// The three loads are issued together (one memory latency per range, not three).  With WANT_H the candidate's own
+// FP32 threshold for "r2 < h_j^2" is formed here, once per candidate, with L = max(|its offset|, amax) - the bound
+// of cand_threshold only needs L >= the components of THIS pair.
 template <bool WANT_H>
 __device__ __forceinline__ int stage_range(WarpStage &S, int ncand, int a, int b, int lane, const GroupF &G, float &lmax,
 					    const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
 					    const int *__restrict__ s_type)
 {
   const int j = a + lane;
-  bool ok = j < b;
+  const bool in = j < b;
+  int ty = -1;
+  double hj = 0;
   double4 pm = make_double4(0, 0, 0, 0);
-  if(ok)
+  if(in)
     {
-      ok = (s_type[j] == 0);	// ngb.c:54 / :191: only gas particles are neighbours
-      if(ok)
-	{
-	  pm = gl_ld4(&s_pm[j]);
-	  ok = (pm.w != 0);	// density.c:832 / hydra.c:1236: skip Mass == 0
-	}
+      ty = __ldg(&s_type[j]);
+      pm = gl_ld4(&s_pm[j]);
+      if(WANT_H) hj = __ldg(&s_vh[j].w);
     }
+  // ngb.c:54 / :191: only gas particles are neighbours; density.c:832 / hydra.c:1236: skip Mass == 0
+  const bool ok = in && ty == 0 && pm.w != 0;
   const unsigned ball = __ballot_sync(FULL, ok);
   if(ok)
     {
       const int pos = ncand + __popc(ball & ((1u << lane) - 1));
       const float bx = (float) (pm.x - G.gcx), by = (float) (pm.y - G.gcy), bz = (float) (pm.z - G.gcz);
-      S.cand[pos] = make_float4(bx, by, bz, WANT_H ? (float) s_vh[j].w : 0.f);
+      const float lj = fmaxf(fabsf(bx), fmaxf(fabsf(by), fabsf(bz)));
+      S.cand[pos] = make_float4(bx, by, bz, WANT_H ? cand_threshold((float) hj, fmaxf(lj, G.amax)) : 0.f);
       S.j[pos] = j;
-      lmax = fmaxf(lmax, fmaxf(fabsf(bx), fmaxf(fabsf(by), fabsf(bz))));
+      lmax = fmaxf(lmax, lj);
     }
   return ncand + __popc(ball);
 }
@@ -186,7 +193,6 @@ __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries
   __syncwarp();
   int sp = 1;
   const unsigned lt = (1u << lane) - 1;
-  const bool mine = (active >> lane) & 1;
   while(sp > 0)
     {
       int k = sp < 32 ? sp : 32;
@@ -200,32 +206,39 @@ __device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries
       const bool isnode = my >= 0;
       const bool ispart = my < -1;
       int2 rg = make_int2(0, 0);
-      float4 cf = make_float4(0.f, 0.f, 0.f, -1.f);	// half < 0 marks "not a cube"
+      float4 cf = make_float4(0.f, 0.f, 0.f, -1.0e30f);	// "half side" -1e30: the distance test below can never pass
       float hm = 0.f;
       if(isnode)
 	{
 	  const double4 B = gl_ld4(&e_B[my]);
 	  rg = __ldg(&e_rng[my]);
-	  if(USE_HMAX) hm = (float) __ldg(&e_hmax[my]) * 1.000001f;
-	  cf = make_float4((float) (B.x - G.gcx), (float) (B.y - G.gcy), (float) (B.z - G.gcz), (float) (0.5 * B.w) * 1.000001f);
+	  if(USE_HMAX) hm = (float) __ldg(&e_hmax[my]) * 1.001002f + 1.0e-6f * G.amax;
+	  const float cx = (float) (B.x - G.gcx), cy = (float) (B.y - G.gcy), cz = (float) (B.z - G.gcz), hf = (float) (0.5 * B.w) * 1.000001f;
+	  // FP32 slack for the coordinates that enter the subtractions, folded into the cube: growing the cube by s
+	  // shortens the distance to it by at least min(distance, s), so this is at least as conservative as adding s
+	  // to the search radius
+	  cf = make_float4(cx, cy, cz, hf + 1.0e-6f * (fabsf(cx) + fabsf(cy) + fabsf(cz) + hf));
 	}
       S.cell[lane] = cf;
       if(USE_HMAX) S.cellh[lane] = hm;
       __syncwarp();
-      // lane = target: which of the k cubes does my sphere touch?
-      unsigned touched = 0;
+      // lane = target: which of the k cubes does my sphere touch?  (idle lanes sit at 1e18: they touch nothing)
+      unsigned mybits = 0;
       for(int i = 0; i < k; i++)
 	{
 	  const float4 c = S.cell[i];
-	  if(c.w < 0.f) continue;
 	  const float dx = fmaxf(0.f, fabsf(c.x - G.ax) - c.w), dy = fmaxf(0.f, fabsf(c.y - G.ay) - c.w),
 	    dz = fmaxf(0.f, fabsf(c.z - G.az) - c.w);
-	  float R = USE_HMAX ? fmaxf(G.r, S.cellh[i]) : G.r;
-	  // FP32 slack: relative on the radius, absolute on the coordinates that entered the subtractions
-	  R = R * 1.001f + 1.0e-6f * (fabsf(c.x) + fabsf(c.y) + fabsf(c.z) + c.w + G.amax);
-	  const bool touch = mine && (dx * dx + dy * dy + dz * dz < R * R);
-	  if(__any_sync(FULL, touch)) touched |= 1u << i;
+	  const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+	  float R2 = G.r2pad;
+	  if(USE_HMAX)
+	    {
+	      const float R = fmaxf(G.rpad, S.cellh[i]);
+	      R2 = R * R;
+	    }
+	  mybits |= (d2 < R2) ? (1u << i) : 0u;
 	}
+      const unsigned touched = __reduce_or_sync(FULL, mybits);
       const bool acc = isnode && ((touched >> lane) & 1);
       const bool small = acc && (rg.y - rg.x <= 32);
       bool big = acc && !small;
@@ -312,6 +325,10 @@ __device__ __forceinline__ GroupF make_group(bool act, double px, double py, dou
   float am = fmaxf(fabsf(G.ax), fmaxf(fabsf(G.ay), fabsf(G.az)));
   for(int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(FULL, am, o));
   G.amax = am;
+  // relative slack on the radius, absolute slack for the target coordinates that entered the subtractions
+  G.rpad = G.r * 1.001f + 1.0e-6f * am;
+  G.r2pad = act ? G.rpad * G.rpad : -1.f;
+  if(!act) G.ax = G.ay = G.az = 1.0e18f;
   return G;
 }
 
@@ -586,45 +603,51 @@ __device__ __forceinline__ void density_chunk(WarpStage &S, int ncand, float lma
 
 
 // Phases 2+3, lane = target.  Used while most of the warp is still active: every lane scans the staged candidates
-// (one broadcast shared-memory read per candidate, FP32 conservative filter) and notes the ones its own target may
-// touch in a private byte list; then every lane walks ITS list and adds the reference's FP64 terms straight into its
-// own accumulators - no broadcasts, no cross-lane reduction, and the neighbours arrive in tree order, i.e. in the
-// reference's own summation order.  (When few targets are left, density_chunk's target-major scheme is cheaper.)
-__device__ __forceinline__ void density_chunk_lt(WarpStage &S, int ncand, float lmax, bool todo, int lane, const GroupF &G,
-						 double px, double py, double pz, double vx, double vy, double vz, double h,
-						 int ptype, DensAcc &A, const double4 *__restrict__ s_pm,
-						 const double4 *__restrict__ s_vh, const double *__restrict__ s_entropy)
+// (broadcast shared-memory reads, FP32 conservative filter, 3 FMAs per test) and appends the tree indices its own
+// target may touch to a PRIVATE RING in shared memory; the reference's FP64 test and the sums ("heavy" step) are
+// taken from that ring - no broadcasts, no cross-lane reduction, and every lane adds its neighbours straight into
+// its own accumulators.  The ring outlives the staged chunk, so the heavy steps are not run chunk by chunk (where
+// most lanes had nothing to do in most steps: 12 of 32 lanes busy in the ncu source view) but only when some lane's
+// ring is nearly full, and then every lane with work takes part.  (When few targets are left, density_chunk's
+// target-major scheme is cheaper.)
+template <class Heavy>
+__device__ __forceinline__ void q_drain(WarpStage &S, int lane, int &qh, const int qt, const int low, Heavy heavy)
+{
+  while(__any_sync(FULL, qt - qh > low))
+    if(qt > qh)
+      {
+	const int j = S.q[(qh & (QCAP - 1)) * 32 + lane];
+	qh++;
+	heavy(j);
+      }
+}
+
+template <bool SYM, class Heavy>
+__device__ __forceinline__ void lt_chunk(WarpStage &S, int ncand, float lmax, int lane, const GroupF &G, int &qh, int &qt, Heavy heavy)
 {
   __syncwarp();
   float L = lmax;
   for(int o = 16; o > 0; o >>= 1) L = fmaxf(L, __shfl_xor_sync(FULL, L, o));
   L = fmaxf(L, G.amax);
-  const float thr = todo ? cand_threshold(G.r, L) : -1.f;
-  int nmine = 0;
-#pragma unroll 4
-  for(int c = 0; c < ncand; c++)
+  const float thr = cand_threshold(G.r, L);
+  for(int c0 = 0; c0 < ncand; c0 += 4)
     {
-      const float4 cd = S.cand[c];
-      const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
-      // branch-free append: the slot is overwritten by the next candidate unless this one is kept
-      S.hl[nmine * 32 + lane] = (unsigned char) c;
-      nmine += (dx * dx + dy * dy + dz * dz <= thr) ? 1 : 0;
-    }
-  const double h2 = h * h, hinv = 1.0 / h, hinv3 = hinv * hinv * hinv, hinv4 = hinv3 * hinv;
-  const int kmax = __reduce_max_sync(FULL, nmine);
-  for(int k = 0; k < kmax; k++)
-    {
-      if(k < nmine)
+      // room for four more entries in every ring?  (the append below is branch-free: the slot is written always
+      // and only kept - tail advanced - when the candidate passed, so the ring must never be full when it runs)
+      if(__any_sync(FULL, qt - qh > QCAP - 4)) q_drain(S, lane, qh, qt, QCAP / 2, heavy);
+#pragma unroll
+      for(int u = 0; u < 4; u++)
 	{
-	  const int j = S.j[S.hl[k * 32 + lane]];
-	  const double4 pj = gl_ld4(&s_pm[j]);
-	  // density.c:835-856: dx = pos_i - pos_j, r2 = dx*dx + dy*dy + dz*dz, r2 < h2
-	  const double dx = px - pj.x, dy = py - pj.y, dz = pz - pj.z;
-	  const double r2 = dx * dx + dy * dy + dz * dz;
-	  if(r2 < h2)
+	  const int c = c0 + u;
+	  if(c < ncand)
 	    {
-	      const double4 vj = gl_ld4(&s_vh[j]);
-	      density_pair(A, ptype, dx, dy, dz, r2, pj.w, hinv, hinv3, hinv4, vx, vy, vz, vj, (ptype != 0) ? __ldg(&s_entropy[j]) : 0.0);
+	      const float4 cd = S.cand[c];
+	      const int jj = S.j[c];
+	      const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
+	      const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+	      S.q[(qt & (QCAP - 1)) * 32 + lane] = jj;
+	      // conservative FP32 version of r2 < h_i^2 (density.c:856), or of r2 < h_i^2 || r2 < h_j^2 (hydra.c:1266)
+	      qt += (r2 <= (SYM ? fmaxf(thr, cd.w) : thr)) ? 1 : 0;
 	    }
 	}
     }
@@ -687,19 +710,35 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
       defer = false;
     }
 
+  int qh = 0, qt = 0;
   while(true)
     {
       const unsigned todo_mask = __ballot_sync(FULL, todo);
       if(todo_mask == 0) break;
       if(todo) A.zero();	// lanes that already converged keep the sums of their final round
       const GroupF G = make_group(todo, px, py, pz, h);
+      const bool ltmode = __popc(todo_mask) >= LT_MIN_ACTIVE;
+      const double h2 = h * h, hinv = 1.0 / h, hinv3 = hinv * hinv * hinv, hinv4 = hinv3 * hinv;
+      // lane = target "heavy" step: the reference's FP64 test and sums for one queued candidate of MY target
+      auto heavy = [&](int j) {
+	const double4 pj = gl_ld4(&s_pm[j]);
+	// density.c:835-856: dx = pos_i - pos_j, r2 = dx*dx + dy*dy + dz*dz, r2 < h2
+	const double dx = px - pj.x, dy = py - pj.y, dz = pz - pj.z;
+	const double r2 = dx * dx + dy * dy + dz * dz;
+	if(r2 < h2)
+	  {
+	    const double4 vj = gl_ld4(&s_vh[j]);
+	    density_pair(A, ptype, dx, dy, dz, r2, pj.w, hinv, hinv3, hinv4, vx, vy, vz, vj, (ptype != 0) ? __ldg(&s_entropy[j]) : 0.0);
+	  }
+      };
       sph_collect<false>(S, lane, nentries, e_next, e_B, nullptr, e_rng, n_child, s_pm, s_vh, s_type, todo_mask, G, visits, staged,
 			 [&](int ncand, float lmax) {
-			   if(__popc(todo_mask) >= LT_MIN_ACTIVE)
-			     density_chunk_lt(S, ncand, lmax, todo, lane, G, px, py, pz, vx, vy, vz, h, ptype, A, s_pm, s_vh, s_entropy);
+			   if(ltmode)
+			     lt_chunk<false>(S, ncand, lmax, lane, G, qh, qt, heavy);
 			   else
 			     density_chunk(S, ncand, lmax, todo_mask, lane, G, px, py, pz, vx, vy, vz, h, ptype, A, s_pm, s_vh, s_entropy);
 			 });
+      if(ltmode) q_drain(S, lane, qh, qt, 0, heavy);
 
       // ---- post-processing and Hsml update, density.c:434-652 (one lane = one target) ----
       if(todo)
@@ -1086,249 +1125,6 @@ struct HydroTarget
   int timestep;
 };
 
-__device__ __forceinline__ void hydro_chunk(WarpStage &S, int ncand, float lmax, unsigned live_mask, int lane, const GroupF &G,
-					    const HydroTarget &T, HydroAcc &A, const double4 *__restrict__ s_pm,
-					    const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
-					    const double4 *__restrict__ h_r, double artvisc, double timebase_interval)
-{
-  __syncwarp();
-  float L = lmax;
-  for(int o = 16; o > 0; o >>= 1) L = fmaxf(L, __shfl_xor_sync(FULL, L, o));
-  L = fmaxf(L, G.amax);
-  const float mythr = cand_threshold(G.r, L);
-  for(unsigned rest = live_mask; rest; rest &= rest - 1)
-    {
-      const int t = __ffs(rest) - 1;
-      const float tax = __shfl_sync(FULL, G.ax, t), tay = __shfl_sync(FULL, G.ay, t), taz = __shfl_sync(FULL, G.az, t);
-      const float thr = __shfl_sync(FULL, mythr, t);
-      HydroAcc P;
-      P.zero();
-      int nh = 0;
-      bool loaded = false;
-      double tx = 0, ty = 0, tz = 0, tvx = 0, tvy = 0, tvz = 0, h_i = 0, mass = 0, rho = 0, f1 = 0, cs_i = 0, p_over_rho2_i = 0,
-	h_i2 = 0, hinv_i = 0, hinv4_i = 0;
-      int timestep = 0;
-      for(int base = 0;; base += 32)
-	{
-	  PH_T(tt0);
-	  if(base < ncand)
-	    {
-	      const int c = base + lane;
-	      bool hit = false;
-	      if(c < ncand)
-		{
-		  // conservative FP32 version of hydra.c:1266 (r2 < h_i^2 || r2 < h_j^2)
-		  const float4 cd = S.cand[c];
-		  const float dx = tax - cd.x, dy = tay - cd.y, dz = taz - cd.z;
-		  const float r2 = dx * dx + dy * dy + dz * dz;
-		  hit = (r2 <= thr) || (r2 <= cand_threshold(cd.w, L));
-		}
-	      const unsigned ball = __ballot_sync(FULL, hit);
-	      if(hit) S.hit[nh + __popc(ball & ((1u << lane) - 1))] = c;
-	      nh += __popc(ball);
-	      __syncwarp();
-	      PH_ADD(S, 2, tt0);
-	      if(nh < 32 && base + 32 < ncand) continue;
-	    }
-	  if(nh == 0) break;
-	  PH_T(th0);
-	  if(!loaded)
-	    {
-#define BC(v) __shfl_sync(FULL, (v), t)
-	      tx = BC(T.px); ty = BC(T.py); tz = BC(T.pz); tvx = BC(T.vx); tvy = BC(T.vy); tvz = BC(T.vz);
-	      h_i = BC(T.h_i); mass = BC(T.mass); rho = BC(T.rho); f1 = BC(T.f1); cs_i = BC(T.cs_i);
-	      p_over_rho2_i = BC(T.p_over_rho2_i);
-	      timestep = BC(T.timestep);
-#undef BC
-	      h_i2 = h_i * h_i;
-	      hinv_i = 1.0 / h_i;
-	      hinv4_i = hinv_i * hinv_i * hinv_i * hinv_i;
-	      loaded = true;
-	    }
-	  const int take = nh < 32 ? nh : 32;
-	  if(lane < take)
-	    {
-	      const int j = S.j[S.hit[lane]];
-	      const double4 pj = gl_ld4(&s_pm[j]);
-	      const double4 vj = gl_ld4(&s_vh[j]);
-	      const double dx = tx - pj.x, dy = ty - pj.y, dz = tz - pj.z;
-	      const double r2 = dx * dx + dy * dy + dz * dz;
-	      const double h_j = vj.w;
-	      const double mass_j = pj.w;
-	      const double h_j2 = h_j * h_j;
-	      if(r2 < h_i2 || r2 < h_j2)	// hydra.c:1266, the reference's FP64 predicate
-		{
-		  if(r2 > 0)
-		    {
-		      const double4 q = gl_ld4(&h_q[j]);
-		      const double4 rr = gl_ld4(&h_r[j]);
-		      P.npairs++;
-		      // r and 1/r from one reciprocal square root; the reference divides by r three times
-		      // (hydra.c:1511, 1602, 1606), here these are multiplications by rinv (1 ulp apart)
-		      const double rinv = rsqrt(r2);
-		      const double r = r2 * rinv;
-		      const double rho_j = q.x;
-		      const double soundspeed_j = q.w;
-		      const double dvx = tvx - vj.x, dvy = tvy - vj.y, dvz = tvz - vj.z;
-		      const double vdotr = dx * dvx + dy * dvy + dz * dvz;
-		      const double vdotr2 = vdotr;	// non-comoving, hydra.c:1279-1282
-		      double dwk_i = 0, dwk_j = 0;
-		      if(r2 < h_i2)
-			{
-			  const double u = r * hinv_i;
-			  if(u < 0.5)
-			    dwk_i = hinv4_i * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
-			  else
-			    dwk_i = hinv4_i * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-			}
-		      if(r2 < h_j2)
-			{
-			  const double hinv = 1.0 / h_j;
-			  const double hinv4 = hinv * hinv * hinv * hinv;
-			  const double u = r * hinv;
-			  if(u < 0.5)
-			    dwk_j = hinv4 * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4);
-			  else
-			    dwk_j = hinv4 * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-			}
-		      double vsig = cs_i + soundspeed_j;	// hydra.c:1502
-		      if(vsig > P.maxsig) P.maxsig = vsig;
-		      double visc = 0;
-		      if(vdotr2 < 0)
-			{
-			  const double mu_ij = vdotr2 * rinv;	// fac_mu = 1
-			  vsig -= 3 * mu_ij;
-			  if(vsig > P.maxsig) P.maxsig = vsig;
-			  const double rho_ij = 0.5 * (rho + rho_j);
-			  const double f2 = rr.x;
-			  visc = 0.25 * artvisc * vsig * (-mu_ij) / rho_ij * (f1 + f2);
-			  // hydra.c:1583-1597 viscosity limiter
-			  const int ts_j = (int) rr.y;
-			  const double dt = 2 * ((timestep > ts_j) ? timestep : ts_j) * timebase_interval;
-			  if(dt > 0 && (dwk_i + dwk_j) < 0)
-			    {
-			      const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (mass + mass_j) * (dwk_i + dwk_j) * r * dt);
-			      visc = (visc < lim) ? visc : lim;
-			    }
-			}
-		      const double p_over_rho2_j = q.z;	// already x DhsmlDensityFactor_j (hydra.c:1600)
-		      const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) * rinv;
-		      const double hfc = hfc_visc + mass_j * (p_over_rho2_i * dwk_i + p_over_rho2_j * dwk_j) * rinv;
-		      P.a0 += (-hfc * dx);
-		      P.a1 += (-hfc * dy);
-		      P.a2 += (-hfc * dz);
-		      P.dtE += (0.5 * hfc_visc * vdotr2);
-		    }
-		}
-	    }
-	  hits_shift(S, nh, lane);
-	  PH_ADD(S, 3, th0);
-	  nh -= take;
-	  if(base + 32 >= ncand && nh == 0) break;
-	}
-      PH_T(tr0);
-      const int tot = __reduce_add_sync(FULL, P.npairs);
-      if(tot == 0) continue;
-      const double r0 = warp_sum_d(P.a0), r1 = warp_sum_d(P.a1), r2s = warp_sum_d(P.a2), r3 = warp_sum_d(P.dtE);
-      const double r4 = warp_max_d(P.maxsig);
-      if(lane == t)
-	{
-	  A.a0 += r0; A.a1 += r1; A.a2 += r2s; A.dtE += r3;
-	  if(r4 > A.maxsig) A.maxsig = r4;
-	  A.npairs += tot;
-	}
-      PH_ADD(S, 4, tr0);
-    }
-  __syncwarp();
-}
-
-
-// lane = target version of hydro_chunk (see density_chunk_lt)
-__device__ __forceinline__ void hydro_chunk_lt(WarpStage &S, int ncand, float lmax, bool live, int lane, const GroupF &G,
-					       const HydroTarget &T, HydroAcc &A, const double4 *__restrict__ s_pm,
-					       const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
-					       const double4 *__restrict__ h_r, double artvisc, double timebase_interval)
-{
-  __syncwarp();
-  float L = lmax;
-  for(int o = 16; o > 0; o >>= 1) L = fmaxf(L, __shfl_xor_sync(FULL, L, o));
-  L = fmaxf(L, G.amax);
-  const float thr = live ? cand_threshold(G.r, L) : -1.f;
-  int nmine = 0;
-#pragma unroll 4
-  for(int c = 0; c < ncand; c++)
-    {
-      const float4 cd = S.cand[c];
-      const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
-      const float r2 = dx * dx + dy * dy + dz * dz;
-      // conservative FP32 version of hydra.c:1266 (r2 < h_i^2 || r2 < h_j^2)
-      S.hl[nmine * 32 + lane] = (unsigned char) c;	// branch-free append (see density_chunk_lt)
-      nmine += (live && (r2 <= thr || r2 <= cand_threshold(cd.w, L))) ? 1 : 0;
-    }
-  const double h_i = T.h_i, h_i2 = h_i * h_i, hinv_i = 1.0 / h_i, hinv4_i = hinv_i * hinv_i * hinv_i * hinv_i;
-  const int kmax = __reduce_max_sync(FULL, nmine);
-  for(int k = 0; k < kmax; k++)
-    {
-      if(k < nmine)
-	{
-	  const int j = S.j[S.hl[k * 32 + lane]];
-	  const double4 pj = gl_ld4(&s_pm[j]);
-	  const double4 vj = gl_ld4(&s_vh[j]);
-	  const double dx = T.px - pj.x, dy = T.py - pj.y, dz = T.pz - pj.z;
-	  const double r2 = dx * dx + dy * dy + dz * dz;
-	  const double h_j = vj.w, mass_j = pj.w, h_j2 = h_j * h_j;
-	  if((r2 < h_i2 || r2 < h_j2) && r2 > 0)	// hydra.c:1266, :1270
-	    {
-	      const double4 q = gl_ld4(&h_q[j]);
-	      const double4 rr = gl_ld4(&h_r[j]);
-	      A.npairs++;
-	      const double rinv = rsqrt(r2);
-	      const double r = r2 * rinv;
-	      const double rho_j = q.x, soundspeed_j = q.w;
-	      const double dvx = T.vx - vj.x, dvy = T.vy - vj.y, dvz = T.vz - vj.z;
-	      const double vdotr2 = dx * dvx + dy * dvy + dz * dvz;	// non-comoving, hydra.c:1279-1282
-	      double dwk_i = 0, dwk_j = 0;
-	      if(r2 < h_i2)
-		{
-		  const double u = r * hinv_i;
-		  dwk_i = (u < 0.5) ? hinv4_i * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : hinv4_i * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-		}
-	      if(r2 < h_j2)
-		{
-		  const double u = r * rr.z;
-		  dwk_j = (u < 0.5) ? rr.w * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : rr.w * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-		}
-	      double vsig = T.cs_i + soundspeed_j;	// hydra.c:1502
-	      if(vsig > A.maxsig) A.maxsig = vsig;
-	      double visc = 0;
-	      if(vdotr2 < 0)
-		{
-		  const double mu_ij = vdotr2 * rinv;	// fac_mu = 1
-		  vsig -= 3 * mu_ij;
-		  if(vsig > A.maxsig) A.maxsig = vsig;
-		  const double rho_ij = 0.5 * (T.rho + rho_j);
-		  visc = 0.25 * artvisc * vsig * (-mu_ij) / rho_ij * (T.f1 + rr.x);
-		  // hydra.c:1583-1597 viscosity limiter
-		  const int ts_j = (int) rr.y;
-		  const double dt = 2 * ((T.timestep > ts_j) ? T.timestep : ts_j) * timebase_interval;
-		  if(dt > 0 && (dwk_i + dwk_j) < 0)
-		    {
-		      const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (T.mass + mass_j) * (dwk_i + dwk_j) * r * dt);
-		      visc = (visc < lim) ? visc : lim;
-		    }
-		}
-	      const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) * rinv;
-	      const double hfc = hfc_visc + mass_j * (T.p_over_rho2_i * dwk_i + q.z * dwk_j) * rinv;	// q.z = P_j/rho_j^2 x Omega_j
-	      A.a0 += (-hfc * dx);
-	      A.a1 += (-hfc * dy);
-	      A.a2 += (-hfc * dz);
-	      A.dtE += (0.5 * hfc_visc * vdotr2);
-	    }
-	}
-    }
-  __syncwarp();
-}
-
 __global__ void __launch_bounds__(SPH_BLOCK, 4)
 k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const int2 *__restrict__ e_rng,
@@ -1377,11 +1173,71 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
 #endif
   PH_T(tk0);
   const GroupF G = make_group(live, T.px, T.py, T.pz, T.h_i);
+  const double h_i = T.h_i, h_i2 = h_i * h_i, hinv_i = 1.0 / h_i, hinv4_i = hinv_i * hinv_i * hinv_i * hinv_i;
+  const double artvisc = par.artvisc, timebase_interval = par.timebase_interval;
+  // lane = target "heavy" step (hydra.c:1236-1621 for one queued candidate j of MY target)
+  auto heavy = [&](int j) {
+    const double4 pj = gl_ld4(&s_pm[j]);
+    const double4 vj = gl_ld4(&s_vh[j]);
+    const double dx = T.px - pj.x, dy = T.py - pj.y, dz = T.pz - pj.z;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double h_j = vj.w, mass_j = pj.w, h_j2 = h_j * h_j;
+    if((r2 < h_i2 || r2 < h_j2) && r2 > 0)	// hydra.c:1266, :1270 - the reference's FP64 predicate
+      {
+	const double4 q = gl_ld4(&h_q[j]);
+	const double4 rr = gl_ld4(&h_r[j]);
+	A.npairs++;
+	// r and 1/r from one reciprocal square root; the reference divides by r three times
+	// (hydra.c:1511, 1602, 1606), here these are multiplications by rinv (1 ulp apart)
+	const double rinv = rsqrt(r2);
+	const double r = r2 * rinv;
+	const double rho_j = q.x, soundspeed_j = q.w;
+	const double dvx = T.vx - vj.x, dvy = T.vy - vj.y, dvz = T.vz - vj.z;
+	const double vdotr2 = dx * dvx + dy * dvy + dz * dvz;	// non-comoving, hydra.c:1279-1282
+	double dwk_i = 0, dwk_j = 0;
+	if(r2 < h_i2)
+	  {
+	    const double u = r * hinv_i;
+	    dwk_i = (u < 0.5) ? hinv4_i * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : hinv4_i * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+	  }
+	if(r2 < h_j2)
+	  {
+	    // 1/h_j and 1/h_j^4 come with the source record (k_hydro_prep forms them as hydra.c:1311-1312 does)
+	    const double u = r * rr.z;
+	    dwk_j = (u < 0.5) ? rr.w * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : rr.w * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+	  }
+	double vsig = T.cs_i + soundspeed_j;	// hydra.c:1502
+	if(vsig > A.maxsig) A.maxsig = vsig;
+	double visc = 0;
+	if(vdotr2 < 0)
+	  {
+	    const double mu_ij = vdotr2 * rinv;	// fac_mu = 1
+	    vsig -= 3 * mu_ij;
+	    if(vsig > A.maxsig) A.maxsig = vsig;
+	    const double rho_ij = 0.5 * (T.rho + rho_j);
+	    visc = 0.25 * artvisc * vsig * (-mu_ij) / rho_ij * (T.f1 + rr.x);
+	    // hydra.c:1583-1597 viscosity limiter
+	    const int ts_j = (int) rr.y;
+	    const double dt = 2 * ((T.timestep > ts_j) ? T.timestep : ts_j) * timebase_interval;
+	    if(dt > 0 && (dwk_i + dwk_j) < 0)
+	      {
+		const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (T.mass + mass_j) * (dwk_i + dwk_j) * r * dt);
+		visc = (visc < lim) ? visc : lim;
+	      }
+	  }
+	const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) * rinv;
+	const double hfc = hfc_visc + mass_j * (T.p_over_rho2_i * dwk_i + q.z * dwk_j) * rinv;	// q.z = P_j/rho_j^2 x Omega_j
+	A.a0 += (-hfc * dx);
+	A.a1 += (-hfc * dy);
+	A.a2 += (-hfc * dz);
+	A.dtE += (0.5 * hfc_visc * vdotr2);
+      }
+  };
+  int qh = 0, qt = 0;
+  // hydro has no iteration: every warp but the last one is full, so lane = target always
   sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, G, visits, staged,
-		    [&](int ncand, float lmax) {
-		      // hydro has no iteration: every warp but the last one is full, so lane = target always
-		      hydro_chunk_lt(S, ncand, lmax, live, lane, G, T, A, s_pm, s_vh, h_q, h_r, par.artvisc, par.timebase_interval);
-		    });
+		    [&](int ncand, float lmax) { lt_chunk<true>(S, ncand, lmax, lane, G, qh, qt, heavy); });
+  q_drain(S, lane, qh, qt, 0, heavy);
 #ifdef GL_PHASE_PROF
   PH_ADD(S, 5, tk0);
   __syncwarp();
