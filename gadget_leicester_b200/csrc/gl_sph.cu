@@ -25,6 +25,7 @@
 // formed in a different order (32 partial sums + butterfly), i.e. they agree to ~1e-15 relative.
 #include "gl_internal.h"
 #include <climits>
+#include <cooperative_groups.h>
 #include <algorithm>
 
 gl_dparams gl_make_dparams(const gl_ctx *c);
@@ -830,18 +831,29 @@ __global__ void k_fat_scan(long long n, const double4 *__restrict__ s_pm, const 
 }
 
 #define FAT_THREADS 1024
-__global__ void __launch_bounds__(FAT_THREADS)
+#define FAT_CLUSTER 8		// CTAs (= SMs) that share one fat target
+// One THREAD-BLOCK CLUSTER per fat target: the candidate list is dealt out over 8 CTAs x 1024 threads, the partial
+// sums of a round meet in the shared memory of cluster rank 0 (distributed shared memory writes), rank 0 takes the
+// reference's Hsml step (density.c:548-652) and posts the new Hsml back into every CTA's shared memory; two
+// cluster barriers per round.  (One CTA per target made the central sink of the 1.6M disc - 11 rounds over a
+// ~50 000-entry list - a 0.9 ms serial tail on a single SM.)
+__global__ void __cluster_dims__(FAT_CLUSTER, 1, 1) __launch_bounds__(FAT_THREADS)
 k_fat_rounds(int nf, const int *__restrict__ fat_p, double4 *__restrict__ fat_state, int *__restrict__ fat_flag,
 	     const FatTarget *__restrict__ ft, const int *__restrict__ cnt, const int *__restrict__ off,
 	     const double4 *__restrict__ rec, const double4 *__restrict__ s_pm, double4 *__restrict__ s_vh,
 	     const int *__restrict__ s_type, const int *__restrict__ perm, double4 *__restrict__ e_B, DensIn in, DensOut out,
 	     unsigned long long *__restrict__ counter, gl_dparams par)
 {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double red[FAT_THREADS / 32][8];
   __shared__ int redn[FAT_THREADS / 32];
+  __shared__ double part[FAT_CLUSTER][8];	// meaningful in rank 0: one row of partial sums per CTA of the cluster
+  __shared__ int partn[FAT_CLUSTER];
   __shared__ double sh_h;
   __shared__ int sh_go;
-  const int f = blockIdx.x;
+  const int f = blockIdx.x / FAT_CLUSTER;	// every CTA of a cluster takes the same branch below
+  const unsigned rank = cluster.block_rank();
   if(f >= nf) return;
   if(fat_flag[f] == 1) return;	// already converged in an earlier sweep
   const int p = fat_p[f];
@@ -858,12 +870,14 @@ k_fat_rounds(int nf, const int *__restrict__ fat_p, double4 *__restrict__ fat_st
   double h = st.x, left = st.y, right = st.z;
   int iter = (int) st.w;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double *part0 = cluster.map_shared_rank(&part[0][0], 0);
+  int *partn0 = cluster.map_shared_rank(&partn[0], 0);
   while(true)
     {
       const double h2 = h * h, hinv = 1.0 / h, hinv3 = hinv * hinv * hinv, hinv4 = hinv3 * hinv;
       DensAcc P;
       P.zero();
-      for(int k = threadIdx.x; k < nrec; k += FAT_THREADS)
+      for(int k = rank * FAT_THREADS + threadIdx.x; k < nrec; k += FAT_CLUSTER * FAT_THREADS)
 	{
 	  const double4 a = my[2ll * k];
 	  const double dx = px - a.x, dy = py - a.y, dz = pz - a.z;
@@ -884,22 +898,36 @@ k_fat_rounds(int nf, const int *__restrict__ fat_p, double4 *__restrict__ fat_st
 	  redn[w] = cn;
 	}
       __syncthreads();
-      if(threadIdx.x == 0)
+      if(threadIdx.x < 8)
+	{
+	  // this CTA's partial sums -> row `rank` of cluster rank 0's table
+	  double sum = 0;
+	  int sn = 0;
+	  for(int ww = 0; ww < FAT_THREADS / 32; ww++)
+	    {
+	      if(threadIdx.x < 7) sum += red[ww][threadIdx.x];
+	      else sn += redn[ww];
+	    }
+	  if(threadIdx.x < 7) part0[rank * 8 + threadIdx.x] = sum;
+	  else partn0[rank] = sn;
+	}
+      cluster.sync();
+      if(rank == 0 && threadIdx.x == 0)
 	{
 	  DensAcc A;
 	  A.zero();
-	  for(int ww = 0; ww < FAT_THREADS / 32; ww++)
+	  for(int r = 0; r < FAT_CLUSTER; r++)
 	    {
-	      A.rho += red[ww][0]; A.wngb += red[ww][1]; A.dhsmlrho += red[ww][2];
+	      A.rho += part[r][0]; A.wngb += part[r][1]; A.dhsmlrho += part[r][2];
 	      if(ptype != 0)
 		{
-		  A.gv0 += red[ww][3]; A.gv1 += red[ww][4]; A.gv2 += red[ww][5]; A.sentr += red[ww][6];
+		  A.gv0 += part[r][3]; A.gv1 += part[r][4]; A.gv2 += part[r][5]; A.sentr += part[r][6];
 		}
 	      else
 		{
-		  A.divv += red[ww][3]; A.rot0 += red[ww][4]; A.rot1 += red[ww][5]; A.rot2 += red[ww][6];
+		  A.divv += part[r][3]; A.rot0 += part[r][4]; A.rot1 += part[r][5]; A.rot2 += part[r][6];
 		}
-	      A.numngb += redn[ww];
+	      A.numngb += partn[r];
 	    }
 	  const double h_eval = h;
 	  const bool redo = hsml_step(A.wngb, A.rho, A.dhsmlrho, ptype, desnumngb, par, h, left, right, counter);
@@ -924,13 +952,18 @@ k_fat_rounds(int nf, const int *__restrict__ fat_p, double4 *__restrict__ fat_st
 	    }
 	  fat_state[f] = make_double4(h, left, right, (double) iter);
 	  atomicMax(&counter[1], (unsigned long long) iter);
-	  sh_h = h;
-	  sh_go = go;
+	  // post the decision into every CTA of the cluster
+	  for(int r = 0; r < FAT_CLUSTER; r++)
+	    {
+	      *cluster.map_shared_rank(&sh_h, r) = h;
+	      *cluster.map_shared_rank(&sh_go, r) = go;
+	    }
 	}
-      __syncthreads();
+      cluster.sync();
       h = sh_h;
       if(!sh_go) break;
     }
+  cluster.sync();		// nobody leaves while a peer may still touch its shared memory
 }
 
 static int density_fat_path(gl_ctx *c, int nfat, const DensIn &in, const DensOut &out, const double *s_entropy,
@@ -988,7 +1021,7 @@ static int density_fat_path(gl_ctx *c, int nfat, const DensIn &in, const DensOut
 	  k_fat_scan<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->s_pm.p, c->s_vh.p, c->s_type.p, s_entropy, nb,
 							    (const FatTarget *) c->fat_tgt.p, cnt, off, c->fat_rec.p);
 	  GL_LAUNCH_COUNT(c);
-	  k_fat_rounds<<<nb, FAT_THREADS, 0, c->stream>>>(nb, c->fat_p.p + b0, c->fat_state.p + b0, flag,
+	  k_fat_rounds<<<nb * FAT_CLUSTER, FAT_THREADS, 0, c->stream>>>(nb, c->fat_p.p + b0, c->fat_state.p + b0, flag,
 							  (const FatTarget *) c->fat_tgt.p, cnt, off, c->fat_rec.p, c->s_pm.p,
 							  c->s_vh.p, c->s_type.p, c->perm.p, c->e_B.p, in, out, c->d_counter.p, dp);
 	  GL_LAUNCH_COUNT(c);
