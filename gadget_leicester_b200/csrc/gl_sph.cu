@@ -631,26 +631,34 @@ __device__ __forceinline__ void lt_chunk(WarpStage &S, int ncand, float lmax, in
   for(int o = 16; o > 0; o >>= 1) L = fmaxf(L, __shfl_xor_sync(FULL, L, o));
   L = fmaxf(L, G.amax);
   const float thr = cand_threshold(G.r, L);
-  for(int c0 = 0; c0 < ncand; c0 += 4)
+  char *const qbase = reinterpret_cast<char *>(S.q);
+  // one candidate against MY target.  The append is branch-free: the slot at the ring's tail is written always and
+  // only kept (tail advanced) when the candidate passed - so the ring must never be full when this runs.
+  auto test = [&](int c, unsigned &qoff) {
+    const float4 cd = S.cand[c];
+    const int jj = S.j[c];
+    const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
+    const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    *reinterpret_cast<int *>(qbase + qoff) = jj;
+    // conservative FP32 version of r2 < h_i^2 (density.c:856), or of r2 < h_i^2 || r2 < h_j^2 (hydra.c:1266)
+    const bool hit = r2 <= (SYM ? fmaxf(thr, cd.w) : thr);
+    qt += hit ? 1 : 0;
+    qoff = hit ? ((qoff + 128u) & (QCAP * 128u - 1u)) : qoff;
+  };
+  int c0 = 0;
+  while(c0 < ncand)
     {
-      // room for four more entries in every ring?  (the append below is branch-free: the slot is written always
-      // and only kept - tail advanced - when the candidate passed, so the ring must never be full when it runs)
-      if(__any_sync(FULL, qt - qh > QCAP - 4)) q_drain(S, lane, qh, qt, QCAP / 2, heavy);
-#pragma unroll
-      for(int u = 0; u < 4; u++)
+      // room for eight more entries in every ring?
+      if(__any_sync(FULL, qt - qh > QCAP - 8)) q_drain(S, lane, qh, qt, QCAP / 2, heavy);
+      unsigned qoff = ((unsigned) (qt & (QCAP - 1)) << 7) | ((unsigned) lane << 2);	// byte offset of the tail slot
+      if(c0 + 8 <= ncand)
 	{
-	  const int c = c0 + u;
-	  if(c < ncand)
-	    {
-	      const float4 cd = S.cand[c];
-	      const int jj = S.j[c];
-	      const float dx = G.ax - cd.x, dy = G.ay - cd.y, dz = G.az - cd.z;
-	      const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-	      S.q[(qt & (QCAP - 1)) * 32 + lane] = jj;
-	      // conservative FP32 version of r2 < h_i^2 (density.c:856), or of r2 < h_i^2 || r2 < h_j^2 (hydra.c:1266)
-	      qt += (r2 <= (SYM ? fmaxf(thr, cd.w) : thr)) ? 1 : 0;
-	    }
+#pragma unroll
+	  for(int u = 0; u < 8; u++) test(c0 + u, qoff);
 	}
+      else
+	for(int c = c0; c < ncand; c++) test(c, qoff);
+      c0 += 8;
     }
   __syncwarp();
 }
