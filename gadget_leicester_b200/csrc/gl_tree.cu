@@ -230,6 +230,141 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
   if(nch > 8) child_tab[0] = INT_MIN;
 }
 
+// first index in [lo, hi) whose (key >> sh) is >= pref (keys are sorted), plain bisection
+__device__ __forceinline__ int lower_bound_prefix(const unsigned long long *__restrict__ key, int lo, int hi, int sh,
+						  unsigned long long pref)
+{
+  while(lo < hi)
+    {
+      const int mid = lo + (hi - lo) / 2;
+      if((key[mid] >> sh) < pref)
+	lo = mid + 1;
+      else
+	hi = mid;
+    }
+  return lo;
+}
+
+// k_moments for the sparsely populated upper levels: EIGHT LANES PER NODE.  A cell near the root spans 10^5..10^6
+// particles, and finding its eight child ranges one after the other is a chain of ~300 dependent loads - with one
+// thread per node the six top levels of the 1.6M disc took 0.7 of the 1.07 ms of all moment launches.  Here lane s
+// bisects for the start of octant s and fetches that child's record, all eight in parallel; the sums are then formed
+// in slot order with exactly the operations of k_moments (bit-identical moments, forcetree.c:543-729).
+__global__ void k_moments_wide(int L, const int *__restrict__ lev_list, int count, const unsigned long long *__restrict__ key,
+			       long long n, const signed char *__restrict__ c, const int *__restrict__ noff,
+			       const int *__restrict__ n_first, int *__restrict__ n_end, int *__restrict__ n_parent,
+			       int *__restrict__ p_father, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
+			       const int *__restrict__ s_type, double4 *__restrict__ n_sm, double4 *__restrict__ n_cl,
+			       double4 *__restrict__ n_aux, int *__restrict__ n_child, gl_domain dom, gl_dparams par)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = t >> 3, s = t & 7;
+  const int lane = threadIdx.x & 31, lbase = lane & ~7;
+  const bool live = g < count;
+  const int id = lev_list[live ? g : 0];
+  const int a = n_first[id];
+  const unsigned long long ka = key[a];
+  const int sh = 3 * (GL_BITS - L);	// the node's own prefix
+  const int sh2 = sh - 3;		// its children's
+  // end of the node's range: first key beyond the node's prefix (lane 0 of the group would do; all eight agree)
+  const int b = (L == 0) ? (int) n : lower_bound_prefix(key, a, (int) n, sh, (ka >> sh) + 1);
+  double len = dom.len, cx = dom.center[0], cy = dom.center[1], cz = dom.center[2];
+  for(int lev = 1; lev <= L; lev++)
+    {
+      int d = (int) ((ka >> (3 * (GL_BITS - lev))) & 7);
+      double lenhalf = __dmul_rn(0.25, len);
+      cx = (d & 1) ? __dadd_rn(cx, lenhalf) : __dsub_rn(cx, lenhalf);
+      cy = (d & 2) ? __dadd_rn(cy, lenhalf) : __dsub_rn(cy, lenhalf);
+      cz = (d & 4) ? __dadd_rn(cz, lenhalf) : __dsub_rn(cz, lenhalf);
+      len = __dmul_rn(0.5, len);
+    }
+  // child range of octant s: [lo, hi)
+  const unsigned long long cpref = ((ka >> sh) << 3) | (unsigned long long) s;
+  const int lo = lower_bound_prefix(key, a, b, sh2, cpref);
+  int hi = __shfl_sync(0xffffffffu, lo, lbase + ((s + 1) & 7));
+  if(s == 7) hi = b;
+  const int np = hi - lo;
+  // this lane's child: mass, m*x, m*y, m*z, hmax, vmax, maxsoft
+  double cm = 0, t0 = 0, t1 = 0, t2 = 0, chm = 0, cvm = 0, cms = 0;
+  int code = -1;
+  if(live && np == 1)
+    {
+      const double4 pm = s_pm[lo];
+      const double4 vh = s_vh[lo];
+      const int ty = s_type[lo];
+      cm = pm.w;
+      t0 = __dmul_rn(pm.w, pm.x); t1 = __dmul_rn(pm.w, pm.y); t2 = __dmul_rn(pm.w, pm.z);
+      if(ty == 0)
+	{
+	  chm = vh.w;
+	  cms = vh.w;
+	}
+      else
+	cms = par.soft[ty];
+      cvm = fmax(fabs(vh.x), fmax(fabs(vh.y), fabs(vh.z)));
+      p_father[lo] = id;
+      code = -(lo + 2);
+    }
+  else if(live && np > 1)
+    {
+      const int child = noff[lo] + (L - (int) c[lo]);
+      const double4 cs = n_sm[child];
+      const double4 ca = n_aux[child];
+      cm = cs.w;
+      t0 = __dmul_rn(cs.w, cs.x); t1 = __dmul_rn(cs.w, cs.y); t2 = __dmul_rn(cs.w, cs.z);
+      chm = ca.y; cvm = ca.z; cms = ca.x;
+      n_parent[child] = id;
+      code = lo + child;	// DFS entry index of the child node
+    }
+  const bool present = live && np > 0;
+  const unsigned pres8 = (__ballot_sync(0xffffffffu, present) >> lbase) & 0xffu;
+  // slot-ordered sums, every lane of the group forms the same values
+  double mass = 0, s0 = 0, s1 = 0, s2 = 0, hmax = 0, vmax = 0, maxsoft = 0;
+#pragma unroll
+  for(int k = 0; k < 8; k++)
+    {
+      const double m_k = __shfl_sync(0xffffffffu, cm, lbase + k), a0 = __shfl_sync(0xffffffffu, t0, lbase + k),
+	a1 = __shfl_sync(0xffffffffu, t1, lbase + k), a2 = __shfl_sync(0xffffffffu, t2, lbase + k);
+      const double h_k = __shfl_sync(0xffffffffu, chm, lbase + k), v_k = __shfl_sync(0xffffffffu, cvm, lbase + k),
+	ms_k = __shfl_sync(0xffffffffu, cms, lbase + k);
+      if((pres8 >> k) & 1)
+	{
+	  mass = __dadd_rn(mass, m_k);
+	  s0 = __dadd_rn(s0, a0); s1 = __dadd_rn(s1, a1); s2 = __dadd_rn(s2, a2);
+	  if(h_k > hmax) hmax = h_k;
+	  if(v_k > vmax) vmax = v_k;
+	  if(ms_k > maxsoft) maxsoft = ms_k;
+	}
+    }
+  if(!live) return;
+  // child table: present children in slot order, then -1
+  int *child_tab = n_child + 8ll * id;
+  const int pos = __popc(pres8 & ((1u << s) - 1));
+  const int nch = __popc(pres8);
+  if(present) child_tab[pos] = code;
+  if(s >= nch) child_tab[s] = -1;
+  if(s == 0)
+    {
+      n_end[id] = b;
+      if(L == 0) n_parent[id] = -1;
+      if(mass != 0)
+	{
+	  s0 = __ddiv_rn(s0, mass);
+	  s1 = __ddiv_rn(s1, mass);
+	  s2 = __ddiv_rn(s2, mass);
+	}
+      else
+	{
+	  s0 = cx;
+	  s1 = cy;
+	  s2 = cz;
+	}
+      n_sm[id] = make_double4(s0, s1, s2, mass);
+      n_cl[id] = make_double4(cx, cy, cz, len);
+      n_aux[id] = make_double4(maxsoft, hmax, vmax, 0.0);
+    }
+}
+
 __global__ void k_entries_particles(long long n, const int *__restrict__ noff, const double4 *__restrict__ s_pm,
 				    const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
 				    int *__restrict__ e_next, double4 *__restrict__ e_A, double4 *__restrict__ e_B,
@@ -371,10 +506,16 @@ int glt_build(gl_ctx *c)
       {
 	int cnt = c->lev_start[L + 1] - c->lev_start[L];
 	if(cnt <= 0) continue;
-	k_moments<<<gl_grid(cnt, 128), 128, 0, c->stream>>>(L, c->lev_list.p + c->lev_start[L], cnt, key, n, c->lev_c.p,
-							   c->noff.p, c->n_first.p, c->n_end.p, c->n_parent.p,
-							   c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->n_sm.p,
-							   c->n_cl.p, c->n_aux.p, c->n_child.p, c->dom, dp);
+	if(L < GL_BITS && cnt <= 16384)	// few, fat cells: eight lanes per node (see k_moments_wide)
+	  k_moments_wide<<<gl_grid(8ll * cnt, 128), 128, 0, c->stream>>>(L, c->lev_list.p + c->lev_start[L], cnt, key, n, c->lev_c.p,
+									 c->noff.p, c->n_first.p, c->n_end.p, c->n_parent.p,
+									 c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->n_sm.p,
+									 c->n_cl.p, c->n_aux.p, c->n_child.p, c->dom, dp);
+	else
+	  k_moments<<<gl_grid(cnt, 128), 128, 0, c->stream>>>(L, c->lev_list.p + c->lev_start[L], cnt, key, n, c->lev_c.p,
+							     c->noff.p, c->n_first.p, c->n_end.p, c->n_parent.p,
+							     c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->n_sm.p,
+							     c->n_cl.p, c->n_aux.p, c->n_child.p, c->dom, dp);
 	GL_LAUNCH_COUNT(c);
       }
   size_t ne = (size_t) c->nentries + 1;
