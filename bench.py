@@ -272,8 +272,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ngas", type=int, default=0, help="override gas particles per GPU (default 1.6M)")
-    ap.add_argument("--config", type=int, default=0, choices=[0, 3, 4],
-                    help="0: disc (default, headline); 3: Plummer sphere, gravity only; 4: uniform gas cube, density+hydro only")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="0: 1.6M disc (default, headline); 1: Evrard sphere, 1M gas; 2: 16M disc; 3: Plummer sphere 2^27, gravity "
+                         "only; 4: uniform gas cube 2^27, density+hydro only")
     ap.add_argument("--nparts", type=int, default=0, help="total particles for --config 3/4 (default 2^27)")
     ap.add_argument("--rebalance", action="store_true", help="config 0: re-split the Peano-Hilbert segments by the settle step's GravCost")
     ap.add_argument("--no-rebalance", action="store_true", help="keep the equal-count Peano-Hilbert split (default: work-balanced "
@@ -304,9 +305,18 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warm = max(3, args.warmup)
-    ngas = (args.ngas or N_GAS_PER_GPU) * world
     par = ics.default_params()
-    ps = ics.disc(ngas, seed=42)
+    if args.config == 1:
+        # BASELINE config 1: Evrard collapse, 1M gas, gravitational softening of the gas = Hsml
+        ngas = (args.ngas or 1000000) * world
+        par = ics.default_params(Softening=[1e-4, 5e-5, 5e-5, 1e-7, 0.01, 5e-5])
+        ps = ics.evrard(ngas, seed=42)
+        workload = "BASELINE config 1: Evrard adiabatic gas-sphere collapse, %d gas particles" % ngas
+    else:
+        ngas = (args.ngas or (16000000 if args.config == 2 else N_GAS_PER_GPU)) * world
+        ps = ics.disc(ngas, seed=42)
+        workload = ("BASELINE config 2: scaled self-gravitating disc, %d gas + 2 sinks" if args.config == 2 else
+                    "BASELINE config 0: Pd_N16e5 protoplanetary disc, %d gas + 2 sinks") % ngas
     ps["hsml"] = ics.guess_hsml(ps, par["DesNumNgb"])
     ps["hsml"][ps["type"] == 5] = par["Softening"][5]
     n = ps["pos"].shape[0]
@@ -371,26 +381,34 @@ def main():
 
     # ---- roofline of the dominant kernel (per-launch durations from the library's CUDA events) ----
     pk = peaks()
-    own_targets = dfp.hi - dfp.lo
     own_gas = int((ps["type"][dfp.order[dfp.lo:dfp.hi]] == 0).sum())
-    cand = dict(gravity_walk=phase["ms_gravity_walk"], density=phase["ms_density"], hydro=phase["ms_hydro"])
+    nsm = torch.cuda.get_device_properties(local).multi_processor_count
+    fp32_peak = nsm * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    fp64_peak = nsm * 64 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12          # 64 DFMA lanes per SM on B200
+    st = dfp.fp.stats()                                                 # pair / pass totals of the last step (this rank)
+    t_w, t_d, t_h = phase["ms_gravity_walk"] * 1e-3, phase["ms_density"] * 1e-3, phase["ms_hydro"] * 1e-3
+    tr = (lambda k: ncu_traffic(k) if world == 1 and not args.ngas and args.config == 0 else None)
+    ach = FLOP_PER_INTERACTION * (inter / args.steps) / t_w / 1e12
+    roofs = dict(
+        gravity_walk=dict(kernel="k_gravity_walk", bound="fp32", achieved=ach, peak=fp32_peak, unit="TFLOP/s", frac=ach / fp32_peak,
+                          traffic=tr("k_gravity_walk"),
+                          note="25 flop/interaction (SURVEY 8(d)) x %d interactions; peak = SMs*128*2*sm_max_mhz from %s"
+                               % (inter // args.steps, pk["source"])))
+    for nm, t, per, units, pairs, fpp, bpp in (("density", t_d, DENS_BYTES_PER_UPDATE, st["density_target_passes"], st["density_pairs"], 68.0, 36.0),
+                                               ("hydro", t_h, HYDRO_BYTES_PER_UPDATE, own_gas, st["hydro_pairs"], 98.0, 60.0)):
+        ach = per * units / t / 1e9
+        roofs[nm] = dict(kernel="k_" + nm, bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
+                         traffic=tr("k_" + nm), algorithmic_bytes=per * units,
+                         pair_work=dict(pairs=int(pairs), flop_per_pair=fpp, fp64_tflops=fpp * pairs / t / 1e12,
+                                        fp64_peak_tflops=fp64_peak, frac_fp64=fpp * pairs / t / 1e12 / fp64_peak,
+                                        gather_bytes_per_pair=bpp, gather_gbs=bpp * pairs / t / 1e9),
+                         note="%g B/update x %d target evaluations (SURVEY 8(d) compulsory HBM bytes; %s passes of the Hsml "
+                              "iteration counted per target); peak from %s; traffic = ncu dram bytes per launch of the same "
+                              "workload (profiles/); pair_work = the L1/L2-served pair arithmetic that actually bounds the kernel"
+                              % (per, units, "all" if nm == "density" else "no", pk["source"]))
+    cand = dict(gravity_walk=t_w, density=t_d, hydro=t_h)
     dom = max(cand, key=cand.get)
-    if dom == "gravity_walk":
-        nsm = torch.cuda.get_device_properties(local).multi_processor_count
-        peak = nsm * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-        ach = FLOP_PER_INTERACTION * (inter / args.steps) / (cand[dom] * 1e-3) / 1e12
-        roof = dict(kernel="k_gravity_walk", bound="fp32", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
-                    traffic=(ncu_traffic("k_gravity_walk") if world == 1 and not args.ngas else None),
-                    note="25 flop/interaction (SURVEY 8(d)); peak = SMs*128*2*sm_max_mhz from " + pk["source"])
-    else:
-        per = DENS_BYTES_PER_UPDATE if dom == "density" else HYDRO_BYTES_PER_UPDATE
-        units = own_gas * (max(1, int(np.mean(passes))) if dom == "density" else 1)
-        ach = per * units / (cand[dom] * 1e-3) / 1e9
-        roof = dict(kernel="k_" + dom, bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"],
-                    traffic=(ncu_traffic("k_" + dom) if world == 1 and not args.ngas else None),
-                    algorithmic_bytes=per * units,
-                    note="%g B/update x %d updates (SURVEY 8(d)); peak from %s; traffic = ncu dram bytes per launch of the same "
-                         "workload (profiles/)" % (per, units, pk["source"]))
+    roof = dict(roofs[dom], others={k: v for k, v in roofs.items() if k != dom})
 
     # ---- e2e: the same step through the drop-in boundary with host P[]/SphP[] (rank-local set) ----
     e2e = None
@@ -463,7 +481,7 @@ def main():
         return
 
     cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == 0:
         try:
             ci, cs, kind = run_cpu_instances(1, 2, CPU_SAMPLE_NGAS)
             cpu_base = dict(value=float(ci[0, 1] / cs[0, 1]), unit=UNIT, cores=1, kind=kind,
@@ -476,8 +494,7 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms_per_step,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 predicates + f32 force magnitude (gravity), f64 (SPH)",
                 data="synthetic",
-                config=dict(workload="BASELINE config 0: Pd_N16e5 protoplanetary disc, %d gas + 2 sinks%s" %
-                            (ngas, "" if world == 1 else " (scaled disc, %d per GPU)" % (ngas // world)),
+                config=dict(workload=workload + ("" if world == 1 else " (weak scaling, %d per GPU)" % (ngas // world)),
                             particles=n, parallelism="ph-segments x%d" % world, l2="256 MiB flush between timed steps",
                             step="tree rebuild + gravity (relative criterion) + density + hmax + hydro"),
                 interactions_per_step=inter_per_step, sph_updates_per_s=(ngas / (ms_per_step * 1e-3)),

@@ -719,7 +719,7 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
       defer = false;
     }
 
-  int qh = 0, qt = 0;
+  int qh = 0, qt = 0, myrounds = 0;
   while(true)
     {
       const unsigned todo_mask = __ballot_sync(FULL, todo);
@@ -752,6 +752,7 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
       // ---- post-processing and Hsml update, density.c:434-652 (one lane = one target) ----
       if(todo)
 	{
+	  myrounds++;
 	  todo = hsml_step(A.wngb, A.rho, A.dhsmlrho, ptype, desnumngb, par, h, left, right, counter);
 	  if(todo && A.numngb > FAT_THRESH) defer = true;
 	}
@@ -779,8 +780,12 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
 
   if(live && !deferred) density_store(A, h, p, pin, ptype, out, in, s_vh, e_B, par);
   const unsigned maxit = __reduce_max_sync(FULL, (unsigned) iter);
+  const unsigned wrounds = __reduce_add_sync(FULL, (unsigned) myrounds);
+  const unsigned wpairs = __reduce_add_sync(FULL, (live && !deferred) ? (unsigned) A.numngb : 0u);
   if(lane == 0)
     {
+      atomicAdd(&counter[9], (unsigned long long) wpairs);	// pairs of the final round (= the integer neighbour counts)
+      atomicAdd(&counter[11], (unsigned long long) wrounds);	// target-passes: every evaluation of every target
       // load-balance diagnostics (the analogue of the reference's work-load balance line, gravtree.c:812)
       const unsigned long long cyc = (unsigned long long) (clock64() - clk0);
       atomicMax(&counter[1], (unsigned long long) maxit);
@@ -960,6 +965,8 @@ k_fat_rounds(int nf, const int *__restrict__ fat_p, double4 *__restrict__ fat_st
 	    }
 	  fat_state[f] = make_double4(h, left, right, (double) iter);
 	  atomicMax(&counter[1], (unsigned long long) iter);
+	  atomicAdd(&counter[11], 1ull);
+	  if(!redo) atomicAdd(&counter[9], (unsigned long long) A.numngb);
 	  // post the decision into every CTA of the cluster
 	  for(int r = 0; r < FAT_CLUSTER; r++)
 	    {
@@ -1106,7 +1113,7 @@ int gls_density(gl_ctx *c)
       c->st.density_fat_targets = (long long) nfat;
     }
   cudaEventRecord(c->ev[1], c->stream);
-  unsigned long long cnt[8];
+  unsigned long long cnt[12];
   GL_CUDA(c, cudaMemcpyAsync(cnt, c->d_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   GL_CUDA(c, cudaGetLastError());
@@ -1115,6 +1122,8 @@ int gls_density(gl_ctx *c)
   c->st.ms_density = ms;
   c->st.density_targets = nt;
   c->st.density_passes_max = (long long) cnt[1];
+  c->st.density_pairs = (long long) cnt[9];
+  c->st.density_target_passes = (long long) cnt[11];
   if(getenv("GL_DEBUG_SPH"))
     fprintf(stderr, "[gl] density: %lld warps, cycles max %.3g avg %.3g | staged max %llu avg %.1f | entry visits max %llu | rounds max %llu | %.2f ms\n",
 	    (nt + 31) / 32, (double) cnt[3], (double) cnt[4] / ((nt + 31) / 32), cnt[5], (double) cnt[6] / ((nt + 31) / 32), cnt[7], cnt[1], ms);
@@ -1173,7 +1182,7 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
 	const double4 *__restrict__ h_q, const double4 *__restrict__ h_r, const int *__restrict__ perm,
 	const double *__restrict__ pressure, const double *__restrict__ dhsml, const double *__restrict__ divvel,
 	const double *__restrict__ curlvel, double *__restrict__ o_hacc, double *__restrict__ o_dtentr,
-	double *__restrict__ o_maxsig, int *__restrict__ o_pairs, gl_dparams par)
+	double *__restrict__ o_maxsig, int *__restrict__ o_pairs, unsigned long long *__restrict__ counter, gl_dparams par)
 {
   extern __shared__ __align__(16) unsigned char gl_smem_raw[];
   WarpStage *stage = reinterpret_cast<WarpStage *>(gl_smem_raw);
@@ -1294,6 +1303,8 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
       o_maxsig[pin] = A.maxsig;
       o_pairs[pin] = A.npairs;
     }
+  const unsigned wpairs = __reduce_add_sync(FULL, live ? (unsigned) A.npairs : 0u);
+  if(lane == 0 && wpairs) atomicAdd(&counter[10], (unsigned long long) wpairs);
 }
 
 int gls_hydro_begin(gl_ctx *c)
@@ -1310,6 +1321,8 @@ int gls_hydro_begin(gl_ctx *c)
   GL_CUDA(c, c->o_hydropairs.ensure(n));
   GL_CUDA(c, c->h_q.ensure(n + 1));
   GL_CUDA(c, c->h_r.ensure(n + 1));
+  GL_CUDA(c, c->d_counter.ensure(16));
+  GL_CUDA(c, cudaMemsetAsync(c->d_counter.p + 10, 0, sizeof(unsigned long long), c->stream));
   cudaEventRecord(c->ev[0], c->stream);
   k_hydro_prep<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->perm.p, c->s_type.p, c->s_vh.p, c->o_density.p, c->o_pressure.p,
 							c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p, c->in_timebin.p, c->h_q.p,
@@ -1333,7 +1346,7 @@ int gls_hydro_launch(gl_ctx *c, const int *tgt, long long nt)
 							  c->e_hmax.p, c->e_rng.p, c->n_child.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
 							  c->h_q.p, c->h_r.p, c->perm.p, c->o_pressure.p, c->o_dhsml.p,
 							  c->o_divvel.p, c->o_curlvel.p, c->o_hacc.p, c->o_dtentr.p,
-							  c->o_maxsig.p, c->o_hydropairs.p, dp);
+							  c->o_maxsig.p, c->o_hydropairs.p, c->d_counter.p, dp);
   GL_LAUNCH_COUNT(c);
   return 0;
 }
@@ -1342,11 +1355,14 @@ int gls_hydro_end(gl_ctx *c)
 {
   cudaEventRecord(c->ev[1], c->stream);
   c->fire_post_launch();
+  unsigned long long hp = 0;
+  GL_CUDA(c, cudaMemcpyAsync(&hp, c->d_counter.p + 10, sizeof(hp), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, c->wait_stream());
   GL_CUDA(c, cudaGetLastError());
   float ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->st.ms_hydro = ms;
+  c->st.hydro_pairs = (long long) hp;
 #ifdef GL_PHASE_PROF
   {
     unsigned long long ph[8];

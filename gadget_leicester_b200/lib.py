@@ -42,7 +42,7 @@ class GLStats(C.Structure):
         "ms_keys_sort", "ms_treebuild", "ms_moments", "ms_gravity_walk", "ms_density", "ms_hmax", "ms_hydro",
         "ms_h2d", "ms_d2h", "ms_potential")] + [(k, C.c_longlong) for k in (
             "interactions", "density_targets", "density_passes_max", "hydro_targets", "numnodes", "numentries",
-            "density_fat_targets", "kernel_launches")]
+            "density_fat_targets", "kernel_launches", "density_pairs", "density_target_passes", "hydro_pairs")]
 
 
 class GLGadgetLayout(C.Structure):

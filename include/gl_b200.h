@@ -155,6 +155,9 @@ typedef struct gl_stats
   long long numnodes, numentries;
   long long density_fat_targets;	/* targets handed to the block-per-target density path */
   long long kernel_launches;	/* kernels launched by this library since gl_create / last reset */
+  long long density_pairs;	/* sum over targets of the integer neighbour count (r2 < h_i^2) of their final pass */
+  long long density_target_passes;	/* number of (target, pass) evaluations of the last gl_density (>= density_targets) */
+  long long hydro_pairs;	/* sum over targets of the pair count (r2 < h_i^2 or r2 < h_j^2, r > 0) */
 } gl_stats;
 int gl_get_stats(gl_ctx * ctx, gl_stats * out);
 void gl_reset_launch_count(gl_ctx * ctx);
