@@ -263,6 +263,49 @@ extern "C" int gl_load_particles_gathered(gl_ctx *c, long long n, int world, lon
   return 0;
 }
 
+// the SPH-side inputs that a split exchange delivers after the tree has been built: rank blocks of 5*m doubles
+// [vel 3m | entropy m | dtentropy m] and 2*m ints [timebin m | ti_begstep m]
+__global__ void k_unpack_late(long long n, gl_segments sg, long long m, const double *__restrict__ fb, const int *__restrict__ ib,
+			      const int *__restrict__ inv, double4 *__restrict__ s_vh, double *__restrict__ vel,
+			      double *__restrict__ entropy, double *__restrict__ dtentropy, int *__restrict__ timebin,
+			      int *__restrict__ tibeg)
+{
+  const long long g = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(g >= n) return;
+  const int r = seg_of(sg, g);
+  const long long j = g - sg.start[r];
+  const double *f = fb + (long long) r * 5 * m;
+  const int *q = ib + (long long) r * 2 * m;
+  const double vx = f[3 * j], vy = f[3 * j + 1], vz = f[3 * j + 2];
+  vel[3 * g] = vx; vel[3 * g + 1] = vy; vel[3 * g + 2] = vz;
+  entropy[g] = f[3 * m + j];
+  dtentropy[g] = f[4 * m + j];
+  timebin[g] = q[j];
+  tibeg[g] = q[m + j];
+  if(inv)
+    {
+      double4 *d = &s_vh[inv[g]];
+      d->x = vx; d->y = vy; d->z = vz;
+    }
+}
+
+extern "C" int gl_set_sph_inputs_gathered(gl_ctx *c, int world, long long m, const long long *seg_start, const double *f64rest,
+					   const int *i32rest)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n;
+  if(n <= 0) return c->fail("gl_set_sph_inputs_gathered: no particles");
+  gl_segments sg;
+  if(make_segments(c, sg, world, seg_start, n, m)) return 1;
+  k_unpack_late<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, sg, m, f64rest, i32rest, c->tree_valid ? c->inv.p : nullptr, c->s_vh.p,
+							 c->in_vel.p, c->in_entropy.p, c->in_dtentropy.p, c->in_timebin.p, c->in_tibegstep.p);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, cudaGetLastError());
+  c->tgt_dirty = true;		// density_isactive (density.c:1035) reads TimeBin
+  return 0;
+}
+
 __global__ void k_unpack_sph(long long n, gl_segments sg, long long m, const double *__restrict__ fb, const int *__restrict__ inv,
 			     double4 *__restrict__ s_vh, double *__restrict__ hsml, double *__restrict__ density,
 			     double *__restrict__ pressure, double *__restrict__ dhsml, double *__restrict__ divvel,

@@ -58,7 +58,7 @@ EXPORTS = [
     "gl_create", "gl_destroy", "gl_last_error", "gl_set_params", "gl_stream", "gl_load_particles", "gl_set_oldacc",
     "gl_set_hsml", "gl_set_sph_state", "gl_domain_find_extent", "gl_domain_set_extent", "gl_peano_keys", "gl_peano_hilbert_order",
     "gl_peano_hilbert_key", "gl_morton_key", "gl_force_treebuild", "gl_get_nodes", "gl_set_targets",
-    "gl_set_targets_ordered", "gl_load_particles_gathered", "gl_set_sph_state_gathered", "gl_set_result_range",
+    "gl_set_targets_ordered", "gl_load_particles_gathered", "gl_set_sph_state_gathered", "gl_set_result_range", "gl_set_sph_inputs_gathered",
     "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations", "gl_compute_potential", "gl_get_potential",
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
@@ -105,6 +105,7 @@ def load_library():
     lib.gl_set_targets_ordered.argtypes = [vp, vp, C.c_longlong, C.c_int]
     lib.gl_load_particles_gathered.argtypes = [vp, C.c_longlong, C.c_int, C.c_longlong, C.POINTER(C.c_longlong), vp, vp, C.c_int]
     lib.gl_set_result_range.argtypes = [vp, C.c_longlong, C.c_longlong]
+    lib.gl_set_sph_inputs_gathered.argtypes = [vp, C.c_int, C.c_longlong, C.POINTER(C.c_longlong), vp, vp]
     lib.gl_set_sph_state_gathered.argtypes = [vp, C.c_int, C.c_longlong, C.POINTER(C.c_longlong), vp]
     lib.gl_get_potential.argtypes = [vp, vp, C.c_int]
     for f in ("gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_potential"):

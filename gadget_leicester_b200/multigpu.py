@@ -151,6 +151,8 @@ class DistributedForcePath:
         self.params = params
         self.n = 0
         self.own = {}
+        self.split_exchange = True   # send what only density / hydro read behind the tree build and the walk
+        self._late = None
         self.t = {}          # wall-clock seconds per sub-phase of the last compute_accelerations (diagnostics)
 
     # -- set-up: the analogue of domain_Decomposition + peano_hilbert_order (domain.c:100, peano.c:25) --------
@@ -231,15 +233,28 @@ class DistributedForcePath:
         import time
         t0 = time.perf_counter()
         m = self.m
-        nf, ni = (F64_ROWS, I32_ROWS) if full else (F64_ROWS_GRAV, I32_ROWS_GRAV)
+        self._late = None
+        split = full and self.world > 1 and self.split_exchange
+        nf, ni = (F64_ROWS, I32_ROWS) if (full and not split) else (F64_ROWS_GRAV, I32_ROWS_GRAV)
         self.full_f64 = allgather_block(self.own_f64[: nf * m], self.world, self.group)
         self.full_i32 = allgather_block(self.own_i32[: ni * m], self.world, self.group)
-        self._sync_lib()
+        if split:
+            # the part only density / hydro read travels while the tree is built and walked
+            ev = torch.cuda.Event()
+            ev.record()
+            rest_f = torch.empty(self.world * (F64_ROWS - nf) * m, dtype=torch.float64, device=self.device)
+            rest_i = torch.empty(self.world * (I32_ROWS - ni) * m, dtype=torch.int32, device=self.device)
+            w1 = dist.all_gather_into_tensor(rest_f, self.own_f64[nf * m:], group=self.group, async_op=True)
+            w2 = dist.all_gather_into_tensor(rest_i, self.own_i32[ni * m:], group=self.group, async_op=True)
+            self._late = (rest_f, rest_i, w1, w2)
+            ev.synchronize()              # the prefix has arrived; the rest is still in flight
+        else:
+            self._sync_lib()
         t0 = self._tick("allgather_state", t0)
         lib, ctx = self.fp._lib, self.fp.ctx
         self.fp._chk(lib.gl_load_particles_gathered(ctx, self.n, self.world, m, self.seg_start,
                                                     C.c_void_p(self.full_f64.data_ptr()), C.c_void_p(self.full_i32.data_ptr()),
-                                                    1 if full else 0))
+                                                    1 if (full and not split) else 0))
         self.fp._chk(lib.gl_set_result_range(ctx, self.lo, self.hi - self.lo))   # this rank only ever reads its own results
         self.fp.N = self.n
         # the segment is consecutive along the Peano-Hilbert curve already: the library keeps the order
@@ -263,9 +278,26 @@ class DistributedForcePath:
         self._sync_lib()
         self._tick("get_gravity", t0)
 
+    def finish_exchange(self):
+        """Second half of a split state exchange: hand the SPH-side inputs to the library (before density)."""
+        if self._late is None:
+            return
+        import time
+        t0 = time.perf_counter()
+        rest_f, rest_i, w1, w2 = self._late
+        w1.wait()
+        w2.wait()
+        self._sync_lib()
+        lib, ctx = self.fp._lib, self.fp.ctx
+        self.fp._chk(lib.gl_set_sph_inputs_gathered(ctx, self.world, self.m, self.seg_start, C.c_void_p(rest_f.data_ptr()),
+                                                    C.c_void_p(rest_i.data_ptr())))
+        self._late = None
+        self._tick("late_state", t0)
+
     def density_and_exchange(self):
         """density() for the owned targets, then exchange step 2 (one all-gather of the packed SphP block)."""
         import time
+        self.finish_exchange()
         t0 = time.perf_counter()
         self.fp.density_nocopy()
         t0 = self._tick("density", t0)
@@ -312,6 +344,7 @@ class DistributedForcePath:
         if sph and self.ngas > 0:
             self.density_and_exchange()
             self.hydro()
+        self.finish_exchange()
 
     def rebalance(self):
         """domain_findSplit_work_balanced (domain.c:1075-1113) with the measured cost of the last gravity call:

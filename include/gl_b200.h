@@ -83,6 +83,11 @@ int gl_set_sph_state(gl_ctx * ctx, const double *density, const double *pressure
  * seg_start[world+1]: global index of each rank's first particle (seg_start[world] = n).  Device pointers. */
 int gl_load_particles_gathered(gl_ctx * ctx, long long n, int world, long long m, const long long *seg_start,
 			       const double *f64buf, const int *i32buf, int full);
+/* split exchange: after a full = 0 load the tree build and the walk can start; the SPH-side inputs follow while they run
+ * and are handed over here before gl_density - rank r's blocks at f64rest + r*5*m = [vel 3m | entropy | dtentropy] and
+ * i32rest + r*2*m = [timebin | ti_begstep].  (Node vmax, which only gl_get_nodes reports, is not refreshed.) */
+int gl_set_sph_inputs_gathered(gl_ctx * ctx, int world, long long m, const long long *seg_start, const double *f64rest,
+			       const int *i32rest);
 /* after density (replaces hydra.c:412 and the hmax exchange forcetree.c:1722-1747): rank r's block at
  * buf + r*6*m = [hsml | density | pressure | dhsml | divvel | curlvel] */
 int gl_set_sph_state_gathered(gl_ctx * ctx, int world, long long m, const long long *seg_start, const double *buf);
