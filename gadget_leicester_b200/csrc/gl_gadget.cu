@@ -50,13 +50,15 @@ static int ensure_pinned(gl_ctx *c, void **p, size_t *cap, size_t bytes)
 struct PullStage
 {
   double *pos, *vel, *mass, *hsml, *oldacc, *entropy, *dtentropy, *velpred;
+  double *sph[5];		// Density, Pressure, DhsmlDensityFactor, DivVel, CurlVel (only pulled with an active list)
   int *type, *timebin, *tibeg;
-  static size_t bytes(long long n) { return (size_t) n * (14 * sizeof(double) + 3 * sizeof(int)); }
+  static size_t bytes(long long n) { return (size_t) n * (19 * sizeof(double) + 3 * sizeof(int)); }
   PullStage(void *base, long long n)
   {
     pos = (double *) base; vel = pos + 3 * n; mass = vel + 3 * n; hsml = mass + n; oldacc = hsml + n;
     entropy = oldacc + n; dtentropy = entropy + n; velpred = dtentropy + n;
-    type = (int *) (velpred + 3 * n); timebin = type + n; tibeg = timebin + n;
+    for(int k = 0; k < 5; k++) sph[k] = velpred + 3 * n + k * n;
+    type = (int *) (sph[4] + n); timebin = type + n; tibeg = timebin + n;
   }
 };
 
@@ -73,6 +75,14 @@ static int ensure_input_buffers(gl_ctx *c, long long n, long long ngas)
   GL_CUDA(c, c->in_entropy.ensure((size_t) n));
   GL_CUDA(c, c->in_dtentropy.ensure((size_t) n));
   GL_CUDA(c, c->in_velpred.ensure(3 * (size_t) std::max<long long>(ngas, 1)));
+  if(c->n_tgt_in >= 0)
+    {				// active list: SphP state of the inactive particles comes from the host (see submit_pack_B)
+      GL_CUDA(c, c->o_density.ensure((size_t) n));
+      GL_CUDA(c, c->o_pressure.ensure((size_t) n));
+      GL_CUDA(c, c->o_dhsml.ensure((size_t) n));
+      GL_CUDA(c, c->o_divvel.ensure((size_t) n));
+      GL_CUDA(c, c->o_curlvel.ensure((size_t) n));
+    }
   return 0;
 }
 
@@ -148,9 +158,12 @@ static std::shared_ptr<HostJob> submit_pack_A(gl_ctx *c, const char *P, long lon
 
 // ---- pack B: the SphP[] fields of the gas block (VelPred, Entropy, DtEntropy) and its TimeBin / Ti_begstep from
 // P[]; checks Type == 0 there (bad_type counts violations).  Copies go out on `cs`. ----
+// With an active list (with_state) the SphP[] results of EARLIER steps are pulled as well: hydro reads Density,
+// Pressure, DhsmlDensityFactor, DivVel, CurlVel of inactive neighbours from memory (hydra.c:1236-1275), and only the
+// active particles get new values from this call's density().
 static std::shared_ptr<HostJob> submit_pack_B(gl_ctx *c, const char *P, const char *S, long long ngas, PullStage st,
 					      std::atomic<int> *left, cudaStream_t cs, cudaEvent_t done_ev,
-					      std::atomic<int> *cuda_err, std::atomic<long long> *bad_type)
+					      std::atomic<int> *cuda_err, std::atomic<long long> *bad_type, bool with_state)
 {
   const gl_gadget_layout L = c->lay;
   const long long nchunks = (ngas + PACK_CHUNK - 1) / PACK_CHUNK;
@@ -175,6 +188,14 @@ static std::shared_ptr<HostJob> submit_pack_B(gl_ctx *c, const char *P, const ch
 	bad += (*(const short *) (pi + L.p_Type) != 0);
 	st.timebin[i] = *(const short *) (pi + L.p_TimeBin);
 	st.tibeg[i] = *(const int *) (pi + L.p_Ti_begstep);
+	if(with_state)
+	  {
+	    st.sph[0][i] = *(const double *) (si + L.s_Density);
+	    st.sph[1][i] = *(const double *) (si + L.s_Pressure);
+	    st.sph[2][i] = *(const double *) (si + L.s_DhsmlDensityFactor);
+	    st.sph[3][i] = *(const double *) (si + L.s_DivVel);
+	    st.sph[4][i] = *(const double *) (si + L.s_CurlVel);
+	  }
       }
     if(bad) bad_type->fetch_add(bad);
     if(left->fetch_sub(1) == 1)
@@ -185,6 +206,12 @@ static std::shared_ptr<HostJob> submit_pack_B(gl_ctx *c, const char *P, const ch
 	if(e == cudaSuccess) e = cudaMemcpyAsync(c->in_dtentropy.p, st.dtentropy, ngas * sizeof(double), cudaMemcpyHostToDevice, cs);
 	if(e == cudaSuccess) e = cudaMemcpyAsync(c->in_timebin.p, st.timebin, ngas * sizeof(int), cudaMemcpyHostToDevice, cs);
 	if(e == cudaSuccess) e = cudaMemcpyAsync(c->in_tibegstep.p, st.tibeg, ngas * sizeof(int), cudaMemcpyHostToDevice, cs);
+	if(with_state)
+	  {
+	    double *dst[5] = { c->o_density.p, c->o_pressure.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p };
+	    for(int k = 0; k < 5 && e == cudaSuccess; k++)
+	      e = cudaMemcpyAsync(dst[k], st.sph[k], ngas * sizeof(double), cudaMemcpyHostToDevice, cs);
+	  }
 	if(e == cudaSuccess) e = cudaEventRecord(done_ev, cs);
 	if(e != cudaSuccess) cuda_err->store((int) e);
       }
@@ -245,7 +272,8 @@ extern "C" int gl_gadget_pull(gl_ctx *c, const void *Pv, const void *SphPv, long
   std::atomic<long long> bad_type{0};
   cudaEventRecord(c->ev[8], c->stream);
   auto ja = submit_pack_A(c, (const char *) Pv, n, ngas, st, sc_left.data(), &cuda_err);
-  auto jb = submit_pack_B(c, (const char *) Pv, (const char *) SphPv, ngas, st, &b_left, c->copy_stream[0], c->ev[12], &cuda_err, &bad_type);
+  auto jb = submit_pack_B(c, (const char *) Pv, (const char *) SphPv, ngas, st, &b_left, c->copy_stream[0], c->ev[12], &cuda_err, &bad_type,
+			  c->n_tgt_in >= 0);
   ja->wait();
   jb->wait();
   if(cuda_err.load()) return c->fail(std::string("gl_gadget_pull: ") + cudaGetErrorString((cudaError_t) cuda_err.load()));
@@ -586,7 +614,7 @@ extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv,
   std::atomic<int> b_left{0}, cuda_err{0};
   std::atomic<long long> bad_type{0};
   auto ja = submit_pack_A(c, P, n, ngas, in, sc_left.data(), &cuda_err);
-  auto jb = submit_pack_B(c, P, S, ngas, in, &b_left, cs0, c->ev[12], &cuda_err, &bad_type);
+  auto jb = submit_pack_B(c, P, S, ngas, in, &b_left, cs0, c->ev[12], &cuda_err, &bad_type, c->n_tgt_in >= 0);
   ja->wait();
   t_packA = now_ms();
   c->have_velpred = false;

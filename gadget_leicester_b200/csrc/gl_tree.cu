@@ -139,15 +139,6 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
   int *child_tab = n_child + 8ll * id;
   int a = n_first[id];
   unsigned long long ka = key[a];
-  int b;
-  if(L == 0)
-    b = (int) n;
-  else
-    {
-      int sh = 3 * (GL_BITS - L);
-      b = range_end(key, a, (int) n, sh, ka >> sh);
-    }
-  n_end[id] = b;
   if(L == 0) n_parent[id] = -1;
 
   // geometric centre and side length: root = domain cube, then the +-len/4 steps of forcetree.c:259-277 / :404-411
@@ -162,18 +153,28 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
       len = __dmul_rn(0.5, len);
     }
 
-  // children in slot order (forcetree.c:543-729)
+  // children in slot order (forcetree.c:543-729).  Child and node boundaries are read off c[] (one BYTE per particle:
+  // c[i] = number of levels keys i-1 and i share): inside the node c[i] > L means "same child", c[i] == L "next
+  // child", c[i] < L "node ends".  The galloping searches on the 8-byte keys this replaces cost ~15 scattered
+  // sectors per node; cells with more than 256 particles fall back to them for the rest of their range.
   double mass = 0, s0 = 0, s1 = 0, s2 = 0, hmax = 0, vmax = 0, maxsoft = 0;
-  int p = a;
-  int sh2 = 3 * (GL_BITS - 1 - L);
-  while(p < b)
+  int p = a, scanned = 0, b;
+  const int sh2 = 3 * (GL_BITS - 1 - L);
+  while(true)
     {
       int q = p + 1;
-      if(L < GL_BITS && q < b) q = range_end(key, p, b, sh2, key[p] >> sh2);
-      if(q - p == 1 || L >= GL_BITS)
+      if(L < GL_BITS)
+	{
+	  while(scanned < 256 && c[q] > L)
+	    {
+	      q++;
+	      scanned++;
+	    }
+	  if(c[q] > L) q = range_end(key, q - 1, (int) n, sh2, key[p] >> sh2);	// big cell: finish this child by bisection
+	}
+      if(q - p == 1)
 	{
 	  // particle leaf (for L == GL_BITS every particle of the finest cell hangs directly below)
-	  q = p + 1;
 	  double4 pm = s_pm[p];
 	  double4 vh = s_vh[p];
 	  int ty = s_type[p];
@@ -209,8 +210,15 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
 	  if(nch < 8) child_tab[nch] = p + child;	// DFS entry index of node (p, L+1): first particle + node id
 	  nch++;
 	}
+      if(c[q] < L)
+	{
+	  b = q;		// keys q-1 and q part company above this cell's level (c[n] = -1 ends the last cell)
+	  break;
+	}
       p = q;
+      scanned++;
     }
+  n_end[id] = b;
   if(mass != 0)
     {
       s0 = __ddiv_rn(s0, mass);
@@ -506,7 +514,8 @@ int glt_build(gl_ctx *c)
       {
 	int cnt = c->lev_start[L + 1] - c->lev_start[L];
 	if(cnt <= 0) continue;
-	if(L < GL_BITS && cnt <= 16384)	// few, fat cells: eight lanes per node (see k_moments_wide)
+	static const int wide_max = getenv("GL_WIDE_MAX") ? atoi(getenv("GL_WIDE_MAX")) : 65536;
+	if(L < GL_BITS && cnt <= wide_max)	// few, fat cells: eight lanes per node (see k_moments_wide)
 	  k_moments_wide<<<gl_grid(8ll * cnt, 128), 128, 0, c->stream>>>(L, c->lev_list.p + c->lev_start[L], cnt, key, n, c->lev_c.p,
 									 c->noff.p, c->n_first.p, c->n_end.p, c->n_parent.p,
 									 c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->n_sm.p,

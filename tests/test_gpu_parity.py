@@ -389,6 +389,97 @@ def test_dropin_aos_boundary_matches_soa_api(FP):
     b.close()
 
 
+def test_dropin_active_subset_only_touches_targets(FP):
+    """An active list (FirstActiveParticle/NextActiveParticle -> gl_set_targets) through the pipelined drop-in call:
+    targets get the values of a full evaluation, every other P[]/SphP[] entry keeps its bytes (the reference only
+    writes active particles, gravtree.c:381, density.c:434, hydra.c:1931)."""
+    from gadget_leicester_b200 import aos
+    ps = ics.disc(12000, seed=5)
+    par = ics.default_params()
+    ps["hsml"] = ics.guess_hsml(ps, par["DesNumNgb"])
+    ps["hsml"][ps["type"] == 5] = par["Softening"][5]
+    n, ngas = ps["pos"].shape[0], 12000
+    # settled state from a full evaluation (so that Density etc. of the non-targets exist for hydro)
+    a = FP(par)
+    arr = aos.GadgetArrays(ps, pinned=False)
+    da = aos.GadgetDropIn(a, arr)
+    da.compute_accelerations()
+    full1 = arr.results()
+    a.set_TreeReconstructFlag(1)
+    da.compute_accelerations()           # second full step: the reference values for the subset step below
+    full2 = arr.results()
+    a.close()
+    # same second step, but only every third particle is active
+    b = FP(dict(par, ErrTolTheta=0.0))
+    arr2 = aos.GadgetArrays(ps, pinned=False)
+    arr2.pview("p_Hsml", np.float64)[:] = full1["Hsml"]
+    arr2.pview("p_OldAcc", np.float64)[:] = full1["OldAcc"]
+    for name, f, c in (("Density", "s_Density", 1), ("Pressure", "s_Pressure", 1), ("DhsmlDensityFactor", "s_DhsmlDensityFactor", 1),
+                       ("DivVel", "s_DivVel", 1), ("CurlVel", "s_CurlVel", 1)):
+        arr2.sview(f, np.float64, c)[:] = full1[name]
+    before_P, before_S = np.array(arr2.P, copy=True), np.array(arr2.SphP, copy=True)
+    sub = np.arange(1, n, 3, dtype=np.int32)
+    db = aos.GadgetDropIn(b, arr2)
+    b.set_targets(sub)
+    # hydro of the subset needs its neighbours' SphP state on the device: the drop-in loads only what the path reads
+    # from P[]/SphP[] inputs, so hand the settled state over like the multi-GPU exchange does
+    db.compute_accelerations()
+    r = arr2.results()
+    assert (r["GravCost"][sub] == full2["GravCost"][sub]).all() and (r["GravAccel"][sub] == full2["GravAccel"][sub]).all()
+    gas_sub = sub[sub < ngas]
+    assert util.rel_err_vec(r["Hsml"][sub], full2["Hsml"][sub]).max() <= 1e-13
+    assert util.rel_err_vec(r["Density"][gas_sub], full2["Density"][gas_sub]).max() <= 1e-13
+    # non-targets: not a byte changed
+    lay = aos.layout()
+    mask = np.ones(n, bool)
+    mask[sub] = False
+    Pb = np.frombuffer(before_P, np.uint8).reshape(n, lay["p_stride"])
+    Pa = np.frombuffer(np.array(arr2.P, copy=True), np.uint8).reshape(n, lay["p_stride"])
+    assert (Pb[mask] == Pa[mask]).all()
+    Sb = np.frombuffer(before_S, np.uint8)[: ngas * lay["sph_stride"]].reshape(ngas, lay["sph_stride"])
+    Sa = np.frombuffer(np.array(arr2.SphP, copy=True), np.uint8)[: ngas * lay["sph_stride"]].reshape(ngas, lay["sph_stride"])
+    assert (Sb[mask[:ngas]] == Sa[mask[:ngas]]).all()
+    b.close()
+
+
+def test_rank_local_dropin_world1(FP):
+    """DistributedDropIn (gl_gadget_pack_segment, gathered load, async push of the owned result slices) with a single
+    rank reproduces the plain drop-in call on the same Peano-Hilbert ordered arrays."""
+    from gadget_leicester_b200 import aos
+    from gadget_leicester_b200.multigpu import DistributedForcePath, DistributedDropIn
+    ps = ics.disc(15000, seed=21)
+    par = ics.default_params()
+    ps["hsml"] = ics.guess_hsml(ps, par["DesNumNgb"])
+    ps["hsml"][ps["type"] == 5] = par["Softening"][5]
+    n = ps["pos"].shape[0]
+    d = DistributedForcePath(par, rank=0, world=1, device=0)
+    order = d.decompose(ps)
+    ph = {k: (np.ascontiguousarray(v[order]) if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+    arr = aos.GadgetArrays(ph, pinned=True)
+    DistributedDropIn(d, arr).compute_accelerations()
+    r1 = arr.results()
+    d.close()
+    a = FP(par)
+    arr2 = aos.GadgetArrays(ph, pinned=False)
+    a._chk(a._lib.gl_gadget_bind(a.ctx, __import__("ctypes").byref(aos.layout_struct())))
+    import gadget_leicester_b200.lib as L
+    a._chk(a._lib.gl_gadget_pull(a.ctx, L._ptr(arr2.P), L._ptr(arr2.SphP), arr2.NumPart, arr2.N_gas))
+    a.N = n
+    a._chk(a._lib.gl_gravity_tree(a.ctx))        # one Barnes-Hut pass, like DistributedForcePath.gravity()
+    a._chk(a._lib.gl_density(a.ctx))
+    a._chk(a._lib.gl_force_update_hmax(a.ctx))
+    a._chk(a._lib.gl_hydro_force(a.ctx))
+    a._chk(a._lib.gl_gadget_push(a.ctx, L._ptr(arr2.P), L._ptr(arr2.SphP), 7))
+    r2 = arr2.results()
+    a.close()
+    assert (r1["GravCost"] == r2["GravCost"]).all() and (r1["GravAccel"] == r2["GravAccel"]).all()
+    assert (r1["OldAcc"] == r2["OldAcc"]).all()
+    assert util.rel_err_vec(r1["Hsml"], r2["Hsml"]).max() <= 1e-13
+    for k in ("Density", "Pressure", "DhsmlDensityFactor", "DivVel", "CurlVel", "MaxSignalVel"):
+        assert util.rel_err_vec(r1[k], r2[k]).max() <= 1e-11, k
+    assert util.rel_err_vec(r1["HydroAccel"], r2["HydroAccel"]).max() <= 1e-8
+
+
 REF_DROPIN = os.path.join(util.ROOT, "oracle", "_ref", "ref_dropin")
 
 
