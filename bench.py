@@ -199,8 +199,9 @@ def big_config(args):
     cold_passes = dfp.fp.stats()["density_passes_max"]
     if world > 1 and args.config == 3 and not args.no_rebalance:
         # domain.c:1075: the next decomposition balances the measured work (GravCost), not the particle count
-        dfp.rebalance()
-        dfp.compute_accelerations(**kw)
+        for _ in range(2):
+            dfp.rebalance(timed=True)
+            dfp.compute_accelerations(**kw)
 
     def one_step():
         dfp.fp.set_TreeReconstructFlag(1)
@@ -232,9 +233,16 @@ def big_config(args):
     clocks = sampler.stop()
     t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
     it = torch.tensor([float(inter)], dtype=torch.float64, device="cuda")
+    rank_phase = None
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(it, op=dist.ReduceOp.SUM)
+        keys = ("ms_gravity_walk", "ms_density", "ms_hydro")
+        mine = torch.tensor([phase[k] for k in keys] + [float(dfp.hi - dfp.lo)], dtype=torch.float64, device="cuda")
+        allr = torch.empty(world * mine.numel(), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, -1).cpu().numpy()
+        rank_phase = {k: [round(float(x), 2) for x in allr[:, j]] for j, k in enumerate(keys + ("targets",))}
     ms_per_step = float(t.item()) / args.steps
     units = (float(it.item()) / args.steps) if args.config == 3 else float(n)
     pk = peaks()
@@ -258,7 +266,8 @@ def big_config(args):
                               config=dict(workload=work, particles=n, parallelism="ph-segments x%d" % world,
                                           l2="inputs larger than L2 (%.1f GB of tree records)" % (n * 150e-9)),
                               phase_ms=phase, density_passes=dict(cold_start=cold_passes), gpu_launches=int(launches), clocks=clocks,
-                              roofline=roof, e2e=None, interactions_per_step=(units if args.config == 3 else None))))
+                              roofline=roof, e2e=None, interactions_per_step=(units if args.config == 3 else None),
+                              rank_phase_ms=rank_phase)))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -346,7 +346,7 @@ class DistributedForcePath:
             self.hydro()
         self.finish_exchange()
 
-    def rebalance(self):
+    def rebalance(self, timed=False):
         """domain_findSplit_work_balanced (domain.c:1075-1113) with the measured cost of the last gravity call:
         weight (1 + GravCost) / 2^TimeBin (domain.c:378-384), one contiguous Peano-Hilbert segment per GPU.
         Three all-gathers (cost, and the current float64 / int32 state blocks); every rank then cuts its new
@@ -356,6 +356,16 @@ class DistributedForcePath:
         send[:k] = 1.0 + self.res["gravcost"][self.lo:self.hi].double()
         send[:k] /= torch.pow(2.0, self.own["timebin"][:k].clamp(min=0).double())
         full = allgather_block(send, self.world, self.group).view(self.world, m)
+        if timed:
+            # cost -> time: scale every rank's weights by (its measured kernel time) / (its summed cost), the role the
+            # measured CPU time plays in the reference's cost adjustment; a GPU whose segment marches through more
+            # tree entries per interaction then gets fewer particles
+            stt = self.fp.stats()
+            mine = torch.tensor([stt["ms_gravity_walk"] + stt["ms_density"] + stt["ms_hydro"], float(send[:k].sum().item())],
+                                dtype=torch.float64, device=dev)
+            allt = allgather_block(mine, self.world, self.group).view(self.world, 2)
+            scale = allt[:, 0] / allt[:, 1].clamp(min=1e-300)
+            full = full * (scale / scale.mean()).view(self.world, 1)
         cost = torch.cat([full[r, : hi - lo] for r, (lo, hi) in enumerate(self.ranges)])
         csum = torch.cumsum(cost, 0)
         tot = float(csum[-1].item())
