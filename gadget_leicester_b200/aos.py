@@ -34,6 +34,79 @@ def layout_struct():
     return g
 
 
+def tree_layout_struct():
+    """gl_tree_layout for the reference's struct NODE / struct extNODE (offsets probed by oracle/refbuild `make layout`)."""
+    lay = layout()
+    g = L.GLTreeLayout()
+    g.node_stride, g.ext_stride = int(lay["sizeof_NODE"]), int(lay["sizeof_extNODE"])
+    for name, _ in L.GLTreeLayout._fields_:
+        if name in lay:
+            setattr(g, name, int(lay[name]))
+    return g
+
+
+class ReferenceTree:
+    """Nodes[] / Extnodes[] / Nextnode[] / Father[] as the reference stores them (allvars.h:1845-1916), filled from
+    the GPU tree by gl_export_tree.  Index space: [0, MaxPart) particles, MaxPart + k = cell k, -1 = end."""
+
+    def __init__(self, fp, max_part=None, tree_alloc_factor=2.0, ti_current=0):
+        lay = layout()
+        n = fp.N
+        self.MaxPart = int(max_part or n)
+        self.MaxNodes = int(tree_alloc_factor * self.MaxPart) + 16
+        self.lay = lay
+        self.nodes = np.zeros(self.MaxNodes * lay["sizeof_NODE"], np.uint8)
+        self.ext = np.zeros(self.MaxNodes * lay["sizeof_extNODE"], np.uint8)
+        self.Nextnode = np.full(self.MaxPart, -2, np.int32)
+        self.Father = np.full(self.MaxPart, -2, np.int32)
+        tl = tree_layout_struct()
+        nn = C.c_longlong(0)
+        fp._chk(fp._lib.gl_export_tree(fp.ctx, C.byref(tl), L._ptr(self.nodes), L._ptr(self.ext), L._ptr(self.Nextnode),
+                                       L._ptr(self.Father), self.MaxPart, self.MaxNodes, int(ti_current), C.byref(nn)))
+        self.Numnodestree = int(nn.value)
+
+    def nfield(self, name, dtype, count=1):
+        st, m = self.lay["sizeof_NODE"], self.Numnodestree
+        item = np.dtype(dtype).itemsize
+        return np.ndarray((m, count) if count > 1 else (m,), dtype=dtype, buffer=self.nodes.data, offset=self.lay[name],
+                          strides=(st, item) if count > 1 else (st,))
+
+    def efield(self, name, dtype, count=1):
+        st, m = self.lay["sizeof_extNODE"], self.Numnodestree
+        item = np.dtype(dtype).itemsize
+        return np.ndarray((m, count) if count > 1 else (m,), dtype=dtype, buffer=self.ext.data, offset=self.lay[name],
+                          strides=(st, item) if count > 1 else (st,))
+
+    def ngb_treefind_variable(self, pos, types, center, hsml):
+        """ngb.c:169-297 on the exported arrays (plain Python, for tests): gas particles within the box/sphere tests of
+        the reference's walk, in the reference's visiting order."""
+        ln, ctr = self.nfield("n_len", np.float64), self.nfield("n_center", np.float64, 3)
+        sib, nxt = self.nfield("n_sibling", np.int32), self.nfield("n_nextnode", np.int32)
+        out, no, MP = [], self.MaxPart, self.MaxPart
+        while no >= 0:
+            if no < MP:
+                p = no
+                no = int(self.Nextnode[no])
+                if types[p] > 0:
+                    continue
+                d = pos[p] - center
+                if (np.abs(d) > hsml).any() or (d * d).sum() > hsml * hsml:
+                    continue
+                out.append(p)
+            else:
+                k = no - MP
+                no = int(sib[k])
+                dist = hsml + 0.5 * ln[k]
+                d = np.abs(ctr[k] - center)
+                if (d > dist).any():
+                    continue
+                dist += 0.366025403785 * ln[k]      # FACT1, ngb.c:30
+                if (d * d).sum() > dist * dist:
+                    continue
+                no = int(nxt[k])
+        return out
+
+
 def _host_buffer(nbytes, pinned):
     if pinned:
         import torch

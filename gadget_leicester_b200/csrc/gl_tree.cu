@@ -636,3 +636,96 @@ int glt_get_nodes(gl_ctx *c, double *table, long long cap)
   tmp.release();
   return 0;
 }
+
+// ---------------------------------------------------------------- tree export (reference layout) ----
+// reference index of DFS entry x: a particle is its P[] index, cell k is MaxPart + k, the end of the tree is -1
+__device__ __forceinline__ int ref_index(long long x, long long nentries, const int *__restrict__ e_next,
+					 const int2 *__restrict__ e_rng, const int *__restrict__ perm, int maxpart)
+{
+  if(x >= nentries) return -1;
+  const int nx = e_next[x];
+  if(nx < 0) return perm[(-1 - nx) >> 3];
+  return maxpart + (int) (x - e_rng[x].x);
+}
+
+__global__ void k_export_nodes(long long m, long long nentries, gl_tree_layout L, int maxpart, int ti_current,
+			       const int *__restrict__ n_first, const int *__restrict__ n_parent,
+			       const double4 *__restrict__ n_sm, const double4 *__restrict__ n_cl,
+			       const double4 *__restrict__ n_aux, const int *__restrict__ e_next,
+			       const int2 *__restrict__ e_rng, const double *__restrict__ e_hmax,
+			       const int *__restrict__ perm, char *__restrict__ nodes, char *__restrict__ ext)
+{
+  const long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(id >= m) return;
+  const long long e = (long long) n_first[id] + id;
+  char *nd = nodes + id * L.node_stride, *ex = ext + id * L.ext_stride;
+  const double4 cl = n_cl[id], sm = n_sm[id], ax = n_aux[id];
+  *(double *) (nd + L.n_len) = cl.w;
+  double *ctr = (double *) (nd + L.n_center);
+  ctr[0] = cl.x; ctr[1] = cl.y; ctr[2] = cl.z;
+  if(L.n_maxsoft >= 0) *(double *) (nd + L.n_maxsoft) = ax.x;
+  double *sp = (double *) (nd + L.n_s);
+  sp[0] = sm.x; sp[1] = sm.y; sp[2] = sm.z;
+  *(double *) (nd + L.n_mass) = sm.w;
+  *(unsigned int *) (nd + L.n_bitflags) = L.bitflags_value;
+  *(int *) (nd + L.n_nextnode) = ref_index(e + 1, nentries, e_next, e_rng, perm, maxpart);	// first daughter follows in DFS order
+  *(int *) (nd + L.n_sibling) = ref_index(e_next[e], nentries, e_next, e_rng, perm, maxpart);
+  *(int *) (nd + L.n_father) = (n_parent[id] >= 0) ? maxpart + n_parent[id] : -1;
+  *(int *) (nd + L.n_Ti_current) = ti_current;
+  // extNODE: vs / divVmax / dp only feed the dynamic tree update (force_drift_node), which a per-step rebuild never runs
+  *(double *) (ex + L.e_vmax) = ax.z;
+  *(double *) (ex + L.e_hmax) = e_hmax[e];
+  *(int *) (ex + L.e_Ti_lastkicked) = ti_current;
+}
+
+__global__ void k_export_particles(long long n, long long nentries, int maxpart, const int *__restrict__ noff,
+				   const int *__restrict__ p_father, const int *__restrict__ e_next,
+				   const int2 *__restrict__ e_rng, const int *__restrict__ perm, int *__restrict__ nextnode,
+				   int *__restrict__ father)
+{
+  const long long p = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(p >= n) return;
+  const int i = perm[p];
+  const long long e = p + noff[p + 1];
+  nextnode[i] = ref_index(e + 1, nentries, e_next, e_rng, perm, maxpart);
+  father[i] = (p_father[p] >= 0) ? maxpart + p_father[p] : -1;
+}
+
+extern "C" int gl_export_tree(gl_ctx *c, const gl_tree_layout *lay, void *nodes_base, void *extnodes_base, int *nextnode,
+			      int *father, long long MaxPart, long long max_nodes, int Ti_Current, long long *numnodes)
+{
+  cudaSetDevice(c->device);
+  if(!c->tree_valid) return c->fail("gl_export_tree: no tree (call gl_force_treebuild or gl_gravity_tree first)");
+  const long long n = c->n, m = c->nnodes;
+  if(n > MaxPart) return c->fail("gl_export_tree: more particles than MaxPart");
+  if(m > max_nodes) return c->fail("gl_export_tree: more cells than MaxNodes (the reference would retry with a larger TreeAllocFactor, forcetree.c:71-91)");
+  if(lay->node_stride <= 0 || lay->ext_stride <= 0) return c->fail("gl_export_tree: bad layout");
+  DBuf<char> dn, de;
+  DBuf<int> dx;
+  GL_CUDA(c, dn.ensure((size_t) std::max<long long>(m, 1) * lay->node_stride));
+  GL_CUDA(c, de.ensure((size_t) std::max<long long>(m, 1) * lay->ext_stride));
+  GL_CUDA(c, dx.ensure(2 * (size_t) n));
+  GL_CUDA(c, cudaMemsetAsync(dn.p, 0, (size_t) m * lay->node_stride, c->stream));
+  GL_CUDA(c, cudaMemsetAsync(de.p, 0, (size_t) m * lay->ext_stride, c->stream));
+  if(m > 0)
+    {
+      k_export_nodes<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->nentries, *lay, (int) MaxPart, Ti_Current, c->n_first.p, c->n_parent.p,
+							    c->n_sm.p, c->n_cl.p, c->n_aux.p, c->e_next.p, c->e_rng.p, c->e_hmax.p,
+							    c->perm.p, dn.p, de.p);
+      GL_LAUNCH_COUNT(c);
+    }
+  k_export_particles<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->nentries, (int) MaxPart, c->noff.p, c->p_father.p, c->e_next.p,
+							      c->e_rng.p, c->perm.p, dx.p, dx.p + n);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaMemcpyAsync(nodes_base, dn.p, (size_t) m * lay->node_stride, cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaMemcpyAsync(extnodes_base, de.p, (size_t) m * lay->ext_stride, cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaMemcpyAsync(nextnode, dx.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaMemcpyAsync(father, dx.p + n, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, cudaGetLastError());
+  dn.release();
+  de.release();
+  dx.release();
+  if(numnodes) *numnodes = m;
+  return 0;
+}

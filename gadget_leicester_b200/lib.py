@@ -53,6 +53,12 @@ class GLGadgetLayout(C.Structure):
         "s_DtEntropy", "s_HydroAccel", "s_DhsmlDensityFactor", "s_DivVel", "s_CurlVel")]
 
 
+class GLTreeLayout(C.Structure):
+    _fields_ = [("node_stride", C.c_longlong), ("ext_stride", C.c_longlong)] + [(k, C.c_int) for k in (
+        "n_len", "n_center", "n_maxsoft", "n_s", "n_mass", "n_bitflags", "n_sibling", "n_nextnode", "n_father", "n_Ti_current",
+        "e_vs", "e_vmax", "e_divVmax", "e_hmax", "e_Ti_lastkicked", "e_Flag")] + [("bitflags_value", C.c_uint)]
+
+
 # every symbol include/gl_b200.h declares (tests check that the .so exports all of them)
 EXPORTS = [
     "gl_create", "gl_destroy", "gl_last_error", "gl_set_params", "gl_stream", "gl_load_particles", "gl_set_oldacc",
@@ -62,7 +68,7 @@ EXPORTS = [
     "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations", "gl_compute_potential", "gl_get_potential",
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
-    "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait",
+    "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree",
 ]
 
 _lib = None
@@ -127,6 +133,8 @@ def load_library():
     lib.gl_gadget_pack_segment.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, vp, vp]
     lib.gl_gadget_push_segment_async.argtypes = [vp, vp, vp, C.c_int]
     lib.gl_gadget_push_wait.argtypes = [vp]
+    lib.gl_export_tree.argtypes = [vp, C.POINTER(GLTreeLayout), vp, vp, vp, vp, C.c_longlong, C.c_longlong, C.c_int,
+                                   C.POINTER(C.c_longlong)]
     _lib = lib
     return lib
 

@@ -189,6 +189,28 @@ int gl_gadget_compute_accelerations(gl_ctx * ctx, void *P, void *SphP, long long
 /* scatter results back in place; what = bit mask: 1 gravity, 2 density, 4 hydro */
 int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
 
+/* ---- the tree, in the reference's own storage (SURVEY.md 8(b) "Tree (if CPU consumers are kept)") ---------------
+ * The sub-grid loops that follow the force path in the reference (sink accretion blackhole.c:794,1201,1351, dust
+ * dust.c:60,263,748, setup_smoothinglengths init.c:719, its own force_update_hmax) walk Nodes[] / Nextnode[] with
+ * ngb_treefind_* (ngb.c).  Instead of re-building that tree on the host (force_treebuild, ~0.4 us/particle on one
+ * core) the GPU tree is written into the reference's arrays: struct NODE / struct extNODE records (allvars.h:1845,
+ * :1887) with the threading of force_update_node_recursive (forcetree.c:468-872): nextnode = first daughter,
+ * sibling = next entry behind the subtree, Nextnode[i] = entry behind particle i, Father[i] = its parent cell;
+ * node k of the library is Nodes[MaxPart + k], the root is Nodes[MaxPart] (density.c:804).  Offsets come from the
+ * reference side via offsetof(), like gl_gadget_layout.  Single rank only: no pseudo-particles are inserted. */
+typedef struct gl_tree_layout
+{
+  long long node_stride, ext_stride;	/* sizeof(struct NODE), sizeof(struct extNODE) */
+  int n_len, n_center, n_maxsoft;	/* n_maxsoft < 0: the build has no ADAPTIVE_GRAVSOFT_FORGAS */
+  int n_s, n_mass, n_bitflags, n_sibling, n_nextnode, n_father, n_Ti_current;
+  int e_vs, e_vmax, e_divVmax, e_hmax, e_Ti_lastkicked, e_Flag;
+  unsigned int bitflags_value;		/* what a cell with >= 2 particles carries: 1 << BITFLAG_MULTIPLEPARTICLES */
+} gl_tree_layout;
+/* nodes_base / extnodes_base: first allocated node (= Nodes + MaxPart); nextnode, father: MaxPart ints each, indexed
+ * like P[]; fails if more than max_nodes cells exist.  *numnodes <- Numnodestree. */
+int gl_export_tree(gl_ctx * ctx, const gl_tree_layout * lay, void *nodes_base, void *extnodes_base, int *nextnode,
+		   int *father, long long MaxPart, long long max_nodes, int Ti_Current, long long *numnodes);
+
 /* ---- multi-GPU drop-in: every rank keeps its own P[] / SphP[] (its Peano-Hilbert segment), as every MPI rank of the
  * reference does; the sources are replicated with gl_load_particles_gathered --------------------------------------- */
 /* pack this rank's arrays into its all-gather block (layout of gl_load_particles_gathered, padded to m particles) and

@@ -22,6 +22,7 @@
 #include <mpi.h>
 #include "allvars.h"
 #include "proto.h"
+#include "forcetree.h"
 #include "gl_b200.h"
 
 static gl_ctx *GL;
@@ -146,6 +147,41 @@ void gravity_tree(void)
   gl_sync_params();
   if(gl_gravity_tree(GL)) gl_fail("gl_gravity_tree");
   if(gl_gadget_push(GL, P, SphP, 1)) gl_fail("gl_gadget_push");
+#ifdef GL_EXPORT_TREE
+  /* The reference's remaining tree walkers (sink / dust loops, setup_smoothinglengths, its own force_update_hmax) find
+   * the GPU tree in Nodes[] / Extnodes[] / Nextnode[] / Father[] - no host tree build at all. */
+  if(TreeReconstructFlag)
+    {
+      gl_tree_layout T;
+      long long nn = 0;
+      T.node_stride = sizeof(struct NODE);
+      T.ext_stride = sizeof(struct extNODE);
+      T.n_len = offsetof(struct NODE, len);
+      T.n_center = offsetof(struct NODE, center);
+#ifdef ADAPTIVE_GRAVSOFT_FORGAS
+      T.n_maxsoft = offsetof(struct NODE, maxsoft);
+#else
+      T.n_maxsoft = -1;
+#endif
+      T.n_s = offsetof(struct NODE, u.d.s);
+      T.n_mass = offsetof(struct NODE, u.d.mass);
+      T.n_bitflags = offsetof(struct NODE, u.d.bitflags);
+      T.n_sibling = offsetof(struct NODE, u.d.sibling);
+      T.n_nextnode = offsetof(struct NODE, u.d.nextnode);
+      T.n_father = offsetof(struct NODE, u.d.father);
+      T.n_Ti_current = offsetof(struct NODE, Ti_current);
+      T.e_vs = offsetof(struct extNODE, vs);
+      T.e_vmax = offsetof(struct extNODE, vmax);
+      T.e_divVmax = offsetof(struct extNODE, divVmax);
+      T.e_hmax = offsetof(struct extNODE, hmax);
+      T.e_Ti_lastkicked = offsetof(struct extNODE, Ti_lastkicked);
+      T.e_Flag = offsetof(struct extNODE, Flag);
+      T.bitflags_value = 1u << BITFLAG_MULTIPLEPARTICLES;
+      if(gl_export_tree(GL, &T, Nodes_base, Extnodes_base, Nextnode, Father, All.MaxPart, MaxNodes, All.Ti_Current, &nn))
+	gl_fail("gl_export_tree");
+      Numnodestree = (int) nn;
+    }
+#endif
 #ifdef GL_KEEP_CPU_TREE
   /* The reference's sub-grid physics (blackhole.c:1351, dust.c:1235), setup_smoothinglengths (init.c:719) and its own
    * force_update_hmax still walk the CPU Nodes[] tree.  Until those loops are ported too a host

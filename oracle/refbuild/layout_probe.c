@@ -21,6 +21,14 @@ int main(void)
   SO("s_Entropy", Entropy); SO("s_Pressure", Pressure); SO("s_VelPred", VelPred); SO("s_MaxSignalVel", MaxSignalVel);
   SO("s_Density", d.Density); SO("s_DtEntropy", e.DtEntropy); SO("s_HydroAccel", a.HydroAccel);
   SO("s_DhsmlDensityFactor", h.DhsmlDensityFactor); SO("s_DivVel", v.DivVel); SO("s_CurlVel", r.CurlVel);
+#define NO(name, field) printf("  \"%s\": %zu,\n", name, offsetof(struct NODE, field))
+#define EO(name, field) printf("  \"%s\": %zu,\n", name, offsetof(struct extNODE, field))
+  NO("n_len", len); NO("n_center", center); NO("n_maxsoft", maxsoft); NO("n_s", u.d.s); NO("n_mass", u.d.mass);
+  NO("n_bitflags", u.d.bitflags); NO("n_sibling", u.d.sibling); NO("n_nextnode", u.d.nextnode); NO("n_father", u.d.father);
+  NO("n_Ti_current", Ti_current);
+  EO("e_vs", vs); EO("e_vmax", vmax); EO("e_divVmax", divVmax); EO("e_hmax", hmax); EO("e_Ti_lastkicked", Ti_lastkicked);
+  EO("e_Flag", Flag);
+  printf("  \"bitflags_value\": %u,\n", 1u << 7);	/* 1 << BITFLAG_MULTIPLEPARTICLES, forcetree.h:18 */
   printf("  \"sizeof_NODE\": %zu,\n  \"sizeof_extNODE\": %zu\n}\n", sizeof(struct NODE), sizeof(struct extNODE));
   return 0;
 }

@@ -141,6 +141,9 @@ static void dump_particles_out(const char *prefix, int what)
   free(d3); free(d1); free(i1);
 }
 
+void ref_density(void) __attribute__((weak));
+void ref_hydro_force(void) __attribute__((weak));
+
 static void dump_nodes(const char *prefix)
 {
   long long nn = Numnodestree, k;
@@ -391,6 +394,10 @@ int main(int argc, char **argv)
 		  }
 	      break;
 	    case 'D': density(); break;
+	    /* drop-in binaries keep the reference's own CPU loops under ref_* (objcopy, see Makefile): 'd' / 'h' run them on
+	       whatever tree Nodes[] holds - the GPU tree written by gl_export_tree in the ref_dropin_tree build */
+	    case 'd': if(!ref_density) { fprintf(stderr, "op d needs a drop-in build\n"); return 2; } ref_density(); break;
+	    case 'h': if(!ref_hydro_force) { fprintf(stderr, "op h needs a drop-in build\n"); return 2; } ref_hydro_force(); break;
 	    case 'R': TreeReconstructFlag = 1; break;
 	    case 'G': gravity_tree(); break;
 	    case 'U': force_update_hmax(); break;
@@ -402,7 +409,7 @@ int main(int argc, char **argv)
 	    default: fprintf(stderr, "unknown op %c\n", op); return 2;
 	    }
 	  dt = now() - t0;
-	  if(strchr("TDGUHP", op)) put(prefix, "time", 'd', 1, 1, &dt);
+	  if(strchr("TDGUHPdh", op)) put(prefix, "time", 'd', 1, 1, &dt);
 	  if(op == 'P')
 	    {
 	      long long q;
@@ -413,7 +420,7 @@ int main(int argc, char **argv)
 	      put(prefix, "Potential", 'd', NumPart, 1, pt);
 	      free(pt); free(ids);
 	    }
-	  if(strchr("GDHS", op)) dump_particles_out(prefix, op);
+	  if(strchr("GDHSdh", op)) dump_particles_out(prefix, (op == 'd') ? 'D' : (op == 'h') ? 'H' : op);
 	  if(op == 'G')
 	    {
 	      interactions = 0;

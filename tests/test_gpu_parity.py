@@ -510,6 +510,80 @@ def test_reference_host_with_dropin_symbols():
     assert float(gpu["5_G_theta_after"][0]) == 0.0     # gravtree.c:396-397 side effect kept by the glue
 
 
+def test_exported_tree_is_a_valid_reference_tree(FP):
+    """gl_export_tree writes the GPU tree into the reference's struct NODE / extNODE / Nextnode / Father storage
+    (allvars.h:1845-1916).  Checked without the reference binary: the threading visits every particle exactly once,
+    fathers enclose their children, the records equal the library's own node table, and ngb_treefind_variable
+    (ngb.c:169-297, restated over the exported arrays) returns exactly the brute-force neighbour sets."""
+    from gadget_leicester_b200 import aos
+    ps = ics.disc(3000, seed=8)
+    par = ics.default_params()
+    ps["hsml"] = ics.guess_hsml(ps, par["DesNumNgb"])
+    ps["hsml"][ps["type"] == 5] = par["Softening"][5]
+    n = ps["pos"].shape[0]
+    fp = FP(par)
+    fp.load(ps)
+    fp.force_treebuild()
+    tab = fp.nodes()
+    T = aos.ReferenceTree(fp, max_part=n + 100, ti_current=7)
+    m = T.Numnodestree
+    assert m == tab.shape[0] and m > n // 4
+    # records
+    assert (T.nfield("n_len", np.float64) == tab[:, 0]).all() and (T.nfield("n_center", np.float64, 3) == tab[:, 1:4]).all()
+    assert (T.nfield("n_mass", np.float64) == tab[:, 4]).all() and (T.nfield("n_s", np.float64, 3) == tab[:, 5:8]).all()
+    assert (T.nfield("n_maxsoft", np.float64) == tab[:, 8]).all() and (T.efield("e_hmax", np.float64) == tab[:, 9]).all()
+    assert (T.nfield("n_bitflags", np.uint32) == 128).all() and (T.nfield("n_Ti_current", np.int32) == 7).all()
+    # threading: "always open" visits every particle once and every cell once, and ends with -1
+    MP = T.MaxPart
+    nxt, sib, fat = T.nfield("n_nextnode", np.int32), T.nfield("n_sibling", np.int32), T.nfield("n_father", np.int32)
+    seen_p, seen_n, no = np.zeros(n, int), np.zeros(m, int), MP
+    while no >= 0:
+        if no < MP:
+            seen_p[no] += 1
+            no = int(T.Nextnode[no])
+        else:
+            seen_n[no - MP] += 1
+            no = int(nxt[no - MP])
+    assert (seen_p == 1).all() and (seen_n == 1).all()
+    assert fat[0] == -1 and (fat[1:] >= MP).all() and (T.Father[:n] >= MP).all()
+    # a particle sits inside its father's cube; skipping a cell (sibling) lands behind all of its particles
+    ctr, ln = T.nfield("n_center", np.float64, 3), T.nfield("n_len", np.float64)
+    f = T.Father[:n] - MP
+    assert (np.abs(ps["pos"] - ctr[f]) <= 0.5 * ln[f][:, None] * (1 + 1e-12)).all()
+    # neighbour search through the exported arrays == brute force with the reference's tests (ngb.c:197-208)
+    rng = np.random.default_rng(2)
+    gas = ps["type"] == 0
+    for i in rng.choice(np.nonzero(gas)[0], 25, replace=False):
+        h = 1.7 * ps["hsml"][i]
+        got = sorted(T.ngb_treefind_variable(ps["pos"], ps["type"], ps["pos"][i], h))
+        d = ps["pos"] - ps["pos"][i]
+        want = np.nonzero(gas & (np.abs(d) <= h).all(1) & ((d * d).sum(1) <= h * h))[0]
+        assert got == sorted(want.tolist())
+    fp.close()
+
+
+REF_DROPIN_TREE = os.path.join(util.ROOT, "oracle", "_ref", "ref_dropin_tree")
+
+
+@pytest.mark.skipif(not (util.have_ref() and os.path.exists(REF_DROPIN_TREE)), reason="compiled reference binaries did not travel")
+def test_reference_cpu_loops_on_exported_gpu_tree():
+    """The reference's OWN CPU density() and hydro_force() (ngb_treefind_variable / _pairs, density_evaluate,
+    hydro_evaluate - unmodified objects) walking the tree that gl_export_tree wrote into Nodes[]/Nextnode[]: same
+    answers as on the tree the reference builds itself.  This is what lets the sub-grid loops behind the force path
+    (sink accretion, dust) run without a host tree build."""
+    ps, par = ics.disc(20000, seed=56), ics.default_params()
+    n, ngas = ps["pos"].shape[0], 20000
+    cpu = util.run_oracle(util.REF_HARNESS, ps, par, "T S D R G D U H")
+    mix = util.run_oracle(REF_DROPIN_TREE, ps, par, "T S D R G d U h")
+    e = util.rel_err_vec(util.by_id(mix, "5_d_", "Hsml", n), util.by_id(cpu, "5_D_", "Hsml", n))
+    assert e.max() <= 1e-9
+    for k in ("Density", "Pressure", "DivVel"):
+        e = util.rel_err_vec(util.by_id(mix, "5_d_", k, ngas), util.by_id(cpu, "5_D_", k, ngas))
+        assert e.max() <= 1e-8, k
+    e = util.rel_err_vec(util.by_id(mix, "7_h_", "HydroAccel", ngas), util.by_id(cpu, "7_H_", "HydroAccel", ngas))
+    assert np.percentile(e, 99) <= 1e-6
+
+
 def test_library_has_no_oracle_dependency():
     """The product must not route through the oracle or any CPU fallback."""
     import gadget_leicester_b200.lib as L
