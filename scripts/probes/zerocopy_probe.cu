@@ -80,7 +80,7 @@ int main(int argc, char **argv)
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float ms;
-  for(int rep = 0; rep < 3; rep++)
+  for(int rep = 0; rep < 2; rep++)
     {
       cudaEventRecord(e0);
       k_pull<<<(n + 127) / 128, 128>>>(n, P, S, d, di);
@@ -94,6 +94,46 @@ int main(int argc, char **argv)
       k_push<<<(n + 127) / 128, 128>>>(n, P, S, d);
       cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
       printf("k_push (thread/particle)   %.2f ms  payload %.0f MB -> %.1f GB/s payload\n", ms, n * 132e-6, n * 132e-6 / ms);
+      // the copy engine's strided (2D) mode: rows of `w` bytes at the struct stride, no SM and no CPU involved
+      for(int w : {24, 40, 68, 128})
+	{
+	  cudaEventRecord(e0);
+	  CK(cudaMemcpy2DAsync(dP, 128, P, 536, w, n, cudaMemcpyHostToDevice));
+	  cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
+	  printf("memcpy2D H2D rows of %3d B      %.2f ms  %.0f MB -> %.1f GB/s\n", w, ms, n * (double) w * 1e-6, n * (double) w * 1e-6 / ms);
+	  cudaEventRecord(e0);
+	  CK(cudaMemcpy2DAsync(P + 64, 536, dP, 128, w, n, cudaMemcpyDeviceToHost));
+	  cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
+	  printf("memcpy2D D2H rows of %3d B      %.2f ms  %.0f MB -> %.1f GB/s\n", w, ms, n * (double) w * 1e-6, n * (double) w * 1e-6 / ms);
+	}
+      {
+	// how many strided copies run at once?  k streams, each scattering 24-byte rows for n/k of the particles
+	cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+	for(int k : {1, 2, 3, 4, 6})
+	  {
+	    cudaStream_t st[6];
+	    for(int q = 0; q < k; q++) cudaStreamCreateWithFlags(&st[q], cudaStreamNonBlocking);
+	    CK(cudaDeviceSynchronize());
+	    cudaEventRecord(e0);
+	    for(int q = 0; q < k; q++) CK(cudaStreamWaitEvent(st[q], e0, 0));
+	    for(int q = 0; q < k; q++)
+	      {
+		long long a = n * q / k, b = n * (q + 1) / k;
+		CK(cudaMemcpy2DAsync(P + 64 + a * 536, 536, dP + a * 128, 128, 24, b - a, cudaMemcpyDeviceToHost, st[q]));
+	      }
+	    for(int q = 0; q < k; q++) { cudaEvent_t d; cudaEventCreate(&d); cudaEventRecord(d, st[q]); cudaStreamWaitEvent(0, d, 0); }
+	    cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
+	    printf("D2H 24-B rows, n split over %d streams: %.2f ms   (asyncEngineCount %d)\n", k, ms, prop.asyncEngineCount);
+	    // same rows count per stream but k different fields for ALL particles (k x the work)
+	    cudaEventRecord(e0);
+	    for(int q = 0; q < k; q++) CK(cudaStreamWaitEvent(st[q], e0, 0));
+	    for(int q = 0; q < k; q++) CK(cudaMemcpy2DAsync(P + 64 + 32 * q, 536, dP + 16 * q, 128, 16, n, cudaMemcpyDeviceToHost, st[q]));
+	    for(int q = 0; q < k; q++) { cudaEvent_t d; cudaEventCreate(&d); cudaEventRecord(d, st[q]); cudaStreamWaitEvent(0, d, 0); }
+	    cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
+	    printf("D2H %d different 16-B fields of all n, one stream each: %.2f ms\n", k, ms);
+	    for(int q = 0; q < k; q++) cudaStreamDestroy(st[q]);
+	  }
+      }
       cudaEventRecord(e0);
       CK(cudaMemcpyAsync(dP, P, n * 536, cudaMemcpyHostToDevice));
       cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
