@@ -44,6 +44,7 @@ extern "C" void gl_destroy(gl_ctx *c)
     if(t.joinable()) t.join();
   cudaStreamSynchronize(c->stream);
   c->in_velpred.release();
+  c->dma_rows.release();
   if(c->ev_blk) cudaEventDestroy(c->ev_blk);
   for(int i = 0; i < 4; i++)
     if(c->ev_res[i]) cudaEventDestroy(c->ev_res[i]);

@@ -92,15 +92,18 @@ static int ensure_input_buffers(gl_ctx *c, long long n, long long ngas)
 // OldAcc, Hsml); TimeBin / Ti_begstep, which sit 460 bytes further on, are fetched by pack B, which also verifies
 // the Type assumption.  The H2D copies of a super-chunk are enqueued on c->stream by the worker that packs its
 // last chunk.
-static std::shared_ptr<HostJob> submit_pack_A(gl_ctx *c, const char *P, long long n, long long ngas, PullStage st,
+// Particles [0, first) are not packed here: the copy engine fetches them (dma_pull_rows).
+static std::shared_ptr<HostJob> submit_pack_A(gl_ctx *c, const char *P, long long first, long long n, long long ngas, PullStage st,
 					      std::atomic<int> *sc_left, std::atomic<int> *cuda_err)
 {
   const gl_gadget_layout L = c->lay;
-  const long long nchunks = (n + PACK_CHUNK - 1) / PACK_CHUNK;
+  const long long nchunks = (n - first + PACK_CHUNK - 1) / PACK_CHUNK;
   const long long nsuper = (nchunks + SUPER_CHUNKS - 1) / SUPER_CHUNKS;
   for(long long s = 0; s < nsuper; s++)
     sc_left[s].store((int) std::min<long long>(SUPER_CHUNKS, nchunks - s * SUPER_CHUNKS));
-  return HostPool::get().submit(n, PACK_CHUNK, [=](long long k, long long a, long long b) {
+  return HostPool::get().submit(n - first, PACK_CHUNK, [=](long long k, long long a, long long b) {
+    a += first;
+    b += first;
     for(long long i = a; i < b; i++)
       {
 	const char *pi = P + i * L.p_stride;
@@ -132,7 +135,7 @@ static std::shared_ptr<HostJob> submit_pack_A(gl_ctx *c, const char *P, long lon
     if(sc_left[s].fetch_sub(1) == 1)
       {
 	// last chunk of this super-chunk: send it
-	const long long a0 = s * SUPER_CHUNKS * (long long) PACK_CHUNK, b0 = std::min(n, a0 + SUPER_CHUNKS * (long long) PACK_CHUNK), m = b0 - a0;
+	const long long a0 = first + s * SUPER_CHUNKS * (long long) PACK_CHUNK, b0 = std::min(n, a0 + SUPER_CHUNKS * (long long) PACK_CHUNK), m = b0 - a0;
 	cudaSetDevice(c->device);
 	cudaError_t e = cudaSuccess;
 	auto up = [&](void *dst, const void *src, size_t bytes) {
@@ -185,7 +188,9 @@ static std::shared_ptr<HostJob> submit_pack_B(gl_ctx *c, const char *P, const ch
 	st.velpred[3 * i] = v[0]; st.velpred[3 * i + 1] = v[1]; st.velpred[3 * i + 2] = v[2];
 	st.entropy[i] = *(const double *) (si + L.s_Entropy);
 	st.dtentropy[i] = *(const double *) (si + L.s_DtEntropy);
-	bad += (*(const short *) (pi + L.p_Type) != 0);
+	const int ty = *(const short *) (pi + L.p_Type);
+	bad += (ty != 0);
+	st.type[i] = ty;
 	st.timebin[i] = *(const short *) (pi + L.p_TimeBin);
 	st.tibeg[i] = *(const int *) (pi + L.p_Ti_begstep);
 	if(with_state)
@@ -216,6 +221,78 @@ static std::shared_ptr<HostJob> submit_pack_B(gl_ctx *c, const char *P, const ch
 	if(e != cudaSuccess) cuda_err->store((int) e);
       }
   });
+}
+
+// ---------------------------------------------------------------- copy-engine (strided DMA) path ----
+// cudaMemcpy2DAsync lets the device side walk the AoS array itself: rows of `width` bytes at the struct stride.  Measured
+// on the B200 box (scripts/probes/zerocopy_probe.cu): ~2 ns per row up to ~70 bytes, 36 GB/s for 128-byte rows, no CPU
+// involved (hand-written zero-copy kernels reach only 5-20 GB/s).  Pack A keeps all cores busy for ~5 ms with the GPU
+// idle, so the two run SIDE BY SIDE: the strided copy fetches the leading 35 % of the gas block, the worker pool packs
+// the rest (-1.2 ms end to end).  Needs page-locked host arrays (cudaHostAlloc / cudaHostRegister); anything else falls
+// back to the pool alone.  The same trick for the RESULT rows (strided D2H into P[] / SphP[]) was measured and dropped:
+// overlapping a running kernel it slowed that kernel by 20-70 %, and in the idle tail of the call it only took the
+// host memory bandwidth the pool's scatter needs (25.9 ms with, 25.9 ms without).
+static bool dma_usable(const void *P, const void *S)
+{
+  if(getenv("GL_NO_DMA")) return false;
+  cudaPointerAttributes a{}, b{};
+  if(cudaPointerGetAttributes(&a, P) != cudaSuccess || cudaPointerGetAttributes(&b, S) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return false;
+    }
+  return a.type == cudaMemoryTypeHost && b.type == cudaMemoryTypeHost;
+}
+
+static double dma_fraction(const char *env, double dflt)
+{
+  if(const char *e = getenv(env)) return std::min(0.9, std::max(0.0, atof(e)));
+  return dflt;
+}
+
+struct PullRow
+{
+  int lo, width, pitch;		// byte range [lo, lo + width) of struct particle_data, device row pitch
+  int pos, vel, mass, hsml, oldacc;	// offsets inside the row
+};
+
+static bool make_pull_row(const gl_gadget_layout &L, PullRow &R)
+{
+  const int lo = std::min(std::min(L.p_Pos, L.p_Vel), std::min(std::min(L.p_Mass, L.p_Hsml), L.p_OldAcc));
+  const int hi = std::max(std::max(L.p_Pos + 24, L.p_Vel + 24), std::max(std::max(L.p_Mass + 8, L.p_Hsml + 8), L.p_OldAcc + 8));
+  R.lo = lo;
+  R.width = hi - lo;
+  R.pitch = (R.width + 15) & ~15;
+  R.pos = L.p_Pos - lo; R.vel = L.p_Vel - lo; R.mass = L.p_Mass - lo; R.hsml = L.p_Hsml - lo; R.oldacc = L.p_OldAcc - lo;
+  return R.width <= 256;	// a layout that scatters these fields further apart is left to the pool
+}
+
+__global__ void k_rows_to_soa(long long nd, const char *__restrict__ rows, PullRow R, double *__restrict__ pos, double *__restrict__ vel,
+			      double *__restrict__ mass, double *__restrict__ hsml, double *__restrict__ oldacc, int *__restrict__ type)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= nd) return;
+  const char *r = rows + i * R.pitch;
+  const double *x = (const double *) (r + R.pos), *v = (const double *) (r + R.vel);
+  pos[3 * i] = x[0]; pos[3 * i + 1] = x[1]; pos[3 * i + 2] = x[2];
+  vel[3 * i] = v[0]; vel[3 * i + 1] = v[1]; vel[3 * i + 2] = v[2];
+  mass[i] = *(const double *) (r + R.mass);
+  hsml[i] = *(const double *) (r + R.hsml);
+  oldacc[i] = *(const double *) (r + R.oldacc);
+  type[i] = 0;			// gas block (pack B verifies it)
+}
+
+// particles [0, nd) of the gas block: one strided H2D copy + an unpack kernel, both on c->stream
+static int dma_pull_rows(gl_ctx *c, const char *P, long long nd)
+{
+  PullRow R;
+  if(nd <= 0 || !make_pull_row(c->lay, R)) return 0;
+  GL_CUDA(c, c->dma_rows.ensure((size_t) nd * R.pitch));
+  GL_CUDA(c, cudaMemcpy2DAsync(c->dma_rows.p, R.pitch, P + R.lo, c->lay.p_stride, R.width, nd, cudaMemcpyHostToDevice, c->stream));
+  k_rows_to_soa<<<gl_grid(nd, 256), 256, 0, c->stream>>>(nd, c->dma_rows.p, R, c->in_pos.p, c->in_vel.p, c->in_mass.p, c->in_hsml.p,
+							 c->in_oldacc.p, c->in_type.p);
+  GL_LAUNCH_COUNT(c);
+  return 0;
 }
 
 static int ensure_copy_streams(gl_ctx *c)
@@ -271,7 +348,7 @@ extern "C" int gl_gadget_pull(gl_ctx *c, const void *Pv, const void *SphPv, long
   std::atomic<int> b_left{0}, cuda_err{0};
   std::atomic<long long> bad_type{0};
   cudaEventRecord(c->ev[8], c->stream);
-  auto ja = submit_pack_A(c, (const char *) Pv, n, ngas, st, sc_left.data(), &cuda_err);
+  auto ja = submit_pack_A(c, (const char *) Pv, 0, n, ngas, st, sc_left.data(), &cuda_err);
   auto jb = submit_pack_B(c, (const char *) Pv, (const char *) SphPv, ngas, st, &b_left, c->copy_stream[0], c->ev[12], &cuda_err, &bad_type,
 			  c->n_tgt_in >= 0);
   ja->wait();
@@ -336,24 +413,27 @@ static int target_list(gl_ctx *c, const int **idx, long long *cnt)
 }
 
 // Results are indexed like the global particle list; the host arrays hold [g_off, g_off + g_numpart) of it.
-static int d2h_gravity(gl_ctx *c, cudaStream_t s, double *A)
+static int d2h_gravity(gl_ctx *c, cudaStream_t s, double *A, long long a = 0)
 {
-  const long long n = c->g_numpart, o = c->g_off;
-  GL_CUDA(c, cudaMemcpyAsync(A, c->o_acc.p + 3 * o, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  GL_CUDA(c, cudaMemcpyAsync(A + 3 * n, c->o_oldacc.p + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  GL_CUDA(c, cudaMemcpyAsync(A + 4 * n, c->o_gravcost.p + o, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  const long long n = c->g_numpart, o = c->g_off, m = n - a;
+  if(m <= 0) return 0;
+  GL_CUDA(c, cudaMemcpyAsync(A + 3 * a, c->o_acc.p + 3 * (o + a), 3 * m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync(A + 3 * n + a, c->o_oldacc.p + o + a, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GL_CUDA(c, cudaMemcpyAsync((float *) (A + 4 * n) + a, c->o_gravcost.p + o + a, m * sizeof(float), cudaMemcpyDeviceToHost, s));
   return 0;
 }
 
-static int d2h_density(gl_ctx *c, cudaStream_t s, double *B)
+static int d2h_density(gl_ctx *c, cudaStream_t s, double *B, long long a = 0)
 {
-  const long long n = c->g_numpart, o = c->g_off;
+  const long long n = c->g_numpart, o = c->g_off, m = n - a;
+  if(m <= 0) return 0;
   const double *src[9] = { c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p,
     c->o_pressure.p, c->o_sinkrho.p, c->o_sinkentr.p };
   const bool have_other = (n > c->g_ngas);	// sink / dust fields only exist for non-gas targets
   for(int k = 0; k < (have_other ? 9 : 7); k++)
-    GL_CUDA(c, cudaMemcpyAsync(B + k * n, src[k] + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if(have_other) GL_CUDA(c, cudaMemcpyAsync(B + 9 * n, c->o_sinkvel.p + 3 * o, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GL_CUDA(c, cudaMemcpyAsync(B + k * n + a, src[k] + o + a, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if(have_other)
+    GL_CUDA(c, cudaMemcpyAsync(B + 9 * n + 3 * a, c->o_sinkvel.p + 3 * (o + a), 3 * m * sizeof(double), cudaMemcpyDeviceToHost, s));
   return 0;
 }
 
@@ -370,14 +450,16 @@ static int d2h_hydro(gl_ctx *c, cudaStream_t s, double *C, long long a, long lon
 
 // reset_swallow: also do density()'s P[i].SwallowID = 0 (density.c:130) here - the field sits right behind
 // GravAccel/OldAcc/Hsml/NumNgb, i.e. in a cache line this loop owns anyway, and nothing reads it in between.
-static void scatter_gravity(gl_ctx *c, char *P, const double *A, const int *idx, long long cnt, bool reset_swallow)
+static void scatter_gravity(gl_ctx *c, char *P, const double *A, const int *idx, long long cnt, bool reset_swallow, long long first = 0)
 {
   const long long n = c->g_numpart;
   const gl_gadget_layout L = c->lay;
   const double *acc = A, *old = A + 3 * n;
   const float *cost = (const float *) (A + 4 * n);
   const int *type = c->g_type;
-  HostPool::get().run(cnt, PACK_CHUNK, [=](long long, long long a, long long b) {
+  HostPool::get().run(cnt - first, PACK_CHUNK, [=](long long, long long a, long long b) {
+    a += first;
+    b += first;
     for(long long k = a; k < b; k++)
       {
 	const long long i = idx ? idx[k] : k;
@@ -404,7 +486,8 @@ static void scatter_gravity(gl_ctx *c, char *P, const double *A, const int *idx,
 // density results: P[].Hsml, .n.NumNgb, .SwallowID = 0 (density.c:130), sink / dust fields; SphP[].d.Density,
 // .h.DhsmlDensityFactor, .v.DivVel, .r.CurlVel, .Pressure (density.c:434-546, :944-988).
 // with_rho_p = false leaves SphP[].d.Density / .Pressure to scatter_hydro, which touches their cache lines anyway.
-static void scatter_density(gl_ctx *c, char *P, char *S, const double *B, const int *idx, long long cnt, bool with_rho_p, bool reset_swallow)
+static void scatter_density(gl_ctx *c, char *P, char *S, const double *B, const int *idx, long long cnt, bool with_rho_p, bool reset_swallow,
+			    long long first = 0)
 {
   const long long n = c->g_numpart, N_gas = c->g_ngas;
   const gl_gadget_layout L = c->lay;
@@ -412,7 +495,9 @@ static void scatter_density(gl_ctx *c, char *P, char *S, const double *B, const 
     *se = sr + n, *sv = se + n;
   const int *type = c->g_type;	// Type column of the pack staging (still valid)
   const bool have_other = (n > N_gas);
-  HostPool::get().run(cnt, PACK_CHUNK, [=](long long, long long a, long long b) {
+  HostPool::get().run(cnt - first, PACK_CHUNK, [=](long long, long long a, long long b) {
+    a += first;
+    b += first;
     for(long long k = a; k < b; k++)
       {
 	const long long i = idx ? idx[k] : k;
@@ -613,7 +698,12 @@ extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv,
   std::vector<std::atomic<int>> sc_left(nsuper);
   std::atomic<int> b_left{0}, cuda_err{0};
   std::atomic<long long> bad_type{0};
-  auto ja = submit_pack_A(c, P, n, ngas, in, sc_left.data(), &cuda_err);
+  // the copy engine fetches the leading part of the gas block while the pool packs the rest
+  const bool dma = dma_usable(P, S) && c->n_tgt_in < 0;
+  PullRow prow;
+  const long long nd_pull = (dma && make_pull_row(c->lay, prow)) ? (long long) (dma_fraction("GL_DMA_PULL", 0.35) * ngas) : 0;
+  if(dma_pull_rows(c, P, nd_pull)) return 1;
+  auto ja = submit_pack_A(c, P, nd_pull, n, ngas, in, sc_left.data(), &cuda_err);
   auto jb = submit_pack_B(c, P, S, ngas, in, &b_left, cs0, c->ev[12], &cuda_err, &bad_type, c->n_tgt_in >= 0);
   ja->wait();
   t_packA = now_ms();

@@ -163,6 +163,8 @@ struct gl_ctx
   void *pin = nullptr, *pin2 = nullptr;
   size_t pin_cap = 0, pin2_cap = 0;
   cudaStream_t copy_stream[2] = { nullptr, nullptr };
+  // strided copy-engine path of the drop-in layer (pinned / registered host arrays only)
+  DBuf<char> dma_rows;		// H2D: the leading bytes of P[] structs, one 128-byte-pitched row per particle
 
   cudaEvent_t ev[16]{};
   // the drop-in call keeps every host core but one busy with pack/scatter work: its long waits must sleep, not spin

@@ -352,9 +352,12 @@ def test_gathered_load_and_ordered_targets_match_plain_api(FP):
     assert util.rel_err_vec(hb["HydroAccel"][sl][gas], ha["HydroAccel"][sl][gas]).max() <= 1e-9
 
 
-def test_dropin_aos_boundary_matches_soa_api(FP):
+@pytest.mark.parametrize("pinned", [False, True])
+def test_dropin_aos_boundary_matches_soa_api(FP, pinned):
     """compute_accelerations on the reference's own P[]/SphP[] byte layout (536 B / 264 B structs, offsets from
-    allvars.h) gives the same numbers as the SoA entry points, and leaves untouched fields untouched."""
+    allvars.h) gives the same numbers as the SoA entry points, and leaves untouched fields untouched.
+    pinned=True: page-locked arrays, where the copy engine reads / writes part of the structs itself (strided DMA)
+    next to the host worker pool; pinned=False: the pool alone."""
     from gadget_leicester_b200 import aos
     ps = ics.disc(20000, seed=31)
     par = ics.default_params()
@@ -374,10 +377,32 @@ def test_dropin_aos_boundary_matches_soa_api(FP):
     a._chk(lib.gl_get_hydro(a.ctx, L._ptr(ha), L._ptr(dt), L._ptr(ms), 0))
     a.close()
     b = FP(par)
-    arr = aos.GadgetArrays(ps, pinned=False)
+    arr = aos.GadgetArrays(ps, pinned=pinned)
     sentinel = arr.pview("p_ID", np.uint32).copy()
+    # every byte the path does not own must survive: fill the structs' other fields with a pattern first
+    lay = aos.layout()
+    Pb = np.frombuffer(arr.P, np.uint8)[: n * lay["p_stride"]].reshape(n, lay["p_stride"])
+    Sb = np.frombuffer(arr.SphP, np.uint8)[: ngas * lay["sph_stride"]].reshape(ngas, lay["sph_stride"])
+    own_P = np.zeros(lay["p_stride"], bool)
+    for f, w in (("p_GravAccel", 24), ("p_OldAcc", 8), ("p_Hsml", 8), ("p_NumNgb", 8), ("p_SwallowID", 4), ("p_GravCost", 4),
+                 ("p_SinkDensity", 8), ("p_SinkEntropy", 8), ("p_SinkGasVel", 24)):
+        own_P[lay[f]: lay[f] + w] = True
+    own_S = np.zeros(lay["sph_stride"], bool)
+    for f, w in (("s_Pressure", 8), ("s_MaxSignalVel", 8), ("s_Density", 8), ("s_DtEntropy", 8), ("s_HydroAccel", 24),
+                 ("s_DhsmlDensityFactor", 8), ("s_DivVel", 8), ("s_CurlVel", 8)):
+        own_S[lay[f]: lay[f] + w] = True
+    inputs_P = np.zeros(lay["p_stride"], bool)
+    for f, w in (("p_Pos", 24), ("p_Vel", 24), ("p_Mass", 8), ("p_ID", 4), ("p_Ti_begstep", 4), ("p_Type", 2), ("p_TimeBin", 2)):
+        inputs_P[lay[f]: lay[f] + w] = True
+    inputs_S = np.zeros(lay["sph_stride"], bool)
+    for f, w in (("s_Entropy", 8), ("s_VelPred", 24)):
+        inputs_S[lay[f]: lay[f] + w] = True
+    Pb[:, ~(own_P | inputs_P)] = 0xA5
+    Sb[:, ~(own_S | inputs_S)] = 0x5A
+    before_P, before_S = Pb.copy(), Sb.copy()
     aos.GadgetDropIn(b, arr).compute_accelerations()
     r = arr.results()
+    assert (Pb[:, ~own_P] == before_P[:, ~own_P]).all() and (Sb[:, ~own_S] == before_S[:, ~own_S]).all()
     assert (arr.pview("p_ID", np.uint32) == sentinel).all()
     assert (arr.pview("p_Pos", np.float64, 3) == ps["pos"]).all()
     assert (r["GravAccel"] == acc).all() and (r["OldAcc"] == old).all() and (r["GravCost"] == cost).all()
