@@ -10,19 +10,26 @@
 // clump).  The Hsml sequence of a target depends on that target alone (the one-sided search only
 // uses h_i), so the whole iteration runs inside ONE kernel launch, round by round, until every
 // lane of the warp has converged - no host round trips, no relaunch, no MPI_Allreduce of
-// "particles left" (density.c:656).  Each round has three phases:
-//   1. collect  - the warp marches through the DFS entry array; a node is entered only if the
-//                 search sphere of at least one still-active lane touches its cube (per-lane
-//                 test + vote, so one far-out lane does not inflate everybody's search); a cell
-//                 with <= 32 particles is swallowed in one coalesced load.  Gas candidates
-//                 (position, mass, h) are STAGED IN SHARED MEMORY, 256 at a time.
-//   2. test     - for every active target the 32 lanes test 32 staged candidates per step with
-//                 the reference's FP64 predicate r2 < h^2 (same operation order, no FMA);
-//                 hits are compacted with ballot/popc into a dense hit list.
-//   3. sum      - full warps of hits evaluate the kernel and its derivative (all lanes busy)
-//                 and the per-lane partial sums are combined with WARP SHUFFLES.
+// "particles left" (density.c:656).  Each round:
+//   1. collect  - the warp keeps a stack of tree cells; every step the lanes pop up to 32 of them
+//                 with independent loads, park the (FP32, slack-padded) cubes in shared memory, and
+//                 every lane tests ITS OWN search sphere against each cube (one far-out lane does
+//                 not inflate everybody's search); a touched cell with <= 32 particles is swallowed
+//                 with one coalesced load, a larger one pushes its children.
+//   2. stage    - the gas candidates of the swallowed cells go to SHARED MEMORY as FP32 offsets from
+//                 the group centre (192 per chunk), with the candidate's own threshold for the
+//                 symmetric search.
+//   3. filter   - lane = target: every lane scans the chunk (broadcast reads, 3 FMAs per test,
+//                 conservative margins) and appends what may be a neighbour of ITS target to a
+//                 private ring in shared memory.
+//   4. heavy    - the reference's FP64 predicate (r2 < h^2, same operation order, no FMA) and the
+//                 kernel sums are taken from the rings whenever one of them is nearly full; every
+//                 lane adds into its own accumulators.  With few targets left in a warp a
+//                 target-major variant (ballot compaction, WARP-SHUFFLE sums) takes over.
 // The neighbour SETS (hence the integer pair counts) are exactly the reference's; the FP64 sums are
-// formed in a different order (32 partial sums + butterfly), i.e. they agree to ~1e-15 relative.
+// formed in tree order per lane (or as 32 partial sums + butterfly in the target-major variant),
+// i.e. they agree with the reference to ~1e-15 relative.  Targets with thousands of neighbours (a
+// sink in the disc hole) go to a thread-block-cluster path (k_fat_scan / k_fat_rounds).
 #include "gl_internal.h"
 #include <climits>
 #include <cooperative_groups.h>
