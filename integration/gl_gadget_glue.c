@@ -193,6 +193,25 @@ void gravity_tree(void)
   TreeReconstructFlag = 0;
   All.TotNumOfForces += nactive;	/* gravtree.c:788 (GlobNumForceUpdate) */
   CPU_Step[CPU_TREEWALK1] += timediff(t0, second());
+  if(ThisTask == 0 && FdTimings)
+    {
+      /* the block gravity_tree() appends to timings.txt (gravtree.c:803-825): same lines, the walk time is the GPU
+         kernel's, nothing is exported (ex-frac 0), one iteration, balance 1 (one rank = one GPU) */
+      gl_stats st;
+      double tw;
+      long long nf = nactive, tot = All.TotNumOfForces;
+      gl_get_stats(GL, &st);
+      tw = st.ms_gravity_walk * 1e-3 + 1.0e-20;
+      fprintf(FdTimings, "Step= %d  t= %g  dt= %g \n", All.NumCurrentTiStep, All.Time, All.TimeStep);
+      fprintf(FdTimings, "Nf= %d%09d  total-Nf= %d%09d  ex-frac= %g (%g) iter= %d\n", (int) (nf / 1000000000), (int) (nf % 1000000000),
+	      (int) (tot / 1000000000), (int) (tot % 1000000000), 0.0, 0.0, 1);
+      fprintf(FdTimings, "work-load balance: %g (%g %g) rel1to2=%g   max=%g avg=%g\n", 1.0, 1.0, 1.0, 1.0, tw, tw);
+      fprintf(FdTimings, "particle-load balance: %g\n", (NumPart / ((double) All.TotNumPart)) * NTask);
+      fprintf(FdTimings, "max. nodes: %d, filled: %g\n", (int) st.numnodes, st.numnodes / (All.TreeAllocFactor * All.MaxPart + NTopnodes));
+      fprintf(FdTimings, "part/sec=%g | %g  ia/part=%g (%g)\n", nf / tw, nf / tw, ((double) st.interactions) / (nf > 0 ? nf : 1), 0.0);
+      fprintf(FdTimings, "\n");
+      fflush(FdTimings);
+    }
 }
 
 void density(void)
