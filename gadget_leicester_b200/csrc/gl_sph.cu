@@ -1182,7 +1182,10 @@ struct HydroTarget
   int timestep;
 };
 
-__global__ void __launch_bounds__(SPH_BLOCK, 4)
+#ifndef HYDRO_MIN_BLOCKS
+#define HYDRO_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(SPH_BLOCK, HYDRO_MIN_BLOCKS)
 k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const int2 *__restrict__ e_rng,
 	const int *__restrict__ n_child, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
