@@ -136,8 +136,8 @@ __device__ __forceinline__ float cand_threshold(float h, float L)
 // The three loads are issued together (one memory latency per range, not three).  With WANT_H the candidate's own
 // FP32 threshold for "r2 < h_j^2" is formed here, once per candidate, with L = max(|its offset|, amax) - the bound
 // of cand_threshold only needs L >= the components of THIS pair.
-template <bool WANT_H>
-__device__ __forceinline__ int stage_range(WarpStage &S, int ncand, int a, int b, int lane, const GroupF &G, float &lmax,
+template <bool WANT_H, class Stage>
+__device__ __forceinline__ int stage_range(Stage &S, int ncand, int a, int b, int lane, const GroupF &G, float &lmax,
 					    const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
 					    const int *__restrict__ s_type)
 {
@@ -186,8 +186,8 @@ __device__ __forceinline__ void hits_shift(WarpStage &S, int nh, int lane)
 // (ngb.c:270-289 / :136-152, here in FP32 with a conservative margin - this test only prunes).  A touched cell
 // is swallowed (<= 32 particles: its tree range is staged with one coalesced load) or its children are pushed
 // (child table written by k_moments).  flush(ncand, lmax) runs phases 2+3.
-template <bool USE_HMAX, class Flush>
-__device__ __forceinline__ void sph_collect(WarpStage &S, int lane, int nentries, const int *__restrict__ e_next,
+template <bool USE_HMAX, class Stage, class Flush>
+__device__ __forceinline__ void sph_collect(Stage &S, int lane, int nentries, const int *__restrict__ e_next,
 					    const double4 *__restrict__ e_B, const double *__restrict__ e_hmax,
 					    const int2 *__restrict__ e_rng, const int *__restrict__ n_child,
 					    const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
@@ -1182,9 +1182,121 @@ struct HydroTarget
   int timestep;
 };
 
+// hydra.c:958-979 target load (per-target quantities formed once: sound speed, Balsara factor, P/rho^2 * Omega)
+__device__ __forceinline__ HydroTarget hydro_load_target(bool live, int p, int pin, const double4 *__restrict__ s_pm,
+							 const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
+							 const double4 *__restrict__ h_r, const double *__restrict__ pressure,
+							 const double *__restrict__ dhsml, const double *__restrict__ divvel,
+							 const double *__restrict__ curlvel)
+{
+  HydroTarget T;
+  T.px = T.py = T.pz = T.vx = T.vy = T.vz = T.h_i = T.mass = T.f1 = T.cs_i = T.p_over_rho2_i = 0;
+  T.rho = 1;
+  T.timestep = 0;
+  if(live)
+    {
+      const double4 pm = s_pm[p], vh = s_vh[p];
+      T.px = pm.x; T.py = pm.y; T.pz = pm.z; T.mass = pm.w;
+      T.vx = vh.x; T.vy = vh.y; T.vz = vh.z; T.h_i = vh.w;
+      T.rho = h_q[p].x;
+      const double P = pressure[pin];
+      T.timestep = (int) h_r[p].y;
+      T.cs_i = sqrt(GL_GAMMA * P / T.rho);
+      const double adv = fabs(divvel[pin]);
+      T.f1 = adv / (adv + curlvel[pin] + 0.0001 * T.cs_i / T.h_i / 1.0);
+      T.p_over_rho2_i = P / (T.rho * T.rho);	// hydra.c:1154-1155
+      T.p_over_rho2_i *= dhsml[pin];
+    }
+  return T;
+}
+
+struct HydroConst
+{
+  double h_i2, hinv_i, hinv4_i, artvisc, timebase_interval;
+};
+
+// hydra.c:1236-1621 for one candidate j of target T: the reference's FP64 predicate, then the pair force
+__device__ __forceinline__ void hydro_pair(const HydroTarget &T, const HydroConst &K, HydroAcc &A, int j, const double4 *__restrict__ s_pm,
+					   const double4 *__restrict__ s_vh, const double4 *__restrict__ h_q,
+					   const double4 *__restrict__ h_r)
+{
+  const double4 pj = gl_ld4(&s_pm[j]);
+  const double4 vj = gl_ld4(&s_vh[j]);
+  const double dx = T.px - pj.x, dy = T.py - pj.y, dz = T.pz - pj.z;
+  const double r2 = dx * dx + dy * dy + dz * dz;
+  const double h_j = vj.w, mass_j = pj.w, h_j2 = h_j * h_j;
+  if((r2 < K.h_i2 || r2 < h_j2) && r2 > 0)	// hydra.c:1266, :1270
+    {
+      const double4 q = gl_ld4(&h_q[j]);
+      const double4 rr = gl_ld4(&h_r[j]);
+      A.npairs++;
+      // r and 1/r from one reciprocal square root; the reference divides by r three times
+      // (hydra.c:1511, 1602, 1606), here these are multiplications by rinv (1 ulp apart)
+      const double rinv = rsqrt(r2);
+      const double r = r2 * rinv;
+      const double rho_j = q.x, soundspeed_j = q.w;
+      const double dvx = T.vx - vj.x, dvy = T.vy - vj.y, dvz = T.vz - vj.z;
+      const double vdotr2 = dx * dvx + dy * dvy + dz * dvz;	// non-comoving, hydra.c:1279-1282
+      double dwk_i = 0, dwk_j = 0;
+      if(r2 < K.h_i2)
+	{
+	  const double u = r * K.hinv_i;
+	  dwk_i = (u < 0.5) ? K.hinv4_i * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : K.hinv4_i * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+	}
+      if(r2 < h_j2)
+	{
+	  // 1/h_j and 1/h_j^4 come with the source record (k_hydro_prep forms them as hydra.c:1311-1312 does)
+	  const double u = r * rr.z;
+	  dwk_j = (u < 0.5) ? rr.w * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : rr.w * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
+	}
+      double vsig = T.cs_i + soundspeed_j;	// hydra.c:1502
+      if(vsig > A.maxsig) A.maxsig = vsig;
+      double visc = 0;
+      if(vdotr2 < 0)
+	{
+	  const double mu_ij = vdotr2 * rinv;	// fac_mu = 1
+	  vsig -= 3 * mu_ij;
+	  if(vsig > A.maxsig) A.maxsig = vsig;
+	  const double rho_ij = 0.5 * (T.rho + rho_j);
+	  visc = 0.25 * K.artvisc * vsig * (-mu_ij) / rho_ij * (T.f1 + rr.x);
+	  // hydra.c:1583-1597 viscosity limiter
+	  const int ts_j = (int) rr.y;
+	  const double dt = 2 * ((T.timestep > ts_j) ? T.timestep : ts_j) * K.timebase_interval;
+	  if(dt > 0 && (dwk_i + dwk_j) < 0)
+	    {
+	      const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (T.mass + mass_j) * (dwk_i + dwk_j) * r * dt);
+	      visc = (visc < lim) ? visc : lim;
+	    }
+	}
+      const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) * rinv;
+      const double hfc = hfc_visc + mass_j * (T.p_over_rho2_i * dwk_i + q.z * dwk_j) * rinv;	// q.z = P_j/rho_j^2 x Omega_j
+      A.a0 += (-hfc * dx);
+      A.a1 += (-hfc * dy);
+      A.a2 += (-hfc * dz);
+      A.dtE += (0.5 * hfc_visc * vdotr2);
+    }
+}
+
+__device__ __forceinline__ void hydro_store(const HydroTarget &T, const HydroAcc &A, int pin, double *__restrict__ o_hacc,
+					    double *__restrict__ o_dtentr, double *__restrict__ o_maxsig, int *__restrict__ o_pairs)
+{
+  o_hacc[3ll * pin] = A.a0;
+  o_hacc[3ll * pin + 1] = A.a1;
+  o_hacc[3ll * pin + 2] = A.a2;
+  // hydra.c:583: DtEntropy *= GAMMA_MINUS1 / (hubble_a2 * rho^GAMMA_MINUS1)
+  o_dtentr[pin] = A.dtE * (GL_GAMMA_MINUS1 / (1.0 * pow(T.rho, GL_GAMMA_MINUS1)));
+  o_maxsig[pin] = A.maxsig;
+  o_pairs[pin] = A.npairs;
+}
+
 #ifndef HYDRO_MIN_BLOCKS
 #define HYDRO_MIN_BLOCKS 4
 #endif
+// Search and pair arithmetic live in ONE kernel on purpose.  A split variant was built and measured (search kernel at 61
+// registers / 32 warps per SM writing per-target candidate lists, pair kernel reading them: bit-identical results): the
+// search alone took 1.8 ms, but the pair kernel alone 3.8 ms against ~1 ms worth of the same work inside this kernel -
+// the pair step is bound by the L1 gather rate (32 distinct lines per load instruction), and only pays off while other
+// warps of the SM are in the ALU-bound search phase.  5.7 ms split vs 3.8 ms fused.
 __global__ void __launch_bounds__(SPH_BLOCK, HYDRO_MIN_BLOCKS)
 k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	const double4 *__restrict__ e_B, const double *__restrict__ e_hmax, const int2 *__restrict__ e_rng,
@@ -1201,28 +1313,8 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
   const long long warp = (blockIdx.x * (long long) blockDim.x + threadIdx.x) >> 5;
   const long long t = warp * 32 + lane;
   const bool live = t < nt;
-  int p = 0, pin = 0;
-  HydroTarget T;
-  T.px = T.py = T.pz = T.vx = T.vy = T.vz = T.h_i = T.mass = T.f1 = T.cs_i = T.p_over_rho2_i = 0;
-  T.rho = 1;
-  T.timestep = 0;
-  if(live)
-    {
-      // hydra.c:958-979 target load
-      p = tgt[t];
-      pin = perm[p];
-      const double4 pm = s_pm[p], vh = s_vh[p];
-      T.px = pm.x; T.py = pm.y; T.pz = pm.z; T.mass = pm.w;
-      T.vx = vh.x; T.vy = vh.y; T.vz = vh.z; T.h_i = vh.w;
-      T.rho = h_q[p].x;
-      const double P = pressure[pin];
-      T.timestep = (int) h_r[p].y;
-      T.cs_i = sqrt(GL_GAMMA * P / T.rho);
-      const double adv = fabs(divvel[pin]);
-      T.f1 = adv / (adv + curlvel[pin] + 0.0001 * T.cs_i / T.h_i / 1.0);
-      T.p_over_rho2_i = P / (T.rho * T.rho);	// hydra.c:1154-1155
-      T.p_over_rho2_i *= dhsml[pin];
-    }
+  const int p = live ? tgt[t] : 0, pin = live ? perm[p] : 0;
+  const HydroTarget T = hydro_load_target(live, p, pin, s_pm, s_vh, h_q, h_r, pressure, dhsml, divvel, curlvel);
   const unsigned live_mask = __ballot_sync(FULL, live);
   HydroAcc A;
   A.zero();
@@ -1233,66 +1325,9 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
 #endif
   PH_T(tk0);
   const GroupF G = make_group(live, T.px, T.py, T.pz, T.h_i);
-  const double h_i = T.h_i, h_i2 = h_i * h_i, hinv_i = 1.0 / h_i, hinv4_i = hinv_i * hinv_i * hinv_i * hinv_i;
-  const double artvisc = par.artvisc, timebase_interval = par.timebase_interval;
-  // lane = target "heavy" step (hydra.c:1236-1621 for one queued candidate j of MY target)
-  auto heavy = [&](int j) {
-    const double4 pj = gl_ld4(&s_pm[j]);
-    const double4 vj = gl_ld4(&s_vh[j]);
-    const double dx = T.px - pj.x, dy = T.py - pj.y, dz = T.pz - pj.z;
-    const double r2 = dx * dx + dy * dy + dz * dz;
-    const double h_j = vj.w, mass_j = pj.w, h_j2 = h_j * h_j;
-    if((r2 < h_i2 || r2 < h_j2) && r2 > 0)	// hydra.c:1266, :1270 - the reference's FP64 predicate
-      {
-	const double4 q = gl_ld4(&h_q[j]);
-	const double4 rr = gl_ld4(&h_r[j]);
-	A.npairs++;
-	// r and 1/r from one reciprocal square root; the reference divides by r three times
-	// (hydra.c:1511, 1602, 1606), here these are multiplications by rinv (1 ulp apart)
-	const double rinv = rsqrt(r2);
-	const double r = r2 * rinv;
-	const double rho_j = q.x, soundspeed_j = q.w;
-	const double dvx = T.vx - vj.x, dvy = T.vy - vj.y, dvz = T.vz - vj.z;
-	const double vdotr2 = dx * dvx + dy * dvy + dz * dvz;	// non-comoving, hydra.c:1279-1282
-	double dwk_i = 0, dwk_j = 0;
-	if(r2 < h_i2)
-	  {
-	    const double u = r * hinv_i;
-	    dwk_i = (u < 0.5) ? hinv4_i * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : hinv4_i * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-	  }
-	if(r2 < h_j2)
-	  {
-	    // 1/h_j and 1/h_j^4 come with the source record (k_hydro_prep forms them as hydra.c:1311-1312 does)
-	    const double u = r * rr.z;
-	    dwk_j = (u < 0.5) ? rr.w * u * (KERNEL_COEFF_3 * u - KERNEL_COEFF_4) : rr.w * KERNEL_COEFF_6 * (1.0 - u) * (1.0 - u);
-	  }
-	double vsig = T.cs_i + soundspeed_j;	// hydra.c:1502
-	if(vsig > A.maxsig) A.maxsig = vsig;
-	double visc = 0;
-	if(vdotr2 < 0)
-	  {
-	    const double mu_ij = vdotr2 * rinv;	// fac_mu = 1
-	    vsig -= 3 * mu_ij;
-	    if(vsig > A.maxsig) A.maxsig = vsig;
-	    const double rho_ij = 0.5 * (T.rho + rho_j);
-	    visc = 0.25 * artvisc * vsig * (-mu_ij) / rho_ij * (T.f1 + rr.x);
-	    // hydra.c:1583-1597 viscosity limiter
-	    const int ts_j = (int) rr.y;
-	    const double dt = 2 * ((T.timestep > ts_j) ? T.timestep : ts_j) * timebase_interval;
-	    if(dt > 0 && (dwk_i + dwk_j) < 0)
-	      {
-		const double lim = 0.5 * 1.0 * vdotr2 / (0.5 * (T.mass + mass_j) * (dwk_i + dwk_j) * r * dt);
-		visc = (visc < lim) ? visc : lim;
-	      }
-	  }
-	const double hfc_visc = 0.5 * mass_j * visc * (dwk_i + dwk_j) * rinv;
-	const double hfc = hfc_visc + mass_j * (T.p_over_rho2_i * dwk_i + q.z * dwk_j) * rinv;	// q.z = P_j/rho_j^2 x Omega_j
-	A.a0 += (-hfc * dx);
-	A.a1 += (-hfc * dy);
-	A.a2 += (-hfc * dz);
-	A.dtE += (0.5 * hfc_visc * vdotr2);
-      }
-  };
+  const double hinv_i = 1.0 / T.h_i;
+  const HydroConst K = { T.h_i * T.h_i, hinv_i, hinv_i * hinv_i * hinv_i * hinv_i, par.artvisc, par.timebase_interval };
+  auto heavy = [&](int j) { hydro_pair(T, K, A, j, s_pm, s_vh, h_q, h_r); };
   int qh = 0, qt = 0;
   // hydro has no iteration: every warp but the last one is full, so lane = target always
   sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, G, visits, staged,
@@ -1303,16 +1338,7 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
   __syncwarp();
   if(lane < 6) atomicAdd(&g_phase[lane], S.ph[lane]);
 #endif
-  if(live)
-    {
-      o_hacc[3ll * pin] = A.a0;
-      o_hacc[3ll * pin + 1] = A.a1;
-      o_hacc[3ll * pin + 2] = A.a2;
-      // hydra.c:583: DtEntropy *= GAMMA_MINUS1 / (hubble_a2 * rho^GAMMA_MINUS1)
-      o_dtentr[pin] = A.dtE * (GL_GAMMA_MINUS1 / (1.0 * pow(T.rho, GL_GAMMA_MINUS1)));
-      o_maxsig[pin] = A.maxsig;
-      o_pairs[pin] = A.npairs;
-    }
+  if(live) hydro_store(T, A, pin, o_hacc, o_dtentr, o_maxsig, o_pairs);
   const unsigned wpairs = __reduce_add_sync(FULL, live ? (unsigned) A.npairs : 0u);
   if(lane == 0 && wpairs) atomicAdd(&counter[10], (unsigned long long) wpairs);
 }
