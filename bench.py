@@ -338,8 +338,9 @@ def main():
     if world > 1 and args.rebalance:
         # domain.c:1075 balances the measured GRAVITY work; two thirds of this step is SPH work, which equal counts
         # balance better on the disc (measured at N=2: 18.3 ms equal counts, 18.7 ms GravCost-balanced) - so off by default
-        dfp.rebalance()
-        dfp.compute_accelerations()
+        for _ in range(2):
+            dfp.rebalance(timed=True)
+            dfp.compute_accelerations()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -387,6 +388,16 @@ def main():
     inter_per_step = float(it.item()) / args.steps
     value = inter_per_step / (ms_per_step * 1e-3)
     phase = {k: v / args.steps for k, v in acc.items()}
+    rank_phase = None
+    if dist is not None:
+        keys = ("ms_keys_sort", "ms_moments", "ms_gravity_walk", "ms_density", "ms_hydro")
+        mine = torch.tensor([phase[k] for k in keys] + [wall.get("allgather_state", 0.0), wall.get("allgather_sph", 0.0),
+                                                        float(dfp.hi - dfp.lo)], dtype=torch.float64, device="cuda")
+        allr = torch.empty(world * mine.numel(), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, -1).cpu().numpy()
+        rank_phase = {k: [round(float(x), 2) for x in allr[:, j]]
+                      for j, k in enumerate(keys + ("wall_allgather_state", "wall_allgather_sph", "targets"))}
 
     # ---- roofline of the dominant kernel (per-launch durations from the library's CUDA events) ----
     pk = peaks()
@@ -509,7 +520,7 @@ def main():
                 interactions_per_step=inter_per_step, sph_updates_per_s=(ngas / (ms_per_step * 1e-3)),
                 force_eval_ms=ms_per_step, phase_ms=phase, density_passes=dict(cold_start=cold_passes, steady=passes),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof,
-                wall_phase_ms={k: round(v, 3) for k, v in wall.items()})
+                wall_phase_ms={k: round(v, 3) for k, v in wall.items()}, rank_phase_ms=rank_phase)
     if e2e is not None:
         line["e2e"] = e2e
     if cpu_base is not None:

@@ -977,3 +977,63 @@ extern "C" int gl_gadget_push_wait(gl_ctx *c)
     }
   return 0;
 }
+
+// ---------------------------------------------------------------- lazy drift of the sources (host) ----
+extern "C" int gl_gadget_drift(const gl_gadget_layout *lay, void *Pv, void *SphPv, long long NumPart, long long N_gas, int time1,
+			       double Timebase_interval, double MinGasHsml, long long *ndrifted)
+{
+  const gl_gadget_layout L = *lay;
+  char *P = (char *) Pv, *S = (char *) SphPv;
+  std::atomic<long long> moved{0}, ahead{0};
+  HostPool::get().run(NumPart, PACK_CHUNK, [&, L, P, S](long long, long long a, long long b) {
+    long long m = 0, bad = 0;
+    for(long long i = a; i < b; i++)
+      {
+	char *pi = P + i * L.p_stride;
+	const int type = *(const short *) (pi + L.p_Type);
+	if(type == 3) continue;	// predict.c:134 (-DVIRTUAL)
+	int *tic = (int *) (pi + L.p_Ti_current);
+	const int time0 = *tic;
+	if(time1 < time0)
+	  {
+	    bad++;		// predict.c:148-152 endrun(12)
+	    continue;
+	  }
+	if(time1 == time0) continue;
+	// predict.c:165: dt_drift = dt_gravkick = dt_hydrokick = (time1 - time0) * All.Timebase_interval
+	const double dt = (time1 - time0) * Timebase_interval;
+	double *pos = (double *) (pi + L.p_Pos);
+	const double *vel = (const double *) (pi + L.p_Vel);
+	for(int j = 0; j < 3; j++) pos[j] += vel[j] * dt;	// predict.c:169-170
+	if(type == 0 && i < N_gas)
+	  {
+	    char *si = S + i * L.sph_stride;
+	    double *vp = (double *) (si + L.s_VelPred);
+	    const double *ga = (const double *) (pi + L.p_GravAccel), *ha = (const double *) (si + L.s_HydroAccel);
+	    for(int j = 0; j < 3; j++) vp[j] += ga[j] * dt + ha[j] * dt;	// predict.c:185-186
+	    if(L.s_DragAccel >= 0)
+	      {
+		const double *da = (const double *) (si + L.s_DragAccel);
+		for(int j = 0; j < 3; j++) vp[j] += da[j] * dt;	// predict.c:194-196 (-DDUST)
+	      }
+	    const double divv = *(const double *) (si + L.s_DivVel);
+	    double *rho = (double *) (si + L.s_Density), *h = (double *) (pi + L.p_Hsml);
+	    *rho *= exp(-divv * dt);	// predict.c:204
+	    *h *= exp(0.333333333333 * divv * dt);	// predict.c:205
+	    if(*h < MinGasHsml) *h = MinGasHsml;
+	    const int tb = *(const short *) (pi + L.p_TimeBin);
+	    const int dt_step = tb ? (1 << tb) : 0;
+	    const double dt_entr = (time1 - (*(const int *) (pi + L.p_Ti_begstep) + dt_step / 2)) * Timebase_interval;	// predict.c:213
+	    // predict.c:217 (neither MHM nor SOFTEREQS in the shipped build)
+	    *(double *) (si + L.s_Pressure) =
+	      (*(const double *) (si + L.s_Entropy) + *(const double *) (si + L.s_DtEntropy) * dt_entr) * pow(*rho, 7.0 / 5);
+	  }
+	*tic = time1;
+	m++;
+      }
+    if(m) moved.fetch_add(m);
+    if(bad) ahead.fetch_add(bad);
+  });
+  if(ndrifted) *ndrifted = moved.load();
+  return ahead.load() ? 1 : 0;
+}

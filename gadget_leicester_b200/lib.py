@@ -50,7 +50,7 @@ class GLGadgetLayout(C.Structure):
         "p_Pos", "p_Vel", "p_Mass", "p_GravAccel", "p_OldAcc", "p_Hsml", "p_NumNgb", "p_GravCost", "p_Ti_begstep",
         "p_Type", "p_TimeBin", "p_SinkDensity", "p_SinkEntropy", "p_SinkGasVel", "p_DustDensity", "p_DustEntropy",
         "p_DustGasVel", "p_SwallowID", "s_Entropy", "s_Pressure", "s_VelPred", "s_MaxSignalVel", "s_Density",
-        "s_DtEntropy", "s_HydroAccel", "s_DhsmlDensityFactor", "s_DivVel", "s_CurlVel")]
+        "s_DtEntropy", "s_HydroAccel", "s_DhsmlDensityFactor", "s_DivVel", "s_CurlVel", "p_Ti_current", "s_DragAccel")]
 
 
 class GLTreeLayout(C.Structure):
@@ -68,7 +68,7 @@ EXPORTS = [
     "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations", "gl_compute_potential", "gl_get_potential",
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
-    "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree",
+    "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree", "gl_gadget_drift",
 ]
 
 _lib = None
@@ -133,6 +133,8 @@ def load_library():
     lib.gl_gadget_pack_segment.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, vp, vp]
     lib.gl_gadget_push_segment_async.argtypes = [vp, vp, vp, C.c_int]
     lib.gl_gadget_push_wait.argtypes = [vp]
+    lib.gl_gadget_drift.argtypes = [C.POINTER(GLGadgetLayout), vp, vp, C.c_longlong, C.c_longlong, C.c_int, C.c_double, C.c_double,
+                                    C.POINTER(C.c_longlong)]
     lib.gl_export_tree.argtypes = [vp, C.POINTER(GLTreeLayout), vp, vp, vp, vp, C.c_longlong, C.c_longlong, C.c_int,
                                    C.POINTER(C.c_longlong)]
     _lib = lib

@@ -179,6 +179,8 @@ typedef struct gl_gadget_layout
   int p_SwallowID;
   int s_Entropy, s_Pressure, s_VelPred, s_MaxSignalVel, s_Density, s_DtEntropy, s_HydroAccel,
     s_DhsmlDensityFactor, s_DivVel, s_CurlVel;
+  int p_Ti_current;		/* only gl_gadget_drift reads these two */
+  int s_DragAccel;		/* SphP.da.DragAccel (-DDUST), < 0: the build has none */
 } gl_gadget_layout;
 int gl_gadget_bind(gl_ctx * ctx, const gl_gadget_layout * lay);
 /* pack P[0..NumPart) / SphP[0..N_gas) into the device SoA (host threads + pinned staging) */
@@ -186,6 +188,14 @@ int gl_gadget_pull(gl_ctx * ctx, const void *P, const void *SphP, long long NumP
 /* compute_accelerations(mode) of accel.c:27 on the reference's own arrays in one call: pull, the force path,
  * and a software-pipelined push (results of one phase cross PCIe and are scattered while the next phase runs) */
 int gl_gadget_compute_accelerations(gl_ctx * ctx, void *P, void *SphP, long long NumPart, long long N_gas, int mode);
+/* The lazy drift of the sources (predict.c:129 drift_particle, called per particle from inside the reference's walks:
+ * forcetree.c:1911, ngb.c:57,194): every particle with Ti_current != time1 is moved to time1 IN PLACE, with the
+ * reference's statements in the reference's order (Pos; for gas VelPred from GravAccel / HydroAccel / DragAccel,
+ * Density and Hsml from DivVel, Pressure from Entropy + DtEntropy * dt_entr; Type 3 is skipped, -DVIRTUAL), on all host
+ * cores.  Host code only - no context, no GPU; non-comoving integration.  Returns non-zero if a particle is ahead of
+ * time1 (endrun(12) in the reference).  *ndrifted <- number of particles moved. */
+int gl_gadget_drift(const gl_gadget_layout * lay, void *P, void *SphP, long long NumPart, long long N_gas, int time1,
+		    double Timebase_interval, double MinGasHsml, long long *ndrifted);
 /* scatter results back in place; what = bit mask: 1 gravity, 2 density, 4 hydro */
 int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
 

@@ -26,6 +26,7 @@
 #include "gl_b200.h"
 
 static gl_ctx *GL;
+static gl_gadget_layout GL_Layout;
 
 static void gl_fail(const char *where)
 {
@@ -92,6 +93,13 @@ static void gl_attach(void)
   L.s_DhsmlDensityFactor = offsetof(struct sph_particle_data, h.DhsmlDensityFactor);
   L.s_DivVel = offsetof(struct sph_particle_data, v.DivVel);
   L.s_CurlVel = offsetof(struct sph_particle_data, r.CurlVel);
+  L.p_Ti_current = offsetof(struct particle_data, Ti_current);
+#ifdef DUST
+  L.s_DragAccel = offsetof(struct sph_particle_data, da.DragAccel);
+#else
+  L.s_DragAccel = -1;
+#endif
+  GL_Layout = L;
   if(gl_gadget_bind(GL, &L)) gl_fail("gl_gadget_bind");
 }
 
@@ -120,8 +128,17 @@ static void gl_pull(void)
   gl_attach();
   gl_sync_params();
   /* sources must be current: the reference drifts lazily inside its walks (forcetree.c:1911, ngb.c:57) */
+#ifdef GL_REFERENCE_DRIFT
   for(i = 0; i < NumPart; i++)
     if(P[i].Ti_current != All.Ti_Current) drift_particle(i, All.Ti_Current);
+#else
+  /* the same statements (predict.c:129), on all host cores */
+  if(All.ComovingIntegrationOn)
+    gl_fail("comoving drift");
+  if(gl_gadget_drift(&GL_Layout, P, SphP, NumPart, N_gas, All.Ti_Current, All.Timebase_interval, All.MinGasHsml, NULL))
+    endrun(12);
+  (void) i;
+#endif
   if(gl_gadget_pull(GL, P, SphP, NumPart, N_gas)) gl_fail("gl_gadget_pull");
   gl_set_tree_reconstruct_flag(GL, 1);
 }

@@ -17,7 +17,8 @@ int main(void)
   PO("p_Type", Type); PO("p_TimeBin", TimeBin);
   PO("p_SinkDensity", b1.BH_Density); PO("p_SinkEntropy", b2.BH_Entropy); PO("p_SinkGasVel", b3.BH_SurroundingGasVel);
   PO("p_DustDensity", d1.DUST_Density); PO("p_DustEntropy", d2.DUST_Entropy); PO("p_DustGasVel", d3.DUST_SurroundingGasVel);
-  PO("p_SwallowID", SwallowID); PO("p_ID", ID);
+  PO("p_SwallowID", SwallowID); PO("p_ID", ID); PO("p_Ti_current", Ti_current);
+  SO("s_DragAccel", da.DragAccel);
   SO("s_Entropy", Entropy); SO("s_Pressure", Pressure); SO("s_VelPred", VelPred); SO("s_MaxSignalVel", MaxSignalVel);
   SO("s_Density", d.Density); SO("s_DtEntropy", e.DtEntropy); SO("s_HydroAccel", a.HydroAccel);
   SO("s_DhsmlDensityFactor", h.DhsmlDensityFactor); SO("s_DivVel", v.DivVel); SO("s_CurlVel", r.CurlVel);

@@ -141,6 +141,30 @@ static void dump_particles_out(const char *prefix, int what)
   free(d3); free(d1); free(i1);
 }
 
+/* everything drift_particle (predict.c:129) reads or writes, in P[] order */
+static void dump_drift_state(const char *prefix, const char *tag)
+{
+  long long n = NumPart, ng = N_gas, i;
+  double *d3 = malloc(sizeof(double) * 3 * n), *d1 = malloc(sizeof(double) * n);
+  int *i1 = malloc(sizeof(int) * n);
+  char nm[40];
+#define PUT3(field, expr, cnt) do { for(i = 0; i < (cnt); i++) { d3[3 * i] = expr[0]; d3[3 * i + 1] = expr[1]; d3[3 * i + 2] = expr[2]; } \
+    snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'd', (cnt), 3, d3); } while(0)
+#define PUT1(field, expr, cnt) do { for(i = 0; i < (cnt); i++) d1[i] = expr; snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'd', (cnt), 1, d1); } while(0)
+#define PUTI(field, expr, cnt) do { for(i = 0; i < (cnt); i++) i1[i] = expr; snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'i', (cnt), 1, i1); } while(0)
+  PUTI("id", (int) P[i].ID, n); PUTI("Type", P[i].Type, n); PUTI("TimeBin", P[i].TimeBin, n); PUTI("Ti_begstep", P[i].Ti_begstep, n);
+  PUTI("Ti_current", P[i].Ti_current, n);
+  PUT3("Pos", P[i].Pos, n); PUT3("Vel", P[i].Vel, n); PUT3("GravAccel", P[i].g.GravAccel, n);
+  PUT1("Mass", P[i].Mass, n); PUT1("Hsml", P[i].Hsml, n);
+  PUT3("VelPred", SphP[i].VelPred, ng); PUT3("HydroAccel", SphP[i].a.HydroAccel, ng); PUT3("DragAccel", SphP[i].da.DragAccel, ng);
+  PUT1("DivVel", SphP[i].v.DivVel, ng); PUT1("Density", SphP[i].d.Density, ng); PUT1("Entropy", SphP[i].Entropy, ng);
+  PUT1("DtEntropy", SphP[i].e.DtEntropy, ng); PUT1("Pressure", SphP[i].Pressure, ng);
+#undef PUT3
+#undef PUT1
+#undef PUTI
+  free(d3); free(d1); free(i1);
+}
+
 void ref_density(void) __attribute__((weak));
 void ref_hydro_force(void) __attribute__((weak));
 
@@ -402,6 +426,26 @@ int main(int argc, char **argv)
 	    case 'G': gravity_tree(); break;
 	    case 'U': force_update_hmax(); break;
 	    case 'H': hydro_force(); break;
+	    case 'X':
+	      /* lazy drift of the sources to a later time (predict.c:129, called from the walks: forcetree.c:1911, ngb.c:57):
+	         give the dust drag a non-zero value, leave every third particle already current, dump, drift, dump */
+	      {
+		int k, t1 = All.Ti_Current + 24;
+		for(i = 0; i < N_gas; i++)
+		  for(k = 0; k < 3; k++) SphP[i].da.DragAccel[k] = 0.01 * SphP[i].a.HydroAccel[(k + 1) % 3];
+		for(i = 0; i < NumPart; i += 3) P[i].Ti_current = t1;
+		{
+		  double q[3] = { (double) All.Ti_Current, (double) t1, All.Timebase_interval };
+		  put(prefix, "times", 'd', 3, 1, q);
+		  q[0] = All.MinGasHsml;
+		  put(prefix, "mingashsml", 'd', 1, 1, q);
+		}
+		dump_drift_state(prefix, "pre");
+		All.Ti_Current = t1;
+		for(i = 0; i < NumPart; i++) drift_particle(i, All.Ti_Current);
+		dump_drift_state(prefix, "post");
+	      }
+	      break;
 	    case 'N': dump_nodes(prefix); break;
 	    case 'C': pair_counts(prefix); break;
 	    case 'K': dump_keys(prefix); break;

@@ -103,5 +103,19 @@ def main():
         print(name, n, "particles ->", os.path.getsize(path) // 1024, "KiB")
 
 
+def drift_fixture():
+    """State before / after the reference's own drift_particle (predict.c:129) for tests/test_drift.py: a settled
+    force evaluation (so GravAccel, HydroAccel, DivVel, Density, Pressure are real), then harness op X."""
+    ps, par = _timebins(), ics.default_params(Ti_Current=16)
+    par["PartAllocFactor"] = 20.0
+    ref = util.run_oracle(util.REF_HARNESS, ps, par, "T S D R G D U H X")
+    out = {k[len("8_X_"):]: v for k, v in ref.items() if k.startswith("8_X_")}
+    os.makedirs(os.path.join(HERE, "aux"), exist_ok=True)
+    path = os.path.join(HERE, "aux", "drift_cube_timebins_2k.npz")
+    np.savez_compressed(path, **out)
+    print("drift fixture ->", os.path.getsize(path) // 1024, "KiB", sorted(out)[:6], "...")
+
+
 if __name__ == "__main__":
     main()
+    drift_fixture()

@@ -1,0 +1,61 @@
+"""CPU suite: gl_gadget_drift (host code of libgl_b200.so, no GPU involved) against the reference's OWN drift_particle
+(predict.c:129).  The fixture tests/golden/aux/drift_cube_timebins_2k.npz was written by oracle/_ref/ref_harness op X
+(tests/golden/make_golden.py): the state the drift reads, and the state the unmodified reference left behind, for
+2000 gas particles on individual time bins after a settled force evaluation; every third particle is already current
+and must not move.  Same statements, same libm: the results are compared bit for bit."""
+import ctypes as C
+import os
+
+import numpy as np
+
+import util
+from gadget_leicester_b200 import aos
+from gadget_leicester_b200 import lib as L
+
+FIX = os.path.join(util.ROOT, "tests", "golden", "aux", "drift_cube_timebins_2k.npz")
+
+P_FIELDS = (("Pos", "p_Pos", np.float64, 3), ("Vel", "p_Vel", np.float64, 3), ("GravAccel", "p_GravAccel", np.float64, 3),
+            ("Mass", "p_Mass", np.float64, 1), ("Hsml", "p_Hsml", np.float64, 1), ("Type", "p_Type", np.int16, 1),
+            ("TimeBin", "p_TimeBin", np.int16, 1), ("Ti_begstep", "p_Ti_begstep", np.int32, 1), ("Ti_current", "p_Ti_current", np.int32, 1))
+S_FIELDS = (("VelPred", "s_VelPred", np.float64, 3), ("HydroAccel", "s_HydroAccel", np.float64, 3), ("DragAccel", "s_DragAccel", np.float64, 3),
+            ("DivVel", "s_DivVel", np.float64, 1), ("Density", "s_Density", np.float64, 1), ("Entropy", "s_Entropy", np.float64, 1),
+            ("DtEntropy", "s_DtEntropy", np.float64, 1), ("Pressure", "s_Pressure", np.float64, 1))
+
+
+def _arrays(z, tag):
+    n = z[tag + "_Pos"].shape[0]
+    ps = dict(pos=z[tag + "_Pos"], vel=z[tag + "_Vel"], mass=z[tag + "_Mass"], id=z[tag + "_id"], hsml=z[tag + "_Hsml"],
+              oldacc=np.zeros(n), type=z[tag + "_Type"], timebin=z[tag + "_TimeBin"], entropy=z[tag + "_Entropy"],
+              dtentropy=z[tag + "_DtEntropy"])
+    a = aos.GadgetArrays(ps, pinned=False)
+    for name, f, dt, c in P_FIELDS:
+        a.pview(f, dt, c)[:] = z[tag + "_" + name]
+    for name, f, dt, c in S_FIELDS:
+        a.sview(f, dt, c)[:] = z[tag + "_" + name]
+    return a
+
+
+def test_library_drift_equals_reference_drift_particle():
+    z = np.load(FIX)
+    t0, t1, tbi = z["times"]
+    a = _arrays(z, "pre")
+    before = np.array(a.P, copy=True)
+    lib = L.load_library()
+    lay = aos.layout_struct()
+    nd = C.c_longlong(0)
+    rc = lib.gl_gadget_drift(C.byref(lay), L._ptr(a.P), L._ptr(a.SphP), a.NumPart, a.N_gas, int(t1), float(tbi), float(z["mingashsml"][0]),
+                             C.byref(nd))
+    assert rc == 0
+    stale = z["pre_Ti_current"] != int(t1)
+    assert nd.value == int(stale.sum()) and 0 < nd.value < a.NumPart
+    for name, f, dt, c in P_FIELDS:
+        assert (a.pview(f, dt, c) == z["post_" + name]).all(), name
+    for name, f, dt, c in S_FIELDS:
+        assert (a.sview(f, dt, c) == z["post_" + name]).all(), name
+    # particles that were already current did not change at all
+    lay_d = aos.layout()
+    Pb = np.frombuffer(before, np.uint8).reshape(a.NumPart, lay_d["p_stride"])
+    Pa = np.frombuffer(np.array(a.P, copy=True), np.uint8).reshape(a.NumPart, lay_d["p_stride"])
+    assert (Pb[~stale] == Pa[~stale]).all()
+    # a particle ahead of the target time is the reference's endrun(12)
+    assert lib.gl_gadget_drift(C.byref(lay), L._ptr(a.P), L._ptr(a.SphP), a.NumPart, a.N_gas, int(t1) - 1, float(tbi), 0.0, None) != 0
