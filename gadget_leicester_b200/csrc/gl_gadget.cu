@@ -1037,3 +1037,35 @@ extern "C" int gl_gadget_drift(const gl_gadget_layout *lay, void *Pv, void *SphP
   if(ndrifted) *ndrifted = moved.load();
   return ahead.load() ? 1 : 0;
 }
+
+// ---------------------------------------------------------------- reorder_gas / reorder_particles (host) ----
+extern "C" int gl_gadget_reorder(const gl_gadget_layout *lay, void *Pv, void *SphPv, long long NumPart, long long N_gas, const int *order)
+{
+  const long long ps = lay->p_stride, ss = lay->sph_stride;
+  if(NumPart <= 0) return 0;
+  for(long long k = 0; k < NumPart; k++)	// a gas slot must take a gas particle (the two blocks are ordered separately)
+    if(order[k] < 0 || order[k] >= NumPart || ((k < N_gas) != (order[k] < N_gas))) return 1;
+  char *P = (char *) Pv, *S = (char *) SphPv;
+  char *tp = (char *) malloc((size_t) NumPart * ps), *tsph = N_gas > 0 ? (char *) malloc((size_t) N_gas * ss) : nullptr;
+  if(!tp || (N_gas > 0 && !tsph))
+    {
+      free(tp);
+      free(tsph);
+      return 1;
+    }
+  HostPool &pool = HostPool::get();
+  pool.run(NumPart, PACK_CHUNK, [=](long long, long long a, long long b) {
+    memcpy(tp + a * ps, P + a * ps, (size_t) (b - a) * ps);
+    if(a < N_gas) memcpy(tsph + a * ss, S + a * ss, (size_t) (std::min(b, N_gas) - a) * ss);
+  });
+  pool.run(NumPart, PACK_CHUNK, [=](long long, long long a, long long b) {
+    for(long long k = a; k < b; k++)
+      {
+	memcpy(P + k * ps, tp + (long long) order[k] * ps, (size_t) ps);
+	if(k < N_gas) memcpy(S + k * ss, tsph + (long long) order[k] * ss, (size_t) ss);
+      }
+  });
+  free(tp);
+  free(tsph);
+  return 0;
+}

@@ -68,7 +68,7 @@ EXPORTS = [
     "gl_gravity_tree", "gl_density", "gl_force_update_hmax", "gl_hydro_force", "gl_compute_accelerations", "gl_compute_potential", "gl_get_potential",
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
-    "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree", "gl_gadget_drift",
+    "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree", "gl_gadget_drift", "gl_gadget_reorder",
 ]
 
 _lib = None
@@ -133,6 +133,7 @@ def load_library():
     lib.gl_gadget_pack_segment.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, vp, vp]
     lib.gl_gadget_push_segment_async.argtypes = [vp, vp, vp, C.c_int]
     lib.gl_gadget_push_wait.argtypes = [vp]
+    lib.gl_gadget_reorder.argtypes = [C.POINTER(GLGadgetLayout), vp, vp, C.c_longlong, C.c_longlong, vp]
     lib.gl_gadget_drift.argtypes = [C.POINTER(GLGadgetLayout), vp, vp, C.c_longlong, C.c_longlong, C.c_int, C.c_double, C.c_double,
                                     C.POINTER(C.c_longlong)]
     lib.gl_export_tree.argtypes = [vp, C.POINTER(GLTreeLayout), vp, vp, vp, vp, C.c_longlong, C.c_longlong, C.c_int,

@@ -196,6 +196,11 @@ int gl_gadget_compute_accelerations(gl_ctx * ctx, void *P, void *SphP, long long
  * time1 (endrun(12) in the reference).  *ndrifted <- number of particles moved. */
 int gl_gadget_drift(const gl_gadget_layout * lay, void *P, void *SphP, long long NumPart, long long N_gas, int time1,
 		    double Timebase_interval, double MinGasHsml, long long *ndrifted);
+/* The second half of peano_hilbert_order() (peano.c:25-92 -> reorder_gas :106, reorder_particles :148): permute the
+ * structs so that new P[k] = old P[order[k]] (order from gl_peano_hilbert_order: gas block and the rest ordered
+ * separately), SphP[] alongside for the gas block.  The reference follows permutation cycles in place, one struct at a
+ * time; here all host cores gather from a temporary copy.  Host code only - no context, no GPU. */
+int gl_gadget_reorder(const gl_gadget_layout * lay, void *P, void *SphP, long long NumPart, long long N_gas, const int *order);
 /* scatter results back in place; what = bit mask: 1 gravity, 2 density, 4 hydro */
 int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
 

@@ -59,3 +59,25 @@ def test_library_drift_equals_reference_drift_particle():
     assert (Pb[~stale] == Pa[~stale]).all()
     # a particle ahead of the target time is the reference's endrun(12)
     assert lib.gl_gadget_drift(C.byref(lay), L._ptr(a.P), L._ptr(a.SphP), a.NumPart, a.N_gas, int(t1) - 1, float(tbi), 0.0, None) != 0
+
+
+def test_reorder_permutes_structs_like_the_reference():
+    """gl_gadget_reorder = reorder_gas + reorder_particles (peano.c:106, :148): new P[k] = old P[order[k]], SphP[] with
+    the gas block, every byte of every struct."""
+    rng = np.random.default_rng(0)
+    lay_d = aos.layout()
+    n, ngas = 1003, 800
+    ps_, ss_ = lay_d["p_stride"], lay_d["sph_stride"]
+    Pb = rng.integers(0, 256, size=n * ps_, dtype=np.uint8)
+    Sb = rng.integers(0, 256, size=ngas * ss_, dtype=np.uint8)
+    order = np.concatenate([rng.permutation(ngas), ngas + rng.permutation(n - ngas)]).astype(np.int32)
+    want_P = Pb.reshape(n, ps_)[order].copy()
+    want_S = Sb.reshape(ngas, ss_)[order[:ngas]].copy()
+    lib = L.load_library()
+    lay = aos.layout_struct()
+    assert lib.gl_gadget_reorder(C.byref(lay), L._ptr(Pb), L._ptr(Sb), n, ngas, L._ptr(order)) == 0
+    assert (Pb.reshape(n, ps_) == want_P).all() and (Sb.reshape(ngas, ss_) == want_S).all()
+    bad = order.copy()
+    bad[0], bad[-1] = bad[-1], bad[0]          # a non-gas particle into the gas block: refused, nothing touched
+    assert lib.gl_gadget_reorder(C.byref(lay), L._ptr(Pb), L._ptr(Sb), n, ngas, L._ptr(bad)) != 0
+    assert (Pb.reshape(n, ps_) == want_P).all()
