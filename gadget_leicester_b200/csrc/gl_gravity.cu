@@ -22,8 +22,11 @@ struct GravTarget
   double x, y, z, aold, soft;
 };
 
+#ifndef GRAV_MIN_BLOCKS
+#define GRAV_MIN_BLOCKS 12	// 40 registers, 48 warps per SM: 3.15 ms for the 1.6M disc (10 blocks: 3.24, 16 blocks with spills: 3.39)
+#endif
 template <bool BH, bool POT>
-__global__ void __launch_bounds__(GL_BLOCK)
+__global__ void __launch_bounds__(GL_BLOCK, GRAV_MIN_BLOCKS)
 k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
 	       const double4 *__restrict__ e_A, const double4 *__restrict__ e_B, const double2 *__restrict__ e_C,
 	       const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
