@@ -239,6 +239,63 @@ def test_edge_cases_tiny_sets(FP):
     fp.close()
 
 
+def test_coincident_particles_bucket(FP):
+    """Collisions: 40 gas particles at ONE position (plus 12 at another) end up in a finest-level bucket (the reference
+    randomises sub-cells there, forcetree.c:219-232, so it cannot be the checker).  Checked against brute force: the
+    neighbour pair counts and densities exactly, gravity against a direct sum, an empty active list is a no-op."""
+    ps = ics.cube(600, seed=41)
+    ps["pos"][100:140] = ps["pos"][100]
+    ps["pos"][300:312] = ps["pos"][300]
+    par = ics.default_params()
+    n = 600
+    ps["hsml"][:] = 0.12
+    fp = FP(par)
+    fp.load(ps)
+    assert fp.force_treebuild() > 0
+    g = fp.gravity_tree()
+    d = fp.density()
+    fp.force_update_hmax()
+    h = fp.hydro_force()
+    assert np.isfinite(g["GravAccel"]).all() and np.isfinite(d["Density"]).all() and np.isfinite(h["HydroAccel"]).all()
+    # density: exact neighbour sets at the final Hsml, including the coincident ones (r2 == 0 < h2)
+    for i in (0, 100, 139, 300, 311, 599):
+        hh = d["Hsml"][i]
+        dx = ps["pos"][i] - ps["pos"]
+        r2 = dx[:, 0] * dx[:, 0] + dx[:, 1] * dx[:, 1] + dx[:, 2] * dx[:, 2]
+        hit = r2 < hh * hh
+        assert int(hit.sum()) == int(d["DensPairs"][i])
+        u = np.sqrt(r2[hit]) / hh
+        wk = np.where(u < 0.5, 2.546479089470 + 15.278874536822 * (u - 1) * u * u, 5.092958178941 * (1.0 - u) ** 3) / hh ** 3
+        assert abs((ps["mass"][hit] * wk).sum() - d["Density"][i]) <= 1e-12 * d["Density"][i]
+    # hydro pairs exclude r == 0 (hydra.c:1270): coincident partners do not count
+    hfin = d["Hsml"]
+    for i in (100, 300):
+        dx = ps["pos"][i] - ps["pos"]
+        r2 = (dx * dx).sum(1)
+        want = ((r2 < hfin[i] ** 2) | (r2 < hfin ** 2)) & (r2 > 0)
+        assert int(want.sum()) == int(h["HydroPairs"][i])
+    # gravity: Barnes-Hut pass vs direct sum with the spline softening (gas: h = max(Hsml_i, Hsml_j) of the INITIAL Hsml)
+    h0 = 0.12
+    for i in (5, 100, 450):
+        dx = ps["pos"] - ps["pos"][i]
+        r2 = (dx * dx).sum(1)
+        r = np.sqrt(r2)
+        u = r / h0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            fac = np.where(r >= h0, ps["mass"] / (r2 * r), np.where(u < 0.5, ps["mass"] / h0 ** 3 * (10.666666666667 + u * u * (32.0 * u - 38.4)),
+                           ps["mass"] / h0 ** 3 * (21.333333333333 - 48.0 * u + 38.4 * u * u - 10.666666666667 * u ** 3 - 0.066666666667 / u ** 3)))
+        fac[r2 == 0] = 0.0
+        acc = (dx * fac[:, None]).sum(0) * par["G"]
+        assert np.linalg.norm(g["GravAccel"][i] - acc) <= 2e-2 * np.linalg.norm(acc)
+    # an empty active list: nothing is evaluated, nothing fails
+    fp.set_targets(np.zeros(0, dtype=np.int32))
+    g0 = fp.gravity_tree()
+    assert fp.stats()["interactions"] == 0 and (g0["OldAcc"] == g["OldAcc"]).all()
+    fp.density()
+    fp.hydro_force()
+    fp.close()
+
+
 def test_ragged_warp_and_target_subset(FP, port_bin):
     """33 + 2 particles (one full warp + a ragged one); results for a target subset (the reference's active
     list / a GPU's Peano-Hilbert segment) are bit-identical to the same particles in a full evaluation."""
