@@ -367,17 +367,8 @@ class DistributedForcePath:
             scale = allt[:, 0] / allt[:, 1].clamp(min=1e-300)
             full = full * (scale / scale.mean()).view(self.world, 1)
         cost = torch.cat([full[r, : hi - lo] for r, (lo, hi) in enumerate(self.ranges)])
-        csum = torch.cumsum(cost, 0)
-        tot = float(csum[-1].item())
-        cuts = [0]
-        for r in range(1, self.world):
-            goal = torch.tensor([tot * r / self.world * (1 + 1e-12)], dtype=torch.float64, device=dev)
-            cuts.append(int(torch.searchsorted(csum, goal, right=True).item()))
-        cuts.append(self.n)
-        for r in range(1, len(cuts)):
-            cuts[r] = max(cuts[r], cuts[r - 1])
-        new_ranges = [(cuts[r], cuts[r + 1]) for r in range(self.world)]
-        del full, cost, csum
+        new_ranges = work_balanced_ranges(cost.cpu().numpy(), self.world)      # (the function the gloo/CPU tests cover)
+        del full, cost
         glob = unpack_gathered(allgather_block(self.own_f64, self.world, self.group),
                                allgather_block(self.own_i32, self.world, self.group), self.ranges, m)
         self.full_f64 = self.full_i32 = None
