@@ -47,9 +47,9 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define GL_GAMMA (7. / 5.)	// allvars.h:64
 #define GL_GAMMA_MINUS1 (GL_GAMMA - 1)
 #define BOX_SLACK 1.0000000001
-#define CAND_CAP 192		// staged candidates per warp (192: four 4-warp blocks of k_hydro fit one SM's shared memory)
+#define CAND_CAP 192		// staged candidates per warp
 #define QCAP 32			// lane = target mode: entries of every lane's private hit queue (power of two)
-#define SPH_WARPS 4
+#define SPH_WARPS 2		// warps per block: 64-thread blocks (3.48 / 3.70 ms density / hydro; 128 threads 3.57 / 3.75, 32 threads 3.52 / 3.74)
 #define STK_CAP 512
 #define LT_MIN_ACTIVE 12	// with at least this many active targets a warp runs lane = target (see density_chunk_lt)
 #define FAT_THRESH 4096	// neighbours above which a target leaves the warp path
@@ -57,7 +57,7 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define STK_RESERVE 160	// 7 pushes per level x 21 levels: pure depth-first continuation never overflows
 #define SPH_BLOCK (32 * SPH_WARPS)
 #ifndef SPH_MIN_BLOCKS
-#define SPH_MIN_BLOCKS 3
+#define SPH_MIN_BLOCKS 6
 #endif
 #define FULL 0xffffffffu
 
@@ -1290,7 +1290,7 @@ __device__ __forceinline__ void hydro_store(const HydroTarget &T, const HydroAcc
 }
 
 #ifndef HYDRO_MIN_BLOCKS
-#define HYDRO_MIN_BLOCKS 4
+#define HYDRO_MIN_BLOCKS 8
 #endif
 // Search and pair arithmetic live in ONE kernel on purpose.  A split variant was built and measured (search kernel at 61
 // registers / 32 warps per SM writing per-target candidate lists, pair kernel reading them: bit-identical results): the
