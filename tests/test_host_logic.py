@@ -141,3 +141,15 @@ def test_allgather_plumbing_gloo_world2(n):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_host_worker_pool_native(tmp_path):
+    """gl_host.h (the worker pool behind the drop-in layer's pack / scatter / drift / reorder loops) as plain C++:
+    chunk coverage, FIFO hand-out, non-blocking submit, concurrent submitters (tests/native/hostpool_check.cpp)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "hostpool_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(root, "gadget_leicester_b200", "csrc"),
+                           "-o", exe, os.path.join(root, "tests", "native", "hostpool_check.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "HOSTPOOL OK" in r.stdout, r.stdout + r.stderr
