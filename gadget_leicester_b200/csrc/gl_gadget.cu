@@ -773,7 +773,11 @@ extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv,
   // the gravity block goes out once the density kernel has been launched (see gl_ctx::post_launch)
   c->post_launch = [&]() {
     if(cudaStreamWaitEvent(cs1, c->ev[11], 0) != cudaSuccess || d2h_gravity(c, cs1, out.A) || cudaEventRecord(evG, cs1) != cudaSuccess)
-      hook_rc = 1;
+      {
+	hook_rc = 1;
+	stages.stop();		// nothing valid will land: the scatter thread must not touch P[]
+	return;
+      }
     stages.post(1);
   };
 
@@ -808,11 +812,19 @@ extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv,
       if(gls_hydro_launch(c, tg + n_lo, c->n_tgt_gas - n_lo)) return bail(1);
       c->post_launch = [&]() {
 	if(cudaStreamWaitEvent(cs0, c->ev[13], 0) != cudaSuccess || d2h_density(c, cs0, out.B) || cudaEventRecord(evD, cs0) != cudaSuccess)
-	  hook_rc = 1;
+	  {
+	    hook_rc = 1;
+	    stages.stop();
+	    return;
+	  }
 	stages.post(2);
 	if(cudaStreamWaitEvent(cs1, c->ev[14], 0) != cudaSuccess || d2h_hydro(c, cs1, out.C, 0, idx ? n : split) ||
 	   cudaEventRecord(evH1, cs1) != cudaSuccess)
-	  hook_rc = 1;
+	  {
+	    hook_rc = 1;
+	    stages.stop();
+	    return;
+	  }
 	stages.post(3);
       };
       rc = gls_hydro_end(c);	// fires the hook, then waits for both launches
