@@ -144,10 +144,12 @@ class DistributedForcePath:
     Per force evaluation the data path has exactly three collectives (NCCL all-gathers over NVLink): the packed
     float64 state block, the packed int32 state block, and - after density - the packed SphP block."""
 
-    def __init__(self, params, rank=0, world=1, device=0, group=None):
+    def __init__(self, params, rank=0, world=1, device=0, group=None, force_path=None):
+        """device: CUDA device index.  force_path: an object with ForcePath's interface to drive instead of the CUDA
+        library - only the CPU (gloo) tests of the exchange choreography pass one, together with device="cpu"."""
         self.rank, self.world, self.group = rank, world, group
-        self.device = torch.device("cuda", device)
-        self.fp = ForcePath(params, device=device)
+        self.device = torch.device(device) if isinstance(device, (str, torch.device)) else torch.device("cuda", device)
+        self.fp = force_path if force_path is not None else ForcePath(params, device=device)
         self.params = params
         self.n = 0
         self.own = {}
@@ -217,7 +219,8 @@ class DistributedForcePath:
     def _sync_lib(self):
         # the library runs on its own stream and synchronises before returning; make sure torch / NCCL work is
         # done before the library reads it
-        torch.cuda.current_stream(self.device).synchronize()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
 
     def _tick(self, key, t0):
         import time
@@ -234,7 +237,7 @@ class DistributedForcePath:
         t0 = time.perf_counter()
         m = self.m
         self._late = None
-        split = full and self.world > 1 and self.split_exchange
+        split = full and self.world > 1 and self.split_exchange and self.device.type == "cuda"
         nf, ni = (F64_ROWS, I32_ROWS) if (full and not split) else (F64_ROWS_GRAV, I32_ROWS_GRAV)
         self.full_f64 = allgather_block(self.own_f64[: nf * m], self.world, self.group)
         self.full_i32 = allgather_block(self.own_i32[: ni * m], self.world, self.group)
