@@ -142,20 +142,20 @@ def reference_arm(args):
     import numpy as np
     cores = max(1, min(os.cpu_count() or 1, 32))
     nwarm, nsteps = min(args.warmup, 1), max(1, min(args.steps, 3))
-    inter, secs, kind = run_cpu_instances(cores, nwarm + nsteps, CPU_SAMPLE_NGAS)
+    inter, secs, kind = run_cpu_instances(cores, nwarm + nsteps, args.cpu_sample_ngas)
     inter, secs = inter[:, nwarm:], secs[:, nwarm:]
     step_s = float(secs.max(axis=0).mean())          # slowest instance per step
     value = float(inter.sum(axis=0).mean() / step_s)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=nsteps, warmup=nwarm, ms_per_step=step_s * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
                 config=dict(workload="config 0 disc generator at %d gas + 2 sinks per instance (bounded sample of the 1.6M disc)"
-                            % CPU_SAMPLE_NGAS, instances=cores),
+                            % args.cpu_sample_ngas, instances=cores),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind,
                                   sample="%d concurrent single-rank instances (no MPI in the image) of the %d-gas disc; "
                                          "step = gravity_tree+density+force_update_hmax+hydro_force after a settled start"
-                                         % (cores, CPU_SAMPLE_NGAS)),
+                                         % (cores, args.cpu_sample_ngas)),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                sph_updates_per_s=float(cores * CPU_SAMPLE_NGAS / step_s), gpu_launches=0)
+                sph_updates_per_s=float(cores * args.cpu_sample_ngas / step_s), gpu_launches=0)
     print(json.dumps(line))
 
 
@@ -288,6 +288,8 @@ def main():
     ap.add_argument("--rebalance", action="store_true", help="config 0: re-split the Peano-Hilbert segments by the settle step's GravCost")
     ap.add_argument("--no-rebalance", action="store_true", help="keep the equal-count Peano-Hilbert split (default: work-balanced "
                     "split from the settle step's GravCost, domain.c:1075)")
+    ap.add_argument("--cpu-sample-ngas", type=int, default=CPU_SAMPLE_NGAS,
+                    help="gas particles per CPU instance of the reference arm / cpu_baseline leg (the line states the sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -503,11 +505,11 @@ def main():
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline and args.config == 0:
         try:
-            ci, cs, kind = run_cpu_instances(1, 2, CPU_SAMPLE_NGAS)
+            ci, cs, kind = run_cpu_instances(1, 2, args.cpu_sample_ngas)
             cpu_base = dict(value=float(ci[0, 1] / cs[0, 1]), unit=UNIT, cores=1, kind=kind,
                             sample="1 single-rank instance, %d-gas disc + 2 sinks (same generator, bounded sample), "
-                                   "one settled force step: %.2f s" % (CPU_SAMPLE_NGAS, cs[0, 1]),
-                            sph_updates_per_s=float(CPU_SAMPLE_NGAS / cs[0, 1]))
+                                   "one settled force step: %.2f s" % (args.cpu_sample_ngas, cs[0, 1]),
+                            sph_updates_per_s=float(args.cpu_sample_ngas / cs[0, 1]))
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
             cpu_base = dict(value=None, unit=UNIT, cores=1, kind="unavailable", sample=str(ex)[:200])
 

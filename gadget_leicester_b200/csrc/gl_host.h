@@ -31,6 +31,11 @@ struct HostJob
     std::unique_lock<std::mutex> lk(m);
     cv.wait(lk, [&] { return finished; });
   }
+  bool is_finished()
+  {
+    std::lock_guard<std::mutex> lk(m);
+    return finished;
+  }
 };
 
 class HostPool

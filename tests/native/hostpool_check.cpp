@@ -39,7 +39,7 @@ int main()
     auto jb = pool.submit(8, 1, [&](long long, long long, long long) {
       if(ja->next.load() < na) order_violation++;	// every chunk of A must have been handed out by now
     });
-    CHECK(!jb->finished || a_started.load() == na);	// (racy read, only a sanity check: B cannot be done before A was handed out)
+    CHECK(!jb->is_finished() || a_started.load() == na);	// B cannot be done before all of A was handed out
     ja->wait();
     jb->wait();
     CHECK(a_started.load() == na);
@@ -49,7 +49,7 @@ int main()
   {
     auto j = pool.submit(0, 16, [&](long long, long long, long long) { fails++; });
     j->wait();
-    CHECK(j->finished);
+    CHECK(j->is_finished());
   }
   // 4. concurrent submitters
   {

@@ -143,13 +143,19 @@ def test_allgather_plumbing_gloo_world2(n):
     assert all(ok for _, ok in res), res
 
 
-def test_host_worker_pool_native(tmp_path):
+@pytest.mark.parametrize("sanitizer", ["", "thread"])
+def test_host_worker_pool_native(tmp_path, sanitizer):
     """gl_host.h (the worker pool behind the drop-in layer's pack / scatter / drift / reorder loops) as plain C++:
-    chunk coverage, FIFO hand-out, non-blocking submit, concurrent submitters (tests/native/hostpool_check.cpp)."""
+    chunk coverage, FIFO hand-out, non-blocking submit, concurrent submitters (tests/native/hostpool_check.cpp) -
+    once optimised, once under ThreadSanitizer (any reported race fails the run)."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "hostpool_check")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(root, "gadget_leicester_b200", "csrc"),
-                           "-o", exe, os.path.join(root, "tests", "native", "hostpool_check.cpp")])
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    flags = ["-O1", "-g", "-fsanitize=" + sanitizer] if sanitizer else ["-O2"]
+    cc = subprocess.run(["g++"] + flags + ["-std=c++17", "-pthread", "-I", os.path.join(root, "gadget_leicester_b200", "csrc"),
+                         "-o", exe, os.path.join(root, "tests", "native", "hostpool_check.cpp")], capture_output=True, text=True)
+    if cc.returncode != 0 and sanitizer:
+        pytest.skip("no lib%ssan for this g++" % sanitizer[0])
+    assert cc.returncode == 0, cc.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, GL_HOST_THREADS="6"))
     assert r.returncode == 0 and "HOSTPOOL OK" in r.stdout, r.stdout + r.stderr
