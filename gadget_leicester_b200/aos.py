@@ -128,6 +128,18 @@ class GadgetArrays:
         self.SphP, self._sk = _host_buffer(max(ngas, 1) * lay["sph_stride"], pinned)
         self.set_from(ps)
 
+    @classmethod
+    def empty(cls, max_part, max_part_sph=None, pinned=False):
+        """Unfilled P[] / SphP[] with room for max_part / max_part_sph structs (allocate_memory, allocate.c:56-82);
+        NumPart = N_gas = 0 until a reader fills them."""
+        lay = layout()
+        self = cls.__new__(cls)
+        self.NumPart = self.N_gas = 0
+        self.MaxPart, self.MaxPartSph = int(max_part), int(max_part if max_part_sph is None else max_part_sph)
+        self.P, self._pk = _host_buffer(max(self.MaxPart, 1) * lay["p_stride"], pinned)
+        self.SphP, self._sk = _host_buffer(max(self.MaxPartSph, 1) * lay["sph_stride"], pinned)
+        return self
+
     def pview(self, field, dtype, count=1):
         lay = layout()
         n = self.NumPart

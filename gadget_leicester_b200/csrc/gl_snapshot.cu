@@ -1,0 +1,447 @@
+// gl_snapshot.cu - the reference's binary snapshot / initial-conditions files (formats 1 and 2) written from and read
+// into its own P[] / SphP[] arrays.  Host code only: no context, no GPU - the file is compiled
+// with the rest of the library so that the reference-side glue links one .so.
+//
+// The record list is the reference's `enum iofields` (allvars.h:1762) restricted to what blockpresent() (io.c:1639)
+// lets through under the shipped -D list; every record is described by one row of the table below (which types carry
+// it: get_particles_in_block io.c:1460; how wide it is: get_bytes_per_blockelement io.c:1184; its format-2 label:
+// get_Tab_IO_Label io.c:2038).  Values are 4-byte floats, IDs 4-byte unsigned.
+#include "gl_internal.h"
+#include "gl_host.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace
+{
+enum Block
+{
+  B_POS, B_VEL, B_ID, B_MASS, B_U, B_RHO, B_NE, B_NH, B_HSML, B_DUST, B_SFR, B_AGE, B_BHMASS, B_BHMDOT, B_ACCDISCMASS, B_BHMSEED,
+  B_NEWDENS, B_DELPHOTONMOM, B_OLDPHOTONMOM, B_BIPHOTONEN, B_ACCMASS, B_ACCMOM, B_COUNT
+};
+
+struct BlockRow
+{
+  Block b;
+  const char *label;		// format 2
+  int ncomp;
+  int types;			// bit mask of the particle types that carry the record (before the MASS / npart rules)
+  bool behind_u;		// not read from initial conditions (read_ic.c:891)
+};
+
+const int ALL_TYPES = 63, GAS = 1, STARS = 1 << 4, SINKS = 1 << 5, VIRTUALS = 1 << 3;
+const BlockRow ROWS[B_COUNT] = {
+  {B_POS, "POS ", 3, ALL_TYPES, false}, {B_VEL, "VEL ", 3, ALL_TYPES, false}, {B_ID, "ID  ", 1, ALL_TYPES, false},
+  {B_MASS, "MASS", 1, ALL_TYPES, false}, {B_U, "U   ", 1, GAS, false}, {B_RHO, "RHO ", 1, GAS, true},
+  {B_NE, "NE  ", 1, GAS, true}, {B_NH, "NH  ", 1, GAS, true}, {B_HSML, "HSML", 1, GAS, true},
+  {B_DUST, "DUST", 1, ALL_TYPES, true}, {B_SFR, "SFR ", 1, GAS, true}, {B_AGE, "AGE ", 1, STARS, true},
+  {B_BHMASS, "BHMA", 1, SINKS, true}, {B_BHMDOT, "BHMD", 1, SINKS, true}, {B_ACCDISCMASS, "ACDM", 1, SINKS, true},
+  {B_BHMSEED, "BHMS", 1, SINKS, true}, {B_NEWDENS, "NEWD", 1, VIRTUALS, true}, {B_DELPHOTONMOM, "DPhM", 1, VIRTUALS, true},
+  {B_OLDPHOTONMOM, "OPhM", 1, VIRTUALS, true}, {B_BIPHOTONEN, "BPhE", 1, VIRTUALS, true}, {B_ACCMASS, "ACMA", 1, GAS, true},
+  // ACMO: get_bytes_per_blockelement() (io.c:1184) gives this record ONE value per particle although fill_write_buffer
+  // (io.c:1003-1014) produces three, so write_file puts only the first N_gas values of the (particle, component)
+  // stream into the file: the momenta of the first N_gas/3 gas particles.  Kept as it is - the record length is part
+  // of the format the reference and its readers expect.  (One CommBuffer pass assumed: N_gas <= BufferSize * 2^18.)
+  {B_ACCMOM, "ACMO", 1, GAS, true},
+};
+
+struct Ctx
+{
+  gl_gadget_layout L;
+  gl_io_layout IO;
+  gl_io_params par;
+  char *err;
+  int errlen;
+  int fail(const char *fmt, ...)
+  {
+    if(err && errlen > 0)
+      {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(err, (size_t) errlen, fmt, ap);
+	va_end(ap);
+      }
+    return 1;
+  }
+};
+
+// blockpresent() io.c:1639 under the shipped -D list, expressed through the layout (a build without the field has no
+// such record) and the two run-time switches
+bool present(const Ctx &c, Block b)
+{
+  switch (b)
+    {
+    case B_POS: case B_VEL: case B_ID: case B_MASS: case B_U: case B_RHO: case B_HSML:
+      return true;
+    case B_NE: case B_NH:
+      return c.par.CoolingOn != 0 && c.IO.s_Ne >= 0;
+    case B_SFR:
+      return c.par.StarformationOn != 0 && (c.par.build & GL_IO_BUILD_SFR);
+    case B_AGE:
+      return c.par.StarformationOn != 0 && c.IO.p_StellarAge >= 0;
+    case B_DUST:
+      return c.IO.p_DustRadius >= 0;
+    case B_BHMASS: return c.IO.p_BH_Mass >= 0;
+    case B_BHMDOT: return c.IO.p_BH_Mdot >= 0;
+    case B_ACCDISCMASS: return c.IO.p_AccDisc_Mass >= 0;
+    case B_BHMSEED: return c.IO.p_BH_Mseed >= 0;
+    case B_NEWDENS: return c.IO.p_NewDensity >= 0;
+    case B_DELPHOTONMOM: return c.IO.p_DeltaPhotonMomentum >= 0;
+    case B_OLDPHOTONMOM: return c.IO.p_OldPhotonMomentum >= 0;
+    case B_BIPHOTONEN: return c.IO.p_BirthPhotonEnergy >= 0;
+    case B_ACCMASS: return c.IO.s_accreted_mass >= 0;
+    case B_ACCMOM: return c.IO.s_accreted_momentum >= 0;
+    default: return false;
+    }
+}
+
+// get_particles_in_block() io.c:1460: which types the record holds in THIS file, and how many elements
+long long particles_in_block(const Ctx &c, const BlockRow &r, const int npart[6], int typelist[6])
+{
+  long long n = 0;
+  for(int t = 0; t < 6; t++)
+    {
+      typelist[t] = (npart[t] > 0) && ((r.types >> t) & 1);
+      if(r.b == B_MASS && c.par.MassTable[t] != 0) typelist[t] = 0;	// io.c:1492-1498
+      if(typelist[t]) n += npart[t];
+    }
+  return n;
+}
+
+// a P[] field of particle i / an SphP[] field of gas particle i as double
+inline double pf(const Ctx &c, const char *P, long long i, int off, int k = 0) { return ((const double *) (P + i * c.L.p_stride + off))[k]; }
+inline double sf(const Ctx &c, const char *S, long long i, int off, int k = 0) { return ((const double *) (S + i * c.L.sph_stride + off))[k]; }
+
+// fill_write_buffer() io.c:173 for one particle; out gets ncomp 4-byte values
+inline void value_out(const Ctx &c, Block b, const char *P, const char *S, long long i, const double *nh, const double *sfr, float *out)
+{
+  const gl_gadget_layout &L = c.L;
+  switch (b)
+    {
+    case B_POS:
+      for(int k = 0; k < 3; k++) out[k] = (float) pf(c, P, i, L.p_Pos, k);
+      break;
+    case B_VEL:
+      {
+	// io.c:256-299, non-comoving: the kick from the middle of the particle's step to the output time
+	const char *pi = P + i * L.p_stride;
+	const int tb = *(const short *) (pi + L.p_TimeBin), type = *(const short *) (pi + L.p_Type);
+	const int dt_step = tb ? (1 << tb) : 0;
+	const double dt_kick = (c.par.Ti_Current - (*(const int *) (pi + L.p_Ti_begstep) + dt_step / 2)) * c.par.Timebase_interval;
+	for(int k = 0; k < 3; k++)
+	  {
+	    float f = (float) (pf(c, P, i, L.p_Vel, k) + pf(c, P, i, L.p_GravAccel, k) * dt_kick);
+	    if(type == 0) f = (float) (f + sf(c, S, i, L.s_HydroAccel, k) * dt_kick);	// the reference accumulates in the 4-byte buffer
+	    out[k] = f;
+	  }
+	break;
+      }
+    case B_ID:
+      memcpy(out, P + i * L.p_stride + c.IO.p_ID, 4);
+      break;
+    case B_MASS: out[0] = (float) pf(c, P, i, L.p_Mass); break;
+    case B_U:
+      {
+	// io.c:320-324: u = A / (gamma-1) * rho^(gamma-1), floored
+	const double u = sf(c, S, i, L.s_Entropy) / c.par.GammaMinus1 * pow(sf(c, S, i, L.s_Density), c.par.GammaMinus1);
+	out[0] = (float) (c.par.MinEgySpec > u ? c.par.MinEgySpec : u);
+	break;
+      }
+    case B_RHO: out[0] = (float) sf(c, S, i, L.s_Density); break;
+    case B_NE: out[0] = (float) sf(c, S, i, c.IO.s_Ne); break;
+    case B_NH: out[0] = nh ? (float) nh[i] : 0.0f; break;
+    case B_HSML: out[0] = (float) pf(c, P, i, L.p_Hsml); break;
+    case B_DUST: out[0] = (float) pf(c, P, i, c.IO.p_DustRadius); break;
+    case B_SFR: out[0] = sfr ? (float) sfr[i] : 0.0f; break;
+    case B_AGE: out[0] = (float) pf(c, P, i, c.IO.p_StellarAge); break;
+    case B_BHMASS: out[0] = (float) pf(c, P, i, c.IO.p_BH_Mass); break;
+    case B_BHMDOT: out[0] = (float) pf(c, P, i, c.IO.p_BH_Mdot); break;
+    case B_ACCDISCMASS: out[0] = (float) pf(c, P, i, c.IO.p_AccDisc_Mass); break;
+    case B_BHMSEED: out[0] = (float) pf(c, P, i, c.IO.p_BH_Mseed); break;
+    case B_NEWDENS: out[0] = (float) pf(c, P, i, c.IO.p_NewDensity); break;
+    case B_DELPHOTONMOM: out[0] = (float) pf(c, P, i, c.IO.p_DeltaPhotonMomentum); break;
+    case B_OLDPHOTONMOM: out[0] = (float) pf(c, P, i, c.IO.p_OldPhotonMomentum); break;
+    case B_BIPHOTONEN: out[0] = (float) pf(c, P, i, c.IO.p_BirthPhotonEnergy); break;
+    case B_ACCMASS: out[0] = (float) sf(c, S, i, c.IO.s_accreted_mass); break;
+    default: break;		// B_ACCMOM: see accmom_slot
+    }
+}
+
+// ACMO (see the table): slot k of the record = component k % 3 of the gas particle k / 3
+inline float accmom_slot(const Ctx &c, const char *S, const std::vector<long long> &gas, long long slot)
+{
+  return (float) sf(c, S, gas[(size_t) (slot / 3)], c.IO.s_accreted_momentum, (int) (slot % 3));
+}
+
+// empty_read_buffer() read_ic.c:238 for one particle
+inline void value_in(const Ctx &c, Block b, char *P, char *S, long long i, int type, const float *in)
+{
+  const gl_gadget_layout &L = c.L;
+  auto pset = [&](int off, int k, double v) { ((double *) (P + i * L.p_stride + off))[k] = v; };
+  auto sset = [&](int off, int k, double v) { ((double *) (S + i * L.sph_stride + off))[k] = v; };
+  switch (b)
+    {
+    case B_POS:
+      for(int k = 0; k < 3; k++) pset(L.p_Pos, k, in[k]);
+      *(short *) (P + i * L.p_stride + L.p_Type) = (short) type;	// read_ic.c:268-269
+      break;
+    case B_VEL:
+      for(int k = 0; k < 3; k++) pset(L.p_Vel, k, in[k]);
+      break;
+    case B_ID: memcpy(P + i * L.p_stride + c.IO.p_ID, in, 4); break;
+    case B_MASS: pset(L.p_Mass, 0, in[0]); break;
+    case B_U: sset(L.s_Entropy, 0, in[0]); break;	// converted to entropy by init() once densities exist (read_ic.c:206)
+    case B_RHO: sset(L.s_Density, 0, in[0]); break;
+    case B_NE: sset(c.IO.s_Ne, 0, in[0]); break;
+    case B_HSML: pset(L.p_Hsml, 0, in[0]); break;
+    case B_DUST:
+      if(c.par.RestartFlag == 2) pset(c.IO.p_DustRadius, 0, in[0]);	// read_ic.c:306-311
+      break;
+    case B_AGE: pset(c.IO.p_StellarAge, 0, in[0]); break;
+    case B_BHMASS: pset(c.IO.p_BH_Mass, 0, in[0]); break;
+    case B_BHMDOT: pset(c.IO.p_BH_Mdot, 0, in[0]); break;
+    case B_ACCDISCMASS: pset(c.IO.p_AccDisc_Mass, 0, in[0]); break;
+    case B_BHMSEED: pset(c.IO.p_BH_Mseed, 0, in[0]); break;
+    case B_NEWDENS: pset(c.IO.p_NewDensity, 0, in[0]); break;
+    case B_DELPHOTONMOM: pset(c.IO.p_DeltaPhotonMomentum, 0, in[0]); break;
+    case B_OLDPHOTONMOM: pset(c.IO.p_OldPhotonMomentum, 0, in[0]); break;
+    case B_BIPHOTONEN: pset(c.IO.p_BirthPhotonEnergy, 0, in[0]); break;
+    case B_ACCMASS: sset(c.IO.s_accreted_mass, 0, in[0]); break;
+    case B_ACCMOM:		// handled per slot by the caller (the record holds one value per particle, see the table)
+    case B_NH: case B_SFR:	// derived records: "not needed to define the initial conditions" (read_ic.c:585-590)
+    default: break;
+    }
+}
+
+bool put(FILE *fd, const void *p, size_t bytes) { return fwrite(p, 1, bytes, fd) == bytes; }
+bool get(FILE *fd, void *p, size_t bytes) { return fread(p, 1, bytes, fd) == bytes; }
+bool put_int(FILE *fd, int v) { return put(fd, &v, 4); }
+
+// the format-2 record that precedes every data record: [8] LABEL nextblock [8] (io.c:2634-2642, :2672-2680)
+bool put_label(FILE *fd, const char *label, long long payload)
+{
+  const int next = (int) (payload + 8);
+  return put_int(fd, 8) && put(fd, label, 4) && put_int(fd, next) && put_int(fd, 8);
+}
+
+const long long CHUNK = 1 << 20;	// particles converted per fwrite / fread
+}				// namespace
+
+extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay, const gl_io_layout *io, const gl_io_params *par,
+				 const void *Pv, const void *SphPv, long long NumPart, const double *nh, const double *sfr,
+				 char *err, int errlen)
+{
+  Ctx c{*lay, *io, *par, err, errlen};
+  if(err && errlen > 0) err[0] = 0;
+  if(par->format != 1 && par->format != 2) return c.fail("gl_snapshot_write: format %d is not 1 or 2 (format 3 = HDF5 is not available)", par->format);
+  const char *P = (const char *) Pv, *S = (const char *) SphPv;
+
+  // particle indices per type, in P[] order (fill_write_buffer scans P[] for Type == type, io.c:212-216)
+  std::vector<long long> idx[6];
+  for(long long i = 0; i < NumPart; i++)
+    {
+      const int t = *(const short *) (P + i * c.L.p_stride + c.L.p_Type);
+      if(t < 0 || t > 5) return c.fail("gl_snapshot_write: particle %lld has Type %d", i, t);
+      idx[t].push_back(i);
+    }
+  gl_io_header h;
+  memset(&h, 0, sizeof(h));
+  static_assert(sizeof(gl_io_header) == 256, "struct io_header is 256 bytes (allvars.h:1733)");
+  for(int t = 0; t < 6; t++)
+    {
+      h.npart[t] = (int) idx[t].size();	// io.c:2566-2574 (one file: totals = this file)
+      h.npartTotal[t] = (unsigned int) idx[t].size();
+      h.npartTotalHighWord[t] = (unsigned int) ((long long) idx[t].size() >> 32);
+      h.mass[t] = par->MassTable[t];
+    }
+  h.time = par->Time;
+  h.redshift = 0;		// non-comoving (io.c:2581-2584)
+  h.flag_cooling = (par->build & GL_IO_BUILD_COOLING) ? 1 : 0;	// io.c:2589-2608
+  if(par->build & GL_IO_BUILD_SFR)
+    {
+      h.flag_sfr = h.flag_feedback = 1;
+      h.flag_stellarage = (par->build & GL_IO_BUILD_STELLARAGE) ? 1 : 0;
+      h.flag_metals = (par->build & GL_IO_BUILD_METALS) ? 1 : 0;
+    }
+  h.num_files = 1;
+  h.BoxSize = par->BoxSize;
+  h.Omega0 = par->Omega0;
+  h.OmegaLambda = par->OmegaLambda;
+  h.HubbleParam = par->HubbleParam;
+  h.flag_doubleprecision = 0;
+
+  FILE *fd = fopen(fname, "wb");
+  if(!fd) return c.fail("can't open file `%s' for writing snapshot.", fname);	// io.c:2626-2630 endrun(123)
+  bool ok = true;
+  if(par->format == 2) ok = ok && put_label(fd, "HEAD", 256);
+  ok = ok && put_int(fd, 256) && put(fd, &h, 256) && put_int(fd, 256);
+
+  std::vector<float> buf;
+  for(int r = 0; r < B_COUNT && ok; r++)
+    {
+      const BlockRow &row = ROWS[r];
+      if(!present(c, row.b)) continue;
+      int typelist[6];
+      const long long npart = particles_in_block(c, row, h.npart, typelist);
+      if(npart <= 0) continue;
+      const long long bytes = npart * row.ncomp * 4;
+      if(bytes + 8 > 0x7fffffffLL)
+	{
+	  fclose(fd);
+	  return c.fail("gl_snapshot_write: record %s needs %lld bytes, more than a 4-byte record marker holds", row.label, bytes);
+	}
+      if(par->format == 2) ok = ok && put_label(fd, row.label, bytes);
+      ok = ok && put_int(fd, (int) bytes);
+      for(int t = 0; t < 6 && ok; t++)
+	{
+	  if(!typelist[t]) continue;
+	  const std::vector<long long> &ix = idx[t];
+	  for(long long a = 0; a < (long long) ix.size() && ok; a += CHUNK)
+	    {
+	      const long long m = std::min<long long>(CHUNK, (long long) ix.size() - a);
+	      buf.resize((size_t) (m * row.ncomp));
+	      float *out = buf.data();
+	      const long long *src = ix.data() + a;
+	      const int nc = row.ncomp;
+	      const Block b = row.b;
+	      HostPool::get().run(m, 8192, [&, out, src, nc, b, a](long long, long long lo, long long hi) {
+		if(b == B_ACCMOM)
+		  for(long long k = lo; k < hi; k++) out[k] = accmom_slot(c, S, ix, a + k);
+		else
+		  for(long long k = lo; k < hi; k++) value_out(c, b, P, S, src[k], nh, sfr, out + k * nc);
+	      });
+	      ok = ok && put(fd, out, (size_t) (m * nc * 4));
+	    }
+	}
+      ok = ok && put_int(fd, (int) bytes);
+    }
+  if(fclose(fd) != 0) ok = false;
+  if(!ok) return c.fail("gl_snapshot_write: I/O error on `%s'", fname);	// my_fwrite io.c:2988 endrun(777)
+  return 0;
+}
+
+extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, const gl_io_layout *io, gl_io_params *par, void *Pv,
+				void *SphPv, long long MaxPart, long long MaxPartSph, long long *NumPart, long long *N_gas,
+				gl_io_header *hdr, char *err, int errlen)
+{
+  Ctx c{*lay, *io, *par, err, errlen};
+  if(err && errlen > 0) err[0] = 0;
+  if(par->format != 1 && par->format != 2) return c.fail("gl_snapshot_read: format %d is not 1 or 2 (format 3 = HDF5 is not available)", par->format);
+  char *P = (char *) Pv, *S = (char *) SphPv;
+  FILE *fd = fopen(fname, "rb");
+  if(!fd) return c.fail("can't open file `%s' for reading initial conditions.", fname);	// read_ic.c:663-667 endrun(123)
+  struct Closer
+  {
+    FILE *f;
+    ~Closer() { fclose(f); }
+  } closer{fd};
+
+  int b1 = 0, b2 = 0, next = 0;
+  char label[4];
+  if(par->format == 2 && !(get(fd, &b1, 4) && get(fd, label, 4) && get(fd, &next, 4) && get(fd, &b2, 4)))
+    return c.fail("gl_snapshot_read: `%s' ends inside the header label", fname);
+  gl_io_header h;
+  if(!(get(fd, &b1, 4) && get(fd, &h, 256) && get(fd, &b2, 4)) || b1 != 256 || b2 != 256)
+    return c.fail("incorrect header format");	// read_ic.c:699-704 endrun(890)
+  if(h.flag_doubleprecision)	// read_ic.c:744-750
+    return c.fail("Problem: Code not compiled with INPUT_IN_DOUBLEPRECISION, but input files are in double precision!");
+  if(h.num_files > 1) return c.fail("gl_snapshot_read: `%s' is one of %d files; multi-file snapshots are not supported", fname, h.num_files);
+  for(int t = 0; t < 6; t++)
+    {
+      h.npartTotal[t] = (unsigned int) h.npart[t];	// read_ic.c:757-765 (num_files <= 1)
+      if(par->build & GL_IO_BUILD_SFR) h.npartTotalHighWord[t] = 0;
+      par->MassTable[t] = c.par.MassTable[t] = h.mass[t];	// read_ic.c:783-784
+      if(h.npart[t] < 0) return c.fail("gl_snapshot_read: negative particle number for type %d", t);
+    }
+  long long nall = 0, first[7];
+  for(int t = 0; t < 6; t++)
+    {
+      first[t] = nall;
+      nall += h.npart[t];
+    }
+  first[6] = nall;
+  if(h.npart[0] > MaxPartSph)	// read_ic.c:851-858 endrun(172)
+    return c.fail("Not enough space for SPH particles (space for %lld, need at least %d)", MaxPartSph, h.npart[0]);
+  if(nall > MaxPart)		// read_ic.c:864-869 endrun(173)
+    return c.fail("Not enough space (space for %lld, need at least %lld)", MaxPart, nall);
+
+  std::vector<float> buf;
+  for(int r = 0; r < B_COUNT; r++)
+    {
+      const BlockRow &row = ROWS[r];
+      if(!present(c, row.b)) continue;
+      if(par->RestartFlag == 0 && row.behind_u) continue;	// read_ic.c:891: "ignore all other blocks in initial conditions"
+      int typelist[6];
+      const long long npart = particles_in_block(c, row, h.npart, typelist);
+      if(npart <= 0) continue;
+      if(par->format == 2)
+	{
+	  if(!(get(fd, &b1, 4) && get(fd, label, 4) && get(fd, &next, 4) && get(fd, &b2, 4)))
+	    return c.fail("gl_snapshot_read: `%s' ends before record %s", fname, row.label);
+	  if(strncmp(label, row.label, 4) != 0)	// read_ic.c:936-946 endrun(1890)
+	    return c.fail("incorrect block-structure! expected '%.4s' but found '%.4s'", row.label, label);
+	}
+      const long long bytes = npart * row.ncomp * 4;
+      if(!get(fd, &b1, 4)) return c.fail("gl_snapshot_read: `%s' ends before record %s", fname, row.label);
+      if(b1 != (int) bytes)
+	return c.fail("gl_snapshot_read: record %s holds %d bytes, the header's particle numbers need %lld", row.label, b1, bytes);
+      for(int t = 0; t < 6; t++)
+	{
+	  if(!typelist[t]) continue;
+	  for(long long a = 0; a < h.npart[t]; a += CHUNK)
+	    {
+	      const long long m = std::min<long long>(CHUNK, h.npart[t] - a);
+	      buf.resize((size_t) (m * row.ncomp));
+	      if(!get(fd, buf.data(), (size_t) (m * row.ncomp * 4)))	// my_fread io.c:3005 endrun(778)
+		return c.fail("I/O error (fread) on `%s' inside record %s", fname, row.label);
+	      const float *in = buf.data();
+	      const long long base = first[t] + a;
+	      const int nc = row.ncomp;
+	      const Block b = row.b;
+	      HostPool::get().run(m, 8192, [&, in, base, nc, b, t, a](long long, long long lo, long long hi) {
+		if(b == B_ACCMOM)
+		  {
+		    // the values the record really holds; the reference goes on to fill the momenta of the remaining
+		    // particles from whatever its I/O buffer held before (read_ic.c:555-562) - those are left untouched
+		    for(long long k = lo; k < hi; k++)
+		      ((double *) (S + (first[t] + (a + k) / 3) * c.L.sph_stride + c.IO.s_accreted_momentum))[(a + k) % 3] = in[k];
+		  }
+		else
+		  for(long long k = lo; k < hi; k++) value_in(c, b, P, S, base + k, t, in + k * nc);
+	      });
+	    }
+	}
+      if(!get(fd, &b2, 4) || b2 != b1) return c.fail("gl_snapshot_read: record %s is not closed by its length", row.label);
+    }
+
+  // read_ic.c:106-111: "this makes sure that masses are initialized in the case that the mass-block is completely empty"
+  for(long long i = 0; i < nall; i++)
+    {
+      const int t = *(const short *) (P + i * c.L.p_stride + c.L.p_Type);
+      if(par->MassTable[t] != 0) *(double *) (P + i * c.L.p_stride + c.L.p_Mass) = par->MassTable[t];
+    }
+  if(par->RestartFlag == 0)
+    {
+      if(par->build & GL_IO_BUILD_BH_SWALLOWGAS) par->MassTable[5] = 0;	// read_ic.c:162-167
+      if((par->build & GL_IO_BUILD_SFR) && par->MassTable[4] == 0 && par->MassTable[0] > 0)	// read_ic.c:169-178
+	par->MassTable[0] = par->MassTable[4] = 0;
+      if(par->InitGasTemp > 0)	// read_ic.c:196-210
+	for(long long i = 0; i < h.npart[0]; i++)
+	  {
+	    double *A = (double *) (S + i * c.L.sph_stride + c.L.s_Entropy);
+	    if(*A == 0) *A = par->InitGasU;
+	  }
+    }
+  for(long long i = 0; i < h.npart[0]; i++)	// read_ic.c:214-215
+    {
+      double *A = (double *) (S + i * c.L.sph_stride + c.L.s_Entropy);
+      if(par->MinEgySpec > *A) *A = par->MinEgySpec;
+    }
+  if(NumPart) *NumPart = nall;
+  if(N_gas) *N_gas = h.npart[0];
+  if(hdr) *hdr = h;
+  return 0;
+}

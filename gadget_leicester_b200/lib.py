@@ -53,6 +53,30 @@ class GLGadgetLayout(C.Structure):
         "s_DtEntropy", "s_HydroAccel", "s_DhsmlDensityFactor", "s_DivVel", "s_CurlVel", "p_Ti_current", "s_DragAccel")]
 
 
+class GLIOHeader(C.Structure):
+    """struct io_header (allvars.h:1733), 256 bytes."""
+    _fields_ = [("npart", C.c_int * 6), ("mass", C.c_double * 6), ("time", C.c_double), ("redshift", C.c_double),
+                ("flag_sfr", C.c_int), ("flag_feedback", C.c_int), ("npartTotal", C.c_uint * 6), ("flag_cooling", C.c_int),
+                ("num_files", C.c_int), ("BoxSize", C.c_double), ("Omega0", C.c_double), ("OmegaLambda", C.c_double),
+                ("HubbleParam", C.c_double), ("flag_stellarage", C.c_int), ("flag_metals", C.c_int),
+                ("npartTotalHighWord", C.c_uint * 6), ("flag_entropy_instead_u", C.c_int), ("flag_doubleprecision", C.c_int),
+                ("fill", C.c_char * 56)]
+
+
+class GLIOLayout(C.Structure):
+    _fields_ = [(k, C.c_int) for k in (
+        "p_ID", "p_DustRadius", "p_StellarAge", "p_BH_Mass", "p_BH_Mdot", "p_AccDisc_Mass", "p_BH_Mseed", "p_NewDensity",
+        "p_DeltaPhotonMomentum", "p_OldPhotonMomentum", "p_BirthPhotonEnergy", "s_Ne", "s_accreted_mass", "s_accreted_momentum")]
+
+
+class GLIOParams(C.Structure):
+    _fields_ = [("format", C.c_int), ("build", C.c_int), ("CoolingOn", C.c_int), ("StarformationOn", C.c_int),
+                ("RestartFlag", C.c_int), ("Ti_Current", C.c_int), ("Timebase_interval", C.c_double), ("Time", C.c_double),
+                ("MassTable", C.c_double * 6), ("MinEgySpec", C.c_double), ("GammaMinus1", C.c_double),
+                ("InitGasTemp", C.c_double), ("InitGasU", C.c_double), ("BoxSize", C.c_double), ("Omega0", C.c_double),
+                ("OmegaLambda", C.c_double), ("HubbleParam", C.c_double)]
+
+
 class GLTreeLayout(C.Structure):
     _fields_ = [("node_stride", C.c_longlong), ("ext_stride", C.c_longlong)] + [(k, C.c_int) for k in (
         "n_len", "n_center", "n_maxsoft", "n_s", "n_mass", "n_bitflags", "n_sibling", "n_nextnode", "n_father", "n_Ti_current",
@@ -69,6 +93,7 @@ EXPORTS = [
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
     "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree", "gl_gadget_drift", "gl_gadget_reorder",
+    "gl_snapshot_write", "gl_snapshot_read",
 ]
 
 _lib = None
@@ -136,6 +161,11 @@ def load_library():
     lib.gl_gadget_reorder.argtypes = [C.POINTER(GLGadgetLayout), vp, vp, C.c_longlong, C.c_longlong, vp]
     lib.gl_gadget_drift.argtypes = [C.POINTER(GLGadgetLayout), vp, vp, C.c_longlong, C.c_longlong, C.c_int, C.c_double, C.c_double,
                                     C.POINTER(C.c_longlong)]
+    lib.gl_snapshot_write.argtypes = [C.c_char_p, C.POINTER(GLGadgetLayout), C.POINTER(GLIOLayout), C.POINTER(GLIOParams), vp, vp,
+                                      C.c_longlong, vp, vp, C.c_char_p, C.c_int]
+    lib.gl_snapshot_read.argtypes = [C.c_char_p, C.POINTER(GLGadgetLayout), C.POINTER(GLIOLayout), C.POINTER(GLIOParams), vp, vp,
+                                     C.c_longlong, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                     C.POINTER(GLIOHeader), C.c_char_p, C.c_int]
     lib.gl_export_tree.argtypes = [vp, C.POINTER(GLTreeLayout), vp, vp, vp, vp, C.c_longlong, C.c_longlong, C.c_int,
                                    C.POINTER(C.c_longlong)]
     _lib = lib

@@ -237,6 +237,74 @@ int gl_gadget_pack_segment(gl_ctx * ctx, const void *P, const void *SphP, long l
 int gl_gadget_push_segment_async(gl_ctx * ctx, void *P, void *SphP, int what);
 int gl_gadget_push_wait(gl_ctx * ctx);
 
+/* ---- on-disk formats: initial-conditions reader and snapshot writer --------------------------
+ * The reference's binary formats 1 and 2 (All.ICFormat / All.SnapFormat; format 3 = HDF5 needs a library this image
+ * does not have), single file, as the shipped -D list stores them: 4-byte floats (neither INPUT_ nor
+ * OUTPUT_IN_DOUBLEPRECISION), 4-byte IDs (no LONGIDS), Fortran record markers, blocks in `enum iofields` order
+ * (allvars.h:1762).  Files written here are byte-identical to what savepositions() (io.c:33 -> write_file :2521 ->
+ * fill_write_buffer :173) writes from the same P[]/SphP[]; files are read the way read_ic() (read_ic.c:28 -> read_file
+ * :634 -> empty_read_buffer :238) reads them.  Host code only - no context, no GPU. */
+typedef struct gl_io_header	/* struct io_header, allvars.h:1733 (256 bytes) */
+{
+  int npart[6];
+  double mass[6];
+  double time, redshift;
+  int flag_sfr, flag_feedback;
+  unsigned int npartTotal[6];
+  int flag_cooling, num_files;
+  double BoxSize, Omega0, OmegaLambda, HubbleParam;
+  int flag_stellarage, flag_metals;
+  unsigned int npartTotalHighWord[6];
+  int flag_entropy_instead_u, flag_doubleprecision;
+  char fill[56];
+} gl_io_header;
+/* offsets of the fields only the files carry, next to gl_gadget_layout; < 0: the build has no such field and its
+ * block is absent (blockpresent(), io.c:1639) */
+typedef struct gl_io_layout
+{
+  int p_ID;			/* IO_ID */
+  int p_DustRadius;		/* IO_DUST (-DDUST), every type */
+  int p_StellarAge;		/* IO_AGE (-DSTELLARAGE), Type 4, only with StarformationOn */
+  int p_BH_Mass, p_BH_Mdot, p_AccDisc_Mass, p_BH_Mseed;	/* IO_BHMASS ... IO_BHMSEED (-DBLACK_HOLES), Type 5 */
+  int p_NewDensity, p_DeltaPhotonMomentum, p_OldPhotonMomentum, p_BirthPhotonEnergy;	/* -DVIRTUAL, Type 3 */
+  int s_Ne;			/* IO_NE (-DCOOLING), gas, only with CoolingOn */
+  int s_accreted_mass, s_accreted_momentum;	/* IO_ACCMASS, IO_ACCMOM (-DBLACK_HOLES -DVIRTUAL), gas */
+} gl_io_layout;
+#define GL_IO_BUILD_COOLING 1	/* the reference's compile-time switches that reach the files */
+#define GL_IO_BUILD_SFR 2
+#define GL_IO_BUILD_STELLARAGE 4
+#define GL_IO_BUILD_METALS 8
+#define GL_IO_BUILD_BH_SWALLOWGAS 16
+typedef struct gl_io_params
+{
+  int format;			/* All.SnapFormat / All.ICFormat: 1 or 2 */
+  int build;			/* GL_IO_BUILD_* mask: header flags (io.c:2589-2608), MassTable rules (read_ic.c:162-179) */
+  int CoolingOn, StarformationOn;	/* All.*: NE/NH and SFR/AGE blocks exist (io.c:1652-1680) */
+  int RestartFlag;		/* reader: 0 = initial conditions (blocks behind U are not read, read_ic.c:891), 2 = snapshot */
+  int Ti_Current;		/* writer: velocities are synchronised to All.Ti_Current (io.c:253-299) */
+  double Timebase_interval;
+  double Time;			/* writer: header.time */
+  double MassTable[6];		/* All.MassTable: types with an entry != 0 have no MASS record; the reader sets it from the file */
+  double MinEgySpec;		/* All.MinEgySpec: floor of U (io.c:322) and of the entropy read (read_ic.c:215) */
+  double GammaMinus1;		/* GAMMA_MINUS1 (allvars.h:64-65): U = A / (gamma-1) * rho^(gamma-1) */
+  double InitGasTemp, InitGasU;	/* reader, RestartFlag 0: gas read with u == 0 gets All.InitGasU if InitGasTemp > 0 (read_ic.c:196-210) */
+  double BoxSize, Omega0, OmegaLambda, HubbleParam;	/* header only */
+} gl_io_params;
+/* savepositions(): nh / sfr = the two derived records that come out of the cooling / star-formation modules
+ * (AbundanceRatios, get_starformation_rate: outside the path), indexed like SphP[]; NULL writes zeros.
+ * err (may be NULL) receives the message of a non-zero return. */
+int gl_snapshot_write(const char *fname, const gl_gadget_layout * lay, const gl_io_layout * io, const gl_io_params * par,
+		      const void *P, const void *SphP, long long NumPart, const double *nh, const double *sfr, char *err,
+		      int errlen);
+/* read_ic(): fills P[0..*NumPart) / SphP[0..*N_gas) (gas first, types in order) and only the fields the reference
+ * sets; par->MassTable is updated the way read_file / read_ic leave All.MassTable; *hdr <- the file header.
+ * Non-zero return where the reference calls endrun(): unreadable file, bad header record (890), double-precision
+ * file (read_ic.c:744-750), not enough room (172, 173), wrong format-2 label (1890); also for a record whose length does
+ * not match the header's particle numbers (the reference reads on regardless) and for multi-file snapshots. */
+int gl_snapshot_read(const char *fname, const gl_gadget_layout * lay, const gl_io_layout * io, gl_io_params * par, void *P,
+		     void *SphP, long long MaxPart, long long MaxPartSph, long long *NumPart, long long *N_gas,
+		     gl_io_header * hdr, char *err, int errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,13 @@ int main(void)
   SO("s_Entropy", Entropy); SO("s_Pressure", Pressure); SO("s_VelPred", VelPred); SO("s_MaxSignalVel", MaxSignalVel);
   SO("s_Density", d.Density); SO("s_DtEntropy", e.DtEntropy); SO("s_HydroAccel", a.HydroAccel);
   SO("s_DhsmlDensityFactor", h.DhsmlDensityFactor); SO("s_DivVel", v.DivVel); SO("s_CurlVel", r.CurlVel);
+  /* fields only the snapshot / IC files carry (io.c:173, read_ic.c:238) */
+  PO("io_p_DustRadius", DustRadius); PO("io_p_StellarAge", StellarAge); PO("io_p_BH_Mass", BH_Mass); PO("io_p_BH_Mdot", BH_Mdot);
+  PO("io_p_AccDisc_Mass", AccDisc_Mass); PO("io_p_BH_Mseed", BH_Mseed); PO("io_p_NewDensity", NewDensity);
+  PO("io_p_DeltaPhotonMomentum", DeltaPhotonMomentum); PO("io_p_OldPhotonMomentum", OldPhotonMomentum);
+  PO("io_p_BirthPhotonEnergy", BirthPhotonEnergy);
+  SO("io_s_Ne", Ne); SO("io_s_accreted_mass", accreted_mass); SO("io_s_accreted_momentum", accreted_momentum);
+  printf("  \"io_sizeof_ID\": %zu,\n  \"io_sizeof_header\": %zu,\n", sizeof(MyIDType), sizeof(struct io_header));
 #define NO(name, field) printf("  \"%s\": %zu,\n", name, offsetof(struct NODE, field))
 #define EO(name, field) printf("  \"%s\": %zu,\n", name, offsetof(struct extNODE, field))
   NO("n_len", len); NO("n_center", center); NO("n_maxsoft", maxsoft); NO("n_s", u.d.s); NO("n_mass", u.d.mass);

@@ -56,6 +56,8 @@ static int p2p_unreachable(const char *what)
 }
 int MPI_Send(const void *s, int n, MPI_Datatype t, int d, int tag, MPI_Comm c)
 { (void) s; (void) n; (void) t; (void) d; (void) tag; (void) c; return p2p_unreachable("MPI_Send"); }
+int MPI_Ssend(const void *s, int n, MPI_Datatype t, int d, int tag, MPI_Comm c)
+{ (void) s; (void) n; (void) t; (void) d; (void) tag; (void) c; return p2p_unreachable("MPI_Ssend"); }
 int MPI_Recv(void *r, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Status *st)
 { (void) r; (void) n; (void) t; (void) src; (void) tag; (void) c; (void) st; return p2p_unreachable("MPI_Recv"); }
 int MPI_Isend(const void *s, int n, MPI_Datatype t, int d, int tag, MPI_Comm c, MPI_Request *rq)

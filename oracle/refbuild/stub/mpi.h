@@ -38,6 +38,7 @@ int MPI_Reduce(const void *s, void *r, int n, MPI_Datatype t, MPI_Op op, int roo
 int MPI_Sendrecv(const void *s, int ns, MPI_Datatype ts, int dest, int stag, void *r, int nr, MPI_Datatype tr,
                  int src, int rtag, MPI_Comm c, MPI_Status *st);
 int MPI_Send(const void *s, int n, MPI_Datatype t, int dest, int tag, MPI_Comm c);
+int MPI_Ssend(const void *s, int n, MPI_Datatype t, int dest, int tag, MPI_Comm c);
 int MPI_Recv(void *r, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Status *st);
 int MPI_Isend(const void *s, int n, MPI_Datatype t, int dest, int tag, MPI_Comm c, MPI_Request *rq);
 int MPI_Irecv(void *r, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Request *rq);
