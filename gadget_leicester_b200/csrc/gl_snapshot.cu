@@ -323,6 +323,32 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
   return 0;
 }
 
+// the header record alone (read_file reads it first and sizes P[] / SphP[] from it: read_ic.c:688-697, :754-790)
+static int read_header(Ctx &c, FILE *fd, int format, gl_io_header *h)
+{
+  int b1 = 0, b2 = 0, next = 0;
+  char label[4];
+  if(format == 2 && !(get(fd, &b1, 4) && get(fd, label, 4) && get(fd, &next, 4) && get(fd, &b2, 4)))
+    return c.fail("incorrect header format");
+  if(!(get(fd, &b1, 4) && get(fd, h, 256) && get(fd, &b2, 4)) || b1 != 256 || b2 != 256)
+    return c.fail("incorrect header format");	// read_ic.c:699-704 endrun(890)
+  return 0;
+}
+
+extern "C" int gl_snapshot_read_header(const char *fname, int format, gl_io_header *hdr, char *err, int errlen)
+{
+  Ctx c{};
+  c.err = err;
+  c.errlen = errlen;
+  if(err && errlen > 0) err[0] = 0;
+  if(format != 1 && format != 2) return c.fail("gl_snapshot_read_header: format %d is not 1 or 2 (format 3 = HDF5 is not available)", format);
+  FILE *fd = fopen(fname, "rb");
+  if(!fd) return c.fail("can't open file `%s' for reading initial conditions.", fname);
+  const int rc = read_header(c, fd, format, hdr);
+  fclose(fd);
+  return rc;
+}
+
 extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, const gl_io_layout *io, gl_io_params *par, void *Pv,
 				void *SphPv, long long MaxPart, long long MaxPartSph, long long *NumPart, long long *N_gas,
 				gl_io_header *hdr, char *err, int errlen)
@@ -341,11 +367,8 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
 
   int b1 = 0, b2 = 0, next = 0;
   char label[4];
-  if(par->format == 2 && !(get(fd, &b1, 4) && get(fd, label, 4) && get(fd, &next, 4) && get(fd, &b2, 4)))
-    return c.fail("gl_snapshot_read: `%s' ends inside the header label", fname);
   gl_io_header h;
-  if(!(get(fd, &b1, 4) && get(fd, &h, 256) && get(fd, &b2, 4)) || b1 != 256 || b2 != 256)
-    return c.fail("incorrect header format");	// read_ic.c:699-704 endrun(890)
+  if(read_header(c, fd, par->format, &h)) return 1;
   if(h.flag_doubleprecision)	// read_ic.c:744-750
     return c.fail("Problem: Code not compiled with INPUT_IN_DOUBLEPRECISION, but input files are in double precision!");
   if(h.num_files > 1) return c.fail("gl_snapshot_read: `%s' is one of %d files; multi-file snapshots are not supported", fname, h.num_files);

@@ -67,6 +67,16 @@ def write_snapshot(fname, arrays, par, nh=None, sfr=None):
         raise SnapshotError(err.value.decode())
 
 
+def read_header(fname, format=1):
+    """The header record alone (what read_file() sizes the particle storage from, read_ic.c:754-790)."""
+    lib = L.load_library()
+    hdr = L.GLIOHeader()
+    err = C.create_string_buffer(512)
+    if lib.gl_snapshot_read_header(str(fname).encode(), format, C.byref(hdr), err, len(err)):
+        raise SnapshotError(err.value.decode())
+    return hdr
+
+
 def read_snapshot(fname, par, max_part, max_part_sph=None, pinned=False):
     """read_ic(): returns (arrays, header); par.MassTable is updated like All.MassTable.  max_part / max_part_sph play
     All.MaxPart / All.MaxPartSph."""

@@ -301,6 +301,8 @@ int gl_snapshot_write(const char *fname, const gl_gadget_layout * lay, const gl_
  * Non-zero return where the reference calls endrun(): unreadable file, bad header record (890), double-precision
  * file (read_ic.c:744-750), not enough room (172, 173), wrong format-2 label (1890); also for a record whose length does
  * not match the header's particle numbers (the reference reads on regardless) and for multi-file snapshots. */
+/* only the header record - what read_file() looks at before P[] / SphP[] exist (read_ic.c:688-697, :754-790) */
+int gl_snapshot_read_header(const char *fname, int format, gl_io_header * hdr, char *err, int errlen);
 int gl_snapshot_read(const char *fname, const gl_gadget_layout * lay, const gl_io_layout * io, gl_io_params * par, void *P,
 		     void *SphP, long long MaxPart, long long MaxPartSph, long long *NumPart, long long *N_gas,
 		     gl_io_header * hdr, char *err, int errlen);

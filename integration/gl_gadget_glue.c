@@ -57,12 +57,9 @@ static void gl_sync_params(void)
   if(gl_set_params(GL, &p)) gl_fail("gl_set_params");
 }
 
-static void gl_attach(void)
+static void gl_fill_layout(void)
 {
   gl_gadget_layout L;
-  if(GL) return;
-  /* one rank <-> one GPU of the node */
-  if(gl_create(&GL, ThisTask % 8, All.MaxPart)) gl_fail("gl_create");
   L.p_stride = sizeof(struct particle_data);
   L.sph_stride = sizeof(struct sph_particle_data);
   L.p_Pos = offsetof(struct particle_data, Pos);
@@ -100,7 +97,15 @@ static void gl_attach(void)
   L.s_DragAccel = -1;
 #endif
   GL_Layout = L;
-  if(gl_gadget_bind(GL, &L)) gl_fail("gl_gadget_bind");
+}
+
+static void gl_attach(void)
+{
+  if(GL) return;
+  /* one rank <-> one GPU of the node */
+  if(gl_create(&GL, ThisTask % 8, All.MaxPart)) gl_fail("gl_create");
+  gl_fill_layout();
+  if(gl_gadget_bind(GL, &GL_Layout)) gl_fail("gl_gadget_bind");
 }
 
 /* the library evaluates the particles it is told to; the reference's active list is
@@ -264,3 +269,194 @@ void gl_compute_force_path(int mode)
   TreeReconstructFlag = 0;
 }
 #endif
+
+#ifdef GL_SNAPSHOT_IO
+/* ---- read_ic() / savepositions() (proto.h; read_ic.c:28, io.c:33) on the library's reader / writer -----------------
+ * Binary formats 1 and 2, one file, one rank (the library has no HDF5; a multi-rank run keeps the reference's own
+ * read_ic.o / io.o).  Needs no GPU and no context.  The two derived records of a snapshot (NH, SFR) are computed here
+ * with the reference's own cooling / star-formation functions and handed to the writer. */
+#include <math.h>
+#include <string.h>
+#include "cooling.h"
+
+static void gl_io_setup(gl_io_layout * io, gl_io_params * par)
+{
+  int i;
+  memset(par, 0, sizeof(*par));
+  io->p_ID = offsetof(struct particle_data, ID);
+  io->p_DustRadius = io->p_StellarAge = io->p_BH_Mass = io->p_BH_Mdot = io->p_AccDisc_Mass = io->p_BH_Mseed = -1;
+  io->p_NewDensity = io->p_DeltaPhotonMomentum = io->p_OldPhotonMomentum = io->p_BirthPhotonEnergy = -1;
+  io->s_Ne = io->s_accreted_mass = io->s_accreted_momentum = -1;
+#ifdef DUST
+  io->p_DustRadius = offsetof(struct particle_data, DustRadius);
+#endif
+#ifdef STELLARAGE
+  io->p_StellarAge = offsetof(struct particle_data, StellarAge);
+  par->build |= GL_IO_BUILD_STELLARAGE;
+#endif
+#ifdef BLACK_HOLES
+  io->p_BH_Mass = offsetof(struct particle_data, BH_Mass);
+  io->p_BH_Mdot = offsetof(struct particle_data, BH_Mdot);
+  io->p_AccDisc_Mass = offsetof(struct particle_data, AccDisc_Mass);
+  io->p_BH_Mseed = offsetof(struct particle_data, BH_Mseed);
+#ifdef VIRTUAL
+  io->s_accreted_mass = offsetof(struct sph_particle_data, accreted_mass);
+  io->s_accreted_momentum = offsetof(struct sph_particle_data, accreted_momentum);
+#endif
+#ifdef SWALLOWGAS
+  par->build |= GL_IO_BUILD_BH_SWALLOWGAS;
+#endif
+#endif
+#ifdef VIRTUAL
+  io->p_NewDensity = offsetof(struct particle_data, NewDensity);
+  io->p_DeltaPhotonMomentum = offsetof(struct particle_data, DeltaPhotonMomentum);
+  io->p_OldPhotonMomentum = offsetof(struct particle_data, OldPhotonMomentum);
+  io->p_BirthPhotonEnergy = offsetof(struct particle_data, BirthPhotonEnergy);
+#endif
+#ifdef COOLING
+  io->s_Ne = offsetof(struct sph_particle_data, Ne);
+  par->build |= GL_IO_BUILD_COOLING;
+#endif
+#ifdef SFR
+  par->build |= GL_IO_BUILD_SFR;
+#endif
+#ifdef METALS
+  par->build |= GL_IO_BUILD_METALS;
+#endif
+  par->CoolingOn = All.CoolingOn;
+  par->StarformationOn = All.StarformationOn;
+  par->RestartFlag = RestartFlag;
+  par->Ti_Current = All.Ti_Current;
+  par->Timebase_interval = All.Timebase_interval;
+  par->Time = All.Time;
+  for(i = 0; i < 6; i++)
+    par->MassTable[i] = All.MassTable[i];
+  par->MinEgySpec = All.MinEgySpec;
+  par->GammaMinus1 = GAMMA_MINUS1;
+  par->InitGasTemp = All.InitGasTemp;
+  par->BoxSize = All.BoxSize;
+  par->Omega0 = All.Omega0;
+  par->OmegaLambda = All.OmegaLambda;
+  par->HubbleParam = All.HubbleParam;
+}
+
+static void gl_io_fail(const char *what, const char *err, int code)
+{
+  printf("%s: %s\n", what, err);
+  fflush(stdout);
+  endrun(code);
+}
+
+void read_ic(char *fname)
+{
+  gl_io_layout io;
+  gl_io_params par;
+  gl_io_header h;
+  char err[512];
+  long long n = 0, ngas = 0;
+  double u_init, molecular_weight;
+  int i;
+
+  CPU_Step[CPU_MISC] += measure_time();
+  if(NTask > 1 || (All.ICFormat != 1 && All.ICFormat != 2))
+    gl_io_fail("read_ic", "the library reads formats 1 and 2 on a single rank; link the reference's read_ic.o otherwise", 8801);
+  gl_fill_layout();
+  gl_io_setup(&io, &par);
+  par.format = All.ICFormat;
+  NumPart = 0;
+  N_gas = 0;
+  if(gl_snapshot_read_header(fname, All.ICFormat, &h, err, sizeof(err)))
+    gl_io_fail("read_ic", err, 123);
+  /* read_file(): particle storage is sized from the header (read_ic.c:754-790) */
+  All.TotN_gas = (h.num_files <= 1 ? (unsigned int) h.npart[0] : h.npartTotal[0]);
+  for(i = 0, All.TotNumPart = 0; i < 6; i++)
+    All.TotNumPart += (h.num_files <= 1 ? (unsigned int) h.npart[i] : h.npartTotal[i]);
+  All.MaxPart = (int) (All.PartAllocFactor * (All.TotNumPart / NTask));
+  All.MaxPartSph = (int) (All.PartAllocFactor * (All.TotN_gas / NTask));
+#ifdef INHOMOG_GASDISTR_HINT
+  All.MaxPartSph = All.MaxPart;
+#endif
+  allocate_memory();
+  if(RestartFlag >= 2)
+    All.Time = All.TimeBegin = h.time;
+  /* read_ic.c:181-192 */
+  u_init = (1.0 / GAMMA_MINUS1) * (BOLTZMANN / PROTONMASS) * All.InitGasTemp;
+  u_init *= All.UnitMass_in_g / All.UnitEnergy_in_cgs;
+  if(All.InitGasTemp > 1.0e4)
+    molecular_weight = 4 / (8 - 5 * (1 - HYDROGEN_MASSFRAC));
+  else
+    molecular_weight = 4 / (1 + 3 * HYDROGEN_MASSFRAC);
+  u_init /= molecular_weight;
+  All.InitGasU = u_init;
+  par.InitGasU = All.InitGasU;
+  if(gl_snapshot_read(fname, &GL_Layout, &io, &par, P, SphP, All.MaxPart, All.MaxPartSph, &n, &ngas, &h, err, sizeof(err)))
+    gl_io_fail("read_ic", err, 890);
+  NumPart = (int) n;
+  N_gas = (int) ngas;
+  for(i = 0; i < 6; i++)
+    All.MassTable[i] = par.MassTable[i];
+  memcpy(&header, &h, sizeof(header));
+  if(ThisTask == 0)
+    {
+      printf("reading done.\n");
+      printf("Total number of particles :  %d%09d\n\n", (int) (All.TotNumPart / 1000000000), (int) (All.TotNumPart % 1000000000));
+      fflush(stdout);
+    }
+  CPU_Step[CPU_SNAPSHOT] += measure_time();
+}
+
+void savepositions(int num)
+{
+  gl_io_layout io;
+  gl_io_params par;
+  char err[512], buf[500];
+  double *nh = NULL, *sfr = NULL;
+  int i;
+
+  if(ThisTask == 0)
+    printf("\nwriting snapshot file... \n");
+  CPU_Step[CPU_MISC] += measure_time();
+#if defined(SFR) || defined(BLACK_HOLES)
+  rearrange_particle_sequence();
+  /* ensures that new tree will be constructed (io.c:47-49) */
+  All.NumForcesSinceLastDomainDecomp = (long long) (1 + All.TreeDomainUpdateFrequency * All.TotNumPart);
+#endif
+  if(NTask > 1 || All.NumFilesPerSnapshot > 1 || All.SnapFormat < 1 || All.SnapFormat > 2)
+    gl_io_fail("savepositions", "the library writes formats 1 and 2, one file, on a single rank; link the reference's io.o otherwise", 8802);
+  gl_fill_layout();
+  gl_io_setup(&io, &par);
+  par.format = All.SnapFormat;
+#ifdef COOLING
+  if(All.CoolingOn && N_gas > 0)
+    {
+      double ne, nh0, nHeII, dmax1, dmax2;
+      nh = (double *) malloc(sizeof(double) * N_gas);
+      for(i = 0; i < N_gas; i++)
+	{
+	  /* io.c:349-360 (non-comoving: a3inv = 1) */
+	  ne = SphP[i].Ne;
+	  AbundanceRatios(DMAX(All.MinEgySpec, SphP[i].Entropy / GAMMA_MINUS1 * pow(SphP[i].d.Density, GAMMA_MINUS1)),
+			  SphP[i].d.Density, &ne, &nh0, &nHeII);
+	  nh[i] = nh0;
+	}
+    }
+#endif
+#ifdef SFR
+  if(All.StarformationOn && N_gas > 0)
+    {
+      sfr = (double *) malloc(sizeof(double) * N_gas);
+      for(i = 0; i < N_gas; i++)
+	sfr[i] = get_starformation_rate(i);	/* io.c:469-477 */
+    }
+#endif
+  sprintf(buf, "%s%s_%03d", All.OutputDir, All.SnapshotFileBase, num);
+  i = gl_snapshot_write(buf, &GL_Layout, &io, &par, P, SphP, NumPart, nh, sfr, err, sizeof(err));
+  free(nh);
+  free(sfr);
+  if(i)
+    gl_io_fail("savepositions", err, 123);
+  if(ThisTask == 0)
+    printf("done with snapshot.\n");
+  CPU_Step[CPU_SNAPSHOT] += measure_time();
+}
+#endif /* GL_SNAPSHOT_IO */

@@ -10,6 +10,7 @@ from gadget_leicester_b200 import aos, snapshot
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_IO = os.path.join(ROOT, "oracle", "_ref", "ref_io")
+REF_IO_DROPIN = os.path.join(ROOT, "oracle", "_ref", "ref_io_dropin")      # same main, read_ic/savepositions from the glue
 
 P_IO_FIELDS = ("io_p_DustRadius", "io_p_StellarAge", "io_p_BH_Mass", "io_p_BH_Mdot", "io_p_AccDisc_Mass", "io_p_BH_Mseed",
                "io_p_NewDensity", "io_p_DeltaPhotonMomentum", "io_p_OldPhotonMomentum", "io_p_BirthPhotonEnergy")
@@ -53,13 +54,13 @@ def common_args(par):
     return args + ["mt%d=%.17g" % (t, par.MassTable[t]) for t in range(6)]
 
 
-def reference_write(a, par, workdir):
+def reference_write(a, par, workdir, binary=REF_IO):
     """savepositions() of the reference on a's P[] / SphP[] images -> file bytes"""
     lay = aos.layout()
     pf, sf = os.path.join(workdir, "P.img"), os.path.join(workdir, "SphP.img")
     a.P[: a.NumPart * lay["p_stride"]].tofile(pf)
     a.SphP[: max(a.N_gas, 1) * lay["sph_stride"]].tofile(sf)
-    subprocess.run([REF_IO, "W", "p=" + pf, "sph=" + sf, "n=%d" % a.NumPart, "ngas=%d" % a.N_gas, "dir=" + workdir, "base=ref"]
+    subprocess.run([binary, "W", "p=" + pf, "sph=" + sf, "n=%d" % a.NumPart, "ngas=%d" % a.N_gas, "dir=" + workdir, "base=ref"]
                    + common_args(par), check=True, stdout=subprocess.DEVNULL)
     with open(os.path.join(workdir, "ref_000"), "rb") as f:
         return f.read()
@@ -75,8 +76,12 @@ READ_S_SNAP = (("s_Density", np.float64, 1), ("io_s_Ne", np.float64, 1), ("io_s_
 def read_fields(a, restart, cooling=True):
     """the fields a reader sets, as plain arrays (everything else in the structs is left as it was)"""
     out = {}
+    types = a.pview("p_Type", np.int16)
+    only = {"p_Hsml": 0, "io_p_StellarAge": 4, "io_p_BH_Mass": 5, "io_p_BH_Mdot": 5, "io_p_AccDisc_Mass": 5, "io_p_BH_Mseed": 5,
+            "io_p_NewDensity": 3, "io_p_DeltaPhotonMomentum": 3, "io_p_OldPhotonMomentum": 3, "io_p_BirthPhotonEnergy": 3}
     for f, dt, c in READ_P + (READ_P_SNAP if restart == 2 else ()):
-        out[f] = a.pview(f, dt, c).copy()
+        v = a.pview(f, dt, c)
+        out[f] = (v[types == only[f]] if f in only else v).copy()      # a record only reaches the types that carry it
     for f, dt, c in READ_S + (READ_S_SNAP if restart == 2 else ()):
         if f == "io_s_Ne" and not cooling:
             continue
@@ -88,11 +93,11 @@ def read_fields(a, restart, cooling=True):
     return out
 
 
-def reference_read(fname, par, workdir):
+def reference_read(fname, par, workdir, binary=REF_IO):
     """read_ic() of the reference -> (fields dict, meta dict)"""
     lay = aos.layout()
     pf, sf, mf = (os.path.join(workdir, x) for x in ("Pr.img", "SphPr.img", "meta.txt"))
-    subprocess.run([REF_IO, "R", "file=" + str(fname), "p=" + pf, "sph=" + sf, "meta=" + mf] + common_args(par), check=True,
+    subprocess.run([binary, "R", "file=" + str(fname), "p=" + pf, "sph=" + sf, "meta=" + mf] + common_args(par), check=True,
                    stdout=subprocess.DEVNULL)
     meta = {}
     with open(mf) as f:

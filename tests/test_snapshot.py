@@ -91,6 +91,41 @@ def test_reader_initial_gas_temperature_and_floor(tmp_path):
     assert np.all(b.sview("s_Entropy", np.float64)[:6] == meta["InitGasU"])
 
 
+# ---- the reference host with read_ic() / savepositions() taken from integration/gl_gadget_glue.c ----------------
+needs_dropin = pytest.mark.skipif(not (HAVE_REF and os.path.exists(U.REF_IO_DROPIN)),
+                                  reason="oracle/_ref/ref_io_dropin not built (needs /root/reference)")
+
+
+@needs_dropin
+@pytest.mark.parametrize("fmt", [1, 2])
+@pytest.mark.parametrize("cooling,sfr", [(0, 0), (1, 1)])
+def test_glue_savepositions_writes_the_reference_file(tmp_path, fmt, cooling, sfr):
+    a = U.particle_arrays()
+    par = _write_par(fmt, cooling, sfr, (0, 0.5, 0, 0, 0, 0))
+    d1, d2 = tmp_path / "ref", tmp_path / "glue"
+    d1.mkdir()
+    d2.mkdir()
+    assert U.reference_write(a, par, str(d2), binary=U.REF_IO_DROPIN) == U.reference_write(a, par, str(d1))
+
+
+@needs_dropin
+@pytest.mark.parametrize("fmt", [1, 2])
+@pytest.mark.parametrize("restart,temp", [(0, 0.0), (0, 80.0), (2, 0.0)])
+def test_glue_read_ic_fills_the_reference_arrays(tmp_path, fmt, restart, temp):
+    a = U.particle_arrays(zero_u=5)
+    fn, _ = _ours(a, _write_par(fmt, 1, 1, (0, 0.5, 0, 0, 0, 0.75)), tmp_path, "snap")
+    par = snapshot.io_params(format=fmt, CoolingOn=1, StarformationOn=1, RestartFlag=restart, MinEgySpec=0.2, InitGasTemp=temp)
+    d1, d2 = tmp_path / "ref", tmp_path / "glue"
+    d1.mkdir()
+    d2.mkdir()
+    want, meta1 = U.reference_read(fn, par, str(d1))
+    got, meta2 = U.reference_read(fn, par, str(d2), binary=U.REF_IO_DROPIN)
+    assert meta1 == meta2                                     # NumPart, N_gas, totals, MassTable, InitGasU, header
+    assert set(got) == set(want)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+
+
 # ---- anywhere: the files the reference wrote, committed ----------------------------------------------------
 def _golden_arrays(g):
     lay = aos.layout()
