@@ -77,6 +77,16 @@ class GLIOParams(C.Structure):
                 ("OmegaLambda", C.c_double), ("HubbleParam", C.c_double)]
 
 
+class GLTimestepParams(C.Structure):
+    _fields_ = [("Ti_Current", C.c_int), ("TimeBinActive", C.c_int * 32), ("Timebase_interval", C.c_double),
+                ("ErrTolIntAccuracy", C.c_double), ("CourantFac", C.c_double), ("MaxSizeTimestep", C.c_double),
+                ("MinSizeTimestep", C.c_double), ("MinEgySpec", C.c_double), ("GammaMinus1", C.c_double),
+                ("SofteningTable", C.c_double * 6), ("OuterBoundary", C.c_double), ("UnitVelocity_in_cm_per_s", C.c_double),
+                ("FeedBackVelocity", C.c_double), ("SMBHmass", C.c_double), ("InnerBoundary", C.c_double),
+                ("SinkBoundary", C.c_double), ("AccDtBlackHole", C.c_double), ("p_DeltaDustMomentum", C.c_int),
+                ("p_NewDensity", C.c_int)]
+
+
 class GLTreeLayout(C.Structure):
     _fields_ = [("node_stride", C.c_longlong), ("ext_stride", C.c_longlong)] + [(k, C.c_int) for k in (
         "n_len", "n_center", "n_maxsoft", "n_s", "n_mass", "n_bitflags", "n_sibling", "n_nextnode", "n_father", "n_Ti_current",
@@ -93,7 +103,7 @@ EXPORTS = [
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
     "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree", "gl_gadget_drift", "gl_gadget_reorder",
-    "gl_snapshot_write", "gl_snapshot_read", "gl_snapshot_read_header",
+    "gl_snapshot_write", "gl_snapshot_read", "gl_snapshot_read_header", "gl_gadget_advance_and_find_timesteps",
 ]
 
 _lib = None
@@ -163,6 +173,8 @@ def load_library():
                                     C.POINTER(C.c_longlong)]
     lib.gl_snapshot_write.argtypes = [C.c_char_p, C.POINTER(GLGadgetLayout), C.POINTER(GLIOLayout), C.POINTER(GLIOParams), vp, vp,
                                       C.c_longlong, vp, vp, C.c_char_p, C.c_int]
+    lib.gl_gadget_advance_and_find_timesteps.argtypes = [C.POINTER(GLGadgetLayout), C.POINTER(GLTimestepParams), vp, vp, vp,
+                                                         C.c_longlong, vp, C.c_char_p, C.c_int]
     lib.gl_snapshot_read_header.argtypes = [C.c_char_p, C.c_int, C.POINTER(GLIOHeader), C.c_char_p, C.c_int]
     lib.gl_snapshot_read.argtypes = [C.c_char_p, C.POINTER(GLGadgetLayout), C.POINTER(GLIOLayout), C.POINTER(GLIOParams), vp, vp,
                                      C.c_longlong, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),

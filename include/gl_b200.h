@@ -201,6 +201,33 @@ int gl_gadget_drift(const gl_gadget_layout * lay, void *P, void *SphP, long long
  * separately), SphP[] alongside for the gas block.  The reference follows permutation cycles in place, one struct at a
  * time; here all host cores gather from a temporary copy.  Host code only - no context, no GPU. */
 int gl_gadget_reorder(const gl_gadget_layout * lay, void *P, void *SphP, long long NumPart, long long N_gas, const int *order);
+/* Individual time steps: the per-particle part of advance_and_find_timesteps() (timestep.c:29) for
+ * the particles of the active list - get_timestep (timestep.c:607: acceleration, Courant, dust, sink-accretion and
+ * feedback criteria of the shipped -D list), the power-of-two bin with the "only onto a synchronised bin" rule
+ * (timestep.c:136-154), P.TimeBin / P.Ti_begstep, and do_the_kick (timestep.c:364: Vel, VelPred, DragAccel = 0, Entropy
+ * and DtEntropy with their limiters) - in place, on all host cores, with the reference's statements in the reference's
+ * order.  Host code only - no context, no GPU; non-comoving integration, no dynamic tree update (the tree is rebuilt).
+ * What stays with the caller is the serial bookkeeping of the time-bin lists (TimeBinCount[], First/Last/Next/
+ * PrevInTimeBin[], timestep.c:170-233): binold[k] <- the bin particle active[k] had, so the caller relinks exactly the
+ * particles whose P.TimeBin differs from it, in active-list order. */
+typedef struct gl_timestep_params
+{
+  int Ti_Current;		/* All.Ti_Current */
+  int TimeBinActive[32];	/* TimeBinActive[TIMEBINS] */
+  double Timebase_interval, ErrTolIntAccuracy, CourantFac, MaxSizeTimestep, MinSizeTimestep, MinEgySpec;
+  double GammaMinus1;		/* GAMMA_MINUS1 (allvars.h:64-65) */
+  double SofteningTable[6];	/* All.SofteningTable[] */
+  /* fork-specific criteria: Type 3 (virtual particles) and Type 5 (sinks), timestep.c:889-1000 */
+  double OuterBoundary, UnitVelocity_in_cm_per_s, FeedBackVelocity, SMBHmass, InnerBoundary, SinkBoundary, AccDtBlackHole;
+  int p_DeltaDustMomentum;	/* P.DeltaDustMomentum (-DDUST), < 0: the build has none */
+  int p_NewDensity;		/* P.NewDensity (-DVIRTUAL), < 0: the build has none */
+} gl_timestep_params;
+/* Non-zero return where the reference calls endrun(): a step below MinSizeTimestep (888), of integer size 0 or 1 (818,
+ * 112313), beyond the end of the time line (888); also for a Type-3 particle with NewDensity > 0, whose criterion
+ * reads an uninitialised variable in the reference (`rho`, timestep.c:894).  Particles are independent: on error the ones
+ * already processed keep their kick, like in the reference, which aborts. */
+int gl_gadget_advance_and_find_timesteps(const gl_gadget_layout * lay, const gl_timestep_params * par, void *P, void *SphP,
+					 const int *active, long long nactive, int *binold, char *err, int errlen);
 /* scatter results back in place; what = bit mask: 1 gravity, 2 density, 4 hydro */
 int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
 

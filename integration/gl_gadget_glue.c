@@ -160,6 +160,7 @@ static void gl_ensure_loaded(void)
   gl_send_active_list();
 }
 
+#ifndef GL_NO_FORCE_PATH	/* (a build that only takes the host-side pieces below: the CPU test binaries of oracle/refbuild) */
 void gravity_tree(void)
 {
   double t0 = second();
@@ -254,6 +255,8 @@ void hydro_force(void)
   if(gl_gadget_push(GL, P, SphP, 4)) gl_fail("gl_gadget_push");
   CPU_Step[CPU_HYDCOMPUTE] += timediff(t0, second());
 }
+
+#endif /* GL_NO_FORCE_PATH */
 
 #ifdef GL_TAKE_OVER_ACCEL
 /* the whole force part of accel.c:27-106 in one pipelined call; the sub-grid physics that follows in the
@@ -460,3 +463,123 @@ void savepositions(int num)
   CPU_Step[CPU_SNAPSHOT] += measure_time();
 }
 #endif /* GL_SNAPSHOT_IO */
+
+#ifdef GL_TIMESTEP
+/* ---- advance_and_find_timesteps() (proto.h; timestep.c:29) --------------------------------------------------------
+ * The per-particle work - get_timestep, the bin decision, do_the_kick - runs in the library on all host cores
+ * (gl_gadget_advance_and_find_timesteps); what stays here is the reference's serial bookkeeping of the time-bin lists
+ * (timestep.c:170-233), executed for the particles whose bin changed, in active-list order, with the reference's own
+ * statements.  Non-comoving integration without PMGRID / MAKEGLASS (the shipped build); the tree is rebuilt after the
+ * kicks, so no dynamic tree update is prepared (All.DoDynamicUpdate = 0). */
+void advance_and_find_timesteps(void)
+{
+  gl_timestep_params t;
+  char err[512];
+  int i, k, n, bin, binold, prev, next, *act, *old;
+
+  CPU_Step[CPU_MISC] += measure_time();
+  if(All.ComovingIntegrationOn)
+    gl_fail("advance_and_find_timesteps: comoving integration");
+  gl_fill_layout();
+  All.DoDynamicUpdate = 0;
+  t.Ti_Current = All.Ti_Current;
+  for(i = 0; i < 32; i++)
+    t.TimeBinActive[i] = i < TIMEBINS ? TimeBinActive[i] : 0;
+  t.Timebase_interval = All.Timebase_interval;
+  t.ErrTolIntAccuracy = All.ErrTolIntAccuracy;
+  t.CourantFac = All.CourantFac;
+  t.MaxSizeTimestep = All.MaxSizeTimestep;
+  t.MinSizeTimestep = All.MinSizeTimestep;
+  t.MinEgySpec = All.MinEgySpec;
+  t.GammaMinus1 = GAMMA_MINUS1;
+  for(i = 0; i < 6; i++)
+    t.SofteningTable[i] = All.SofteningTable[i];
+  t.OuterBoundary = All.OuterBoundary;
+  t.UnitVelocity_in_cm_per_s = All.UnitVelocity_in_cm_per_s;
+  t.FeedBackVelocity = All.FeedBackVelocity;
+  t.SMBHmass = All.SMBHmass;
+  t.InnerBoundary = All.InnerBoundary;
+  t.SinkBoundary = All.SinkBoundary;
+  t.AccDtBlackHole = All.AccDtBlackHole;
+#ifdef DUST
+  t.p_DeltaDustMomentum = offsetof(struct particle_data, DeltaDustMomentum);
+#else
+  t.p_DeltaDustMomentum = -1;
+#endif
+#ifdef VIRTUAL
+  t.p_NewDensity = offsetof(struct particle_data, NewDensity);
+#else
+  t.p_NewDensity = -1;
+#endif
+  for(i = FirstActiveParticle, n = 0; i >= 0; i = NextActiveParticle[i]) n++;
+  act = (int *) malloc(sizeof(int) * (n > 0 ? n : 1));	/* private scratch: the mymalloc stack stays as found */
+  old = (int *) malloc(sizeof(int) * (n > 0 ? n : 1));
+  for(i = FirstActiveParticle, n = 0; i >= 0; i = NextActiveParticle[i]) act[n++] = i;
+  if(gl_gadget_advance_and_find_timesteps(&GL_Layout, &t, P, SphP, act, n, old, err, sizeof(err)))
+    {
+      printf("%s\n", err);
+      fflush(stdout);
+      endrun(888);
+    }
+  for(k = 0; k < n; k++)
+    {
+      i = act[k];
+      binold = old[k];
+      bin = P[i].TimeBin;
+      if(bin == binold) continue;
+      /* timestep.c:170-233 */
+      TimeBinCount[binold]--;
+      if(P[i].Type == 0)
+	{
+	  TimeBinCountSph[binold]--;
+#ifdef SFR
+	  TimeBinSfr[binold] -= SphP[i].Sfr;
+	  TimeBinSfr[bin] += SphP[i].Sfr;
+#endif
+	}
+#ifdef BLACK_HOLES
+      if(P[i].Type == 5)
+	{
+#ifndef DUST
+	  TimeBin_BH_mass[binold] -= P[i].BH_Mass;
+	  TimeBin_BH_dynamicalmass[binold] -= P[i].Mass;
+	  TimeBin_BH_Mdot[binold] -= P[i].BH_Mdot;
+	  TimeBin_BH_mass[bin] += P[i].BH_Mass;
+	  TimeBin_BH_dynamicalmass[bin] += P[i].Mass;
+	  TimeBin_BH_Mdot[bin] += P[i].BH_Mdot;
+#else
+	  TimeBin_BH_mass[binold] -= P[i].Dust_Mass;
+	  TimeBin_BH_dynamicalmass[binold] -= P[i].Total_Mass;
+	  TimeBin_BH_Mdot[binold] -= P[i].Mass;
+	  TimeBin_BH_mass[bin] += P[i].Dust_Mass;
+	  TimeBin_BH_dynamicalmass[bin] += P[i].Total_Mass;
+	  TimeBin_BH_Mdot[bin] += P[i].Mass;
+#endif
+	}
+#endif
+      prev = PrevInTimeBin[i];
+      next = NextInTimeBin[i];
+      if(FirstInTimeBin[binold] == i) FirstInTimeBin[binold] = next;
+      if(LastInTimeBin[binold] == i) LastInTimeBin[binold] = prev;
+      if(prev >= 0) NextInTimeBin[prev] = next;
+      if(next >= 0) PrevInTimeBin[next] = prev;
+      if(TimeBinCount[bin] > 0)
+	{
+	  PrevInTimeBin[i] = LastInTimeBin[bin];
+	  NextInTimeBin[LastInTimeBin[bin]] = i;
+	  NextInTimeBin[i] = -1;
+	  LastInTimeBin[bin] = i;
+	}
+      else
+	{
+	  FirstInTimeBin[bin] = LastInTimeBin[bin] = i;
+	  PrevInTimeBin[i] = NextInTimeBin[i] = -1;
+	}
+      TimeBinCount[bin]++;
+      if(P[i].Type == 0) TimeBinCountSph[bin]++;
+    }
+  free(act);
+  free(old);
+  CPU_Step[CPU_TIMELINE] += measure_time();
+}
+#endif /* GL_TIMESTEP */

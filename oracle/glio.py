@@ -19,6 +19,7 @@ P_TIMEBASE_INTERVAL = P_MINGASHSMLFRAC + 1
 P_TI_CURRENT = P_TIMEBASE_INTERVAL + 1
 P_BHNGBFACTOR = P_TI_CURRENT + 1
 P_PARTALLOC = P_BHNGBFACTOR + 1
+P_MINEGYSPEC = P_PARTALLOC + 1
 
 
 def pack_params(p):
@@ -37,6 +38,7 @@ def pack_params(p):
     par[P_TI_CURRENT] = p["Ti_Current"]
     par[P_BHNGBFACTOR] = p["BlackHoleNgbFactor"]
     par[P_PARTALLOC] = p.get("PartAllocFactor", 1.2)
+    par[P_MINEGYSPEC] = p.get("MinEgySpec", 0.0)
     return par
 
 

@@ -27,6 +27,7 @@ int main(void)
   PO("io_p_AccDisc_Mass", AccDisc_Mass); PO("io_p_BH_Mseed", BH_Mseed); PO("io_p_NewDensity", NewDensity);
   PO("io_p_DeltaPhotonMomentum", DeltaPhotonMomentum); PO("io_p_OldPhotonMomentum", OldPhotonMomentum);
   PO("io_p_BirthPhotonEnergy", BirthPhotonEnergy);
+  PO("ts_p_DeltaDustMomentum", DeltaDustMomentum);	/* get_timestep / do_the_kick, timestep.c:686, :459 */
   SO("io_s_Ne", Ne); SO("io_s_accreted_mass", accreted_mass); SO("io_s_accreted_momentum", accreted_momentum);
   printf("  \"io_sizeof_ID\": %zu,\n  \"io_sizeof_header\": %zu,\n", sizeof(MyIDType), sizeof(struct io_header));
 #define NO(name, field) printf("  \"%s\": %zu,\n", name, offsetof(struct NODE, field))

@@ -24,6 +24,8 @@
  *     P  compute_potential()                  (potential.c:22; run.c:74 at statistics times)
  *     K  Peano-Hilbert and Morton key of every particle (peano_and_morton_key, peano.c:335)
  *     A  compute_accelerations-order block:  R G D U H   (accel.c:61-106 without sub-grid physics)
+ *     V  advance_and_find_timesteps()         (timestep.c:29) at a synchronisation point of an individual-time-step
+ *        state built from the input's time bins; dumps everything it reads and everything it leaves behind
  *   every op that computes dumps its outputs under the prefix "<k>_<op>_" with k the
  *   position in the list.
  */
@@ -44,6 +46,7 @@ double get_hydrokick_factor(int t0, int t1) { (void) t0; (void) t1; return 0; }
 double hubble_function(double a) { (void) a; return 0; }
 size_t my_fwrite(void *ptr, size_t size, size_t nmemb, FILE * stream) { return fwrite(ptr, size, nmemb, stream); }
 void rearrange_particle_sequence(void) { /* no Mass==0 particles in harness inputs (sfr_eff.c:1018) */ }
+int ShouldWeDoDynamicUpdate(void) { return 0; }	/* run.c:345: the tree is rebuilt every step */
 static unsigned long long lcg_state = 42;
 double gsl_rng_uniform(gsl_rng * r)
 {
@@ -76,7 +79,7 @@ static double now(void)
 #define NPAR 32
 static double par[NPAR];
 enum { P_THETA, P_ERRTOLFORCEACC, P_OPENCRIT, P_DESNUMNGB, P_MAXNGBDEV, P_ARTVISC, P_G, P_SOFT0,
-  P_MINGASHSMLFRAC = P_SOFT0 + 6, P_TIMEBASE_INTERVAL, P_TI_CURRENT, P_BHNGBFACTOR, P_PARTALLOC
+  P_MINGASHSMLFRAC = P_SOFT0 + 6, P_TIMEBASE_INTERVAL, P_TI_CURRENT, P_BHNGBFACTOR, P_PARTALLOC, P_MINEGYSPEC
 };
 
 static void dump_particles_out(const char *prefix, int what)
@@ -159,6 +162,33 @@ static void dump_drift_state(const char *prefix, const char *tag)
   PUT3("VelPred", SphP[i].VelPred, ng); PUT3("HydroAccel", SphP[i].a.HydroAccel, ng); PUT3("DragAccel", SphP[i].da.DragAccel, ng);
   PUT1("DivVel", SphP[i].v.DivVel, ng); PUT1("Density", SphP[i].d.Density, ng); PUT1("Entropy", SphP[i].Entropy, ng);
   PUT1("DtEntropy", SphP[i].e.DtEntropy, ng); PUT1("Pressure", SphP[i].Pressure, ng);
+#undef PUT3
+#undef PUT1
+#undef PUTI
+  free(d3); free(d1); free(i1);
+}
+
+/* everything advance_and_find_timesteps (timestep.c:29 -> get_timestep :607, do_the_kick :364) reads or writes */
+static void dump_kick_state(const char *prefix, const char *tag)
+{
+  long long n = NumPart, ng = N_gas, i;
+  double *d3 = malloc(sizeof(double) * 3 * n), *d1 = malloc(sizeof(double) * n);
+  int *i1 = malloc(sizeof(int) * n);
+  char nm[40];
+#define PUT3(field, expr, cnt) do { for(i = 0; i < (cnt); i++) { d3[3 * i] = expr[0]; d3[3 * i + 1] = expr[1]; d3[3 * i + 2] = expr[2]; } \
+    snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'd', (cnt), 3, d3); } while(0)
+#define PUT1(field, expr, cnt) do { for(i = 0; i < (cnt); i++) d1[i] = expr; snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'd', (cnt), 1, d1); } while(0)
+#define PUTI(field, expr, cnt) do { for(i = 0; i < (cnt); i++) i1[i] = expr; snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'i', (cnt), 1, i1); } while(0)
+  PUTI("id", (int) P[i].ID, n); PUTI("Type", P[i].Type, n); PUTI("TimeBin", P[i].TimeBin, n); PUTI("Ti_begstep", P[i].Ti_begstep, n);
+  PUT3("Pos", P[i].Pos, n); PUT3("Vel", P[i].Vel, n); PUT3("GravAccel", P[i].g.GravAccel, n); PUT3("DeltaDustMomentum", P[i].DeltaDustMomentum, n);
+  PUT1("Mass", P[i].Mass, n); PUT1("Hsml", P[i].Hsml, n); PUT1("NewDensity", P[i].NewDensity, n);
+  PUT3("VelPred", SphP[i].VelPred, ng); PUT3("HydroAccel", SphP[i].a.HydroAccel, ng); PUT3("DragAccel", SphP[i].da.DragAccel, ng);
+  PUT1("Density", SphP[i].d.Density, ng); PUT1("Entropy", SphP[i].Entropy, ng); PUT1("DtEntropy", SphP[i].e.DtEntropy, ng);
+  PUT1("Pressure", SphP[i].Pressure, ng); PUT1("MaxSignalVel", SphP[i].MaxSignalVel, ng);
+  PUTI("NextInTimeBin", NextInTimeBin[i], n); PUTI("PrevInTimeBin", PrevInTimeBin[i], n);
+  PUTI("TimeBinCount", TimeBinCount[i], TIMEBINS); PUTI("TimeBinCountSph", TimeBinCountSph[i], TIMEBINS);
+  PUTI("FirstInTimeBin", FirstInTimeBin[i], TIMEBINS); PUTI("LastInTimeBin", LastInTimeBin[i], TIMEBINS);
+  PUTI("TimeBinActive", TimeBinActive[i], TIMEBINS);
 #undef PUT3
 #undef PUT1
 #undef PUTI
@@ -444,6 +474,56 @@ int main(int argc, char **argv)
 		All.Ti_Current = t1;
 		for(i = 0; i < NumPart; i++) drift_particle(i, All.Ti_Current);
 		dump_drift_state(prefix, "post");
+	      }
+	      break;
+	    case 'V':
+	      /* advance_and_find_timesteps (timestep.c:29) at the synchronisation point Ti_Current = 64 of an individual-time-
+	         step state: a particle on bin b (1..6, from the input) began its step at 64 - 2^b; bins above 6 are not
+	         synchronised there, so a particle that wants a longer step than 64 has to stay where it is (timestep.c:147-154) */
+	      {
+		int k, nact = 0;
+		double q[20];
+		All.Ti_Current = 64;
+		All.ErrTolIntAccuracy = 0.025; All.CourantFac = 0.15; All.TypeOfTimestepCriterion = 0;
+		All.MaxSizeTimestep = 200 * All.Timebase_interval; All.MinSizeTimestep = 0;
+		All.MinEgySpec = par[P_MINEGYSPEC];
+		All.OuterBoundary = 1.4e10; All.UnitVelocity_in_cm_per_s = 2.98e6; All.FeedBackVelocity = 1.0;
+		All.SMBHmass = 0.5; All.InnerBoundary = 2.0e-2; All.SinkBoundary = 1.0e-4; All.AccDtBlackHole = 0.007;
+		for(i = 0; i < NumPart; i++)
+		  {
+		    int b = P[i].TimeBin < 1 ? 1 : (P[i].TimeBin > 6 ? 6 : P[i].TimeBin);
+		    P[i].TimeBin = b;
+		    P[i].Ti_begstep = All.Ti_Current - (1 << b);
+		    P[i].Ti_current = All.Ti_Current;
+		    if(i % 5 == 0)
+		      for(k = 0; k < 3; k++) P[i].DeltaDustMomentum[k] = 1.0e-3 * P[i].Mass * P[i].g.GravAccel[(k + 2) % 3];
+		  }
+		for(i = 0; i < N_gas; i++)
+		  {
+		    for(k = 0; k < 3; k++) SphP[i].da.DragAccel[k] = 0.01 * SphP[i].a.HydroAccel[(k + 1) % 3];
+		    /* strong cooling for every seventh particle: both entropy limiters of do_the_kick (timestep.c:546-583) */
+		    if(i % 7 == 0) SphP[i].e.DtEntropy = -50 * fabs(SphP[i].e.DtEntropy) - 1.0;
+		  }
+		for(i = 0; i < TIMEBINS; i++) TimeBinActive[i] = (i <= 6);
+		reconstruct_timebins();
+		for(i = FirstActiveParticle; i >= 0; i = NextActiveParticle[i]) nact++;
+		Flag_FullStep = 1;
+		q[0] = All.Ti_Current; q[1] = All.Timebase_interval; q[2] = All.ErrTolIntAccuracy; q[3] = All.CourantFac;
+		q[4] = All.MaxSizeTimestep; q[5] = All.MinSizeTimestep; q[6] = All.MinEgySpec; q[7] = All.OuterBoundary;
+		q[8] = All.UnitVelocity_in_cm_per_s; q[9] = All.FeedBackVelocity; q[10] = All.SMBHmass; q[11] = All.InnerBoundary;
+		q[12] = All.SinkBoundary; q[13] = All.AccDtBlackHole; q[14] = nact;
+		for(k = 0; k < 6; k++) q[15 + k < 20 ? 15 + k : 19] = 0;
+		put(prefix, "params", 'd', 15, 1, q);
+		put(prefix, "SofteningTable", 'd', 6, 1, All.SofteningTable);
+		{
+		  int *act = malloc(sizeof(int) * (nact + 1));
+		  for(i = FirstActiveParticle, k = 0; i >= 0; i = NextActiveParticle[i]) act[k++] = i;
+		  put(prefix, "active", 'i', nact, 1, act);
+		  free(act);
+		}
+		dump_kick_state(prefix, "pre");
+		advance_and_find_timesteps();
+		dump_kick_state(prefix, "post");
 	      }
 	      break;
 	    case 'N': dump_nodes(prefix); break;

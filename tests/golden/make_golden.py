@@ -116,6 +116,53 @@ def drift_fixture():
     print("drift fixture ->", os.path.getsize(path) // 1024, "KiB", sorted(out)[:6], "...")
 
 
+def _kick_set():
+    """1500 gas particles on individual time bins with entropy rates, plus 40 particles of the types the time-step
+    code treats specially: 1 (plain), 2 (dust: no gravity kick, half the step), 4, 5 (sinks: accretion time step)."""
+    n_gas, extra = 1500, 40
+    ps = ics.cube(n_gas, seed=31)
+    g = np.random.Generator(np.random.Philox(key=32))
+    n = n_gas + extra
+    out = {}
+    out["pos"] = np.vstack([ps["pos"], g.random((extra, 3))])
+    out["vel"] = np.vstack([ps["vel"] * 200.0, g.standard_normal((extra, 3)) * 0.1])
+    out["mass"] = np.concatenate([ps["mass"], g.random(extra) * 0.002 + 1e-4])
+    out["mass"][n_gas + 3] = 0.6            # one sink above All.SMBHmass = 0.5: the InnerBoundary branch
+    out["type"] = np.concatenate([ps["type"], np.array([1, 2, 4, 5] * (extra // 4))]).astype(np.int32)
+    out["hsml"] = np.zeros(n)
+    out["id"] = np.arange(1, n + 1, dtype=np.int32)
+    out["timebin"] = g.integers(1, 7, size=n).astype(np.int32)
+    out["oldacc"] = np.zeros(n)
+    out["entropy"] = np.concatenate([ps["entropy"], np.zeros(extra)])
+    out["dtentropy"] = np.concatenate([(g.random(n_gas) - 0.5) * 40.0, np.zeros(extra)])
+    return out
+
+
+def kick_run(binary):
+    """A settled force evaluation, then harness op V (advance_and_find_timesteps); returns the op's dump."""
+    ps = _kick_set()
+    par = ics.default_params(Ti_Current=16, MinEgySpec=1.8)
+    par["Timebase_interval"] = 4.0e-5
+    par["PartAllocFactor"] = 20.0
+    ref = util.run_oracle(binary, ps, par, "T S D R G D U H V")
+    return {k[len("8_V_"):]: v for k, v in ref.items() if k.startswith("8_V_")}
+
+
+def kick_fixture():
+    """State before / after the reference's own advance_and_find_timesteps (timestep.c:29) for tests/test_timestep.py."""
+    out = kick_run(util.REF_HARNESS)
+    os.makedirs(os.path.join(HERE, "aux"), exist_ok=True)
+    path = os.path.join(HERE, "aux", "kick_mixed_1540.npz")
+    np.savez_compressed(path, **out)
+    old, new = out["pre_TimeBin"], out["post_TimeBin"]
+    print("kick fixture ->", os.path.getsize(path) // 1024, "KiB; bins before", np.bincount(old, minlength=10)[:10],
+          "after", np.bincount(new, minlength=10)[:10], "changed", int((old != new).sum()))
+
+
 if __name__ == "__main__":
-    main()
-    drift_fixture()
+    if len(sys.argv) > 1 and sys.argv[1] == "kick":
+        kick_fixture()
+    else:
+        main()
+        drift_fixture()
+        kick_fixture()
