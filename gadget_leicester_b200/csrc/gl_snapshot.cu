@@ -14,9 +14,20 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <time.h>
+#include <unistd.h>
 
 namespace
 {
+double gl_now()
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
 enum Block
 {
   B_POS, B_VEL, B_ID, B_MASS, B_U, B_RHO, B_NE, B_NH, B_HSML, B_DUST, B_SFR, B_AGE, B_BHMASS, B_BHMDOT, B_ACCDISCMASS, B_BHMSEED,
@@ -216,18 +227,8 @@ inline void value_in(const Ctx &c, Block b, char *P, char *S, long long i, int t
     }
 }
 
-bool put(FILE *fd, const void *p, size_t bytes) { return fwrite(p, 1, bytes, fd) == bytes; }
 bool get(FILE *fd, void *p, size_t bytes) { return fread(p, 1, bytes, fd) == bytes; }
-bool put_int(FILE *fd, int v) { return put(fd, &v, 4); }
 
-// the format-2 record that precedes every data record: [8] LABEL nextblock [8] (io.c:2634-2642, :2672-2680)
-bool put_label(FILE *fd, const char *label, long long payload)
-{
-  const int next = (int) (payload + 8);
-  return put_int(fd, 8) && put(fd, label, 4) && put_int(fd, next) && put_int(fd, 8);
-}
-
-const long long CHUNK = 1 << 20;	// particles converted per fwrite / fread
 }				// namespace
 
 extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay, const gl_io_layout *io, const gl_io_params *par,
@@ -239,14 +240,36 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
   if(par->format != 1 && par->format != 2) return c.fail("gl_snapshot_write: format %d is not 1 or 2 (format 3 = HDF5 is not available)", par->format);
   const char *P = (const char *) Pv, *S = (const char *) SphPv;
 
-  // particle indices per type, in P[] order (fill_write_buffer scans P[] for Type == type, io.c:212-216)
+  const double T0 = gl_now();
+  // particle indices per type, in P[] order (fill_write_buffer scans P[] for Type == type, io.c:212-216): every work
+  // item lists its own stretch, the stretches are joined in order
   std::vector<long long> idx[6];
-  for(long long i = 0; i < NumPart; i++)
-    {
-      const int t = *(const short *) (P + i * c.L.p_stride + c.L.p_Type);
-      if(t < 0 || t > 5) return c.fail("gl_snapshot_write: particle %lld has Type %d", i, t);
-      idx[t].push_back(i);
-    }
+  {
+    const long long STRETCH = 65536, nst = (NumPart + STRETCH - 1) / STRETCH;
+    std::vector<std::vector<long long> > part((size_t) (nst * 6));
+    std::atomic<long long> badtype{-1};
+    HostPool::get().run(NumPart, STRETCH, [&](long long k, long long lo, long long hi) {
+      for(long long i = lo; i < hi; i++)
+	{
+	  const int t = *(const short *) (P + i * c.L.p_stride + c.L.p_Type);
+	  if(t < 0 || t > 5)
+	    {
+	      badtype.store(i);
+	      return;
+	    }
+	  part[(size_t) (k * 6 + t)].push_back(i);
+	}
+    });
+    if(badtype.load() >= 0) return c.fail("gl_snapshot_write: particle %lld has a Type outside 0..5", badtype.load());
+    for(int t = 0; t < 6; t++)
+      {
+	size_t tot = 0;
+	for(long long k = 0; k < nst; k++) tot += part[(size_t) (k * 6 + t)].size();
+	idx[t].reserve(tot);
+	for(long long k = 0; k < nst; k++) idx[t].insert(idx[t].end(), part[(size_t) (k * 6 + t)].begin(), part[(size_t) (k * 6 + t)].end());
+      }
+  }
+  const double T1 = gl_now();
   gl_io_header h;
   memset(&h, 0, sizeof(h));
   static_assert(sizeof(gl_io_header) == 256, "struct io_header is 256 bytes (allvars.h:1733)");
@@ -273,14 +296,32 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
   h.HubbleParam = par->HubbleParam;
   h.flag_doubleprecision = 0;
 
-  FILE *fd = fopen(fname, "wb");
-  if(!fd) return c.fail("can't open file `%s' for writing snapshot.", fname);	// io.c:2626-2630 endrun(123)
-  bool ok = true;
-  if(par->format == 2) ok = ok && put_label(fd, "HEAD", 256);
-  ok = ok && put_int(fd, 256) && put(fd, &h, 256) && put_int(fd, 256);
-
-  std::vector<float> buf;
-  for(int r = 0; r < B_COUNT && ok; r++)
+  // Where everything goes is known before a byte is written: lay the file out first, then fill the payloads with ONE
+  // sweep over the structs - a chunk of particles is converted for all its records while its cache lines are hot
+  // (the reference makes one pass over P[] per record) - and write every piece at its offset.
+  struct Piece
+  {
+    int row;
+    long long off;		// file offset of this type's part of the record
+  };
+  std::vector<Piece> pieces[6];
+  std::vector<std::pair<long long, int> > marks;	// (offset, value) of the 4-byte record markers
+  std::vector<std::pair<long long, const char *> > labels;	// format 2
+  long long off = 0;
+  auto label_at = [&](const char *label, long long payload) {	// [8] LABEL nextblock [8] (io.c:2634-2642, :2672-2680)
+    marks.push_back({off, 8});
+    labels.push_back({off + 4, label});
+    marks.push_back({off + 8, (int) (payload + 8)});
+    marks.push_back({off + 12, 8});
+    off += 16;
+  };
+  if(par->format == 2) label_at("HEAD", 256);
+  const long long header_off = off + 4;
+  marks.push_back({off, 256});
+  marks.push_back({off + 4 + 256, 256});
+  off += 4 + 256 + 4;
+  long long accmom_off = -1;
+  for(int r = 0; r < B_COUNT; r++)
     {
       const BlockRow &row = ROWS[r];
       if(!present(c, row.b)) continue;
@@ -289,37 +330,101 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
       if(npart <= 0) continue;
       const long long bytes = npart * row.ncomp * 4;
       if(bytes + 8 > 0x7fffffffLL)
-	{
-	  fclose(fd);
-	  return c.fail("gl_snapshot_write: record %s needs %lld bytes, more than a 4-byte record marker holds", row.label, bytes);
-	}
-      if(par->format == 2) ok = ok && put_label(fd, row.label, bytes);
-      ok = ok && put_int(fd, (int) bytes);
-      for(int t = 0; t < 6 && ok; t++)
-	{
-	  if(!typelist[t]) continue;
-	  const std::vector<long long> &ix = idx[t];
-	  for(long long a = 0; a < (long long) ix.size() && ok; a += CHUNK)
-	    {
-	      const long long m = std::min<long long>(CHUNK, (long long) ix.size() - a);
-	      buf.resize((size_t) (m * row.ncomp));
-	      float *out = buf.data();
-	      const long long *src = ix.data() + a;
-	      const int nc = row.ncomp;
-	      const Block b = row.b;
-	      HostPool::get().run(m, 8192, [&, out, src, nc, b, a](long long, long long lo, long long hi) {
-		if(b == B_ACCMOM)
-		  for(long long k = lo; k < hi; k++) out[k] = accmom_slot(c, S, ix, a + k);
-		else
-		  for(long long k = lo; k < hi; k++) value_out(c, b, P, S, src[k], nh, sfr, out + k * nc);
-	      });
-	      ok = ok && put(fd, out, (size_t) (m * nc * 4));
-	    }
-	}
-      ok = ok && put_int(fd, (int) bytes);
+	return c.fail("gl_snapshot_write: record %s needs %lld bytes, more than a 4-byte record marker holds", row.label, bytes);
+      if(par->format == 2) label_at(row.label, bytes);
+      marks.push_back({off, (int) bytes});
+      off += 4;
+      for(int t = 0; t < 6; t++)
+	if(typelist[t])
+	  {
+	    if(row.b == B_ACCMOM)
+	      accmom_off = off;	// gas only; written by slot, see the table
+	    else
+	      pieces[t].push_back({r, off});
+	    off += (long long) h.npart[t] * row.ncomp * 4;
+	  }
+      marks.push_back({off, (int) bytes});
+      off += 4;
     }
-  if(fclose(fd) != 0) ok = false;
-  if(!ok) return c.fail("gl_snapshot_write: I/O error on `%s'", fname);	// my_fwrite io.c:2988 endrun(777)
+
+  // The file is assembled in place: it is given its final length and mapped, and every work item converts its particles
+  // straight into the mapping (concurrent write() calls on one file would queue on the inode lock).  Where the file
+  // cannot be mapped (a pipe, an odd file system) the image is built in memory and written in one call.
+  const long long total = off;
+  const int fd = open(fname, O_RDWR | O_CREAT | O_TRUNC, 0644);
+  if(fd < 0) return c.fail("can't open file `%s' for writing snapshot.", fname);	// io.c:2626-2630 endrun(123)
+  std::atomic<int> bad{0};
+  char *image = nullptr;
+  bool mapped = false;
+  if(ftruncate(fd, (off_t) total) == 0)
+    {
+      void *m = mmap(nullptr, (size_t) total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if(m != MAP_FAILED)
+	{
+	  image = (char *) m;
+	  mapped = true;
+	}
+    }
+  if(!image) image = (char *) malloc((size_t) total);
+  if(!image)
+    {
+      close(fd);
+      return c.fail("gl_snapshot_write: no memory for a %lld-byte file image", total);
+    }
+  memcpy(image + header_off, &h, 256);
+  for(auto &m : marks) memcpy(image + m.first, &m.second, 4);
+  for(auto &l : labels) memcpy(image + l.first, l.second, 4);
+
+  const double T2 = gl_now();
+  const long long FUSE = 1024;	// particles per work item: 0.8 MB of structs, which stay in L2 across the 22 records
+  for(int t = 0; t < 6; t++)
+    {
+      const std::vector<long long> &ix = idx[t];
+      const std::vector<Piece> &pc = pieces[t];
+      if(ix.empty() || pc.empty()) continue;
+      HostPool::get().run((long long) ix.size(), FUSE, [&](long long, long long lo, long long hi) {
+	for(const Piece &q : pc)
+	  {
+	    const BlockRow &row = ROWS[q.row];
+	    float *out = (float *) (image + q.off) + lo * row.ncomp;
+	    for(long long k = lo; k < hi; k++, out += row.ncomp) value_out(c, row.b, P, S, ix[(size_t) k], nh, sfr, out);
+	  }
+      });
+    }
+  if(accmom_off >= 0)
+    {
+      const std::vector<long long> &gas = idx[0];
+      float *out = (float *) (image + accmom_off);
+      HostPool::get().run((long long) gas.size(), FUSE, [&](long long, long long lo, long long hi) {
+	for(long long k = lo; k < hi; k++) out[k] = accmom_slot(c, S, gas, k);
+      });
+    }
+  const double T3 = gl_now();
+  if(mapped)
+    {
+      if(munmap(image, (size_t) total) != 0) bad.store(1);
+    }
+  else
+    {
+      const char *q = image;
+      long long left = total, where = 0;
+      while(left > 0)
+	{
+	  const ssize_t w = pwrite(fd, q, (size_t) left, (off_t) where);
+	  if(w <= 0)
+	    {
+	      bad.store(1);	// my_fwrite io.c:2988 endrun(777)
+	      break;
+	    }
+	  q += w;
+	  where += w;
+	  left -= w;
+	}
+      free(image);
+    }
+  if(close(fd) != 0) bad.store(1);
+  if(getenv("GL_DEBUG_IO")) fprintf(stderr, "snapshot_write: index %.2f ms, layout+open %.2f ms, payload %.2f ms, close %.2f ms\n", (T1 - T0) * 1e3, (T2 - T1) * 1e3, (T3 - T2) * 1e3, (gl_now() - T3) * 1e3);
+  if(bad.load()) return c.fail("gl_snapshot_write: I/O error on `%s'", fname);
   return 0;
 }
 
@@ -391,7 +496,17 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
   if(nall > MaxPart)		// read_ic.c:864-869 endrun(173)
     return c.fail("Not enough space (space for %lld, need at least %lld)", MaxPart, nall);
 
-  std::vector<float> buf;
+  // Pass 1 (serial, a few reads): walk the record structure - labels, lengths - and note where every type's part of
+  // every record lies.  Pass 2: map the file and let every work item fill ALL fields of its particles in one go, so
+  // that P[] / SphP[] are swept once instead of once per record; the per-particle rules that follow the records in
+  // read_ic() (mass table, InitGasU, MinEgySpec) ride along.
+  struct Piece
+  {
+    int row;
+    long long off;
+  };
+  std::vector<Piece> pieces[6];
+  long long accmom_off = -1;
   for(int r = 0; r < B_COUNT; r++)
     {
       const BlockRow &row = ROWS[r];
@@ -411,57 +526,70 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
       if(!get(fd, &b1, 4)) return c.fail("gl_snapshot_read: `%s' ends before record %s", fname, row.label);
       if(b1 != (int) bytes)
 	return c.fail("gl_snapshot_read: record %s holds %d bytes, the header's particle numbers need %lld", row.label, b1, bytes);
+      long long off = (long long) ftello(fd);
       for(int t = 0; t < 6; t++)
-	{
-	  if(!typelist[t]) continue;
-	  for(long long a = 0; a < h.npart[t]; a += CHUNK)
-	    {
-	      const long long m = std::min<long long>(CHUNK, h.npart[t] - a);
-	      buf.resize((size_t) (m * row.ncomp));
-	      if(!get(fd, buf.data(), (size_t) (m * row.ncomp * 4)))	// my_fread io.c:3005 endrun(778)
-		return c.fail("I/O error (fread) on `%s' inside record %s", fname, row.label);
-	      const float *in = buf.data();
-	      const long long base = first[t] + a;
-	      const int nc = row.ncomp;
-	      const Block b = row.b;
-	      HostPool::get().run(m, 8192, [&, in, base, nc, b, t, a](long long, long long lo, long long hi) {
-		if(b == B_ACCMOM)
-		  {
-		    // the values the record really holds; the reference goes on to fill the momenta of the remaining
-		    // particles from whatever its I/O buffer held before (read_ic.c:555-562) - those are left untouched
-		    for(long long k = lo; k < hi; k++)
-		      ((double *) (S + (first[t] + (a + k) / 3) * c.L.sph_stride + c.IO.s_accreted_momentum))[(a + k) % 3] = in[k];
-		  }
-		else
-		  for(long long k = lo; k < hi; k++) value_in(c, b, P, S, base + k, t, in + k * nc);
-	      });
-	    }
-	}
-      if(!get(fd, &b2, 4) || b2 != b1) return c.fail("gl_snapshot_read: record %s is not closed by its length", row.label);
+	if(typelist[t])
+	  {
+	    if(row.b == B_ACCMOM)
+	      accmom_off = off;
+	    else
+	      pieces[t].push_back({r, off});
+	    off += (long long) h.npart[t] * row.ncomp * 4;
+	  }
+      if(fseeko(fd, (off_t) off, SEEK_SET) != 0 || !get(fd, &b2, 4) || b2 != b1)	// my_fread io.c:3005 endrun(778)
+	return c.fail("gl_snapshot_read: record %s is cut short or not closed by its length (I/O error on `%s')", row.label, fname);
     }
-
-  // read_ic.c:106-111: "this makes sure that masses are initialized in the case that the mass-block is completely empty"
-  for(long long i = 0; i < nall; i++)
+  const long long used = (long long) ftello(fd);
+  const char *image = nullptr;
+  std::vector<char> copy;
+  void *mapping = mmap(nullptr, (size_t) used, PROT_READ, MAP_PRIVATE, fileno(fd), 0);
+  if(mapping != MAP_FAILED)
+    image = (const char *) mapping;
+  else
     {
-      const int t = *(const short *) (P + i * c.L.p_stride + c.L.p_Type);
-      if(par->MassTable[t] != 0) *(double *) (P + i * c.L.p_stride + c.L.p_Mass) = par->MassTable[t];
+      copy.resize((size_t) used);
+      if(fseeko(fd, 0, SEEK_SET) != 0 || !get(fd, copy.data(), (size_t) used)) return c.fail("I/O error (fread) on `%s'", fname);
+      image = copy.data();
     }
+  const bool ic_rules = par->RestartFlag == 0 && par->InitGasTemp > 0;	// read_ic.c:196-210
+  for(int t = 0; t < 6; t++)
+    {
+      if(h.npart[t] == 0) continue;
+      const std::vector<Piece> &pc = pieces[t];
+      const double mass_t = par->MassTable[t];
+      HostPool::get().run(h.npart[t], 1024, [&, t, mass_t](long long, long long lo, long long hi) {
+	for(const Piece &q : pc)
+	  {
+	    const BlockRow &row = ROWS[q.row];
+	    const float *in = (const float *) (image + q.off) + lo * row.ncomp;
+	    for(long long k = lo; k < hi; k++, in += row.ncomp) value_in(c, row.b, P, S, first[t] + k, t, in);
+	  }
+	// read_ic.c:106-111: "this makes sure that masses are initialized in the case that the mass-block is completely empty"
+	if(mass_t != 0)
+	  for(long long k = lo; k < hi; k++) *(double *) (P + (first[t] + k) * c.L.p_stride + c.L.p_Mass) = mass_t;
+	if(t == 0)
+	  for(long long k = lo; k < hi; k++)
+	    {
+	      double *A = (double *) (S + k * c.L.sph_stride + c.L.s_Entropy);
+	      if(ic_rules && *A == 0) *A = par->InitGasU;
+	      if(par->MinEgySpec > *A) *A = par->MinEgySpec;	// read_ic.c:214-215
+	    }
+      });
+    }
+  if(accmom_off >= 0)
+    {
+      // the values the record really holds; the reference goes on to fill the momenta of the remaining particles from
+      // whatever its I/O buffer held before (read_ic.c:555-562) - those are left untouched
+      const float *in = (const float *) (image + accmom_off);
+      for(long long k = 0; k < h.npart[0]; k++)
+	((double *) (S + (k / 3) * c.L.sph_stride + c.IO.s_accreted_momentum))[k % 3] = in[k];
+    }
+  if(mapping != MAP_FAILED) munmap(mapping, (size_t) used);
   if(par->RestartFlag == 0)
     {
       if(par->build & GL_IO_BUILD_BH_SWALLOWGAS) par->MassTable[5] = 0;	// read_ic.c:162-167
       if((par->build & GL_IO_BUILD_SFR) && par->MassTable[4] == 0 && par->MassTable[0] > 0)	// read_ic.c:169-178
 	par->MassTable[0] = par->MassTable[4] = 0;
-      if(par->InitGasTemp > 0)	// read_ic.c:196-210
-	for(long long i = 0; i < h.npart[0]; i++)
-	  {
-	    double *A = (double *) (S + i * c.L.sph_stride + c.L.s_Entropy);
-	    if(*A == 0) *A = par->InitGasU;
-	  }
-    }
-  for(long long i = 0; i < h.npart[0]; i++)	// read_ic.c:214-215
-    {
-      double *A = (double *) (S + i * c.L.sph_stride + c.L.s_Entropy);
-      if(par->MinEgySpec > *A) *A = par->MinEgySpec;
     }
   if(NumPart) *NumPart = nall;
   if(N_gas) *N_gas = h.npart[0];
