@@ -19,6 +19,7 @@
 #include "gl_internal.h"
 #include "gl_host.h"
 #include <chrono>
+#include <sys/mman.h>
 #include <algorithm>
 
 #define PACK_CHUNK 8192		// particles per work item of the host pool
@@ -1058,7 +1059,15 @@ extern "C" int gl_gadget_reorder(const gl_gadget_layout *lay, void *Pv, void *Sp
   for(long long k = 0; k < NumPart; k++)	// a gas slot must take a gas particle (the two blocks are ordered separately)
     if(order[k] < 0 || order[k] >= NumPart || ((k < N_gas) != (order[k] < N_gas))) return 1;
   char *P = (char *) Pv, *S = (char *) SphPv;
-  char *tp = (char *) malloc((size_t) NumPart * ps), *tsph = N_gas > 0 ? (char *) malloc((size_t) N_gas * ss) : nullptr;
+  // scratch of the size of the arrays: ask for huge pages, first-touch faults of 4 KB pages cost more than the copies
+  auto big_alloc = [](size_t bytes) -> char * {
+    const size_t two_mb = (size_t) 2 << 20;
+    void *p = nullptr;
+    if(posix_memalign(&p, two_mb, (bytes + two_mb - 1) / two_mb * two_mb) != 0) return nullptr;
+    madvise(p, (bytes + two_mb - 1) / two_mb * two_mb, MADV_HUGEPAGE);
+    return (char *) p;
+  };
+  char *tp = big_alloc((size_t) NumPart * ps), *tsph = N_gas > 0 ? big_alloc((size_t) N_gas * ss) : nullptr;
   if(!tp || (N_gas > 0 && !tsph))
     {
       free(tp);
@@ -1080,4 +1089,71 @@ extern "C" int gl_gadget_reorder(const gl_gadget_layout *lay, void *Pv, void *Sp
   free(tp);
   free(tsph);
   return 0;
+}
+
+// ---------------------------------------------------------------- peano_hilbert_order on the host ----
+// peano.c:25-92 with the keys the domain decomposition has already computed (the reference's global Key[],
+// domain.c:1750): (key, index) records of the gas block and of the rest are sorted separately - the reference's merge
+// sort takes the left element on equal keys (peano.c:551), i.e. it is stable, and so is this one - and the structs are
+// permuted accordingly.  The sort runs on all host cores: contiguous stretches are sorted independently, then merged
+// pairwise, level by level.
+namespace
+{
+struct KeyIdx
+{
+  unsigned long long key;
+  int index;
+};
+
+void sort_block(const unsigned long long *Key, long long first, long long n, int *order)
+{
+  if(n <= 0) return;
+  std::vector<KeyIdx> a((size_t) n), b((size_t) n);
+  HostPool &pool = HostPool::get();
+  const long long nth = std::max(1, pool.threads());
+  long long stretch = (n + nth - 1) / nth;
+  if(stretch < 4096) stretch = 4096;
+  const long long nst = (n + stretch - 1) / stretch;
+  pool.run(nst, 1, [&](long long, long long s0, long long s1) {
+    for(long long s = s0; s < s1; s++)
+      {
+	const long long lo = s * stretch, hi = std::min(n, lo + stretch);
+	for(long long i = lo; i < hi; i++) a[(size_t) i] = KeyIdx{Key[first + i], (int) (first + i)};
+	std::stable_sort(a.begin() + lo, a.begin() + hi, [](const KeyIdx &x, const KeyIdx &y) { return x.key < y.key; });
+      }
+  });
+  KeyIdx *src = a.data(), *dst = b.data();
+  for(long long width = stretch; width < n; width *= 2)
+    {
+      const long long npairs = (n + 2 * width - 1) / (2 * width);
+      pool.run(npairs, 1, [&](long long, long long p0, long long p1) {
+	for(long long p = p0; p < p1; p++)
+	  {
+	    const long long lo = p * 2 * width, mid = std::min(n, lo + width), hi = std::min(n, lo + 2 * width);
+	    // std::merge keeps the element of the first range on equal keys: the reference's "b1->key <= b2->key"
+	    std::merge(src + lo, src + mid, src + mid, src + hi, dst + lo, [](const KeyIdx &x, const KeyIdx &y) { return x.key < y.key; });
+	  }
+      });
+      std::swap(src, dst);
+    }
+  for(long long i = 0; i < n; i++) order[first + i] = src[i].index;
+}
+}				// namespace
+
+extern "C" int gl_gadget_peano_hilbert_order(const gl_gadget_layout *lay, void *P, void *SphP, long long NumPart, long long N_gas,
+					     const unsigned long long *Key, int *order_out)
+{
+  if(NumPart <= 0) return 0;
+  if(N_gas < 0 || N_gas > NumPart || NumPart > 0x7fffffffLL) return 1;
+  std::vector<int> order((size_t) NumPart);
+  const auto t0 = std::chrono::steady_clock::now();
+  sort_block(Key, 0, N_gas, order.data());
+  sort_block(Key, N_gas, NumPart - N_gas, order.data());
+  const auto t1 = std::chrono::steady_clock::now();
+  if(order_out) memcpy(order_out, order.data(), sizeof(int) * (size_t) NumPart);
+  const int rc = gl_gadget_reorder(lay, P, SphP, NumPart, N_gas, order.data());
+  if(getenv("GL_DEBUG_E2E"))
+    fprintf(stderr, "peano_hilbert_order: sort %.2f ms, reorder %.2f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+	    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+  return rc;
 }

@@ -201,6 +201,13 @@ int gl_gadget_drift(const gl_gadget_layout * lay, void *P, void *SphP, long long
  * separately), SphP[] alongside for the gas block.  The reference follows permutation cycles in place, one struct at a
  * time; here all host cores gather from a temporary copy.  Host code only - no context, no GPU. */
 int gl_gadget_reorder(const gl_gadget_layout * lay, void *P, void *SphP, long long NumPart, long long N_gas, const int *order);
+/* peano_hilbert_order() (peano.c:25-92) as a whole, on the host, from the keys the domain decomposition has already
+ * computed (the reference's global Key[], domain.c:1750): stable sort of the gas block and of the rest by key (the
+ * reference's merge sort is stable, peano.c:551) on all host cores, then gl_gadget_reorder.  order_out (may be NULL)
+ * receives the permutation (new P[k] = old P[order[k]]).  Host code only - no context, no GPU.  (gl_peano_hilbert_order
+ * above is the GPU form for particles that are already loaded.) */
+int gl_gadget_peano_hilbert_order(const gl_gadget_layout * lay, void *P, void *SphP, long long NumPart, long long N_gas,
+				  const gl_peanokey * Key, int *order_out);
 /* Individual time steps: the per-particle part of advance_and_find_timesteps() (timestep.c:29) for
  * the particles of the active list - get_timestep (timestep.c:607: acceleration, Courant, dust, sink-accretion and
  * feedback criteria of the shipped -D list), the power-of-two bin with the "only onto a synchronised bin" rule

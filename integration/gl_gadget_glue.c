@@ -583,3 +583,25 @@ void advance_and_find_timesteps(void)
   CPU_Step[CPU_TIMELINE] += measure_time();
 }
 #endif /* GL_TIMESTEP */
+
+#ifdef GL_PEANO_ORDER
+/* ---- peano_hilbert_order() (proto.h; peano.c:25) ------------------------------------------------------------------
+ * Called by domain_Decomposition() after the particle exchange (domain.c:132) with the keys in the global Key[]
+ * (domain.c:1750).  The reference sorts 16-byte records with a serial merge sort and then follows permutation cycles
+ * through 536-byte structs one at a time; the library does both on all host cores.  The mymalloc stack is left as
+ * found (the library uses malloc). */
+void peano_hilbert_order(void)
+{
+  if(ThisTask == 0)
+    printf("begin Peano-Hilbert order...\n");
+  gl_fill_layout();
+  if(gl_gadget_peano_hilbert_order(&GL_Layout, P, SphP, NumPart, N_gas, Key, NULL))
+    {
+      printf("libgl_b200: gl_gadget_peano_hilbert_order failed\n");
+      fflush(stdout);
+      endrun(8803);
+    }
+  if(ThisTask == 0)
+    printf("Peano-Hilbert done.\n");
+}
+#endif /* GL_PEANO_ORDER */

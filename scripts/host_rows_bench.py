@@ -97,6 +97,15 @@ def main():
     out["kick"] = dict(ms=t * 1e3, particles_per_s=n / t, struct_GBps=struct_bytes / t / 1e9,
                        bins_changed=int((binold != a.pview("p_TimeBin", np.int16)).sum()))
 
+    # peano_hilbert_order from given keys (random 63-bit keys: the worst case for the permutation's locality)
+    keys = g.integers(0, 1 << 62, size=n, dtype=np.int64).astype(np.uint64)
+
+    def ph_run():
+        drift()
+        assert lib.gl_gadget_peano_hilbert_order(C.byref(lay), L._ptr(a.P), L._ptr(a.SphP), n, ng, L._ptr(keys), None) == 0
+    t = best(ph_run, max(2, args.reps // 2)) - t_copy
+    out["peano_hilbert_order"] = dict(ms=t * 1e3, particles_per_s=n / t, struct_GBps=2 * struct_bytes / t / 1e9)
+
     # snapshot files
     drift()
     a.sview("s_Density", np.float64)[:] = g.random(ng) + 0.1

@@ -81,3 +81,25 @@ def test_reorder_permutes_structs_like_the_reference():
     bad[0], bad[-1] = bad[-1], bad[0]          # a non-gas particle into the gas block: refused, nothing touched
     assert lib.gl_gadget_reorder(C.byref(lay), L._ptr(Pb), L._ptr(Sb), n, ngas, L._ptr(bad)) != 0
     assert (Pb.reshape(n, ps_) == want_P).all()
+
+
+def test_host_peano_hilbert_order_is_the_reference_stable_sort():
+    """gl_gadget_peano_hilbert_order = peano_hilbert_order() (peano.c:25-92) from given keys: gas block and the rest sorted
+    separately, equal keys keep their order (the reference's merge takes the left element, peano.c:551), structs
+    permuted.  Many ties on purpose; sizes around the parallel sort's stretch boundaries."""
+    lib = L.load_library()
+    lay = aos.layout_struct()
+    lay_d = aos.layout()
+    ps_, ss_ = lay_d["p_stride"], lay_d["sph_stride"]
+    for n, ngas, seed in ((1, 1, 0), (5000, 0, 1), (70001, 50000, 2), (20000, 20000, 3)):
+        rng = np.random.default_rng(seed)
+        Pb = rng.integers(0, 256, size=n * ps_, dtype=np.uint8)
+        Sb = rng.integers(0, 256, size=max(ngas, 1) * ss_, dtype=np.uint8)
+        keys = rng.integers(0, max(2, n // 7), size=n).astype(np.uint64) << np.uint64(40)
+        want = np.concatenate([np.argsort(keys[:ngas], kind="stable"), ngas + np.argsort(keys[ngas:], kind="stable")]).astype(np.int32)
+        want_P = Pb.reshape(n, ps_)[want].copy()
+        want_S = Sb[: ngas * ss_].reshape(ngas, ss_)[want[:ngas]].copy()
+        order = np.full(n, -1, np.int32)
+        assert lib.gl_gadget_peano_hilbert_order(C.byref(lay), L._ptr(Pb), L._ptr(Sb), n, ngas, L._ptr(keys), L._ptr(order)) == 0
+        assert np.array_equal(order, want)
+        assert (Pb.reshape(n, ps_) == want_P).all() and (Sb[: ngas * ss_].reshape(ngas, ss_) == want_S).all()

@@ -173,19 +173,20 @@ def test_failures_where_the_reference_would_endrun():
     assert rc != 0 and "uninitialised" in msg
 
 
-REF_KICK_DROPIN = os.path.join(util.ROOT, "oracle", "_ref", "ref_kick_dropin")
+REF_HOST_DROPIN = os.path.join(util.ROOT, "oracle", "_ref", "ref_host_dropin")
 
 
-@pytest.mark.skipif(not os.path.exists(REF_KICK_DROPIN), reason="oracle/_ref/ref_kick_dropin not built (needs /root/reference)")
+@pytest.mark.skipif(not os.path.exists(REF_HOST_DROPIN), reason="oracle/_ref/ref_host_dropin not built (needs /root/reference)")
 def test_reference_host_with_the_glue_advance_and_find_timesteps():
-    """The reference harness (its own CPU force path) linked with advance_and_find_timesteps() from
-    integration/gl_gadget_glue.c (-DGL_TIMESTEP): every array of the committed all-reference fixture, the time-bin
-    lists included, comes out the same."""
+    """The reference harness (its own CPU force path) linked with advance_and_find_timesteps() AND peano_hilbert_order()
+    from integration/gl_gadget_glue.c (-DGL_TIMESTEP -DGL_PEANO_ORDER): every array of the committed all-reference
+    fixture comes out the same - the particle order domain_Decomposition() leaves behind (the dumps are in P[] order,
+    ids included) and the time-bin lists as well."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(util.ROOT, "tests", "golden", "make_golden.py"))
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
-    got = mg.kick_run(REF_KICK_DROPIN)
+    got = mg.kick_run(REF_HOST_DROPIN)
     z = np.load(FIX)
     assert set(got) == set(z.files)
     used = z["post_TimeBinCount"] > 0
