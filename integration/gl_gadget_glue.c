@@ -9,12 +9,18 @@
  *     void force_update_hmax(void)       forcetree.h / forcetree.c:1661   (only when GL_TAKE_OVER_HMAX is set)
  *     void hydro_force(void)             proto.h / hydra.c:145
  *     void compute_accelerations(int)    proto.h / accel.c:27             (only when GL_TAKE_OVER_ACCEL is set)
+ * and, each behind its own switch, the host-side neighbours of the path (no GPU involved):
+ *     void advance_and_find_timesteps(void)   proto.h / timestep.c:29     -DGL_TIMESTEP
+ *     void peano_hilbert_order(void)          proto.h / peano.c:25        -DGL_PEANO_ORDER
+ *     void read_ic(char *), void savepositions(int)   read_ic.c:28, io.c:33   -DGL_SNAPSHOT_IO (formats 1 and 2, one rank)
  * on top of the C ABI of include/gl_b200.h, keeps the reference's side effects (All.ErrTolTheta = 0 after the
  * first call, TreeReconstructFlag = 0, All.TotNumOfForces, CPU_Step[] buckets), leaves the mymalloc stack
  * untouched (mymalloc.c:159-164) and maps any library error onto endrun() (endrun.c:23).
  *
  * It is compiled in the build container by oracle/refbuild (target `dropin`) into oracle/_ref/ref_dropin,
- * where the reference's own harness runs with THESE symbols instead of gravtree.c/density.c/hydra.c.
+ * where the reference's own harness runs with THESE symbols instead of gravtree.c/density.c/hydra.c; targets
+ * `host_dropin` and `io_dropin` do the same for the host-side entry points (ref_host_dropin, ref_io_dropin; with
+ * -DGL_NO_FORCE_PATH the force path stays the reference's, so those binaries run without a GPU).
  */
 #include <stdio.h>
 #include <stdlib.h>
