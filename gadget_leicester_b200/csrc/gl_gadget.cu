@@ -1157,3 +1157,136 @@ extern "C" int gl_gadget_peano_hilbert_order(const gl_gadget_layout *lay, void *
 	    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   return rc;
 }
+
+// ---------------------------------------------------------------- the top-level tree of the domain decomposition ----
+// domain_determineTopTree (domain.c:1738-1916) for one rank: the string of Peano-Hilbert keys is chopped into eight
+// segments recursively while a segment holds more than 1/(TOPNODEFACTOR * MULTIPLEDOMAINS * NTask) of the particles or
+// of the cost, or more than 80 % of its parent's (domain_check_for_local_refine, domain.c:1524-1590).  The reference
+// sorts (key, index) records serially and then walks every refined node's particle range once per level; here the sort
+// runs on all host cores and the ranges are found by bisection in the sorted keys.  What must stay exactly as in the
+// reference is the ARITHMETIC of the decisions: the root cost is the sum over the particles in P[] order, a daughter's
+// cost the sum over its range in sorted order, each started from zero (FP64 addition is not associative), and the
+// node numbering, which follows the depth-first order of the recursion.
+namespace
+{
+struct TopBuild
+{
+  gl_topnode *T;
+  int n, max_nodes;
+  const unsigned long long *key;	// sorted
+  const double *cost;		// in the same order
+  double countlimit, costlimit;
+
+  int refine(int i)
+  {
+    int flag = 0;
+    if(T[i].Parent >= 0)
+      if(T[i].Count > 0.8 * T[T[i].Parent].Count || T[i].Cost > 0.8 * T[T[i].Parent].Cost) flag = 1;
+    if((T[i].Count > countlimit || T[i].Cost > costlimit || flag == 1) && T[i].Size >= 8)
+      {
+	if(n + 8 > max_nodes) return 1;
+	T[i].Daughter = n;
+	for(int j = 0; j < 8; j++)
+	  {
+	    gl_topnode &d = T[n + j];
+	    d.Daughter = -1;
+	    d.Parent = i;
+	    d.Size = T[i].Size >> 3;
+	    d.StartKey = T[i].StartKey + j * d.Size;
+	    d.PIndex = T[i].PIndex;
+	    d.Count = 0;
+	    d.Cost = 0;
+	    d.Leaf = 0;
+	  }
+	n += 8;
+	const int first = T[i].Daughter;
+	const long long lo = T[i].PIndex, hi = T[i].PIndex + T[i].Count;
+	long long begin = lo;
+	for(int j = 0; j < 8 && begin < hi; j++)
+	  {
+	    // particles of daughter j: keys below the next daughter's first key (the last daughter takes the rest)
+	    const long long end = j < 7 ? std::lower_bound(key + begin, key + hi, T[first + j + 1].StartKey) - key : hi;
+	    gl_topnode &d = T[first + j];
+	    if(j > 0) d.PIndex = (int) begin;	// domain.c:1563-1570: set when the scan steps into the daughter
+	    double c = 0;
+	    for(long long p = begin; p < end; p++) c += cost[p];
+	    d.Cost = c;
+	    d.Count = end - begin;
+	    begin = end;
+	  }
+	for(int j = 0; j < 8; j++)
+	  if(refine(first + j)) return 1;
+      }
+    return 0;
+  }
+
+  void number_leaves(int no, int &nleaves)	// domain_walktoptree, domain.c:1495
+  {
+    if(T[no].Daughter == -1)
+      T[no].Leaf = nleaves++;
+    else
+      for(int j = 0; j < 8; j++) number_leaves(T[no].Daughter + j, nleaves);
+  }
+};
+}				// namespace
+
+extern "C" int gl_domain_top_tree(const gl_peanokey *Key, const double *costfactor, long long NumPart, int NTask, int multipledomains,
+				  double topnodefactor, gl_topnode *nodes, int max_nodes, int *ntopnodes, int *ntopleaves)
+{
+  if(NumPart <= 0 || NumPart > 0x7fffffffLL || max_nodes < 1) return 2;
+  std::vector<int> order((size_t) NumPart);
+  sort_block(Key, 0, NumPart, order.data());	// stable, like mysort_domain (domain.c:1758)
+  std::vector<unsigned long long> ks((size_t) NumPart);
+  std::vector<double> cs((size_t) NumPart);
+  HostPool::get().run(NumPart, 65536, [&](long long, long long a, long long b) {
+    for(long long p = a; p < b; p++)
+      {
+	ks[(size_t) p] = Key[order[(size_t) p]];
+	cs[(size_t) p] = costfactor[order[(size_t) p]];
+      }
+  });
+  double gravcost = 0;		// domain.c:407-414, in P[] order
+  for(long long i = 0; i < NumPart; i++) gravcost += costfactor[i];
+  TopBuild B;
+  B.T = nodes;
+  B.n = 1;
+  B.max_nodes = max_nodes;
+  B.key = ks.data();
+  B.cost = cs.data();
+  B.costlimit = gravcost / (topnodefactor * multipledomains * NTask);	// domain.c:1772-1773 (one rank: totals = local sums)
+  B.countlimit = (double) NumPart / (topnodefactor * multipledomains * NTask);
+  nodes[0].Daughter = -1;
+  nodes[0].Parent = -1;
+  nodes[0].Size = ((gl_peanokey) 1) << 63;	// PEANOCELLS, 3 * BITS_PER_DIMENSION
+  nodes[0].StartKey = 0;
+  nodes[0].PIndex = 0;
+  nodes[0].Count = NumPart;
+  nodes[0].Cost = gravcost;
+  nodes[0].Leaf = 0;
+  if(B.refine(0)) return 1;	// "We are out of Topnodes" - the caller repeats with more room (domain.c:246-269)
+  // domain.c:1871-1900: leaves that are still too heavy get daughters with an eighth of their count and cost
+  for(int i = 0; i < B.n; i++)
+    if(nodes[i].Daughter < 0 && (nodes[i].Count > B.countlimit || nodes[i].Cost > B.costlimit) && nodes[i].Size > 1)
+      {
+	if(B.n + 8 > max_nodes) return 1;
+	nodes[i].Daughter = B.n;
+	for(int j = 0; j < 8; j++)
+	  {
+	    gl_topnode &d = nodes[B.n + j];
+	    d.Size = nodes[i].Size >> 3;
+	    d.Count = nodes[i].Count / 8;
+	    d.Cost = nodes[i].Cost / 8;
+	    d.Daughter = -1;
+	    d.Parent = i;
+	    d.StartKey = nodes[i].StartKey + j * d.Size;
+	    d.PIndex = 0;
+	    d.Leaf = 0;
+	  }
+	B.n += 8;
+      }
+  int nleaves = 0;
+  B.number_leaves(0, nleaves);
+  if(ntopnodes) *ntopnodes = B.n;
+  if(ntopleaves) *ntopleaves = nleaves;
+  return 0;
+}

@@ -87,6 +87,12 @@ class GLTimestepParams(C.Structure):
                 ("p_NewDensity", C.c_int)]
 
 
+class GLTopNode(C.Structure):
+    """struct local_topnode_data (domain.c:48)."""
+    _fields_ = [("Size", C.c_ulonglong), ("StartKey", C.c_ulonglong), ("Count", C.c_longlong), ("Cost", C.c_double),
+                ("Daughter", C.c_int), ("Leaf", C.c_int), ("Parent", C.c_int), ("PIndex", C.c_int)]
+
+
 class GLTreeLayout(C.Structure):
     _fields_ = [("node_stride", C.c_longlong), ("ext_stride", C.c_longlong)] + [(k, C.c_int) for k in (
         "n_len", "n_center", "n_maxsoft", "n_s", "n_mass", "n_bitflags", "n_sibling", "n_nextnode", "n_father", "n_Ti_current",
@@ -103,7 +109,7 @@ EXPORTS = [
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
     "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree", "gl_gadget_drift", "gl_gadget_reorder",
-    "gl_snapshot_write", "gl_snapshot_read", "gl_snapshot_read_header", "gl_gadget_advance_and_find_timesteps", "gl_gadget_peano_hilbert_order",
+    "gl_snapshot_write", "gl_snapshot_read", "gl_snapshot_read_header", "gl_gadget_advance_and_find_timesteps", "gl_gadget_peano_hilbert_order", "gl_domain_top_tree",
 ]
 
 _lib = None
@@ -173,6 +179,8 @@ def load_library():
                                     C.POINTER(C.c_longlong)]
     lib.gl_snapshot_write.argtypes = [C.c_char_p, C.POINTER(GLGadgetLayout), C.POINTER(GLIOLayout), C.POINTER(GLIOParams), vp, vp,
                                       C.c_longlong, vp, vp, C.c_char_p, C.c_int]
+    lib.gl_domain_top_tree.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, C.c_double, C.POINTER(GLTopNode), C.c_int,
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.gl_gadget_peano_hilbert_order.argtypes = [C.POINTER(GLGadgetLayout), vp, vp, C.c_longlong, C.c_longlong, vp, vp]
     lib.gl_gadget_advance_and_find_timesteps.argtypes = [C.POINTER(GLGadgetLayout), C.POINTER(GLTimestepParams), vp, vp, vp,
                                                          C.c_longlong, vp, C.c_char_p, C.c_int]

@@ -208,6 +208,22 @@ int gl_gadget_reorder(const gl_gadget_layout * lay, void *P, void *SphP, long lo
  * above is the GPU form for particles that are already loaded.) */
 int gl_gadget_peano_hilbert_order(const gl_gadget_layout * lay, void *P, void *SphP, long long NumPart, long long N_gas,
 				  const gl_peanokey * Key, int *order_out);
+/* The top-level tree of the domain decomposition for one rank: domain_determineTopTree
+ * (domain.c:1738-1916) with domain_check_for_local_refine (domain.c:1524) and the leaf numbering of domain_walktoptree
+ * (domain.c:1495), from the particles' Peano-Hilbert keys and cost factors (1 + GravCost) / 2^TimeBin (domain.c:378), both
+ * in P[] order.  The node numbering, every Count and every Cost (summation order included) are the reference's; the key
+ * sort runs on all host cores and the particle ranges are found by bisection.  nodes[] = struct local_topnode_data
+ * (domain.c:48); returns 1 when max_nodes is too small (the reference then raises TopNodeAllocFactor and repeats,
+ * domain.c:246-269).  Host code only - no context, no GPU. */
+typedef struct gl_topnode
+{
+  gl_peanokey Size, StartKey;
+  long long Count;
+  double Cost;
+  int Daughter, Leaf, Parent, PIndex;
+} gl_topnode;
+int gl_domain_top_tree(const gl_peanokey * Key, const double *costfactor, long long NumPart, int NTask, int multipledomains,
+		       double topnodefactor, gl_topnode * nodes, int max_nodes, int *ntopnodes, int *ntopleaves);
 /* Individual time steps: the per-particle part of advance_and_find_timesteps() (timestep.c:29) for
  * the particles of the active list - get_timestep (timestep.c:607: acceleration, Courant, dust, sink-accretion and
  * feedback criteria of the shipped -D list), the power-of-two bin with the "only onto a synchronised bin" rule

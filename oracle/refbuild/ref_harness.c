@@ -420,6 +420,25 @@ int main(int argc, char **argv)
     t1 = now() - t0;
     put("", "time_domain", 'd', 1, 1, &t1);
   }
+  {
+    /* the top-level tree the decomposition built (domain.c:1738 domain_determineTopTree -> TopNodes[], domain.c:220-226) */
+    long long *sk = malloc(8 * (NTopnodes + 1)), *sz = malloc(8 * (NTopnodes + 1));
+    int *da = malloc(4 * (NTopnodes + 1)), *lf = malloc(4 * (NTopnodes + 1)), nn[2];
+    for(i = 0; i < NTopnodes; i++)
+      {
+	sk[i] = (long long) TopNodes[i].StartKey; sz[i] = (long long) TopNodes[i].Size;
+	da[i] = TopNodes[i].Daughter; lf[i] = TopNodes[i].Daughter < 0 ? TopNodes[i].Leaf : -1;
+      }
+    nn[0] = NTopnodes; nn[1] = NTopleaves;
+    put("", "top_n", 'i', 2, 1, nn);
+    put("", "top_StartKey", 'q', NTopnodes, 1, sk); put("", "top_Size", 'q', NTopnodes, 1, sz);
+    put("", "top_Daughter", 'i', NTopnodes, 1, da); put("", "top_Leaf", 'i', NTopnodes, 1, lf);
+    {
+      double dom[5] = { DomainCorner[0], DomainCorner[1], DomainCorner[2], DomainFac, (double) (int) (All.TopNodeAllocFactor * All.MaxPart + 1) };
+      put("", "top_domain", 'd', 5, 1, dom);
+    }
+    free(sk); free(sz); free(da); free(lf);
+  }
 
   ops = strdup(argv[3]);
   for(tok = strtok(ops, " "); tok; tok = strtok(NULL, " "), opidx++)
