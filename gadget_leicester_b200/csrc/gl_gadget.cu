@@ -1290,3 +1290,125 @@ extern "C" int gl_domain_top_tree(const gl_peanokey *Key, const double *costfact
   if(ntopleaves) *ntopleaves = nleaves;
   return 0;
 }
+
+// domain_findExtent (domain.c:1972-2014) + the key loop of domain_determineTopTree (domain.c:1748-1755) on all host
+// cores: minimum / maximum are exact in any order, the cube is formed with the reference's expressions, and every key is
+// peano_hilbert_key((int) ((Pos - DomainCorner) * DomainFac), ...) (peano.c:300).
+extern "C" int gl_gadget_domain_keys(const gl_gadget_layout *lay, const void *Pv, long long NumPart, double DomainCorner[3],
+				     double DomainCenter[3], double *DomainLen, double *DomainFac, gl_peanokey *Key)
+{
+  if(NumPart <= 0) return 1;
+  const gl_gadget_layout L = *lay;
+  const char *P = (const char *) Pv;
+  const long long STRETCH = 65536, nst = (NumPart + STRETCH - 1) / STRETCH;
+  std::vector<double> lo((size_t) (3 * nst), 1e300), hi((size_t) (3 * nst), -1e300);
+  HostPool &pool = HostPool::get();
+  pool.run(NumPart, STRETCH, [&](long long k, long long a, long long b) {
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for(long long i = a; i < b; i++)
+      {
+	const double *x = (const double *) (P + i * L.p_stride + L.p_Pos);
+	for(int j = 0; j < 3; j++)
+	  {
+	    if(mn[j] > x[j]) mn[j] = x[j];
+	    if(mx[j] < x[j]) mx[j] = x[j];
+	  }
+      }
+    for(int j = 0; j < 3; j++)
+      {
+	lo[(size_t) (3 * k + j)] = mn[j];
+	hi[(size_t) (3 * k + j)] = mx[j];
+      }
+  });
+  double xmin[3] = {1e300, 1e300, 1e300}, xmax[3] = {-1e300, -1e300, -1e300};
+  for(long long k = 0; k < nst; k++)
+    for(int j = 0; j < 3; j++)
+      {
+	if(xmin[j] > lo[(size_t) (3 * k + j)]) xmin[j] = lo[(size_t) (3 * k + j)];
+	if(xmax[j] < hi[(size_t) (3 * k + j)]) xmax[j] = hi[(size_t) (3 * k + j)];
+      }
+  double len = 0;
+  for(int j = 0; j < 3; j++)
+    if(xmax[j] - xmin[j] > len) len = xmax[j] - xmin[j];
+  len *= 1.001;
+  for(int j = 0; j < 3; j++)
+    {
+      DomainCenter[j] = 0.5 * (xmin[j] + xmax[j]);
+      DomainCorner[j] = 0.5 * (xmin[j] + xmax[j]) - 0.5 * len;
+    }
+  *DomainLen = len;
+  const double fac = 1.0 / len * (((gl_peanokey) 1) << 21);	// BITS_PER_DIMENSION
+  *DomainFac = fac;
+  const double c0 = DomainCorner[0], c1 = DomainCorner[1], c2 = DomainCorner[2];
+  pool.run(NumPart, 8192, [=](long long, long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	const double *x = (const double *) (P + i * L.p_stride + L.p_Pos);
+	Key[i] = gl_peano_hilbert_key((int) ((x[0] - c0) * fac), (int) ((x[1] - c1) * fac), (int) ((x[2] - c2) * fac), 21);
+      }
+  });
+  return 0;
+}
+
+// domain_particle_costfactor (domain.c:378-384) for every particle
+extern "C" int gl_gadget_costfactors(const gl_gadget_layout *lay, const void *Pv, long long NumPart, double *cost)
+{
+  const gl_gadget_layout L = *lay;
+  const char *P = (const char *) Pv;
+  HostPool::get().run(NumPart, 16384, [=](long long, long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	const char *pi = P + i * L.p_stride;
+	const int tb = *(const short *) (pi + L.p_TimeBin);
+	const double g = 1.0 + *(const float *) (pi + L.p_GravCost);
+	cost[i] = tb ? g / (1 << tb) : g / (1 << 29);	// TIMEBASE
+      }
+  });
+  return 0;
+}
+
+// domain_sumCost (domain.c:1920-1966: work and count of every top-level leaf; the work is a 4-byte float accumulated in
+// P[] order) followed by domain_findSplit_work_balanced (domain.c:1075-1113, all speed factors 1): ncpu consecutive
+// stretches of leaves of about equal work.
+extern "C" int gl_domain_split(const gl_topnode *T, int ntopleaves, const gl_peanokey *Key, const double *costfactor,
+			       long long NumPart, int ncpu, int *start_list, int *end_list, float *leaf_work, int *leaf_count)
+{
+  if(ntopleaves < ncpu || ncpu < 1) return 1;	// endrun(112), domain.c:1912
+  std::vector<float> work((size_t) ntopleaves, 0.0f);
+  std::vector<int> count((size_t) ntopleaves, 0);
+  for(long long n = 0; n < NumPart; n++)
+    {
+      int no = 0;
+      while(T[no].Daughter >= 0) no = T[no].Daughter + (int) ((Key[n] - T[no].StartKey) / (T[no].Size >> 3));
+      no = T[no].Leaf;
+      work[(size_t) no] += costfactor[n];
+      count[(size_t) no] += 1;
+    }
+  double w = 0;
+  for(int i = 0; i < ntopleaves; i++) w += work[(size_t) i];
+  const double workavg = w / ncpu;
+  double work_before = 0, workavg_before = 0;
+  int start = 0;
+  for(int i = 0; i < ncpu; i++)
+    {
+      double wk = 0;
+      int end = start;
+      wk += work[(size_t) end] / 1.0;
+      while((wk + work_before < workavg + workavg_before) || (i == ncpu - 1 && end < ntopleaves - 1))
+	{
+	  if((ntopleaves - end) > (ncpu - i))
+	    end++;
+	  else
+	    break;
+	  wk += work[(size_t) end] / 1.0;
+	}
+      start_list[i] = start;
+      end_list[i] = end;
+      work_before += wk;
+      workavg_before += workavg;
+      start = end + 1;
+    }
+  if(leaf_work) memcpy(leaf_work, work.data(), sizeof(float) * (size_t) ntopleaves);
+  if(leaf_count) memcpy(leaf_count, count.data(), sizeof(int) * (size_t) ntopleaves);
+  return 0;
+}

@@ -224,6 +224,14 @@ typedef struct gl_topnode
 } gl_topnode;
 int gl_domain_top_tree(const gl_peanokey * Key, const double *costfactor, long long NumPart, int NTask, int multipledomains,
 		       double topnodefactor, gl_topnode * nodes, int max_nodes, int *ntopnodes, int *ntopleaves);
+/* The other host pieces of a one-rank domain_Decomposition() (domain.c:100): the cube and the keys (domain_findExtent
+ * domain.c:1972 + the key loop domain.c:1748), the cost factors (domain.c:378), and the leaf work / leaf count tables
+ * with the split into ncpu stretches of leaves (domain_sumCost domain.c:1920, domain_findSplit_work_balanced :1075). */
+int gl_gadget_domain_keys(const gl_gadget_layout * lay, const void *P, long long NumPart, double DomainCorner[3],
+			  double DomainCenter[3], double *DomainLen, double *DomainFac, gl_peanokey * Key);
+int gl_gadget_costfactors(const gl_gadget_layout * lay, const void *P, long long NumPart, double *costfactor);
+int gl_domain_split(const gl_topnode * nodes, int ntopleaves, const gl_peanokey * Key, const double *costfactor, long long NumPart,
+		    int ncpu, int *start_list, int *end_list, float *leaf_work, int *leaf_count);
 /* Individual time steps: the per-particle part of advance_and_find_timesteps() (timestep.c:29) for
  * the particles of the active list - get_timestep (timestep.c:607: acceleration, Courant, dust, sink-accretion and
  * feedback criteria of the shipped -D list), the power-of-two bin with the "only onto a synchronised bin" rule

@@ -12,6 +12,7 @@
  * and, each behind its own switch, the host-side neighbours of the path (no GPU involved):
  *     void advance_and_find_timesteps(void)   proto.h / timestep.c:29     -DGL_TIMESTEP
  *     void peano_hilbert_order(void)          proto.h / peano.c:25        -DGL_PEANO_ORDER
+ *     void domain_Decomposition(void)         proto.h / domain.c:100      -DGL_DOMAIN (one rank)
  *     void read_ic(char *), void savepositions(int)   read_ic.c:28, io.c:33   -DGL_SNAPSHOT_IO (formats 1 and 2, one rank)
  * on top of the C ABI of include/gl_b200.h, keeps the reference's side effects (All.ErrTolTheta = 0 after the
  * first call, TreeReconstructFlag = 0, All.TotNumOfForces, CPU_Step[] buckets), leaves the mymalloc stack
@@ -611,3 +612,111 @@ void peano_hilbert_order(void)
     printf("Peano-Hilbert done.\n");
 }
 #endif /* GL_PEANO_ORDER */
+
+#ifdef GL_DOMAIN
+/* ---- domain_Decomposition() (proto.h; domain.c:100) for a run on ONE rank (one GPU) ----------------------------------
+ * With a single rank nothing is exchanged; what the reference's function leaves behind is the cube (DomainCorner / Center /
+ * Len / Fac), the top-level tree TopNodes[] with NTopnodes / NTopleaves, DomainTask[] / DomainStartList[] /
+ * DomainEndList[], P[] and SphP[] in Peano-Hilbert order, a freshly allocated tree and rebuilt time-bin lists.  All of
+ * that is reproduced here with the heavy loops - drift, extent, keys, key sort, top-level tree, struct permutation - in
+ * the library on all host cores (the reference spends 0.65 s per call on 4e5 particles, most of it in reorder_gas and in
+ * two serial merge sorts).  The mymalloc stack is left exactly as the reference leaves it: DomainStartList,
+ * DomainEndList, TopNodes (shrunk), then the tree. */
+void domain_Decomposition(void)
+{
+  int i, nn = 0, nl = 0, rc;
+  double *cost, dlen, dfac;
+  gl_topnode *nodes;
+
+  if(NTask != 1)
+    gl_fail("domain_Decomposition: the library's version is for one rank; link the reference's domain.o otherwise");
+  if(!(All.NumForcesSinceLastDomainDecomp >= All.TotNumPart * All.TreeDomainUpdateFrequency || All.DoDynamicUpdate == 0))
+    return;
+  CPU_Step[CPU_MISC] += measure_time();
+  gl_fill_layout();
+  if(gl_gadget_drift(&GL_Layout, P, SphP, NumPart, N_gas, All.Ti_Current, All.Timebase_interval, All.MinGasHsml, NULL))
+    endrun(12);			/* domain.c:120-122 */
+  force_treefree();
+  domain_free();
+#if defined(SFR) || defined(BLACK_HOLES) || defined(DUST)
+  rearrange_particle_sequence();
+#endif
+  All.NumForcesSinceLastDomainDecomp = 0;
+  TreeReconstructFlag = 1;	/* ensures that new tree will be constructed */
+  if(ThisTask == 0)
+    printf("domain decomposition... (presently allocated=%g MB)\n", AllocatedBytes / (1024.0 * 1024.0));
+  cost = (double *) malloc(sizeof(double) * (NumPart > 0 ? NumPart : 1));
+  do
+    {
+      domain_allocate();
+      Key = (peanokey *) mymalloc_msg(sizeof(peanokey) * All.MaxPart, "domain_key");
+      /* domain_decompose(), domain.c:404-427 */
+      gl_gadget_costfactors(&GL_Layout, P, NumPart, cost);
+      for(i = 0; i < 6; i++)
+	NtypeLocal[i] = 0;
+      for(i = 0; i < NumPart; i++)
+	{
+	  NtypeLocal[P[i].Type]++;
+	  All.Cadj_Cost += cost[i];
+	}
+      for(i = 0; i < 6; i++)
+	Ntype[i] = NtypeLocal[i];
+      All.Cadj_Cpu *= 0.9;
+      All.Cadj_Cost *= 0.9;
+      if(gl_gadget_domain_keys(&GL_Layout, P, NumPart, DomainCorner, DomainCenter, &dlen, &dfac, (gl_peanokey *) Key))
+	gl_fail("gl_gadget_domain_keys");
+      DomainLen = dlen;
+      DomainFac = dfac;
+      nodes = (gl_topnode *) malloc(sizeof(gl_topnode) * MaxTopNodes);
+      rc = gl_domain_top_tree((gl_peanokey *) Key, cost, NumPart, NTask, MULTIPLEDOMAINS, TOPNODEFACTOR, nodes, MaxTopNodes, &nn, &nl);
+      if(rc == 0)
+	{
+	  NTopnodes = nn;
+	  NTopleaves = nl;
+	  if(NTopleaves < MULTIPLEDOMAINS * NTask)
+	    endrun(112);
+	  for(i = 0; i < NTopnodes; i++)
+	    {
+	      TopNodes[i].StartKey = nodes[i].StartKey;
+	      TopNodes[i].Size = nodes[i].Size;
+	      TopNodes[i].Daughter = nodes[i].Daughter;
+	      TopNodes[i].Leaf = nodes[i].Leaf;
+	    }
+	  if(gl_domain_split(nodes, NTopleaves, (gl_peanokey *) Key, cost, NumPart, MULTIPLEDOMAINS * NTask, DomainStartList, DomainEndList,
+			     NULL, NULL))
+	    endrun(112);
+	  for(i = 0; i < NTopleaves; i++)
+	    DomainTask[i] = 0;	/* domain_assign_load_or_work_balanced on one rank */
+	}
+      free(nodes);
+      if(rc == 1)
+	{
+	  /* out of top nodes: domain.c:246-269 */
+	  myfree(Key);
+	  domain_free();
+	  if(ThisTask == 0)
+	    printf("Increasing TopNodeAllocFactor=%g  ", All.TopNodeAllocFactor);
+	  All.TopNodeAllocFactor *= 1.3;
+	  if(ThisTask == 0)
+	    printf("new value=%g\n", All.TopNodeAllocFactor);
+	  if(All.TopNodeAllocFactor > 1000)
+	    endrun(781);
+	}
+      else if(rc)
+	gl_fail("gl_domain_top_tree");
+    }
+  while(rc);
+  free(cost);
+  if(ThisTask == 0)
+    printf("domain decomposition done. \n");
+  CPU_Step[CPU_DOMAIN] += measure_time();
+  peano_hilbert_order();
+  CPU_Step[CPU_PEANO] += measure_time();
+  myfree(Key);
+  memmove(TopNodes + NTopnodes, DomainTask, NTopnodes * sizeof(int));
+  TopNodes = (struct topnode_data *) myrealloc(TopNodes, NTopnodes * sizeof(struct topnode_data) + NTopnodes * sizeof(int));
+  DomainTask = (int *) (TopNodes + NTopnodes);
+  force_treeallocate((int) (All.TreeAllocFactor * All.MaxPart) + NTopnodes, All.MaxPart);
+  reconstruct_timebins();
+}
+#endif /* GL_DOMAIN */

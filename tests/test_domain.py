@@ -89,6 +89,30 @@ def test_top_tree_equals_committed_reference_dump(name):
     check({k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + ".")})
 
 
+REF_HOST_DROPIN = os.path.join(util.ROOT, "oracle", "_ref", "ref_host_dropin")
+
+
+@pytest.mark.skipif(not (util.have_ref() and os.path.exists(REF_HOST_DROPIN)), reason="oracle/_ref/ref_host_dropin not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["cube_timebins_2k", "disc_3k_sinks", "mixed_336", "disc_40k_timebins"])
+def test_reference_host_with_the_glue_domain_decomposition(name):
+    """The reference harness linked with the one-rank domain_Decomposition() of integration/gl_gadget_glue.c (-DGL_DOMAIN;
+    its pieces run in the library) next to the all-reference harness: the cube, TopNodes[], the particle order and -
+    through the CPU tree built on that top-level tree - every output of a tree build, a density pass, a gravity pass and
+    the node table come out bit-identical."""
+    ps, par = cases()[name]
+    ops = "K T S D R G N"
+    want = util.run_oracle(util.REF_HARNESS, ps, par, ops)
+    got = util.run_oracle(REF_HOST_DROPIN, ps, par, ops)
+    assert set(got) == set(want)
+    compared = 0
+    for k in want:
+        if "time" in k or "CPU_Step" in k:
+            continue
+        assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
+        compared += 1
+    assert compared > 30
+
+
 def test_top_tree_reports_lack_of_room():
     z = np.load(FIX)
     pre = "disc_40k_timebins."
