@@ -38,7 +38,7 @@ def top_tree(keys, cost, max_nodes, ntask=1, multipledomains=16, topnodefactor=2
 
 def cases():
     out = {}
-    for name in ("cube_timebins_2k", "disc_3k_sinks", "mixed_336"):
+    for name in ("cube_timebins_2k", "disc_3k_sinks", "mixed_336", "plummer_2k"):
         ps, par, _ = G.load_golden(name)
         out[name] = (ps, par)
     ps = ics.disc(40000, seed=7)
@@ -73,7 +73,7 @@ def check(d):
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/ref_harness not built (needs /root/reference)")
-@pytest.mark.parametrize("name", ["cube_timebins_2k", "disc_3k_sinks", "mixed_336", "disc_40k_timebins"])
+@pytest.mark.parametrize("name", ["cube_timebins_2k", "disc_3k_sinks", "mixed_336", "plummer_2k", "disc_40k_timebins"])
 def test_top_tree_equals_reference(name):
     ps, par = cases()[name]
     a = check(reference_dump(ps, par))
@@ -93,14 +93,14 @@ REF_HOST_DROPIN = os.path.join(util.ROOT, "oracle", "_ref", "ref_host_dropin")
 
 
 @pytest.mark.skipif(not (util.have_ref() and os.path.exists(REF_HOST_DROPIN)), reason="oracle/_ref/ref_host_dropin not built (needs /root/reference)")
-@pytest.mark.parametrize("name", ["cube_timebins_2k", "disc_3k_sinks", "mixed_336", "disc_40k_timebins"])
+@pytest.mark.parametrize("name", ["cube_timebins_2k", "disc_3k_sinks", "mixed_336", "plummer_2k", "disc_40k_timebins"])
 def test_reference_host_with_the_glue_domain_decomposition(name):
     """The reference harness linked with the one-rank domain_Decomposition() of integration/gl_gadget_glue.c (-DGL_DOMAIN;
     its pieces run in the library) next to the all-reference harness: the cube, TopNodes[], the particle order and -
     through the CPU tree built on that top-level tree - every output of a tree build, a density pass, a gravity pass and
     the node table come out bit-identical."""
     ps, par = cases()[name]
-    ops = "K T S D R G N"
+    ops = "K T S D R G N" if (ps["type"] == 0).any() else "K T R G N"        # (no gas: no density pass)
     want = util.run_oracle(util.REF_HARNESS, ps, par, ops)
     got = util.run_oracle(REF_HOST_DROPIN, ps, par, ops)
     assert set(got) == set(want)
@@ -110,7 +110,7 @@ def test_reference_host_with_the_glue_domain_decomposition(name):
             continue
         assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
         compared += 1
-    assert compared > 30
+    assert compared > 15
 
 
 def test_top_tree_reports_lack_of_room():
