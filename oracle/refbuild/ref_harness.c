@@ -24,6 +24,7 @@
  *     P  compute_potential()                  (potential.c:22; run.c:74 at statistics times)
  *     K  Peano-Hilbert and Morton key of every particle (peano_and_morton_key, peano.c:335)
  *     A  compute_accelerations-order block:  R G D U H   (accel.c:61-106 without sub-grid physics)
+ *     L  eight iterations of run()'s loop: find_next_sync_point_and_drift, domain_Decomposition, force path, kick
  *     V  advance_and_find_timesteps()         (timestep.c:29) at a synchronisation point of an individual-time-step
  *        state built from the input's time bins; dumps everything it reads and everything it leaves behind
  *   every op that computes dumps its outputs under the prefix "<k>_<op>_" with k the
@@ -44,9 +45,7 @@ double get_drift_factor(int t0, int t1) { (void) t0; (void) t1; return 0; }
 double get_gravkick_factor(int t0, int t1) { (void) t0; (void) t1; return 0; }
 double get_hydrokick_factor(int t0, int t1) { (void) t0; (void) t1; return 0; }
 double hubble_function(double a) { (void) a; return 0; }
-size_t my_fwrite(void *ptr, size_t size, size_t nmemb, FILE * stream) { return fwrite(ptr, size, nmemb, stream); }
 void rearrange_particle_sequence(void) { /* no Mass==0 particles in harness inputs (sfr_eff.c:1018) */ }
-int ShouldWeDoDynamicUpdate(void) { return 0; }	/* run.c:345: the tree is rebuilt every step */
 static unsigned long long lcg_state = 42;
 double gsl_rng_uniform(gsl_rng * r)
 {
@@ -193,6 +192,20 @@ static void dump_kick_state(const char *prefix, const char *tag)
 #undef PUT1
 #undef PUTI
   free(d3); free(d1); free(i1);
+}
+
+/* accel.c:27 reduced to the force path (accel.c:61-106; the sub-grid physics behind it is outside the path): what
+ * run.c's loop calls between the drift and the kick */
+void compute_accelerations(int mode)
+{
+  (void) mode;
+  gravity_tree();
+  if(All.TotN_gas > 0)
+    {
+      density();
+      force_update_hmax();
+      hydro_force();
+    }
 }
 
 void ref_density(void) __attribute__((weak));
@@ -543,6 +556,46 @@ int main(int argc, char **argv)
 		dump_kick_state(prefix, "pre");
 		advance_and_find_timesteps();
 		dump_kick_state(prefix, "post");
+	      }
+	      break;
+	    case 'L':
+	      /* several iterations of run()'s loop (run.c:63-110) on individual time steps, starting at the synchronisation
+	         point of op V: find_next_sync_point_and_drift (run.c:190), domain_Decomposition, the force path for the
+	         active particles, advance_and_find_timesteps.  TreeDomainUpdateFrequency = 0: a new decomposition and a new
+	         tree in every step (no dynamic tree update), which is how the GPU path runs. */
+	      {
+		int k, step;
+		double q[4];
+		All.Ti_Current = 64;
+		All.ErrTolIntAccuracy = 0.025; All.CourantFac = 0.15; All.TypeOfTimestepCriterion = 0;
+		All.MaxSizeTimestep = 200 * All.Timebase_interval; All.MinSizeTimestep = 0;
+		All.MinEgySpec = par[P_MINEGYSPEC];
+		All.OuterBoundary = 1.4e10; All.UnitVelocity_in_cm_per_s = 2.98e6; All.FeedBackVelocity = 1.0;
+		All.SMBHmass = 0.5; All.InnerBoundary = 2.0e-2; All.SinkBoundary = 1.0e-4; All.AccDtBlackHole = 0.007;
+		All.TreeDomainUpdateFrequency = 0; All.Ti_nextoutput = -1; All.TimeBegin = 0;
+		for(i = 0; i < NumPart; i++)
+		  {
+		    int b = P[i].TimeBin < 1 ? 1 : (P[i].TimeBin > 6 ? 6 : P[i].TimeBin);
+		    P[i].TimeBin = b;
+		    P[i].Ti_begstep = All.Ti_Current - (1 << b);
+		    P[i].Ti_current = All.Ti_Current;
+		  }
+		for(i = 0; i < TIMEBINS; i++) TimeBinActive[i] = (i <= 6);
+		reconstruct_timebins();
+		Flag_FullStep = 1;
+		advance_and_find_timesteps();
+		for(step = 0; step < 8; step++)
+		  {
+		    find_next_sync_point_and_drift();
+		    domain_Decomposition();
+		    compute_accelerations(0);
+		    advance_and_find_timesteps();
+		    All.NumCurrentTiStep++;
+		  }
+		for(i = 0, k = 0; i < NumPart; i++) k += (P[i].Ti_current == All.Ti_Current);
+		q[0] = All.Ti_Current; q[1] = All.Time; q[2] = k; q[3] = step;
+		put(prefix, "loop", 'd', 4, 1, q);
+		dump_kick_state(prefix, "end");
 	      }
 	      break;
 	    case 'N': dump_nodes(prefix); break;

@@ -30,17 +30,7 @@ double get_hydrokick_factor(int t0, int t1) { (void) t0; (void) t1; return 0; }
 double hubble_function(double a) { (void) a; return 0; }
 void rearrange_particle_sequence(void) { /* no Mass==0 particles in the test images (sfr_eff.c:1018) */ }
 double gsl_rng_uniform(gsl_rng * r) { (void) r; return 0.5; }
-int ShouldWeDoDynamicUpdate(void) { return 0; }	/* run.c:345 (timestep.o is linked with the other reference objects) */
-/* cooling.c / sfr_eff.c physics is outside the path: the NH and SFR blocks get a recognisable function of the
- * particle so that block placement can still be compared (the library takes these two blocks from the caller) */
-double AbundanceRatios(double u, double rho, double *ne_guess, double *nH0_pointer, double *nHeII_pointer)
-{
-  (void) u; (void) ne_guess;
-  *nH0_pointer = 0.25 + 0.5 * rho / (1.0 + rho);
-  *nHeII_pointer = 0;
-  return 0;
-}
-double get_starformation_rate(int i) { return 1.0e-3 * (i % 17); }
+void compute_accelerations(int mode) { (void) mode; }	/* run.o is linked with the other reference objects */
 
 static const char *arg(int argc, char **argv, const char *key, const char *dflt)
 {

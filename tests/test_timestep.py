@@ -195,3 +195,33 @@ def test_reference_host_with_the_glue_advance_and_find_timesteps():
             assert np.array_equal(got[k][used], z[k][used]), k
         else:
             assert np.array_equal(got[k], z[k]), k
+
+
+@pytest.mark.skipif(not (util.have_ref() and os.path.exists(REF_HOST_DROPIN)), reason="oracle/_ref binaries not built (needs /root/reference)")
+def test_integration_loop_with_the_glue_host_pieces_is_bit_identical():
+    """Eight iterations of the reference's run() loop (harness op L: find_next_sync_point_and_drift -> domain_Decomposition
+    -> gravity / density / hydro for the ACTIVE particles -> advance_and_find_timesteps, individual time steps, a new
+    decomposition and tree in every step) through the all-reference harness and through the one linked with the glue's
+    domain_Decomposition(), peano_hilbert_order() and advance_and_find_timesteps(): the end state - positions,
+    velocities, entropies, bins, time-bin lists, in P[] order - is the same bit for bit."""
+    import importlib.util
+    from gadget_leicester_b200 import ics
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(util.ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ps = mg._kick_set()
+    par = ics.default_params(Ti_Current=16, MinEgySpec=1.8)
+    par["Timebase_interval"] = 4.0e-5
+    par["PartAllocFactor"] = 20.0
+    out = {}
+    for name, binary in (("ref", util.REF_HARNESS), ("glue", REF_HOST_DROPIN)):
+        o = util.run_oracle(binary, ps, par, "T S D R G D U H L")
+        out[name] = {k[len("8_L_"):]: v for k, v in o.items() if k.startswith("8_L_")}
+    ref, glue = out["ref"], out["glue"]
+    assert ref["loop"][3] == 8 and ref["loop"][0] == 80                     # eight sync points: 66 ... 80
+    assert set(ref) == set(glue) and len(ref) > 25
+    for k in ref:
+        assert np.array_equal(ref[k], glue[k]), k
+    # the loop did something: particles moved, several bins were active along the way
+    z = np.load(FIX)
+    assert not np.array_equal(np.sort(ref["end_Pos"], axis=0), np.sort(z["pre_Pos"], axis=0))
