@@ -992,16 +992,17 @@ extern "C" int gl_gadget_push_wait(gl_ctx *c)
 }
 
 // ---------------------------------------------------------------- lazy drift of the sources (host) ----
-extern "C" int gl_gadget_drift(const gl_gadget_layout *lay, void *Pv, void *SphPv, long long NumPart, long long N_gas, int time1,
-			       double Timebase_interval, double MinGasHsml, long long *ndrifted)
+static int drift_particles(const gl_gadget_layout *lay, void *Pv, void *SphPv, const int *list, long long nlist, long long N_gas,
+			   int time1, double Timebase_interval, double MinGasHsml, long long *ndrifted)
 {
   const gl_gadget_layout L = *lay;
   char *P = (char *) Pv, *S = (char *) SphPv;
   std::atomic<long long> moved{0}, ahead{0};
-  HostPool::get().run(NumPart, PACK_CHUNK, [&, L, P, S](long long, long long a, long long b) {
+  HostPool::get().run(nlist, PACK_CHUNK, [&, L, P, S](long long, long long a, long long b) {
     long long m = 0, bad = 0;
-    for(long long i = a; i < b; i++)
+    for(long long k = a; k < b; k++)
       {
+	const long long i = list ? list[k] : k;
 	char *pi = P + i * L.p_stride;
 	const int type = *(const short *) (pi + L.p_Type);
 	if(type == 3) continue;	// predict.c:134 (-DVIRTUAL)
@@ -1049,6 +1050,21 @@ extern "C" int gl_gadget_drift(const gl_gadget_layout *lay, void *Pv, void *SphP
   });
   if(ndrifted) *ndrifted = moved.load();
   return ahead.load() ? 1 : 0;
+}
+
+extern "C" int gl_gadget_drift(const gl_gadget_layout *lay, void *P, void *SphP, long long NumPart, long long N_gas, int time1,
+			       double Timebase_interval, double MinGasHsml, long long *ndrifted)
+{
+  return drift_particles(lay, P, SphP, nullptr, NumPart, N_gas, time1, Timebase_interval, MinGasHsml, ndrifted);
+}
+
+// the drift of the ACTIVE particles at a synchronisation point (find_next_sync_point_and_drift, run.c:325-329: "drift the
+// active particles, others will be drifted on the fly if needed"): only the listed particles are touched
+extern "C" int gl_gadget_drift_list(const gl_gadget_layout *lay, void *P, void *SphP, const int *list, long long nlist, long long N_gas,
+				    int time1, double Timebase_interval, double MinGasHsml, long long *ndrifted)
+{
+  if(nlist > 0 && !list) return 1;
+  return drift_particles(lay, P, SphP, list, nlist, N_gas, time1, Timebase_interval, MinGasHsml, ndrifted);
 }
 
 // ---------------------------------------------------------------- reorder_gas / reorder_particles (host) ----

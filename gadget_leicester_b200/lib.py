@@ -109,7 +109,7 @@ EXPORTS = [
     "gl_set_tree_reconstruct_flag", "gl_get_gravity", "gl_get_density", "gl_get_hydro", "gl_get_pair_counts",
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
     "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree", "gl_gadget_drift", "gl_gadget_reorder",
-    "gl_snapshot_write", "gl_snapshot_read", "gl_snapshot_read_header", "gl_gadget_advance_and_find_timesteps", "gl_gadget_peano_hilbert_order", "gl_domain_top_tree", "gl_gadget_domain_keys", "gl_gadget_costfactors", "gl_domain_split",
+    "gl_snapshot_write", "gl_snapshot_read", "gl_snapshot_read_header", "gl_gadget_advance_and_find_timesteps", "gl_gadget_drift_list", "gl_gadget_peano_hilbert_order", "gl_domain_top_tree", "gl_gadget_domain_keys", "gl_gadget_costfactors", "gl_domain_split",
 ]
 
 _lib = None
@@ -181,6 +181,8 @@ def load_library():
                                       C.c_longlong, vp, vp, C.c_char_p, C.c_int]
     lib.gl_domain_top_tree.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, C.c_double, C.POINTER(GLTopNode), C.c_int,
                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.gl_gadget_drift_list.argtypes = [C.POINTER(GLGadgetLayout), vp, vp, vp, C.c_longlong, C.c_longlong, C.c_int, C.c_double,
+                                         C.c_double, C.POINTER(C.c_longlong)]
     lib.gl_gadget_domain_keys.argtypes = [C.POINTER(GLGadgetLayout), vp, C.c_longlong, vp, vp, vp, vp, vp]
     lib.gl_gadget_costfactors.argtypes = [C.POINTER(GLGadgetLayout), vp, C.c_longlong, vp]
     lib.gl_domain_split.argtypes = [C.POINTER(GLTopNode), C.c_int, vp, vp, C.c_longlong, C.c_int, vp, vp, vp, vp]

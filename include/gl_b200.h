@@ -196,6 +196,10 @@ int gl_gadget_compute_accelerations(gl_ctx * ctx, void *P, void *SphP, long long
  * time1 (endrun(12) in the reference).  *ndrifted <- number of particles moved. */
 int gl_gadget_drift(const gl_gadget_layout * lay, void *P, void *SphP, long long NumPart, long long N_gas, int time1,
 		    double Timebase_interval, double MinGasHsml, long long *ndrifted);
+/* The same for the particles of a list only - the drift of the ACTIVE particles at a synchronisation point
+ * (find_next_sync_point_and_drift, run.c:325-329); everybody else is left for the lazy drift. */
+int gl_gadget_drift_list(const gl_gadget_layout * lay, void *P, void *SphP, const int *list, long long nlist, long long N_gas,
+			 int time1, double Timebase_interval, double MinGasHsml, long long *ndrifted);
 /* The second half of peano_hilbert_order() (peano.c:25-92 -> reorder_gas :106, reorder_particles :148): permute the
  * structs so that new P[k] = old P[order[k]] (order from gl_peano_hilbert_order: gas block and the rest ordered
  * separately), SphP[] alongside for the gas block.  The reference follows permutation cycles in place, one struct at a

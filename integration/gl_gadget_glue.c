@@ -589,6 +589,24 @@ void advance_and_find_timesteps(void)
   free(old);
   CPU_Step[CPU_TIMELINE] += measure_time();
 }
+
+/* The one loop of find_next_sync_point_and_drift() that scales with the particle number (run.c:325-329):
+ *     for(i = FirstActiveParticle, NumForceUpdate = 0; i >= 0; i = NextActiveParticle[i])
+ *       { drift_particle(i, All.Ti_Current); NumForceUpdate++; }
+ * A maintainer replaces it by   NumForceUpdate = gl_drift_active_particles();   (the function itself is all
+ * bookkeeping of the time line and stays the reference's). */
+int gl_drift_active_particles(void)
+{
+  int i, n, *act;
+  for(i = FirstActiveParticle, n = 0; i >= 0; i = NextActiveParticle[i]) n++;
+  act = (int *) malloc(sizeof(int) * (n > 0 ? n : 1));
+  for(i = FirstActiveParticle, n = 0; i >= 0; i = NextActiveParticle[i]) act[n++] = i;
+  gl_fill_layout();
+  if(gl_gadget_drift_list(&GL_Layout, P, SphP, act, n, N_gas, All.Ti_Current, All.Timebase_interval, All.MinGasHsml, NULL))
+    endrun(12);
+  free(act);
+  return n;
+}
 #endif /* GL_TIMESTEP */
 
 #ifdef GL_PEANO_ORDER

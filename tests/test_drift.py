@@ -103,3 +103,31 @@ def test_host_peano_hilbert_order_is_the_reference_stable_sort():
         assert lib.gl_gadget_peano_hilbert_order(C.byref(lay), L._ptr(Pb), L._ptr(Sb), n, ngas, L._ptr(keys), L._ptr(order)) == 0
         assert np.array_equal(order, want)
         assert (Pb.reshape(n, ps_) == want_P).all() and (Sb[: ngas * ss_].reshape(ngas, ss_) == want_S).all()
+
+
+def test_drift_of_a_list_touches_only_the_listed_particles():
+    """gl_gadget_drift_list = the drift loop of find_next_sync_point_and_drift (run.c:325-329): the listed particles end
+    up exactly where the reference's drift_particle puts them, everything else keeps every byte."""
+    z = np.load(FIX)
+    t0, t1, tbi = z["times"]
+    a = _arrays(z, "pre")
+    lay_d = aos.layout()
+    before_P = np.array(a.P, copy=True).reshape(a.NumPart, lay_d["p_stride"])
+    before_S = np.array(a.SphP, copy=True).reshape(-1, lay_d["sph_stride"])[: a.N_gas]
+    stale = np.flatnonzero(z["pre_Ti_current"] != int(t1))
+    chosen = np.ascontiguousarray(stale[::2][::-1], dtype=np.int32)          # every other stale particle, in reverse order
+    lib = L.load_library()
+    lay = aos.layout_struct()
+    nd = C.c_longlong(0)
+    rc = lib.gl_gadget_drift_list(C.byref(lay), L._ptr(a.P), L._ptr(a.SphP), L._ptr(chosen), chosen.size, a.N_gas, int(t1), float(tbi),
+                                  float(z["mingashsml"][0]), C.byref(nd))
+    assert rc == 0 and nd.value == chosen.size
+    for name, f, dt, c in P_FIELDS:
+        assert (a.pview(f, dt, c)[chosen] == z["post_" + name][chosen]).all(), name
+    for name, f, dt, c in S_FIELDS:
+        assert (a.sview(f, dt, c)[chosen] == z["post_" + name][chosen]).all(), name
+    rest = np.ones(a.NumPart, bool)
+    rest[chosen] = False
+    after_P = np.asarray(a.P).reshape(a.NumPart, lay_d["p_stride"])
+    after_S = np.asarray(a.SphP).reshape(-1, lay_d["sph_stride"])[: a.N_gas]
+    assert (after_P[rest] == before_P[rest]).all() and (after_S[rest[: a.N_gas]] == before_S[rest[: a.N_gas]]).all()
