@@ -446,6 +446,10 @@ int main(int argc, char **argv)
     put("", "top_n", 'i', 2, 1, nn);
     put("", "top_StartKey", 'q', NTopnodes, 1, sk); put("", "top_Size", 'q', NTopnodes, 1, sz);
     put("", "top_Daughter", 'i', NTopnodes, 1, da); put("", "top_Leaf", 'i', NTopnodes, 1, lf);
+    /* the split of the leaves into MULTIPLEDOMAINS * NTask stretches and their owners (domain.c:1075, :1153) */
+    put("", "top_StartList", 'i', MULTIPLEDOMAINS * NTask, 1, DomainStartList);
+    put("", "top_EndList", 'i', MULTIPLEDOMAINS * NTask, 1, DomainEndList);
+    put("", "top_DomainTask", 'i', NTopleaves, 1, DomainTask);
     {
       double dom[5] = { DomainCorner[0], DomainCorner[1], DomainCorner[2], DomainFac, (double) (int) (All.TopNodeAllocFactor * All.MaxPart + 1) };
       put("", "top_domain", 'd', 5, 1, dom);

@@ -103,7 +103,7 @@ def test_reference_host_with_the_glue_domain_decomposition(name):
     ops = "K T S D R G N" if (ps["type"] == 0).any() else "K T R G N"        # (no gas: no density pass)
     want = util.run_oracle(util.REF_HARNESS, ps, par, ops)
     got = util.run_oracle(REF_HOST_DROPIN, ps, par, ops)
-    assert set(got) == set(want)
+    assert set(got) == set(want) and {"top_StartKey", "top_Leaf", "top_StartList", "top_EndList", "top_DomainTask"} <= set(want)
     compared = 0
     for k in want:
         if "time" in k or "CPU_Step" in k:
