@@ -643,7 +643,7 @@ void peano_hilbert_order(void)
 void domain_Decomposition(void)
 {
   int i, nn = 0, nl = 0, rc;
-  double *cost, dlen, dfac;
+  double *cost, dlen, dfac, tm[8];
   gl_topnode *nodes;
 
   if(NTask != 1)
@@ -652,6 +652,7 @@ void domain_Decomposition(void)
     return;
   CPU_Step[CPU_MISC] += measure_time();
   gl_fill_layout();
+  tm[0] = second();
   if(gl_gadget_drift(&GL_Layout, P, SphP, NumPart, N_gas, All.Ti_Current, All.Timebase_interval, All.MinGasHsml, NULL))
     endrun(12);			/* domain.c:120-122 */
   force_treefree();
@@ -664,6 +665,7 @@ void domain_Decomposition(void)
   if(ThisTask == 0)
     printf("domain decomposition... (presently allocated=%g MB)\n", AllocatedBytes / (1024.0 * 1024.0));
   cost = (double *) malloc(sizeof(double) * (NumPart > 0 ? NumPart : 1));
+  tm[1] = second();
   do
     {
       domain_allocate();
@@ -685,8 +687,10 @@ void domain_Decomposition(void)
 	gl_fail("gl_gadget_domain_keys");
       DomainLen = dlen;
       DomainFac = dfac;
+      tm[2] = second();
       nodes = (gl_topnode *) malloc(sizeof(gl_topnode) * MaxTopNodes);
       rc = gl_domain_top_tree((gl_peanokey *) Key, cost, NumPart, NTask, MULTIPLEDOMAINS, TOPNODEFACTOR, nodes, MaxTopNodes, &nn, &nl);
+      tm[3] = second();
       if(rc == 0)
 	{
 	  NTopnodes = nn;
@@ -728,13 +732,21 @@ void domain_Decomposition(void)
   if(ThisTask == 0)
     printf("domain decomposition done. \n");
   CPU_Step[CPU_DOMAIN] += measure_time();
+  tm[4] = second();
   peano_hilbert_order();
+  tm[5] = second();
   CPU_Step[CPU_PEANO] += measure_time();
   myfree(Key);
   memmove(TopNodes + NTopnodes, DomainTask, NTopnodes * sizeof(int));
   TopNodes = (struct topnode_data *) myrealloc(TopNodes, NTopnodes * sizeof(struct topnode_data) + NTopnodes * sizeof(int));
   DomainTask = (int *) (TopNodes + NTopnodes);
   force_treeallocate((int) (All.TreeAllocFactor * All.MaxPart) + NTopnodes, All.MaxPart);
+  tm[6] = second();
   reconstruct_timebins();
+  tm[7] = second();
+  if(getenv("GL_DEBUG_E2E"))
+    fprintf(stderr, "domain_Decomposition: drift+free %.1f ms, costs+keys %.1f, top tree %.1f, split %.1f, peano order %.1f, "
+	    "tree allocate %.1f, time bins %.1f\n", (tm[1] - tm[0]) * 1e3, (tm[2] - tm[1]) * 1e3, (tm[3] - tm[2]) * 1e3,
+	    (tm[4] - tm[3]) * 1e3, (tm[5] - tm[4]) * 1e3, (tm[6] - tm[5]) * 1e3, (tm[7] - tm[6]) * 1e3);
 }
 #endif /* GL_DOMAIN */
