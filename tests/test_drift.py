@@ -61,6 +61,25 @@ def test_library_drift_equals_reference_drift_particle():
     assert lib.gl_gadget_drift(C.byref(lay), L._ptr(a.P), L._ptr(a.SphP), a.NumPart, a.N_gas, int(t1) - 1, float(tbi), 0.0, None) != 0
 
 
+def test_drift_over_many_work_items():
+    """the same fixture twelve times over: 24 000 particles, several work items of the host pool"""
+    z0 = np.load(FIX)
+    n0 = z0["pre_Pos"].shape[0]
+    z = {k: (np.concatenate([z0[k]] * 12) if (k.startswith(("pre_", "post_")) and z0[k].shape[0] == n0) else z0[k]) for k in z0.files}
+    t0, t1, tbi = z["times"]
+    a = _arrays(z, "pre")
+    lib = L.load_library()
+    lay = aos.layout_struct()
+    nd = C.c_longlong(0)
+    assert lib.gl_gadget_drift(C.byref(lay), L._ptr(a.P), L._ptr(a.SphP), a.NumPart, a.N_gas, int(t1), float(tbi),
+                               float(z["mingashsml"][0]), C.byref(nd)) == 0
+    assert nd.value == int((z["pre_Ti_current"] != int(t1)).sum())
+    for name, f, dt, c in P_FIELDS:
+        assert (a.pview(f, dt, c) == z["post_" + name]).all(), name
+    for name, f, dt, c in S_FIELDS:
+        assert (a.sview(f, dt, c) == z["post_" + name]).all(), name
+
+
 def test_reorder_permutes_structs_like_the_reference():
     """gl_gadget_reorder = reorder_gas + reorder_particles (peano.c:106, :148): new P[k] = old P[order[k]], SphP[] with
     the gas block, every byte of every struct."""

@@ -49,9 +49,26 @@ def test_writer_without_gas_and_with_one_type(tmp_path):
     assert _ours(a, par, tmp_path)[1] == U.reference_write(a, par, str(tmp_path))
 
 
+@needs_ref
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_writer_and_reader_at_a_size_that_spans_many_work_items(tmp_path, fmt):
+    # 140 001 particles: several index stretches (65 536) and well over a hundred fused work items (1 024) per type
+    a = U.particle_arrays(n=140001, ngas=90001, seed=5, zero_u=100)
+    par = _write_par(fmt, 1, 1, (0, 0.5, 0, 0, 0, 0))
+    ref = U.reference_write(a, par, str(tmp_path))
+    fn, ours = _ours(a, par, tmp_path)
+    assert ours == ref
+    _compare_read(fn, dict(format=fmt, CoolingOn=1, StarformationOn=1, RestartFlag=2, MinEgySpec=0.35), tmp_path, max_part=150000)
+    _compare_read(fn, dict(format=fmt, CoolingOn=1, StarformationOn=1, RestartFlag=0, MinEgySpec=0.35, InitGasTemp=30.0), tmp_path,
+                  max_part=150000)
+
+
 def _compare_read(fn, par_kw, tmp_path, max_part=200):
-    par_ref, par_ours = snapshot.io_params(**par_kw), snapshot.io_params(**par_kw)
+    par_ref = snapshot.io_params(**par_kw)
     want, meta = U.reference_read(fn, par_ref, str(tmp_path))
+    if par_kw.get("InitGasTemp", 0) > 0 and par_kw.get("InitGasU") is None:
+        par_kw = dict(par_kw, InitGasU=meta["InitGasU"])          # the glue computes it like read_ic.c:181-192; here: taken over
+    par_ours = snapshot.io_params(**par_kw)
     a, hdr = snapshot.read_snapshot(fn, par_ours, max_part)
     assert (a.NumPart, a.N_gas) == (int(meta["NumPart"]), int(meta["N_gas"]))
     got = U.read_fields(a, par_ours.RestartFlag, bool(par_ours.CoolingOn))

@@ -137,6 +137,33 @@ def test_library_kick_equals_reference_advance_and_find_timesteps():
             assert np.array_equal(got, want), name
 
 
+def _tiled(z, reps):
+    """the fixture `reps` times over (gas blocks first, as P[] wants them): enough particles for several work items"""
+    ng = int((z["pre_Type"] == 0).sum())
+    out = {}
+    for k in z.files:
+        v = z[k]
+        if k.startswith(("pre_", "post_")) and v.shape[0] == z["pre_Type"].shape[0]:
+            out[k] = np.concatenate([np.concatenate([v[:ng]] * reps), np.concatenate([v[ng:]] * reps)])
+        elif k.startswith(("pre_", "post_")) and v.shape[0] == ng:
+            out[k] = np.concatenate([v] * reps)
+        else:
+            out[k] = v
+    return out
+
+
+def test_kick_over_many_work_items():
+    z = np.load(FIX)
+    zt = _tiled(z, 12)                                      # 18 480 particles: five work items of 4 096
+    a, t = _arrays(zt), _params(z)
+    rc, msg = _call(a, t, np.arange(a.NumPart, dtype=np.int32)[::-1])          # any order of the active list will do
+    assert rc == 0, msg
+    for name, f, dt, c in P_FIELDS:
+        assert (a.pview(f, dt, c) == zt["post_" + name]).all(), name
+    for name, f, dt, c in S_FIELDS:
+        assert (a.sview(f, dt, c) == zt["post_" + name]).all(), name
+
+
 def test_subset_of_active_particles_leaves_the_others_alone():
     z = np.load(FIX)
     a, t = _arrays(z), _params(z)
