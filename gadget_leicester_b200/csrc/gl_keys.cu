@@ -58,11 +58,9 @@ const Affine3 kChild[8] = {
   {{1, 2, 4}, 6}, {{1, 2, 4}, 6}, {{4, 2, 1}, 0}, {{4, 2, 1}, 5}
 };
 
-const HilbertTables &hilbert_tables()
+HilbertTables build_hilbert_tables()
 {
-  static HilbertTables T;
-  static bool done = false;
-  if(done) return T;
+  HilbertTables T;
   Affine3 states[64];
   int ns = 1;
   states[0] = Affine3{{1, 2, 4}, 0};
@@ -83,7 +81,14 @@ const HilbertTables &hilbert_tables()
 	T.next[s][pix] = (unsigned char) id;
       }
   T.nstates = ns;		// 24 for this curve
-  done = true;
+  return T;
+}
+
+// built once; the initialisation of a function-local static is thread-safe (the scalar key function is called from the
+// host pool's workers, gl_gadget_domain_keys)
+const HilbertTables &hilbert_tables()
+{
+  static const HilbertTables T = build_hilbert_tables();
   return T;
 }
 }				// namespace
