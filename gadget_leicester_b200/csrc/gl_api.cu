@@ -120,6 +120,11 @@ extern "C" int gl_load_particles(gl_ctx *c, long long n, const double *pos, cons
   float ms;
   cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]);
   c->st.ms_h2d = ms;
+  if(c->res_count >= 0 && c->res_first + c->res_count > n)
+    {				// a result range set for a larger particle set does not survive the new one
+      c->res_first = 0;
+      c->res_count = -1;
+    }
   c->n = n;
   c->tree_valid = false;
   c->tree_flag = true;
@@ -255,6 +260,11 @@ extern "C" int gl_load_particles_gathered(gl_ctx *c, long long n, int world, lon
   GL_LAUNCH_COUNT(c);
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   GL_CUDA(c, cudaGetLastError());
+  if(c->res_count >= 0 && c->res_first + c->res_count > n)
+    {
+      c->res_first = 0;
+      c->res_count = -1;
+    }
   c->n = n;
   c->tree_valid = false;
   c->tree_flag = true;
@@ -425,10 +435,20 @@ extern "C" int gl_set_targets(gl_ctx *c, const int *index, long long n, int wher
   return 0;
 }
 
-__global__ void k_mark(long long nt, const int *__restrict__ tin, const int *__restrict__ inv, int *__restrict__ flag)
+// An index outside [0, n) is reported through *bad instead of being dereferenced (the reference would simply never
+// list such a particle; an out-of-bounds device access would leave a sticky error and kill the context).
+__global__ void k_mark(long long nt, const int *__restrict__ tin, const int *__restrict__ inv, int *__restrict__ flag, long long n,
+		       int *__restrict__ bad)
 {
   long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(i < nt) flag[inv[tin[i]]] = 1;
+  if(i >= nt) return;
+  const int t = tin[i];
+  if(t < 0 || t >= n)
+    {
+      *bad = 1;
+      return;
+    }
+  flag[inv[t]] = 1;
 }
 
 // flags: bit0 target, bit1 SPH target (density_isactive, density.c:1035-1057), bit2 gas target
@@ -449,10 +469,19 @@ __global__ void k_classify(long long n, const int *__restrict__ cand, const int 
   f_gas[k] = f && ty == 0;
 }
 
-__global__ void k_list_candidates(long long nt, const int *__restrict__ tin, const int *__restrict__ inv, int *__restrict__ cand)
+__global__ void k_list_candidates(long long nt, const int *__restrict__ tin, const int *__restrict__ inv, int *__restrict__ cand,
+				  long long n, int *__restrict__ bad)
 {
   long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(k < nt) cand[k] = inv[tin[k]];
+  if(k >= nt) return;
+  const int t = tin[k];
+  if(t < 0 || t >= n)
+    {
+      *bad = 1;
+      cand[k] = 0;
+      return;
+    }
+  cand[k] = inv[t];
 }
 
 static int select_flagged(gl_ctx *c, const int *items, const int *flags, int *out, long long n, long long *count)
@@ -484,6 +513,9 @@ int gl_prepare_targets(gl_ctx *c)
   int all = c->n_tgt_in < 0;
   const int *cand;
   long long ncand = n;
+  int *bad = c->scan_tmp_i.p + 62;
+  const bool have_list = !all;
+  if(have_list) GL_CUDA(c, cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
   if(!all && c->tgt_ordered)
     {
       // the caller's list order is kept: candidates = the list itself, every one of them a target
@@ -491,7 +523,7 @@ int gl_prepare_targets(gl_ctx *c)
       if(ncand > n) return c->fail("targets: ordered list longer than the particle set");
       if(ncand > 0)
 	{
-	  k_list_candidates<<<gl_grid(ncand, 256), 256, 0, c->stream>>>(ncand, c->tgt_in.p, c->inv.p, mark);
+	  k_list_candidates<<<gl_grid(ncand, 256), 256, 0, c->stream>>>(ncand, c->tgt_in.p, c->inv.p, mark, n, bad);
 	  GL_LAUNCH_COUNT(c);
 	}
       cand = mark;
@@ -506,12 +538,19 @@ int gl_prepare_targets(gl_ctx *c)
 	  GL_CUDA(c, cudaMemsetAsync(mark, 0, n * sizeof(int), c->stream));
 	  if(c->n_tgt_in > 0)
 	    {
-	      k_mark<<<gl_grid(c->n_tgt_in, 256), 256, 0, c->stream>>>(c->n_tgt_in, c->tgt_in.p, c->inv.p, mark);
+	      k_mark<<<gl_grid(c->n_tgt_in, 256), 256, 0, c->stream>>>(c->n_tgt_in, c->tgt_in.p, c->inv.p, mark, n, bad);
 	      GL_LAUNCH_COUNT(c);
 	    }
 	}
     }
   c->n_tgt = c->n_tgt_sph = c->n_tgt_gas = 0;
+  if(have_list)
+    {
+      int hbad = 0;
+      GL_CUDA(c, cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      if(hbad) return c->fail("targets: the list holds an index outside [0, n) of the loaded particle set");
+    }
   if(ncand > 0)
     {
       k_classify<<<gl_grid(ncand, 256), 256, 0, c->stream>>>(ncand, cand, c->s_type.p, c->in_timebin.p, c->perm.p, all, mark, f0, f1, f2);

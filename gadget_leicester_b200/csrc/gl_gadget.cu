@@ -305,6 +305,11 @@ static int ensure_copy_streams(gl_ctx *c)
 
 static void mark_loaded(gl_ctx *c, long long n, long long ngas)
 {
+  if(c->res_count >= 0 && c->res_first + c->res_count > n)
+    {
+      c->res_first = 0;
+      c->res_count = -1;
+    }
   c->n = n;
   c->g_numpart = n;
   c->g_ngas = ngas;

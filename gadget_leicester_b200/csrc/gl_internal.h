@@ -86,6 +86,8 @@ struct gl_ctx
   gl_domain dom{};
   long long kernel_launches = 0;
   gl_stats st{};
+  // once-per-device set-up that must not be process-global: a process may hold contexts on several GPUs
+  bool tables_up = false, attr_density = false, attr_hydro = false;
 
   // ---- input-order particle state (index = P[] index) ----
   DBuf<double> in_pos, in_vel, in_mass, in_hsml, in_oldacc, in_entropy, in_dtentropy;

@@ -120,13 +120,12 @@ __constant__ unsigned char c_hnext[24 * 8];
 
 static int upload_tables(gl_ctx *c)
 {
-  static bool up = false;
-  if(up) return 0;
+  if(c->tables_up) return 0;	// per context: __constant__ memory is per device, and a process may open several GPUs
   const HilbertTables &T = hilbert_tables();
   if(T.nstates != 24) return c->fail("hilbert automaton closure != 24 states");
   GL_CUDA(c, cudaMemcpyToSymbol(c_hsub, T.sub, 24 * 8));
   GL_CUDA(c, cudaMemcpyToSymbol(c_hnext, T.next, 24 * 8));
-  up = true;
+  c->tables_up = true;
   return 0;
 }
 

@@ -1100,11 +1100,10 @@ int gls_density(gl_ctx *c)
   GL_CUDA(c, c->fat_state.ensure(FAT_MAX));
   if(nt > 0)
     {
-      static bool attr_done = false;
-      if(!attr_done)
+      if(!c->attr_density)	// per context (= per device), not per process
 	{
 	  GL_CUDA(c, cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (SPH_WARPS * sizeof(WarpStage))));
-	  attr_done = true;
+	  c->attr_density = true;
 	}
       k_density<<<gl_grid(nt, SPH_BLOCK), SPH_BLOCK, SPH_WARPS * sizeof(WarpStage), c->stream>>>(
 	c->tgt_sph.p, nt, (int) c->nentries, c->e_next.p, c->e_B.p, c->e_rng.p, c->n_child.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
@@ -1371,11 +1370,10 @@ int gls_hydro_begin(gl_ctx *c)
 int gls_hydro_launch(gl_ctx *c, const int *tgt, long long nt)
 {
   if(nt <= 0) return 0;
-  static bool attr_done = false;
-  if(!attr_done)
+  if(!c->attr_hydro)
     {
       GL_CUDA(c, cudaFuncSetAttribute(k_hydro, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (SPH_WARPS * sizeof(WarpStage))));
-      attr_done = true;
+      c->attr_hydro = true;
     }
   gl_dparams dp = gl_make_dparams(c);
   k_hydro<<<gl_grid(nt, SPH_BLOCK), SPH_BLOCK, SPH_WARPS * sizeof(WarpStage), c->stream>>>(tgt, nt, (int) c->nentries, c->e_next.p, c->e_B.p,

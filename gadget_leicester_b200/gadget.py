@@ -47,6 +47,7 @@ class ForcePath:
 
     def set_ErrTolTheta(self, theta):
         """All.ErrTolTheta (gravtree.c:396-397 sets it to 0 after the first call)."""
+        self.params["ErrTolTheta"] = float(theta)
         self._gp.ErrTolTheta = theta
         self._chk(self._lib.gl_set_params(self._ctx, C.byref(self._gp)))
 
@@ -140,8 +141,17 @@ class ForcePath:
         return tab
 
     # -- the force entry points ------------------------------------------------------------
+    def _relative_criterion_engaged(self):
+        """gravtree.c:396-397: after a force computation with TypeOfOpeningCriterion == 1 the reference leaves
+        All.ErrTolTheta = 0 for good.  The library does that in its own copy of the parameters; mirror it here so that
+        a later set_params() (Ti_Current per step, ...) does not switch back to the Barnes-Hut criterion."""
+        if int(self.params.get("TypeOfOpeningCriterion", 0)) == 1:
+            self.params["ErrTolTheta"] = 0.0
+            self._gp.ErrTolTheta = 0.0
+
     def gravity_tree(self):
         self._chk(self._lib.gl_gravity_tree(self._ctx))
+        self._relative_criterion_engaged()
         acc = np.zeros((self.N, 3))
         old = np.zeros(self.N)
         cost = np.zeros(self.N, dtype=np.float32)
@@ -178,6 +188,7 @@ class ForcePath:
     def compute_accelerations(self, mode=0):
         """accel.c:27 (force part): gravity (twice at Ti_Current==0), density, hmax, hydro."""
         self._chk(self._lib.gl_compute_accelerations(self._ctx, int(mode)))
+        self._relative_criterion_engaged()
 
     def compute_potential(self):
         """potential.c:22: P[].p.Potential for all particles with the current tree / OldAcc / criterion."""
@@ -189,6 +200,7 @@ class ForcePath:
     # device-resident variants used by bench.py's `value` leg (no result download)
     def gravity_tree_nocopy(self):
         self._chk(self._lib.gl_gravity_tree(self._ctx))
+        self._relative_criterion_engaged()
 
     def density_nocopy(self):
         self._chk(self._lib.gl_density(self._ctx))

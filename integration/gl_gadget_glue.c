@@ -157,14 +157,32 @@ static void gl_pull(void)
 
 static int gl_loaded_for = -1;	/* All.NumCurrentTiStep the device copy belongs to */
 
+/* This binding covers ONE rank: the library's multi-rank form (gl_comm_init + the locally-essential exchange,
+ * include/gl_b200.h) needs every rank's sources, which the three entry points below do not exchange.  The reference's
+ * own functions work at any NTask (gravtree.c:175-347, density.c:193-342, hydra.c:274-520), so a multi-rank run must
+ * stop here instead of silently computing forces from the local particles only. */
+static void gl_require_single_rank(const char *where)
+{
+  if(NTask != 1)
+    {
+      printf("libgl_b200 glue: %s() of this binding handles NTask == 1 only (NTask = %d)\n", where, NTask);
+      fflush(stdout);
+      endrun(8801);
+    }
+}
+
 static void gl_ensure_loaded(void)
 {
+  gl_attach();
+  /* the active list first: gl_gadget_pull() uploads the SphP state of the INACTIVE particles (hydro reads the density /
+   * pressure of every neighbour, hydra.c:1236) only when the list of THIS step is a subset - with the previous step's
+   * list still set, a full step followed by a sub-step would read stale, undrifted values */
+  gl_send_active_list();
   if(gl_loaded_for != All.NumCurrentTiStep || TreeReconstructFlag)
     {
       gl_pull();
       gl_loaded_for = All.NumCurrentTiStep;
     }
-  gl_send_active_list();
 }
 
 #ifndef GL_NO_FORCE_PATH	/* (a build that only takes the host-side pieces below: the CPU test binaries of oracle/refbuild) */
@@ -172,6 +190,7 @@ void gravity_tree(void)
 {
   double t0 = second();
   int nactive;
+  gl_require_single_rank("gravity_tree");
   gl_ensure_loaded();
   nactive = gl_send_active_list();
   gl_sync_params();
@@ -247,6 +266,7 @@ void gravity_tree(void)
 void density(void)
 {
   double t0 = second();
+  gl_require_single_rank("density");
   gl_ensure_loaded();
   if(gl_density(GL)) gl_fail("gl_density");
   if(gl_gadget_push(GL, P, SphP, 2)) gl_fail("gl_gadget_push");
@@ -256,6 +276,7 @@ void density(void)
 void hydro_force(void)
 {
   double t0 = second();
+  gl_require_single_rank("hydro_force");
   gl_ensure_loaded();
   if(gl_force_update_hmax(GL)) gl_fail("gl_force_update_hmax");
   if(gl_hydro_force(GL)) gl_fail("gl_hydro_force");
@@ -270,6 +291,7 @@ void hydro_force(void)
  * reference (accel.c:176-256) still runs on the host and still finds its inputs in P[]/SphP[] */
 void gl_compute_force_path(int mode)
 {
+  gl_require_single_rank("compute_accelerations");
   gl_attach();
   gl_sync_params();
   gl_send_active_list();
