@@ -55,6 +55,7 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->s_type.release(); c->lev_c.release(); c->ncnt.release(); c->noff.release(); c->n_first.release(); c->n_end.release();
   c->n_parent.release(); c->n_level.release(); c->lev_list.release(); c->n_sm.release(); c->n_cl.release();
   c->n_aux.release(); c->p_father.release(); c->scan_tmp_i.release(); c->e_next.release(); c->e_A.release();
+  c->e_F0.release(); c->e_F1.release(); c->e_F2.release(); c->grav_scale.release();
   c->e_B.release(); c->e_C.release(); c->e_hmax.release(); c->tgt_in.release(); c->tgt_sorted.release();
   c->tgt_sph.release(); c->tgt_flag.release(); c->tgt_gas.release(); c->o_acc.release(); c->o_oldacc.release();
   c->o_numngb.release(); c->o_density.release(); c->o_dhsml.release(); c->o_divvel.release(); c->o_curlvel.release();

@@ -17,45 +17,98 @@
 
 gl_dparams gl_make_dparams(const gl_ctx *c);
 
-struct GravTarget
-{
-  double x, y, z, aold, soft;
-};
-
 #ifndef GRAV_MIN_BLOCKS
-#define GRAV_MIN_BLOCKS 12	// 40 registers, 48 warps per SM: 3.15 ms for the 1.6M disc (10 blocks: 3.24, 16 blocks with spills: 3.39)
+#define GRAV_MIN_BLOCKS 8	// resident 128-thread blocks per SM the walk is compiled for (64 registers)
 #endif
-template <bool BH, bool POT>
-__global__ void __launch_bounds__(GL_BLOCK, GRAV_MIN_BLOCKS)
+
+// ---- margins of the FP32 pre-test (units: domain cube [1,2) wide, total mass [1,2); u = 2^-24) --------------------
+// A coordinate difference d_f = (hi_s - hi_t) + (lo_s - lo_t) obeys |d_f - d| <= u|d| + 2^-43 (gl_split), hence
+// |r2_f - r2| <= 2^-20.8 r2 + 2^-62: the interval [r2_f - err, r2_f + err] with err = 2^-20 r2_f + 2^-58 holds the
+// reference's FP64 r2.  Every product below is rounded a few more times (<= 13 u in total); the factors (1 +- 2^-20)
+// on the node side of each comparison cover that.  A lane whose interval straddles a threshold repeats the decision
+// with the reference's own FP64 statements (node_open_exact): decisions - and interaction counts - are the reference's.
+#define GW_REL 9.5367431640625e-07f	// 2^-20
+#define GW_ABS 3.4694469519536142e-18f	// 2^-58
+#define GW_ONE_LO (1.0f - GW_REL)
+#define GW_ONE_HI (1.0f + GW_REL)
+
+// The reference's opening decision for node entry e and ONE target, in FP64, statement by statement
+// (forcetree.c:2009-2011, :2074-2137).  Returns -1 = open, else the softening length to use for the accepted node.
+template <bool BH>
+__device__ __noinline__ double node_open_exact(int e, const double4 *__restrict__ e_A, const double4 *__restrict__ e_B,
+					     const double2 *__restrict__ e_C, double px, double py, double pz, double aold,
+					     double theta, double hi)
+{
+  const double4 A = gl_ld4(&e_A[e]);
+  const double4 B = gl_ld4(&e_B[e]);
+  const double2 C = __ldg(&e_C[e]);
+  const double dx = __dsub_rn(A.x, px), dy = __dsub_rn(A.y, py), dz = __dsub_rn(A.z, pz);
+  const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  double h = hi;
+  bool open;
+  if(BH)
+    open = __dmul_rn(B.w, B.w) > __dmul_rn(__dmul_rn(r2, theta), theta);	// forcetree.c:2076
+  else
+    {
+      open = C.y > __dmul_rn(__dmul_rn(r2, r2), aold);	// forcetree.c:2085
+      if(!open)
+	{
+	  const double lim = __dmul_rn(0.60, B.w);	// forcetree.c:2094-2105
+	  if(fabs(__dsub_rn(B.x, px)) < lim && fabs(__dsub_rn(B.y, py)) < lim && fabs(__dsub_rn(B.z, pz)) < lim) open = true;
+	}
+    }
+  if(!open && h < C.x)
+    {				// forcetree.c:2124-2137
+      h = C.x;
+      if(r2 < __dmul_rn(h, h)) open = true;
+    }
+  return open ? -1.0 : h;
+}
+
+// K6.  One warp = 32 consecutive targets, marching once through the DFS entry array (warp-uniform record loads).
+// Per entry every lane takes ITS OWN opening decision - in FP32 on the split coordinates, inside error bounds that
+// make the decision certain, and in FP64 (node_open_exact) in the rare uncertain shell.  Force magnitude in FP32,
+// FP64 accumulation.
+template <bool BH, bool POT, int MINB>
+__global__ void __launch_bounds__(GL_BLOCK, MINB)
 k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const int *__restrict__ e_next,
+	       const float4 *__restrict__ e_F0, const float4 *__restrict__ e_F1, const float4 *__restrict__ e_F2,
 	       const double4 *__restrict__ e_A, const double4 *__restrict__ e_B, const double2 *__restrict__ e_C,
 	       const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
-	       const int *__restrict__ perm, const double *__restrict__ in_oldacc, double *__restrict__ o_acc,
-	       double *__restrict__ o_oldacc, float *__restrict__ o_gravcost, double *__restrict__ o_pot,
-	       unsigned long long *__restrict__ counter, gl_dparams par, int last_first)
+	       const int *__restrict__ perm, const double *__restrict__ in_oldacc, const double *__restrict__ scale,
+	       double *__restrict__ o_acc, double *__restrict__ o_oldacc, float *__restrict__ o_gravcost,
+	       double *__restrict__ o_pot, unsigned long long *__restrict__ counter, gl_dparams par, gl_domain dom, int last_first)
 {
   const int lane = threadIdx.x & 31;
   long long warp = (blockIdx.x * (long long) blockDim.x + threadIdx.x) >> 5;
   // A caller-ordered list (a Peano-Hilbert segment) ends with the few non-gas particles (the gas block comes
   // first, peano.c:37-88): the warp that mixes them with far-away gas particles marches through two unrelated
-  // parts of the tree and takes about twice as long as the others.  Started last it was a 0.7 ms tail of the
-  // 1.6M disc's walk; started first it disappears behind the rest.
+  // parts of the tree and takes about twice as long as the others.  Started first it disappears behind the rest.
   if(last_first) warp = ((nt + 31) >> 5) - 1 - warp;
   const long long t = warp * 32 + lane;
   const bool live = t >= 0 && t < nt;
+  const double S = scale[0], Ms = scale[1];
   int p = 0, ptype = 0, pin = 0;
-  double px = 0, py = 0, pz = 0, aold = 0, hi = 0;
+  float thx = 0, thy = 0, thz = 0, tlx = 0, tly = 0, tlz = 0;	// split target position
+  float hif = 0, a_lo = 0, a_hi = 0;
   if(live)
     {
       p = tgt[t];
-      double4 pm = s_pm[p];
-      px = pm.x; py = pm.y; pz = pm.z;
+      const double4 pm = s_pm[p];
       ptype = s_type[p];
       pin = perm[p];
-      aold = __dmul_rn(par.errtolforceacc, in_oldacc[pin]);	// forcetree.c:1850
-      hi = (ptype == 0) ? s_vh[p].w : par.soft[ptype];	// forcetree.c:2039-2042 / :2117-2120
+      gl_split(pm.x, dom.center[0], S, thx, tlx);
+      gl_split(pm.y, dom.center[1], S, thy, tly);
+      gl_split(pm.z, dom.center[2], S, thz, tlz);
+      const double hi = (ptype == 0) ? s_vh[p].w : par.soft[ptype];	// forcetree.c:2039-2042 / :2117-2120
+      hif = (float) (hi * S);
+      // aold = ErrTolForceAcc * OldAcc (forcetree.c:1850), in the scaled units: x Ms / S^2
+      const double aold = __dmul_rn(par.errtolforceacc, in_oldacc[pin]) * (Ms / (S * S));
+      const float af = (float) aold;
+      a_lo = af * GW_ONE_LO;
+      a_hi = af * GW_ONE_HI;
     }
-  const double theta2f = par.theta;
+  const float thetaf = (float) par.theta;
   double ax = 0, ay = 0, az = 0;
   int ninter = 0;
   int skip_until = live ? 0 : nentries;
@@ -63,49 +116,76 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
   while(e < nentries)
     {
       const int nx = __ldg(&e_next[e]);
-      const double4 A = gl_ld4(&e_A[e]);
+      const float4 F0 = __ldg(&e_F0[e]);
+      const float4 F1 = __ldg(&e_F1[e]);
       const bool active = e >= skip_until;
-      double dx = __dsub_rn(A.x, px), dy = __dsub_rn(A.y, py), dz = __dsub_rn(A.z, pz);
-      double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-      double h = hi;
+      const float dx = (F0.x - thx) + (F1.x - tlx), dy = (F0.y - thy) + (F1.y - tly), dz = (F0.z - thz) + (F1.z - tlz);
+      const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+      float hf = hif;
       bool interact = false;
       if(nx < 0)
 	{
-	  // particle leaf (forcetree.c:1906-1918, :2035-2070)
-	  const double hj = __ldg(&e_B[e].x);
-	  if(h < hj) h = hj;
+	  // particle leaf (forcetree.c:1906-1918, :2035-2070): no decision to take
+	  hf = fmaxf(hf, F1.w);
 	  interact = active;
 	  e = e + 1;
 	}
       else
 	{
-	  const double4 B = gl_ld4(&e_B[e]);
-	  const double2 C = __ldg(&e_C[e]);
+	  const float4 F2 = __ldg(&e_F2[e]);
 	  if(active)
 	    {
-	      bool open;
+	      const float err = fmaf(r2, GW_REL, GW_ABS);
+	      const float r2lo = fmaxf(r2 - err, 0.f), r2hi = r2 + err;
+	      bool open, sure;
 	      if(BH)
 		{
 		  // forcetree.c:2076  len*len > r2*theta*theta
-		  open = __dmul_rn(B.w, B.w) > __dmul_rn(__dmul_rn(r2, theta2f), theta2f);
+		  const float lq = F1.w * F1.w;
+		  const float t_hi = (r2hi * thetaf) * thetaf, t_lo = (r2lo * thetaf) * thetaf;
+		  open = lq * GW_ONE_LO > t_hi;
+		  sure = open || (lq * GW_ONE_HI < t_lo);
 		}
 	      else
 		{
 		  // forcetree.c:2085  mass*len*len > r2*r2*aold
-		  open = C.y > __dmul_rn(__dmul_rn(r2, r2), aold);
-		  if(!open)
+		  const float ml2 = (F0.w * F1.w) * F1.w;
+		  const float t_hi = (r2hi * r2hi) * a_hi, t_lo = (r2lo * r2lo) * a_lo;
+		  open = ml2 * GW_ONE_LO > t_hi;
+		  sure = open || (ml2 * GW_ONE_HI < t_lo);
+		  if(sure && !open)
 		    {
 		      // forcetree.c:2094-2105  inside the 0.6*len box around the geometric centre
-		      const double lim = __dmul_rn(0.60, B.w);
-		      if(fabs(__dsub_rn(B.x, px)) < lim && fabs(__dsub_rn(B.y, py)) < lim && fabs(__dsub_rn(B.z, pz)) < lim)
-			open = true;
+		      const float cx = fabsf(dx + F2.x), cy = fabsf(dy + F2.y), cz = fabsf(dz + F2.z);
+		      const float lim_in = F1.w * (0.6f - GW_REL), lim_out = F1.w * (0.6f + GW_REL);
+		      const bool in = cx < lim_in && cy < lim_in && cz < lim_in;
+		      const bool out = cx > lim_out || cy > lim_out || cz > lim_out;
+		      open = in;
+		      sure = in || out;
 		    }
 		}
-	      if(!open && h < C.x)
+	      if(sure && !open)
 		{
-		  // forcetree.c:2124-2137  softening guard
-		  h = C.x;
-		  if(r2 < __dmul_rn(h, h)) open = true;
+		  // forcetree.c:2124-2137  softening guard: h_i < maxsoft -> h = maxsoft, opened if r2 < h*h
+		  const float ms2 = F2.w * F2.w;
+		  if(hif < F2.w)	// monotone rounding: then h_i < maxsoft in FP64 as well
+		    {
+		      hf = F2.w;
+		      open = r2hi < ms2 * GW_ONE_LO;
+		      sure = open || (r2lo > ms2 * GW_ONE_HI);
+		    }
+		  else if(hif == F2.w)	// FP64 order unknown; it only matters when r2 < maxsoft^2 is possible
+		    sure = r2lo > ms2 * GW_ONE_HI;
+		}
+	      if(!sure)
+		{
+		  // the uncertain shell: the reference's own FP64 statements
+		  const double4 pm = s_pm[p];
+		  const double hi = (ptype == 0) ? s_vh[p].w : par.soft[ptype];
+		  const double aold = __dmul_rn(par.errtolforceacc, in_oldacc[pin]);
+		  const double hn = node_open_exact<BH>(e, e_A, e_B, e_C, pm.x, pm.y, pm.z, aold, par.theta, hi);
+		  open = hn < 0;
+		  hf = (float) (hn * S);
 		}
 	      if(!open)
 		{
@@ -119,11 +199,10 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
       if(interact)
 	{
 	  // forcetree.c:2143-2198, magnitude in FP32
-	  const float r2f = (float) r2, mf = (float) A.w, hf = (float) h;
-	  // one MUFU.RSQ gives r and 1/r^3 (2 ulp, FP32): the IEEE sqrtf + divide it replaces cost ~4x the instructions.
-	  // r2f == 0 is the target's own leaf: rinv = inf, r = NaN -> the comparison is false -> spline branch with r = 0
-	  const float rinv = rsqrtf(r2f);
-	  const float r = (r2f > 0.f) ? r2f * rinv : 0.f;
+	  const float mf = F0.w;
+	  // one MUFU.RSQ gives r and 1/r^3.  r2 == 0 is the target's own leaf: rinv = inf, r = 0 -> spline branch with u = 0
+	  const float rinv = rsqrtf(r2);
+	  const float r = (r2 > 0.f) ? r2 * rinv : 0.f;
 	  float fac;
 	  if(POT)
 	    {
@@ -159,33 +238,41 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 	  if(!POT)
 	    {
 	      const double fd = (double) fac;
-	      ax = fma(dx, fd, ax);
-	      ay = fma(dy, fd, ay);
-	      az = fma(dz, fd, az);
+	      ax = fma((double) dx, fd, ax);
+	      ay = fma((double) dy, fd, ay);
+	      az = fma((double) dz, fd, az);
 	    }
-	  if(A.w > 0) ninter++;	// forcetree.c:2214
+	  if(mf > 0.f) ninter++;	// forcetree.c:2214
 	}
     }
   if(live && POT)
     {
       // potential.c:169-184: remove the self term with All.SofteningTable, then x G (the Lambda term of :235 is 0 here)
       const double m_i = s_pm[p].w;
+      ax *= S / Ms;		// back from the scaled units: m'/r' = m/r * Ms / S
       o_pot[pin] = __dmul_rn(__dadd_rn(ax, __ddiv_rn(m_i, par.softtab[ptype])), par.G);
     }
   if(live && !POT)
     {
       // gravtree.c:388-403: OldAcc from the un-scaled acceleration, then x G (+ the Lambda term, :405-411)
+      const double un = (S * S) / Ms;	// d' m'/r'^3 = d m/r^3 * Ms / S^2
+      ax *= un; ay *= un; az *= un;
+      const double4 pm = s_pm[p];
       const double old = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
       o_oldacc[pin] = old;
-      o_acc[3ll * pin + 0] = __dadd_rn(__dmul_rn(ax, par.G), __dmul_rn(par.lambda_fac, px));
-      o_acc[3ll * pin + 1] = __dadd_rn(__dmul_rn(ay, par.G), __dmul_rn(par.lambda_fac, py));
-      o_acc[3ll * pin + 2] = __dadd_rn(__dmul_rn(az, par.G), __dmul_rn(par.lambda_fac, pz));
+      o_acc[3ll * pin + 0] = __dadd_rn(__dmul_rn(ax, par.G), __dmul_rn(par.lambda_fac, pm.x));
+      o_acc[3ll * pin + 1] = __dadd_rn(__dmul_rn(ay, par.G), __dmul_rn(par.lambda_fac, pm.y));
+      o_acc[3ll * pin + 2] = __dadd_rn(__dmul_rn(az, par.G), __dmul_rn(par.lambda_fac, pm.z));
       o_gravcost[pin] = (float) ninter;
     }
   // interaction total (timings.txt "ia/part", gravtree.c:822)
   unsigned long long tot = (unsigned long long) __reduce_add_sync(0xffffffffu, live ? ninter : 0);
   if(lane == 0 && tot && !POT) atomicAdd(&counter[0], tot);
 }
+
+#define GRAV_ARGS                                                                                                          \
+  c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_F0.p, c->e_F1.p, c->e_F2.p, c->e_A.p, c->e_B.p, c->e_C.p, c->s_pm.p, \
+    c->s_vh.p, c->s_type.p, c->perm.p, c->in_oldacc.p, c->grav_scale.p
 
 int glg_gravity(gl_ctx *c)
 {
@@ -209,15 +296,22 @@ int glg_gravity(gl_ctx *c)
       int grid = gl_grid(nt, GL_BLOCK);
       const int lf = (c->n_tgt_in >= 0 && c->tgt_ordered) ? 1 : 0;
       if(c->par.ErrTolTheta != 0)
-	k_gravity_walk<true, false><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p,
-							      c->e_B.p, c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
-							      c->perm.p, c->in_oldacc.p, c->o_acc.p, c->o_oldacc.p,
-							      c->o_gravcost.p, nullptr, c->d_counter.p, dp, lf);
+	k_gravity_walk<true, false, GRAV_MIN_BLOCKS><<<grid, GL_BLOCK, 0, c->stream>>>(GRAV_ARGS, c->o_acc.p, c->o_oldacc.p, c->o_gravcost.p, nullptr,
+							      c->d_counter.p, dp, c->dom, lf);
       else
-	k_gravity_walk<false, false><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p,
-							       c->e_B.p, c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
-							       c->perm.p, c->in_oldacc.p, c->o_acc.p, c->o_oldacc.p,
-							       c->o_gravcost.p, nullptr, c->d_counter.p, dp, lf);
+	{
+	  // tuning switch (GL_GRAV_MINB = 12 / 10 / 8 resident blocks per SM = 40 / 48 / 64 registers); default GRAV_MIN_BLOCKS
+	  static const int minb = getenv("GL_GRAV_MINB") ? atoi(getenv("GL_GRAV_MINB")) : GRAV_MIN_BLOCKS;
+	  if(minb == 12)
+	    k_gravity_walk<false, false, 12><<<grid, GL_BLOCK, 0, c->stream>>>(GRAV_ARGS, c->o_acc.p, c->o_oldacc.p, c->o_gravcost.p, nullptr,
+									       c->d_counter.p, dp, c->dom, lf);
+	  else if(minb == 10)
+	    k_gravity_walk<false, false, 10><<<grid, GL_BLOCK, 0, c->stream>>>(GRAV_ARGS, c->o_acc.p, c->o_oldacc.p, c->o_gravcost.p, nullptr,
+									       c->d_counter.p, dp, c->dom, lf);
+	  else
+	    k_gravity_walk<false, false, 8><<<grid, GL_BLOCK, 0, c->stream>>>(GRAV_ARGS, c->o_acc.p, c->o_oldacc.p, c->o_gravcost.p, nullptr,
+									      c->d_counter.p, dp, c->dom, lf);
+	}
       GL_LAUNCH_COUNT(c);
     }
   cudaEventRecord(c->ev[1], c->stream);
@@ -257,13 +351,9 @@ int glg_potential(gl_ctx *c)
   cudaEventRecord(c->ev[0], c->stream);
   int grid = gl_grid(nt, GL_BLOCK);
   if(c->par.ErrTolTheta != 0)
-    k_gravity_walk<true, true><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p, c->e_B.p,
-								c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->perm.p, c->in_oldacc.p,
-								nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp, 0);
+    k_gravity_walk<true, true, GRAV_MIN_BLOCKS><<<grid, GL_BLOCK, 0, c->stream>>>(GRAV_ARGS, nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp, c->dom, 0);
   else
-    k_gravity_walk<false, true><<<grid, GL_BLOCK, 0, c->stream>>>(c->tgt_sorted.p, nt, (int) c->nentries, c->e_next.p, c->e_A.p, c->e_B.p,
-								 c->e_C.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->perm.p, c->in_oldacc.p,
-								 nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp, 0);
+    k_gravity_walk<false, true, GRAV_MIN_BLOCKS><<<grid, GL_BLOCK, 0, c->stream>>>(GRAV_ARGS, nullptr, nullptr, nullptr, c->o_pot.p, c->d_counter.p, dp, c->dom, 0);
   GL_LAUNCH_COUNT(c);
   cudaEventRecord(c->ev[1], c->stream);
   GL_CUDA(c, cudaStreamSynchronize(c->stream));

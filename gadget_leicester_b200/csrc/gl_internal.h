@@ -129,6 +129,12 @@ struct gl_ctx
   DBuf<double2> e_C;		// node: maxsoft, mass*len*len ; particle: unused
   DBuf<double> e_hmax;		// node: hmax (for the symmetric search)
   DBuf<int2> e_rng;		// node: [first,end) range of tree-ordered particles below it
+  // FP32 walk records (gl_gravity.cu): positions as an exact grid part + a small remainder, in units that make the
+  // domain cube [1,2) wide and the total mass [1,2) (powers of two: the opening decisions do not change)
+  DBuf<float4> e_F0;		// hi(x,y,z) of s / pos, mass
+  DBuf<float4> e_F1;		// lo(x,y,z), node: len ; particle: softening length
+  DBuf<float4> e_F2;		// node: centre - s (x,y,z), maxsoft
+  DBuf<double> grav_scale;	// [0] length scale S, [1] mass scale Ms (device-written after the moments)
   // ---- targets ----
   DBuf<int> tgt_in;		// user-supplied P[] indices (or empty = all)
   std::vector<int> tgt_host;	// host copy of the same list (the drop-in scatter only touches targets)
@@ -235,6 +241,20 @@ int gl_prepare_targets(gl_ctx *c);
 static inline int gl_grid(long long n, int block) { return (int) ((n + block - 1) / block); }
 
 #ifdef __CUDACC__
+// ---- split FP32 coordinates of the gravity walk ----
+// q = (x - centre) * S lies in (-1, 1); hi = the nearest multiple of 2^-20 (exact in FP32), lo = the remainder
+// (|lo| <= 2^-21, FP32 error <= 2^-46).  A coordinate difference (hi_a - hi_b) + (lo_a - lo_b) is then good to
+// 2^-24 relative + 2^-43 absolute without any FP64 instruction in the walk.
+#define GL_SPLIT_G 9.5367431640625e-07	// 2^-20
+#define GL_SPLIT_GINV 1048576.0
+__device__ __forceinline__ void gl_split(double x, double centre, double S, float &hi, float &lo)
+{
+  const double q = (x - centre) * S;
+  const double k = rint(q * GL_SPLIT_GINV);
+  const double H = k * GL_SPLIT_G;
+  hi = (float) H;
+  lo = (float) (q - H);
+}
 // read-only 32-byte record load as two 16-byte LDG.NC
 __device__ __forceinline__ double4 gl_ld4(const double4 *p)
 {

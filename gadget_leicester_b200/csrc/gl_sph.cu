@@ -344,6 +344,8 @@ struct DensOut
 {
   double *hsml_in, *numngb, *density, *dhsml, *divvel, *curlvel, *pressure, *sinkrho, *sinkentr, *sinkvel;
   int *pairs;
+  float4 *e_F1;			// FP32 walk record of the particle's DFS entry (its softening length follows Hsml)
+  const double *grav_scale;
 };
 
 struct DensAcc
@@ -432,6 +434,7 @@ __device__ __forceinline__ void density_store(const DensAcc &A, double h, int p,
   if(ptype == 0)
     {
       e_B[(long long) p + in.noff[p + 1]].x = h;	// live Hsml for the gravity softening, forcetree.c:2046-2054
+      out.e_F1[(long long) p + in.noff[p + 1]].w = (float) (h * out.grav_scale[0]);
       double dfac = A.dhsmlrho, curl = 0, dv = A.divv;
       if(rho > 0)
 	{
@@ -1093,7 +1096,7 @@ int gls_density(gl_ctx *c)
   k_gather_d<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->perm.p, c->in_entropy.p, s_entropy);
   GL_LAUNCH_COUNT(c);
   DensOut out{c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p, c->o_pressure.p,
-	      c->o_sinkrho.p, c->o_sinkentr.p, c->o_sinkvel.p, c->o_denspairs.p};
+	      c->o_sinkrho.p, c->o_sinkentr.p, c->o_sinkvel.p, c->o_denspairs.p, c->e_F1.p, c->grav_scale.p};
   DensIn in{c->noff.p, c->in_entropy.p, c->in_dtentropy.p, c->in_timebin.p, c->in_tibegstep.p};
   gl_dparams dp = gl_make_dparams(c);
   GL_CUDA(c, c->fat_p.ensure(FAT_MAX));

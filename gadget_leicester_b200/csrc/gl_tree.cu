@@ -373,28 +373,54 @@ __global__ void k_moments_wide(int L, const int *__restrict__ lev_list, int coun
     }
 }
 
+// Scales of the FP32 walk records: S = 2^-floor(log2(DomainLen)) makes the cube [1,2) wide, Ms = 2^-floor(log2(total
+// mass)) the root mass [1,2).  Powers of two, so scaled and unscaled comparisons decide alike; FP32 then never
+// overflows or underflows whatever the unit system.
+__global__ void k_grav_scale(long long m, long long n, const double4 *__restrict__ n_sm, const double4 *__restrict__ s_pm,
+			     double domlen, double *__restrict__ scale)
+{
+  if(blockIdx.x || threadIdx.x) return;
+  double mt = (m > 0) ? n_sm[0].w : s_pm[0].w;
+  if(!(mt > 0) || !isfinite(mt)) mt = 1.0;
+  scale[0] = (domlen > 0 && isfinite(domlen)) ? exp2(-floor(log2(domlen))) : 1.0;	// one particle: a cube of size 0
+  scale[1] = exp2(-floor(log2(mt)));
+}
+
 __global__ void k_entries_particles(long long n, const int *__restrict__ noff, const double4 *__restrict__ s_pm,
 				    const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
 				    int *__restrict__ e_next, double4 *__restrict__ e_A, double4 *__restrict__ e_B,
-				    double2 *__restrict__ e_C, double *__restrict__ e_hmax, gl_dparams par)
+				    double2 *__restrict__ e_C, double *__restrict__ e_hmax, float4 *__restrict__ e_F0,
+				    float4 *__restrict__ e_F1, const double *__restrict__ scale, gl_domain dom, gl_dparams par)
 {
   long long p = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(p >= n) return;
   long long e = p + noff[p + 1];
   int ty = s_type[p];
   double soft = (ty == 0) ? s_vh[p].w : par.soft[ty];
+  const double4 pm = s_pm[p];
   e_next[e] = -1 - (int) (p * 8 + ty);
-  e_A[e] = s_pm[p];
+  e_A[e] = pm;
   e_B[e] = make_double4(soft, 0.0, 0.0, -1.0);
   e_C[e] = make_double2(0.0, 0.0);
   e_hmax[e] = 0.0;
+  const double S = scale[0], Ms = scale[1];
+  float4 f0, f1;
+  gl_split(pm.x, dom.center[0], S, f0.x, f1.x);
+  gl_split(pm.y, dom.center[1], S, f0.y, f1.y);
+  gl_split(pm.z, dom.center[2], S, f0.z, f1.z);
+  f0.w = (float) (pm.w * Ms);
+  f1.w = (float) (soft * S);
+  e_F0[e] = f0;
+  e_F1[e] = f1;
 }
 
 __global__ void k_entries_nodes(long long m, long long n, const int *__restrict__ noff, const int *__restrict__ n_first,
 				const int *__restrict__ n_end, const double4 *__restrict__ n_sm,
 				const double4 *__restrict__ n_cl, const double4 *__restrict__ n_aux,
 				int *__restrict__ e_next, double4 *__restrict__ e_A, double4 *__restrict__ e_B,
-				double2 *__restrict__ e_C, double *__restrict__ e_hmax)
+				double2 *__restrict__ e_C, double *__restrict__ e_hmax, float4 *__restrict__ e_F0,
+				float4 *__restrict__ e_F1, float4 *__restrict__ e_F2, const double *__restrict__ scale,
+				gl_domain dom)
 {
   long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(id >= m) return;
@@ -409,6 +435,16 @@ __global__ void k_entries_nodes(long long m, long long n, const int *__restrict_
   // mass * nop->len * nop->len, evaluated left to right as in forcetree.c:2085
   e_C[e] = make_double2(ax.x, __dmul_rn(__dmul_rn(sm.w, cl.w), cl.w));
   e_hmax[e] = ax.y;
+  const double S = scale[0], Ms = scale[1];
+  float4 f0, f1;
+  gl_split(sm.x, dom.center[0], S, f0.x, f1.x);
+  gl_split(sm.y, dom.center[1], S, f0.y, f1.y);
+  gl_split(sm.z, dom.center[2], S, f0.z, f1.z);
+  f0.w = (float) (sm.w * Ms);
+  f1.w = (float) (cl.w * S);
+  e_F0[e] = f0;
+  e_F1[e] = f1;
+  e_F2[e] = make_float4((float) ((cl.x - sm.x) * S), (float) ((cl.y - sm.y) * S), (float) ((cl.z - sm.z) * S), (float) (ax.x * S));
 }
 
 // particle range [a,b) below every node entry: lets the SPH walks swallow a small cell in one coalesced step
@@ -533,14 +569,21 @@ int glt_build(gl_ctx *c)
   GL_CUDA(c, c->e_B.ensure(ne));
   GL_CUDA(c, c->e_C.ensure(ne));
   GL_CUDA(c, c->e_hmax.ensure(ne));
+  GL_CUDA(c, c->e_F0.ensure(ne));
+  GL_CUDA(c, c->e_F1.ensure(ne));
+  GL_CUDA(c, c->e_F2.ensure(ne));
+  GL_CUDA(c, c->grav_scale.ensure(2));
+  k_grav_scale<<<1, 32, 0, c->stream>>>(m, n, c->n_sm.p, c->s_pm.p, c->dom.len, c->grav_scale.p);
   k_entries_particles<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->noff.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
-							      c->e_next.p, c->e_A.p, c->e_B.p, c->e_C.p, c->e_hmax.p, dp);
-  GL_LAUNCH_COUNT(c);
+							      c->e_next.p, c->e_A.p, c->e_B.p, c->e_C.p, c->e_hmax.p, c->e_F0.p,
+							      c->e_F1.p, c->grav_scale.p, c->dom, dp);
+  c->kernel_launches += 2;
   if(m > 0)
     {
       k_entries_nodes<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, n, c->noff.p, c->n_first.p, c->n_end.p, c->n_sm.p,
 							       c->n_cl.p, c->n_aux.p, c->e_next.p, c->e_A.p, c->e_B.p,
-							       c->e_C.p, c->e_hmax.p);
+							       c->e_C.p, c->e_hmax.p, c->e_F0.p, c->e_F1.p, c->e_F2.p, c->grav_scale.p,
+							       c->dom);
       GL_LAUNCH_COUNT(c);
       GL_CUDA(c, c->e_rng.ensure(ne));
       k_entries_range<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->n_first.p, c->n_end.p, c->e_rng.p);

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgl_b200.so")
+LIB_PATH = os.environ.get("GL_B200_LIB") or os.path.join(_HERE, "libgl_b200.so")   # GL_B200_LIB: A/B a second in-tree build
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
