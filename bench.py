@@ -5,8 +5,10 @@ A "step" is one full force evaluation (accel.c:61-106): tree rebuild (keys, sort
 gravity walk with the relative criterion + density (converged-Hsml pass) + hmax refresh + hydro, on the
 configuration BASELINE.json's target is quoted on: config 0, the 1.6M-gas protoplanetary disc + 2 sinks.
 With --gpus N (torchrun) the disc is scaled to N x 1.6M gas particles (BASELINE config 2's "scaled disc",
-weak scaling): each rank owns one Peano-Hilbert segment of targets and the sources are replicated by NCCL
-all-gathers (gadget_leicester_b200/multigpu.py).
+weak scaling): each rank owns one Peano-Hilbert segment and the library exchanges the locally-essential tree over
+NCCL (csrc/gl_let.cu; --exchange replicate selects the round-1 all-gather of every source instead).  At N > 1 the
+line also carries `ngpu_equals_1gpu` (the N-rank results against one GPU on the same particles) and, unless
+--no-strong, `strong_2p27`: BASELINE configs 3 and 4 at 2^27 particles on 1 GPU (rank 0) and on N GPUs.
 
   value  = gravity particle-node interactions per second of whole-step time, inputs resident in HBM
   e2e    = the same metric through the drop-in boundary with HOST P[]/SphP[] buffers
@@ -104,8 +106,13 @@ def oracle_binary():
     return os.path.join(ROOT, "oracle", "gl_oracle"), "port"
 
 
-def run_cpu_instances(ninst, nsteps, ngas, seed0=42):
-    """ninst concurrent single-rank instances; returns (interactions per step per instance, per-step seconds)."""
+CONFIG0 = "BASELINE config 0: Pd_N16e5 protoplanetary disc, %d gas + 2 sinks"
+SETTLE_OPS = "T S D R G G D U H C"      # cold start, BH pass, relative pass, settled density / hmax / hydro, pair counts
+
+
+def run_cpu_instances(ninst, nsteps, ngas, seed0=42, keep_dump=False):
+    """ninst concurrent single-rank instances; returns (interactions per step per instance, per-step seconds, kind,
+    [dump of instance 0])."""
     import numpy as np
     import tempfile
     from gadget_leicester_b200 import ics
@@ -114,46 +121,54 @@ def run_cpu_instances(ninst, nsteps, ngas, seed0=42):
     td = tempfile.mkdtemp(prefix="glbench_")
     par = ics.default_params()
     procs = []
-    ops = "T S D R G G D U H" + " A" * nsteps      # settle (cold start), then nsteps timed force evaluations
+    ops = SETTLE_OPS + " A" * nsteps      # settle (cold start), then nsteps timed force evaluations
+    nset = len(SETTLE_OPS.split())
+    inputs = []
     for k in range(ninst):
         ps = ics.disc(ngas, seed=seed0 + k)
         fin, fout = os.path.join(td, "in%d.glin" % k), os.path.join(td, "out%d.glou" % k)
         glio.write_glin(fin, ps, par)
+        inputs.append(ps)
         procs.append((subprocess.Popen([binary, fin, fout, ops], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), fout))
-    inter, secs = [], []
-    for p, fout in procs:
+    inter, secs, dump = [], [], None
+    for k, (p, fout) in enumerate(procs):
         if p.wait() != 0:
             raise RuntimeError("CPU reference instance failed")
         o = glio.read_glou(fout)
-        for s in range(nsteps):
-            pre = "%d_" % (9 + s)
+        if k == 0 and keep_dump:
+            dump = (inputs[0], par, o)
+        for s_ in range(nsteps):
+            pre = "%d_" % (nset + s_)
             t = sum(float(o[pre + op + "_time"][0]) for op in "GDUH")
             inter.append(float(o[pre + "G_interactions"][0]))
             secs.append(t)
     inter = np.array(inter).reshape(ninst, nsteps)
     secs = np.array(secs).reshape(ninst, nsteps)
-    return inter, secs, kind
+    return inter, secs, kind, dump
 
 
 def reference_arm(args):
+    """The reference's own CPU code on the box's host cores: `--steps K --warmup W` force evaluations per instance
+    (honoured as given), one single-rank instance per core (the image has no MPI), each on a bounded sample of the
+    configuration our arm names (the 1.6M disc at full size is about two minutes per evaluation on one core)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
     cores = max(1, min(os.cpu_count() or 1, 32))
-    nwarm, nsteps = min(args.warmup, 1), max(1, min(args.steps, 3))
-    inter, secs, kind = run_cpu_instances(cores, nwarm + nsteps, args.cpu_sample_ngas)
+    nwarm, nsteps = max(0, args.warmup), max(1, args.steps)
+    inter, secs, kind, _ = run_cpu_instances(cores, nwarm + nsteps, args.cpu_sample_ngas)
     inter, secs = inter[:, nwarm:], secs[:, nwarm:]
     step_s = float(secs.max(axis=0).mean())          # slowest instance per step
     value = float(inter.sum(axis=0).mean() / step_s)
+    ngas = N_GAS_PER_GPU * max(1, args.gpus)
+    sample = ("%d concurrent single-rank instances (no MPI in the image) of the same generator at %d gas + 2 sinks each "
+              "(bounded sample of the workload); step = gravity_tree + density + force_update_hmax + hydro_force after a "
+              "settled start" % (cores, args.cpu_sample_ngas))
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=nsteps, warmup=nwarm, ms_per_step=step_s * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload="config 0 disc generator at %d gas + 2 sinks per instance (bounded sample of the 1.6M disc)"
-                            % args.cpu_sample_ngas, instances=cores),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind,
-                                  sample="%d concurrent single-rank instances (no MPI in the image) of the %d-gas disc; "
-                                         "step = gravity_tree+density+force_update_hmax+hydro_force after a settled start"
-                                         % (cores, args.cpu_sample_ngas)),
+                config=dict(workload=CONFIG0 % ngas + ("" if args.gpus <= 1 else " (weak scaling, %d per GPU)" % N_GAS_PER_GPU),
+                            sample=sample, instances=cores, particles_per_instance=args.cpu_sample_ngas + 2),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 sph_updates_per_s=float(cores * args.cpu_sample_ngas / step_s), gpu_launches=0)
     print(json.dumps(line))
@@ -191,13 +206,18 @@ def big_config(args):
         kw = dict(sph=True, gravity=False)
         metric, unit = "SPH particle updates/s (tree rebuild + density + hydro)", "updates/s"
         work = "BASELINE config 4: uniform random SPH cube, %d gas particles, Ngb=64, density+hydro only" % n
-    dfp = DistributedForcePath(par, rank=rank, world=world, device=local)
+    use_let = world > 1 and args.exchange == "let"
+    if use_let:
+        from gadget_leicester_b200.multigpu import LetForcePath
+        dfp = LetForcePath(par, rank=rank, world=world, device=local)
+    else:
+        dfp = DistributedForcePath(par, rank=rank, world=world, device=local)
     dfp.decompose_device(ps)
     del ps
     torch.cuda.empty_cache()
     dfp.compute_accelerations(**kw)          # settle: Barnes-Hut pass / cold-start density
     cold_passes = dfp.fp.stats()["density_passes_max"]
-    if world > 1 and args.config == 3 and not args.no_rebalance:
+    if world > 1 and args.config == 3 and not args.no_rebalance and not use_let:
         # domain.c:1075: the next decomposition balances the measured work (GravCost), not the particle count
         for _ in range(2):
             dfp.rebalance(timed=True)
@@ -263,7 +283,7 @@ def big_config(args):
         print(json.dumps(dict(metric=metric, value=units / (ms_per_step * 1e-3), unit=unit, n_gpus=world, steps=args.steps, warmup=warm,
                               ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None,
                               dtype="f64 predicates + f32 force magnitude" if args.config == 3 else "f64", data="synthetic",
-                              config=dict(workload=work, particles=n, parallelism="ph-segments x%d" % world,
+                              config=dict(workload=work, particles=n, parallelism="ph-segments x%d" % world + ("" if world == 1 else ", exchange=" + args.exchange),
                                           l2="inputs larger than L2 (%.1f GB of tree records)" % (n * 150e-9)),
                               phase_ms=phase, density_passes=dict(cold_start=cold_passes), gpu_launches=int(launches), clocks=clocks,
                               roofline=roof, e2e=None, interactions_per_step=(units if args.config == 3 else None),
@@ -271,6 +291,138 @@ def big_config(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def identity_check(dfp, ps, par, n, rank, world, dist):
+    """One more step on N ranks and the same step on ONE GPU (rank 0) from the same state (Hsml and OldAcc gathered from
+    the ranks): interaction counts, pair counts and accelerations of every rank's own particles must be those of the
+    single-GPU run - the merged locally-essential tree is the global tree wherever a target can look."""
+    import numpy as np
+    import torch
+    from gadget_leicester_b200.gadget import ForcePath
+    from gadget_leicester_b200.multigpu import gather_ragged
+    r = dfp.fetch()
+    k = dfp.hi - dfp.lo
+    hs = gather_ragged(r["hsml"][:k].contiguous(), dfp.ranges)
+    oa = gather_ragged(r["oldacc"][:k].contiguous(), dfp.ranges)
+    # every rank: one more step from that state (its own in_hsml / in_oldacc already hold it)
+    dfp.fp.set_TreeReconstructFlag(1)
+    dfp.compute_accelerations()
+    mine = dfp.fetch()
+    lib, ctx = dfp.fp._lib, dfp.fp.ctx
+    dp = torch.zeros(k, dtype=torch.int32, device="cuda")
+    hp = torch.zeros(k, dtype=torch.int32, device="cuda")
+    import ctypes as C
+    dfp.fp._chk(lib.gl_get_pair_counts(ctx, C.c_void_p(dp.data_ptr()), C.c_void_p(hp.data_ptr()), 1))
+    torch.cuda.synchronize()
+    ref = torch.zeros(n, 6, dtype=torch.float64, device="cuda")      # gravcost, denspairs, hydropairs, acc[3]
+    if rank == 0:
+        order = dfp.order
+        pso = {kk: (v[order] if hasattr(v, "shape") and v.shape[0] == n else v) for kk, v in ps.items()}
+        pso["hsml"] = hs.cpu().numpy()
+        pso["oldacc"] = oa.cpu().numpy()
+        one = ForcePath(dict(par, ErrTolTheta=0.0))
+        one.load(pso)
+        g = one.gravity_tree()
+        d = one.density()
+        one.force_update_hmax()
+        h = one.hydro_force()
+        one.close()
+        ref[:, 0] = torch.from_numpy(g["GravCost"].astype(np.float64)).cuda()
+        ref[:, 1] = torch.from_numpy(d["DensPairs"].astype(np.float64)).cuda()
+        ref[:, 2] = torch.from_numpy(h["HydroPairs"].astype(np.float64)).cuda()
+        ref[:, 3:6] = torch.from_numpy(g["GravAccel"]).cuda()
+    dist.broadcast(ref, src=0)
+    own = ref[dfp.lo:dfp.hi]
+    ty = torch.from_numpy(ps["type"][dfp.order[dfp.lo:dfp.hi]]).cuda()
+    gas = ty == 0
+    sphm = gas | (ty == 5) | (ty == 2)
+    bad = torch.stack([(mine["gravcost"].double() != own[:, 0]).sum(),
+                       ((dp.double() != own[:, 1]) & sphm).sum(),
+                       ((hp.double() != own[:, 2]) & gas).sum(),
+                       (mine["acc"] != own[:, 3:6]).any(dim=1).sum()]).double()
+    dist.all_reduce(bad, op=dist.ReduceOp.SUM)
+    b = [int(x) for x in bad.cpu().numpy()]
+    return dict(particles=int(n), gravcost_mismatches=b[0], density_pair_mismatches=b[1], hydro_pair_mismatches=b[2],
+                gravaccel_not_bitwise_equal=b[3], identical=bool(b[0] == 0 and b[1] == 0 and b[2] == 0),
+                how="one step on %d ranks vs the same step on one GPU (rank 0) from the same Hsml / OldAcc state" % world)
+
+
+def strong_scaling(args, rank, world, local, dist):
+    """BASELINE configs 3 (Plummer sphere, gravity only) and 4 (uniform gas cube, density + hydro only) at 2^27
+    particles: the same set on ONE GPU (rank 0, the others wait) and on all N GPUs; efficiency = t1 / (N * tN)."""
+    import numpy as np
+    import torch
+    from gadget_leicester_b200 import ics
+    from gadget_leicester_b200.multigpu import DistributedForcePath, LetForcePath
+    n = args.strong_nparts or (1 << 27)
+    dev = torch.device("cuda", local)
+    out = dict(particles=n, steps=3)
+
+    def setup(cfg):
+        if cfg == 3:
+            par = ics.default_params(Softening=[1e-5, ics.plummer_softening(n), 5e-5, 1e-7, 0.01, 5e-5])
+            ps = ics.plummer_torch(n, dev, seed=42)
+            kw = dict(sph=False, gravity=True)
+        else:
+            par = ics.default_params(DesNumNgb=64, MaxNumNgbDeviation=0.5)
+            ps = ics.cube_torch(n, dev, seed=42)
+            ps["hsml"].fill_((3.0 * 64 / (4 * np.pi * n)) ** (1.0 / 3.0) * 1.3)
+            kw = dict(sph=True, gravity=False)
+        return par, ps, kw
+
+    def timed(d, kw, steps=3, warm=2):
+        d.compute_accelerations(**kw)                  # settle: Barnes-Hut pass / cold-start density
+        for _ in range(warm):
+            d.fp.set_TreeReconstructFlag(1)
+            d.compute_accelerations(**kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(steps):
+            torch.cuda.synchronize()
+            e0.record(torch.cuda.current_stream())
+            d.fp.set_TreeReconstructFlag(1)
+            d.compute_accelerations(**kw)
+            torch.cuda.synchronize()
+            e1.record(torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / steps
+
+    for cfg in (3, 4):
+        par, ps, kw = setup(cfg)
+        t1 = torch.zeros(1, dtype=torch.float64, device=dev)
+        if rank == 0:
+            one = DistributedForcePath(par, rank=0, world=1, device=local)
+            one.decompose_device(ps)
+            t1[0] = timed(one, kw)
+            one.close()
+            del one
+            torch.cuda.empty_cache()
+        dist.barrier()
+        dist.broadcast(t1, src=0)
+        d = LetForcePath(par, rank=rank, world=world, device=local)
+        d.decompose_device(ps)
+        del ps
+        torch.cuda.empty_cache()
+        tn = torch.tensor([timed(d, kw)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        ls = d.fp.let_stats()
+        imp = torch.tensor([float(ls["imported_particles"]), float(ls["violations"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(imp, op=dist.ReduceOp.MAX)
+        d.close()
+        del d
+        torch.cuda.empty_cache()
+        out["config%d_ms_1gpu" % cfg] = float(t1.item())
+        out["config%d_ms" % cfg] = float(tn.item())
+        out["config%d_efficiency" % cfg] = float(t1.item() / (world * tn.item()))
+        out["config%d_imported_particles_max" % cfg] = float(imp[0].item())
+        out["config%d_let_violations" % cfg] = float(imp[1].item())
+    out["efficiency"] = min(out["config3_efficiency"], out["config4_efficiency"])
+    out["note"] = ("same 2^27-particle set on 1 GPU (rank 0) and on %d GPUs in this run; step = tree build (+ locally-essential "
+                   "exchange) + gravity walk (config 3) or density + hydro (config 4); efficiency = t1 / (N tN), the smaller of the two" % world)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- our arm ----
@@ -291,6 +443,12 @@ def main():
     ap.add_argument("--cpu-sample-ngas", type=int, default=CPU_SAMPLE_NGAS,
                     help="gas particles per CPU instance of the reference arm / cpu_baseline leg (the line states the sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="let", choices=["let", "replicate"],
+                    help="N > 1: 'let' = locally-essential tree exchanged inside the library over NCCL (default); 'replicate' = the "
+                         "round-1 path, every source all-gathered and the global tree built on every GPU")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the 2^27-particle strong-scaling lines (configs 3 and 4)")
+    ap.add_argument("--strong-nparts", type=int, default=0, help="particles of the strong-scaling sets (default 2^27)")
+    ap.add_argument("--no-identity", action="store_true", help="N > 1: skip the N-GPU == 1-GPU comparison")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -332,12 +490,17 @@ def main():
     ps["hsml"][ps["type"] == 5] = par["Softening"][5]
     n = ps["pos"].shape[0]
 
-    dfp = DistributedForcePath(par, rank=rank, world=world, device=local)
+    use_let = world > 1 and args.exchange == "let"
+    if use_let:
+        from gadget_leicester_b200.multigpu import LetForcePath
+        dfp = LetForcePath(par, rank=rank, world=world, device=local)
+    else:
+        dfp = DistributedForcePath(par, rank=rank, world=world, device=local)
     dfp.decompose(ps)
     # settle: Barnes-Hut pass (OldAcc=0) then cold-start density; afterwards every step is a steady-state step
     dfp.compute_accelerations()
     cold_passes = dfp.fp.stats()["density_passes_max"]
-    if world > 1 and args.rebalance:
+    if world > 1 and args.rebalance and not use_let:
         # domain.c:1075 balances the measured GRAVITY work; two thirds of this step is SPH work, which equal counts
         # balance better on the disc (measured at N=2: 18.3 ms equal counts, 18.7 ms GravCost-balanced) - so off by default
         for _ in range(2):
@@ -391,15 +554,33 @@ def main():
     value = inter_per_step / (ms_per_step * 1e-3)
     phase = {k: v / args.steps for k, v in acc.items()}
     rank_phase = None
+    let_line = None
     if dist is not None:
         keys = ("ms_keys_sort", "ms_moments", "ms_gravity_walk", "ms_density", "ms_hydro")
-        mine = torch.tensor([phase[k] for k in keys] + [wall.get("allgather_state", 0.0), wall.get("allgather_sph", 0.0),
-                                                        float(dfp.hi - dfp.lo)], dtype=torch.float64, device="cuda")
+        extra = [wall.get("allgather_state", 0.0), wall.get("allgather_sph", 0.0), float(dfp.hi - dfp.lo)]
+        names = ("wall_allgather_state", "wall_allgather_sph", "targets")
+        if use_let:
+            ls = dfp.fp.let_stats()
+            extra = [ls["ms_own_tree"], ls["ms_select"], ls["ms_exchange"], ls["ms_sph_exchange"], float(ls["imported_particles"]),
+                     float(ls["imported_cells"]), float(ls["exported_particles"]), float(ls["violations"]), float(dfp.hi - dfp.lo)]
+            names = ("let_ms_own_tree", "let_ms_select", "let_ms_exchange", "let_ms_sph_exchange", "let_imported_particles",
+                     "let_imported_cells", "let_exported_particles", "let_violations", "targets")
+        mine = torch.tensor([phase[k] for k in keys] + extra, dtype=torch.float64, device="cuda")
         allr = torch.empty(world * mine.numel(), dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(allr, mine)
         allr = allr.view(world, -1).cpu().numpy()
-        rank_phase = {k: [round(float(x), 2) for x in allr[:, j]]
-                      for j, k in enumerate(keys + ("wall_allgather_state", "wall_allgather_sph", "targets"))}
+        rank_phase = {k: [round(float(x), 2) for x in allr[:, j]] for j, k in enumerate(keys + names)}
+        if use_let:
+            imp = allr[:, len(keys) + 4]
+            let_line = dict(exchange="locally-essential tree inside libgl_b200 (NCCL all-gather of target boxes + two all-to-alls)",
+                            imported_particles_mean=float(imp.mean()), imported_particles_max=float(imp.max()),
+                            replicated_would_import=float(n - (dfp.hi - dfp.lo)),
+                            bytes_received_per_rank_max=float(imp.max() * 80 + allr[:, len(keys) + 5].max() * 64))
+
+    # ---- N ranks against ONE GPU on the same particles and the same state (north_star: identical results) ----
+    identity = None
+    if dist is not None and use_let and not args.no_identity:
+        identity = identity_check(dfp, ps, par, n, rank, world, dist)
 
     # ---- roofline of the dominant kernel (per-launch durations from the library's CUDA events) ----
     pk = peaks()
@@ -434,7 +615,39 @@ def main():
 
     # ---- e2e: the same step through the drop-in boundary with host P[]/SphP[] (rank-local set) ----
     e2e = None
-    if not args.no_e2e and world > 1:
+    if not args.no_e2e and world > 1 and use_let:
+        # every rank owns the host P[]/SphP[] of its Peano-Hilbert segment, like every MPI rank of the reference, and
+        # calls the drop-in entry point on it; the exchange happens inside the library
+        r = dfp.fetch()
+        seg = dfp.order[dfp.lo:dfp.hi]
+        ps_seg = {k: (v[seg] if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+        ps_seg["hsml"] = r["hsml"].cpu().numpy()
+        ps_seg["oldacc"] = r["oldacc"].cpu().numpy()
+        dfp.fp.set_params(ErrTolTheta=0.0)
+        arr = aos.GadgetArrays(ps_seg, pinned=True)
+        drop = aos.GadgetDropIn(dfp.fp, arr)
+        for _ in range(2):
+            drop.compute_accelerations()
+        ksteps = max(2, min(args.steps, 5))
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        ie = 0
+        for _ in range(ksteps):
+            drop.compute_accelerations()
+            ie += dfp.fp.stats()["interactions"]
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ksteps
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        ii = torch.tensor([float(ie) / ksteps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ii, op=dist.ReduceOp.SUM)
+        h2d, d2h = drop.bytes_per_step()
+        e2e = dict(value=float(ii.item()) / float(tt.item()), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
+                   ms_per_step=float(tt.item()) * 1e3, steps=ksteps,
+                   api="gl_gadget_compute_accelerations on every rank's own pinned host P[]/SphP[] segment (pack + H2D, "
+                       "locally-essential exchange over NCCL, force path, D2H + scatter); max over ranks")
+    if not args.no_e2e and world > 1 and not use_let:
         # every rank owns the host P[]/SphP[] of its Peano-Hilbert segment, like every MPI rank of the reference
         from gadget_leicester_b200.multigpu import DistributedDropIn
         seg = dfp.order[dfp.lo:dfp.hi]
@@ -496,28 +709,48 @@ def main():
                    steps=ksteps, api="gl_gadget_compute_accelerations on pinned host P[]/SphP[] (pack + H2D, force path, pipelined D2H + scatter)")
         fp.close()
 
+    # ---- strong scaling on the 2^27-particle sets (north_star: >= 70 % at 8 GPUs), part of the N > 1 line ----
+    strong = None
+    if dist is not None and use_let and not args.no_strong and args.config == 0:
+        dfp.close()
+        del dfp
+        torch.cuda.empty_cache()
+        strong = strong_scaling(args, rank, world, local, dist)
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return
 
-    cpu_base = None
+    cpu_base, parity = None, None
     if world == 1 and not args.no_cpu_baseline and args.config == 0:
         try:
-            ci, cs, kind = run_cpu_instances(1, 2, args.cpu_sample_ngas)
+            ci, cs, kind, dump = run_cpu_instances(1, 2, args.cpu_sample_ngas, keep_dump=True)
             cpu_base = dict(value=float(ci[0, 1] / cs[0, 1]), unit=UNIT, cores=1, kind=kind,
                             sample="1 single-rank instance, %d-gas disc + 2 sinks (same generator, bounded sample), "
                                    "one settled force step: %.2f s" % (args.cpu_sample_ngas, cs[0, 1]),
                             sph_updates_per_s=float(args.cpu_sample_ngas / cs[0, 1]))
+            if kind == "reference":
+                # the same run is the checker for a parity record at this size (tests/parity_bench.py): the CUDA path
+                # on the sample's particles against the reference's dump
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import parity_bench
+                psd, pard, out = dump
+                npd, ngd = psd["pos"].shape[0], int((psd["type"] == 0).sum())
+                parity = parity_bench.parity_record(ForcePath, psd, pard, parity_bench.golden_layout(out, npd, ngd))
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
-            cpu_base = dict(value=None, unit=UNIT, cores=1, kind="unavailable", sample=str(ex)[:200])
+            if cpu_base is None:
+                cpu_base = dict(value=None, unit=UNIT, cores=1, kind="unavailable", sample=str(ex)[:200])
+            else:
+                parity = dict(ok=None, error=str(ex)[:300])
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms_per_step,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 predicates + f32 force magnitude (gravity), f64 (SPH)",
                 data="synthetic",
                 config=dict(workload=workload + ("" if world == 1 else " (weak scaling, %d per GPU)" % (ngas // world)),
-                            particles=n, parallelism="ph-segments x%d" % world, l2="256 MiB flush between timed steps",
+                            particles=n, parallelism="ph-segments x%d" % world + ("" if world == 1 else ", exchange=" + args.exchange),
+                            l2="256 MiB flush between timed steps",
                             step="tree rebuild + gravity (relative criterion) + density + hmax + hydro"),
                 interactions_per_step=inter_per_step, sph_updates_per_s=(ngas / (ms_per_step * 1e-3)),
                 force_eval_ms=ms_per_step, phase_ms=phase, density_passes=dict(cold_start=cold_passes, steady=passes),
@@ -527,6 +760,14 @@ def main():
         line["e2e"] = e2e
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
+    if parity is not None:
+        line["parity_at_bench"] = parity
+    if let_line is not None:
+        line["exchange"] = let_line
+    if identity is not None:
+        line["ngpu_equals_1gpu"] = identity
+    if strong is not None:
+        line["strong_2p27"] = strong
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -43,6 +43,10 @@ extern "C" void gl_destroy(gl_ctx *c)
   for(auto &t : c->push_threads)
     if(t.joinable()) t.join();
   cudaStreamSynchronize(c->stream);
+  delete c->comm;
+  c->comm = nullptr;
+  gll_release(c);
+  c->c_key.release(); c->c_level.release(); c->c_sm.release(); c->c_aux.release(); c->s_lev.release(); c->let_hsml_backup.release();
   c->in_velpred.release();
   c->dma_rows.release();
   if(c->ev_blk) cudaEventDestroy(c->ev_blk);
@@ -86,6 +90,22 @@ extern "C" int gl_set_params(gl_ctx *c, const gl_params *p)
   return 0;
 }
 
+// a new particle set: own = all of it until a multi-rank build appends imports; a target list the multi-rank build had
+// installed by itself goes with the old set
+void gl_fresh_particle_set(gl_ctx *c)
+{
+  c->n_own = c->n;
+  c->ncell = 0;
+  c->nit = c->n;
+  if(c->let_auto_targets)
+    {
+      c->n_tgt_in = -1;
+      c->tgt_ordered = false;
+      c->let_auto_targets = false;
+    }
+  if(c->comm) gll_set_full(c, false);
+}
+
 template <class T> static int put(gl_ctx *c, DBuf<T> &dst, const T *src, size_t cnt, int where, T fill)
 {
   GL_CUDA(c, dst.ensure(cnt));
@@ -127,6 +147,7 @@ extern "C" int gl_load_particles(gl_ctx *c, long long n, const double *pos, cons
       c->res_count = -1;
     }
   c->n = n;
+  gl_fresh_particle_set(c);
   c->tree_valid = false;
   c->tree_flag = true;
   c->tgt_dirty = true;
@@ -267,6 +288,7 @@ extern "C" int gl_load_particles_gathered(gl_ctx *c, long long n, int world, lon
       c->res_count = -1;
     }
   c->n = n;
+  gl_fresh_particle_set(c);
   c->tree_valid = false;
   c->tree_flag = true;
   c->tgt_dirty = true;
@@ -405,7 +427,13 @@ extern "C" int gl_get_nodes(gl_ctx *c, double *table, long long cap)
   return glt_get_nodes(c, table, cap);
 }
 
-extern "C" void gl_set_tree_reconstruct_flag(gl_ctx *c, int flag) { c->tree_flag = flag != 0; }
+extern "C" void gl_set_tree_reconstruct_flag(gl_ctx *c, int flag)
+{
+  c->tree_flag = flag != 0;
+  // multi-rank mode: a new decomposition / tree starts again with the pruned export (a full export after a cut cell was
+  // met only lasts until then)
+  if(flag && c->comm) gll_set_full(c, false);
+}
 
 // ---------------------------------------------------------------- targets ----
 extern "C" int gl_set_targets_ordered(gl_ctx *c, const int *index, long long n, int where)
@@ -420,6 +448,7 @@ extern "C" int gl_set_targets(gl_ctx *c, const int *index, long long n, int wher
   cudaSetDevice(c->device);
   c->tgt_dirty = true;
   c->tgt_ordered = false;
+  c->let_auto_targets = false;
   c->tgt_host.clear();
   if(n < 0 || !index)
     {
@@ -598,17 +627,67 @@ int gl_split_gas_targets(gl_ctx *c, long long split, long long *n_lo)
 }
 
 // ---------------------------------------------------------------- force entry points ----
+// Multi-rank mode: a phase that met a cut cell (GL_ERR_LET_VIOLATION, see gl_let.cu) is repeated by ALL ranks with a
+// full export - the decision is collective (one 8-byte all-gather per phase), because the rebuild is.
+static int run_phase(gl_ctx *c, int (*fn)(gl_ctx *), const char *name, bool gravity)
+{
+  if(!(c->comm && c->comm->world > 1)) return fn(c);
+  for(int attempt = 0; attempt < 2; attempt++)
+    {
+      const int rc = fn(c);
+      const bool viol = rc != 0 && c->err.find("GL_ERR_LET_VIOLATION") != std::string::npos;
+      if(rc != 0 && !viol) return rc;
+      int any = 0;
+      if(gll_agree_violation(c, viol ? 1 : 0, &any)) return 1;
+      if(!any) return 0;
+      if(attempt == 1) break;
+      if(getenv("GL_DEBUG_LET")) fprintf(stderr, "[gl] rank %d: %s met a cut cell somewhere - repeating with a full export\n", c->comm->rank, name);
+      c->let_violations++;
+      gll_set_full(c, true);
+      c->tree_flag = true;
+      c->tree_valid = false;
+      if(!gravity)
+	{
+	  c->let_need_sph_exchange = true;
+	  if(c->let_hsml_backup.cap >= (size_t) c->n_own && c->n_own > 0)
+	    GL_CUDA(c, cudaMemcpyAsync(c->in_hsml.p, c->let_hsml_backup.p, c->n_own * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	  if(glt_build(c)) return 1;
+	}
+    }
+  return c->fail(std::string(name) + ": a cut cell was met although every particle was exported");
+}
+
+static int density_phase(gl_ctx *c)
+{
+  if(c->comm && c->comm->world > 1)
+    {
+      // a repeated density() must start its Hsml iteration from the same values as the first attempt
+      if(!c->tree_valid || c->tree_flag)
+	if(glt_build(c)) return 1;
+      GL_CUDA(c, c->let_hsml_backup.ensure((size_t) c->n_own + 1));
+      GL_CUDA(c, cudaMemcpyAsync(c->let_hsml_backup.p, c->in_hsml.p, c->n_own * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+  return gls_density(c);
+}
+
 extern "C" int gl_gravity_tree(gl_ctx *c)
 {
   cudaSetDevice(c->device);
+  if(c->comm && c->comm->world > 1)
+    {
+      c->let_want_grav = true;
+      // the merged tree was selected for one opening criterion (and maybe without the gravity tests at all)
+      if(c->tree_valid && !gll_built_for(c, c->par.ErrTolTheta != 0, true)) c->tree_flag = true;
+    }
   bool rebuilt = c->tree_flag || !c->tree_valid;
   if(rebuilt) c->tgt_dirty = true;
-  return glg_gravity(c);
+  return run_phase(c, glg_gravity, "gravity_tree", true);
 }
 
 extern "C" int gl_compute_potential(gl_ctx *c)
 {
   cudaSetDevice(c->device);
+  if(c->comm && c->comm->world > 1) return c->fail("compute_potential: single rank only (all particles are targets, potential.c:54)");
   return glg_potential(c);
 }
 
@@ -623,7 +702,7 @@ extern "C" int gl_get_potential(gl_ctx *c, double *potential, int where)
 extern "C" int gl_density(gl_ctx *c)
 {
   cudaSetDevice(c->device);
-  return gls_density(c);
+  return run_phase(c, density_phase, "density", false);
 }
 
 extern "C" int gl_force_update_hmax(gl_ctx *c)
@@ -632,10 +711,71 @@ extern "C" int gl_force_update_hmax(gl_ctx *c)
   return glt_update_hmax(c);
 }
 
+static int hydro_phase(gl_ctx *c)
+{
+  // after a repeat the tree is new: the SphP state of the imports and the cells' hmax have to come again
+  if(c->comm && c->comm->world > 1 && c->let_need_sph_exchange)
+    if(glt_update_hmax(c)) return 1;
+  return gls_hydro(c);
+}
+
 extern "C" int gl_hydro_force(gl_ctx *c)
 {
   cudaSetDevice(c->device);
-  return gls_hydro(c);
+  return run_phase(c, hydro_phase, "hydro_force", false);
+}
+
+// ---- multi-rank mode ----
+extern "C" int gl_comm_unique_id(void *id128)
+{
+  std::string err;
+  if(gl_comm_nccl_unique_id(id128, err))
+    {
+      fprintf(stderr, "libgl_b200: %s\n", err.c_str());
+      return 1;
+    }
+  return 0;
+}
+
+extern "C" int gl_comm_init(gl_ctx *c, int rank, int world, const void *id128)
+{
+  cudaSetDevice(c->device);
+  if(c->comm) return c->fail("gl_comm_init: a communicator is attached already");
+  if(world < 1 || world > GL_LET_MAXRANKS || rank < 0 || rank >= world) return c->fail("gl_comm_init: bad rank / world");
+  std::string err;
+  c->comm = gl_comm_make_nccl(rank, world, id128, c->device, err);
+  if(!c->comm) return c->fail(err);
+  return 0;
+}
+
+extern "C" void *gl_comm_local_group_create(int world) { return gl_comm_local_group_create_impl(world); }
+extern "C" void gl_comm_local_group_destroy(void *group) { gl_comm_local_group_destroy_impl(group); }
+
+extern "C" int gl_comm_init_local(gl_ctx *c, int rank, void *group)
+{
+  if(c->comm) return c->fail("gl_comm_init_local: a communicator is attached already");
+  std::string err;
+  c->comm = gl_comm_make_local(group, rank, err);
+  if(!c->comm) return c->fail(err);
+  return 0;
+}
+
+extern "C" int gl_comm_finalize(gl_ctx *c)
+{
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  delete c->comm;
+  c->comm = nullptr;
+  return 0;
+}
+
+extern "C" int gl_comm_set_options(gl_ctx *c, int want_gravity, double search_padding)
+{
+  if(!c->comm) return c->fail("gl_comm_set_options: no communicator attached");
+  if(search_padding < 1.0) return c->fail("gl_comm_set_options: search_padding < 1");
+  c->let_want_grav = want_gravity != 0;
+  gll_set_padding(c, search_padding);
+  return 0;
 }
 
 extern "C" int gl_compute_accelerations(gl_ctx *c, int mode)

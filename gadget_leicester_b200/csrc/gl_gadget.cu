@@ -311,6 +311,7 @@ static void mark_loaded(gl_ctx *c, long long n, long long ngas)
       c->res_count = -1;
     }
   c->n = n;
+  gl_fresh_particle_set(c);
   c->g_numpart = n;
   c->g_ngas = ngas;
   c->g_off = 0;
@@ -345,6 +346,12 @@ extern "C" int gl_gadget_pull(gl_ctx *c, const void *Pv, const void *SphPv, long
   const long long n = NumPart, ngas = std::min(N_gas, NumPart);
   if(n <= 0) return c->fail("gl_gadget_pull: NumPart <= 0");
   if(n >= (1ll << 27) + (1ll << 24)) return c->fail("gl_gadget_pull: n exceeds the 2^27 design limit of the index encoding");
+  if(c->let_auto_targets)
+    {				// the target list a multi-rank build installed for the previous particle set
+      c->n_tgt_in = -1;
+      c->tgt_ordered = false;
+      c->let_auto_targets = false;
+    }
   if(ensure_pinned(c, &c->pin, &c->pin_cap, PullStage::bytes(n))) return 1;
   if(ensure_input_buffers(c, n, ngas)) return 1;
   if(ensure_copy_streams(c)) return 1;
@@ -398,7 +405,7 @@ struct PushStage
 // the scatter only touches the particles that were evaluated: the active list when one was set (gl_set_targets)
 static int target_list(gl_ctx *c, const int **idx, long long *cnt)
 {
-  if(c->n_tgt_in < 0)
+  if(c->n_tgt_in < 0 || c->let_auto_targets)	// (multi-rank mode lists the own particles by itself: that is "all" here)
     {
       *idx = nullptr;
       *cnt = c->g_numpart;
@@ -680,6 +687,16 @@ struct Stages
 // compute_accelerations (accel.c:27, force part :61-106) on the reference's host arrays.
 extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv, long long NumPart, long long N_gas, int mode)
 {
+  if(c->comm && c->comm->world > 1)
+    {
+      // multi-rank mode: this rank's own P[] / SphP[]; the phases are collective and may be repeated (gl_let.cu), so
+      // they run through the ordinary entry points, without the software pipeline of the single-rank path below
+      cudaSetDevice(c->device);
+      if(gl_gadget_pull(c, Pv, SphPv, NumPart, N_gas)) return 1;
+      gl_set_tree_reconstruct_flag(c, 1);
+      if(gl_compute_accelerations(c, mode)) return 1;
+      return gl_gadget_push(c, Pv, SphPv, 7);
+    }
   (void) mode;
   cudaSetDevice(c->device);
   if(!c->have_lay) return c->fail("gl_gadget_compute_accelerations: gl_gadget_bind not called");

@@ -18,7 +18,7 @@
 gl_dparams gl_make_dparams(const gl_ctx *c);
 
 #ifndef GRAV_MIN_BLOCKS
-#define GRAV_MIN_BLOCKS 8	// resident 128-thread blocks per SM the walk is compiled for (64 registers)
+#define GRAV_MIN_BLOCKS 10	// resident 128-thread blocks per SM the walk is compiled for (48 registers; 8: 3.37 ms, 10: 3.18, 12: 3.18 on the 1.6M disc)
 #endif
 
 // ---- margins of the FP32 pre-test (units: domain cube [1,2) wide, total mass [1,2); u = 2^-24) --------------------
@@ -187,6 +187,13 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 		  open = hn < 0;
 		  hf = (float) (hn * S);
 		}
+	      if(open && nx == e + 1)
+		{
+		  // a CUT CELL of the locally-essential tree (multi-rank mode): its descendants stayed with their owner,
+		  // whose export test promised that no target of this rank opens it.  Report instead of guessing.
+		  atomicMax(&counter[2], GL_ERR_LET_VIOLATION);
+		  open = false;
+		}
 	      if(!open)
 		{
 		  interact = true;
@@ -316,14 +323,16 @@ int glg_gravity(gl_ctx *c)
     }
   cudaEventRecord(c->ev[1], c->stream);
   c->fire_post_launch();
-  unsigned long long tot = 0;
-  GL_CUDA(c, cudaMemcpyAsync(&tot, c->d_counter.p, sizeof(tot), cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long cnt3[3] = { 0, 0, 0 };
+  GL_CUDA(c, cudaMemcpyAsync(cnt3, c->d_counter.p, sizeof(cnt3), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, c->wait_stream());
   GL_CUDA(c, cudaGetLastError());
+  const unsigned long long tot = cnt3[0];
   float ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->st.ms_gravity_walk = ms;
   c->st.interactions = (long long) tot;
+  if(cnt3[2] == GL_ERR_LET_VIOLATION) return c->fail("gravity_tree: GL_ERR_LET_VIOLATION");
   // gravtree.c:392: the new OldAcc feeds the next call's relative criterion (accel.c:61-67 calls twice at Ti=0)
   GL_CUDA(c, cudaMemcpyAsync(c->in_oldacc.p, c->o_oldacc.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   // gravtree.c:396-397: switch to the relative criterion for all following force computations

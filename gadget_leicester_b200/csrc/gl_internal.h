@@ -10,6 +10,7 @@
 #include <functional>
 #include <thread>
 #include "../../include/gl_b200.h"
+#include "gl_comm.h"
 
 #define GL_BITS 21			// BITS_PER_DIMENSION, allvars.h:58
 #define GL_MAXITER 150			// MAXITER, allvars.h:139
@@ -43,6 +44,32 @@ template <class T> struct DBuf
     cudaError_t e = cudaMalloc((void **) &p, want * sizeof(T));
     if(e == cudaSuccess) cap = want;
     return e;
+  }
+  // grow without losing the contents (multi-rank mode appends imported particles behind the caller's own, and a
+  // rebuild with more imports must not lose results of an earlier phase).  Rare: waits for the device.
+  cudaError_t ensure_keep(size_t n)
+  {
+    if(n <= cap) return cudaSuccess;
+    size_t want = n + n / 8 + 64;
+    T *q = nullptr;
+    cudaError_t e = cudaMalloc((void **) &q, want * sizeof(T));
+    if(e != cudaSuccess) return e;
+    if(p)
+      {
+	cudaDeviceSynchronize();
+	e = cudaMemcpy(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
+	cudaFree(p);
+	if(e != cudaSuccess)
+	  {
+	    cudaFree(q);
+	    p = nullptr;
+	    cap = 0;
+	    return e;
+	  }
+      }
+    p = q;
+    cap = want;
+    return cudaSuccess;
   }
   void release()
   {
@@ -89,6 +116,22 @@ struct gl_ctx
   // once-per-device set-up that must not be process-global: a process may hold contexts on several GPUs
   bool tables_up = false, attr_density = false, attr_hydro = false;
 
+  // ---- multi-rank mode (gl_comm_init): the caller loads its OWN particles; the tree build imports, per other rank,
+  // the locally-essential set that rank selects for us - particles and whole cells ("cut cells": moments only, never
+  // opened).  Input arrays then hold own particles [0, n_own) followed by the imported ones [n_own, n); the imported
+  // cells are items n .. nit-1 of the sorted order.  Single rank: n_own = n, nit = n.
+  gl_comm *comm = nullptr;
+  long long n_own = 0, ncell = 0, nit = 0;
+  DBuf<unsigned long long> c_key;	// cut cells: lowest Morton key of the cell
+  DBuf<signed char> c_level;	// its level (1..21)
+  DBuf<double4> c_sm, c_aux;	// (s, mass), (maxsoft, hmax, vmax, -)
+  DBuf<signed char> s_lev;	// tree order: level of a cut-cell item, 22 for a particle
+  struct gl_let_state *let = nullptr;
+  bool let_auto_targets = false;	// the target list was set by the multi-rank build (own particles), not by the caller
+  long long let_violations = 0;
+  bool let_need_sph_exchange = false;	// the tree was rebuilt after density(): the imports' SphP state has to come again
+  bool let_want_grav = true;	// the export test includes the gravity opening criteria (gl_comm_set_options)
+  DBuf<double> let_hsml_backup;	// own Hsml before density(): a repeated density() must start from the same values
   // ---- input-order particle state (index = P[] index) ----
   DBuf<double> in_pos, in_vel, in_mass, in_hsml, in_oldacc, in_entropy, in_dtentropy;
   // drop-in layer only: SphP[].VelPred of the gas block, kept apart from P[].Vel (node vmax uses P.Vel,
@@ -219,6 +262,13 @@ int glk_export_keys(gl_ctx *c, gl_peanokey *ph, gl_peanokey *mo, int where);
 int glk_ph_order(gl_ctx *c, long long n_gas, int *order, int where);
 int glk_apply_velpred(gl_ctx *c);
 int glk_ph_sequence(gl_ctx *c);
+int glk_local_minmax(gl_ctx *c, double *dev6);	// min[3], max[3] of the loaded positions, left on the device
+void glk_set_domain_minmax(gl_ctx *c, const double lo[3], const double hi[3]);
+// Peano-Hilbert key hull {min, max} of each of nchunks stretches [bounds[b], bounds[b+1]) of the own particles (input order)
+int glk_ph_chunk_hulls(gl_ctx *c, const long long *bounds_dev, int nchunks, unsigned long long *out);
+// per node of the current tree: 1 if no other rank has a particle inside the cell (its Peano-Hilbert key range
+// misses every key hull of every other rank); rank r's nhull hulls start at ranges + r * stride (device)
+int glk_node_complete(gl_ctx *c, const unsigned long long *ranges, int world, int nhull, long long stride, int me, unsigned char *complete);
 // gl_tree.cu
 int glt_build(gl_ctx *c);
 int glt_update_hmax(gl_ctx *c);
@@ -235,6 +285,19 @@ int gls_hydro_end(gl_ctx *c);
 int gl_split_gas_targets(gl_ctx *c, long long split, long long *n_lo);
 // gl_api.cu
 int gl_prepare_targets(gl_ctx *c);
+void gl_fresh_particle_set(gl_ctx *c);
+// gl_let.cu (multi-rank: locally-essential tree exchange)
+int gll_distributed_build(gl_ctx *c);	// what glt_build does when a communicator is attached
+int gll_exchange_sph_state(gl_ctx *c);	// before force_update_hmax: Hsml + SphP of exported particles, hmax of exported cells
+void gll_release(gl_ctx *c);
+int glt_build_local(gl_ctx *c, bool entries);
+int glt_launch_update_hmax(gl_ctx *c);
+int gll_agree_violation(gl_ctx *c, int mine, int *any);
+void gll_set_full(gl_ctx *c, bool full);
+void gll_set_padding(gl_ctx *c, double fs);
+bool gll_built_for(gl_ctx *c, bool bh, bool grav);
+#define GL_LET_MAXRANKS 64	// the single-context build over the items currently loaded
+#define GL_ERR_LET_VIOLATION 7001ull	// d_counter[2]: a walk wanted to open / a search touched a cut cell
 
 #define GL_LAUNCH_COUNT(c) ((c)->kernel_launches++)
 

@@ -232,6 +232,22 @@ int glk_find_extent(gl_ctx *c)
   return 0;
 }
 
+int glk_local_minmax(gl_ctx *c, double *dev6)
+{
+  const int nb = 148 * 4;
+  GL_CUDA(c, c->dom_dev.ensure((size_t) nb * 6 + 16));
+  k_extent_partial<<<nb, GL_BLOCK, 0, c->stream>>>(c->in_pos.p, c->n, c->dom_dev.p + 16);
+  k_extent_final<<<1, 32, 0, c->stream>>>(c->dom_dev.p + 16, nb, dev6);
+  c->kernel_launches += 2;
+  return 0;
+}
+
+void glk_set_domain_minmax(gl_ctx *c, const double lo[3], const double hi[3])
+{
+  domain_from_minmax(c->dom, lo, hi);
+  c->have_domain = true;
+}
+
 extern "C" int gl_domain_set_extent(gl_ctx *c, const double xmin[3], const double xmax[3])
 {
   domain_from_minmax(c->dom, xmin, xmax);
@@ -328,18 +344,29 @@ __global__ void k_ph_from_morton(const unsigned long long *__restrict__ mkey, lo
 }
 
 // ---------------------------------------------------------------- K3 sort + gather ----
-__global__ void k_gather_sorted(long long n, const int *__restrict__ perm, const double *__restrict__ pos,
+__global__ void k_gather_sorted(long long nit, long long n, const int *__restrict__ perm, const double *__restrict__ pos,
 				const double *__restrict__ vel, const double *__restrict__ mass,
 				const double *__restrict__ hsml, const int *__restrict__ type,
+				const double4 *__restrict__ c_sm, const double4 *__restrict__ c_aux, const signed char *__restrict__ c_level,
 				double4 *__restrict__ s_pm, double4 *__restrict__ s_vh, int *__restrict__ s_type,
-				int *__restrict__ inv)
+				signed char *__restrict__ s_lev, int *__restrict__ inv)
 {
   long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(i >= n) return;
+  if(i >= nit) return;
   int j = perm[i];
+  if(j >= n)
+    {
+      // a cut cell of the locally-essential tree (multi-rank mode): an item that carries moments instead of a particle
+      s_pm[i] = c_sm[j - n];
+      s_vh[i] = c_aux[j - n];	// maxsoft, hmax, vmax: what a child cell contributes to the moments besides (s, mass)
+      s_type[i] = -1;
+      s_lev[i] = c_level[j - n];
+      return;
+    }
   s_pm[i] = make_double4(pos[3ll * j], pos[3ll * j + 1], pos[3ll * j + 2], mass[j]);
   s_vh[i] = make_double4(vel[3ll * j], vel[3ll * j + 1], vel[3ll * j + 2], hsml[j]);
   s_type[i] = type[j];
+  s_lev[i] = GL_BITS + 1;
   inv[j] = (int) i;
 }
 
@@ -375,26 +402,38 @@ static int sort_pairs(gl_ctx *c, const unsigned long long *kin, unsigned long lo
   return 0;
 }
 
+__global__ void k_iota(int *p, long long n, int base);
+
 int glk_keys_and_sort(gl_ctx *c)
 {
-  long long n = c->n;
+  // items of the sorted order: the n loaded particles and, in multi-rank mode, the ncell imported cut cells (sorted
+  // in by the lowest Morton key of the cell - no particle of the set lies inside a cut cell)
+  const long long n = c->n, nc = c->ncell, nit = n + nc;
+  c->nit = nit;
   if(upload_tables(c)) return 1;
   if(!c->have_domain)
     if(glk_find_extent(c)) return 1;
-  GL_CUDA(c, c->key_m.ensure(n));
-  GL_CUDA(c, c->key_m_sorted.ensure(n));
-  GL_CUDA(c, c->idx.ensure(n));
-  GL_CUDA(c, c->perm.ensure(n));
+  GL_CUDA(c, c->key_m.ensure(nit));
+  GL_CUDA(c, c->key_m_sorted.ensure(nit));
+  GL_CUDA(c, c->idx.ensure(nit));
+  GL_CUDA(c, c->perm.ensure(nit));
   GL_CUDA(c, c->inv.ensure(n));
-  GL_CUDA(c, c->s_pm.ensure(n + 1));
-  GL_CUDA(c, c->s_vh.ensure(n + 1));
-  GL_CUDA(c, c->s_type.ensure(n + 1));
+  GL_CUDA(c, c->s_pm.ensure(nit + 1));
+  GL_CUDA(c, c->s_vh.ensure(nit + 1));
+  GL_CUDA(c, c->s_type.ensure(nit + 1));
+  GL_CUDA(c, c->s_lev.ensure(nit + 1));
   k_keys<false><<<gl_grid(n, 256), 256, 0, c->stream>>>(c->in_pos.p, n, c->dom, c->key_m.p, nullptr, c->idx.p);
   GL_LAUNCH_COUNT(c);
-  if(sort_pairs(c, c->key_m.p, c->key_m_sorted.p, c->idx.p, c->perm.p, n)) return 1;
-  k_gather_sorted<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->perm.p, c->in_pos.p, c->in_vel.p, c->in_mass.p,
-							  c->in_hsml.p, c->in_type.p, c->s_pm.p, c->s_vh.p,
-							  c->s_type.p, c->inv.p);
+  if(nc > 0)
+    {
+      GL_CUDA(c, cudaMemcpyAsync(c->key_m.p + n, c->c_key.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+      k_iota<<<gl_grid(nc, 256), 256, 0, c->stream>>>(c->idx.p + n, nc, (int) n);
+      GL_LAUNCH_COUNT(c);
+    }
+  if(sort_pairs(c, c->key_m.p, c->key_m_sorted.p, c->idx.p, c->perm.p, nit)) return 1;
+  k_gather_sorted<<<gl_grid(nit, 256), 256, 0, c->stream>>>(nit, n, c->perm.p, c->in_pos.p, c->in_vel.p, c->in_mass.p,
+							    c->in_hsml.p, c->in_type.p, c->c_sm.p, c->c_aux.p, c->c_level.p, c->s_pm.p, c->s_vh.p,
+							    c->s_type.p, c->s_lev.p, c->inv.p);
   GL_LAUNCH_COUNT(c);
   c->have_ph_order = false;
   // a caller that hands over its targets already ordered along the curve (a GPU's Peano-Hilbert segment, or the
@@ -411,6 +450,7 @@ int glk_keys_and_sort(gl_ctx *c)
 int glk_ph_sequence(gl_ctx *c)
 {
   if(c->have_ph_order) return 0;
+  if(c->ncell > 0) return c->fail("Peano-Hilbert sequence: not available on a locally-essential tree (multi-rank mode orders its own targets)");
   long long n = c->n;
   GL_CUDA(c, c->key_ph.ensure(n));
   GL_CUDA(c, c->ph_order.ensure(n + 1));
@@ -469,5 +509,119 @@ int glk_ph_order(gl_ctx *c, long long n_gas, int *order, int where)
   GL_CUDA(c, cudaMemcpyAsync(order, c->perm.p, n * sizeof(int), kind, c->stream));
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->tree_valid = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------- multi-rank helpers (gl_let.cu) ----
+__device__ __forceinline__ unsigned long long ph_from_morton_dev(unsigned long long m, const unsigned char *s_sub, const unsigned char *s_next)
+{
+  unsigned s = 0;
+  unsigned long long key = 0;
+#pragma unroll 1
+  for(int b = GL_BITS - 1; b >= 0; b--)
+    {
+      const unsigned d = (unsigned) (m >> (3 * b)) & 7u;
+      const unsigned pix = ((d & 1u) << 2) | (d & 2u) | (d >> 2);
+      const unsigned t = s * 8 + pix;
+      key = (key << 3) | s_sub[t];
+      s = s_next[t];
+    }
+  return key;
+}
+
+// Peano-Hilbert key hull of every stretch of the own particles (input order): block b reduces [bounds[b], bounds[b+1])
+__global__ void k_ph_chunk_hulls(const unsigned long long *__restrict__ mkey_in, const long long *__restrict__ bounds,
+				 unsigned long long *__restrict__ out)
+{
+  __shared__ unsigned char s_sub[192], s_next[192];
+  __shared__ unsigned long long sh[8][2];
+  for(int t = threadIdx.x; t < 192; t += blockDim.x)
+    {
+      s_sub[t] = c_hsub[t];
+      s_next[t] = c_hnext[t];
+    }
+  __syncthreads();
+  const int b = blockIdx.x;
+  unsigned long long lo = ~0ull, hi = 0;
+  for(long long i = bounds[b] + threadIdx.x; i < bounds[b + 1]; i += blockDim.x)
+    {
+      const unsigned long long k = ph_from_morton_dev(mkey_in[i], s_sub, s_next);
+      lo = k < lo ? k : lo;
+      hi = k > hi ? k : hi;
+    }
+  for(int o = 16; o > 0; o >>= 1)
+    {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o), bb = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = a < lo ? a : lo;
+      hi = bb > hi ? bb : hi;
+    }
+  if((threadIdx.x & 31) == 0)
+    {
+      sh[threadIdx.x >> 5][0] = lo;
+      sh[threadIdx.x >> 5][1] = hi;
+    }
+  __syncthreads();
+  if(threadIdx.x == 0)
+    {
+      for(int w = 1; w < blockDim.x / 32; w++)
+	{
+	  lo = sh[w][0] < lo ? sh[w][0] : lo;
+	  hi = sh[w][1] > hi ? sh[w][1] : hi;
+	}
+      out[2 * b] = lo;	// an empty stretch leaves lo > hi
+      out[2 * b + 1] = hi;
+    }
+}
+
+// key_m still holds the Morton keys in INPUT order after the sort (it was only read)
+int glk_ph_chunk_hulls(gl_ctx *c, const long long *bounds_dev, int nchunks, unsigned long long *out)
+{
+  if(upload_tables(c)) return 1;
+  k_ph_chunk_hulls<<<nchunks, 256, 0, c->stream>>>(c->key_m.p, bounds_dev, out);
+  GL_LAUNCH_COUNT(c);
+  return 0;
+}
+
+// A cell of level L is a contiguous stretch of the Peano-Hilbert curve: all keys that share its leading 3 L bits.
+__global__ void k_node_complete(long long m, const int *__restrict__ n_first, const signed char *__restrict__ n_level,
+				const unsigned long long *__restrict__ mkey, const unsigned long long *__restrict__ ranges, int world,
+				int nhull, long long stride, int me, unsigned char *__restrict__ complete)
+{
+  __shared__ unsigned char s_sub[192], s_next[192];
+  for(int t = threadIdx.x; t < 192; t += blockDim.x)
+    {
+      s_sub[t] = c_hsub[t];
+      s_next[t] = c_hnext[t];
+    }
+  __syncthreads();
+  const long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(id >= m) return;
+  const int L = n_level[id];
+  const unsigned long long ph = ph_from_morton_dev(mkey[n_first[id]], s_sub, s_next);
+  const int sh = 3 * (GL_BITS - L);
+  const unsigned long long lo = (sh >= 63) ? 0ull : ((ph >> sh) << sh);
+  const unsigned long long hi = (sh >= 63) ? ~0ull : (lo + ((1ull << sh) - 1ull));
+  bool ok = true;
+  for(int r = 0; r < world && ok; r++)
+    {
+      if(r == me) continue;
+      const unsigned long long *hr = ranges + (long long) r * stride;
+      for(int q = 0; q < nhull; q++)
+	{
+	  const unsigned long long a = hr[2 * q], b = hr[2 * q + 1];
+	  if(a > b) continue;	// an empty stretch
+	  if(!(b < lo || a > hi)) ok = false;
+	}
+    }
+  complete[id] = ok ? 1 : 0;
+}
+
+int glk_node_complete(gl_ctx *c, const unsigned long long *ranges, int world, int nhull, long long stride, int me, unsigned char *complete)
+{
+  if(upload_tables(c)) return 1;
+  if(c->nnodes <= 0) return 0;
+  k_node_complete<<<gl_grid(c->nnodes, 256), 256, 0, c->stream>>>(c->nnodes, c->n_first.p, c->n_level.p, c->key_m_sorted.p, ranges, world,
+								   nhull, stride, me, complete);
+  GL_LAUNCH_COUNT(c);
   return 0;
 }

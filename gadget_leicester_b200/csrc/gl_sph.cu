@@ -192,7 +192,7 @@ __device__ __forceinline__ void sph_collect(Stage &S, int lane, int nentries, co
 					    const int2 *__restrict__ e_rng, const int *__restrict__ n_child,
 					    const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
 					    const int *__restrict__ s_type, unsigned active, const GroupF &G,
-					    unsigned &visits, unsigned &staged, Flush flush)
+					    unsigned &visits, unsigned &staged, unsigned long long *__restrict__ counter, Flush flush)
 {
   if(nentries <= 0 || active == 0) return;
   int ncand = 0;
@@ -247,7 +247,14 @@ __device__ __forceinline__ void sph_collect(Stage &S, int lane, int nentries, co
 	  mybits |= (d2 < R2) ? (1u << i) : 0u;
 	}
       const unsigned touched = __reduce_or_sync(FULL, mybits);
-      const bool acc = isnode && ((touched >> lane) & 1);
+      bool acc = isnode && ((touched >> lane) & 1);
+      if(acc && rg.x < 0)
+	{
+	  // a CUT CELL of the locally-essential tree (multi-rank mode) within reach of a search sphere: the gas below it
+	  // stayed with its owner, whose export test promised this cannot happen.  Report instead of missing neighbours.
+	  atomicMax(&counter[2], GL_ERR_LET_VIOLATION);
+	  acc = false;
+	}
       const bool small = acc && (rg.y - rg.x <= 32);
       bool big = acc && !small;
       bool bucket = false;
@@ -750,7 +757,7 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
 	    density_pair(A, ptype, dx, dy, dz, r2, pj.w, hinv, hinv3, hinv4, vx, vy, vz, vj, (ptype != 0) ? __ldg(&s_entropy[j]) : 0.0);
 	  }
       };
-      sph_collect<false>(S, lane, nentries, e_next, e_B, nullptr, e_rng, n_child, s_pm, s_vh, s_type, todo_mask, G, visits, staged,
+      sph_collect<false>(S, lane, nentries, e_next, e_B, nullptr, e_rng, n_child, s_pm, s_vh, s_type, todo_mask, G, visits, staged, counter,
 			 [&](int ncand, float lmax) {
 			   if(ltmode)
 			     lt_chunk<false>(S, ncand, lmax, lane, G, qh, qt, heavy);
@@ -791,6 +798,10 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
   if(live && !deferred) density_store(A, h, p, pin, ptype, out, in, s_vh, e_B, par);
   const unsigned maxit = __reduce_max_sync(FULL, (unsigned) iter);
   const unsigned wrounds = __reduce_add_sync(FULL, (unsigned) myrounds);
+  // which target needed the most passes (diagnostics: the analogue of the reference's "ngb iteration" lines, density.c:661)
+  const unsigned mostr = __reduce_max_sync(FULL, (live && !deferred) ? (unsigned) myrounds : 0u);
+  if(live && !deferred && mostr > 1 && (unsigned) myrounds == mostr)
+    atomicMax(&counter[12], ((unsigned long long) mostr << 32) | (unsigned long long) (unsigned) pin);
   const unsigned wpairs = __reduce_add_sync(FULL, (live && !deferred) ? (unsigned) A.numngb : 0u);
   if(lane == 0)
     {
@@ -807,10 +818,12 @@ k_density(const int *__restrict__ tgt, long long nt, int nentries, const int *__
     }
 }
 
-__global__ void k_gather_d(long long n, const int *__restrict__ perm, const double *__restrict__ in, double *__restrict__ out)
+__global__ void k_gather_d(long long nit, long long n, const int *__restrict__ perm, const double *__restrict__ in, double *__restrict__ out)
 {
   long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(i < n) out[i] = in[perm[i]];
+  if(i >= nit) return;
+  const int j = perm[i];
+  out[i] = (j < n) ? in[j] : 0.0;	// (items >= n: cut cells of the multi-rank mode)
 }
 
 // ---------------------------------------------------------------- fat targets ----
@@ -827,13 +840,23 @@ struct FatTarget
 __global__ void k_fat_scan(long long n, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
 			   const int *__restrict__ s_type, const double *__restrict__ s_entropy, int nf,
 			   const FatTarget *__restrict__ ft, int *__restrict__ cnt, const int *__restrict__ off,
-			   double4 *__restrict__ rec)
+			   double4 *__restrict__ rec, const double4 *__restrict__ e_B, const int *__restrict__ noff,
+			   unsigned long long *__restrict__ counter)
 {
   __shared__ FatTarget sh[8];
   if(threadIdx.x < nf) sh[threadIdx.x] = ft[threadIdx.x];
   __syncthreads();
   const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(i >= n) return;
+  if(s_type[i] == -1)
+    {
+      // cut cell (multi-rank mode): the gas below it is not here - a guard sphere that reaches it is a violation
+      const double4 B = e_B[i + noff[i + 1]];
+      for(int f = 0; f < nf; f++)
+	if(sh[f].rc > 0 && dist2_to_cube(sh[f].x, sh[f].y, sh[f].z, B, 0.5 * B.w) < sh[f].rc * sh[f].rc * 1.0001)
+	  atomicMax(&counter[2], GL_ERR_LET_VIOLATION);
+      return;
+    }
   if(s_type[i] != 0) return;
   const double4 pm = s_pm[i];
   if(pm.w == 0) return;
@@ -975,6 +998,7 @@ k_fat_rounds(int nf, const int *__restrict__ fat_p, double4 *__restrict__ fat_st
 	    }
 	  fat_state[f] = make_double4(h, left, right, (double) iter);
 	  atomicMax(&counter[1], (unsigned long long) iter);
+	  atomicMax(&counter[12], ((unsigned long long) (unsigned) iter << 32) | (unsigned long long) (unsigned) pin);
 	  atomicAdd(&counter[11], 1ull);
 	  if(!redo) atomicAdd(&counter[9], (unsigned long long) A.numngb);
 	  // post the decision into every CTA of the cluster
@@ -994,7 +1018,7 @@ k_fat_rounds(int nf, const int *__restrict__ fat_p, double4 *__restrict__ fat_st
 static int density_fat_path(gl_ctx *c, int nfat, const DensIn &in, const DensOut &out, const double *s_entropy,
 			    const gl_dparams &dp)
 {
-  long long n = c->n;
+  long long n = c->nit;	// tree-ordered items
   std::vector<int> hp(nfat), hflag(nfat, 0);
   std::vector<double4> hst(nfat);
   GL_CUDA(c, cudaMemcpyAsync(hp.data(), c->fat_p.p, nfat * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1026,7 +1050,7 @@ static int density_fat_path(gl_ctx *c, int nfat, const DensIn &in, const DensOut
 	  GL_CUDA(c, cudaMemcpyAsync(c->fat_i.p, hz, sizeof(hz), cudaMemcpyHostToDevice, c->stream));
 	  int *cnt = c->fat_i.p, *off = c->fat_i.p + 8, *flag = c->fat_i.p + 16;
 	  k_fat_scan<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->s_pm.p, c->s_vh.p, c->s_type.p, s_entropy, nb,
-							    (const FatTarget *) c->fat_tgt.p, cnt, off, nullptr);
+							    (const FatTarget *) c->fat_tgt.p, cnt, off, nullptr, c->e_B.p, c->noff.p, c->d_counter.p);
 	  GL_LAUNCH_COUNT(c);
 	  int hc[8];
 	  GL_CUDA(c, cudaMemcpyAsync(hc, cnt, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
@@ -1044,7 +1068,7 @@ static int density_fat_path(gl_ctx *c, int nfat, const DensIn &in, const DensOut
 	  GL_CUDA(c, cudaMemcpyAsync(off, ho, sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
 	  GL_CUDA(c, cudaMemcpyAsync(flag, hfl, sizeof(int) * nb, cudaMemcpyHostToDevice, c->stream));
 	  k_fat_scan<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->s_pm.p, c->s_vh.p, c->s_type.p, s_entropy, nb,
-							    (const FatTarget *) c->fat_tgt.p, cnt, off, c->fat_rec.p);
+							    (const FatTarget *) c->fat_tgt.p, cnt, off, c->fat_rec.p, c->e_B.p, c->noff.p, c->d_counter.p);
 	  GL_LAUNCH_COUNT(c);
 	  k_fat_rounds<<<nb * FAT_CLUSTER, FAT_THREADS, 0, c->stream>>>(nb, c->fat_p.p + b0, c->fat_state.p + b0, flag,
 							  (const FatTarget *) c->fat_tgt.p, cnt, off, c->fat_rec.p, c->s_pm.p,
@@ -1088,12 +1112,12 @@ int gls_density(gl_ctx *c)
       GL_CUDA(c, cudaMemsetAsync(c->o_denspairs.p, 0, c->o_denspairs.cap * sizeof(int), c->stream));	// no history: nobody is fat yet
     }
   GL_CUDA(c, c->d_counter.ensure(16));
-  GL_CUDA(c, c->h_q.ensure(n + 1));
-  GL_CUDA(c, c->h_r.ensure(n + 1));	// scratch: the tree-ordered entropy lives here until hydro overwrites it
+  GL_CUDA(c, c->h_q.ensure(c->nit + 1));
+  GL_CUDA(c, c->h_r.ensure(c->nit + 1));	// scratch: the tree-ordered entropy lives here until hydro overwrites it
   double *s_entropy = (double *) c->h_r.p;
   GL_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16 * sizeof(unsigned long long), c->stream));
   cudaEventRecord(c->ev[0], c->stream);
-  k_gather_d<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->perm.p, c->in_entropy.p, s_entropy);
+  k_gather_d<<<gl_grid(c->nit, 256), 256, 0, c->stream>>>(c->nit, n, c->perm.p, c->in_entropy.p, s_entropy);
   GL_LAUNCH_COUNT(c);
   DensOut out{c->in_hsml.p, c->o_numngb.p, c->o_density.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p, c->o_pressure.p,
 	      c->o_sinkrho.p, c->o_sinkentr.p, c->o_sinkvel.p, c->o_denspairs.p, c->e_F1.p, c->grav_scale.p};
@@ -1122,7 +1146,7 @@ int gls_density(gl_ctx *c)
       c->st.density_fat_targets = (long long) nfat;
     }
   cudaEventRecord(c->ev[1], c->stream);
-  unsigned long long cnt[12];
+  unsigned long long cnt[13];
   GL_CUDA(c, cudaMemcpyAsync(cnt, c->d_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   GL_CUDA(c, cudaGetLastError());
@@ -1133,9 +1157,12 @@ int gls_density(gl_ctx *c)
   c->st.density_passes_max = (long long) cnt[1];
   c->st.density_pairs = (long long) cnt[9];
   c->st.density_target_passes = (long long) cnt[11];
+  c->st.density_slowest_index = (cnt[12] >> 32) ? (long long) (cnt[12] & 0xffffffffull) : -1;
+  c->st.density_slowest_passes = (long long) (cnt[12] >> 32);
   if(getenv("GL_DEBUG_SPH"))
     fprintf(stderr, "[gl] density: %lld warps, cycles max %.3g avg %.3g | staged max %llu avg %.1f | entry visits max %llu | rounds max %llu | %.2f ms\n",
 	    (nt + 31) / 32, (double) cnt[3], (double) cnt[4] / ((nt + 31) / 32), cnt[5], (double) cnt[6] / ((nt + 31) / 32), cnt[7], cnt[1], ms);
+  if(cnt[2] == GL_ERR_LET_VIOLATION) return c->fail("density: GL_ERR_LET_VIOLATION");
   if(cnt[2] == 1155) return c->fail("density: failed to converge in neighbour iteration (endrun(1155), density.c:669)");
   if(cnt[2] == 8188) return c->fail("density: Left == Right == 0 (endrun(8188), density.c:608)");
   return 0;
@@ -1332,7 +1359,7 @@ k_hydro(const int *__restrict__ tgt, long long nt, int nentries, const int *__re
   auto heavy = [&](int j) { hydro_pair(T, K, A, j, s_pm, s_vh, h_q, h_r); };
   int qh = 0, qt = 0;
   // hydro has no iteration: every warp but the last one is full, so lane = target always
-  sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, G, visits, staged,
+  sph_collect<true>(S, lane, nentries, e_next, e_B, e_hmax, e_rng, n_child, s_pm, s_vh, s_type, live_mask, G, visits, staged, counter,
 		    [&](int ncand, float lmax) { lt_chunk<true>(S, ncand, lmax, lane, G, qh, qt, heavy); });
   q_drain(S, lane, qh, qt, 0, heavy);
 #ifdef GL_PHASE_PROF
@@ -1357,12 +1384,13 @@ int gls_hydro_begin(gl_ctx *c)
   GL_CUDA(c, c->o_dtentr.ensure(n));
   GL_CUDA(c, c->o_maxsig.ensure(n));
   GL_CUDA(c, c->o_hydropairs.ensure(n));
-  GL_CUDA(c, c->h_q.ensure(n + 1));
-  GL_CUDA(c, c->h_r.ensure(n + 1));
+  GL_CUDA(c, c->h_q.ensure(c->nit + 1));
+  GL_CUDA(c, c->h_r.ensure(c->nit + 1));
   GL_CUDA(c, c->d_counter.ensure(16));
   GL_CUDA(c, cudaMemsetAsync(c->d_counter.p + 10, 0, sizeof(unsigned long long), c->stream));
+  GL_CUDA(c, cudaMemsetAsync(c->d_counter.p + 2, 0, sizeof(unsigned long long), c->stream));
   cudaEventRecord(c->ev[0], c->stream);
-  k_hydro_prep<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->perm.p, c->s_type.p, c->s_vh.p, c->o_density.p, c->o_pressure.p,
+  k_hydro_prep<<<gl_grid(c->nit, 256), 256, 0, c->stream>>>(c->nit, c->perm.p, c->s_type.p, c->s_vh.p, c->o_density.p, c->o_pressure.p,
 							c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p, c->in_timebin.p, c->h_q.p,
 							c->h_r.p);
   GL_LAUNCH_COUNT(c);
@@ -1392,10 +1420,12 @@ int gls_hydro_end(gl_ctx *c)
 {
   cudaEventRecord(c->ev[1], c->stream);
   c->fire_post_launch();
-  unsigned long long hp = 0;
+  unsigned long long hp = 0, viol = 0;
   GL_CUDA(c, cudaMemcpyAsync(&hp, c->d_counter.p + 10, sizeof(hp), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaMemcpyAsync(&viol, c->d_counter.p + 2, sizeof(viol), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, c->wait_stream());
   GL_CUDA(c, cudaGetLastError());
+  if(viol == GL_ERR_LET_VIOLATION) return c->fail("hydro_force: GL_ERR_LET_VIOLATION");
   float ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
   c->st.ms_hydro = ms;

@@ -39,20 +39,29 @@ __global__ void k_levels(const unsigned long long *__restrict__ key, long long n
     c[i] = (signed char) common_level(key[i - 1], key[i]);
 }
 
-__global__ void k_count(const signed char *__restrict__ c, long long n, int *__restrict__ cnt)
+// Items, not only particles: in multi-rank mode the sorted order also holds CUT CELLS (s_lev = level of the cell, 22 for
+// a particle) - cells another rank has summarised for us.  A cut cell stands for >= 2 particles, so every proper ancestor
+// of it exists as a node; the ones that start at item a reach down to level s_lev - 1 (chain nodes with one child).
+__device__ __forceinline__ int top_level_at(const signed char *__restrict__ c, const signed char *__restrict__ s_lev, long long a)
+{
+  const int up = c[a + 1], lv = s_lev[a];
+  return (lv <= GL_BITS && lv - 1 > up) ? lv - 1 : up;
+}
+
+__global__ void k_count(const signed char *__restrict__ c, const signed char *__restrict__ s_lev, long long n, int *__restrict__ cnt)
 {
   long long a = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(a > n) return;
   int v = 0;
   if(a < n)
     {
-      v = (int) c[a + 1] - (int) c[a];
+      v = top_level_at(c, s_lev, a) - (int) c[a];
       if(v < 0) v = 0;
     }
   cnt[a] = v;
 }
 
-__global__ void k_make_nodes(const signed char *__restrict__ c, const int *__restrict__ noff, long long n,
+__global__ void k_make_nodes(const signed char *__restrict__ c, const signed char *__restrict__ s_lev, const int *__restrict__ noff, long long n,
 			     int *__restrict__ n_first, signed char *__restrict__ n_level, int *__restrict__ levcount)
 {
   __shared__ int sh[GL_BITS + 1];
@@ -61,7 +70,7 @@ __global__ void k_make_nodes(const signed char *__restrict__ c, const int *__res
   long long a = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(a < n)
     {
-      int c0 = c[a], c1 = c[a + 1];
+      int c0 = c[a], c1 = top_level_at(c, s_lev, a);
       int base = noff[a];
       for(int L = c0 + 1; L <= c1; L++)
 	{
@@ -127,11 +136,12 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
 			  long long n, const signed char *__restrict__ c, const int *__restrict__ noff,
 			  const int *__restrict__ n_first, int *__restrict__ n_end, int *__restrict__ n_parent,
 			  int *__restrict__ p_father, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
-			  const int *__restrict__ s_type, double4 *__restrict__ n_sm, double4 *__restrict__ n_cl,
-			  double4 *__restrict__ n_aux, int *__restrict__ n_child, gl_domain dom, gl_dparams par)
+			  const int *__restrict__ s_type, const signed char *__restrict__ s_lev, double4 *__restrict__ n_sm,
+			  double4 *__restrict__ n_cl, double4 *__restrict__ n_aux, int *__restrict__ n_child, gl_domain dom, gl_dparams par)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if(t >= count) return;
+  bool cut = false;		// a cut cell somewhere below this node (multi-rank mode)
   int id = lev_list[t];
   // child table for the parallel SPH walks: DFS entry index of a child node, -(p+2) for a particle leaf p,
   // -1 = no further child; a finest-level bucket (coincident keys) is flagged by n_child[0] = INT_MIN
@@ -172,7 +182,24 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
 	    }
 	  if(c[q] > L) q = range_end(key, q - 1, (int) n, sh2, key[p] >> sh2);	// big cell: finish this child by bisection
 	}
-      if(q - p == 1)
+      const int lvp = s_lev[p];
+      if(q - p == 1 && lvp <= GL_BITS && lvp <= L + 1)
+	{
+	  // cut-cell leaf: the moments its owner computed, added exactly like a child cell's (s_vh = maxsoft, hmax, vmax)
+	  const double4 cs = s_pm[p], ca = s_vh[p];
+	  mass = __dadd_rn(mass, cs.w);
+	  s0 = __dadd_rn(s0, __dmul_rn(cs.w, cs.x));
+	  s1 = __dadd_rn(s1, __dmul_rn(cs.w, cs.y));
+	  s2 = __dadd_rn(s2, __dmul_rn(cs.w, cs.z));
+	  if(ca.y > hmax) hmax = ca.y;
+	  if(ca.z > vmax) vmax = ca.z;
+	  if(ca.x > maxsoft) maxsoft = ca.x;
+	  p_father[p] = id;
+	  if(nch < 8) child_tab[nch] = p + noff[p + 1];	// its DFS entry (a node-type record without descendants)
+	  nch++;
+	  cut = true;
+	}
+      else if(q - p == 1 && lvp > GL_BITS)
 	{
 	  // particle leaf (for L == GL_BITS every particle of the finest cell hangs directly below)
 	  double4 pm = s_pm[p];
@@ -206,6 +233,7 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
 	  if(ca.y > hmax) hmax = ca.y;
 	  if(ca.z > vmax) vmax = ca.z;
 	  if(ca.x > maxsoft) maxsoft = ca.x;
+	  if(ca.w != 0) cut = true;
 	  n_parent[child] = id;
 	  if(nch < 8) child_tab[nch] = p + child;	// DFS entry index of node (p, L+1): first particle + node id
 	  nch++;
@@ -233,7 +261,7 @@ __global__ void k_moments(int L, const int *__restrict__ lev_list, int count, co
     }
   n_sm[id] = make_double4(s0, s1, s2, mass);
   n_cl[id] = make_double4(cx, cy, cz, len);
-  n_aux[id] = make_double4(maxsoft, hmax, vmax, 0.0);
+  n_aux[id] = make_double4(maxsoft, hmax, vmax, cut ? 1.0 : 0.0);
   for(int k = nch; k < 8; k++) child_tab[k] = -1;
   if(nch > 8) child_tab[0] = INT_MIN;
 }
@@ -262,8 +290,8 @@ __global__ void k_moments_wide(int L, const int *__restrict__ lev_list, int coun
 			       long long n, const signed char *__restrict__ c, const int *__restrict__ noff,
 			       const int *__restrict__ n_first, int *__restrict__ n_end, int *__restrict__ n_parent,
 			       int *__restrict__ p_father, const double4 *__restrict__ s_pm, const double4 *__restrict__ s_vh,
-			       const int *__restrict__ s_type, double4 *__restrict__ n_sm, double4 *__restrict__ n_cl,
-			       double4 *__restrict__ n_aux, int *__restrict__ n_child, gl_domain dom, gl_dparams par)
+			       const int *__restrict__ s_type, const signed char *__restrict__ s_lev, double4 *__restrict__ n_sm,
+			       double4 *__restrict__ n_cl, double4 *__restrict__ n_aux, int *__restrict__ n_child, gl_domain dom, gl_dparams par)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = t >> 3, s = t & 7;
@@ -295,7 +323,20 @@ __global__ void k_moments_wide(int L, const int *__restrict__ lev_list, int coun
   // this lane's child: mass, m*x, m*y, m*z, hmax, vmax, maxsoft
   double cm = 0, t0 = 0, t1 = 0, t2 = 0, chm = 0, cvm = 0, cms = 0;
   int code = -1;
-  if(live && np == 1)
+  bool mycut = false;
+  const int lvlo = (live && np == 1) ? (int) s_lev[lo] : GL_BITS + 1;
+  if(live && np == 1 && lvlo <= GL_BITS && lvlo <= L + 1)
+    {
+      // cut-cell leaf (multi-rank mode): its owner's moments, s_vh = (maxsoft, hmax, vmax)
+      const double4 cs = s_pm[lo], ca = s_vh[lo];
+      cm = cs.w;
+      t0 = __dmul_rn(cs.w, cs.x); t1 = __dmul_rn(cs.w, cs.y); t2 = __dmul_rn(cs.w, cs.z);
+      chm = ca.y; cvm = ca.z; cms = ca.x;
+      p_father[lo] = id;
+      code = lo + noff[lo + 1];
+      mycut = true;
+    }
+  else if(live && np == 1 && lvlo > GL_BITS)
     {
       const double4 pm = s_pm[lo];
       const double4 vh = s_vh[lo];
@@ -313,7 +354,7 @@ __global__ void k_moments_wide(int L, const int *__restrict__ lev_list, int coun
       p_father[lo] = id;
       code = -(lo + 2);
     }
-  else if(live && np > 1)
+  else if(live && np >= 1)	// several items, or one cut cell that lies deeper than the next level (chain of one-child cells)
     {
       const int child = noff[lo] + (L - (int) c[lo]);
       const double4 cs = n_sm[child];
@@ -321,11 +362,13 @@ __global__ void k_moments_wide(int L, const int *__restrict__ lev_list, int coun
       cm = cs.w;
       t0 = __dmul_rn(cs.w, cs.x); t1 = __dmul_rn(cs.w, cs.y); t2 = __dmul_rn(cs.w, cs.z);
       chm = ca.y; cvm = ca.z; cms = ca.x;
+      mycut = ca.w != 0;
       n_parent[child] = id;
       code = lo + child;	// DFS entry index of the child node
     }
   const bool present = live && np > 0;
   const unsigned pres8 = (__ballot_sync(0xffffffffu, present) >> lbase) & 0xffu;
+  const bool cut = ((__ballot_sync(0xffffffffu, mycut) >> lbase) & 0xffu) != 0;
   // slot-ordered sums, every lane of the group forms the same values
   double mass = 0, s0 = 0, s1 = 0, s2 = 0, hmax = 0, vmax = 0, maxsoft = 0;
 #pragma unroll
@@ -369,7 +412,7 @@ __global__ void k_moments_wide(int L, const int *__restrict__ lev_list, int coun
 	}
       n_sm[id] = make_double4(s0, s1, s2, mass);
       n_cl[id] = make_double4(cx, cy, cz, len);
-      n_aux[id] = make_double4(maxsoft, hmax, vmax, 0.0);
+      n_aux[id] = make_double4(maxsoft, hmax, vmax, cut ? 1.0 : 0.0);
     }
 }
 
@@ -388,27 +431,60 @@ __global__ void k_grav_scale(long long m, long long n, const double4 *__restrict
 
 __global__ void k_entries_particles(long long n, const int *__restrict__ noff, const double4 *__restrict__ s_pm,
 				    const double4 *__restrict__ s_vh, const int *__restrict__ s_type,
+				    const signed char *__restrict__ s_lev, const unsigned long long *__restrict__ key,
 				    int *__restrict__ e_next, double4 *__restrict__ e_A, double4 *__restrict__ e_B,
-				    double2 *__restrict__ e_C, double *__restrict__ e_hmax, float4 *__restrict__ e_F0,
-				    float4 *__restrict__ e_F1, const double *__restrict__ scale, gl_domain dom, gl_dparams par)
+				    double2 *__restrict__ e_C, double *__restrict__ e_hmax, int2 *__restrict__ e_rng, float4 *__restrict__ e_F0,
+				    float4 *__restrict__ e_F1, float4 *__restrict__ e_F2, const double *__restrict__ scale, gl_domain dom,
+				    gl_dparams par)
 {
   long long p = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(p >= n) return;
   long long e = p + noff[p + 1];
-  int ty = s_type[p];
-  double soft = (ty == 0) ? s_vh[p].w : par.soft[ty];
-  const double4 pm = s_pm[p];
-  e_next[e] = -1 - (int) (p * 8 + ty);
-  e_A[e] = pm;
-  e_B[e] = make_double4(soft, 0.0, 0.0, -1.0);
-  e_C[e] = make_double2(0.0, 0.0);
-  e_hmax[e] = 0.0;
   const double S = scale[0], Ms = scale[1];
+  const double4 pm = s_pm[p];
   float4 f0, f1;
   gl_split(pm.x, dom.center[0], S, f0.x, f1.x);
   gl_split(pm.y, dom.center[1], S, f0.y, f1.y);
   gl_split(pm.z, dom.center[2], S, f0.z, f1.z);
   f0.w = (float) (pm.w * Ms);
+  const int lv = s_lev[p];
+  if(lv <= GL_BITS)
+    {
+      // CUT CELL (multi-rank mode): a cell record whose descendants stayed with their owner.  It takes part like any
+      // accepted cell; a walk that wants to open it, or a neighbour search that touches it, raises
+      // GL_ERR_LET_VIOLATION instead (e_next = e + 1 and e_rng = (-1,-1) mark it).  Centre and side length by the
+      // same +-len/4 steps as k_moments, so they are the values of the global tree.
+      const unsigned long long ka = key[p];
+      double len = dom.len, cx = dom.center[0], cy = dom.center[1], cz = dom.center[2];
+      for(int l = 1; l <= lv; l++)
+	{
+	  int d = (int) ((ka >> (3 * (GL_BITS - l))) & 7);
+	  double lenhalf = __dmul_rn(0.25, len);
+	  cx = (d & 1) ? __dadd_rn(cx, lenhalf) : __dsub_rn(cx, lenhalf);
+	  cy = (d & 2) ? __dadd_rn(cy, lenhalf) : __dsub_rn(cy, lenhalf);
+	  cz = (d & 4) ? __dadd_rn(cz, lenhalf) : __dsub_rn(cz, lenhalf);
+	  len = __dmul_rn(0.5, len);
+	}
+      const double4 ax = s_vh[p];	// maxsoft, hmax, vmax
+      e_next[e] = (int) e + 1;
+      e_A[e] = pm;
+      e_B[e] = make_double4(cx, cy, cz, len);
+      e_C[e] = make_double2(ax.x, __dmul_rn(__dmul_rn(pm.w, len), len));
+      e_hmax[e] = ax.y;
+      e_rng[e] = make_int2(-1, -1);
+      f1.w = (float) (len * S);
+      e_F0[e] = f0;
+      e_F1[e] = f1;
+      e_F2[e] = make_float4((float) ((cx - pm.x) * S), (float) ((cy - pm.y) * S), (float) ((cz - pm.z) * S), (float) (ax.x * S));
+      return;
+    }
+  int ty = s_type[p];
+  double soft = (ty == 0) ? s_vh[p].w : par.soft[ty];
+  e_next[e] = -1 - (int) (p * 8 + ty);
+  e_A[e] = pm;
+  e_B[e] = make_double4(soft, 0.0, 0.0, -1.0);
+  e_C[e] = make_double2(0.0, 0.0);
+  e_hmax[e] = 0.0;
   f1.w = (float) (soft * S);
   e_F0[e] = f0;
   e_F1[e] = f1;
@@ -449,11 +525,13 @@ __global__ void k_entries_nodes(long long m, long long n, const int *__restrict_
 
 // particle range [a,b) below every node entry: lets the SPH walks swallow a small cell in one coalesced step
 __global__ void k_entries_range(long long m, const int *__restrict__ n_first, const int *__restrict__ n_end,
-				int2 *__restrict__ e_rng)
+				const double4 *__restrict__ n_aux, int2 *__restrict__ e_rng)
 {
   long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(id >= m) return;
-  e_rng[(long long) n_first[id] + id] = make_int2(n_first[id], n_end[id]);	// node id = entry index - first
+  // node id = entry index - first.  A cell with a cut cell somewhere below is never swallowed whole by the SPH
+  // searches (end = INT_MAX makes it "large"): they descend, so the cut cell itself meets the cube test.
+  e_rng[(long long) n_first[id] + id] = make_int2(n_first[id], n_aux[id].w != 0 ? INT_MAX : n_end[id]);
 }
 
 static int scan_exclusive(gl_ctx *c, const int *in, int *out, long long n)
@@ -487,11 +565,22 @@ gl_dparams gl_make_dparams(const gl_ctx *c)
 
 int glt_build(gl_ctx *c)
 {
-  long long n = c->n;
-  if(n <= 0) return c->fail("force_treebuild: no particles loaded");
+  // multi-rank mode: keys of the global cube, own tree, locally-essential exchange, merged tree (gl_let.cu)
+  if(c->comm && c->comm->world > 1) return gll_distributed_build(c);
+  c->n_own = c->n;
+  c->ncell = 0;
+  return glt_build_local(c, true);
+}
+
+// The build over the items currently loaded: c->n particles (+ c->ncell cut cells).  entries = false stops after the
+// moments (the own-particle tree a rank only selects its exports from).
+int glt_build_local(gl_ctx *c, bool entries)
+{
+  if(c->n <= 0) return c->fail("force_treebuild: no particles loaded");
   if(!c->have_par) return c->fail("force_treebuild: gl_set_params not called");
   cudaEventRecord(c->ev[0], c->stream);
   if(glk_keys_and_sort(c)) return 1;
+  const long long n = c->nit;	// items of the sorted order
   cudaEventRecord(c->ev[1], c->stream);
   const unsigned long long *key = c->key_m_sorted.p;
   GL_CUDA(c, c->lev_c.ensure(n + 2));
@@ -499,7 +588,7 @@ int glt_build(gl_ctx *c)
   GL_CUDA(c, c->noff.ensure(n + 2));
   GL_CUDA(c, c->scan_tmp_i.ensure(64));
   k_levels<<<gl_grid(n + 1, 256), 256, 0, c->stream>>>(key, n, c->lev_c.p);
-  k_count<<<gl_grid(n + 1, 256), 256, 0, c->stream>>>(c->lev_c.p, n, c->ncnt.p);
+  k_count<<<gl_grid(n + 1, 256), 256, 0, c->stream>>>(c->lev_c.p, c->s_lev.p, n, c->ncnt.p);
   c->kernel_launches += 2;
   if(scan_exclusive(c, c->ncnt.p, c->noff.p, n + 1)) return 1;
   int m = 0;
@@ -525,7 +614,7 @@ int glt_build(gl_ctx *c)
   int hcount[GL_BITS + 1];
   if(m > 0)
     {
-      k_make_nodes<<<gl_grid(n, 256), 256, 0, c->stream>>>(c->lev_c.p, c->noff.p, n, c->n_first.p, c->n_level.p,
+      k_make_nodes<<<gl_grid(n, 256), 256, 0, c->stream>>>(c->lev_c.p, c->s_lev.p, c->noff.p, n, c->n_first.p, c->n_level.p,
 							  levcount);
       GL_LAUNCH_COUNT(c);
       GL_CUDA(c, cudaMemcpyAsync(hcount, levcount, sizeof(hcount), cudaMemcpyDeviceToHost, c->stream));
@@ -543,6 +632,8 @@ int glt_build(gl_ctx *c)
       k_fill_levels<<<gl_grid(m, 256), 256, 0, c->stream>>>(c->n_level.p, m, levcount + 32, c->lev_list.p);
       GL_LAUNCH_COUNT(c);
     }
+  else
+    for(int L = 0; L <= GL_BITS + 1; L++) c->lev_start[L] = 0;
   cudaEventRecord(c->ev[2], c->stream);
   gl_dparams dp = gl_make_dparams(c);
   if(m > 0)
@@ -554,42 +645,45 @@ int glt_build(gl_ctx *c)
 	if(L < GL_BITS && cnt <= wide_max)	// few, fat cells: eight lanes per node (see k_moments_wide)
 	  k_moments_wide<<<gl_grid(8ll * cnt, 128), 128, 0, c->stream>>>(L, c->lev_list.p + c->lev_start[L], cnt, key, n, c->lev_c.p,
 									 c->noff.p, c->n_first.p, c->n_end.p, c->n_parent.p,
-									 c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->n_sm.p,
+									 c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->s_lev.p, c->n_sm.p,
 									 c->n_cl.p, c->n_aux.p, c->n_child.p, c->dom, dp);
 	else
 	  k_moments<<<gl_grid(cnt, 128), 128, 0, c->stream>>>(L, c->lev_list.p + c->lev_start[L], cnt, key, n, c->lev_c.p,
 							     c->noff.p, c->n_first.p, c->n_end.p, c->n_parent.p,
-							     c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->n_sm.p,
+							     c->p_father.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->s_lev.p, c->n_sm.p,
 							     c->n_cl.p, c->n_aux.p, c->n_child.p, c->dom, dp);
 	GL_LAUNCH_COUNT(c);
       }
-  size_t ne = (size_t) c->nentries + 1;
-  GL_CUDA(c, c->e_next.ensure(ne));
-  GL_CUDA(c, c->e_A.ensure(ne));
-  GL_CUDA(c, c->e_B.ensure(ne));
-  GL_CUDA(c, c->e_C.ensure(ne));
-  GL_CUDA(c, c->e_hmax.ensure(ne));
-  GL_CUDA(c, c->e_F0.ensure(ne));
-  GL_CUDA(c, c->e_F1.ensure(ne));
-  GL_CUDA(c, c->e_F2.ensure(ne));
-  GL_CUDA(c, c->grav_scale.ensure(2));
-  k_grav_scale<<<1, 32, 0, c->stream>>>(m, n, c->n_sm.p, c->s_pm.p, c->dom.len, c->grav_scale.p);
-  k_entries_particles<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->noff.p, c->s_pm.p, c->s_vh.p, c->s_type.p,
-							      c->e_next.p, c->e_A.p, c->e_B.p, c->e_C.p, c->e_hmax.p, c->e_F0.p,
-							      c->e_F1.p, c->grav_scale.p, c->dom, dp);
-  c->kernel_launches += 2;
-  if(m > 0)
+  if(entries)
     {
-      k_entries_nodes<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, n, c->noff.p, c->n_first.p, c->n_end.p, c->n_sm.p,
-							       c->n_cl.p, c->n_aux.p, c->e_next.p, c->e_A.p, c->e_B.p,
-							       c->e_C.p, c->e_hmax.p, c->e_F0.p, c->e_F1.p, c->e_F2.p, c->grav_scale.p,
-							       c->dom);
-      GL_LAUNCH_COUNT(c);
+      size_t ne = (size_t) c->nentries + 1;
+      GL_CUDA(c, c->e_next.ensure(ne));
+      GL_CUDA(c, c->e_A.ensure(ne));
+      GL_CUDA(c, c->e_B.ensure(ne));
+      GL_CUDA(c, c->e_C.ensure(ne));
+      GL_CUDA(c, c->e_hmax.ensure(ne));
       GL_CUDA(c, c->e_rng.ensure(ne));
-      k_entries_range<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->n_first.p, c->n_end.p, c->e_rng.p);
-      GL_LAUNCH_COUNT(c);
+      GL_CUDA(c, c->e_F0.ensure(ne));
+      GL_CUDA(c, c->e_F1.ensure(ne));
+      GL_CUDA(c, c->e_F2.ensure(ne));
+      GL_CUDA(c, c->grav_scale.ensure(2));
+      k_grav_scale<<<1, 32, 0, c->stream>>>(m, n, c->n_sm.p, c->s_pm.p, c->dom.len, c->grav_scale.p);
+      k_entries_particles<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->noff.p, c->s_pm.p, c->s_vh.p, c->s_type.p, c->s_lev.p, key,
+								  c->e_next.p, c->e_A.p, c->e_B.p, c->e_C.p, c->e_hmax.p, c->e_rng.p,
+								  c->e_F0.p, c->e_F1.p, c->e_F2.p, c->grav_scale.p, c->dom, dp);
+      c->kernel_launches += 2;
+      if(m > 0)
+	{
+	  k_entries_nodes<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, n, c->noff.p, c->n_first.p, c->n_end.p, c->n_sm.p,
+								   c->n_cl.p, c->n_aux.p, c->e_next.p, c->e_A.p, c->e_B.p,
+								   c->e_C.p, c->e_hmax.p, c->e_F0.p, c->e_F1.p, c->e_F2.p, c->grav_scale.p,
+								   c->dom);
+	  GL_LAUNCH_COUNT(c);
+	  k_entries_range<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->n_first.p, c->n_end.p, c->n_aux.p, c->e_rng.p);
+	  GL_LAUNCH_COUNT(c);
+	}
+      if(glk_apply_velpred(c)) return 1;	// after the moments: node vmax is built from P[].Vel (forcetree.c:684)
     }
-  if(glk_apply_velpred(c)) return 1;	// after the moments: node vmax is built from P[].Vel (forcetree.c:684)
   cudaEventRecord(c->ev[3], c->stream);
   GL_CUDA(c, cudaGetLastError());
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -602,8 +696,8 @@ int glt_build(gl_ctx *c)
   c->st.ms_moments = ms;
   c->st.numnodes = m;
   c->st.numentries = c->nentries;
-  c->tree_valid = true;
-  c->tree_flag = false;
+  c->tree_valid = entries;
+  c->tree_flag = !entries;
   c->tgt_dirty = true;
   return 0;
 }
@@ -613,7 +707,7 @@ int glt_build(gl_ctx *c)
 // Hsml raises the node's hmax.  Positive doubles order like their bit patterns, so an unsigned
 // 64-bit atomicMax implements "if(h > hmax) hmax = h" without a lock.
 __global__ void k_update_hmax(long long n, const int *__restrict__ s_type, const double4 *__restrict__ s_vh,
-			      const int *__restrict__ p_father, const int *__restrict__ n_parent,
+			      const int *__restrict__ noff, const int *__restrict__ p_father, const int *__restrict__ n_parent,
 			      const int *__restrict__ n_first, double *__restrict__ e_hmax)
 {
   // every gas particle of the tree, not only this call's targets: particles whose Hsml did not change
@@ -622,8 +716,10 @@ __global__ void k_update_hmax(long long n, const int *__restrict__ s_type, const
   // forcetree.c:1722-1747)
   long long p = blockIdx.x * (long long) blockDim.x + threadIdx.x;
   if(p >= n) return;
-  if(s_type[p] != 0) return;
-  double h = s_vh[p].w;
+  const int ty = s_type[p];
+  if(ty != 0 && ty != -1) return;
+  // a cut cell (type -1, multi-rank mode) climbs with the hmax its owner sent after density (its own entry)
+  double h = (ty == 0) ? s_vh[p].w : e_hmax[p + noff[p + 1]];
   unsigned long long hb = (unsigned long long) __double_as_longlong(h);
   int no = p_father[p];
   while(no >= 0)
@@ -635,13 +731,21 @@ __global__ void k_update_hmax(long long n, const int *__restrict__ s_type, const
     }
 }
 
+int glt_launch_update_hmax(gl_ctx *c)
+{
+  k_update_hmax<<<gl_grid(c->nit, 256), 256, 0, c->stream>>>(c->nit, c->s_type.p, c->s_vh.p, c->noff.p, c->p_father.p, c->n_parent.p,
+							      c->n_first.p, c->e_hmax.p);
+  GL_LAUNCH_COUNT(c);
+  return 0;
+}
+
 int glt_update_hmax(gl_ctx *c)
 {
   if(!c->tree_valid) return c->fail("force_update_hmax: no tree");
   cudaEventRecord(c->ev[0], c->stream);
-  k_update_hmax<<<gl_grid(c->n, 256), 256, 0, c->stream>>>(c->n, c->s_type.p, c->s_vh.p, c->p_father.p, c->n_parent.p,
-							    c->n_first.p, c->e_hmax.p);
-  GL_LAUNCH_COUNT(c);
+  if(c->comm && c->comm->world > 1)
+    if(gll_exchange_sph_state(c)) return 1;	// multi-rank: Hsml + SphP of the imported particles, hmax of the cut cells
+  if(glt_launch_update_hmax(c)) return 1;
   cudaEventRecord(c->ev[1], c->stream);
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   float ms;
@@ -739,6 +843,7 @@ extern "C" int gl_export_tree(gl_ctx *c, const gl_tree_layout *lay, void *nodes_
 {
   cudaSetDevice(c->device);
   if(!c->tree_valid) return c->fail("gl_export_tree: no tree (call gl_force_treebuild or gl_gravity_tree first)");
+  if(c->ncell > 0 || (c->comm && c->comm->world > 1)) return c->fail("gl_export_tree: single rank only (the reference inserts pseudo-particles here, forcetree.c:439)");
   const long long n = c->n, m = c->nnodes;
   if(n > MaxPart) return c->fail("gl_export_tree: more particles than MaxPart");
   if(m > max_nodes) return c->fail("gl_export_tree: more cells than MaxNodes (the reference would retry with a larger TreeAllocFactor, forcetree.c:71-91)");

@@ -208,6 +208,27 @@ class ForcePath:
     def hydro_force_nocopy(self):
         self._chk(self._lib.gl_hydro_force(self._ctx))
 
+    # -- multi-rank mode (include/gl_b200.h "multi-rank mode") ---------------------------------
+    def comm_init(self, rank, world, unique_id):
+        """NCCL communicator inside the library; unique_id = the 128 bytes of gl_comm_unique_id(), broadcast by the caller."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._chk(self._lib.gl_comm_init(self._ctx, int(rank), int(world), C.cast(buf, C.c_void_p)))
+
+    def comm_init_local(self, rank, group):
+        """Attach to an in-process group (gl_comm_local_group_create): several contexts of one process as ranks."""
+        self._chk(self._lib.gl_comm_init_local(self._ctx, int(rank), group))
+
+    def comm_set_options(self, want_gravity=True, search_padding=1.25):
+        self._chk(self._lib.gl_comm_set_options(self._ctx, 1 if want_gravity else 0, float(search_padding)))
+
+    def comm_finalize(self):
+        self._chk(self._lib.gl_comm_finalize(self._ctx))
+
+    def let_stats(self):
+        st = L.GLLetStats()
+        self._chk(self._lib.gl_get_let_stats(self._ctx, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in L.GLLetStats._fields_}
+
     def stats(self):
         s = L.GLStats()
         self._chk(self._lib.gl_get_stats(self._ctx, C.byref(s)))

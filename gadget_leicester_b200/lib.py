@@ -42,7 +42,14 @@ class GLStats(C.Structure):
         "ms_keys_sort", "ms_treebuild", "ms_moments", "ms_gravity_walk", "ms_density", "ms_hmax", "ms_hydro",
         "ms_h2d", "ms_d2h", "ms_potential")] + [(k, C.c_longlong) for k in (
             "interactions", "density_targets", "density_passes_max", "hydro_targets", "numnodes", "numentries",
-            "density_fat_targets", "kernel_launches", "density_pairs", "density_target_passes", "hydro_pairs")]
+            "density_fat_targets", "kernel_launches", "density_pairs", "density_target_passes", "hydro_pairs",
+            "density_slowest_index", "density_slowest_passes")]
+
+
+class GLLetStats(C.Structure):
+    _fields_ = [(k, C.c_longlong) for k in ("own_particles", "exported_cells", "exported_particles", "imported_cells",
+                                            "imported_particles", "builds", "violations")] + [("full", C.c_int)] + \
+               [(k, C.c_double) for k in ("ms_own_tree", "ms_select", "ms_exchange", "ms_sph_exchange")]
 
 
 class GLGadgetLayout(C.Structure):
@@ -110,6 +117,8 @@ EXPORTS = [
     "gl_get_stats", "gl_reset_launch_count", "gl_gadget_bind", "gl_gadget_pull", "gl_gadget_push", "gl_gadget_compute_accelerations",
     "gl_gadget_pack_segment", "gl_gadget_push_segment_async", "gl_gadget_push_wait", "gl_export_tree", "gl_gadget_drift", "gl_gadget_reorder",
     "gl_snapshot_write", "gl_snapshot_read", "gl_snapshot_read_header", "gl_gadget_advance_and_find_timesteps", "gl_gadget_drift_list", "gl_gadget_peano_hilbert_order", "gl_domain_top_tree", "gl_gadget_domain_keys", "gl_gadget_costfactors", "gl_domain_split",
+    "gl_comm_unique_id", "gl_comm_init", "gl_comm_local_group_create", "gl_comm_local_group_destroy", "gl_comm_init_local",
+    "gl_comm_finalize", "gl_comm_set_options", "gl_get_let_stats",
 ]
 
 _lib = None
@@ -165,6 +174,16 @@ def load_library():
     lib.gl_get_hydro.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.gl_get_pair_counts.argtypes = [vp, vp, vp, C.c_int]
     lib.gl_get_stats.argtypes = [vp, C.POINTER(GLStats)]
+    lib.gl_get_let_stats.argtypes = [vp, C.POINTER(GLLetStats)]
+    lib.gl_comm_unique_id.argtypes = [vp]
+    lib.gl_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.gl_comm_local_group_create.argtypes = [C.c_int]
+    lib.gl_comm_local_group_create.restype = vp
+    lib.gl_comm_local_group_destroy.argtypes = [vp]
+    lib.gl_comm_local_group_destroy.restype = None
+    lib.gl_comm_init_local.argtypes = [vp, C.c_int, vp]
+    lib.gl_comm_finalize.argtypes = [vp]
+    lib.gl_comm_set_options.argtypes = [vp, C.c_int, C.c_double]
     lib.gl_reset_launch_count.argtypes = [vp]
     lib.gl_reset_launch_count.restype = None
     lib.gl_gadget_bind.argtypes = [vp, C.POINTER(GLGadgetLayout)]

@@ -382,6 +382,89 @@ class DistributedForcePath:
         self.fp.close()
 
 
+class LetForcePath(DistributedForcePath):
+    """The multi-rank force path with the exchange INSIDE the library (include/gl_b200.h "multi-rank mode",
+    csrc/gl_let.cu): every rank loads its own Peano-Hilbert segment, gl_comm_init attaches an NCCL communicator, and one
+    gl_compute_accelerations call per step does the rest - own tree, locally-essential exchange over NVLink, merged
+    tree, gravity, density, SphP exchange, hydro.  No Python between the phases.
+
+    torch.distributed is used once, to broadcast the 128-byte NCCL id (the reference would MPI_Bcast it)."""
+
+    def __init__(self, params, rank=0, world=1, device=0, group=None):
+        super().__init__(params, rank=rank, world=world, device=device, group=group)
+        self._comm = False
+
+    def _attach(self):
+        if self._comm or self.world == 1:
+            return
+        lib = self.fp._lib
+        idt = torch.zeros(128, dtype=torch.uint8, device=self.device)
+        if self.rank == 0:
+            buf = C.create_string_buffer(128)
+            if lib.gl_comm_unique_id(C.cast(buf, C.c_void_p)) != 0:
+                raise L.GLError("gl_comm_unique_id failed")
+            idt.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(idt, src=0, group=self.group)
+        self.fp.comm_init(self.rank, self.world, bytes(idt.cpu().numpy().tobytes()))
+        self._comm = True
+
+    def _adopt(self, n, ngas, order, ranges, take):
+        order = super()._adopt(n, ngas, order, ranges, take)
+        self._attach()
+        k = self.hi - self.lo
+        f64 = lambda *s: torch.zeros(*s, dtype=torch.float64, device=self.device)
+        # results of the own particles only, indexed like the own segment
+        self.own_res = dict(acc=f64(k, 3), oldacc=f64(k), gravcost=torch.zeros(k, dtype=torch.float32, device=self.device))
+        if ngas > 0:
+            self.own_res.update(hsml=f64(k), numngb=f64(k), density=f64(k), dhsml=f64(k), divvel=f64(k), curlvel=f64(k),
+                                pressure=f64(k), hacc=f64(k, 3), dtentr=f64(k), maxsig=f64(k))
+        self._load_own()
+        return order
+
+    def _load_own(self):
+        """gl_load_particles of the own segment (device pointers into the packed block the base class keeps)."""
+        k = self.hi - self.lo
+        self._sync_lib()
+        self.fp.load_device(k, [self.own[f].data_ptr() for f in STATE_FIELDS])
+
+    def compute_accelerations(self, sph=True, gravity=True):
+        import time
+        self.t = {}
+        t0 = time.perf_counter()
+        lib, ctx = self.fp._lib, self.fp.ctx
+        if self.world > 1 and not gravity:
+            self.fp.comm_set_options(False, 1.3)
+        if gravity and sph and self.ngas > 0:
+            self.fp._chk(lib.gl_compute_accelerations(ctx, 0))
+            self.fp._relative_criterion_engaged()
+        else:
+            if gravity:
+                self.fp.gravity_tree_nocopy()
+            else:
+                self.fp.force_treebuild()
+            if sph and self.ngas > 0:
+                self.fp.density_nocopy()
+                self.fp.force_update_hmax()
+                self.fp.hydro_force_nocopy()
+        self._tick("compute_accelerations", t0)
+
+    def fetch(self):
+        """Copy the own results into self.own_res (device) and keep Hsml / OldAcc of the own block current."""
+        lib, ctx = self.fp._lib, self.fp.ctx
+        r = self.own_res
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self.fp._chk(lib.gl_get_gravity(ctx, p(r["acc"]), p(r["oldacc"]), p(r["gravcost"]), 1))
+        if self.ngas > 0 and "hsml" in r:
+            self.fp._chk(lib.gl_get_density(ctx, p(r["hsml"]), p(r["numngb"]), p(r["density"]), p(r["dhsml"]), p(r["divvel"]),
+                                            p(r["curlvel"]), p(r["pressure"]), None, None, None, 1))
+            self.fp._chk(lib.gl_get_hydro(ctx, p(r["hacc"]), p(r["dtentr"]), p(r["maxsig"]), 1))
+        self._sync_lib()
+        return r
+
+    def rebalance(self, timed=False):
+        raise NotImplementedError("LetForcePath keeps the decomposition it was given (bench.py re-splits through DistributedForcePath)")
+
+
 class DistributedDropIn:
     """compute_accelerations() (accel.c:27, force part) on THIS RANK'S OWN host P[] / SphP[] - its Peano-Hilbert
     segment, the way every MPI rank of the reference holds its local particles - at any GPU count:

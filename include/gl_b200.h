@@ -163,9 +163,44 @@ typedef struct gl_stats
   long long density_pairs;	/* sum over targets of the integer neighbour count (r2 < h_i^2) of their final pass */
   long long density_target_passes;	/* number of (target, pass) evaluations of the last gl_density (>= density_targets) */
   long long hydro_pairs;	/* sum over targets of the pair count (r2 < h_i^2 or r2 < h_j^2, r > 0) */
+  long long density_slowest_index, density_slowest_passes;	/* P[] index of the target with the most Hsml passes in the last gl_density (-1: all took one) */
 } gl_stats;
 int gl_get_stats(gl_ctx * ctx, gl_stats * out);
 void gl_reset_launch_count(gl_ctx * ctx);
+
+/* ---- multi-rank mode: one rank <-> one GPU, NCCL inside the library -----------------------------------------------
+ * Replaces the reference's MPI choreography of the force path: the pseudo-particle exchange of the tree build
+ * (force_exchange_pseudodata forcetree.c:879-1016, force_treeupdate_pseudos :1025, force_insert_pseudo_particles :439)
+ * and the export/import loops of gravity_tree() (gravtree.c:175-347), density() (density.c:193-342), hydro_force()
+ * (hydra.c:274-520) and force_update_hmax() (forcetree.c:1722-1747).  With a communicator attached
+ *   - gl_load_particles() loads the rank's OWN particles (any decomposition; contiguous Peano-Hilbert key ranges
+ *     as domain.c:1075 produces them prune best), in the caller's order (P[] is Peano-Hilbert ordered, peano.c:25);
+ *   - the tree build inside gl_gravity_tree / gl_force_treebuild / gl_density all-reduces the domain extent
+ *     (domain.c:1996), exchanges the locally-essential tree (csrc/gl_let.cu) and builds the merged tree; every rank
+ *     must make the same sequence of calls (they are collective, like the reference's);
+ *   - gl_force_update_hmax() first exchanges Hsml, the SphP fields hydro reads and the cells' hmax;
+ *   - results (gl_get_*) cover the own particles [0, n).  Interaction counts, neighbour sets and sums are those of a
+ *     single-rank run on the union of all ranks' particles.
+ * The 128-byte id comes from gl_comm_unique_id() on one rank and is broadcast by the CALLER (the reference's
+ * MPI_Bcast; torch.distributed in bench.py): the library opens no rendezvous of its own. */
+int gl_comm_unique_id(void *id128);
+int gl_comm_init(gl_ctx * ctx, int rank, int world, const void *id128);
+/* several contexts of ONE process as ranks (one host thread each): how the multi-rank path is tested on a single GPU */
+void *gl_comm_local_group_create(int world);
+void gl_comm_local_group_destroy(void *group);
+int gl_comm_init_local(gl_ctx * ctx, int rank, void *group);
+int gl_comm_finalize(gl_ctx * ctx);
+/* want_gravity = 0: the export test leaves out the gravity opening criteria (a run that only calls density / hydro);
+ * search_padding (>= 1, default 1.3): factor on the search radii in the export test (room for Hsml to grow) */
+int gl_comm_set_options(gl_ctx * ctx, int want_gravity, double search_padding);
+typedef struct gl_let_stats
+{
+  long long own_particles, exported_cells, exported_particles, imported_cells, imported_particles;
+  long long builds, violations;	/* multi-rank builds since gl_create; phases repeated with a full export */
+  int full;			/* the last build exported every particle */
+  double ms_own_tree, ms_select, ms_exchange, ms_sph_exchange;
+} gl_let_stats;
+int gl_get_let_stats(gl_ctx * ctx, gl_let_stats * out);
 
 /* ---- drop-in layer for the reference's AoS arrays ------------------------------------------------- */
 /* Byte offsets inside struct particle_data / struct sph_particle_data; the glue fills them with

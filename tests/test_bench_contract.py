@@ -31,7 +31,10 @@ def test_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["unit"] == "interactions/s" and d["value"] > 0 and d["ms_per_step"] > 0
-    assert "workload" in d["config"] and "4000" in d["config"]["workload"]
+    # same workload string as our arm's line (BASELINE config 0), the bounded sample is named beside it
+    assert d["config"]["workload"].startswith("BASELINE config 0") and "1600000 gas" in d["config"]["workload"]
+    assert "4000" in d["config"]["sample"] and d["config"]["particles_per_instance"] == 4002
+    assert d["steps"] == 1 and d["warmup"] == 1       # --steps / --warmup are honoured as given
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == dict(value=d["value"], unit=d["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0)
