@@ -629,7 +629,7 @@ int gl_split_gas_targets(gl_ctx *c, long long split, long long *n_lo)
 // ---------------------------------------------------------------- force entry points ----
 // Multi-rank mode: a phase that met a cut cell (GL_ERR_LET_VIOLATION, see gl_let.cu) is repeated by ALL ranks with a
 // full export - the decision is collective (one 8-byte all-gather per phase), because the rebuild is.
-static int run_phase(gl_ctx *c, int (*fn)(gl_ctx *), const char *name, bool gravity)
+static int run_phase(gl_ctx *c, int (*fn)(gl_ctx *), const char *name, bool gravity, bool restore_hsml = false)
 {
   if(!(c->comm && c->comm->world > 1)) return fn(c);
   for(int attempt = 0; attempt < 2; attempt++)
@@ -649,7 +649,8 @@ static int run_phase(gl_ctx *c, int (*fn)(gl_ctx *), const char *name, bool grav
       if(!gravity)
 	{
 	  c->let_need_sph_exchange = true;
-	  if(c->let_hsml_backup.cap >= (size_t) c->n_own && c->n_own > 0)
+	  // density only: the repeated Hsml iteration starts from the values the first attempt started from
+	  if(restore_hsml && c->let_hsml_backup.cap >= (size_t) c->n_own && c->n_own > 0)
 	    GL_CUDA(c, cudaMemcpyAsync(c->in_hsml.p, c->let_hsml_backup.p, c->n_own * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
 	  if(glt_build(c)) return 1;
 	}
@@ -702,7 +703,7 @@ extern "C" int gl_get_potential(gl_ctx *c, double *potential, int where)
 extern "C" int gl_density(gl_ctx *c)
 {
   cudaSetDevice(c->device);
-  return run_phase(c, density_phase, "density", false);
+  return run_phase(c, density_phase, "density", false, true);
 }
 
 extern "C" int gl_force_update_hmax(gl_ctx *c)

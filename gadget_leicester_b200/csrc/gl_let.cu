@@ -30,6 +30,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <climits>
+#include <chrono>
 
 gl_dparams gl_make_dparams(const gl_ctx *c);
 
@@ -89,13 +90,9 @@ __global__ void k_let_boxes(long long n_own, const long long *__restrict__ bound
 			    const double *__restrict__ oldacc, const double *__restrict__ hsml, const int *__restrict__ type,
 			    double errtolforceacc, double fs, double *__restrict__ boxes)
 {
-  const int b = blockIdx.x;
-  long long i0 = 0, i1 = n_own;
-  if(b > 0)
-    {
-      i0 = bounds[b - 1];
-      i1 = bounds[b];
-    }
+  const int b = blockIdx.x + 1;	// box 0 (the whole rank) is the union of the others: k_let_box_union
+  const long long i0 = bounds[b - 1], i1 = bounds[b];
+  (void) n_own;
   // v[0..2] min pos, [3..5] max pos, [6] min aold, [7] max search radius, [8..10] min (pos - fs h), [11..13] max (pos + fs h)
   double v[GL_LET_BOXDBL];
   for(int k = 0; k < 3; k++)
@@ -149,6 +146,22 @@ __global__ void k_let_boxes(long long n_own, const long long *__restrict__ bound
     }
 }
 
+__global__ void k_let_box_union(double *__restrict__ boxes)
+{
+  const int k = threadIdx.x;
+  if(k >= GL_LET_BOXDBL) return;
+  const bool ismin = k < 3 || k == 6 || (k >= 8 && k < 11);
+  double v = ismin ? 1e300 : -1e300;
+  if(k == 7) v = -1.0;
+  for(int b = 1; b <= GL_LET_BOXES; b++)
+    {
+      const double *o = boxes + GL_LET_HDR + (long long) b * GL_LET_BOXDBL;
+      if(o[0] > o[3]) continue;	// empty stretch
+      v = ismin ? fmin(v, o[k]) : fmax(v, o[k]);
+    }
+  boxes[GL_LET_HDR + k] = v;
+}
+
 __global__ void k_let_count_gas(long long n, const int *__restrict__ type, int *__restrict__ count)
 {
   const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
@@ -171,13 +184,9 @@ __device__ __forceinline__ bool box_may_need(const double *__restrict__ box, con
   if(box[0] > box[3]) return false;	// empty stretch
   if(P.want_grav)
     {
-      double d2 = 0;
-      const double sx[3] = { sm.x, sm.y, sm.z };
-      for(int k = 0; k < 3; k++)
-	{
-	  const double d = fmax(fmax(box[k] - sx[k], sx[k] - box[3 + k]), 0.0);
-	  d2 += d * d;
-	}
+      const double d0 = fmax(fmax(box[0] - sm.x, sm.x - box[3]), 0.0), d1 = fmax(fmax(box[1] - sm.y, sm.y - box[4]), 0.0),
+	d2z = fmax(fmax(box[2] - sm.z, sm.z - box[5]), 0.0);
+      const double d2 = d0 * d0 + d1 * d1 + d2z * d2z;
       const double len2 = cl.w * cl.w;
       if(P.bh)
 	{
@@ -186,10 +195,10 @@ __device__ __forceinline__ bool box_may_need(const double *__restrict__ box, con
       else
 	{
 	  if(sm.w * len2 >= d2 * d2 * box[6] * (1 - 1e-6)) return true;	// forcetree.c:2085 with the smallest aold of the box
-	  const double cc[3] = { cl.x, cl.y, cl.z };
-	  bool inside = true;	// forcetree.c:2094-2105: some target position may lie in the 0.6 len cube
-	  for(int k = 0; k < 3; k++)
-	    if(box[k] >= cc[k] + 0.6001 * cl.w || box[3 + k] <= cc[k] - 0.6001 * cl.w) inside = false;
+	  // forcetree.c:2094-2105: some target position may lie in the 0.6 len cube
+	  const double q = 0.6001 * cl.w;
+	  const bool inside = !(box[0] >= cl.x + q || box[3] <= cl.x - q || box[1] >= cl.y + q || box[4] <= cl.y - q ||
+				box[2] >= cl.z + q || box[5] <= cl.z - q);
 	  if(inside) return true;
 	}
       if(ax.x > 0 && d2 <= ax.x * ax.x * (1 + 1e-6)) return true;	// forcetree.c:2124-2137 softening guard
@@ -197,38 +206,40 @@ __device__ __forceinline__ bool box_may_need(const double *__restrict__ box, con
   if(P.want_sph && ax.y > 0 && box[7] >= 0)
     {
       // gas below the cell and SPH targets in the box
-      const double cc[3] = { cl.x, cl.y, cl.z };
       const double half = 0.5 * cl.w * 1.000001;
       // (1) some target's search sphere r < h_i (ngb.c:270-289; hydra.c:1266 first half) may reach the cell: the cell
       // meets the bounding box of the spheres (radii padded by fs, formed per target in k_let_boxes)
-      bool meets = true;
-      for(int k = 0; k < 3; k++)
-	if(box[8 + k] > cc[k] + half || box[11 + k] < cc[k] - half) meets = false;
+      const bool meets = !(box[8] > cl.x + half || box[11] < cl.x - half || box[9] > cl.y + half || box[12] < cl.y - half ||
+			   box[10] > cl.z + half || box[13] < cl.z - half);
       if(meets) return true;
       // (2) some particle of the cell may reach a target with ITS radius, r < h_j <= hmax (ngb.c:136-152)
       const double R = P.fs * ax.y;
-      double e2 = 0;
-      for(int k = 0; k < 3; k++)
-	{
-	  const double e = fmax(fmax(box[k] - (cc[k] + half), (cc[k] - half) - box[3 + k]), 0.0);
-	  e2 += e * e;
-	}
-      if(e2 <= R * R) return true;
+      const double e0 = fmax(fmax(box[0] - (cl.x + half), (cl.x - half) - box[3]), 0.0),
+	e1 = fmax(fmax(box[1] - (cl.y + half), (cl.y - half) - box[4]), 0.0),
+	e2z = fmax(fmax(box[2] - (cl.z + half), (cl.z - half) - box[5]), 0.0);
+      if(e0 * e0 + e1 * e1 + e2z * e2z <= R * R) return true;
     }
   return false;
 }
 
-// one level of the top-down pass, thread = (cell of that level, destination rank)
-// state: 0 = descend (children are looked at), 1 = exported as a cut cell, 2 = below an exported cell
-__global__ void k_let_select_level(int count, const int *__restrict__ lev_list, long long m, const int *__restrict__ n_parent,
-				   const double4 *__restrict__ n_sm, const double4 *__restrict__ n_cl, const double4 *__restrict__ n_aux,
-				   const unsigned char *__restrict__ complete, const double *__restrict__ box_all,
-				   unsigned char *__restrict__ state, LetSel P)
+// one level of the top-down pass: blockIdx.y = destination rank (its target boxes are staged in shared memory),
+// thread = cell of that level.  state: 0 = descend (children are looked at), 1 = exported as a cut cell,
+// 2 = below an exported cell
+__global__ void __launch_bounds__(128)
+k_let_select_level(int count, const int *__restrict__ lev_list, long long m, const int *__restrict__ n_parent,
+		   const double4 *__restrict__ n_sm, const double4 *__restrict__ n_cl, const double4 *__restrict__ n_aux,
+		   const unsigned char *__restrict__ complete, const double *__restrict__ box_all,
+		   unsigned char *__restrict__ state, LetSel P)
 {
-  const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(t >= (long long) count * P.world) return;
-  const int d = (int) (t / count), id = lev_list[t % count];
+  __shared__ double sbox[(GL_LET_BOXES + 1) * GL_LET_BOXDBL];
+  const int d = blockIdx.y;
   if(d == P.me) return;
+  const double *rb = box_all + (long long) d * (GL_LET_HDR + (GL_LET_BOXES + 1) * GL_LET_BOXDBL) + GL_LET_HDR;
+  for(int k = threadIdx.x; k < (GL_LET_BOXES + 1) * GL_LET_BOXDBL; k += blockDim.x) sbox[k] = rb[k];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= count) return;
+  const int id = lev_list[t];
   unsigned char *st = state + (long long) d * m;
   const int par = n_parent[id];
   if(par >= 0 && st[par] != 0)
@@ -240,12 +251,11 @@ __global__ void k_let_select_level(int count, const int *__restrict__ lev_list, 
   if(!P.full && complete[id])
     {
       const double4 sm = n_sm[id], cl = n_cl[id], ax = n_aux[id];
-      const double *rb = box_all + (long long) d * (GL_LET_HDR + (GL_LET_BOXES + 1) * GL_LET_BOXDBL) + GL_LET_HDR;
-      bool need = box_may_need(rb, sm, cl, ax, P);	// the whole rank first: far ranks are settled by one test
+      bool need = box_may_need(sbox, sm, cl, ax, P);	// the whole rank first: far ranks are settled by one test
       if(need)
 	{
 	  need = false;
-	  for(int b = 1; b <= GL_LET_BOXES && !need; b++) need = box_may_need(rb + b * GL_LET_BOXDBL, sm, cl, ax, P);
+	  for(int b = 1; b <= GL_LET_BOXES && !need; b++) need = box_may_need(sbox + b * GL_LET_BOXDBL, sm, cl, ax, P);
 	}
       res = need ? 0 : 1;
     }
@@ -440,6 +450,19 @@ int gll_distributed_build(gl_ctx *c)
   if(c->n_own <= 0) return c->fail("multi-rank build: no own particles loaded (gl_load_particles)");
   cudaEvent_t e0 = c->ev[4], e1 = c->ev[5], e2 = c->ev[6], e3 = c->ev[7];
   cudaEventRecord(e0, c->stream);
+  // GL_DEBUG_LET_TIME: wall-clock of every sub-step (with a device synchronisation in front of each stamp)
+  static const bool dbgt = getenv("GL_DEBUG_LET_TIME") != nullptr;
+  auto tnow = [&]() {
+    cudaStreamSynchronize(c->stream);
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  double tl = dbgt ? tnow() : 0;
+  auto stamp = [&](const char *what) {
+    if(!dbgt) return;
+    const double t = tnow();
+    if(me == 0) fprintf(stderr, "[gl let] %-28s %8.3f ms\n", what, t - tl);
+    tl = t;
+  };
   // ---- 1. own particles only, global cube (domain.c:1996-1997: MPI_Allreduce of the extent) ----
   c->n = c->n_own;
   c->ncell = 0;
@@ -460,6 +483,7 @@ int gll_distributed_build(gl_ctx *c)
 	}
     if(!c->domain_imposed) glk_set_domain_minmax(c, lo, hi);
   }
+  stamp("extent all-reduce");
   // ---- 2. the tree of the own particles (no walk records) ----
   const bool keep_ordered = c->tgt_ordered;
   const long long keep_tgt = c->n_tgt_in;
@@ -470,6 +494,7 @@ int gll_distributed_build(gl_ctx *c)
   c->n_tgt_in = keep_tgt;
   const long long n = c->n_own, m = c->nnodes, per = m + n;
   cudaEventRecord(e1, c->stream);
+  stamp("own tree");
   // ---- 3. target description of every rank ----
   const size_t blk = GL_LET_HDR + (size_t) (GL_LET_BOXES + 1) * GL_LET_BOXDBL;
   GL_CUDA(c, L->box_own.ensure(blk));
@@ -499,12 +524,14 @@ int gll_distributed_build(gl_ctx *c)
     hbnd[GL_LET_BOXES] = n;
     GL_CUDA(c, cudaMemcpyAsync(bdev, hbnd, sizeof(hbnd), cudaMemcpyHostToDevice, c->stream));
     if(glk_ph_chunk_hulls(c, bdev, GL_LET_BOXES, (unsigned long long *) L->box_own.p)) return 1;
-    k_let_boxes<<<GL_LET_BOXES + 1, 256, 0, c->stream>>>(n, bdev, c->in_pos.p, c->in_oldacc.p, c->in_hsml.p, c->in_type.p,
-							  c->par.ErrTolForceAcc, L->fs, L->box_own.p);
-    GL_LAUNCH_COUNT(c);
+    k_let_boxes<<<GL_LET_BOXES, 256, 0, c->stream>>>(n, bdev, c->in_pos.p, c->in_oldacc.p, c->in_hsml.p, c->in_type.p,
+						      c->par.ErrTolForceAcc, L->fs, L->box_own.p);
+    k_let_box_union<<<1, 32, 0, c->stream>>>(L->box_own.p);
+    c->kernel_launches += 2;
     GL_CUDA(c, cudaStreamSynchronize(c->stream));	// hbnd is a stack array
   }
   GL_COMM(c, cm->allgather(L->box_own.p, L->box_all.p, blk * sizeof(double), c->stream));
+  stamp("boxes + hulls + all-gather");
   // ---- 4. what each other rank needs from here ----
   GL_CUDA(c, L->complete.ensure((size_t) m + 1));
   GL_CUDA(c, L->state.ensure((size_t) W * (m + 1)));
@@ -512,6 +539,7 @@ int gll_distributed_build(gl_ctx *c)
   if(glk_node_complete(c, (const unsigned long long *) L->box_all.p, W, GL_LET_BOXES, (long long) blk, me, L->complete.p)) return 1;
   LetSel P;
   P.world = W; P.me = me; P.bh = c->par.ErrTolTheta != 0; P.want_grav = c->let_want_grav ? 1 : 0; P.full = L->full ? 1 : 0;
+  if(getenv("GL_DEBUG_LET_FULL")) P.full = 1;
   P.theta = c->par.ErrTolTheta; P.fs = L->fs;
   P.want_sph = getenv("GL_DEBUG_LET_NOSPH") ? 0 : 1;	// (debug switches: results are then wrong or violations follow)
   if(getenv("GL_DEBUG_LET_NOGRAV")) P.want_grav = 0;
@@ -519,11 +547,12 @@ int gll_distributed_build(gl_ctx *c)
     {
       const int cnt = c->lev_start[lev + 1] - c->lev_start[lev];
       if(cnt <= 0) continue;
-      k_let_select_level<<<gl_grid((long long) cnt * W, 128), 128, 0, c->stream>>>(cnt, c->lev_list.p + c->lev_start[lev], m, c->n_parent.p,
-										   c->n_sm.p, c->n_cl.p, c->n_aux.p, L->complete.p,
-										   L->box_all.p, L->state.p, P);
+      k_let_select_level<<<dim3(gl_grid(cnt, 128), W), 128, 0, c->stream>>>(cnt, c->lev_list.p + c->lev_start[lev], m, c->n_parent.p,
+									    c->n_sm.p, c->n_cl.p, c->n_aux.p, L->complete.p,
+									    L->box_all.p, L->state.p, P);
       GL_LAUNCH_COUNT(c);
     }
+  stamp("complete + level passes");
   k_let_flags<<<gl_grid(per * W, 256), 256, 0, c->stream>>>(m, n, W, me, L->state.p, c->p_father.p, L->xflag.p);
   GL_LAUNCH_COUNT(c);
   if(per * W >= (1ll << 31)) return c->fail("multi-rank build: selection index space exceeds 2^31");
@@ -576,6 +605,7 @@ int gll_distributed_build(gl_ctx *c)
       GL_LAUNCH_COUNT(c);
     }
   cudaEventRecord(e2, c->stream);
+  stamp("flags + compaction + pack");
   // ---- 5. the exchange ----
   if(exchange_counts(c, L, mine, all)) return 1;
   L->rc_off.assign(W, 0); L->rc_cnt.assign(W, 0); L->rp_off.assign(W, 0); L->rp_cnt.assign(W, 0);
@@ -608,6 +638,7 @@ int gll_distributed_build(gl_ctx *c)
       }
     GL_COMM(c, cm->alltoallv(L->send_p.p, so.data(), sc.data(), L->recv_p.p, ro.data(), rc.data(), c->stream));
   }
+  stamp("counts + two all-to-alls");
   // ---- 6. imported particles behind the own ones, cut cells as extra items ----
   const size_t nn = (size_t) (n + ip);
   GL_CUDA(c, c->in_pos.ensure_keep(3 * nn)); GL_CUDA(c, c->in_vel.ensure_keep(3 * nn)); GL_CUDA(c, c->in_mass.ensure_keep(nn));
@@ -644,9 +675,11 @@ int gll_distributed_build(gl_ctx *c)
   c->res_first = 0;
   c->res_count = n;
   cudaEventRecord(e3, c->stream);
+  stamp("unpack imports");
   // ---- 7. the merged tree ----
   if(c->n_tgt_in >= 0) c->tgt_ordered = true;	// a caller's list is taken as it comes (results do not depend on the order)
   if(glt_build_local(c, true)) return 1;
+  stamp("merged tree");
   L->built_bh = P.bh != 0;
   L->built_grav = P.want_grav != 0;
   float t01, t12, t23;

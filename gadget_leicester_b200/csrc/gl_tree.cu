@@ -739,6 +739,16 @@ int glt_launch_update_hmax(gl_ctx *c)
   return 0;
 }
 
+__global__ void k_debug_hsml_consistency(long long nit, long long n, const int *__restrict__ perm, const int *__restrict__ s_type,
+					 const double4 *__restrict__ s_vh, const double *__restrict__ in_hsml, int *__restrict__ bad)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= nit) return;
+  const int j = perm[i];
+  if(j >= n || s_type[i] != 0) return;
+  if(s_vh[i].w != in_hsml[j]) atomicAdd(bad, 1);
+}
+
 int glt_update_hmax(gl_ctx *c)
 {
   if(!c->tree_valid) return c->fail("force_update_hmax: no tree");
@@ -746,6 +756,16 @@ int glt_update_hmax(gl_ctx *c)
   if(c->comm && c->comm->world > 1)
     if(gll_exchange_sph_state(c)) return 1;	// multi-rank: Hsml + SphP of the imported particles, hmax of the cut cells
   if(glt_launch_update_hmax(c)) return 1;
+  if(getenv("GL_DEBUG_LET"))
+    {
+      int *bad = c->scan_tmp_i.p + 63, hb = 0;
+      cudaMemsetAsync(bad, 0, sizeof(int), c->stream);
+      k_debug_hsml_consistency<<<gl_grid(c->nit, 256), 256, 0, c->stream>>>(c->nit, c->n, c->perm.p, c->s_type.p, c->s_vh.p, c->in_hsml.p, bad);
+      cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+      cudaStreamSynchronize(c->stream);
+      fprintf(stderr, "[gl] rank %d: force_update_hmax: %d gas particles whose tree-order Hsml differs from the input-order Hsml (n %lld, own %lld)\n",
+	      c->comm ? c->comm->rank : 0, hb, c->n, c->n_own);
+    }
   cudaEventRecord(c->ev[1], c->stream);
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   float ms;

@@ -173,6 +173,15 @@ def main():
                 g = seg[b]
                 print("   %s mismatch: particle %d type %d pairs %d vs %d  Hsml %.17g vs %.17g" % (
                     ht, g, ps["type"][g], mine[b], ref[ht]["HydroPairs"][g], hs[b], ref[dt]["Hsml"][g]))
+            if len(badi):
+                # who is right?  brute force over all gas particles with the single-context Hsml (hydra.c:1266)
+                hall = ref[dt]["Hsml"]
+                gasm = (ps["type"] == 0) & (ps["mass"] != 0)
+                for b in badi[:5]:
+                    g = seg[b]
+                    d2 = ((ps["pos"][gasm] - ps["pos"][g]) ** 2).sum(axis=1)
+                    cnt = int((((d2 < hall[g] ** 2) | (d2 < hall[gasm] ** 2)) & (d2 > 0)).sum())
+                    print("      brute force for particle %d: %d pairs" % (g, cnt))
             dh = np.abs(hs - ref[dt]["Hsml"][seg]) / ref[dt]["Hsml"][seg]
             print("   %s: particles whose Hsml differs: %d (max rel %.3g)" % (dt, int((dh > 0).sum()), dh.max()))
     if sph:

@@ -1,0 +1,91 @@
+"""GPU suite: the multi-rank force path (include/gl_b200.h "multi-rank mode", csrc/gl_let.cu) against a single-context
+run of the union of all ranks' particles - through the C ABI, several contexts of this process as ranks (in-process
+group: one GPU is enough), plus the NCCL transport on two GPUs when the box has them.
+
+What must hold (north_star: "results must match ... on the same particles, tree and opening criterion"):
+  * P.GravCost of every rank's own particles, Barnes-Hut and relative criterion: bit-exact, and GravAccel BITWISE equal
+    (the merged locally-essential tree is the global tree wherever a target can look, and the walk is the same walk);
+  * density and hydro pair counts: bit-exact; Hsml, Density, HydroAccel, DtEntropy to 1e-12 (FP64 sums formed in a
+    different candidate order);
+  * a cut cell that a walk wants to open / a search sphere reaches is detected and the phase is repeated with a full
+    export on all ranks (cold-start density of the disc: the sinks' Hsml grows a thousandfold).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(case, n, world):
+    import let_check as LC
+    from gadget_leicester_b200.gadget import ForcePath
+    ps, par = LC.make_case(case, n)
+    ngas = int((ps["type"] == 0).sum())
+    sph = ngas > 0
+    one = ForcePath(par)
+    one.load(ps)
+    order = one.peano_hilbert_order(ngas)
+    one.load(ps)
+
+    def reload_one(out):
+        one.load(dict(ps, hsml=out["d"]["Hsml"].copy(), oldacc=out["g2"]["OldAcc"].copy()))
+    ref = LC.sequence(one, sph, reload_one)
+    one.close()
+    res, stats, _ = LC.run_world(ps, par, order, world, sph)
+    return LC.compare(ref, res, sph, ps["type"]), stats, ps
+
+
+@pytest.mark.parametrize("case,n,world", [("plummer", 30000, 2), ("disc", 40000, 4), ("evrard", 60000, 3), ("cube", 50000, 8)])
+def test_ranks_reproduce_the_single_context_run(case, n, world):
+    rep, stats, ps = _run(case, n, world)
+    for k, v in rep.items():
+        if k.endswith("mismatches"):
+            assert v == 0, "%s: %s = %d" % (case, k, v)          # counts bit-exact, accelerations bitwise equal
+        elif k.endswith("max rel") or k.endswith("abs/scale"):
+            assert v <= 1e-12, "%s: %s = %g" % (case, k, v)
+    a, b = rep["interactions"]
+    assert a == b
+    assert sum(s["own_particles"] for s in stats) == ps["pos"].shape[0]
+    if case in ("evrard", "cube", "plummer"):
+        # the export is a pruned set, not a replication, and no phase had to be repeated
+        for s in stats:
+            assert s["violations"] == 0 and s["full"] == 0
+            assert s["imported_particles"] < 0.9 * (ps["pos"].shape[0] - s["own_particles"])
+            assert s["imported_cells"] > 0
+
+
+def test_cut_cell_violation_is_detected_and_repeated():
+    """Cold-start density of the disc: the two sinks start at Hsml = 5e-5 and end near 0.1 - far beyond the padding of
+    the export test.  Every rank must notice, all must repeat with a full export, and the results must still be exact."""
+    rep, stats, _ = _run("disc", 200000, 4)
+    assert all(s["violations"] >= 1 for s in stats)
+    assert len({s["violations"] for s in stats}) == 1               # the decision was collective
+    assert all(v == 0 for k, v in rep.items() if k.endswith("mismatches"))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "scripts", "let_nccl_check.py")), reason="driver script missing")
+def test_two_gpus_over_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (the in-process tests above cover the same path on one)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "scripts", "let_nccl_check.py"), "--n", "200000"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "IDENTICAL" in r.stdout
+
+
+def test_c_abi_two_ranks_from_cpp(tmp_path):
+    """tests/native/let_ranks.cpp: the same through the C ABI alone - what a reference-side binding does at NTask = 2."""
+    exe = str(tmp_path / "let_ranks")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "native", "let_ranks.cpp"), "-ldl", "-pthread"])
+    r = subprocess.run([exe, os.path.join(ROOT, "gadget_leicester_b200", "libgl_b200.so"), "40000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout and "mismatching particles 0" in r.stdout
