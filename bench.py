@@ -45,8 +45,17 @@ def peaks():
             p = json.load(f)
     except Exception:
         pass
-    return dict(hbm_gbs=p.get("hbm_gbs", 6650.0), sm_max_mhz=p.get("sm_max_mhz", 1965.0),
-                source="MEASURED_PEAKS.json" if p else "fallback (B200_PROFILING.md)")
+    out = dict(hbm_gbs=p.get("hbm_gbs", 6650.0), sm_max_mhz=p.get("sm_max_mhz", 1965.0),
+               source="MEASURED_PEAKS.json" if p else "fallback (B200_PROFILING.md)")
+    # non-tensor FMA peaks measured on this pool's B200 by scripts/probes/fma_peaks.cu (newest committed record)
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_fma_peaks.json"))):
+        try:
+            q = json.load(open(f))
+            out.update(fp32_tflops=float(q["fp32_fma_tflops"]), fp64_tflops=float(q["fp64_fma_tflops"]), fma_source=os.path.basename(f))
+        except Exception:
+            pass
+    return out
 
 
 def ncu_traffic(kernel):
@@ -586,8 +595,10 @@ def main():
     pk = peaks()
     own_gas = int((ps["type"][dfp.order[dfp.lo:dfp.hi]] == 0).sum())
     nsm = torch.cuda.get_device_properties(local).multi_processor_count
-    fp32_peak = nsm * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-    fp64_peak = nsm * 64 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12          # 64 DFMA lanes per SM on B200
+    fp32_peak = pk.get("fp32_tflops") or nsm * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    fp64_peak = pk.get("fp64_tflops") or nsm * 64 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12          # 64 DFMA lanes per SM on B200
+    peak_note = ("measured FFMA / DFMA peak, profiles/" + pk["fma_source"]) if pk.get("fma_source") else \
+        "SMs*128*2*sm_max_mhz (derived; no profiles/*_fma_peaks.json)"
     st = dfp.fp.stats()                                                 # pair / pass totals of the last step (this rank)
     t_w, t_d, t_h = phase["ms_gravity_walk"] * 1e-3, phase["ms_density"] * 1e-3, phase["ms_hydro"] * 1e-3
     tr = (lambda k: ncu_traffic(k) if world == 1 and not args.ngas and args.config == 0 else None)
@@ -595,8 +606,7 @@ def main():
     roofs = dict(
         gravity_walk=dict(kernel="k_gravity_walk", bound="fp32", achieved=ach, peak=fp32_peak, unit="TFLOP/s", frac=ach / fp32_peak,
                           traffic=tr("k_gravity_walk"),
-                          note="25 flop/interaction (SURVEY 8(d)) x %d interactions; peak = SMs*128*2*sm_max_mhz from %s"
-                               % (inter // args.steps, pk["source"])))
+                          note="25 flop/interaction (SURVEY 8(d)) x %d interactions; peak = %s" % (inter // args.steps, peak_note)))
     for nm, t, per, units, pairs, fpp, bpp in (("density", t_d, DENS_BYTES_PER_UPDATE, st["density_target_passes"], st["density_pairs"], 68.0, 36.0),
                                                ("hydro", t_h, HYDRO_BYTES_PER_UPDATE, own_gas, st["hydro_pairs"], 98.0, 60.0)):
         ach = per * units / t / 1e9

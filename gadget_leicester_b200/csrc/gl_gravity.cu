@@ -135,48 +135,39 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 	  const float4 F2 = __ldg(&e_F2[e]);
 	  if(active)
 	    {
+	      // all sub-tests are evaluated unconditionally (branch-free): with ~14 of 32 lanes active nearly every path
+	      // is taken by some lane anyway, and the predicated form drops the divergence bookkeeping
 	      const float err = fmaf(r2, GW_REL, GW_ABS);
 	      const float r2lo = fmaxf(r2 - err, 0.f), r2hi = r2 + err;
-	      bool open, sure;
+	      float lhs, t_hi, t_lo;
 	      if(BH)
 		{
 		  // forcetree.c:2076  len*len > r2*theta*theta
-		  const float lq = F1.w * F1.w;
-		  const float t_hi = (r2hi * thetaf) * thetaf, t_lo = (r2lo * thetaf) * thetaf;
-		  open = lq * GW_ONE_LO > t_hi;
-		  sure = open || (lq * GW_ONE_HI < t_lo);
+		  lhs = F1.w * F1.w;
+		  t_hi = (r2hi * thetaf) * thetaf;
+		  t_lo = (r2lo * thetaf) * thetaf;
 		}
 	      else
 		{
 		  // forcetree.c:2085  mass*len*len > r2*r2*aold
-		  const float ml2 = (F0.w * F1.w) * F1.w;
-		  const float t_hi = (r2hi * r2hi) * a_hi, t_lo = (r2lo * r2lo) * a_lo;
-		  open = ml2 * GW_ONE_LO > t_hi;
-		  sure = open || (ml2 * GW_ONE_HI < t_lo);
-		  if(sure && !open)
-		    {
-		      // forcetree.c:2094-2105  inside the 0.6*len box around the geometric centre
-		      const float cx = fabsf(dx + F2.x), cy = fabsf(dy + F2.y), cz = fabsf(dz + F2.z);
-		      const float lim_in = F1.w * (0.6f - GW_REL), lim_out = F1.w * (0.6f + GW_REL);
-		      const bool in = cx < lim_in && cy < lim_in && cz < lim_in;
-		      const bool out = cx > lim_out || cy > lim_out || cz > lim_out;
-		      open = in;
-		      sure = in || out;
-		    }
+		  lhs = (F0.w * F1.w) * F1.w;
+		  t_hi = (r2hi * r2hi) * a_hi;
+		  t_lo = (r2lo * r2lo) * a_lo;
 		}
-	      if(sure && !open)
-		{
-		  // forcetree.c:2124-2137  softening guard: h_i < maxsoft -> h = maxsoft, opened if r2 < h*h
-		  const float ms2 = F2.w * F2.w;
-		  if(hif < F2.w)	// monotone rounding: then h_i < maxsoft in FP64 as well
-		    {
-		      hf = F2.w;
-		      open = r2hi < ms2 * GW_ONE_LO;
-		      sure = open || (r2lo > ms2 * GW_ONE_HI);
-		    }
-		  else if(hif == F2.w)	// FP64 order unknown; it only matters when r2 < maxsoft^2 is possible
-		    sure = r2lo > ms2 * GW_ONE_HI;
-		}
+	      const bool mac_open = lhs * GW_ONE_LO > t_hi, mac_closed = lhs * GW_ONE_HI < t_lo;
+	      // forcetree.c:2094-2105  inside the 0.6*len box around the geometric centre (relative criterion only)
+	      const float cmax = fmaxf(fmaxf(fabsf(dx + F2.x), fabsf(dy + F2.y)), fabsf(dz + F2.z));
+	      const bool box_in = !BH && cmax < F1.w * (0.6f - GW_REL), box_out = BH || cmax > F1.w * (0.6f + GW_REL);
+	      // forcetree.c:2124-2137  softening guard: h_i < maxsoft -> h = maxsoft, opened if r2 < h*h
+	      // (monotone rounding: hif < F2.w implies h_i < maxsoft in FP64 as well; equal floats leave the order open,
+	      //  which only matters when r2 < maxsoft^2 is possible)
+	      const float ms2 = F2.w * F2.w;
+	      const bool g_lt = hif < F2.w, g_gt = hif > F2.w;
+	      const bool g_open = r2hi < ms2 * GW_ONE_LO, g_closed = r2lo > ms2 * GW_ONE_HI;
+	      const bool closedpath = mac_closed && box_out;
+	      bool open = mac_open || (mac_closed && box_in) || (closedpath && g_lt && g_open);
+	      const bool sure = open || (closedpath && (g_gt || g_closed));
+	      hf = g_lt ? F2.w : hif;
 	      if(!sure)
 		{
 		  // the uncertain shell: the reference's own FP64 statements
@@ -218,13 +209,13 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 		fac = -mf * rinv;
 	      else
 		{
-		  const float hinv = 1.0f / hf;
+		  const float hinv = __fdividef(1.0f, hf);	// MUFU.RCP (2 ulp): the magnitude is FP32 anyway
 		  const float u = r * hinv;
 		  float wp;
 		  if(u < 0.5f)
 		    wp = -2.8f + u * u * (5.333333333333f + u * u * (6.4f * u - 9.6f));
 		  else
-		    wp = -3.2f + 0.066666666667f / u + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u)));
+		    wp = -3.2f + 0.066666666667f * __fdividef(1.0f, u) + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u)));
 		  fac = mf * hinv * wp;
 		}
 	      ax += (double) fac;
@@ -233,14 +224,17 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 	    fac = mf * rinv * rinv * rinv;
 	  else
 	    {
-	      const float hinv = 1.0f / hf;
+	      const float hinv = __fdividef(1.0f, hf);	// MUFU.RCP (2 ulp): the magnitude is FP32 anyway
 	      const float h3inv = hinv * hinv * hinv;
 	      const float u = r * hinv;
 	      if(u < 0.5f)
 		fac = mf * h3inv * (10.666666666667f + u * u * (32.0f * u - 38.4f));
 	      else
-		fac = mf * h3inv * (21.333333333333f - 48.0f * u + 38.4f * u * u - 10.666666666667f * u * u * u -
-				    0.066666666667f / (u * u * u));
+		{
+		  const float uinv = __fdividef(1.0f, u);
+		  fac = mf * h3inv * (21.333333333333f - 48.0f * u + 38.4f * u * u - 10.666666666667f * u * u * u -
+				      0.066666666667f * (uinv * uinv * uinv));
+		}
 	    }
 	  if(!POT)
 	    {

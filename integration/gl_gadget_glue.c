@@ -106,13 +106,26 @@ static void gl_fill_layout(void)
   GL_Layout = L;
 }
 
+#ifndef GL_GPUS_PER_NODE
+#define GL_GPUS_PER_NODE 8
+#endif
 static void gl_attach(void)
 {
   if(GL) return;
   /* one rank <-> one GPU of the node */
-  if(gl_create(&GL, ThisTask % 8, All.MaxPart)) gl_fail("gl_create");
+  if(gl_create(&GL, ThisTask % GL_GPUS_PER_NODE, All.MaxPart)) gl_fail("gl_create");
   gl_fill_layout();
   if(gl_gadget_bind(GL, &GL_Layout)) gl_fail("gl_gadget_bind");
+#ifndef GL_SINGLE_RANK_ONLY
+  if(NTask > 1)
+    {
+      /* the communicator of the force path: the id travels the way the reference broadcasts All (begrun.c:1922) */
+      char id[128];
+      if(ThisTask == 0 && gl_comm_unique_id(id)) gl_fail("gl_comm_unique_id");
+      MPI_Bcast(id, 128, MPI_BYTE, 0, MPI_COMM_WORLD);
+      if(gl_comm_init(GL, ThisTask, NTask, id)) gl_fail("gl_comm_init");
+    }
+#endif
 }
 
 /* the library evaluates the particles it is told to; the reference's active list is
@@ -157,18 +170,26 @@ static void gl_pull(void)
 
 static int gl_loaded_for = -1;	/* All.NumCurrentTiStep the device copy belongs to */
 
-/* This binding covers ONE rank: the library's multi-rank form (gl_comm_init + the locally-essential exchange,
- * include/gl_b200.h) needs every rank's sources, which the three entry points below do not exchange.  The reference's
- * own functions work at any NTask (gravtree.c:175-347, density.c:193-342, hydra.c:274-520), so a multi-rank run must
- * stop here instead of silently computing forces from the local particles only. */
+/* NTask > 1.  The reference's own functions work at any NTask: they export targets that touch a pseudo-particle to its
+ * owner and add the partial results (gravtree.c:175-347, density.c:193-342, hydra.c:274-520).  The library does the
+ * opposite - every rank imports the locally-essential part of the other ranks' trees over NCCL and evaluates its own
+ * particles completely (include/gl_b200.h "multi-rank mode") - behind the same three entry points: gl_attach() creates
+ * the communicator from an id that rank 0 draws and MPI_Bcast distributes, and from then on gl_gravity_tree /
+ * gl_density / gl_force_update_hmax / gl_hydro_force are collective, exactly like the functions they replace.
+ * One rank <-> one GPU: ranks of a node take the GPUs in PTask-local order (GL_GPUS_PER_NODE, default 8).
+ * -DGL_SINGLE_RANK_ONLY keeps the old behaviour of stopping at NTask != 1 (a build without NCCL on the nodes). */
 static void gl_require_single_rank(const char *where)
 {
+#ifdef GL_SINGLE_RANK_ONLY
   if(NTask != 1)
     {
-      printf("libgl_b200 glue: %s() of this binding handles NTask == 1 only (NTask = %d)\n", where, NTask);
+      printf("libgl_b200 glue: %s() of this build handles NTask == 1 only (NTask = %d)\n", where, NTask);
       fflush(stdout);
       endrun(8801);
     }
+#else
+  (void) where;
+#endif
 }
 
 static void gl_ensure_loaded(void)
