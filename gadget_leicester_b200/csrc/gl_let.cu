@@ -37,6 +37,11 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define GL_LET_BOXES 64		// target boxes per rank (plus one for the whole rank)
 #define GL_LET_BOXDBL 14		// lo[3], hi[3], aold_min, hsph_max (-1: no SPH target inside), reach lo[3], hi[3]: bbox of the search spheres
 #define GL_LET_HDR (2 * GL_LET_BOXES)	// per-rank header: the Peano-Hilbert key hull {min, max} of every stretch (bit patterns)
+#define GL_LET_SUB 8		// every stretch is cut into GL_LET_SUB sub-stretches with boxes of their own (second level of the test)
+#define GL_LET_LEAVES (GL_LET_BOXES * GL_LET_SUB)
+// one rank's block: [hulls | box 0 = whole rank, boxes 1..GL_LET_BOXES = stretches | GL_LET_LEAVES sub-stretch boxes]
+#define GL_LET_BLK (GL_LET_HDR + (GL_LET_BOXES + 1 + GL_LET_LEAVES) * GL_LET_BOXDBL)
+#define GL_LET_LEAF0 (GL_LET_HDR + (GL_LET_BOXES + 1) * GL_LET_BOXDBL)
 #define GL_LET_PART_DBL 10	// exported particle: pos[3], vel[3], mass, hsml, entropy, (type | timebin << 32)
 #define GL_LET_CELL_DBL 8	// exported cell: key (bits), s[3], mass, maxsoft, hmax, level + 32 * vmax-less flag
 #define GL_LET_SPH_DBL 6	// second exchange, per particle: hsml, density, pressure, dhsml, divvel, curlvel
@@ -90,8 +95,10 @@ __global__ void k_let_boxes(long long n_own, const long long *__restrict__ bound
 			    const double *__restrict__ oldacc, const double *__restrict__ hsml, const int *__restrict__ type,
 			    double errtolforceacc, double fs, double *__restrict__ boxes)
 {
-  const int b = blockIdx.x + 1;	// box 0 (the whole rank) is the union of the others: k_let_box_union
-  const long long i0 = bounds[b - 1], i1 = bounds[b];
+  // block = (stretch b, sub-stretch q): a box per sub-stretch; stretch boxes and the whole-rank box are unions (k_let_box_union)
+  const int b = blockIdx.x / GL_LET_SUB, q = blockIdx.x % GL_LET_SUB;
+  const long long s0 = bounds[b], s1 = bounds[b + 1];
+  const long long i0 = s0 + (s1 - s0) * q / GL_LET_SUB, i1 = s0 + (s1 - s0) * (q + 1) / GL_LET_SUB;
   (void) n_own;
   // v[0..2] min pos, [3..5] max pos, [6] min aold, [7] max search radius, [8..10] min (pos - fs h), [11..13] max (pos + fs h)
   double v[GL_LET_BOXDBL];
@@ -141,25 +148,38 @@ __global__ void k_let_boxes(long long n_own, const long long *__restrict__ bound
 	    const bool ismin = k < 3 || k == 6 || (k >= 8 && k < 11);
 	    sh[0][k] = ismin ? fmin(sh[0][k], sh[ww][k]) : fmax(sh[0][k], sh[ww][k]);
 	  }
-      double *o = boxes + GL_LET_HDR + (long long) b * GL_LET_BOXDBL;
+      double *o = boxes + GL_LET_LEAF0 + (long long) blockIdx.x * GL_LET_BOXDBL;
       for(int k = 0; k < GL_LET_BOXDBL; k++) o[k] = sh[0][k];
     }
 }
 
-__global__ void k_let_box_union(double *__restrict__ boxes)
+// block b >= 1: stretch b = union of its sub-stretch boxes; then (second launch, block 0) the whole rank = union of the stretches
+__global__ void k_let_box_union(double *__restrict__ boxes, int whole)
 {
   const int k = threadIdx.x;
   if(k >= GL_LET_BOXDBL) return;
   const bool ismin = k < 3 || k == 6 || (k >= 8 && k < 11);
   double v = ismin ? 1e300 : -1e300;
   if(k == 7) v = -1.0;
-  for(int b = 1; b <= GL_LET_BOXES; b++)
+  if(whole)
     {
-      const double *o = boxes + GL_LET_HDR + (long long) b * GL_LET_BOXDBL;
-      if(o[0] > o[3]) continue;	// empty stretch
+      for(int b = 1; b <= GL_LET_BOXES; b++)
+	{
+	  const double *o = boxes + GL_LET_HDR + (long long) b * GL_LET_BOXDBL;
+	  if(o[0] > o[3]) continue;	// empty stretch
+	  v = ismin ? fmin(v, o[k]) : fmax(v, o[k]);
+	}
+      boxes[GL_LET_HDR + k] = v;
+      return;
+    }
+  const int b = blockIdx.x;	// stretch b -> box b + 1
+  for(int q = 0; q < GL_LET_SUB; q++)
+    {
+      const double *o = boxes + GL_LET_LEAF0 + (long long) (b * GL_LET_SUB + q) * GL_LET_BOXDBL;
+      if(o[0] > o[3]) continue;
       v = ismin ? fmin(v, o[k]) : fmax(v, o[k]);
     }
-  boxes[GL_LET_HDR + k] = v;
+  boxes[GL_LET_HDR + (long long) (b + 1) * GL_LET_BOXDBL + k] = v;
 }
 
 __global__ void k_let_count_gas(long long n, const int *__restrict__ type, int *__restrict__ count)
@@ -234,7 +254,8 @@ k_let_select_level(int count, const int *__restrict__ lev_list, long long m, con
   __shared__ double sbox[(GL_LET_BOXES + 1) * GL_LET_BOXDBL];
   const int d = blockIdx.y;
   if(d == P.me) return;
-  const double *rb = box_all + (long long) d * (GL_LET_HDR + (GL_LET_BOXES + 1) * GL_LET_BOXDBL) + GL_LET_HDR;
+  const double *rb = box_all + (long long) d * GL_LET_BLK + GL_LET_HDR;
+  const double *leaves = box_all + (long long) d * GL_LET_BLK + GL_LET_LEAF0;
   for(int k = threadIdx.x; k < (GL_LET_BOXES + 1) * GL_LET_BOXDBL; k += blockDim.x) sbox[k] = rb[k];
   __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,8 +275,13 @@ k_let_select_level(int count, const int *__restrict__ lev_list, long long m, con
       bool need = box_may_need(sbox, sm, cl, ax, P);	// the whole rank first: far ranks are settled by one test
       if(need)
 	{
+	  // the stretches, and below a stretch that may need the cell its sub-stretches (their boxes are 8x smaller,
+	  // so the zone in which a cell has to be resolved shrinks with them)
 	  need = false;
-	  for(int b = 1; b <= GL_LET_BOXES && !need; b++) need = box_may_need(sbox + b * GL_LET_BOXDBL, sm, cl, ax, P);
+	  for(int b = 1; b <= GL_LET_BOXES && !need; b++)
+	    if(box_may_need(sbox + b * GL_LET_BOXDBL, sm, cl, ax, P))
+	      for(int q = 0; q < GL_LET_SUB && !need; q++)
+		need = box_may_need(leaves + (long long) ((b - 1) * GL_LET_SUB + q) * GL_LET_BOXDBL, sm, cl, ax, P);
 	}
       res = need ? 0 : 1;
     }
@@ -496,7 +522,7 @@ int gll_distributed_build(gl_ctx *c)
   cudaEventRecord(e1, c->stream);
   stamp("own tree");
   // ---- 3. target description of every rank ----
-  const size_t blk = GL_LET_HDR + (size_t) (GL_LET_BOXES + 1) * GL_LET_BOXDBL;
+  const size_t blk = GL_LET_BLK;
   GL_CUDA(c, L->box_own.ensure(blk));
   GL_CUDA(c, L->box_all.ensure(blk * W));
   GL_CUDA(c, L->ranges.ensure(2 * (size_t) W + 2));
@@ -524,10 +550,11 @@ int gll_distributed_build(gl_ctx *c)
     hbnd[GL_LET_BOXES] = n;
     GL_CUDA(c, cudaMemcpyAsync(bdev, hbnd, sizeof(hbnd), cudaMemcpyHostToDevice, c->stream));
     if(glk_ph_chunk_hulls(c, bdev, GL_LET_BOXES, (unsigned long long *) L->box_own.p)) return 1;
-    k_let_boxes<<<GL_LET_BOXES, 256, 0, c->stream>>>(n, bdev, c->in_pos.p, c->in_oldacc.p, c->in_hsml.p, c->in_type.p,
-						      c->par.ErrTolForceAcc, L->fs, L->box_own.p);
-    k_let_box_union<<<1, 32, 0, c->stream>>>(L->box_own.p);
-    c->kernel_launches += 2;
+    k_let_boxes<<<GL_LET_LEAVES, 128, 0, c->stream>>>(n, bdev, c->in_pos.p, c->in_oldacc.p, c->in_hsml.p, c->in_type.p,
+						       c->par.ErrTolForceAcc, L->fs, L->box_own.p);
+    k_let_box_union<<<GL_LET_BOXES, 32, 0, c->stream>>>(L->box_own.p, 0);
+    k_let_box_union<<<1, 32, 0, c->stream>>>(L->box_own.p, 1);
+    c->kernel_launches += 3;
     GL_CUDA(c, cudaStreamSynchronize(c->stream));	// hbnd is a stack array
   }
   GL_COMM(c, cm->allgather(L->box_own.p, L->box_all.p, blk * sizeof(double), c->stream));
