@@ -691,11 +691,27 @@ extern "C" int gl_gadget_compute_accelerations(gl_ctx *c, void *Pv, void *SphPv,
     {
       // multi-rank mode: this rank's own P[] / SphP[]; the phases are collective and may be repeated (gl_let.cu), so
       // they run through the ordinary entry points, without the software pipeline of the single-rank path below
+      // (collective, repeatable entry points); every result block goes home behind the next phase's kernel launch and
+      // is scattered by a host thread while that phase computes (gl_gadget_push_segment_async)
       cudaSetDevice(c->device);
+      (void) mode;
       if(gl_gadget_pull(c, Pv, SphPv, NumPart, N_gas)) return 1;
       gl_set_tree_reconstruct_flag(c, 1);
-      if(gl_compute_accelerations(c, mode)) return 1;
-      return gl_gadget_push(c, Pv, SphPv, 7);
+      const bool first = (c->par.TypeOfOpeningCriterion == 1 && c->par.Ti_Current == 0 && c->par.ErrTolTheta != 0);
+      if(gl_gravity_tree(c)) return 1;	// accel.c:61
+      if(first)
+	if(gl_gravity_tree(c)) return 1;	// accel.c:63-67
+      if(gl_gadget_push_segment_async(c, Pv, SphPv, 1)) return 1;
+      if(gl_prepare_targets(c)) return 1;
+      if(c->n_tgt_sph > 0)
+	{
+	  if(gl_density(c)) return 1;	// accel.c:84
+	  if(gl_gadget_push_segment_async(c, Pv, SphPv, 2)) return 1;
+	  if(gl_force_update_hmax(c)) return 1;	// accel.c:96
+	  if(gl_hydro_force(c)) return 1;	// accel.c:106
+	  if(gl_gadget_push_segment_async(c, Pv, SphPv, 4)) return 1;
+	}
+      return gl_gadget_push_wait(c);
     }
   (void) mode;
   cudaSetDevice(c->device);

@@ -90,3 +90,75 @@ def test_c_abi_two_ranks_from_cpp(tmp_path):
     r = subprocess.run([exe, os.path.join(ROOT, "gadget_leicester_b200", "libgl_b200.so"), "40000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout and "mismatching particles 0" in r.stdout
+
+
+def test_dropin_call_on_every_ranks_own_arrays():
+    """gl_gadget_compute_accelerations at NTask = 3: every rank calls it on its OWN P[] / SphP[] (its Peano-Hilbert
+    segment, gas first), like the reference's compute_accelerations() at any NTask.  The structs must end up with the
+    values a single rank writes into the same particles (counts exact, GravAccel bitwise, SPH fields to 1e-12), twice in a
+    row (the second call starts from the Hsml / OldAcc the first one left in P[])."""
+    import threading
+    import let_check as LC
+    from gadget_leicester_b200 import aos, lib as L
+    from gadget_leicester_b200.gadget import ForcePath
+    ps, par = LC.make_case("disc", 60000)
+    n = ps["pos"].shape[0]
+    ngas = int((ps["type"] == 0).sum())
+    one = ForcePath(par)
+    one.load(ps)
+    order = one.peano_hilbert_order(ngas)
+    pso = {k: (np.ascontiguousarray(v[order]) if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+    arr1 = aos.GadgetArrays(pso, pinned=False)
+    d1 = aos.GadgetDropIn(one, arr1)
+    d1.compute_accelerations()
+    one.set_params(Ti_Current=1)
+    d1.compute_accelerations()
+    ref = arr1.results()
+    one.close()
+
+    world = 3
+    lib = L.load_library()
+    group = lib.gl_comm_local_group_create(world)
+    # segments: gas split evenly, the two sinks go to the last rank (every rank's P[] has its gas first)
+    cuts = [ngas * r // world for r in range(world + 1)]
+    segs = [np.arange(cuts[r], cuts[r + 1]) for r in range(world)]
+    segs[-1] = np.concatenate([segs[-1], np.arange(ngas, n)])
+    out, err = [None] * world, [None] * world
+
+    def worker(r):
+        try:
+            psr = {k: (np.ascontiguousarray(v[segs[r]]) if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in pso.items()}
+            fp = ForcePath(par)
+            fp.comm_init_local(r, group)
+            arr = aos.GadgetArrays(psr, pinned=False)
+            d = aos.GadgetDropIn(fp, arr)
+            d.compute_accelerations()
+            fp.set_params(Ti_Current=1)
+            d.compute_accelerations()
+            out[r] = arr.results()
+            fp.close()
+        except Exception as ex:     # noqa: BLE001
+            err[r] = ex
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    lib.gl_comm_local_group_destroy(group)
+    for e in err:
+        if e is not None:
+            raise e
+    for r in range(world):
+        sg = segs[r]
+        g = sg[sg < ngas]
+        assert (out[r]["GravCost"] == ref["GravCost"][sg]).all()
+        assert (out[r]["GravAccel"] == ref["GravAccel"][sg]).all()
+        assert (out[r]["OldAcc"] == ref["OldAcc"][sg]).all()
+        for k in ("Hsml", "NumNgb"):
+            e = np.abs(out[r][k] - ref[k][sg]) / np.maximum(np.abs(ref[k][sg]), 1e-300)
+            assert e.max() <= 1e-12, k
+        for k in ("Density", "Pressure", "HydroAccel", "MaxSignalVel", "DhsmlDensityFactor"):
+            a, b = out[r][k][: len(g)], ref[k][g]
+            num = np.abs(a - b) if a.ndim == 1 else np.linalg.norm(a - b, axis=-1)
+            den = np.abs(b) if a.ndim == 1 else np.linalg.norm(b, axis=-1)
+            assert (num / np.maximum(den, 1e-300)).max() <= 1e-11, k
