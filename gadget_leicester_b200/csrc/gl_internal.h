@@ -9,6 +9,7 @@
 #include <vector>
 #include <functional>
 #include <thread>
+#include <atomic>
 #include "../../include/gl_b200.h"
 #include "gl_comm.h"
 
@@ -224,7 +225,7 @@ struct gl_ctx
   // the copies had finished (2.9 ms per step), although they run on another stream.
   std::function<void()> post_launch;
   std::vector<std::thread> push_threads;	// gl_gadget_push_segment_async scatter threads, joined by gl_gadget_push_wait
-  int push_failed = 0;
+  std::atomic<int> push_failed{0};	// written by the scatter threads
   void fire_post_launch()
   {
     if(post_launch)

@@ -351,12 +351,17 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
   // straight into the mapping (concurrent write() calls on one file would queue on the inode lock).  Where the file
   // cannot be mapped (a pipe, an odd file system) the image is built in memory and written in one call.
   const long long total = off;
-  const int fd = open(fname, O_RDWR | O_CREAT | O_TRUNC, 0644);
+  // written under a temporary name and renamed when complete: a failure (full disk, quota) leaves the previous snapshot
+  // of that name alone, where the reference would already have truncated it before endrun(777)
+  const std::string tmpname = std::string(fname) + ".gl_tmp";
+  const int fd = open(tmpname.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
   if(fd < 0) return c.fail("can't open file `%s' for writing snapshot.", fname);	// io.c:2626-2630 endrun(123)
   std::atomic<int> bad{0};
   char *image = nullptr;
   bool mapped = false;
-  if(ftruncate(fd, (off_t) total) == 0)
+  // the blocks are RESERVED before the file is mapped (posix_fallocate): on a full disk that fails here with an error
+  // code instead of raising SIGBUS inside a worker when a page of the mapping cannot be backed
+  if(ftruncate(fd, (off_t) total) == 0 && posix_fallocate(fd, 0, (off_t) total) == 0)
     {
       void *m = mmap(nullptr, (size_t) total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
       if(m != MAP_FAILED)
@@ -402,6 +407,7 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
   const double T3 = gl_now();
   if(mapped)
     {
+      if(msync(image, (size_t) total, MS_SYNC) != 0) bad.store(1);	// write-back errors are reported here, not lost
       if(munmap(image, (size_t) total) != 0) bad.store(1);
     }
   else
@@ -424,7 +430,16 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
     }
   if(close(fd) != 0) bad.store(1);
   if(getenv("GL_DEBUG_IO")) fprintf(stderr, "snapshot_write: index %.2f ms, layout+open %.2f ms, payload %.2f ms, close %.2f ms\n", (T1 - T0) * 1e3, (T2 - T1) * 1e3, (T3 - T2) * 1e3, (gl_now() - T3) * 1e3);
-  if(bad.load()) return c.fail("gl_snapshot_write: I/O error on `%s'", fname);
+  if(bad.load())
+    {
+      unlink(tmpname.c_str());
+      return c.fail("gl_snapshot_write: I/O error on `%s'", fname);	// my_fwrite io.c:2988 endrun(777)
+    }
+  if(rename(tmpname.c_str(), fname) != 0)
+    {
+      unlink(tmpname.c_str());
+      return c.fail("gl_snapshot_write: cannot rename the finished file to `%s'", fname);
+    }
   return 0;
 }
 
