@@ -243,8 +243,10 @@ __device__ __forceinline__ bool box_may_need(const double *__restrict__ box, con
 }
 
 // one level of the top-down pass: blockIdx.y = destination rank (its target boxes are staged in shared memory),
-// thread = cell of that level.  state: 0 = descend (children are looked at), 1 = exported as a cut cell,
-// 2 = below an exported cell
+// EIGHT LANES per cell of that level: lane q looks at the stretches q+1, q+9, ... (and, below a stretch that may
+// need the cell, at its sub-stretches); the eight leave together as soon as one of them found a box that needs the cell
+// (the work per cell varies from one test to several hundred - one thread per cell left most of a warp idle).
+// state: 0 = descend (children are looked at), 1 = exported as a cut cell, 2 = below an exported cell
 __global__ void __launch_bounds__(128)
 k_let_select_level(int count, const int *__restrict__ lev_list, long long m, const int *__restrict__ n_parent,
 		   const double4 *__restrict__ n_sm, const double4 *__restrict__ n_cl, const double4 *__restrict__ n_aux,
@@ -258,34 +260,45 @@ k_let_select_level(int count, const int *__restrict__ lev_list, long long m, con
   const double *leaves = box_all + (long long) d * GL_LET_BLK + GL_LET_LEAF0;
   for(int k = threadIdx.x; k < (GL_LET_BOXES + 1) * GL_LET_BOXDBL; k += blockDim.x) sbox[k] = rb[k];
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if(t >= count) return;
-  const int id = lev_list[t];
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, q = threadIdx.x & 7;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);	// my group of eight lanes
+  const bool live = t < count;
+  const int id = live ? lev_list[t] : 0;
   unsigned char *st = state + (long long) d * m;
-  const int par = n_parent[id];
-  if(par >= 0 && st[par] != 0)
+  const int par = live ? n_parent[id] : -1;
+  int res = 0;			// all eight lanes of a cell compute the same res
+  bool test = false;
+  if(live)
     {
-      st[id] = 2;
-      return;
+      if(par >= 0 && st[par] != 0)
+	res = 2;
+      else if(!P.full && complete[id])
+	test = true;
     }
-  unsigned char res = 0;
-  if(!P.full && complete[id])
+  if(test)
     {
       const double4 sm = n_sm[id], cl = n_cl[id], ax = n_aux[id];
       bool need = box_may_need(sbox, sm, cl, ax, P);	// the whole rank first: far ranks are settled by one test
       if(need)
 	{
-	  // the stretches, and below a stretch that may need the cell its sub-stretches (their boxes are 8x smaller,
-	  // so the zone in which a cell has to be resolved shrinks with them)
 	  need = false;
-	  for(int b = 1; b <= GL_LET_BOXES && !need; b++)
-	    if(box_may_need(sbox + b * GL_LET_BOXDBL, sm, cl, ax, P))
-	      for(int q = 0; q < GL_LET_SUB && !need; q++)
-		need = box_may_need(leaves + (long long) ((b - 1) * GL_LET_SUB + q) * GL_LET_BOXDBL, sm, cl, ax, P);
+	  for(int it = 0; it < GL_LET_BOXES / 8; it++)
+	    {
+	      const int b = it * 8 + q + 1;
+	      bool mine = false;
+	      if(box_may_need(sbox + b * GL_LET_BOXDBL, sm, cl, ax, P))
+		for(int k = 0; k < GL_LET_SUB && !mine; k++)
+		  mine = box_may_need(leaves + (long long) ((b - 1) * GL_LET_SUB + k) * GL_LET_BOXDBL, sm, cl, ax, P);
+	      if(__ballot_sync(gmask, mine) & gmask)
+		{
+		  need = true;
+		  break;
+		}
+	    }
 	}
       res = need ? 0 : 1;
     }
-  st[id] = res;
+  if(live && q == 0) st[id] = (unsigned char) res;
 }
 
 // selection flags: per destination M cell flags followed by n particle flags
@@ -574,7 +587,7 @@ int gll_distributed_build(gl_ctx *c)
     {
       const int cnt = c->lev_start[lev + 1] - c->lev_start[lev];
       if(cnt <= 0) continue;
-      k_let_select_level<<<dim3(gl_grid(cnt, 128), W), 128, 0, c->stream>>>(cnt, c->lev_list.p + c->lev_start[lev], m, c->n_parent.p,
+      k_let_select_level<<<dim3(gl_grid(8ll * cnt, 128), W), 128, 0, c->stream>>>(cnt, c->lev_list.p + c->lev_start[lev], m, c->n_parent.p,
 									    c->n_sm.p, c->n_cl.p, c->n_aux.p, L->complete.p,
 									    L->box_all.p, L->state.p, P);
       GL_LAUNCH_COUNT(c);
