@@ -807,7 +807,6 @@ extern "C" int gl_compute_accelerations(gl_ctx *c, int mode)
 template <class T> static int get(gl_ctx *c, T *dst, const DBuf<T> &src, size_t cnt, int where, const char *what)
 {
   if(!dst) return 0;
-  if(src.cap < cnt) return c->fail(std::string("result not available: ") + what);
   size_t off = 0;
   if(c->res_count >= 0 && c->n > 0)
     {
@@ -815,6 +814,9 @@ template <class T> static int get(gl_ctx *c, T *dst, const DBuf<T> &src, size_t 
       off = (size_t) c->res_first * w;
       cnt = (size_t) c->res_count * w;
     }
+  // (multi-rank mode: a later phase that had to be repeated with more imports makes c->n larger than it was when an
+  // earlier phase sized its result arrays - only the requested range has to exist)
+  if(src.cap < off + cnt) return c->fail(std::string("result not available: ") + what);
   if(cnt == 0) return 0;
   GL_CUDA(c, cudaMemcpyAsync(dst + off, src.p + off, cnt * sizeof(T), where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
 			     c->stream));

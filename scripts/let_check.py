@@ -124,8 +124,8 @@ def compare(ref, res, sph, ps_type):
         for tag, htag in (("d", "h"), ("d2", "h2")):
             put(tag + ".DensPairs mismatches", cat(tag, "DensPairs"), ref[tag]["DensPairs"][seg], True)
             put(tag + ".Hsml max rel", cat(tag, "Hsml"), ref[tag]["Hsml"][seg])
-            put(tag + ".Density max rel", cat(tag, "Density"), ref[tag]["Density"][seg])
-            gas = ps_type[seg] == 0         # hydro targets are gas only (hydra.c:258): other entries are never written
+            gas = ps_type[seg] == 0         # SphP fields exist for gas only (hydra.c:258, density.c:440): other entries are never written
+            put(tag + ".Density max rel", cat(tag, "Density")[gas], ref[tag]["Density"][seg][gas])
             put(htag + ".HydroPairs mismatches", cat(htag, "HydroPairs")[gas], ref[htag]["HydroPairs"][seg][gas], True)
             put(htag + ".HydroAccel max rel", cat(htag, "HydroAccel"), ref[htag]["HydroAccel"][seg])
             put(htag + ".DtEntropy max abs/scale", cat(htag, "DtEntropy") / (np.abs(ref[htag]["DtEntropy"]).max() + 1e-300),
