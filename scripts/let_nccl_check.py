@@ -18,7 +18,7 @@ from gadget_leicester_b200.multigpu import LetForcePath           # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=200000)
+    ap.add_argument("--particles", dest="n", type=int, default=200000)
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)

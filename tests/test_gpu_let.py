@@ -77,7 +77,7 @@ def test_two_gpus_over_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (the in-process tests above cover the same path on one)")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", os.path.join(ROOT, "scripts", "let_nccl_check.py"), "--n", "200000"],
+                        "--master-port", "29533", os.path.join(ROOT, "scripts", "let_nccl_check.py"), "--particles", "200000"],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "IDENTICAL" in r.stdout
