@@ -206,6 +206,14 @@ struct gl_ctx
   DBuf<int> fat_p, fat_i;
   DBuf<double4> fat_state, fat_rec;
   DBuf<double> fat_tgt;
+  // ---- sub-grid neighbour loops (gl_subgrid.cu) ----
+  gl_subgrid_params subgrid{};
+  bool have_subgrid = false;
+  DBuf<int> sg_active, sg_list, sg_cnt;
+  DBuf<unsigned char> sg_flag;
+  DBuf<double> sg_scratch, sg_vals;
+  DBuf<unsigned long long> sg_claim, sg_keys;
+  DBuf<long long> sg_off;
   // ---- gadget AoS layer ----
   gl_gadget_layout lay{};
   bool have_lay = false;

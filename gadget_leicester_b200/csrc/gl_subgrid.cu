@@ -1,0 +1,788 @@
+// gl_subgrid.cu - the sub-grid neighbour loops that follow the force path, on the tree of the step
+//
+// accel.c:189-196 calls, right behind hydro_force(): blackhole_accretion() (blackhole.c:70) and, under -DDUST,
+// dust_density() (dust.c:60) and dust_drag() (dust.c:263).  Each is a "search a sphere, then sum or mark" loop over
+// ngb_treefind_blackhole (blackhole.c:1351) / ngb_treefind_dust_active (dust.c:1235).  Here they run on the array
+// tree the force path built for this step:
+//   * one warp per target (sink or dust grain); the warp marches the DFS entry array with the reference's cell test
+//     (blackhole.c:1445-1463) and takes every cell of <= SG_BUCKET particles as one contiguous range of the sorted
+//     particle arrays, 32 candidates per step - candidates reach the caller's code in the reference's Ngblist order
+//     (tree order), which two statements of blackhole_evaluate depend on;
+//   * what the reference resolves by visiting sinks one after the other is resolved by keys: "the last sink that
+//     claims a dust grain or another sink gets it" (blackhole.c:991, :1030) = atomicMax over (position in the active
+//     list, id); "the largest id gets the gas particle" (:1071) = atomicMax over the id;
+//   * dust_evaluate_select (dust.c:889) SCATTERS onto gas neighbours and its entropy update does not commute
+//     (clip at 1.5, floor MinEgySpec: dust.c:1000-1004): the (gas, dust) pairs are sorted by (gas index, position of
+//     the grain in the active list) and applied per gas particle in that order - the reference's order.
+// Single rank (the multi-rank build's cut cells are reported, not searched).
+#include "gl_internal.h"
+#include <cub/cub.cuh>
+
+namespace
+{
+constexpr unsigned FULL = 0xffffffffu;
+#define SG_BUCKET 96		// cells with at most this many particles are tested as one range
+#define SG_GAMMA (7. / 5.)	// allvars.h:64
+#define SG_GAMMA_MINUS1 (SG_GAMMA - 1)
+#define SG_PI 3.14159265358979323846
+#define SG_PROTONMASS 1.6726e-24	// allvars.h
+#define SG_KC1 2.546479089470	// KERNEL_COEFF_1, _2, _5 (allvars.h:247-253)
+#define SG_KC2 15.278874536822
+#define SG_KC5 5.092958178941
+
+struct SgTree
+{
+  int nentries;
+  const int *e_next;
+  const double4 *e_B;
+  const int2 *e_rng;
+  const double4 *s_pm;
+  const int *s_type;
+  const int *perm;
+};
+
+// The reference's neighbour search (blackhole.c:1351-1470, dust.c:1235-1330) as an ordered march: f(valid, p, dx, dy,
+// dz, r2) is called by all 32 lanes for 32 consecutive tree-order particles at a time; valid = the particle is on the
+// reference's Ngblist (type wanted, |d| <= h per axis, r2 <= h*h).  d = target - particle, r2 rounded as the reference's
+// unfused dx*dx + dy*dy + dz*dz.
+template <class F>
+__device__ __forceinline__ void sg_march(const SgTree &T, int lane, double px, double py, double pz, double h, unsigned typemask,
+					 unsigned long long *counter, F f)
+{
+  const double h2 = __dmul_rn(h, h);
+  int e = 0;
+  while(e < T.nentries)
+    {
+      const int nx = __ldg(&T.e_next[e]);
+      int a, b;
+      if(nx < 0)
+	{
+	  a = (-1 - nx) >> 3;
+	  b = a + 1;
+	  e = e + 1;
+	}
+      else
+	{
+	  const double4 B = gl_ld4(&T.e_B[e]);
+	  double dist = h + 0.5 * B.w;
+	  const double cx = fabs(B.x - px), cy = fabs(B.y - py), cz = fabs(B.z - pz);
+	  bool skip = cx > dist || cy > dist || cz > dist;
+	  if(!skip)
+	    {
+	      dist += 0.366025403785 * B.w;
+	      skip = cx * cx + cy * cy + cz * cz > dist * dist;
+	    }
+	  if(skip)
+	    {
+	      e = nx;
+	      continue;
+	    }
+	  const int2 rg = __ldg(&T.e_rng[e]);
+	  if(rg.x < 0)
+	    {
+	      if(lane == 0) atomicMax(&counter[2], GL_ERR_LET_VIOLATION);
+	      e = nx;
+	      continue;
+	    }
+	  if(rg.y - rg.x > SG_BUCKET)
+	    {
+	      e = e + 1;
+	      continue;
+	    }
+	  a = rg.x;
+	  b = rg.y;
+	  e = nx;
+	}
+      for(int q = a; q < b; q += 32)
+	{
+	  const int p = q + lane;
+	  bool valid = p < b;
+	  double dx = 0, dy = 0, dz = 0, r2 = 0;
+	  if(valid)
+	    {
+	      valid = (typemask >> __ldg(&T.s_type[p])) & 1u;
+	      if(valid)
+		{
+		  const double4 pm = gl_ld4(&T.s_pm[p]);
+		  dx = px - pm.x;
+		  dy = py - pm.y;
+		  dz = pz - pm.z;
+		  r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+		  valid = !(fabs(dx) > h || fabs(dy) > h || fabs(dz) > h || r2 > h2);
+		}
+	    }
+	  f(valid, p, dx, dy, dz, r2);
+	}
+    }
+}
+
+__device__ __forceinline__ double sg_kernel_wk(double u, double hinv3)
+{
+  // density.c:862-871 / blackhole.c:1046-1053 / dust.c:841-847
+  if(u < 0.5) return hinv3 * (SG_KC1 + SG_KC2 * (u - 1) * u * u);
+  return hinv3 * SG_KC5 * (1.0 - u) * (1.0 - u) * (1.0 - u);
+}
+__device__ __forceinline__ double sg_warp_sum(double v)
+{
+  for(int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double sg_dt(int timebin, double tbi) { return (timebin ? (double) (1 << timebin) : 0.0) * tbi; }
+
+// ---- target lists: the active particles of one type, in active-list order ----
+__global__ void k_sg_iota(long long n, int *out)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i < n) out[i] = (int) i;
+}
+__global__ void k_sg_flag_type(long long m, const int *__restrict__ active, const int *__restrict__ type, long long n, int want,
+			       unsigned char *__restrict__ flag, int *__restrict__ bad)
+{
+  const long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(k >= m) return;
+  const int i = active[k];
+  if(i < 0 || i >= n)
+    {
+      atomicAdd(bad, 1);
+      flag[k] = 0;
+      return;
+    }
+  flag[k] = type[i] == want;
+}
+
+// ---- sinks ----
+struct SinkArr
+{
+  double *vel;
+  const int *id;
+  int *swallow;
+  double *bh_mass, *bh_mdot, *accdisc, *dust_mass, *total_mass;
+  const double *sinkrho;
+  double *inj;
+};
+#define SINK_SC 12		// per-sink scratch: dt, mdot, energy, acc_mass, acc_dust, mom[3], spare
+
+// blackhole.c:181-214: the accretion-disc reservoir feeds the sink on the viscous time scale
+__global__ void k_sink_mdot(int ns, const int *__restrict__ sinks, const int *__restrict__ timebin, const double *__restrict__ mass,
+			    gl_subgrid_params par, double tbi, SinkArr A, double *__restrict__ sc)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if(s >= ns) return;
+  const int i = sinks[s];
+  const double dt = sg_dt(timebin[i], tbi);
+  const double mdot = A.accdisc[i] / (dt + (par.ViscousTimescale / par.UnitTime_in_s));
+  const double dm = __dmul_rn(mdot, dt);
+  A.accdisc[i] = __dadd_rn(A.accdisc[i], -dm);
+  A.bh_mass[i] = __dadd_rn(A.bh_mass[i], dm);
+  A.bh_mdot[i] = mdot;
+  // blackhole.c:1139-1150: thermal feedback of a planet-mass sink (the SMBH-class sink injects nothing)
+  const double m = mass[i];
+  double energy = 0.;
+  if(m < 0.95 * par.SMBHmass)
+    energy = par.BlackHoleFeedbackFactor * pow(m * par.UnitMass_in_g, 0.6667) * 6.67e-8 * pow(4. * 3.1415 / 3. * 5., 0.3333) /
+      par.UnitEnergy_in_cgs * mdot * par.UnitMass_in_g * dt;
+  double *q = sc + (size_t) s * SINK_SC;
+  q[0] = dt;
+  q[1] = mdot;
+  q[2] = energy;
+  for(int k = 3; k < SINK_SC; k++) q[k] = 0;
+}
+
+// blackhole_evaluate (blackhole.c:794-1199): one warp per active sink
+__global__ void __launch_bounds__(GL_BLOCK) k_sink_evaluate(int ns, const int *__restrict__ sinks, SgTree T, const double *__restrict__ in_pos,
+							    const double *__restrict__ in_hsml, const double *__restrict__ in_mass, gl_subgrid_params par,
+							    SinkArr A, const double *__restrict__ sc, unsigned long long *__restrict__ claim,
+							    unsigned long long *__restrict__ counter)
+{
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(s >= ns) return;
+  const int i = sinks[s];
+  const double mass = in_mass[i];
+  if(!(mass > 0)) return;	// blackhole.c:903
+  const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
+  const double h = in_hsml[i], h2 = __dmul_rn(h, h);
+  const double vx = A.vel[3 * (size_t) i], vy = A.vel[3 * (size_t) i + 1], vz = A.vel[3 * (size_t) i + 2];
+  const int id = A.id[i];
+  const double rho = A.sinkrho[i];
+  const double energy = sc[(size_t) s * SINK_SC + 2];
+  const bool smbh = mass > 0.95 * par.SMBHmass;
+  const unsigned long long key = ((unsigned long long) (s + 1) << 32) | (unsigned int) id;
+  const unsigned lt = (1u << lane) - 1;
+  double r_stale = 0.;		// `r` of blackhole_evaluate: written for gas neighbours only (:1042), read for dust (:1024)
+  sg_march(T, lane, px, py, pz, h, (1u << 0) | (1u << 2) | (1u << 5), counter, [&](bool valid, int p, double dx, double dy, double dz, double r2) {
+    (void) dx; (void) dy; (void) dz;
+    int type = -1, j = 0;
+    double mj = 0;
+    if(valid)
+      {
+	type = T.s_type[p];
+	mj = T.s_pm[p].w;
+	j = T.perm[p];
+      }
+    const bool ok = valid && mj > 0 && r2 < h2;	// blackhole.c:901, :921
+    const bool isgas = ok && type == 0;
+    const double r = sqrt(r2);
+    const unsigned gasmask = __ballot_sync(FULL, isgas);
+    const unsigned below = gasmask & lt;
+    const int src = below ? 31 - __clz(below) : 0;
+    const double r_from = __shfl_sync(FULL, r, src);
+    const double r_seen = below ? r_from : r_stale;
+    if(gasmask) r_stale = __shfl_sync(FULL, r, 31 - __clz(gasmask));
+    if(!ok) return;
+    if(type == 5)
+      {
+	// blackhole.c:956-1003 (-DBH_MERGERS_WITHIN_H): merge when closer than the accretion boundary
+	if(r2 > 0)
+	  {
+	    const double accb = smbh ? par.InnerBoundary : par.SofteningBndry;
+	    if(!(r > accb) && mj <= mass) atomicMax(&claim[j], key);
+	  }
+      }
+    else if(type == 2)
+      {
+	// blackhole.c:1006-1035: dust on a bound orbit inside the accretion boundary
+	if(r2 > 0)
+	  {
+	    const double wx = A.vel[3 * (size_t) j] - vx, wy = A.vel[3 * (size_t) j + 1] - vy, wz = A.vel[3 * (size_t) j + 2] - vz;
+	    const double vrel = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(wx, wx), __dmul_rn(wy, wy)), __dmul_rn(wz, wz)));
+	    const double accb = smbh ? par.InnerBoundary : par.SinkBoundary;
+	    if(r < accb)
+	      {
+		const double etotal = __dadd_rn(__dmul_rn(vrel, vrel) / 2., -(mass / (r_seen + 1.e-20)));
+		if(etotal <= 0.) atomicMax(&claim[j], key);
+	      }
+	  }
+      }
+    else
+      {
+	// blackhole.c:1038-1160
+	const double hinv = 1 / h;
+	const double hinv3 = hinv * hinv * hinv;
+	const double wk = sg_kernel_wk(r * hinv, hinv3);
+	if(smbh && r < par.InnerBoundary) atomicMax(&A.swallow[j], id);	// :1068-1073
+	if(energy != 0.) atomicAdd(&A.inj[j], energy * mj * wk / rho);	// :1154
+      }
+  });
+}
+
+__global__ void k_sink_apply_claims(long long n, const unsigned long long *__restrict__ claim, int *__restrict__ swallow)
+{
+  const long long j = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(j >= n) return;
+  const unsigned long long c = claim[j];
+  if(c) swallow[j] = (int) (unsigned int) (c & 0xffffffffull);
+}
+
+// blackhole_evaluate_swallow (blackhole.c:1201-1349): one warp per active sink that is not being swallowed itself
+__global__ void __launch_bounds__(GL_BLOCK) k_sink_swallow(int ns, const int *__restrict__ sinks, SgTree T, const double *__restrict__ in_pos,
+							   const double *__restrict__ in_hsml, double *__restrict__ in_mass, double4 *__restrict__ s_pm,
+							   SinkArr A, double *__restrict__ sc, unsigned long long *__restrict__ counter)
+{
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(s >= ns) return;
+  const int i = sinks[s];
+  if(A.swallow[i] != 0) return;	// blackhole.c:508
+  const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
+  const double h = in_hsml[i];
+  const int id = A.id[i];
+  double am = 0, ad = 0, mx = 0, my = 0, mz = 0;
+  int ng = 0, nb = 0, nd = 0;
+  sg_march(T, lane, px, py, pz, h, (1u << 0) | (1u << 2) | (1u << 5), counter, [&](bool valid, int p, double, double, double, double) {
+    if(!valid) return;
+    const int j = T.perm[p];
+    if(A.swallow[j] != id) return;
+    const int type = T.s_type[p];
+    const double mj = in_mass[j];
+    am += mj;
+    mx += mj * A.vel[3 * (size_t) j];
+    my += mj * A.vel[3 * (size_t) j + 1];
+    mz += mj * A.vel[3 * (size_t) j + 2];
+    if(type == 5)
+      {
+	A.bh_mass[j] = 0;
+	nb++;
+      }
+    else if(type == 2)
+      {
+	ad += mj;
+	nd++;
+      }
+    else
+      ng++;
+    in_mass[j] = 0;
+    s_pm[p].w = 0;
+  });
+  am = sg_warp_sum(am); ad = sg_warp_sum(ad); mx = sg_warp_sum(mx); my = sg_warp_sum(my); mz = sg_warp_sum(mz);
+  ng = __reduce_add_sync(FULL, ng); nb = __reduce_add_sync(FULL, nb); nd = __reduce_add_sync(FULL, nd);
+  if(lane == 0)
+    {
+      double *q = sc + (size_t) s * SINK_SC;
+      q[3] = am; q[4] = ad; q[5] = mx; q[6] = my; q[7] = mz;
+      if(ng) atomicAdd(&counter[4], (unsigned long long) ng);
+      if(nb) atomicAdd(&counter[5], (unsigned long long) nb);
+      if(nd) atomicAdd(&counter[6], (unsigned long long) nd);
+    }
+}
+
+// blackhole.c:686-716: the sink takes mass and momentum of what it swallowed
+__global__ void k_sink_finish(int ns, const int *__restrict__ sinks, const int *__restrict__ inv, double *__restrict__ in_mass,
+			      double4 *__restrict__ s_pm, SinkArr A, const double *__restrict__ sc)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if(s >= ns) return;
+  const int i = sinks[s];
+  const double *q = sc + (size_t) s * SINK_SC;
+  const double am = q[3], ad = q[4];
+  if(am > 0)
+    {
+      const double m = in_mass[i];
+      for(int k = 0; k < 3; k++)
+	A.vel[3 * (size_t) i + k] = __dadd_rn(__dmul_rn(A.vel[3 * (size_t) i + k], m), q[5 + k]) / __dadd_rn(m, am);
+      const double mnew = __dadd_rn(m, am);
+      in_mass[i] = mnew;
+      s_pm[inv[i]].w = mnew;
+      // BH_accreted_BHMass and BH_accreted_DustMass are ONE union member (allvars.h:1261-1267); the dust mass is stored
+      // last (blackhole.c:1328-1329), so both sums below receive it (blackhole.c:699-701)
+      A.bh_mass[i] = __dadd_rn(A.bh_mass[i], ad);
+      A.dust_mass[i] = __dadd_rn(A.dust_mass[i], ad);
+      A.accdisc[i] = __dadd_rn(A.accdisc[i], am);
+      A.total_mass[i] = __dadd_rn(A.total_mass[i], am);
+    }
+}
+
+// ---- dust ----
+// dust_evaluate_density (dust.c:748-887): sum over the Type-2 neighbours inside the grain's own Hsml
+__global__ void __launch_bounds__(GL_BLOCK) k_dust_density(int nd, const int *__restrict__ dust, SgTree T, const double *__restrict__ in_pos,
+							   const double *__restrict__ in_hsml, const double *__restrict__ in_mass,
+							   double *__restrict__ out, unsigned long long *__restrict__ counter)
+{
+  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(d >= nd) return;
+  const int i = dust[d];
+  const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
+  const double h = in_hsml[i], mi = in_mass[i];
+  double sum = 0;
+  sg_march(T, lane, px, py, pz, h, 1u << 2, counter, [&](bool valid, int p, double, double, double, double r2) {
+    if(!valid || !(T.s_pm[p].w > 0)) return;
+    const double u = sqrt(r2) / h;
+    if(u < 1)
+      {
+	const double hinv = 1 / h;
+	sum += mi * sg_kernel_wk(u, hinv * hinv * hinv);
+      }
+  });
+  sum = sg_warp_sum(sum);
+  if(lane == 0) out[i] = sum;
+}
+
+struct DustArr
+{
+  double *vel;
+  const double *gravaccel, *rho, *entr, *gasvel, *d7;
+  double *d9;
+  const double *radius;
+  double *vcoll, *ddm, *newdrag, *dde;
+  double *entropy, *dragheat;
+};
+#define DUST_SC 6		// per-grain scratch: DeltaDustMomentum[3] / density, DeltaDragEnergy, density, spare
+
+// the grain's own update, dust_drag() dust.c:340-452: stopping time in the Epstein or Stokes regime, then the exact
+// solution of dv/dt = -(v - v_steady)/ts + g over the grain's time step
+__global__ void k_dust_own(int nd, const int *__restrict__ dust, const int *__restrict__ timebin, const double *__restrict__ in_pos,
+			   const double *__restrict__ in_mass, gl_subgrid_params par, double tbi, DustArr A, double *__restrict__ sc)
+{
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if(d >= nd) return;
+  const int i = dust[d];
+  const size_t i3 = 3 * (size_t) i;
+  for(int k = 0; k < 3; k++)
+    {
+      A.newdrag[i3 + k] = 0.;
+      A.ddm[i3 + k] = 0.;
+    }
+  double dde = 0.;
+  const double dt = sg_dt(timebin[i], tbi);
+  const double rho = A.rho[i];
+  const double soundspeed = sqrt(8. / SG_PI * A.entr[i] * pow(rho, SG_GAMMA_MINUS1));
+  const double v0 = A.vel[i3], v1 = A.vel[i3 + 1], v2 = A.vel[i3 + 2];
+  const double g0 = v0 - A.gasvel[i3], g1 = v1 - A.gasvel[i3 + 1], g2 = v2 - A.gasvel[i3 + 2];
+  const double delta_vel = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
+  const double d7 = A.d7[i];
+  double vcoll = A.vcoll[i];
+  if(d7 > 0.)
+    {
+      double w[3] = { 0, 0, 0 };
+      if(A.d9)
+	for(int k = 0; k < 3; k++)
+	  {
+	    w[k] = A.d9[i3 + k] / d7;
+	    A.d9[i3 + k] = w[k];
+	  }
+      const double delta_peb_vel = sqrt((v0 - w[0]) * (v0 - w[0]) + (v1 - w[1]) * (v1 - w[1]) + (v2 - w[2]) * (v2 - w[2]));
+      vcoll = delta_peb_vel * par.UnitVelocity_in_cm_per_s / 1.e2 + 1.e-30;
+    }
+  const double rho_dust = 3.;
+  const double a = A.radius[i];
+  const double mi = in_mass[i];
+  double ddm[3] = { 0, 0, 0 };
+  if(dt > 0)
+    {
+      const double lambda_h2 = par.MeanWeight * SG_PROTONMASS / (par.UnitDensity_in_cgs * rho) / 1.e-15 / par.UnitLength_in_cm;
+      const double rey = 6 * delta_vel * a / par.UnitLength_in_cm / (lambda_h2 * soundspeed);
+      double ts;
+      if(3. / 2 * lambda_h2 * par.UnitLength_in_cm >= a)
+	ts = 1. / (rho * soundspeed / (rho_dust * a) * par.UnitMass_in_g / par.UnitLength_in_cm / par.UnitLength_in_cm);	// Epstein
+      else if(delta_vel > 0)
+	{
+	  double C_drag = 0.44;	// Stokes
+	  if(rey < 800. && rey >= 1.) C_drag = 24. * pow(rey, -0.6);
+	  if(rey < 1.) C_drag = 24. / rey;
+	  ts = rho_dust * a / (rho * delta_vel) / par.UnitMass_in_g * par.UnitLength_in_cm * par.UnitLength_in_cm;
+	  ts *= 8. / 3. / C_drag;
+	}
+      else
+	ts = 0.66667 / (rho * soundspeed / (rho_dust * a)) / par.UnitMass_in_g * par.UnitLength_in_cm * a / lambda_h2;
+      const double ex = exp(-dt / ts), ex2 = exp(-2. * dt / ts);
+      double gacc2 = 0;
+      for(int k = 0; k < 3; k++)
+	{
+	  const double vold = A.vel[i3 + k], ga = A.gravaccel[i3 + k];
+	  const double vsteady = (vold * d7 + A.gasvel[i3 + k] * rho) / (d7 + rho + 1.e-30);
+	  const double vnew = vsteady + (vold - vsteady) * ex + ga * ts * (1. - ex);
+	  A.vel[i3 + k] = vnew;
+	  const double vnew_nog = vold + ga * dt;
+	  ddm[k] -= mi * (vnew_nog - vnew);
+	  dde += mi * (vnew - vsteady) * (vnew - vsteady) * (1. - ex2) / 2.;
+	  gacc2 += ga * ga;
+	}
+      vcoll = sqrt(gacc2) * ts * par.UnitVelocity_in_cm_per_s / 1.e2;
+      vcoll += 0.2;
+    }
+  for(int k = 0; k < 3; k++) A.ddm[i3 + k] = ddm[k];
+  A.dde[i] = dde;
+  A.vcoll[i] = vcoll;
+  double *q = sc + (size_t) d * DUST_SC;
+  q[0] = ddm[0]; q[1] = ddm[1]; q[2] = ddm[2]; q[3] = dde; q[4] = rho; q[5] = 0;
+}
+
+// dust_evaluate_select (dust.c:889-1029), search half: the gas inside the grain's Hsml.  COUNT: pairs per grain;
+// otherwise the pairs themselves, key = (gas P[] index, position of the grain in the active list), value = wk
+template <bool COUNT>
+__global__ void __launch_bounds__(GL_BLOCK) k_dust_pairs(int nd, const int *__restrict__ dust, SgTree T, const double *__restrict__ in_pos,
+							 const double *__restrict__ in_hsml, const double *__restrict__ sc, int *__restrict__ cnt,
+							 const long long *__restrict__ off, unsigned long long *__restrict__ keys, double *__restrict__ vals,
+							 unsigned long long *__restrict__ counter)
+{
+  const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(d >= nd) return;
+  const int i = dust[d];
+  if(!(sc[(size_t) d * DUST_SC + 4] > 0))	// dust.c:995: nothing is returned where the gas density at the grain is zero
+    {
+      if(COUNT && lane == 0) cnt[d] = 0;
+      return;
+    }
+  const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
+  const double h = in_hsml[i];
+  const unsigned lt = (1u << lane) - 1;
+  long long base = COUNT ? 0 : off[d];
+  int n = 0;
+  sg_march(T, lane, px, py, pz, h, 1u << 0, counter, [&](bool valid, int p, double, double, double, double r2) {
+    const double u = sqrt(r2) / h;
+    const bool hit = valid && T.s_pm[p].w > 0 && u < 1;
+    const unsigned m = __ballot_sync(FULL, hit);
+    if(!COUNT && hit)
+      {
+	const double hinv = 1 / h;
+	const long long at = base + n + __popc(m & lt);
+	keys[at] = ((unsigned long long) (unsigned int) T.perm[p] << 32) | (unsigned int) d;
+	vals[at] = sg_kernel_wk(u, hinv * hinv * hinv);
+      }
+    n += __popc(m);
+  });
+  if(COUNT && lane == 0) cnt[d] = n;
+}
+
+// dust.c:988-1007 per gas particle, contributions in the order the reference applies them
+__global__ void k_dust_apply(long long npairs, const unsigned long long *__restrict__ keys, const double *__restrict__ vals,
+			     const double *__restrict__ sc, const int *__restrict__ timebin, const double *__restrict__ in_mass,
+			     gl_subgrid_params par, double tbi, DustArr A)
+{
+  const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(t >= npairs) return;
+  const unsigned int j = (unsigned int) (keys[t] >> 32);
+  if(t > 0 && (unsigned int) (keys[t - 1] >> 32) == j) return;
+  const double dt = sg_dt(timebin[j], tbi);
+  if(!(dt > 0.)) return;
+  const double mj = in_mass[j];
+  double v0 = A.vel[3 * (size_t) j], v1 = A.vel[3 * (size_t) j + 1], v2 = A.vel[3 * (size_t) j + 2];
+  double S = A.entropy[j], heat = A.dragheat[j];
+  for(long long q = t; q < npairs && (unsigned int) (keys[q] >> 32) == j; q++)
+    {
+      const double *g = sc + (size_t) (unsigned int) (keys[q] & 0xffffffffull) * DUST_SC;
+      const double wk = vals[q], dens = g[4], ret = g[3];
+      v0 -= g[0] / dens * wk;
+      v1 -= g[1] / dens * wk;
+      v2 -= g[2] / dens * wk;
+      const double u_old = fmax(par.MinEgySpec, S / SG_GAMMA_MINUS1 * pow(dens, SG_GAMMA_MINUS1));
+      const double u_new = u_old + (ret * wk / dens);
+      double u_inc = u_new / u_old;
+      if(u_inc > 1.5) u_inc = 1.5;
+      S *= u_inc;
+      heat += 1.e-20 * (ret * wk / dens * mj / dt);
+    }
+  A.vel[3 * (size_t) j] = v0;
+  A.vel[3 * (size_t) j + 1] = v1;
+  A.vel[3 * (size_t) j + 2] = v2;
+  A.entropy[j] = S;
+  A.dragheat[j] = heat;
+}
+
+// ---- host side ----
+// a caller array on the device: itself when it already lives there, a staged copy otherwise
+template <class T> struct Staged
+{
+  T *dev = nullptr;
+  T *host = nullptr;
+  size_t cnt = 0;
+  bool owned = false, out = false;
+  int bind(gl_ctx *c, const T *src, size_t n, int where, bool in, bool writeback)
+  {
+    cnt = n;
+    out = writeback;
+    if(!src) return 0;
+    if(where)
+      {
+	dev = const_cast<T *>(src);
+	return 0;
+      }
+    host = const_cast<T *>(src);
+    owned = true;
+    GL_CUDA(c, cudaMalloc((void **) &dev, n * sizeof(T)));
+    if(in)
+      GL_CUDA(c, cudaMemcpyAsync(dev, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    else
+      GL_CUDA(c, cudaMemsetAsync(dev, 0, n * sizeof(T), c->stream));
+    return 0;
+  }
+  int finish(gl_ctx *c)
+  {
+    if(owned && out && dev) GL_CUDA(c, cudaMemcpyAsync(host, dev, cnt * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+  }
+  ~Staged()
+  {
+    if(owned && dev) cudaFree(dev);
+  }
+};
+
+int sg_ready(gl_ctx *c, const char *who)
+{
+  cudaSetDevice(c->device);
+  if(!c->have_par) return c->fail(std::string(who) + ": gl_set_params first");
+  if(!c->have_subgrid) return c->fail(std::string(who) + ": gl_set_subgrid_params first");
+  if(c->comm && c->comm->world > 1) return c->fail(std::string(who) + ": single rank only (no sub-grid loops over a locally-essential tree)");
+  if(!c->tree_valid || c->nentries <= 0) return c->fail(std::string(who) + ": no tree - call gl_gravity_tree / gl_density of this step first");
+  if(!c->in_timebin.p || !c->in_hsml.p) return c->fail(std::string(who) + ": time bins and Hsml must be loaded");
+  GL_CUDA(c, c->d_counter.ensure(16));
+  GL_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 16 * sizeof(unsigned long long), c->stream));
+  return 0;
+}
+SgTree sg_tree(gl_ctx *c)
+{
+  return SgTree{ (int) c->nentries, c->e_next.p, c->e_B.p, c->e_rng.p, c->s_pm.p, c->s_type.p, c->perm.p };
+}
+
+// the active particles of type `want`, in active-list order -> c->sg_list (device), *count
+int sg_targets(gl_ctx *c, const int *active, long long nactive, int want, long long *count)
+{
+  const long long n = c->n;
+  const long long m = active ? nactive : n;
+  *count = 0;
+  if(m <= 0) return 0;
+  GL_CUDA(c, c->sg_active.ensure((size_t) m));
+  GL_CUDA(c, c->sg_list.ensure((size_t) m + 1));
+  GL_CUDA(c, c->sg_flag.ensure((size_t) m));
+  if(active)
+    GL_CUDA(c, cudaMemcpyAsync(c->sg_active.p, active, m * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  else
+    {
+      k_sg_iota<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->sg_active.p);
+      GL_LAUNCH_COUNT(c);
+    }
+  int *bad = (int *) (c->d_counter.p + 8), *nsel = (int *) (c->d_counter.p + 9);
+  k_sg_flag_type<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->sg_active.p, c->in_type.p, n, want, c->sg_flag.p, bad);
+  GL_LAUNCH_COUNT(c);
+  size_t tmp = 0;
+  cub::DeviceSelect::Flagged(nullptr, tmp, c->sg_active.p, c->sg_flag.p, c->sg_list.p, nsel, (int) m, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, c->sg_active.p, c->sg_flag.p, c->sg_list.p, nsel, (int) m, c->stream));
+  GL_LAUNCH_COUNT(c);
+  unsigned long long hc[2];
+  GL_CUDA(c, cudaMemcpyAsync(hc, c->d_counter.p + 8, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if((int) hc[0] != 0) return c->fail("sub-grid loop: active list holds an index outside [0, n)");
+  *count = (int) hc[1];
+  return 0;
+}
+int sg_check(gl_ctx *c, const char *who)
+{
+  unsigned long long hc[8];
+  GL_CUDA(c, cudaMemcpyAsync(hc, c->d_counter.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if(hc[2]) return c->fail(std::string(who) + ": the search reached a cut cell of a multi-rank tree");
+  return 0;
+}
+}	// namespace
+
+extern "C" int gl_set_subgrid_params(gl_ctx *c, const gl_subgrid_params *p)
+{
+  if(!p) return c->fail("gl_set_subgrid_params: null");
+  if(!(p->UnitTime_in_s > 0) || !(p->UnitMass_in_g > 0) || !(p->UnitLength_in_cm > 0) || !(p->UnitEnergy_in_cgs > 0))
+    return c->fail("gl_set_subgrid_params: the unit system must be set (UnitTime_in_s, UnitMass_in_g, UnitLength_in_cm, UnitEnergy_in_cgs > 0)");
+  c->subgrid = *p;
+  c->have_subgrid = true;
+  return 0;
+}
+
+extern "C" int gl_blackhole_accretion(gl_ctx *c, const int *active, long long nactive, const gl_sink_state *st, int where,
+				      long long n_swallowed[3])
+{
+  if(sg_ready(c, "gl_blackhole_accretion")) return 1;
+  if(!st || !st->vel || !st->id || !st->swallow_id || !st->bh_mass || !st->bh_mdot || !st->accdisc_mass || !st->dust_mass || !st->total_mass ||
+     !st->injected_bh_energy)
+    return c->fail("gl_blackhole_accretion: vel, id, swallow_id, bh_mass, bh_mdot, accdisc_mass, dust_mass, total_mass, injected_bh_energy are required");
+  if(!st->sink_density && !c->o_sinkrho.p) return c->fail("gl_blackhole_accretion: no sink_density given and gl_density has not run");
+  const size_t n = (size_t) c->n;
+  long long ns = 0;
+  if(sg_targets(c, active, nactive, 5, &ns)) return 1;
+  if(n_swallowed) n_swallowed[0] = n_swallowed[1] = n_swallowed[2] = 0;
+  Staged<double> vel, bhm, bhd, acd, dum, tom, rho, inj;
+  Staged<int> id, swl;
+  if(vel.bind(c, st->vel, 3 * n, where, true, true) || id.bind(c, st->id, n, where, true, false) || swl.bind(c, st->swallow_id, n, where, true, true) ||
+     bhm.bind(c, st->bh_mass, n, where, true, true) || bhd.bind(c, st->bh_mdot, n, where, true, true) || acd.bind(c, st->accdisc_mass, n, where, true, true) ||
+     dum.bind(c, st->dust_mass, n, where, true, true) || tom.bind(c, st->total_mass, n, where, true, true) ||
+     rho.bind(c, st->sink_density, n, where, true, false) || inj.bind(c, st->injected_bh_energy, n, where, true, true))
+    return 1;
+  SinkArr A{ vel.dev, id.dev, swl.dev, bhm.dev, bhd.dev, acd.dev, dum.dev, tom.dev, st->sink_density ? rho.dev : c->o_sinkrho.p, inj.dev };
+  if(ns > 0)
+    {
+      GL_CUDA(c, c->sg_scratch.ensure((size_t) ns * SINK_SC));
+      GL_CUDA(c, c->sg_claim.ensure(n));
+      GL_CUDA(c, cudaMemsetAsync(c->sg_claim.p, 0, n * sizeof(unsigned long long), c->stream));
+      const SgTree T = sg_tree(c);
+      const double tbi = c->par.Timebase_interval;
+      const int wgrid = gl_grid(ns * 32, GL_BLOCK);
+      k_sink_mdot<<<gl_grid(ns, 128), 128, 0, c->stream>>>((int) ns, c->sg_list.p, c->in_timebin.p, c->in_mass.p, c->subgrid, tbi, A, c->sg_scratch.p);
+      k_sink_evaluate<<<wgrid, GL_BLOCK, 0, c->stream>>>((int) ns, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->in_mass.p, c->subgrid, A, c->sg_scratch.p,
+							  c->sg_claim.p, c->d_counter.p);
+      k_sink_apply_claims<<<gl_grid(n, 256), 256, 0, c->stream>>>((long long) n, c->sg_claim.p, A.swallow);
+      k_sink_swallow<<<wgrid, GL_BLOCK, 0, c->stream>>>((int) ns, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->in_mass.p, c->s_pm.p, A, c->sg_scratch.p,
+							 c->d_counter.p);
+      k_sink_finish<<<gl_grid(ns, 128), 128, 0, c->stream>>>((int) ns, c->sg_list.p, c->inv.p, c->in_mass.p, c->s_pm.p, A, c->sg_scratch.p);
+      c->kernel_launches += 5;
+      GL_CUDA(c, cudaGetLastError());
+    }
+  if(vel.finish(c) || swl.finish(c) || bhm.finish(c) || bhd.finish(c) || acd.finish(c) || dum.finish(c) || tom.finish(c) || inj.finish(c)) return 1;
+  if(st->mass)
+    GL_CUDA(c, cudaMemcpyAsync(st->mass, c->in_mass.p, n * sizeof(double), where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long hc[8];
+  GL_CUDA(c, cudaMemcpyAsync(hc, c->d_counter.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if(hc[2]) return c->fail("gl_blackhole_accretion: the search reached a cut cell of a multi-rank tree");
+  if(n_swallowed)
+    {
+      n_swallowed[0] = (long long) hc[4];
+      n_swallowed[1] = (long long) hc[5];
+      n_swallowed[2] = (long long) hc[6];
+    }
+  return 0;
+}
+
+extern "C" int gl_dust_density(gl_ctx *c, const int *active, long long nactive, double *dust_particle_density, int where)
+{
+  if(sg_ready(c, "gl_dust_density")) return 1;
+  if(!dust_particle_density) return c->fail("gl_dust_density: output array is required");
+  const size_t n = (size_t) c->n;
+  long long nd = 0;
+  if(sg_targets(c, active, nactive, 2, &nd)) return 1;
+  if(nd == 0) return 0;
+  Staged<double> out;
+  if(out.bind(c, dust_particle_density, n, where, true, true)) return 1;
+  k_dust_density<<<gl_grid(nd * 32, GL_BLOCK), GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, sg_tree(c), c->in_pos.p, c->in_hsml.p, c->in_mass.p,
+									  out.dev, c->d_counter.p);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaGetLastError());
+  if(out.finish(c)) return 1;
+  return sg_check(c, "gl_dust_density");
+}
+
+extern "C" int gl_dust_drag(gl_ctx *c, const int *active, long long nactive, const gl_dust_state *st, int where)
+{
+  if(sg_ready(c, "gl_dust_drag")) return 1;
+  if(!st || !st->vel || !st->dust_particle_density || !st->dust_radius || !st->dust_vcoll || !st->delta_dust_momentum || !st->new_drag_acc ||
+     !st->delta_drag_energy || !st->drag_heating)
+    return c->fail("gl_dust_drag: vel, dust_particle_density, dust_radius, dust_vcoll, delta_dust_momentum, new_drag_acc, delta_drag_energy, "
+		   "drag_heating are required");
+  if(!st->gravaccel && !c->o_acc.p) return c->fail("gl_dust_drag: no gravaccel given and gl_gravity_tree has not run");
+  if((!st->gas_density || !st->gas_entropy || !st->gas_vel) && !c->o_sinkrho.p)
+    return c->fail("gl_dust_drag: no gas_density / gas_entropy / gas_vel given and gl_density has not run");
+  if(!st->entropy && !c->in_entropy.p) return c->fail("gl_dust_drag: no entropy given and none loaded");
+  const size_t n = (size_t) c->n;
+  long long nd = 0;
+  if(sg_targets(c, active, nactive, 2, &nd)) return 1;
+  if(nd == 0) return 0;
+  Staged<double> vel, ga, rho, entr, gv, d7, d9, rad, vc, ddm, nda, dde, S, heat;
+  if(vel.bind(c, st->vel, 3 * n, where, true, true) || ga.bind(c, st->gravaccel, 3 * n, where, true, false) || rho.bind(c, st->gas_density, n, where, true, false) ||
+     entr.bind(c, st->gas_entropy, n, where, true, false) || gv.bind(c, st->gas_vel, 3 * n, where, true, false) ||
+     d7.bind(c, st->dust_particle_density, n, where, true, false) || d9.bind(c, st->dust_particle_velocity, 3 * n, where, true, true) ||
+     rad.bind(c, st->dust_radius, n, where, true, false) || vc.bind(c, st->dust_vcoll, n, where, true, true) ||
+     ddm.bind(c, st->delta_dust_momentum, 3 * n, where, true, true) || nda.bind(c, st->new_drag_acc, 3 * n, where, true, true) ||
+     dde.bind(c, st->delta_drag_energy, n, where, true, true) || S.bind(c, st->entropy, n, where, true, true) ||
+     heat.bind(c, st->drag_heating, n, where, true, true))
+    return 1;
+  DustArr A{ vel.dev, st->gravaccel ? ga.dev : c->o_acc.p, st->gas_density ? rho.dev : c->o_sinkrho.p, st->gas_entropy ? entr.dev : c->o_sinkentr.p,
+	     st->gas_vel ? gv.dev : c->o_sinkvel.p, d7.dev, d9.dev, rad.dev, vc.dev, ddm.dev, nda.dev, dde.dev, st->entropy ? S.dev : c->in_entropy.p, heat.dev };
+  const SgTree T = sg_tree(c);
+  const double tbi = c->par.Timebase_interval;
+  GL_CUDA(c, c->sg_scratch.ensure((size_t) nd * DUST_SC));
+  GL_CUDA(c, c->sg_cnt.ensure((size_t) nd + 1));
+  GL_CUDA(c, c->sg_off.ensure((size_t) nd + 1));
+  const int wgrid = gl_grid(nd * 32, GL_BLOCK);
+  k_dust_own<<<gl_grid(nd, 128), 128, 0, c->stream>>>((int) nd, c->sg_list.p, c->in_timebin.p, c->in_pos.p, c->in_mass.p, c->subgrid, tbi, A, c->sg_scratch.p);
+  k_dust_pairs<true><<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, c->sg_cnt.p, nullptr, nullptr,
+							 nullptr, c->d_counter.p);
+  c->kernel_launches += 2;
+  GL_CUDA(c, cudaMemsetAsync(c->sg_cnt.p + nd, 0, sizeof(int), c->stream));
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->sg_cnt.p, c->sg_off.p, (int) nd + 1, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->sg_cnt.p, c->sg_off.p, (int) nd + 1, c->stream));
+  GL_LAUNCH_COUNT(c);
+  long long npairs = 0;
+  GL_CUDA(c, cudaMemcpyAsync(&npairs, c->sg_off.p + nd, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if(npairs >= (1ll << 31)) return c->fail("gl_dust_drag: more than 2^31 (grain, gas) pairs");
+  if(npairs > 0)
+    {
+      GL_CUDA(c, c->sg_keys.ensure(2 * (size_t) npairs));
+      GL_CUDA(c, c->sg_vals.ensure(2 * (size_t) npairs));
+      unsigned long long *k0 = c->sg_keys.p, *k1 = c->sg_keys.p + npairs;
+      double *v0 = c->sg_vals.p, *v1 = c->sg_vals.p + npairs;
+      k_dust_pairs<false><<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, nullptr, c->sg_off.p, k0, v0,
+							      c->d_counter.p);
+      GL_LAUNCH_COUNT(c);
+      int top = 33;	// bits of the key that vary: 32 of the grain's position + those of the gas index
+      for(long long m = (long long) n; m > 1; m >>= 1) top++;
+      if(top > 64) top = 64;
+      tmp = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, v0, v1, (int) npairs, 0, top, c->stream);
+      GL_CUDA(c, c->cub_tmp.ensure(tmp));
+      GL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k0, k1, v0, v1, (int) npairs, 0, top, c->stream));
+      GL_LAUNCH_COUNT(c);
+      k_dust_apply<<<gl_grid(npairs, 256), 256, 0, c->stream>>>(npairs, k1, v1, c->sg_scratch.p, c->in_timebin.p, c->in_mass.p, c->subgrid, tbi, A);
+      GL_LAUNCH_COUNT(c);
+    }
+  GL_CUDA(c, cudaGetLastError());
+  if(vel.finish(c) || d9.finish(c) || vc.finish(c) || ddm.finish(c) || nda.finish(c) || dde.finish(c) || S.finish(c) || heat.finish(c)) return 1;
+  return sg_check(c, "gl_dust_drag");
+}

@@ -197,6 +197,87 @@ class ForcePath:
         self._chk(self._lib.gl_get_potential(self._ctx, L._ptr(pot), 0))
         return pot
 
+    # -- the sub-grid neighbour loops behind the force path (accel.c:189-196), on the tree of the step -------------------
+    def set_subgrid_params(self, **kw):
+        """All.SMBHmass, InnerBoundary, SinkBoundary, ViscousTimescale, BlackHoleFeedbackFactor, the unit system,
+        MeanWeight, MinEgySpec.  Units default to the shipped run's (Pd_N16e5_*.txt:86-88); derived units as begrun.c."""
+        q = dict(SMBHmass=0.5, InnerBoundary=2.0e-2, SinkBoundary=1.0e-4, SofteningBndry=self.params["Softening"][5],
+                 ViscousTimescale=3.15e9, BlackHoleFeedbackFactor=0.0, UnitLength_in_cm=1.496e15, UnitMass_in_g=1.989e33,
+                 UnitVelocity_in_cm_per_s=297837.66, MeanWeight=2.45, MinEgySpec=0.0)
+        q.update(kw)
+        q.setdefault("UnitTime_in_s", q["UnitLength_in_cm"] / q["UnitVelocity_in_cm_per_s"])
+        q.setdefault("UnitDensity_in_cgs", q["UnitMass_in_g"] / q["UnitLength_in_cm"] ** 3)
+        q.setdefault("UnitEnergy_in_cgs", q["UnitMass_in_g"] * q["UnitLength_in_cm"] ** 2 / q["UnitTime_in_s"] ** 2)
+        sp = L.GLSubgridParams()
+        for k, v in q.items():
+            if k == "xbh":
+                sp.xbh[:] = v
+            else:
+                setattr(sp, k, float(v))
+        self._chk(self._lib.gl_set_subgrid_params(self._ctx, C.byref(sp)))
+        self.subgrid = q
+
+    @staticmethod
+    def _active(active):
+        if active is None:
+            return None, 0, None
+        a = np.ascontiguousarray(active, dtype=np.int32)
+        return L._ptr(a), a.shape[0], a
+
+    def blackhole_accretion(self, S, active=None):
+        """blackhole.c:70.  S: dict of P[]-indexed arrays Vel, ID, SwallowID, BH_Mass, BH_Mdot, AccDisc_Mass, Dust_Mass,
+        Total_Mass, Injected_BH_Energy (float64 / int32, updated in place) and optionally SinkDensity.  Returns the new
+        P.Mass and the swallowed counts (gas, sinks, dust)."""
+        n = self.N
+        st = L.GLSinkState()
+        keep = []
+        for field, key, dt in (("vel", "Vel", np.float64), ("id", "ID", np.int32), ("swallow_id", "SwallowID", np.int32),
+                               ("bh_mass", "BH_Mass", np.float64), ("bh_mdot", "BH_Mdot", np.float64),
+                               ("accdisc_mass", "AccDisc_Mass", np.float64), ("dust_mass", "Dust_Mass", np.float64),
+                               ("total_mass", "Total_Mass", np.float64), ("injected_bh_energy", "Injected_BH_Energy", np.float64),
+                               ("sink_density", "SinkDensity", np.float64)):
+            a = S.get(key)
+            if a is None:
+                continue
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"] or a.shape[0] != n:
+                raise ValueError("blackhole_accretion: %s must be a contiguous %s array of %d rows" % (key, dt.__name__, n))
+            keep.append(a)
+            setattr(st, field, a.ctypes.data)
+        mass = np.zeros(n)
+        st.mass = mass.ctypes.data
+        ap, na, ak = self._active(active)
+        cnt = (C.c_longlong * 3)()
+        self._chk(self._lib.gl_blackhole_accretion(self._ctx, ap, na, C.byref(st), 0, cnt))
+        return mass, tuple(int(x) for x in cnt)
+
+    def dust_density(self, out, active=None):
+        """dust.c:60: P.d7.DUST_particle_density of the active dust grains, written into `out` (float64[n])."""
+        ap, na, ak = self._active(active)
+        self._chk(self._lib.gl_dust_density(self._ctx, ap, na, L._ptr(out), 0))
+        return out
+
+    def dust_drag(self, S, active=None):
+        """dust.c:263.  S: dict of P[]-indexed float64 arrays Vel, DustParticleDensity, DustRadius, DustVcoll,
+        DeltaDustMomentum, NewDragAcc, DeltaDragEnergy, DragHeating (updated in place), optionally GravAccel, GasDensity,
+        GasEntropy, GasVel, DustParticleVelocity, Entropy."""
+        n = self.N
+        st = L.GLDustState()
+        keep = []
+        for field, key in (("vel", "Vel"), ("gravaccel", "GravAccel"), ("gas_density", "GasDensity"), ("gas_entropy", "GasEntropy"),
+                           ("gas_vel", "GasVel"), ("dust_particle_density", "DustParticleDensity"),
+                           ("dust_particle_velocity", "DustParticleVelocity"), ("dust_radius", "DustRadius"), ("dust_vcoll", "DustVcoll"),
+                           ("delta_dust_momentum", "DeltaDustMomentum"), ("new_drag_acc", "NewDragAcc"),
+                           ("delta_drag_energy", "DeltaDragEnergy"), ("entropy", "Entropy"), ("drag_heating", "DragHeating")):
+            a = S.get(key)
+            if a is None:
+                continue
+            if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"] or a.shape[0] != n:
+                raise ValueError("dust_drag: %s must be a contiguous float64 array of %d rows" % (key, n))
+            keep.append(a)
+            setattr(st, field, a.ctypes.data)
+        ap, na, ak = self._active(active)
+        self._chk(self._lib.gl_dust_drag(self._ctx, ap, na, C.byref(st), 0))
+
     # device-resident variants used by bench.py's `value` leg (no result download)
     def gravity_tree_nocopy(self):
         self._chk(self._lib.gl_gravity_tree(self._ctx))

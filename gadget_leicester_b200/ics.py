@@ -87,6 +87,42 @@ def disc(n_gas, seed=42, with_sinks=True, m_disc=0.01, m_star=1.0, m_planet=4.77
     return _finish(pos, vel, mass, ptype, entropy)
 
 
+def disc_subgrid(n_gas, n_dust, seed=42, m_disc=0.01, m_star=1.0, m_planet=4.77e-3, r_in=0.008, r_out=1.0, aspect=0.05):
+    """The disc of config 0 arranged so that the sub-grid neighbour loops behind the force path have work
+    (blackhole.c:794/:1201, dust.c:748/:889): gas reaching inside InnerBoundary of the star, dust grains (Type 2) mixed
+    into the disc, around the star and around the planet, a small third sink next to the planet and a fourth next to
+    the star (mergers).  Gas first, then the other types in the order dust, sinks."""
+    g = _rng(seed)
+    ps = disc(n_gas, seed=seed, with_sinks=False, m_disc=m_disc, m_star=m_star, r_in=r_in, r_out=r_out, aspect=aspect)
+    rp = 0.5
+    # dust: 70 % through the disc, 15 % within 0.03 of the star, 15 % within 0.03 of the planet
+    na = int(0.7 * n_dust)
+    nb = (n_dust - na) // 2
+    nc = n_dust - na - nb
+    R = r_in + (r_out - r_in) * g.random(na)
+    phi = 2 * np.pi * g.random(na)
+    z = g.standard_normal(na) * 0.5 * aspect * R
+    dpos = [np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1)]
+    dpos.append(0.03 * (g.random((nb, 3)) - 0.5) * [1, 1, 0.3])
+    dpos.append(np.array([rp, 0, 0]) + 0.03 * (g.random((nc, 3)) - 0.5) * [1, 1, 0.3])
+    dpos = np.vstack(dpos)
+    Rd = np.maximum(np.hypot(dpos[:, 0], dpos[:, 1]), 1e-3)
+    vk = np.sqrt(m_star / Rd)
+    dvel = np.stack([-vk * dpos[:, 1] / Rd, vk * dpos[:, 0] / Rd, np.zeros(n_dust)], axis=1) * (0.9 + 0.2 * g.random((n_dust, 1)))
+    dmass = np.full(n_dust, 0.01 * m_disc / max(n_dust, 1))
+    # sinks: star, planet, a light sink 2e-5 from the planet, a light sink 0.01 from the star
+    spos = np.array([[0.0, 0.0, 0.0], [rp, 0.0, 0.0], [rp + 2.0e-5, 1.0e-5, 0.0], [0.01, 0.002, 0.0]])
+    svel = np.array([[0.0, 0.0, 0.0], [0.0, np.sqrt(m_star / rp), 0.0], [0.0, np.sqrt(m_star / rp), 0.0], [0.0, 3.0, 0.0]])
+    smass = np.array([m_star, m_planet, 1.0e-5, 2.0e-5])
+    ng = n_gas
+    pos = np.vstack([ps["pos"][:ng], dpos, spos])
+    vel = np.vstack([ps["vel"][:ng], dvel, svel])
+    mass = np.concatenate([ps["mass"][:ng], dmass, smass])
+    ptype = np.concatenate([np.zeros(ng), np.full(n_dust, 2), np.full(4, 5)]).astype(np.int32)
+    entropy = np.concatenate([ps["entropy"][:ng], np.zeros(n_dust + 4)])
+    return _finish(pos, vel, mass, ptype, entropy)
+
+
 def evrard(n_gas, seed=42, u0=0.05):
     """Config 1: Evrard sphere, M=1, R=1, rho ~ 1/r, at rest, u = 0.05."""
     g = _rng(seed)

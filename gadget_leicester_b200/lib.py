@@ -106,6 +106,25 @@ class GLTreeLayout(C.Structure):
         "e_vs", "e_vmax", "e_divVmax", "e_hmax", "e_Ti_lastkicked", "e_Flag")] + [("bitflags_value", C.c_uint)]
 
 
+class GLSubgridParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "SMBHmass", "InnerBoundary", "SinkBoundary", "SofteningBndry", "ViscousTimescale", "BlackHoleFeedbackFactor",
+        "UnitTime_in_s", "UnitMass_in_g", "UnitLength_in_cm", "UnitVelocity_in_cm_per_s", "UnitEnergy_in_cgs", "UnitDensity_in_cgs",
+        "MeanWeight", "MinEgySpec")] + [("xbh", C.c_double * 3)]
+
+
+class GLSinkState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "vel", "id", "swallow_id", "mass", "bh_mass", "bh_mdot", "accdisc_mass", "dust_mass", "total_mass", "sink_density",
+        "injected_bh_energy")]
+
+
+class GLDustState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "vel", "gravaccel", "gas_density", "gas_entropy", "gas_vel", "dust_particle_density", "dust_particle_velocity", "dust_radius",
+        "dust_vcoll", "delta_dust_momentum", "new_drag_acc", "delta_drag_energy", "entropy", "drag_heating")]
+
+
 # every symbol include/gl_b200.h declares (tests check that the .so exports all of them)
 EXPORTS = [
     "gl_create", "gl_destroy", "gl_last_error", "gl_set_params", "gl_stream", "gl_load_particles", "gl_set_oldacc",
@@ -119,6 +138,7 @@ EXPORTS = [
     "gl_snapshot_write", "gl_snapshot_read", "gl_snapshot_read_header", "gl_gadget_advance_and_find_timesteps", "gl_gadget_drift_list", "gl_gadget_peano_hilbert_order", "gl_domain_top_tree", "gl_gadget_domain_keys", "gl_gadget_costfactors", "gl_domain_split",
     "gl_comm_unique_id", "gl_comm_init", "gl_comm_local_group_create", "gl_comm_local_group_destroy", "gl_comm_init_local",
     "gl_comm_finalize", "gl_comm_set_options", "gl_get_let_stats",
+    "gl_set_subgrid_params", "gl_blackhole_accretion", "gl_dust_density", "gl_dust_drag",
 ]
 
 _lib = None
@@ -185,6 +205,10 @@ def load_library():
     lib.gl_comm_finalize.argtypes = [vp]
     lib.gl_comm_set_options.argtypes = [vp, C.c_int, C.c_double]
     lib.gl_reset_launch_count.argtypes = [vp]
+    lib.gl_set_subgrid_params.argtypes = [vp, C.POINTER(GLSubgridParams)]
+    lib.gl_blackhole_accretion.argtypes = [vp, vp, C.c_longlong, C.POINTER(GLSinkState), C.c_int, C.POINTER(C.c_longlong)]
+    lib.gl_dust_density.argtypes = [vp, vp, C.c_longlong, vp, C.c_int]
+    lib.gl_dust_drag.argtypes = [vp, vp, C.c_longlong, C.POINTER(GLDustState), C.c_int]
     lib.gl_reset_launch_count.restype = None
     lib.gl_gadget_bind.argtypes = [vp, C.POINTER(GLGadgetLayout)]
     lib.gl_gadget_pull.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong]

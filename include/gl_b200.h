@@ -323,6 +323,62 @@ typedef struct gl_tree_layout
 int gl_export_tree(gl_ctx * ctx, const gl_tree_layout * lay, void *nodes_base, void *extnodes_base, int *nextnode,
 		   int *father, long long MaxPart, long long max_nodes, int Ti_Current, long long *numnodes);
 
+/* ---- the sub-grid neighbour loops on the same tree -------------------------------------------
+ * What accel.c:189-196 calls right behind hydro_force(): sink accretion (blackhole_accretion blackhole.c:70 with its two
+ * neighbour loops blackhole_evaluate :794 and blackhole_evaluate_swallow :1201 over ngb_treefind_blackhole :1351) and the
+ * dust loops (dust_density dust.c:60 -> dust_evaluate_density :748; dust_drag :263 -> dust_evaluate_select :889 over
+ * ngb_treefind_dust_active :1235), under the shipped Makefile's switches.  They search the tree of the last build
+ * (gl_gravity_tree / gl_density of this step; positions, masses, types, Hsml and time bins are the loaded ones, Hsml
+ * the one gl_density left) - no second tree, no Nodes[] on the host.  Single rank.
+ * Arrays are indexed like P[] (n elements, gas first), `where` as in gl_load_particles; arrays marked in/out are updated
+ * in place.  `active`: the active list in FirstActiveParticle order (host pointer; NULL = every particle in index
+ * order) - the order decides which sink gets a particle two sinks claim (blackhole.c:991, :1030: the last one). */
+typedef struct gl_subgrid_params
+{
+  double SMBHmass, InnerBoundary, SinkBoundary, SofteningBndry;	/* All.* of the same names (.txt:167-171, :102) */
+  double ViscousTimescale, BlackHoleFeedbackFactor;	/* .txt:138, :126 */
+  double UnitTime_in_s, UnitMass_in_g, UnitLength_in_cm, UnitVelocity_in_cm_per_s, UnitEnergy_in_cgs, UnitDensity_in_cgs;
+  double MeanWeight, MinEgySpec;
+  double xbh[3];		/* All.xbh, ybh, zbh (FindQuasars, blackhole.c:1482) */
+} gl_subgrid_params;
+int gl_set_subgrid_params(gl_ctx * ctx, const gl_subgrid_params * par);
+
+typedef struct gl_sink_state
+{
+  double *vel;			/* P.Vel[3n], every type (NOT SphP.VelPred); in/out: sinks that accreted */
+  const int *id;		/* P.ID[n] */
+  int *swallow_id;		/* P.SwallowID[n]; in/out */
+  double *mass;			/* out (may be NULL): P.Mass[n] afterwards - swallowed particles 0, sinks grown.  The input
+				   is the loaded mass; the library's own copy is updated, so the dust loops see it */
+  double *bh_mass, *bh_mdot, *accdisc_mass, *dust_mass, *total_mass;	/* P.BH_Mass ... P.Total_Mass [n]; in/out at Type 5 */
+  const double *sink_density;	/* P.b1.BH_Density[n] at Type 5; NULL = what gl_density computed */
+  double *injected_bh_energy;	/* SphP.i.Injected_BH_Energy, indexed like P[] (n elements, gas entries used); in/out */
+} gl_sink_state;
+/* n_swallowed[3] <- N_gas_swallowed, N_BH_swallowed, N_dust_swallowed (blackhole.c:300, :648).
+ * Two statements of the reference are restated as written, not as probably meant: the bound-orbit test for dust near a
+ * sink uses the distance of the LAST GAS neighbour visited (blackhole.c:1024 reads `r`, set only at :1042), and
+ * BH_accreted_BHMass / BH_accreted_DustMass share one union (allvars.h:1261-1267), so a sink's BH_Mass grows by the
+ * accreted DUST mass (blackhole.c:699-701). */
+int gl_blackhole_accretion(gl_ctx * ctx, const int *active, long long nactive, const gl_sink_state * st, int where,
+			   long long n_swallowed[3]);
+
+/* dust_density(): P.d7.DUST_particle_density of the active Type-2 particles (other entries untouched) */
+int gl_dust_density(gl_ctx * ctx, const int *active, long long nactive, double *dust_particle_density, int where);
+
+typedef struct gl_dust_state
+{
+  double *vel;			/* P.Vel[3n]; in/out: active dust (drag) and the gas around it (momentum returned) */
+  const double *gravaccel;	/* P.g.GravAccel[3n]; NULL = the last gl_gravity_tree result */
+  const double *gas_density, *gas_entropy, *gas_vel;	/* P.d1/d2/d3 at Type 2 ([n], [n], [3n]); NULL = gl_density's */
+  const double *dust_particle_density;	/* P.d7 [n] (gl_dust_density) */
+  double *dust_particle_velocity;	/* P.d9 [3n]; in/out (divided by d7 in place, dust.c:362-366); NULL = zeros */
+  const double *dust_radius;	/* P.DustRadius[n], cm */
+  double *dust_vcoll, *delta_dust_momentum, *new_drag_acc, *delta_drag_energy;	/* out at active Type 2: [n], [3n], [3n], [n] */
+  double *entropy;		/* SphP.Entropy, indexed like P[]; in/out at gas; NULL = the loaded one, updated in the library */
+  double *drag_heating;		/* SphP.dh.DragHeating, indexed like P[]; in/out at gas */
+} gl_dust_state;
+int gl_dust_drag(gl_ctx * ctx, const int *active, long long nactive, const gl_dust_state * st, int where);
+
 /* ---- multi-GPU drop-in: every rank keeps its own P[] / SphP[] (its Peano-Hilbert segment), as every MPI rank of the
  * reference does; the sources are replicated with gl_load_particles_gathered --------------------------------------- */
 /* pack this rank's arrays into its all-gather block (layout of gl_load_particles_gathered, padded to m particles) and

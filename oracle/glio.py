@@ -20,6 +20,7 @@ P_TI_CURRENT = P_TIMEBASE_INTERVAL + 1
 P_BHNGBFACTOR = P_TI_CURRENT + 1
 P_PARTALLOC = P_BHNGBFACTOR + 1
 P_MINEGYSPEC = P_PARTALLOC + 1
+P_BHFEEDBACK, P_SMBHMASS, P_INNERBOUNDARY, P_SINKBOUNDARY, P_VISCOUSTIMESCALE, P_MEANWEIGHT = range(P_MINEGYSPEC + 1, P_MINEGYSPEC + 7)
 
 
 def pack_params(p):
@@ -39,6 +40,13 @@ def pack_params(p):
     par[P_BHNGBFACTOR] = p["BlackHoleNgbFactor"]
     par[P_PARTALLOC] = p.get("PartAllocFactor", 1.2)
     par[P_MINEGYSPEC] = p.get("MinEgySpec", 0.0)
+    # sub-grid loops (ops B / Y / Z): 0 = the shipped run's value
+    par[P_BHFEEDBACK] = p.get("BlackHoleFeedbackFactor", 0.0)
+    par[P_SMBHMASS] = p.get("SMBHmass", 0.0)
+    par[P_INNERBOUNDARY] = p.get("InnerBoundary", 0.0)
+    par[P_SINKBOUNDARY] = p.get("SinkBoundary", 0.0)
+    par[P_VISCOUSTIMESCALE] = p.get("ViscousTimescale", 0.0)
+    par[P_MEANWEIGHT] = p.get("MeanWeight", 0.0)
     return par
 
 

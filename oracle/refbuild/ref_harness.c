@@ -25,6 +25,11 @@
  *     K  Peano-Hilbert and Morton key of every particle (peano_and_morton_key, peano.c:335)
  *     A  compute_accelerations-order block:  R G D U H   (accel.c:61-106 without sub-grid physics)
  *     L  eight iterations of run()'s loop: find_next_sync_point_and_drift, domain_Decomposition, force path, kick
+ *     B  blackhole_accretion()               (accel.c:189, blackhole.c:70: sink accretion loops blackhole_evaluate :794 and
+ *        blackhole_evaluate_swallow :1201 over ngb_treefind_blackhole :1351) on the current tree; sink state is derived
+ *        from the input (see set_subgrid_state), everything read and written is dumped (pre / post)
+ *     Y  dust_density()                       (accel.c:192, dust.c:60 -> dust_evaluate_density :748)
+ *     Z  dust_drag()                          (accel.c:196, dust.c:263 -> dust_evaluate_select :889)
  *     V  advance_and_find_timesteps()         (timestep.c:29) at a synchronisation point of an individual-time-step
  *        state built from the input's time bins; dumps everything it reads and everything it leaves behind
  *   every op that computes dumps its outputs under the prefix "<k>_<op>_" with k the
@@ -78,7 +83,8 @@ static double now(void)
 #define NPAR 32
 static double par[NPAR];
 enum { P_THETA, P_ERRTOLFORCEACC, P_OPENCRIT, P_DESNUMNGB, P_MAXNGBDEV, P_ARTVISC, P_G, P_SOFT0,
-  P_MINGASHSMLFRAC = P_SOFT0 + 6, P_TIMEBASE_INTERVAL, P_TI_CURRENT, P_BHNGBFACTOR, P_PARTALLOC, P_MINEGYSPEC
+  P_MINGASHSMLFRAC = P_SOFT0 + 6, P_TIMEBASE_INTERVAL, P_TI_CURRENT, P_BHNGBFACTOR, P_PARTALLOC, P_MINEGYSPEC,
+  P_BHFEEDBACK, P_SMBHMASS, P_INNERBOUNDARY, P_SINKBOUNDARY, P_VISCOUSTIMESCALE, P_MEANWEIGHT
 };
 
 static void dump_particles_out(const char *prefix, int what)
@@ -188,6 +194,95 @@ static void dump_kick_state(const char *prefix, const char *tag)
   PUTI("TimeBinCount", TimeBinCount[i], TIMEBINS); PUTI("TimeBinCountSph", TimeBinCountSph[i], TIMEBINS);
   PUTI("FirstInTimeBin", FirstInTimeBin[i], TIMEBINS); PUTI("LastInTimeBin", LastInTimeBin[i], TIMEBINS);
   PUTI("TimeBinActive", TimeBinActive[i], TIMEBINS);
+#undef PUT3
+#undef PUT1
+#undef PUTI
+  free(d3); free(d1); free(i1);
+}
+
+
+/* ---- sub-grid neighbour loops: blackhole.c, dust.c ---- */
+/* run-time parameters of the shipped run (Pd_N16e5_*.txt:76,86-88,126,138,167-171) unless the input overrides them */
+static int subgrid_ready;
+static void set_subgrid_state(void)
+{
+  int i;
+  if(subgrid_ready) return;
+  subgrid_ready = 1;
+  All.UnitLength_in_cm = 1.496e15; All.UnitMass_in_g = 1.989e33; All.UnitVelocity_in_cm_per_s = 297837.66;
+  All.UnitTime_in_s = All.UnitLength_in_cm / All.UnitVelocity_in_cm_per_s;			/* begrun.c */
+  All.UnitDensity_in_cgs = All.UnitMass_in_g / pow(All.UnitLength_in_cm, 3);
+  All.UnitEnergy_in_cgs = All.UnitMass_in_g * pow(All.UnitLength_in_cm, 2) / pow(All.UnitTime_in_s, 2);
+  All.BlackHoleFeedbackFactor = par[P_BHFEEDBACK];
+  All.SMBHmass = par[P_SMBHMASS] > 0 ? par[P_SMBHMASS] : 0.5;
+  All.InnerBoundary = par[P_INNERBOUNDARY] > 0 ? par[P_INNERBOUNDARY] : 2.0e-2;
+  All.SinkBoundary = par[P_SINKBOUNDARY] > 0 ? par[P_SINKBOUNDARY] : 1.0e-4;
+  All.ViscousTimescale = par[P_VISCOUSTIMESCALE] > 0 ? par[P_VISCOUSTIMESCALE] : 3.15e9;
+  All.MeanWeight = par[P_MEANWEIGHT] > 0 ? par[P_MEANWEIGHT] : 2.45;
+  All.MinEgySpec = par[P_MINEGYSPEC];
+  All.xbh = All.ybh = All.zbh = 0;
+  FdBlackHoles = fopen("/dev/null", "w");
+  FdBlackHolesDetails = fopen("/dev/null", "w");
+  /* the per-particle state no input array carries: a fixed function of what the input does carry */
+  for(i = 0; i < NumPart; i++)
+    {
+      if(P[i].Type == 5)
+	{
+	  P[i].BH_Mass = 0.8 * P[i].Mass; P[i].AccDisc_Mass = 0.1 * P[i].Mass;
+	  P[i].Dust_Mass = 0.01 * P[i].Mass; P[i].Total_Mass = P[i].Mass;
+	}
+      if(P[i].Type == 2)
+	P[i].DustRadius = pow(10.0, (double) (P[i].ID % 7) - 3.0);	/* cm: both drag regimes of dust.c:340-366 */
+    }
+}
+static void dump_subgrid_params(const char *prefix)
+{
+  double q[16];
+  q[0] = All.SMBHmass; q[1] = All.InnerBoundary; q[2] = All.SinkBoundary; q[3] = All.SofteningBndry; q[4] = All.ViscousTimescale;
+  q[5] = All.UnitTime_in_s; q[6] = All.UnitMass_in_g; q[7] = All.UnitEnergy_in_cgs; q[8] = All.BlackHoleFeedbackFactor;
+  q[9] = All.Timebase_interval; q[10] = All.UnitLength_in_cm; q[11] = All.UnitDensity_in_cgs; q[12] = All.MeanWeight;
+  q[13] = All.MinEgySpec; q[14] = All.UnitVelocity_in_cm_per_s; q[15] = All.Time;
+  put(prefix, "params", 'd', 16, 1, q);
+}
+/* everything blackhole_accretion / dust_density / dust_drag read or write, in P[] order */
+static void dump_subgrid_state(const char *prefix, const char *tag)
+{
+  long long n = NumPart, ng = N_gas, i;
+  double *d3 = malloc(sizeof(double) * 3 * n), *d1 = malloc(sizeof(double) * n);
+  int *i1 = malloc(sizeof(int) * n);
+  char nm[40];
+#define PUT3(field, expr, cnt) do { for(i = 0; i < (cnt); i++) { d3[3 * i] = expr[0]; d3[3 * i + 1] = expr[1]; d3[3 * i + 2] = expr[2]; } \
+    snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'd', (cnt), 3, d3); } while(0)
+#define PUT1(field, expr, cnt) do { for(i = 0; i < (cnt); i++) d1[i] = expr; snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'd', (cnt), 1, d1); } while(0)
+#define PUTI(field, expr, cnt) do { for(i = 0; i < (cnt); i++) i1[i] = expr; snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'i', (cnt), 1, i1); } while(0)
+  PUTI("id", (int) P[i].ID, n); PUTI("Type", P[i].Type, n); PUTI("TimeBin", P[i].TimeBin, n); PUTI("SwallowID", P[i].SwallowID, n);
+  PUT3("Pos", P[i].Pos, n); PUT3("Vel", P[i].Vel, n); PUT3("GravAccel", P[i].g.GravAccel, n);
+  PUT1("Mass", P[i].Mass, n); PUT1("Hsml", P[i].Hsml, n);
+  PUT1("BH_Mass", P[i].BH_Mass, n); PUT1("BH_Mdot", P[i].BH_Mdot, n); PUT1("AccDisc_Mass", P[i].AccDisc_Mass, n);
+  PUT1("Dust_Mass", P[i].Dust_Mass, n); PUT1("Total_Mass", P[i].Total_Mass, n);
+  PUT1("SinkDensity", ((P[i].Type == 5) ? P[i].b1.BH_Density : (P[i].Type == 2 ? P[i].d1.DUST_Density : 0)), n);
+  PUT1("SinkEntropy", ((P[i].Type == 5) ? P[i].b2.BH_Entropy : (P[i].Type == 2 ? P[i].d2.DUST_Entropy : 0)), n);
+  for(i = 0; i < n; i++)
+    {
+      int k;
+      for(k = 0; k < 3; k++)
+	d3[3 * i + k] = (P[i].Type == 5) ? P[i].b3.BH_SurroundingGasVel[k] : (P[i].Type == 2 ? P[i].d3.DUST_SurroundingGasVel[k] : 0);
+    }
+  snprintf(nm, sizeof(nm), "%s_SinkGasVel", tag); put(prefix, nm, 'd', n, 3, d3);
+  PUT1("DustParticleDensity", (P[i].Type == 2 ? P[i].d7.DUST_particle_density : 0), n);
+  PUT1("DustRadius", P[i].DustRadius, n); PUT1("DustVcoll", P[i].DustVcoll, n);
+  PUT3("DeltaDustMomentum", P[i].DeltaDustMomentum, n); PUT3("NewDragAcc", P[i].NewDragAcc, n);
+  PUT1("DeltaDragEnergy", P[i].DeltaDragEnergy, n);
+  PUT1("Entropy", SphP[i].Entropy, ng); PUT1("Density", SphP[i].d.Density, ng);
+  PUT1("Injected_BH_Energy", SphP[i].i.Injected_BH_Energy, ng); PUT1("DragHeating", SphP[i].dh.DragHeating, ng);
+  {
+    int nact = 0, k = 0, *act;
+    for(i = FirstActiveParticle; i >= 0; i = NextActiveParticle[i]) nact++;
+    act = malloc(sizeof(int) * (nact + 1));
+    for(i = FirstActiveParticle; i >= 0; i = NextActiveParticle[i]) act[k++] = (int) i;
+    snprintf(nm, sizeof(nm), "%s_active", tag); put(prefix, nm, 'i', nact, 1, act);
+    free(act);
+  }
 #undef PUT3
 #undef PUT1
 #undef PUTI
@@ -601,6 +696,21 @@ int main(int argc, char **argv)
 		put(prefix, "loop", 'd', 4, 1, q);
 		dump_kick_state(prefix, "end");
 	      }
+	      break;
+	    case 'B':
+	      set_subgrid_state(); dump_subgrid_params(prefix); dump_subgrid_state(prefix, "pre");
+	      blackhole_accretion();
+	      dump_subgrid_state(prefix, "post");
+	      break;
+	    case 'Y':
+	      set_subgrid_state(); dump_subgrid_params(prefix); dump_subgrid_state(prefix, "pre");
+	      dust_density();
+	      dump_subgrid_state(prefix, "post");
+	      break;
+	    case 'Z':
+	      set_subgrid_state(); dump_subgrid_params(prefix); dump_subgrid_state(prefix, "pre");
+	      dust_drag();
+	      dump_subgrid_state(prefix, "post");
 	      break;
 	    case 'N': dump_nodes(prefix); break;
 	    case 'C': pair_counts(prefix); break;
