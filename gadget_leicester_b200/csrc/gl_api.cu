@@ -69,7 +69,7 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->o_hydropairs.release(); c->d_counter.release(); c->h_q.release(); c->h_r.release();
   c->tgt_gas_part.release(); c->tgt_part_flag.release();
   c->sg_active.release(); c->sg_list.release(); c->sg_cnt.release(); c->sg_flag.release(); c->sg_scratch.release(); c->sg_vals.release();
-  c->sg_claim.release(); c->sg_keys.release(); c->sg_off.release();
+  c->sg_claim.release(); c->sg_keys.release(); c->sg_off.release(); c->sg_pflag.release(); c->sg_slot.release(); c->sg_plist.release();
   c->e_rng.release(); c->n_child.release(); c->fat_p.release(); c->fat_i.release(); c->fat_state.release();
   c->fat_rec.release(); c->fat_tgt.release();
   if(c->pin) cudaFreeHost(c->pin);

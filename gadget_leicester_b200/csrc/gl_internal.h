@@ -209,7 +209,7 @@ struct gl_ctx
   // ---- sub-grid neighbour loops (gl_subgrid.cu) ----
   gl_subgrid_params subgrid{};
   bool have_subgrid = false;
-  DBuf<int> sg_active, sg_list, sg_cnt;
+  DBuf<int> sg_active, sg_list, sg_cnt, sg_pflag, sg_slot, sg_plist;
   DBuf<unsigned char> sg_flag;
   DBuf<double> sg_scratch, sg_vals;
   DBuf<unsigned long long> sg_claim, sg_keys;

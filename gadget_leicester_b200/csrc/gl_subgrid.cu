@@ -159,7 +159,10 @@ struct SinkArr
   double *bh_mass, *bh_mdot, *accdisc, *dust_mass, *total_mass;
   const double *sinkrho;
   double *inj;
+  const int *slot;		// compact mode: the arrays above hold only the particles the loops touch; slot[P index] = row
 };
+// row of particle j in the caller's arrays
+#define SL(A, j) ((A).slot ? (A).slot[j] : (j))
 #define SINK_SC 12		// per-sink scratch: dt, mdot, energy, acc_mass, acc_dust, mom[3], spare
 
 // blackhole.c:181-214: the accretion-disc reservoir feeds the sink on the viscous time scale
@@ -168,13 +171,13 @@ __global__ void k_sink_mdot(int ns, const int *__restrict__ sinks, const int *__
 {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if(s >= ns) return;
-  const int i = sinks[s];
+  const int i = sinks[s], is = SL(A, i);
   const double dt = sg_dt(timebin[i], tbi);
-  const double mdot = A.accdisc[i] / (dt + (par.ViscousTimescale / par.UnitTime_in_s));
+  const double mdot = A.accdisc[is] / (dt + (par.ViscousTimescale / par.UnitTime_in_s));
   const double dm = __dmul_rn(mdot, dt);
-  A.accdisc[i] = __dadd_rn(A.accdisc[i], -dm);
-  A.bh_mass[i] = __dadd_rn(A.bh_mass[i], dm);
-  A.bh_mdot[i] = mdot;
+  A.accdisc[is] = __dadd_rn(A.accdisc[is], -dm);
+  A.bh_mass[is] = __dadd_rn(A.bh_mass[is], dm);
+  A.bh_mdot[is] = mdot;
   // blackhole.c:1139-1150: thermal feedback of a planet-mass sink (the SMBH-class sink injects nothing)
   const double m = mass[i];
   double energy = 0.;
@@ -186,6 +189,42 @@ __global__ void k_sink_mdot(int ns, const int *__restrict__ sinks, const int *__
   q[1] = mdot;
   q[2] = energy;
   for(int k = 3; k < SINK_SC; k++) q[k] = 0;
+}
+
+// `r` of blackhole_evaluate is assigned for gas neighbours only (blackhole.c:1042) and read for dust neighbours (:1024).
+// In the compiled reference it lives in a stack slot that survives from one call to the next, so a sink that meets dust
+// before gas tests it with the distance of the last gas neighbour of the sink visited BEFORE it.  Reproduced: a first
+// pass finds every sink's last gas distance, one thread hands them down the active list.  (Before any sink has met gas
+// the reference reads whatever the stack held; the library uses 0 there.)
+__global__ void __launch_bounds__(GL_BLOCK) k_sink_last_gas_r(int ns, const int *__restrict__ sinks, SgTree T, const double *__restrict__ in_pos,
+							      const double *__restrict__ in_hsml, const double *__restrict__ in_mass,
+							      double *__restrict__ sc, unsigned long long *__restrict__ counter)
+{
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(s >= ns) return;
+  const int i = sinks[s];
+  double last = -1.;
+  if(in_mass[i] > 0)
+    {
+      const double h = in_hsml[i], h2 = __dmul_rn(h, h);
+      sg_march(T, lane, in_pos[3 * (size_t) i], in_pos[3 * (size_t) i + 1], in_pos[3 * (size_t) i + 2], h, 1u << 0, counter,
+	       [&](bool valid, int p, double, double, double, double r2) {
+		 const bool isgas = valid && T.s_pm[p].w > 0 && r2 < h2;
+		 const unsigned m = __ballot_sync(FULL, isgas);
+		 if(m) last = __shfl_sync(FULL, sqrt(r2), 31 - __clz(m));
+	       });
+    }
+  if(lane == 0) sc[(size_t) s * SINK_SC + 8] = last;
+}
+__global__ void k_sink_carry_r(int ns, double *__restrict__ sc)
+{
+  if(blockIdx.x || threadIdx.x) return;
+  double run = 0.;
+  for(int s = 0; s < ns; s++)
+    {
+      sc[(size_t) s * SINK_SC + 9] = run;
+      if(sc[(size_t) s * SINK_SC + 8] >= 0) run = sc[(size_t) s * SINK_SC + 8];
+    }
 }
 
 // blackhole_evaluate (blackhole.c:794-1199): one warp per active sink
@@ -201,14 +240,15 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sink_evaluate(int ns, const int *_
   if(!(mass > 0)) return;	// blackhole.c:903
   const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
   const double h = in_hsml[i], h2 = __dmul_rn(h, h);
-  const double vx = A.vel[3 * (size_t) i], vy = A.vel[3 * (size_t) i + 1], vz = A.vel[3 * (size_t) i + 2];
-  const int id = A.id[i];
-  const double rho = A.sinkrho[i];
+  const int is = SL(A, i);
+  const double vx = A.vel[3 * (size_t) is], vy = A.vel[3 * (size_t) is + 1], vz = A.vel[3 * (size_t) is + 2];
+  const int id = A.id[is];
+  const double rho = A.sinkrho[is];
   const double energy = sc[(size_t) s * SINK_SC + 2];
   const bool smbh = mass > 0.95 * par.SMBHmass;
   const unsigned long long key = ((unsigned long long) (s + 1) << 32) | (unsigned int) id;
   const unsigned lt = (1u << lane) - 1;
-  double r_stale = 0.;		// `r` of blackhole_evaluate: written for gas neighbours only (:1042), read for dust (:1024)
+  double r_stale = sc[(size_t) s * SINK_SC + 9];	// `r` of blackhole_evaluate as the previous sink left it (see k_sink_last_gas_r)
   sg_march(T, lane, px, py, pz, h, (1u << 0) | (1u << 2) | (1u << 5), counter, [&](bool valid, int p, double dx, double dy, double dz, double r2) {
     (void) dx; (void) dy; (void) dz;
     int type = -1, j = 0;
@@ -243,7 +283,8 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sink_evaluate(int ns, const int *_
 	// blackhole.c:1006-1035: dust on a bound orbit inside the accretion boundary
 	if(r2 > 0)
 	  {
-	    const double wx = A.vel[3 * (size_t) j] - vx, wy = A.vel[3 * (size_t) j + 1] - vy, wz = A.vel[3 * (size_t) j + 2] - vz;
+	    const size_t js = (size_t) SL(A, j);
+	    const double wx = A.vel[3 * js] - vx, wy = A.vel[3 * js + 1] - vy, wz = A.vel[3 * js + 2] - vz;
 	    const double vrel = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(wx, wx), __dmul_rn(wy, wy)), __dmul_rn(wz, wz)));
 	    const double accb = smbh ? par.InnerBoundary : par.SinkBoundary;
 	    if(r < accb)
@@ -259,18 +300,19 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sink_evaluate(int ns, const int *_
 	const double hinv = 1 / h;
 	const double hinv3 = hinv * hinv * hinv;
 	const double wk = sg_kernel_wk(r * hinv, hinv3);
-	if(smbh && r < par.InnerBoundary) atomicMax(&A.swallow[j], id);	// :1068-1073
-	if(energy != 0.) atomicAdd(&A.inj[j], energy * mj * wk / rho);	// :1154
+	const int js = SL(A, j);
+	if(smbh && r < par.InnerBoundary) atomicMax(&A.swallow[js], id);	// :1068-1073
+	if(energy != 0.) atomicAdd(&A.inj[js], energy * mj * wk / rho);	// :1154
       }
   });
 }
 
-__global__ void k_sink_apply_claims(long long n, const unsigned long long *__restrict__ claim, int *__restrict__ swallow)
+__global__ void k_sink_apply_claims(long long m, const int *__restrict__ plist, const unsigned long long *__restrict__ claim, int *__restrict__ swallow)
 {
-  const long long j = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(j >= n) return;
-  const unsigned long long c = claim[j];
-  if(c) swallow[j] = (int) (unsigned int) (c & 0xffffffffull);
+  const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(t >= m) return;
+  const unsigned long long c = claim[plist ? plist[t] : t];	// compact mode: row t holds particle plist[t]
+  if(c) swallow[t] = (int) (unsigned int) (c & 0xffffffffull);
 }
 
 // blackhole_evaluate_swallow (blackhole.c:1201-1349): one warp per active sink that is not being swallowed itself
@@ -280,26 +322,27 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sink_swallow(int ns, const int *__
 {
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if(s >= ns) return;
-  const int i = sinks[s];
-  if(A.swallow[i] != 0) return;	// blackhole.c:508
+  const int i = sinks[s], is = SL(A, i);
+  if(A.swallow[is] != 0) return;	// blackhole.c:508
   const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
   const double h = in_hsml[i];
-  const int id = A.id[i];
+  const int id = A.id[is];
   double am = 0, ad = 0, mx = 0, my = 0, mz = 0;
   int ng = 0, nb = 0, nd = 0;
   sg_march(T, lane, px, py, pz, h, (1u << 0) | (1u << 2) | (1u << 5), counter, [&](bool valid, int p, double, double, double, double) {
     if(!valid) return;
     const int j = T.perm[p];
-    if(A.swallow[j] != id) return;
+    const size_t js = (size_t) SL(A, j);
+    if(A.swallow[js] != id) return;
     const int type = T.s_type[p];
     const double mj = in_mass[j];
     am += mj;
-    mx += mj * A.vel[3 * (size_t) j];
-    my += mj * A.vel[3 * (size_t) j + 1];
-    mz += mj * A.vel[3 * (size_t) j + 2];
+    mx += mj * A.vel[3 * js];
+    my += mj * A.vel[3 * js + 1];
+    mz += mj * A.vel[3 * js + 2];
     if(type == 5)
       {
-	A.bh_mass[j] = 0;
+	A.bh_mass[js] = 0;
 	nb++;
       }
     else if(type == 2)
@@ -336,17 +379,18 @@ __global__ void k_sink_finish(int ns, const int *__restrict__ sinks, const int *
   if(am > 0)
     {
       const double m = in_mass[i];
+      const size_t is = (size_t) SL(A, i);
       for(int k = 0; k < 3; k++)
-	A.vel[3 * (size_t) i + k] = __dadd_rn(__dmul_rn(A.vel[3 * (size_t) i + k], m), q[5 + k]) / __dadd_rn(m, am);
+	A.vel[3 * is + k] = __dadd_rn(__dmul_rn(A.vel[3 * is + k], m), q[5 + k]) / __dadd_rn(m, am);
       const double mnew = __dadd_rn(m, am);
       in_mass[i] = mnew;
       s_pm[inv[i]].w = mnew;
       // BH_accreted_BHMass and BH_accreted_DustMass are ONE union member (allvars.h:1261-1267); the dust mass is stored
       // last (blackhole.c:1328-1329), so both sums below receive it (blackhole.c:699-701)
-      A.bh_mass[i] = __dadd_rn(A.bh_mass[i], ad);
-      A.dust_mass[i] = __dadd_rn(A.dust_mass[i], ad);
-      A.accdisc[i] = __dadd_rn(A.accdisc[i], am);
-      A.total_mass[i] = __dadd_rn(A.total_mass[i], am);
+      A.bh_mass[is] = __dadd_rn(A.bh_mass[is], ad);
+      A.dust_mass[is] = __dadd_rn(A.dust_mass[is], ad);
+      A.accdisc[is] = __dadd_rn(A.accdisc[is], am);
+      A.total_mass[is] = __dadd_rn(A.total_mass[is], am);
     }
 }
 
@@ -354,7 +398,7 @@ __global__ void k_sink_finish(int ns, const int *__restrict__ sinks, const int *
 // dust_evaluate_density (dust.c:748-887): sum over the Type-2 neighbours inside the grain's own Hsml
 __global__ void __launch_bounds__(GL_BLOCK) k_dust_density(int nd, const int *__restrict__ dust, SgTree T, const double *__restrict__ in_pos,
 							   const double *__restrict__ in_hsml, const double *__restrict__ in_mass,
-							   double *__restrict__ out, unsigned long long *__restrict__ counter)
+							   double *__restrict__ out, bool by_target, unsigned long long *__restrict__ counter)
 {
   const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if(d >= nd) return;
@@ -372,7 +416,7 @@ __global__ void __launch_bounds__(GL_BLOCK) k_dust_density(int nd, const int *__
       }
   });
   sum = sg_warp_sum(sum);
-  if(lane == 0) out[i] = sum;
+  if(lane == 0) out[by_target ? d : i] = sum;
 }
 
 struct DustArr
@@ -383,6 +427,7 @@ struct DustArr
   const double *radius;
   double *vcoll, *ddm, *newdrag, *dde;
   double *entropy, *dragheat;
+  const int *slot;
 };
 #define DUST_SC 6		// per-grain scratch: DeltaDustMomentum[3] / density, DeltaDragEnergy, density, spare
 
@@ -394,7 +439,7 @@ __global__ void k_dust_own(int nd, const int *__restrict__ dust, const int *__re
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if(d >= nd) return;
   const int i = dust[d];
-  const size_t i3 = 3 * (size_t) i;
+  const size_t ir = (size_t) SL(A, i), i3 = 3 * ir;
   for(int k = 0; k < 3; k++)
     {
       A.newdrag[i3 + k] = 0.;
@@ -402,13 +447,13 @@ __global__ void k_dust_own(int nd, const int *__restrict__ dust, const int *__re
     }
   double dde = 0.;
   const double dt = sg_dt(timebin[i], tbi);
-  const double rho = A.rho[i];
-  const double soundspeed = sqrt(8. / SG_PI * A.entr[i] * pow(rho, SG_GAMMA_MINUS1));
+  const double rho = A.rho[ir];
+  const double soundspeed = sqrt(8. / SG_PI * A.entr[ir] * pow(rho, SG_GAMMA_MINUS1));
   const double v0 = A.vel[i3], v1 = A.vel[i3 + 1], v2 = A.vel[i3 + 2];
   const double g0 = v0 - A.gasvel[i3], g1 = v1 - A.gasvel[i3 + 1], g2 = v2 - A.gasvel[i3 + 2];
   const double delta_vel = sqrt(g0 * g0 + g1 * g1 + g2 * g2);
-  const double d7 = A.d7[i];
-  double vcoll = A.vcoll[i];
+  const double d7 = A.d7[ir];
+  double vcoll = A.vcoll[ir];
   if(d7 > 0.)
     {
       double w[3] = { 0, 0, 0 };
@@ -422,7 +467,7 @@ __global__ void k_dust_own(int nd, const int *__restrict__ dust, const int *__re
       vcoll = delta_peb_vel * par.UnitVelocity_in_cm_per_s / 1.e2 + 1.e-30;
     }
   const double rho_dust = 3.;
-  const double a = A.radius[i];
+  const double a = A.radius[ir];
   const double mi = in_mass[i];
   double ddm[3] = { 0, 0, 0 };
   if(dt > 0)
@@ -459,8 +504,8 @@ __global__ void k_dust_own(int nd, const int *__restrict__ dust, const int *__re
       vcoll += 0.2;
     }
   for(int k = 0; k < 3; k++) A.ddm[i3 + k] = ddm[k];
-  A.dde[i] = dde;
-  A.vcoll[i] = vcoll;
+  A.dde[ir] = dde;
+  A.vcoll[ir] = vcoll;
   double *q = sc + (size_t) d * DUST_SC;
   q[0] = ddm[0]; q[1] = ddm[1]; q[2] = ddm[2]; q[3] = dde; q[4] = rho; q[5] = 0;
 }
@@ -514,8 +559,9 @@ __global__ void k_dust_apply(long long npairs, const unsigned long long *__restr
   const double dt = sg_dt(timebin[j], tbi);
   if(!(dt > 0.)) return;
   const double mj = in_mass[j];
-  double v0 = A.vel[3 * (size_t) j], v1 = A.vel[3 * (size_t) j + 1], v2 = A.vel[3 * (size_t) j + 2];
-  double S = A.entropy[j], heat = A.dragheat[j];
+  const size_t js = (size_t) SL(A, j);
+  double v0 = A.vel[3 * js], v1 = A.vel[3 * js + 1], v2 = A.vel[3 * js + 2];
+  double S = A.entropy[js], heat = A.dragheat[js];
   for(long long q = t; q < npairs && (unsigned int) (keys[q] >> 32) == j; q++)
     {
       const double *g = sc + (size_t) (unsigned int) (keys[q] & 0xffffffffull) * DUST_SC;
@@ -530,11 +576,11 @@ __global__ void k_dust_apply(long long npairs, const unsigned long long *__restr
       S *= u_inc;
       heat += 1.e-20 * (ret * wk / dens * mj / dt);
     }
-  A.vel[3 * (size_t) j] = v0;
-  A.vel[3 * (size_t) j + 1] = v1;
-  A.vel[3 * (size_t) j + 2] = v2;
-  A.entropy[j] = S;
-  A.dragheat[j] = heat;
+  A.vel[3 * js] = v0;
+  A.vel[3 * js + 1] = v1;
+  A.vel[3 * js + 2] = v2;
+  A.entropy[js] = S;
+  A.dragheat[js] = heat;
 }
 
 // ---- host side ----
@@ -624,12 +670,210 @@ int sg_targets(gl_ctx *c, const int *active, long long nactive, int want, long l
   *count = (int) hc[1];
   return 0;
 }
-int sg_check(gl_ctx *c, const char *who)
+
+// ---- compact mode (the AoS drop-in): only the particles the loops touch travel ----
+// mark the targets and everything on their neighbour lists
+__global__ void __launch_bounds__(GL_BLOCK) k_sg_mark(int nt, const int *__restrict__ targets, SgTree T, const double *__restrict__ in_pos,
+						      const double *__restrict__ in_hsml, unsigned typemask, int *__restrict__ flag,
+						      unsigned long long *__restrict__ counter)
+{
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if(t >= nt) return;
+  const int i = targets[t];
+  if(lane == 0) flag[i] = 1;
+  if(!typemask) return;
+  const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
+  sg_march(T, lane, px, py, pz, in_hsml[i], typemask, counter, [&](bool valid, int p, double, double, double, double) {
+    if(valid) flag[T.perm[p]] = 1;
+  });
+}
+__global__ void k_sg_list(long long n, const int *__restrict__ flag, const int *__restrict__ slot, int *__restrict__ plist)
+{
+  const long long j = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(j < n && flag[j]) plist[slot[j]] = (int) j;
+}
+__global__ void k_sg_gather(long long m, const int *__restrict__ plist, const double *__restrict__ src, double *__restrict__ dst, int ncomp)
+{
+  const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(t >= m * ncomp) return;
+  dst[t] = src[(size_t) plist[t / ncomp] * ncomp + t % ncomp];
+}
+
+// targets (c->sg_list, nt of them) + their neighbours of the given types -> c->sg_plist (ascending P[] indices, *m of
+// them, also copied to `host`) and c->sg_slot (P index -> row)
+int sg_compact(gl_ctx *c, long long nt, unsigned typemask, long long *m, std::vector<int> &host)
+{
+  const long long n = c->n;
+  GL_CUDA(c, c->sg_pflag.ensure((size_t) n + 1));
+  GL_CUDA(c, c->sg_slot.ensure((size_t) n + 1));
+  GL_CUDA(c, cudaMemsetAsync(c->sg_pflag.p, 0, ((size_t) n + 1) * sizeof(int), c->stream));
+  k_sg_mark<<<gl_grid(nt * 32, GL_BLOCK), GL_BLOCK, 0, c->stream>>>((int) nt, c->sg_list.p, sg_tree(c), c->in_pos.p, c->in_hsml.p, typemask, c->sg_pflag.p,
+								     c->d_counter.p);
+  GL_LAUNCH_COUNT(c);
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->sg_pflag.p, c->sg_slot.p, (int) n + 1, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->sg_pflag.p, c->sg_slot.p, (int) n + 1, c->stream));
+  GL_LAUNCH_COUNT(c);
+  int mm = 0;
+  GL_CUDA(c, cudaMemcpyAsync(&mm, c->sg_slot.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  *m = mm;
+  GL_CUDA(c, c->sg_plist.ensure((size_t) mm + 1));
+  k_sg_list<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->sg_pflag.p, c->sg_slot.p, c->sg_plist.p);
+  GL_LAUNCH_COUNT(c);
+  host.resize((size_t) mm);
+  GL_CUDA(c, cudaMemcpyAsync(host.data(), c->sg_plist.p, (size_t) mm * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// the five kernels of blackhole_accretion on ns sinks (c->sg_list); rows = A's arrays: all n particles (plist null) or
+// the m listed ones
+int sg_run_sinks(gl_ctx *c, long long ns, const SinkArr &A, const int *plist, long long m)
+{
+  if(ns <= 0) return 0;
+  const size_t n = (size_t) c->n;
+  GL_CUDA(c, c->sg_scratch.ensure((size_t) ns * SINK_SC));
+  GL_CUDA(c, c->sg_claim.ensure(n));
+  GL_CUDA(c, cudaMemsetAsync(c->sg_claim.p, 0, n * sizeof(unsigned long long), c->stream));
+  const SgTree T = sg_tree(c);
+  const double tbi = c->par.Timebase_interval;
+  const int wgrid = gl_grid(ns * 32, GL_BLOCK);
+  k_sink_mdot<<<gl_grid(ns, 128), 128, 0, c->stream>>>((int) ns, c->sg_list.p, c->in_timebin.p, c->in_mass.p, c->subgrid, tbi, A, c->sg_scratch.p);
+  k_sink_last_gas_r<<<wgrid, GL_BLOCK, 0, c->stream>>>((int) ns, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->in_mass.p, c->sg_scratch.p, c->d_counter.p);
+  k_sink_carry_r<<<1, 32, 0, c->stream>>>((int) ns, c->sg_scratch.p);
+  k_sink_evaluate<<<wgrid, GL_BLOCK, 0, c->stream>>>((int) ns, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->in_mass.p, c->subgrid, A, c->sg_scratch.p,
+						      c->sg_claim.p, c->d_counter.p);
+  k_sink_apply_claims<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, plist, c->sg_claim.p, A.swallow);
+  k_sink_swallow<<<wgrid, GL_BLOCK, 0, c->stream>>>((int) ns, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->in_mass.p, c->s_pm.p, A, c->sg_scratch.p,
+						     c->d_counter.p);
+  k_sink_finish<<<gl_grid(ns, 128), 128, 0, c->stream>>>((int) ns, c->sg_list.p, c->inv.p, c->in_mass.p, c->s_pm.p, A, c->sg_scratch.p);
+  c->kernel_launches += 7;
+  GL_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+// dust_drag on nd grains (c->sg_list)
+int sg_run_dust(gl_ctx *c, long long nd, const DustArr &A)
+{
+  if(nd <= 0) return 0;
+  const size_t n = (size_t) c->n;
+  const SgTree T = sg_tree(c);
+  const double tbi = c->par.Timebase_interval;
+  GL_CUDA(c, c->sg_scratch.ensure((size_t) nd * DUST_SC));
+  GL_CUDA(c, c->sg_cnt.ensure((size_t) nd + 1));
+  GL_CUDA(c, c->sg_off.ensure((size_t) nd + 1));
+  const int wgrid = gl_grid(nd * 32, GL_BLOCK);
+  k_dust_own<<<gl_grid(nd, 128), 128, 0, c->stream>>>((int) nd, c->sg_list.p, c->in_timebin.p, c->in_pos.p, c->in_mass.p, c->subgrid, tbi, A, c->sg_scratch.p);
+  k_dust_pairs<true><<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, c->sg_cnt.p, nullptr, nullptr,
+							 nullptr, c->d_counter.p);
+  c->kernel_launches += 2;
+  GL_CUDA(c, cudaMemsetAsync(c->sg_cnt.p + nd, 0, sizeof(int), c->stream));
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->sg_cnt.p, c->sg_off.p, (int) nd + 1, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->sg_cnt.p, c->sg_off.p, (int) nd + 1, c->stream));
+  GL_LAUNCH_COUNT(c);
+  long long npairs = 0;
+  GL_CUDA(c, cudaMemcpyAsync(&npairs, c->sg_off.p + nd, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if(npairs >= (1ll << 31)) return c->fail("gl_dust_drag: more than 2^31 (grain, gas) pairs");
+  if(npairs > 0)
+    {
+      GL_CUDA(c, c->sg_keys.ensure(2 * (size_t) npairs));
+      GL_CUDA(c, c->sg_vals.ensure(2 * (size_t) npairs));
+      unsigned long long *k0 = c->sg_keys.p, *k1 = c->sg_keys.p + npairs;
+      double *v0 = c->sg_vals.p, *v1 = c->sg_vals.p + npairs;
+      k_dust_pairs<false><<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, nullptr, c->sg_off.p, k0, v0,
+							      c->d_counter.p);
+      GL_LAUNCH_COUNT(c);
+      int top = 33;	// bits of the key that vary: 32 of the grain's position + those of the gas index
+      for(long long q = (long long) n; q > 1; q >>= 1) top++;
+      if(top > 64) top = 64;
+      tmp = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, v0, v1, (int) npairs, 0, top, c->stream);
+      GL_CUDA(c, c->cub_tmp.ensure(tmp));
+      GL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k0, k1, v0, v1, (int) npairs, 0, top, c->stream));
+      GL_LAUNCH_COUNT(c);
+      k_dust_apply<<<gl_grid(npairs, 256), 256, 0, c->stream>>>(npairs, k1, v1, c->sg_scratch.p, c->in_timebin.p, c->in_mass.p, c->subgrid, tbi, A);
+      GL_LAUNCH_COUNT(c);
+    }
+  GL_CUDA(c, cudaGetLastError());
+  return 0;
+}
+int sg_counts(gl_ctx *c, const char *who, long long n_swallowed[3])
 {
   unsigned long long hc[8];
   GL_CUDA(c, cudaMemcpyAsync(hc, c->d_counter.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   if(hc[2]) return c->fail(std::string(who) + ": the search reached a cut cell of a multi-rank tree");
+  if(n_swallowed)
+    {
+      n_swallowed[0] = (long long) hc[4];
+      n_swallowed[1] = (long long) hc[5];
+      n_swallowed[2] = (long long) hc[6];
+    }
+  return 0;
+}
+
+// compact device block of the AoS entry points: ncols columns of m doubles, staged through one host vector
+struct Block
+{
+  std::vector<double> h;
+  double *d = nullptr;
+  long long m = 0;
+  int ncols = 0;
+  int alloc(gl_ctx *c, long long rows, int cols)
+  {
+    m = rows;
+    ncols = cols;
+    h.assign((size_t) rows * cols, 0.0);
+    GL_CUDA(c, cudaMalloc((void **) &d, (size_t) (rows * cols + 1) * sizeof(double)));
+    return 0;
+  }
+  double *hcol(int k) { return h.data() + (size_t) k * m; }
+  double *dcol(int k) { return d + (size_t) k * m; }
+  int up(gl_ctx *c)
+  {
+    GL_CUDA(c, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+  }
+  int down(gl_ctx *c)
+  {
+    GL_CUDA(c, cudaMemcpyAsync(h.data(), d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  ~Block()
+  {
+    if(d) cudaFree(d);
+  }
+};
+int sg_gadget_ready(gl_ctx *c, const char *who, const gl_gadget_subgrid_layout *L2, const void *P)
+{
+  if(!c->have_lay) return c->fail(std::string(who) + ": gl_gadget_bind first");
+  if(!L2 || !P) return c->fail(std::string(who) + ": layout and P[] are required");
+  if(c->g_numpart != c->n || c->g_off != 0) return c->fail(std::string(who) + ": the context does not hold this P[] (gl_gadget_pull / gl_gadget_compute_accelerations first)");
+  return 0;
+}
+// the active particles of one type from the reference's own arrays, in active-list order -> c->sg_list
+int sg_gadget_targets(gl_ctx *c, const void *P, const int *active, long long nactive, int want, long long *count)
+{
+  const gl_gadget_layout &L = c->lay;
+  const long long n = c->n, m = active ? nactive : n;
+  std::vector<int> t;
+  for(long long k = 0; k < m; k++)
+    {
+      const long long i = active ? active[k] : k;
+      if(i < 0 || i >= n) return c->fail("sub-grid loop: active list holds an index outside [0, NumPart)");
+      if(*(const short *) ((const char *) P + i * L.p_stride + L.p_Type) == want) t.push_back((int) i);
+    }
+  *count = (long long) t.size();
+  if(t.empty()) return 0;
+  GL_CUDA(c, c->sg_list.ensure(t.size() + 1));
+  GL_CUDA(c, cudaMemcpyAsync(c->sg_list.p, t.data(), t.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
 }	// namespace
@@ -663,39 +907,12 @@ extern "C" int gl_blackhole_accretion(gl_ctx *c, const int *active, long long na
      dum.bind(c, st->dust_mass, n, where, true, true) || tom.bind(c, st->total_mass, n, where, true, true) ||
      rho.bind(c, st->sink_density, n, where, true, false) || inj.bind(c, st->injected_bh_energy, n, where, true, true))
     return 1;
-  SinkArr A{ vel.dev, id.dev, swl.dev, bhm.dev, bhd.dev, acd.dev, dum.dev, tom.dev, st->sink_density ? rho.dev : c->o_sinkrho.p, inj.dev };
-  if(ns > 0)
-    {
-      GL_CUDA(c, c->sg_scratch.ensure((size_t) ns * SINK_SC));
-      GL_CUDA(c, c->sg_claim.ensure(n));
-      GL_CUDA(c, cudaMemsetAsync(c->sg_claim.p, 0, n * sizeof(unsigned long long), c->stream));
-      const SgTree T = sg_tree(c);
-      const double tbi = c->par.Timebase_interval;
-      const int wgrid = gl_grid(ns * 32, GL_BLOCK);
-      k_sink_mdot<<<gl_grid(ns, 128), 128, 0, c->stream>>>((int) ns, c->sg_list.p, c->in_timebin.p, c->in_mass.p, c->subgrid, tbi, A, c->sg_scratch.p);
-      k_sink_evaluate<<<wgrid, GL_BLOCK, 0, c->stream>>>((int) ns, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->in_mass.p, c->subgrid, A, c->sg_scratch.p,
-							  c->sg_claim.p, c->d_counter.p);
-      k_sink_apply_claims<<<gl_grid(n, 256), 256, 0, c->stream>>>((long long) n, c->sg_claim.p, A.swallow);
-      k_sink_swallow<<<wgrid, GL_BLOCK, 0, c->stream>>>((int) ns, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->in_mass.p, c->s_pm.p, A, c->sg_scratch.p,
-							 c->d_counter.p);
-      k_sink_finish<<<gl_grid(ns, 128), 128, 0, c->stream>>>((int) ns, c->sg_list.p, c->inv.p, c->in_mass.p, c->s_pm.p, A, c->sg_scratch.p);
-      c->kernel_launches += 5;
-      GL_CUDA(c, cudaGetLastError());
-    }
+  SinkArr A{ vel.dev, id.dev, swl.dev, bhm.dev, bhd.dev, acd.dev, dum.dev, tom.dev, st->sink_density ? rho.dev : c->o_sinkrho.p, inj.dev, nullptr };
+  if(sg_run_sinks(c, ns, A, nullptr, (long long) n)) return 1;
   if(vel.finish(c) || swl.finish(c) || bhm.finish(c) || bhd.finish(c) || acd.finish(c) || dum.finish(c) || tom.finish(c) || inj.finish(c)) return 1;
   if(st->mass)
     GL_CUDA(c, cudaMemcpyAsync(st->mass, c->in_mass.p, n * sizeof(double), where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
-  unsigned long long hc[8];
-  GL_CUDA(c, cudaMemcpyAsync(hc, c->d_counter.p, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
-  GL_CUDA(c, cudaStreamSynchronize(c->stream));
-  if(hc[2]) return c->fail("gl_blackhole_accretion: the search reached a cut cell of a multi-rank tree");
-  if(n_swallowed)
-    {
-      n_swallowed[0] = (long long) hc[4];
-      n_swallowed[1] = (long long) hc[5];
-      n_swallowed[2] = (long long) hc[6];
-    }
-  return 0;
+  return sg_counts(c, "gl_blackhole_accretion", n_swallowed);
 }
 
 extern "C" int gl_dust_density(gl_ctx *c, const int *active, long long nactive, double *dust_particle_density, int where)
@@ -709,11 +926,11 @@ extern "C" int gl_dust_density(gl_ctx *c, const int *active, long long nactive, 
   Staged<double> out;
   if(out.bind(c, dust_particle_density, n, where, true, true)) return 1;
   k_dust_density<<<gl_grid(nd * 32, GL_BLOCK), GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, sg_tree(c), c->in_pos.p, c->in_hsml.p, c->in_mass.p,
-									  out.dev, c->d_counter.p);
+									  out.dev, false, c->d_counter.p);
   GL_LAUNCH_COUNT(c);
   GL_CUDA(c, cudaGetLastError());
   if(out.finish(c)) return 1;
-  return sg_check(c, "gl_dust_density");
+  return sg_counts(c, "gl_dust_density", nullptr);
 }
 
 extern "C" int gl_dust_drag(gl_ctx *c, const int *active, long long nactive, const gl_dust_state *st, int where)
@@ -741,48 +958,181 @@ extern "C" int gl_dust_drag(gl_ctx *c, const int *active, long long nactive, con
      heat.bind(c, st->drag_heating, n, where, true, true))
     return 1;
   DustArr A{ vel.dev, st->gravaccel ? ga.dev : c->o_acc.p, st->gas_density ? rho.dev : c->o_sinkrho.p, st->gas_entropy ? entr.dev : c->o_sinkentr.p,
-	     st->gas_vel ? gv.dev : c->o_sinkvel.p, d7.dev, d9.dev, rad.dev, vc.dev, ddm.dev, nda.dev, dde.dev, st->entropy ? S.dev : c->in_entropy.p, heat.dev };
-  const SgTree T = sg_tree(c);
-  const double tbi = c->par.Timebase_interval;
-  GL_CUDA(c, c->sg_scratch.ensure((size_t) nd * DUST_SC));
-  GL_CUDA(c, c->sg_cnt.ensure((size_t) nd + 1));
-  GL_CUDA(c, c->sg_off.ensure((size_t) nd + 1));
-  const int wgrid = gl_grid(nd * 32, GL_BLOCK);
-  k_dust_own<<<gl_grid(nd, 128), 128, 0, c->stream>>>((int) nd, c->sg_list.p, c->in_timebin.p, c->in_pos.p, c->in_mass.p, c->subgrid, tbi, A, c->sg_scratch.p);
-  k_dust_pairs<true><<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, c->sg_cnt.p, nullptr, nullptr,
-							 nullptr, c->d_counter.p);
-  c->kernel_launches += 2;
-  GL_CUDA(c, cudaMemsetAsync(c->sg_cnt.p + nd, 0, sizeof(int), c->stream));
-  size_t tmp = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->sg_cnt.p, c->sg_off.p, (int) nd + 1, c->stream);
-  GL_CUDA(c, c->cub_tmp.ensure(tmp));
-  GL_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->sg_cnt.p, c->sg_off.p, (int) nd + 1, c->stream));
-  GL_LAUNCH_COUNT(c);
-  long long npairs = 0;
-  GL_CUDA(c, cudaMemcpyAsync(&npairs, c->sg_off.p + nd, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  GL_CUDA(c, cudaStreamSynchronize(c->stream));
-  if(npairs >= (1ll << 31)) return c->fail("gl_dust_drag: more than 2^31 (grain, gas) pairs");
-  if(npairs > 0)
-    {
-      GL_CUDA(c, c->sg_keys.ensure(2 * (size_t) npairs));
-      GL_CUDA(c, c->sg_vals.ensure(2 * (size_t) npairs));
-      unsigned long long *k0 = c->sg_keys.p, *k1 = c->sg_keys.p + npairs;
-      double *v0 = c->sg_vals.p, *v1 = c->sg_vals.p + npairs;
-      k_dust_pairs<false><<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, nullptr, c->sg_off.p, k0, v0,
-							      c->d_counter.p);
-      GL_LAUNCH_COUNT(c);
-      int top = 33;	// bits of the key that vary: 32 of the grain's position + those of the gas index
-      for(long long m = (long long) n; m > 1; m >>= 1) top++;
-      if(top > 64) top = 64;
-      tmp = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, v0, v1, (int) npairs, 0, top, c->stream);
-      GL_CUDA(c, c->cub_tmp.ensure(tmp));
-      GL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k0, k1, v0, v1, (int) npairs, 0, top, c->stream));
-      GL_LAUNCH_COUNT(c);
-      k_dust_apply<<<gl_grid(npairs, 256), 256, 0, c->stream>>>(npairs, k1, v1, c->sg_scratch.p, c->in_timebin.p, c->in_mass.p, c->subgrid, tbi, A);
-      GL_LAUNCH_COUNT(c);
-    }
-  GL_CUDA(c, cudaGetLastError());
+	     st->gas_vel ? gv.dev : c->o_sinkvel.p, d7.dev, d9.dev, rad.dev, vc.dev, ddm.dev, nda.dev, dde.dev, st->entropy ? S.dev : c->in_entropy.p, heat.dev,
+	     nullptr };
+  if(sg_run_dust(c, nd, A)) return 1;
   if(vel.finish(c) || d9.finish(c) || vc.finish(c) || ddm.finish(c) || nda.finish(c) || dde.finish(c) || S.finish(c) || heat.finish(c)) return 1;
-  return sg_check(c, "gl_dust_drag");
+  return sg_counts(c, "gl_dust_drag", nullptr);
+}
+
+// ---- the same three on the reference's own P[] / SphP[] (drop-in layer) -------------------------------------------
+// Only the particles the loops touch cross PCIe: the search runs first and returns their indices, the host gathers their
+// fields from the structs, the kernels run on those rows, the host scatters what changed.
+#define PFIELD(i, off) ((char *) P + (i) * L.p_stride + (off))
+#define SFIELD(i, off) ((char *) SphP + (i) * L.sph_stride + (off))
+
+extern "C" int gl_gadget_blackhole_accretion(gl_ctx *c, const gl_gadget_subgrid_layout *L2, void *P, void *SphP, const int *active, long long nactive,
+					     long long n_swallowed[3])
+{
+  if(sg_ready(c, "gl_gadget_blackhole_accretion") || sg_gadget_ready(c, "gl_gadget_blackhole_accretion", L2, P)) return 1;
+  const gl_gadget_layout &L = c->lay;
+  const long long ngas = c->g_ngas;
+  if(n_swallowed) n_swallowed[0] = n_swallowed[1] = n_swallowed[2] = 0;
+  long long ns = 0, m = 0;
+  if(sg_gadget_targets(c, P, active, nactive, 5, &ns)) return 1;
+  if(ns == 0) return 0;
+  std::vector<int> rows;
+  if(sg_compact(c, ns, (1u << 0) | (1u << 2) | (1u << 5), &m, rows)) return 1;
+  enum { VX, VY, VZ, BHM, BHD, ACD, DUM, TOM, RHO, INJ, MASS, NCOL };
+  Block B;
+  if(B.alloc(c, m, NCOL)) return 1;
+  std::vector<int> ids((size_t) 2 * m);
+  // the kernels address vel as 3 doubles per row: columns VX..VZ are laid out row-major in one 3*m block
+  double *hv = B.hcol(VX);
+  for(long long t = 0; t < m; t++)
+    {
+      const long long i = rows[t];
+      const double *v = (const double *) PFIELD(i, L.p_Vel);
+      hv[3 * t] = v[0]; hv[3 * t + 1] = v[1]; hv[3 * t + 2] = v[2];
+      ids[t] = *(const int *) PFIELD(i, L2->p_ID);
+      ids[m + t] = *(const int *) PFIELD(i, L.p_SwallowID);
+      const int type = *(const short *) PFIELD(i, L.p_Type);
+      if(type == 5)
+	{
+	  B.hcol(BHM)[t] = *(const double *) PFIELD(i, L2->p_BH_Mass);
+	  B.hcol(BHD)[t] = *(const double *) PFIELD(i, L2->p_BH_Mdot);
+	  B.hcol(ACD)[t] = *(const double *) PFIELD(i, L2->p_AccDisc_Mass);
+	  B.hcol(DUM)[t] = *(const double *) PFIELD(i, L2->p_Dust_Mass);
+	  B.hcol(TOM)[t] = *(const double *) PFIELD(i, L2->p_Total_Mass);
+	  B.hcol(RHO)[t] = *(const double *) PFIELD(i, L.p_SinkDensity);
+	}
+      // injected energy: the device accumulates from zero, the host adds the sum to SphP (same sum, one rounding more)
+    }
+  int *dids = nullptr;
+  GL_CUDA(c, cudaMalloc((void **) &dids, (size_t) (2 * m + 1) * sizeof(int)));
+  struct Free { int *p; ~Free() { cudaFree(p); } } fr{ dids };
+  GL_CUDA(c, cudaMemcpyAsync(dids, ids.data(), (size_t) 2 * m * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if(B.up(c)) return 1;
+  SinkArr A{ B.dcol(VX), dids, dids + m, B.dcol(BHM), B.dcol(BHD), B.dcol(ACD), B.dcol(DUM), B.dcol(TOM), B.dcol(RHO), B.dcol(INJ), c->sg_slot.p };
+  if(sg_run_sinks(c, ns, A, c->sg_plist.p, m)) return 1;
+  k_sg_gather<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, c->sg_plist.p, c->in_mass.p, B.dcol(MASS), 1);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaMemcpyAsync(ids.data(), dids, (size_t) 2 * m * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if(B.down(c)) return 1;
+  for(long long t = 0; t < m; t++)
+    {
+      const long long i = rows[t];
+      const int type = *(const short *) PFIELD(i, L.p_Type);
+      *(int *) PFIELD(i, L.p_SwallowID) = ids[m + t];
+      *(double *) PFIELD(i, L.p_Mass) = B.hcol(MASS)[t];
+      if(type == 5)
+	{
+	  double *v = (double *) PFIELD(i, L.p_Vel);
+	  v[0] = hv[3 * t]; v[1] = hv[3 * t + 1]; v[2] = hv[3 * t + 2];
+	  *(double *) PFIELD(i, L2->p_BH_Mass) = B.hcol(BHM)[t];
+	  *(double *) PFIELD(i, L2->p_BH_Mdot) = B.hcol(BHD)[t];
+	  *(double *) PFIELD(i, L2->p_AccDisc_Mass) = B.hcol(ACD)[t];
+	  *(double *) PFIELD(i, L2->p_Dust_Mass) = B.hcol(DUM)[t];
+	  *(double *) PFIELD(i, L2->p_Total_Mass) = B.hcol(TOM)[t];
+	}
+      else if(type == 0 && i < ngas && SphP && B.hcol(INJ)[t] != 0)
+	*(double *) SFIELD(i, L2->s_Injected_BH_Energy) += B.hcol(INJ)[t];
+    }
+  return sg_counts(c, "gl_gadget_blackhole_accretion", n_swallowed);
+}
+
+extern "C" int gl_gadget_dust_density(gl_ctx *c, const gl_gadget_subgrid_layout *L2, void *P, const int *active, long long nactive)
+{
+  if(sg_ready(c, "gl_gadget_dust_density") || sg_gadget_ready(c, "gl_gadget_dust_density", L2, P)) return 1;
+  const gl_gadget_layout &L = c->lay;
+  long long nd = 0;
+  if(sg_gadget_targets(c, P, active, nactive, 2, &nd)) return 1;
+  if(nd == 0) return 0;
+  Block B;
+  if(B.alloc(c, nd, 1)) return 1;
+  k_dust_density<<<gl_grid(nd * 32, GL_BLOCK), GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, sg_tree(c), c->in_pos.p, c->in_hsml.p, c->in_mass.p,
+									  B.d, true, c->d_counter.p);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaGetLastError());
+  std::vector<int> t((size_t) nd);
+  GL_CUDA(c, cudaMemcpyAsync(t.data(), c->sg_list.p, (size_t) nd * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if(B.down(c)) return 1;
+  for(long long d = 0; d < nd; d++) *(double *) PFIELD((long long) t[d], L2->p_DustParticleDensity) = B.h[d];
+  return sg_counts(c, "gl_gadget_dust_density", nullptr);
+}
+
+extern "C" int gl_gadget_dust_drag(gl_ctx *c, const gl_gadget_subgrid_layout *L2, void *P, void *SphP, const int *active, long long nactive)
+{
+  if(sg_ready(c, "gl_gadget_dust_drag") || sg_gadget_ready(c, "gl_gadget_dust_drag", L2, P)) return 1;
+  if(!SphP) return c->fail("gl_gadget_dust_drag: SphP[] is required");
+  const gl_gadget_layout &L = c->lay;
+  const long long ngas = c->g_ngas;
+  long long nd = 0, m = 0;
+  if(sg_gadget_targets(c, P, active, nactive, 2, &nd)) return 1;
+  if(nd == 0) return 0;
+  std::vector<int> rows;
+  if(sg_compact(c, nd, 1u << 0, &m, rows)) return 1;
+  // 3-vectors first (row-major blocks of 3*m), then the scalars
+  enum { VEL = 0, GACC = 3, GVEL = 6, D9 = 9, DDM = 12, NDA = 15, RHO = 18, ENTR, D7, RAD, VC, DDE, S, HEAT, NCOL };
+  Block B;
+  if(B.alloc(c, m, NCOL)) return 1;
+  for(long long t = 0; t < m; t++)
+    {
+      const long long i = rows[t];
+      const int type = *(const short *) PFIELD(i, L.p_Type);
+      const double *v = (const double *) PFIELD(i, L.p_Vel);
+      for(int k = 0; k < 3; k++) B.hcol(VEL)[3 * t + k] = v[k];
+      if(type == 2)
+	{
+	  const double *g = (const double *) PFIELD(i, L.p_GravAccel), *gv = (const double *) PFIELD(i, L.p_DustGasVel),
+	    *w = (const double *) PFIELD(i, L2->p_DustParticleVelocity);
+	  for(int k = 0; k < 3; k++)
+	    {
+	      B.hcol(GACC)[3 * t + k] = g[k];
+	      B.hcol(GVEL)[3 * t + k] = gv[k];
+	      B.hcol(D9)[3 * t + k] = w[k];
+	    }
+	  B.hcol(RHO)[t] = *(const double *) PFIELD(i, L.p_DustDensity);
+	  B.hcol(ENTR)[t] = *(const double *) PFIELD(i, L.p_DustEntropy);
+	  B.hcol(D7)[t] = *(const double *) PFIELD(i, L2->p_DustParticleDensity);
+	  B.hcol(RAD)[t] = *(const double *) PFIELD(i, L2->p_DustRadius);
+	  B.hcol(VC)[t] = *(const double *) PFIELD(i, L2->p_DustVcoll);
+	}
+      else if(type == 0 && i < ngas)
+	{
+	  B.hcol(S)[t] = *(const double *) SFIELD(i, L.s_Entropy);
+	  B.hcol(HEAT)[t] = *(const double *) SFIELD(i, L2->s_DragHeating);
+	}
+    }
+  if(B.up(c)) return 1;
+  DustArr A{ B.dcol(VEL), B.dcol(GACC), B.dcol(RHO), B.dcol(ENTR), B.dcol(GVEL), B.dcol(D7), B.dcol(D9), B.dcol(RAD), B.dcol(VC), B.dcol(DDM), B.dcol(NDA),
+	     B.dcol(DDE), B.dcol(S), B.dcol(HEAT), c->sg_slot.p };
+  if(sg_run_dust(c, nd, A)) return 1;
+  if(B.down(c)) return 1;
+  for(long long t = 0; t < m; t++)
+    {
+      const long long i = rows[t];
+      const int type = *(const short *) PFIELD(i, L.p_Type);
+      double *v = (double *) PFIELD(i, L.p_Vel);
+      for(int k = 0; k < 3; k++) v[k] = B.hcol(VEL)[3 * t + k];
+      if(type == 2)
+	{
+	  double *w = (double *) PFIELD(i, L2->p_DustParticleVelocity), *dm = (double *) PFIELD(i, L2->p_DeltaDustMomentum),
+	    *na = (double *) PFIELD(i, L2->p_NewDragAcc);
+	  for(int k = 0; k < 3; k++)
+	    {
+	      w[k] = B.hcol(D9)[3 * t + k];
+	      dm[k] = B.hcol(DDM)[3 * t + k];
+	      na[k] = B.hcol(NDA)[3 * t + k];
+	    }
+	  *(double *) PFIELD(i, L2->p_DustVcoll) = B.hcol(VC)[t];
+	  *(double *) PFIELD(i, L2->p_DeltaDragEnergy) = B.hcol(DDE)[t];
+	}
+      else if(type == 0 && i < ngas)
+	{
+	  *(double *) SFIELD(i, L.s_Entropy) = B.hcol(S)[t];
+	  *(double *) SFIELD(i, L2->s_DragHeating) = B.hcol(HEAT)[t];
+	}
+    }
+  return sg_counts(c, "gl_gadget_dust_drag", nullptr);
 }

@@ -356,7 +356,8 @@ typedef struct gl_sink_state
 } gl_sink_state;
 /* n_swallowed[3] <- N_gas_swallowed, N_BH_swallowed, N_dust_swallowed (blackhole.c:300, :648).
  * Two statements of the reference are restated as written, not as probably meant: the bound-orbit test for dust near a
- * sink uses the distance of the LAST GAS neighbour visited (blackhole.c:1024 reads `r`, set only at :1042), and
+ * sink uses the distance of the LAST GAS neighbour visited - of this sink or, before it has met gas, of the sinks visited
+ * before it (blackhole.c:1024 reads `r`, set only at :1042; the compiled reference keeps it in a stack slot across calls) -, and
  * BH_accreted_BHMass / BH_accreted_DustMass share one union (allvars.h:1261-1267), so a sink's BH_Mass grows by the
  * accreted DUST mass (blackhole.c:699-701). */
 int gl_blackhole_accretion(gl_ctx * ctx, const int *active, long long nactive, const gl_sink_state * st, int where,
@@ -371,13 +372,29 @@ typedef struct gl_dust_state
   const double *gravaccel;	/* P.g.GravAccel[3n]; NULL = the last gl_gravity_tree result */
   const double *gas_density, *gas_entropy, *gas_vel;	/* P.d1/d2/d3 at Type 2 ([n], [n], [3n]); NULL = gl_density's */
   const double *dust_particle_density;	/* P.d7 [n] (gl_dust_density) */
-  double *dust_particle_velocity;	/* P.d9 [3n]; in/out (divided by d7 in place, dust.c:362-366); NULL = zeros */
+  double *dust_particle_velocity;	/* P.d9 [3n]; in/out (divided by d7 in place, dust.c:368-370); NULL = zeros */
   const double *dust_radius;	/* P.DustRadius[n], cm */
   double *dust_vcoll, *delta_dust_momentum, *new_drag_acc, *delta_drag_energy;	/* out at active Type 2: [n], [3n], [3n], [n] */
   double *entropy;		/* SphP.Entropy, indexed like P[]; in/out at gas; NULL = the loaded one, updated in the library */
   double *drag_heating;		/* SphP.dh.DragHeating, indexed like P[]; in/out at gas */
 } gl_dust_state;
 int gl_dust_drag(gl_ctx * ctx, const int *active, long long nactive, const gl_dust_state * st, int where);
+
+/* The same three on the reference's own P[] / SphP[] (after gl_gadget_compute_accelerations / gl_gadget_pull of this
+ * step; gl_gadget_bind supplies the offsets the force path already uses, this struct the ones only these loops need).
+ * The search runs first and returns the indices of the particles the loops touch; only their fields are gathered from
+ * the structs, sent, updated and scattered back - for the two sinks of the shipped run a few hundred particles. */
+typedef struct gl_gadget_subgrid_layout
+{
+  int p_ID, p_BH_Mass, p_BH_Mdot, p_AccDisc_Mass, p_Dust_Mass, p_Total_Mass;
+  int p_DustParticleDensity, p_DustParticleVelocity;	/* d7, d9 */
+  int p_DustRadius, p_DustVcoll, p_DeltaDustMomentum, p_NewDragAcc, p_DeltaDragEnergy;
+  int s_Injected_BH_Energy, s_DragHeating;
+} gl_gadget_subgrid_layout;
+int gl_gadget_blackhole_accretion(gl_ctx * ctx, const gl_gadget_subgrid_layout * lay, void *P, void *SphP, const int *active,
+				  long long nactive, long long n_swallowed[3]);
+int gl_gadget_dust_density(gl_ctx * ctx, const gl_gadget_subgrid_layout * lay, void *P, const int *active, long long nactive);
+int gl_gadget_dust_drag(gl_ctx * ctx, const gl_gadget_subgrid_layout * lay, void *P, void *SphP, const int *active, long long nactive);
 
 /* ---- multi-GPU drop-in: every rank keeps its own P[] / SphP[] (its Peano-Hilbert segment), as every MPI rank of the
  * reference does; the sources are replicated with gl_load_particles_gathered --------------------------------------- */

@@ -9,6 +9,11 @@
  *     void force_update_hmax(void)       forcetree.h / forcetree.c:1661   (only when GL_TAKE_OVER_HMAX is set)
  *     void hydro_force(void)             proto.h / hydra.c:145
  *     void compute_accelerations(int)    proto.h / accel.c:27             (only when GL_TAKE_OVER_ACCEL is set)
+ * the sub-grid neighbour loops that follow it in accel.c:189-196, on the GPU tree of the step (-DGL_SUBGRID, one rank;
+ * remove blackhole_accretion / dust_density / dust_drag from blackhole.c / dust.c or rename them with objcopy):
+ *     void blackhole_accretion(void)     proto.h / blackhole.c:70
+ *     void dust_density(void)            proto.h / dust.c:60
+ *     void dust_drag(void)               proto.h / dust.c:263
  * and, each behind its own switch, the host-side neighbours of the path (no GPU involved):
  *     void advance_and_find_timesteps(void)   proto.h / timestep.c:29     -DGL_TIMESTEP
  *     void peano_hilbert_order(void)          proto.h / peano.c:25        -DGL_PEANO_ORDER
@@ -26,6 +31,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <stddef.h>
+#include <math.h>
 #include <mpi.h>
 #include "allvars.h"
 #include "proto.h"
@@ -322,6 +328,135 @@ void gl_compute_force_path(int mode)
   TreeReconstructFlag = 0;
 }
 #endif
+
+#ifdef GL_SUBGRID
+/* ---- blackhole_accretion() / dust_density() / dust_drag() (accel.c:189-196) on the tree the force path built ----------
+ * The reference walks Nodes[] on the host for these (blackhole.c:1351, dust.c:1235); here the searches run on the device
+ * copy of the same step, and only the particles they touch are gathered from P[] / SphP[] and written back.  Kept from
+ * the reference: the log lines, the swallow counters, the TimeBin_BH_* sums and the blackholes.txt record.  One rank. */
+static gl_gadget_subgrid_layout GL_SubLayout;
+static void gl_subgrid_setup(const char *where)
+{
+  gl_subgrid_params sp;
+  gl_gadget_subgrid_layout *S = &GL_SubLayout;
+  if(NTask != 1)
+    {
+      printf("libgl_b200 glue: %s() on the GPU tree handles NTask == 1 only (NTask = %d)\n", where, NTask);
+      fflush(stdout);
+      endrun(8802);
+    }
+  if(All.ComovingIntegrationOn) gl_fail("comoving sub-grid loops");
+  gl_ensure_loaded();
+  S->p_ID = offsetof(struct particle_data, ID);
+  S->p_BH_Mass = offsetof(struct particle_data, BH_Mass);
+  S->p_BH_Mdot = offsetof(struct particle_data, BH_Mdot);
+  S->p_AccDisc_Mass = offsetof(struct particle_data, AccDisc_Mass);
+  S->p_Dust_Mass = offsetof(struct particle_data, Dust_Mass);
+  S->p_Total_Mass = offsetof(struct particle_data, Total_Mass);
+  S->p_DustParticleDensity = offsetof(struct particle_data, d7.DUST_particle_density);
+  S->p_DustParticleVelocity = offsetof(struct particle_data, d9.DUST_particle_velocity);
+  S->p_DustRadius = offsetof(struct particle_data, DustRadius);
+  S->p_DustVcoll = offsetof(struct particle_data, DustVcoll);
+  S->p_DeltaDustMomentum = offsetof(struct particle_data, DeltaDustMomentum);
+  S->p_NewDragAcc = offsetof(struct particle_data, NewDragAcc);
+  S->p_DeltaDragEnergy = offsetof(struct particle_data, DeltaDragEnergy);
+  S->s_Injected_BH_Energy = offsetof(struct sph_particle_data, i.Injected_BH_Energy);
+  S->s_DragHeating = offsetof(struct sph_particle_data, dh.DragHeating);
+  sp.SMBHmass = All.SMBHmass; sp.InnerBoundary = All.InnerBoundary; sp.SinkBoundary = All.SinkBoundary;
+  sp.SofteningBndry = All.SofteningBndry; sp.ViscousTimescale = All.ViscousTimescale;
+  sp.BlackHoleFeedbackFactor = All.BlackHoleFeedbackFactor;
+  sp.UnitTime_in_s = All.UnitTime_in_s; sp.UnitMass_in_g = All.UnitMass_in_g; sp.UnitLength_in_cm = All.UnitLength_in_cm;
+  sp.UnitVelocity_in_cm_per_s = All.UnitVelocity_in_cm_per_s; sp.UnitEnergy_in_cgs = All.UnitEnergy_in_cgs;
+  sp.UnitDensity_in_cgs = All.UnitDensity_in_cgs; sp.MeanWeight = All.MeanWeight; sp.MinEgySpec = All.MinEgySpec;
+  sp.xbh[0] = All.xbh; sp.xbh[1] = All.ybh; sp.xbh[2] = All.zbh;
+  gl_sync_params();
+  if(gl_set_subgrid_params(GL, &sp)) gl_fail("gl_set_subgrid_params");
+}
+static int *gl_active_array(int *n)
+{
+  int i, k = 0, *idx;
+  for(i = FirstActiveParticle; i >= 0; i = NextActiveParticle[i]) k++;
+  idx = (int *) malloc(sizeof(int) * (k > 0 ? k : 1));
+  for(i = FirstActiveParticle, k = 0; i >= 0; i = NextActiveParticle[i]) idx[k++] = i;
+  *n = k;
+  return idx;
+}
+
+void blackhole_accretion(void)
+{
+  int n, bin, nact, *act;
+  long long sw[3];
+  double mass_holes = 0, mass_real = 0, mdot = 0;
+  printf("Beginning black-hole accretion\n");
+  fflush(stdout);
+  CPU_Step[CPU_MISC] += measure_time();
+  gl_subgrid_setup("blackhole_accretion");
+  for(n = 0; n < TIMEBINS; n++)
+    if(TimeBinActive[n])
+      {
+	TimeBin_BH_mass[n] = 0;
+	TimeBin_BH_dynamicalmass[n] = 0;
+	TimeBin_BH_Mdot[n] = 0;
+      }
+  act = gl_active_array(&nact);
+  if(gl_gadget_blackhole_accretion(GL, &GL_SubLayout, P, SphP, act, nact, sw)) gl_fail("gl_gadget_blackhole_accretion");
+  printf("Accretion done: %d gas particles swallowed, %d BH particles swallowed, %d Dust particles swallowed\n", (int) sw[0], (int) sw[1],
+	 (int) sw[2]);
+  fflush(stdout);
+  for(n = 0; n < nact; n++)
+    if(P[act[n]].Type == 5)
+      {
+	bin = P[act[n]].TimeBin;
+	TimeBin_BH_mass[bin] += P[act[n]].BH_Mass;
+	TimeBin_BH_dynamicalmass[bin] += P[act[n]].Mass;
+	TimeBin_BH_Mdot[bin] += P[act[n]].BH_Mdot;
+      }
+  free(act);
+  for(bin = 0; bin < TIMEBINS; bin++)
+    if(TimeBinCount[bin])
+      {
+	mass_holes += TimeBin_BH_mass[bin];
+	mass_real += TimeBin_BH_dynamicalmass[bin];
+	mdot += TimeBin_BH_Mdot[bin];
+      }
+  if(FdBlackHoles)
+    {
+      /* blackhole.c:744-760 */
+      double mdot_in_msun_per_year = mdot * (All.UnitMass_in_g / SOLAR_MASS) / (All.UnitTime_in_s / SEC_PER_YEAR);
+      double total_mdoteddington = 0;
+      if(mass_holes > 0)
+	total_mdoteddington = mdot / ((4 * M_PI * GRAVITY * C * PROTONMASS / (0.1 * C * C * THOMPSON)) * mass_holes * All.UnitTime_in_s);
+      fprintf(FdBlackHoles, "%g %d %g %g %g %g %g\n", All.Time, All.TotBHs, mass_holes, mdot, mdot_in_msun_per_year, mass_real,
+	      total_mdoteddington);
+      fflush(FdBlackHoles);
+    }
+  CPU_Step[CPU_BLACKHOLES] += measure_time();
+}
+
+void dust_density(void)
+{
+  int nact, *act;
+  printf("Beginning dust density estimation\n");
+  fflush(stdout);
+  CPU_Step[CPU_MISC] += measure_time();
+  gl_subgrid_setup("dust_density");
+  act = gl_active_array(&nact);
+  if(gl_gadget_dust_density(GL, &GL_SubLayout, P, act, nact)) gl_fail("gl_gadget_dust_density");
+  free(act);
+}
+
+void dust_drag(void)
+{
+  int nact, *act;
+  printf("Beginning dust management\n");
+  fflush(stdout);
+  CPU_Step[CPU_MISC] += measure_time();
+  gl_subgrid_setup("dust_drag");
+  act = gl_active_array(&nact);
+  if(gl_gadget_dust_drag(GL, &GL_SubLayout, P, SphP, act, nact)) gl_fail("gl_gadget_dust_drag");
+  free(act);
+}
+#endif /* GL_SUBGRID */
 
 #ifdef GL_SNAPSHOT_IO
 /* ---- read_ic() / savepositions() (proto.h; read_ic.c:28, io.c:33) on the library's reader / writer -----------------
