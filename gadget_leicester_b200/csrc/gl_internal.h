@@ -214,6 +214,7 @@ struct gl_ctx
   DBuf<double> sg_scratch, sg_vals;
   DBuf<unsigned long long> sg_claim, sg_keys;
   DBuf<long long> sg_off;
+  long long sg_pairs_seen = 0;	// (grain, gas) pairs of the last gl_dust_drag: sizes the next call's list
   // ---- gadget AoS layer ----
   gl_gadget_layout lay{};
   bool have_lay = false;

@@ -21,7 +21,7 @@
 namespace
 {
 constexpr unsigned FULL = 0xffffffffu;
-#define SG_BUCKET 96		// cells with at most this many particles are tested as one range
+#define SG_BUCKET 96		// cells with at most this many particles are tested as one range (measured: 32 and 192 are both slower)
 #define SG_GAMMA (7. / 5.)	// allvars.h:64
 #define SG_GAMMA_MINUS1 (SG_GAMMA - 1)
 #define SG_PI 3.14159265358979323846
@@ -39,21 +39,46 @@ struct SgTree
   const double4 *s_pm;
   const int *s_type;
   const int *perm;
+  // where a search may start instead of the root: the smallest cell around the target that holds its whole sphere
+  const int *inv, *p_father, *n_parent, *n_first;
+  const double4 *n_cl;
 };
 
-// The reference's neighbour search (blackhole.c:1351-1470, dust.c:1235-1330) as an ordered march: f(valid, p, dx, dy,
-// dz, r2) is called by all 32 lanes for 32 consecutive tree-order particles at a time; valid = the particle is on the
-// reference's Ngblist (type wanted, |d| <= h per axis, r2 <= h*h).  d = target - particle, r2 rounded as the reference's
-// unfused dx*dx + dy*dy + dz*dz.
+// The reference's neighbour search (blackhole.c:1351-1470, dust.c:1235-1330) as an ordered march: f(valid, p, type,
+// mass, r2) is called by all 32 lanes for 32 consecutive tree-order particles at a time; valid = the particle is on the
+// reference's Ngblist (type wanted, |d| <= h per axis, r2 <= h*h), r2 rounded as the reference's unfused
+// dx*dx + dy*dy + dz*dz.
+// The march covers the entries of the smallest cell around the target particle `self` (P[] index) that contains the
+// whole search sphere - every neighbour lies in there, in the same order - instead of starting at the root: most of a
+// root-to-leaf descent is a chain of dependent loads that finds nothing.
 template <class F>
-__device__ __forceinline__ void sg_march(const SgTree &T, int lane, double px, double py, double pz, double h, unsigned typemask,
+__device__ __forceinline__ void sg_march(const SgTree &T, int lane, int self, double px, double py, double pz, double h, unsigned typemask,
 					 unsigned long long *counter, F f)
 {
   const double h2 = __dmul_rn(h, h);
-  int e = 0;
-  while(e < T.nentries)
+  int e = 0, e_end = T.nentries;
+  {
+    int no = __ldg(&T.p_father[__ldg(&T.inv[self])]);
+    while(no >= 0)
+      {
+	const double4 cl = gl_ld4(&T.n_cl[no]);
+	const double half = 0.5 * cl.w - h;
+	if(fabs(px - cl.x) < half && fabs(py - cl.y) < half && fabs(pz - cl.z) < half) break;
+	no = __ldg(&T.n_parent[no]);
+      }
+    if(no > 0)
+      {
+	e = __ldg(&T.n_first[no]) + no;
+	e_end = __ldg(&T.e_next[e]);
+      }
+  }
+  while(e < e_end)
     {
+      // the three records of an entry are fetched together: the march is a chain of dependent L2 round trips and this
+      // makes it one per entry instead of three
       const int nx = __ldg(&T.e_next[e]);
+      const double4 B = gl_ld4(&T.e_B[e]);
+      const int2 rg = __ldg(&T.e_rng[e]);
       int a, b;
       if(nx < 0)
 	{
@@ -63,7 +88,6 @@ __device__ __forceinline__ void sg_march(const SgTree &T, int lane, double px, d
 	}
       else
 	{
-	  const double4 B = gl_ld4(&T.e_B[e]);
 	  double dist = h + 0.5 * B.w;
 	  const double cx = fabs(B.x - px), cy = fabs(B.y - py), cz = fabs(B.z - pz);
 	  bool skip = cx > dist || cy > dist || cz > dist;
@@ -77,7 +101,6 @@ __device__ __forceinline__ void sg_march(const SgTree &T, int lane, double px, d
 	      e = nx;
 	      continue;
 	    }
-	  const int2 rg = __ldg(&T.e_rng[e]);
 	  if(rg.x < 0)
 	    {
 	      if(lane == 0) atomicMax(&counter[2], GL_ERR_LET_VIOLATION);
@@ -97,21 +120,18 @@ __device__ __forceinline__ void sg_march(const SgTree &T, int lane, double px, d
 	{
 	  const int p = q + lane;
 	  bool valid = p < b;
-	  double dx = 0, dy = 0, dz = 0, r2 = 0;
+	  double r2 = 0, mj = 0;
+	  int ty = -1;
 	  if(valid)
 	    {
-	      valid = (typemask >> __ldg(&T.s_type[p])) & 1u;
-	      if(valid)
-		{
-		  const double4 pm = gl_ld4(&T.s_pm[p]);
-		  dx = px - pm.x;
-		  dy = py - pm.y;
-		  dz = pz - pm.z;
-		  r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-		  valid = !(fabs(dx) > h || fabs(dy) > h || fabs(dz) > h || r2 > h2);
-		}
+	      ty = __ldg(&T.s_type[p]);
+	      const double4 pm = gl_ld4(&T.s_pm[p]);
+	      const double dx = px - pm.x, dy = py - pm.y, dz = pz - pm.z;
+	      mj = pm.w;
+	      r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+	      valid = ((typemask >> ty) & 1u) && !(fabs(dx) > h || fabs(dy) > h || fabs(dz) > h || r2 > h2);
 	    }
-	  f(valid, p, dx, dy, dz, r2);
+	  f(valid, p, ty, mj, r2);
 	}
     }
 }
@@ -207,9 +227,9 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sink_last_gas_r(int ns, const int 
   if(in_mass[i] > 0)
     {
       const double h = in_hsml[i], h2 = __dmul_rn(h, h);
-      sg_march(T, lane, in_pos[3 * (size_t) i], in_pos[3 * (size_t) i + 1], in_pos[3 * (size_t) i + 2], h, 1u << 0, counter,
-	       [&](bool valid, int p, double, double, double, double r2) {
-		 const bool isgas = valid && T.s_pm[p].w > 0 && r2 < h2;
+      sg_march(T, lane, i, in_pos[3 * (size_t) i], in_pos[3 * (size_t) i + 1], in_pos[3 * (size_t) i + 2], h, 1u << 0, counter,
+	       [&](bool valid, int, int, double mj, double r2) {
+		 const bool isgas = valid && mj > 0 && r2 < h2;
 		 const unsigned m = __ballot_sync(FULL, isgas);
 		 if(m) last = __shfl_sync(FULL, sqrt(r2), 31 - __clz(m));
 	       });
@@ -249,16 +269,7 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sink_evaluate(int ns, const int *_
   const unsigned long long key = ((unsigned long long) (s + 1) << 32) | (unsigned int) id;
   const unsigned lt = (1u << lane) - 1;
   double r_stale = sc[(size_t) s * SINK_SC + 9];	// `r` of blackhole_evaluate as the previous sink left it (see k_sink_last_gas_r)
-  sg_march(T, lane, px, py, pz, h, (1u << 0) | (1u << 2) | (1u << 5), counter, [&](bool valid, int p, double dx, double dy, double dz, double r2) {
-    (void) dx; (void) dy; (void) dz;
-    int type = -1, j = 0;
-    double mj = 0;
-    if(valid)
-      {
-	type = T.s_type[p];
-	mj = T.s_pm[p].w;
-	j = T.perm[p];
-      }
+  sg_march(T, lane, i, px, py, pz, h, (1u << 0) | (1u << 2) | (1u << 5), counter, [&](bool valid, int p, int type, double mj, double r2) {
     const bool ok = valid && mj > 0 && r2 < h2;	// blackhole.c:901, :921
     const bool isgas = ok && type == 0;
     const double r = sqrt(r2);
@@ -269,6 +280,7 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sink_evaluate(int ns, const int *_
     const double r_seen = below ? r_from : r_stale;
     if(gasmask) r_stale = __shfl_sync(FULL, r, 31 - __clz(gasmask));
     if(!ok) return;
+    const int j = T.perm[p];
     if(type == 5)
       {
 	// blackhole.c:956-1003 (-DBH_MERGERS_WITHIN_H): merge when closer than the accretion boundary
@@ -329,13 +341,11 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sink_swallow(int ns, const int *__
   const int id = A.id[is];
   double am = 0, ad = 0, mx = 0, my = 0, mz = 0;
   int ng = 0, nb = 0, nd = 0;
-  sg_march(T, lane, px, py, pz, h, (1u << 0) | (1u << 2) | (1u << 5), counter, [&](bool valid, int p, double, double, double, double) {
+  sg_march(T, lane, i, px, py, pz, h, (1u << 0) | (1u << 2) | (1u << 5), counter, [&](bool valid, int p, int type, double mj, double) {
     if(!valid) return;
     const int j = T.perm[p];
     const size_t js = (size_t) SL(A, j);
     if(A.swallow[js] != id) return;
-    const int type = T.s_type[p];
-    const double mj = in_mass[j];
     am += mj;
     mx += mj * A.vel[3 * js];
     my += mj * A.vel[3 * js + 1];
@@ -406,8 +416,8 @@ __global__ void __launch_bounds__(GL_BLOCK) k_dust_density(int nd, const int *__
   const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
   const double h = in_hsml[i], mi = in_mass[i];
   double sum = 0;
-  sg_march(T, lane, px, py, pz, h, 1u << 2, counter, [&](bool valid, int p, double, double, double, double r2) {
-    if(!valid || !(T.s_pm[p].w > 0)) return;
+  sg_march(T, lane, i, px, py, pz, h, 1u << 2, counter, [&](bool valid, int, int, double mj, double r2) {
+    if(!valid || !(mj > 0)) return;
     const double u = sqrt(r2) / h;
     if(u < 1)
       {
@@ -510,41 +520,58 @@ __global__ void k_dust_own(int nd, const int *__restrict__ dust, const int *__re
   q[0] = ddm[0]; q[1] = ddm[1]; q[2] = ddm[2]; q[3] = dde; q[4] = rho; q[5] = 0;
 }
 
-// dust_evaluate_select (dust.c:889-1029), search half: the gas inside the grain's Hsml.  COUNT: pairs per grain;
-// otherwise the pairs themselves, key = (gas P[] index, position of the grain in the active list), value = wk
-template <bool COUNT>
+// dust_evaluate_select (dust.c:889-1029), search half: the gas inside the grain's Hsml as (key, value) pairs,
+// key = (gas P[] index, position of the grain in the active list), value = wk.  The pairs are sorted afterwards, so they
+// may land anywhere: a warp parks its hits in shared memory and reserves room in the global list once per DP_BUF hits
+// (one pass, one atomic per grain in the common case).  cursor[0] counts every pair, also those beyond cap: the caller
+// grows the list and repeats when it overflowed.
+#define DP_BUF 128
 __global__ void __launch_bounds__(GL_BLOCK) k_dust_pairs(int nd, const int *__restrict__ dust, SgTree T, const double *__restrict__ in_pos,
-							 const double *__restrict__ in_hsml, const double *__restrict__ sc, int *__restrict__ cnt,
-							 const long long *__restrict__ off, unsigned long long *__restrict__ keys, double *__restrict__ vals,
+							 const double *__restrict__ in_hsml, const double *__restrict__ sc, unsigned long long *__restrict__ cursor,
+							 long long cap, unsigned long long *__restrict__ keys, double *__restrict__ vals,
 							 unsigned long long *__restrict__ counter)
 {
+  __shared__ unsigned long long s_k[GL_WARPS_PER_BLOCK][DP_BUF];
+  __shared__ double s_v[GL_WARPS_PER_BLOCK][DP_BUF];
   const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if(d >= nd) return;
   const int i = dust[d];
-  if(!(sc[(size_t) d * DUST_SC + 4] > 0))	// dust.c:995: nothing is returned where the gas density at the grain is zero
-    {
-      if(COUNT && lane == 0) cnt[d] = 0;
-      return;
-    }
+  if(!(sc[(size_t) d * DUST_SC + 4] > 0)) return;	// dust.c:995: nothing is returned where the gas density at the grain is zero
+  unsigned long long *bk = s_k[threadIdx.x >> 5];
+  double *bv = s_v[threadIdx.x >> 5];
   const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
-  const double h = in_hsml[i];
+  const double h = in_hsml[i], hinv = 1 / h, hinv3 = hinv * hinv * hinv;
   const unsigned lt = (1u << lane) - 1;
-  long long base = COUNT ? 0 : off[d];
-  int n = 0;
-  sg_march(T, lane, px, py, pz, h, 1u << 0, counter, [&](bool valid, int p, double, double, double, double r2) {
+  int nbuf = 0;
+  auto flush = [&]() {
+    __syncwarp();
+    unsigned long long base = 0;
+    if(lane == 0) base = atomicAdd(cursor, (unsigned long long) nbuf);
+    base = __shfl_sync(FULL, base, 0);
+    for(int k = lane; k < nbuf; k += 32)
+      if((long long) (base + k) < cap)
+	{
+	  keys[base + k] = bk[k];
+	  vals[base + k] = bv[k];
+	}
+    nbuf = 0;
+    __syncwarp();
+  };
+  sg_march(T, lane, i, px, py, pz, h, 1u << 0, counter, [&](bool valid, int p, int, double mj, double r2) {
     const double u = sqrt(r2) / h;
-    const bool hit = valid && T.s_pm[p].w > 0 && u < 1;
+    const bool hit = valid && mj > 0 && u < 1;
     const unsigned m = __ballot_sync(FULL, hit);
-    if(!COUNT && hit)
+    if(!m) return;
+    if(nbuf + __popc(m) > DP_BUF) flush();
+    if(hit)
       {
-	const double hinv = 1 / h;
-	const long long at = base + n + __popc(m & lt);
-	keys[at] = ((unsigned long long) (unsigned int) T.perm[p] << 32) | (unsigned int) d;
-	vals[at] = sg_kernel_wk(u, hinv * hinv * hinv);
+	const int at = nbuf + __popc(m & lt);
+	bk[at] = ((unsigned long long) (unsigned int) T.perm[p] << 32) | (unsigned int) d;
+	bv[at] = sg_kernel_wk(u, hinv3);
       }
-    n += __popc(m);
+    nbuf += __popc(m);
   });
-  if(COUNT && lane == 0) cnt[d] = n;
+  if(nbuf) flush();
 }
 
 // dust.c:988-1007 per gas particle, contributions in the order the reference applies them
@@ -635,7 +662,8 @@ int sg_ready(gl_ctx *c, const char *who)
 }
 SgTree sg_tree(gl_ctx *c)
 {
-  return SgTree{ (int) c->nentries, c->e_next.p, c->e_B.p, c->e_rng.p, c->s_pm.p, c->s_type.p, c->perm.p };
+  return SgTree{ (int) c->nentries, c->e_next.p, c->e_B.p, c->e_rng.p, c->s_pm.p, c->s_type.p, c->perm.p,
+		 c->inv.p, c->p_father.p, c->n_parent.p, c->n_first.p, c->n_cl.p };
 }
 
 // the active particles of type `want`, in active-list order -> c->sg_list (device), *count
@@ -683,7 +711,7 @@ __global__ void __launch_bounds__(GL_BLOCK) k_sg_mark(int nt, const int *__restr
   if(lane == 0) flag[i] = 1;
   if(!typemask) return;
   const double px = in_pos[3 * (size_t) i], py = in_pos[3 * (size_t) i + 1], pz = in_pos[3 * (size_t) i + 2];
-  sg_march(T, lane, px, py, pz, in_hsml[i], typemask, counter, [&](bool valid, int p, double, double, double, double) {
+  sg_march(T, lane, i, px, py, pz, in_hsml[i], typemask, counter, [&](bool valid, int p, int, double, double) {
     if(valid) flag[T.perm[p]] = 1;
   });
 }
@@ -762,36 +790,39 @@ int sg_run_dust(gl_ctx *c, long long nd, const DustArr &A)
   const SgTree T = sg_tree(c);
   const double tbi = c->par.Timebase_interval;
   GL_CUDA(c, c->sg_scratch.ensure((size_t) nd * DUST_SC));
-  GL_CUDA(c, c->sg_cnt.ensure((size_t) nd + 1));
-  GL_CUDA(c, c->sg_off.ensure((size_t) nd + 1));
   const int wgrid = gl_grid(nd * 32, GL_BLOCK);
   k_dust_own<<<gl_grid(nd, 128), 128, 0, c->stream>>>((int) nd, c->sg_list.p, c->in_timebin.p, c->in_pos.p, c->in_mass.p, c->subgrid, tbi, A, c->sg_scratch.p);
-  k_dust_pairs<true><<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, c->sg_cnt.p, nullptr, nullptr,
-							 nullptr, c->d_counter.p);
-  c->kernel_launches += 2;
-  GL_CUDA(c, cudaMemsetAsync(c->sg_cnt.p + nd, 0, sizeof(int), c->stream));
-  size_t tmp = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->sg_cnt.p, c->sg_off.p, (int) nd + 1, c->stream);
-  GL_CUDA(c, c->cub_tmp.ensure(tmp));
-  GL_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->sg_cnt.p, c->sg_off.p, (int) nd + 1, c->stream));
-  GL_LAUNCH_COUNT(c);
+  c->kernel_launches += 1;
+  unsigned long long *cursor = c->d_counter.p + 10;
   long long npairs = 0;
-  GL_CUDA(c, cudaMemcpyAsync(&npairs, c->sg_off.p + nd, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  unsigned long long *k0 = nullptr, *k1 = nullptr;
+  double *v0 = nullptr, *v1 = nullptr;
+  long long cap = std::max<long long>(64 * nd, c->sg_pairs_seen + c->sg_pairs_seen / 4);
+  for(int attempt = 0; attempt < 2; attempt++)
+    {
+      GL_CUDA(c, c->sg_keys.ensure(2 * (size_t) cap));
+      GL_CUDA(c, c->sg_vals.ensure(2 * (size_t) cap));
+      k0 = c->sg_keys.p; k1 = c->sg_keys.p + cap;
+      v0 = c->sg_vals.p; v1 = c->sg_vals.p + cap;
+      GL_CUDA(c, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), c->stream));
+      k_dust_pairs<<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, cursor, cap, k0, v0, c->d_counter.p);
+      GL_LAUNCH_COUNT(c);
+      unsigned long long hc = 0;
+      GL_CUDA(c, cudaMemcpyAsync(&hc, cursor, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      npairs = (long long) hc;
+      c->sg_pairs_seen = npairs;
+      if(npairs <= cap) break;
+      if(attempt == 1) return c->fail("gl_dust_drag: pair list overflowed twice");
+      cap = npairs;
+    }
   if(npairs >= (1ll << 31)) return c->fail("gl_dust_drag: more than 2^31 (grain, gas) pairs");
   if(npairs > 0)
     {
-      GL_CUDA(c, c->sg_keys.ensure(2 * (size_t) npairs));
-      GL_CUDA(c, c->sg_vals.ensure(2 * (size_t) npairs));
-      unsigned long long *k0 = c->sg_keys.p, *k1 = c->sg_keys.p + npairs;
-      double *v0 = c->sg_vals.p, *v1 = c->sg_vals.p + npairs;
-      k_dust_pairs<false><<<wgrid, GL_BLOCK, 0, c->stream>>>((int) nd, c->sg_list.p, T, c->in_pos.p, c->in_hsml.p, c->sg_scratch.p, nullptr, c->sg_off.p, k0, v0,
-							      c->d_counter.p);
-      GL_LAUNCH_COUNT(c);
       int top = 33;	// bits of the key that vary: 32 of the grain's position + those of the gas index
       for(long long q = (long long) n; q > 1; q >>= 1) top++;
       if(top > 64) top = 64;
-      tmp = 0;
+      size_t tmp = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, tmp, k0, k1, v0, v1, (int) npairs, 0, top, c->stream);
       GL_CUDA(c, c->cub_tmp.ensure(tmp));
       GL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k0, k1, v0, v1, (int) npairs, 0, top, c->stream));

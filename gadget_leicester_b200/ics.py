@@ -87,7 +87,7 @@ def disc(n_gas, seed=42, with_sinks=True, m_disc=0.01, m_star=1.0, m_planet=4.77
     return _finish(pos, vel, mass, ptype, entropy)
 
 
-def disc_subgrid(n_gas, n_dust, seed=42, m_disc=0.01, m_star=1.0, m_planet=4.77e-3, r_in=0.008, r_out=1.0, aspect=0.05):
+def disc_subgrid(n_gas, n_dust, seed=42, m_disc=0.01, m_star=1.0, m_planet=4.77e-3, r_in=0.008, r_out=1.0, aspect=0.05, clump_frac=0.3):
     """The disc of config 0 arranged so that the sub-grid neighbour loops behind the force path have work
     (blackhole.c:794/:1201, dust.c:748/:889): gas reaching inside InnerBoundary of the star, dust grains (Type 2) mixed
     into the disc, around the star and around the planet, a small third sink next to the planet and a fourth next to
@@ -95,8 +95,8 @@ def disc_subgrid(n_gas, n_dust, seed=42, m_disc=0.01, m_star=1.0, m_planet=4.77e
     g = _rng(seed)
     ps = disc(n_gas, seed=seed, with_sinks=False, m_disc=m_disc, m_star=m_star, r_in=r_in, r_out=r_out, aspect=aspect)
     rp = 0.5
-    # dust: 70 % through the disc, 15 % within 0.03 of the star, 15 % within 0.03 of the planet
-    na = int(0.7 * n_dust)
+    # dust: 70 % through the disc, 15 % within 0.03 of the star, 15 % within 0.03 of the planet (clump_frac = 0.3)
+    na = int((1.0 - clump_frac) * n_dust)
     nb = (n_dust - na) // 2
     nc = n_dust - na - nb
     R = r_in + (r_out - r_in) * g.random(na)

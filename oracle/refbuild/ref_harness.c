@@ -699,17 +699,17 @@ int main(int argc, char **argv)
 	      break;
 	    case 'B':
 	      set_subgrid_state(); dump_subgrid_params(prefix); dump_subgrid_state(prefix, "pre");
-	      blackhole_accretion();
+	      { double tc = now(); blackhole_accretion(); tc = now() - tc; put(prefix, "time", 'd', 1, 1, &tc); }
 	      dump_subgrid_state(prefix, "post");
 	      break;
 	    case 'Y':
 	      set_subgrid_state(); dump_subgrid_params(prefix); dump_subgrid_state(prefix, "pre");
-	      dust_density();
+	      { double tc = now(); dust_density(); tc = now() - tc; put(prefix, "time", 'd', 1, 1, &tc); }
 	      dump_subgrid_state(prefix, "post");
 	      break;
 	    case 'Z':
 	      set_subgrid_state(); dump_subgrid_params(prefix); dump_subgrid_state(prefix, "pre");
-	      dust_drag();
+	      { double tc = now(); dust_drag(); tc = now() - tc; put(prefix, "time", 'd', 1, 1, &tc); }
 	      dump_subgrid_state(prefix, "post");
 	      break;
 	    case 'N': dump_nodes(prefix); break;
