@@ -8,6 +8,7 @@
 // get_Tab_IO_Label io.c:2038).  Values are 4-byte floats, IDs 4-byte unsigned.
 #include "gl_internal.h"
 #include "gl_host.h"
+#include "gl_hdf5.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -38,6 +39,7 @@ struct BlockRow
 {
   Block b;
   const char *label;		// format 2
+  const char *h5name;		// format 3: get_dataset_name() io.c:2270
   int ncomp;
   int types;			// bit mask of the particle types that carry the record (before the MASS / npart rules)
   bool behind_u;		// not read from initial conditions (read_ic.c:891)
@@ -45,18 +47,18 @@ struct BlockRow
 
 const int ALL_TYPES = 63, GAS = 1, STARS = 1 << 4, SINKS = 1 << 5, VIRTUALS = 1 << 3;
 const BlockRow ROWS[B_COUNT] = {
-  {B_POS, "POS ", 3, ALL_TYPES, false}, {B_VEL, "VEL ", 3, ALL_TYPES, false}, {B_ID, "ID  ", 1, ALL_TYPES, false},
-  {B_MASS, "MASS", 1, ALL_TYPES, false}, {B_U, "U   ", 1, GAS, false}, {B_RHO, "RHO ", 1, GAS, true},
-  {B_NE, "NE  ", 1, GAS, true}, {B_NH, "NH  ", 1, GAS, true}, {B_HSML, "HSML", 1, GAS, true},
-  {B_DUST, "DUST", 1, ALL_TYPES, true}, {B_SFR, "SFR ", 1, GAS, true}, {B_AGE, "AGE ", 1, STARS, true},
-  {B_BHMASS, "BHMA", 1, SINKS, true}, {B_BHMDOT, "BHMD", 1, SINKS, true}, {B_ACCDISCMASS, "ACDM", 1, SINKS, true},
-  {B_BHMSEED, "BHMS", 1, SINKS, true}, {B_NEWDENS, "NEWD", 1, VIRTUALS, true}, {B_DELPHOTONMOM, "DPhM", 1, VIRTUALS, true},
-  {B_OLDPHOTONMOM, "OPhM", 1, VIRTUALS, true}, {B_BIPHOTONEN, "BPhE", 1, VIRTUALS, true}, {B_ACCMASS, "ACMA", 1, GAS, true},
+  {B_POS, "POS ", "Coordinates", 3, ALL_TYPES, false}, {B_VEL, "VEL ", "Velocities", 3, ALL_TYPES, false}, {B_ID, "ID  ", "ParticleIDs", 1, ALL_TYPES, false},
+  {B_MASS, "MASS", "Masses", 1, ALL_TYPES, false}, {B_U, "U   ", "InternalEnergy", 1, GAS, false}, {B_RHO, "RHO ", "Density", 1, GAS, true},
+  {B_NE, "NE  ", "ElectronAbundance", 1, GAS, true}, {B_NH, "NH  ", "NeutralHydrogenAbundance", 1, GAS, true}, {B_HSML, "HSML", "SmoothingLength", 1, GAS, true},
+  {B_DUST, "DUST", "DustRadius", 1, ALL_TYPES, true}, {B_SFR, "SFR ", "StarFormationRate", 1, GAS, true}, {B_AGE, "AGE ", "StellarFormationTime", 1, STARS, true},
+  {B_BHMASS, "BHMA", "BH_Mass", 1, SINKS, true}, {B_BHMDOT, "BHMD", "BH_Mdot", 1, SINKS, true}, {B_ACCDISCMASS, "ACDM", "AccDisc_Mass", 1, SINKS, true},
+  {B_BHMSEED, "BHMS", "BH_Mseed", 1, SINKS, true}, {B_NEWDENS, "NEWD", "NewDensity", 1, VIRTUALS, true}, {B_DELPHOTONMOM, "DPhM", "DeltaPhotonMomentum", 1, VIRTUALS, true},
+  {B_OLDPHOTONMOM, "OPhM", "OldPhotonMomentum", 1, VIRTUALS, true}, {B_BIPHOTONEN, "BPhE", "BirthPhotonEnergy", 1, VIRTUALS, true}, {B_ACCMASS, "ACMA", "accreted_mass", 1, GAS, true},
   // ACMO: get_bytes_per_blockelement() (io.c:1184) gives this record ONE value per particle although fill_write_buffer
   // (io.c:1003-1014) produces three, so write_file puts only the first N_gas values of the (particle, component)
   // stream into the file: the momenta of the first N_gas/3 gas particles.  Kept as it is - the record length is part
   // of the format the reference and its readers expect.  (One CommBuffer pass assumed: N_gas <= BufferSize * 2^18.)
-  {B_ACCMOM, "ACMO", 1, GAS, true},
+  {B_ACCMOM, "ACMO", "accreted_momentum", 1, GAS, true},
 };
 
 struct Ctx
@@ -237,8 +239,11 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
 {
   Ctx c{*lay, *io, *par, err, errlen};
   if(err && errlen > 0) err[0] = 0;
-  if(par->format != 1 && par->format != 2) return c.fail("gl_snapshot_write: format %d is not 1 or 2 (format 3 = HDF5 is not available)", par->format);
+  if(par->format < 1 || par->format > 3) return c.fail("gl_snapshot_write: format %d is not 1, 2 or 3", par->format);
   const char *P = (const char *) Pv, *S = (const char *) SphPv;
+  // format 3: the reference appends the suffix itself (io.c:2623)
+  const std::string outname = par->format == 3 ? std::string(fname) + ".hdf5" : std::string(fname);
+  fname = outname.c_str();
 
   const double T0 = gl_now();
   // particle indices per type, in P[] order (fill_write_buffer scans P[] for Type == type, io.c:212-216): every work
@@ -307,7 +312,85 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
   std::vector<Piece> pieces[6];
   std::vector<std::pair<long long, int> > marks;	// (offset, value) of the 4-byte record markers
   std::vector<std::pair<long long, const char *> > labels;	// format 2
-  long long off = 0;
+  std::vector<char> h5meta;	// format 3: everything in front of the raw data
+  long long off = 0, header_off = -1;
+  long long accmom_off = -1;
+  if(par->format == 3)
+    {
+      // io.c:2619-2633: "/Header" with the header fields as attributes (write_header_attributes_in_hdf5, io.c:2866), one
+      // group per type present, one dataset per (record, type): [npart[type]] or [npart[type], values] (io.c:2733-2748)
+      std::vector<glh5::Group> groups;
+      glh5::Group hg;
+      hg.name = "Header";
+      auto attr = [&](const char *name, glh5::Type ty, int count, const void *data) {
+	glh5::Attr a{ name, ty, count, {} };
+	a.data.assign((const char *) data, (const char *) data + (size_t) (count ? count : 1) * glh5::type_size(ty));
+	hg.attrs.push_back(a);
+      };
+      attr("NumPart_ThisFile", glh5::T_I32, 6, h.npart);
+      attr("NumPart_Total", glh5::T_U32, 6, h.npartTotal);
+      attr("NumPart_Total_HighWord", glh5::T_U32, 6, h.npartTotalHighWord);
+      attr("MassTable", glh5::T_F64, 6, h.mass);
+      attr("Time", glh5::T_F64, 0, &h.time);
+      attr("Redshift", glh5::T_F64, 0, &h.redshift);
+      attr("BoxSize", glh5::T_F64, 0, &h.BoxSize);
+      attr("NumFilesPerSnapshot", glh5::T_I32, 0, &h.num_files);
+      attr("Omega0", glh5::T_F64, 0, &h.Omega0);
+      attr("OmegaLambda", glh5::T_F64, 0, &h.OmegaLambda);
+      attr("HubbleParam", glh5::T_F64, 0, &h.HubbleParam);
+      attr("Flag_Sfr", glh5::T_I32, 0, &h.flag_sfr);
+      attr("Flag_Cooling", glh5::T_I32, 0, &h.flag_cooling);
+      attr("Flag_StellarAge", glh5::T_I32, 0, &h.flag_stellarage);
+      attr("Flag_Metals", glh5::T_I32, 0, &h.flag_metals);
+      attr("Flag_Feedback", glh5::T_I32, 0, &h.flag_feedback);
+      attr("Flag_DoublePrecision", glh5::T_I32, 0, &h.flag_doubleprecision);
+      groups.push_back(hg);
+      int gidx[6];
+      for(int t = 0; t < 6; t++)
+	{
+	  gidx[t] = -1;
+	  if(h.npart[t] > 0)
+	    {
+	      glh5::Group g;
+	      g.name = "PartType" + std::to_string(t);
+	      gidx[t] = (int) groups.size();
+	      groups.push_back(g);
+	    }
+	}
+      struct Where { int type, row, group, dset; };
+      std::vector<Where> where;
+      for(int r = 0; r < B_COUNT; r++)
+	{
+	  const BlockRow &row = ROWS[r];
+	  if(!present(c, row.b)) continue;
+	  int typelist[6];
+	  if(particles_in_block(c, row, h.npart, typelist) <= 0) continue;
+	  for(int t = 0; t < 6; t++)
+	    if(typelist[t])
+	      {
+		glh5::Dataset d;
+		d.name = row.h5name;
+		d.type = row.b == B_ID ? glh5::T_U32 : glh5::T_F32;	// get_datatype_in_block io.c:2245 (no LONGIDS, 4-byte output)
+		d.rank = row.ncomp == 1 ? 1 : 2;
+		d.dims[0] = (glh5::u64) h.npart[t];
+		d.dims[1] = (glh5::u64) row.ncomp;
+		where.push_back({ t, r, gidx[t], (int) groups[(size_t) gidx[t]].dsets.size() });
+		groups[(size_t) gidx[t]].dsets.push_back(d);
+	      }
+	}
+      glh5::Writer w(h5meta);
+      off = (long long) w.layout(groups);
+      for(const Where &q : where)
+	{
+	  const long long at = (long long) groups[(size_t) q.group].dsets[(size_t) q.dset].data_off;
+	  if(ROWS[q.row].b == B_ACCMOM)
+	    accmom_off = at;
+	  else
+	    pieces[q.type].push_back({ q.row, at });
+	}
+    }
+  else
+    {
   auto label_at = [&](const char *label, long long payload) {	// [8] LABEL nextblock [8] (io.c:2634-2642, :2672-2680)
     marks.push_back({off, 8});
     labels.push_back({off + 4, label});
@@ -316,11 +399,10 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
     off += 16;
   };
   if(par->format == 2) label_at("HEAD", 256);
-  const long long header_off = off + 4;
+  header_off = off + 4;
   marks.push_back({off, 256});
   marks.push_back({off + 4 + 256, 256});
   off += 4 + 256 + 4;
-  long long accmom_off = -1;
   for(int r = 0; r < B_COUNT; r++)
     {
       const BlockRow &row = ROWS[r];
@@ -345,6 +427,7 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
 	  }
       marks.push_back({off, (int) bytes});
       off += 4;
+    }
     }
 
   // The file is assembled in place: it is given its final length and mapped, and every work item converts its particles
@@ -376,7 +459,10 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
       close(fd);
       return c.fail("gl_snapshot_write: no memory for a %lld-byte file image", total);
     }
-  memcpy(image + header_off, &h, 256);
+  if(par->format == 3)
+    memcpy(image, h5meta.data(), h5meta.size());
+  else
+    memcpy(image + header_off, &h, 256);
   for(auto &m : marks) memcpy(image + m.first, &m.second, 4);
   for(auto &l : labels) memcpy(image + l.first, l.second, 4);
 
@@ -455,13 +541,99 @@ static int read_header(Ctx &c, FILE *fd, int format, gl_io_header *h)
   return 0;
 }
 
+// format 3: struct io_header from the attributes of "/Header" (read_header_attributes_in_hdf5, read_ic.c:1333: the seven it
+// reads; the flags are taken along when the file has them)
+static void h5_header(const glh5::Reader &R, gl_io_header *h)
+{
+  memset(h, 0, sizeof(*h));
+  const glh5::u64 hg = R.find("/Header");
+  if(hg == glh5::UNDEF) throw glh5::Error{ "HDF5: no /Header group" };
+  glh5::Value v;
+  auto need = [&](const char *name, glh5::u64 count) {
+    if(!R.attribute(hg, name, v)) throw glh5::Error{ std::string("HDF5: /Header has no attribute ") + name };
+    if(v.count() < count) throw glh5::Error{ std::string("HDF5: /Header attribute too short: ") + name };
+  };
+  need("NumPart_ThisFile", 6);
+  for(int t = 0; t < 6; t++) h->npart[t] = (int) v.as_u64((glh5::u64) t);
+  need("NumPart_Total", 6);
+  for(int t = 0; t < 6; t++) h->npartTotal[t] = (unsigned int) v.as_u64((glh5::u64) t);
+  if(R.attribute(hg, "NumPart_Total_HighWord", v) && v.count() >= 6)
+    for(int t = 0; t < 6; t++) h->npartTotalHighWord[t] = (unsigned int) v.as_u64((glh5::u64) t);
+  need("MassTable", 6);
+  for(int t = 0; t < 6; t++) h->mass[t] = v.as_double((glh5::u64) t);
+  need("Time", 1);
+  h->time = v.as_double(0);
+  if(R.attribute(hg, "Redshift", v) && v.count()) h->redshift = v.as_double(0);
+  need("BoxSize", 1);
+  h->BoxSize = v.as_double(0);
+  need("NumFilesPerSnapshot", 1);
+  h->num_files = (int) v.as_u64(0);
+  if(R.attribute(hg, "Omega0", v) && v.count()) h->Omega0 = v.as_double(0);
+  if(R.attribute(hg, "OmegaLambda", v) && v.count()) h->OmegaLambda = v.as_double(0);
+  if(R.attribute(hg, "HubbleParam", v) && v.count()) h->HubbleParam = v.as_double(0);
+  struct { const char *name; int *dst; } flags[] = { { "Flag_Sfr", &h->flag_sfr }, { "Flag_Cooling", &h->flag_cooling }, { "Flag_StellarAge", &h->flag_stellarage },
+    { "Flag_Metals", &h->flag_metals }, { "Flag_Feedback", &h->flag_feedback }, { "Flag_DoublePrecision", &h->flag_doubleprecision } };
+  for(auto &f : flags)
+    if(R.attribute(hg, f.name, v) && v.count()) *f.dst = (int) v.as_u64(0);
+}
+// a whole file in memory (mapped when possible)
+struct FileImage
+{
+  const char *p = nullptr;
+  size_t size = 0;
+  void *mapping = MAP_FAILED;
+  std::vector<char> copy;
+  bool open(const char *fname)
+  {
+    FILE *fd = fopen(fname, "rb");
+    if(!fd) return false;
+    fseeko(fd, 0, SEEK_END);
+    size = (size_t) ftello(fd);
+    mapping = size ? mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fileno(fd), 0) : MAP_FAILED;
+    if(mapping != MAP_FAILED)
+      p = (const char *) mapping;
+    else
+      {
+	copy.resize(size);
+	fseeko(fd, 0, SEEK_SET);
+	if(size && fread(copy.data(), 1, size, fd) != size)
+	  {
+	    fclose(fd);
+	    return false;
+	  }
+	p = copy.data();
+      }
+    fclose(fd);
+    return true;
+  }
+  ~FileImage()
+  {
+    if(mapping != MAP_FAILED) munmap(mapping, size);
+  }
+};
+
 extern "C" int gl_snapshot_read_header(const char *fname, int format, gl_io_header *hdr, char *err, int errlen)
 {
   Ctx c{};
   c.err = err;
   c.errlen = errlen;
   if(err && errlen > 0) err[0] = 0;
-  if(format != 1 && format != 2) return c.fail("gl_snapshot_read_header: format %d is not 1 or 2 (format 3 = HDF5 is not available)", format);
+  if(format < 1 || format > 3) return c.fail("gl_snapshot_read_header: format %d is not 1, 2 or 3", format);
+  if(format == 3)
+    {
+      FileImage img;
+      if(!img.open(fname)) return c.fail("can't open file `%s' for reading initial conditions.", fname);
+      try
+	{
+	  glh5::Reader R(img.p, img.size);
+	  h5_header(R, hdr);
+	}
+      catch(const glh5::Error &e)
+	{
+	  return c.fail("%s (`%s')", e.what.c_str(), fname);
+	}
+      return 0;
+    }
   FILE *fd = fopen(fname, "rb");
   if(!fd) return c.fail("can't open file `%s' for reading initial conditions.", fname);
   const int rc = read_header(c, fd, format, hdr);
@@ -475,20 +647,44 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
 {
   Ctx c{*lay, *io, *par, err, errlen};
   if(err && errlen > 0) err[0] = 0;
-  if(par->format != 1 && par->format != 2) return c.fail("gl_snapshot_read: format %d is not 1 or 2 (format 3 = HDF5 is not available)", par->format);
+  if(par->format < 1 || par->format > 3) return c.fail("gl_snapshot_read: format %d is not 1, 2 or 3", par->format);
   char *P = (char *) Pv, *S = (char *) SphPv;
-  FILE *fd = fopen(fname, "rb");
-  if(!fd) return c.fail("can't open file `%s' for reading initial conditions.", fname);	// read_ic.c:663-667 endrun(123)
+  const bool h5 = par->format == 3;
+  FILE *fd = h5 ? nullptr : fopen(fname, "rb");
+  FileImage img;
+  if(h5 ? !img.open(fname) : !fd) return c.fail("can't open file `%s' for reading initial conditions.", fname);	// read_ic.c:663-667 endrun(123)
   struct Closer
   {
     FILE *f;
-    ~Closer() { fclose(f); }
+    ~Closer()
+    {
+      if(f) fclose(f);
+    }
   } closer{fd};
 
   int b1 = 0, b2 = 0, next = 0;
   char label[4];
   gl_io_header h;
-  if(read_header(c, fd, par->format, &h)) return 1;
+  glh5::Reader *R = nullptr;
+  struct RFree
+  {
+    glh5::Reader *&r;
+    ~RFree() { delete r; }
+  } rfree{R};
+  if(h5)
+    {
+      try
+	{
+	  R = new glh5::Reader(img.p, img.size);
+	  h5_header(*R, &h);
+	}
+      catch(const glh5::Error &e)
+	{
+	  return c.fail("%s (`%s')", e.what.c_str(), fname);
+	}
+    }
+  else if(read_header(c, fd, par->format, &h))
+    return 1;
   if(h.flag_doubleprecision)	// read_ic.c:744-750
     return c.fail("Problem: Code not compiled with INPUT_IN_DOUBLEPRECISION, but input files are in double precision!");
   if(h.num_files > 1) return c.fail("gl_snapshot_read: `%s' is one of %d files; multi-file snapshots are not supported", fname, h.num_files);
@@ -511,17 +707,21 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
   if(nall > MaxPart)		// read_ic.c:864-869 endrun(173)
     return c.fail("Not enough space (space for %lld, need at least %lld)", MaxPart, nall);
 
-  // Pass 1 (serial, a few reads): walk the record structure - labels, lengths - and note where every type's part of
-  // every record lies.  Pass 2: map the file and let every work item fill ALL fields of its particles in one go, so
-  // that P[] / SphP[] are swept once instead of once per record; the per-particle rules that follow the records in
+  // Pass 1 (serial, a few reads): walk the record structure - labels, lengths; datasets in format 3 - and note where every
+  // type's part of every record lies.  Pass 2: let every work item fill ALL fields of its particles in one go, so that
+  // P[] / SphP[] are swept once instead of once per record; the per-particle rules that follow the records in
   // read_ic() (mass table, InitGasU, MinEgySpec) ride along.
   struct Piece
   {
     int row;
-    long long off;
+    long long off;		// formats 1 / 2: offset in the file
+    const char *ptr;		// where the 4-byte values are
   };
   std::vector<Piece> pieces[6];
   long long accmom_off = -1;
+  const char *accmom_ptr = nullptr;
+  std::vector<std::vector<float> > converted;	// format 3: datasets stored in another type than the 4-byte one (H5Dread converts, read_ic.c:1020-1036)
+  converted.reserve(6 * B_COUNT);
   for(int r = 0; r < B_COUNT; r++)
     {
       const BlockRow &row = ROWS[r];
@@ -530,6 +730,57 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
       int typelist[6];
       const long long npart = particles_in_block(c, row, h.npart, typelist);
       if(npart <= 0) continue;
+      if(h5)
+	{
+	  for(int t = 0; t < 6; t++)
+	    if(typelist[t])
+	      {
+		char path[96];
+		snprintf(path, sizeof(path), "/PartType%d/%s", t, row.h5name);
+		try
+		  {
+		    const glh5::u64 oh = R->find(path);
+		    if(oh == glh5::UNDEF) return c.fail("gl_snapshot_read: `%s' has no dataset %s (H5Dopen fails in the reference, read_ic.c:998)", fname, path);
+		    glh5::Value v;
+		    R->dataset(oh, v);
+		    const glh5::u64 want = (glh5::u64) h.npart[t] * (glh5::u64) row.ncomp;
+		    if(v.rank < 1 || v.dims[0] != (glh5::u64) h.npart[t] || v.count() != want)
+		      return c.fail("gl_snapshot_read: dataset %s does not hold %d x %d values", path, h.npart[t], row.ncomp);
+		    const char *ptr;
+		    const bool direct = v.size == 4 && (row.b == B_ID ? v.cls == 0 : v.cls == 1);
+		    if(direct)
+		      ptr = (const char *) v.data;
+		    else
+		      {
+			// what H5Dread does with a memory type of NATIVE_FLOAT / NATIVE_UINT
+			converted.emplace_back((size_t) want);
+			std::vector<float> &buf = converted.back();
+			HostPool::get().run((long long) want, 65536, [&](long long, long long lo, long long hi) {
+			  for(long long k = lo; k < hi; k++)
+			    {
+			      if(row.b == B_ID)
+				{
+				  const unsigned int u = (unsigned int) v.as_u64((glh5::u64) k);
+				  memcpy(&buf[(size_t) k], &u, 4);
+				}
+			      else
+				buf[(size_t) k] = (float) v.as_double((glh5::u64) k);
+			    }
+			});
+			ptr = (const char *) buf.data();
+		      }
+		    if(row.b == B_ACCMOM)
+		      accmom_ptr = ptr;
+		    else
+		      pieces[t].push_back({r, 0, ptr});
+		  }
+		catch(const glh5::Error &e)
+		  {
+		    return c.fail("%s (%s in `%s')", e.what.c_str(), path, fname);
+		  }
+	      }
+	  continue;
+	}
       if(par->format == 2)
 	{
 	  if(!(get(fd, &b1, 4) && get(fd, label, 4) && get(fd, &next, 4) && get(fd, &b2, 4)))
@@ -548,23 +799,31 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
 	    if(row.b == B_ACCMOM)
 	      accmom_off = off;
 	    else
-	      pieces[t].push_back({r, off});
+	      pieces[t].push_back({r, off, nullptr});
 	    off += (long long) h.npart[t] * row.ncomp * 4;
 	  }
       if(fseeko(fd, (off_t) off, SEEK_SET) != 0 || !get(fd, &b2, 4) || b2 != b1)	// my_fread io.c:3005 endrun(778)
 	return c.fail("gl_snapshot_read: record %s is cut short or not closed by its length (I/O error on `%s')", row.label, fname);
     }
-  const long long used = (long long) ftello(fd);
-  const char *image = nullptr;
+  void *mapping = MAP_FAILED;
+  long long used = 0;
   std::vector<char> copy;
-  void *mapping = mmap(nullptr, (size_t) used, PROT_READ, MAP_PRIVATE, fileno(fd), 0);
-  if(mapping != MAP_FAILED)
-    image = (const char *) mapping;
-  else
+  if(!h5)
     {
-      copy.resize((size_t) used);
-      if(fseeko(fd, 0, SEEK_SET) != 0 || !get(fd, copy.data(), (size_t) used)) return c.fail("I/O error (fread) on `%s'", fname);
-      image = copy.data();
+      used = (long long) ftello(fd);
+      const char *image = nullptr;
+      mapping = mmap(nullptr, (size_t) used, PROT_READ, MAP_PRIVATE, fileno(fd), 0);
+      if(mapping != MAP_FAILED)
+	image = (const char *) mapping;
+      else
+	{
+	  copy.resize((size_t) used);
+	  if(fseeko(fd, 0, SEEK_SET) != 0 || !get(fd, copy.data(), (size_t) used)) return c.fail("I/O error (fread) on `%s'", fname);
+	  image = copy.data();
+	}
+      for(int t = 0; t < 6; t++)
+	for(Piece &q : pieces[t]) q.ptr = image + q.off;
+      if(accmom_off >= 0) accmom_ptr = image + accmom_off;
     }
   const bool ic_rules = par->RestartFlag == 0 && par->InitGasTemp > 0;	// read_ic.c:196-210
   for(int t = 0; t < 6; t++)
@@ -576,7 +835,7 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
 	for(const Piece &q : pc)
 	  {
 	    const BlockRow &row = ROWS[q.row];
-	    const float *in = (const float *) (image + q.off) + lo * row.ncomp;
+	    const float *in = (const float *) q.ptr + lo * row.ncomp;
 	    for(long long k = lo; k < hi; k++, in += row.ncomp) value_in(c, row.b, P, S, first[t] + k, t, in);
 	  }
 	// read_ic.c:106-111: "this makes sure that masses are initialized in the case that the mass-block is completely empty"
@@ -591,11 +850,11 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
 	    }
       });
     }
-  if(accmom_off >= 0)
+  if(accmom_ptr)
     {
       // the values the record really holds; the reference goes on to fill the momenta of the remaining particles from
       // whatever its I/O buffer held before (read_ic.c:555-562) - those are left untouched
-      const float *in = (const float *) (image + accmom_off);
+      const float *in = (const float *) accmom_ptr;
       for(long long k = 0; k < h.npart[0]; k++)
 	((double *) (S + (k / 3) * c.L.sph_stride + c.IO.s_accreted_momentum))[k % 3] = in[k];
     }
@@ -609,5 +868,48 @@ extern "C" int gl_snapshot_read(const char *fname, const gl_gadget_layout *lay, 
   if(NumPart) *NumPart = nall;
   if(N_gas) *N_gas = h.npart[0];
   if(hdr) *hdr = h;
+  return 0;
+}
+
+// Any numeric dataset or attribute of an HDF5 file as doubles: what the tests pin the reader with (a file the HDF5 library
+// wrote), and a way to look into an initial-conditions file before P[] / SphP[] exist.  path = "/group/dataset", or
+// "/group@attribute".  dims[4], *rank <- the shape; out (may be NULL) receives up to cap values, row-major.
+extern "C" int gl_hdf5_read_f64(const char *fname, const char *path, double *out, long long cap, long long dims[4], int *rank, char *err,
+				int errlen)
+{
+  Ctx c{};
+  c.err = err;
+  c.errlen = errlen;
+  if(err && errlen > 0) err[0] = 0;
+  FileImage img;
+  if(!img.open(fname)) return c.fail("can't open file `%s'", fname);
+  try
+    {
+      glh5::Reader R(img.p, img.size);
+      glh5::Value v;
+      std::string ps(path);
+      const size_t atp = ps.find('@');
+      if(atp != std::string::npos)
+	{
+	  const glh5::u64 oh = R.find(ps.substr(0, atp));
+	  if(oh == glh5::UNDEF || !R.attribute(oh, ps.substr(atp + 1), v)) return c.fail("HDF5: no such attribute: %s", path);
+	}
+      else
+	{
+	  const glh5::u64 oh = R.find(ps);
+	  if(oh == glh5::UNDEF) return c.fail("HDF5: no such object: %s", path);
+	  R.dataset(oh, v);
+	}
+      if(rank) *rank = v.rank;
+      if(dims)
+	for(int k = 0; k < 4; k++) dims[k] = k < v.rank ? (long long) v.dims[k] : 0;
+      const long long n = (long long) v.count();
+      if(out)
+	for(long long k = 0; k < n && k < cap; k++) out[k] = v.as_double((glh5::u64) k);
+    }
+  catch(const glh5::Error &e)
+    {
+      return c.fail("%s (`%s')", e.what.c_str(), fname);
+    }
   return 0;
 }

@@ -3,7 +3,8 @@
 Python stand-in for the two reference entry points `read_ic(fname)` (read_ic.c:28) and `savepositions(num)` (io.c:33):
 it only owns the buffers (aos.GadgetArrays) and the parameter block; the files are read and written by the library
 (gl_snapshot_read / gl_snapshot_write in csrc/gl_snapshot.cu, host code, no GPU needed).  Binary formats 1 and 2,
-single file, 4-byte values - what the shipped -D list produces; format 3 (HDF5) needs a library this image lacks.
+single file, 4-byte values - what the shipped -D list produces - and format 3 (HDF5; the container is written and parsed
+by the library itself, csrc/gl_hdf5.h).
 """
 import ctypes as C
 
@@ -92,3 +93,19 @@ def read_snapshot(fname, par, max_part, max_part_sph=None, pinned=False):
         raise SnapshotError(err.value.decode())
     a.NumPart, a.N_gas = int(n.value), int(ng.value)
     return a, hdr
+
+
+def hdf5_read(fname, path):
+    """A numeric dataset ("/PartType0/Coordinates") or attribute ("/Header@Time") of an HDF5 file as a float64 array."""
+    lib = L.load_library()
+    lib.gl_hdf5_read_f64.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    dims = (C.c_longlong * 4)()
+    rank = C.c_int(0)
+    err = C.create_string_buffer(512)
+    if lib.gl_hdf5_read_f64(str(fname).encode(), path.encode(), None, 0, dims, C.byref(rank), err, len(err)):
+        raise SnapshotError(err.value.decode())
+    shape = tuple(int(dims[k]) for k in range(rank.value))
+    out = np.zeros(int(np.prod(shape)) if shape else 1)
+    if lib.gl_hdf5_read_f64(str(fname).encode(), path.encode(), out.ctypes.data, out.size, dims, C.byref(rank), err, len(err)):
+        raise SnapshotError(err.value.decode())
+    return out.reshape(shape) if shape else out[0]

@@ -408,12 +408,18 @@ int gl_gadget_push_segment_async(gl_ctx * ctx, void *P, void *SphP, int what);
 int gl_gadget_push_wait(gl_ctx * ctx);
 
 /* ---- on-disk formats: initial-conditions reader and snapshot writer --------------------------
- * The reference's binary formats 1 and 2 (All.ICFormat / All.SnapFormat; format 3 = HDF5 needs a library this image
- * does not have), single file, as the shipped -D list stores them: 4-byte floats (neither INPUT_ nor
+ * The reference's binary formats 1 and 2 and its HDF5 format 3 (All.ICFormat / All.SnapFormat; the shipped parameter file
+ * uses 3), single file, as the shipped -D list stores them: 4-byte floats (neither INPUT_ nor
  * OUTPUT_IN_DOUBLEPRECISION), 4-byte IDs (no LONGIDS), Fortran record markers, blocks in `enum iofields` order
  * (allvars.h:1762).  Files written here are byte-identical to what savepositions() (io.c:33 -> write_file :2521 ->
  * fill_write_buffer :173) writes from the same P[]/SphP[]; files are read the way read_ic() (read_ic.c:28 -> read_file
- * :634 -> empty_read_buffer :238) reads them.  Host code only - no context, no GPU. */
+ * :634 -> empty_read_buffer :238) reads them.  Format 3 (io.c:2619-2633, :2715-2800, :2866; read_ic.c:648-1060, :1333): the
+ * container is written and parsed by the library itself (csrc/gl_hdf5.h - the image has no HDF5 library): "/Header" with
+ * the header fields as attributes, "/PartType<t>/<get_dataset_name()>" contiguous datasets of the same 4-byte values the
+ * binary formats hold, in the structures libhdf5 emits for the reference's calls; the writer appends ".hdf5" to fname as
+ * the reference does.  The reader takes files libhdf5 wrote with default settings (old-style groups, contiguous or compact
+ * datasets, any integer / float width - converted like H5Dread does) and names what it does not handle (chunked or
+ * compressed datasets, libver='latest' files, big-endian data).  Host code only - no context, no GPU. */
 typedef struct gl_io_header	/* struct io_header, allvars.h:1733 (256 bytes) */
 {
   int npart[6];
@@ -447,7 +453,7 @@ typedef struct gl_io_layout
 #define GL_IO_BUILD_BH_SWALLOWGAS 16
 typedef struct gl_io_params
 {
-  int format;			/* All.SnapFormat / All.ICFormat: 1 or 2 */
+  int format;			/* All.SnapFormat / All.ICFormat: 1, 2 or 3 */
   int build;			/* GL_IO_BUILD_* mask: header flags (io.c:2589-2608), MassTable rules (read_ic.c:162-179) */
   int CoolingOn, StarformationOn;	/* All.*: NE/NH and SFR/AGE blocks exist (io.c:1652-1680) */
   int RestartFlag;		/* reader: 0 = initial conditions (blocks behind U are not read, read_ic.c:891), 2 = snapshot */
@@ -476,6 +482,11 @@ int gl_snapshot_read_header(const char *fname, int format, gl_io_header * hdr, c
 int gl_snapshot_read(const char *fname, const gl_gadget_layout * lay, const gl_io_layout * io, gl_io_params * par, void *P,
 		     void *SphP, long long MaxPart, long long MaxPartSph, long long *NumPart, long long *N_gas,
 		     gl_io_header * hdr, char *err, int errlen);
+
+/* any numeric dataset ("/PartType0/Coordinates") or attribute ("/Header@Time") of an HDF5 file as doubles; dims[4] and
+ * *rank <- its shape, out (may be NULL) <- up to cap values in row-major order */
+int gl_hdf5_read_f64(const char *fname, const char *path, double *out, long long cap, long long dims[4], int *rank, char *err,
+		     int errlen);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@
  *     void advance_and_find_timesteps(void)   proto.h / timestep.c:29     -DGL_TIMESTEP
  *     void peano_hilbert_order(void)          proto.h / peano.c:25        -DGL_PEANO_ORDER
  *     void domain_Decomposition(void)         proto.h / domain.c:100      -DGL_DOMAIN (one rank)
- *     void read_ic(char *), void savepositions(int)   read_ic.c:28, io.c:33   -DGL_SNAPSHOT_IO (formats 1 and 2, one rank)
+ *     void read_ic(char *), void savepositions(int)   read_ic.c:28, io.c:33   -DGL_SNAPSHOT_IO (formats 1, 2 and 3, one rank)
  * on top of the C ABI of include/gl_b200.h, keeps the reference's side effects (All.ErrTolTheta = 0 after the
  * first call, TreeReconstructFlag = 0, All.TotNumOfForces, CPU_Step[] buckets), leaves the mymalloc stack
  * untouched (mymalloc.c:159-164) and maps any library error onto endrun() (endrun.c:23).
@@ -460,7 +460,7 @@ void dust_drag(void)
 
 #ifdef GL_SNAPSHOT_IO
 /* ---- read_ic() / savepositions() (proto.h; read_ic.c:28, io.c:33) on the library's reader / writer -----------------
- * Binary formats 1 and 2, one file, one rank (the library has no HDF5; a multi-rank run keeps the reference's own
+ * Formats 1, 2 and 3 (HDF5 through the library's own container code), one file, one rank (a multi-rank run keeps the reference's own
  * read_ic.o / io.o).  Needs no GPU and no context.  The two derived records of a snapshot (NH, SFR) are computed here
  * with the reference's own cooling / star-formation functions and handed to the writer. */
 #include <math.h>
@@ -546,8 +546,15 @@ void read_ic(char *fname)
   int i;
 
   CPU_Step[CPU_MISC] += measure_time();
-  if(NTask > 1 || (All.ICFormat != 1 && All.ICFormat != 2))
-    gl_io_fail("read_ic", "the library reads formats 1 and 2 on a single rank; link the reference's read_ic.o otherwise", 8801);
+  if(NTask > 1 || All.ICFormat < 1 || All.ICFormat > 3)
+    gl_io_fail("read_ic", "the library reads formats 1, 2 and 3 on a single rank; link the reference's read_ic.o otherwise", 8801);
+  if(All.ICFormat == 3)
+    {
+      /* read_ic.c:88: the single-file name of an HDF5 initial-conditions file */
+      static char h5name[512];
+      snprintf(h5name, sizeof(h5name), "%s.hdf5", fname);
+      fname = h5name;
+    }
   gl_fill_layout();
   gl_io_setup(&io, &par);
   par.format = All.ICFormat;
@@ -609,8 +616,8 @@ void savepositions(int num)
   /* ensures that new tree will be constructed (io.c:47-49) */
   All.NumForcesSinceLastDomainDecomp = (long long) (1 + All.TreeDomainUpdateFrequency * All.TotNumPart);
 #endif
-  if(NTask > 1 || All.NumFilesPerSnapshot > 1 || All.SnapFormat < 1 || All.SnapFormat > 2)
-    gl_io_fail("savepositions", "the library writes formats 1 and 2, one file, on a single rank; link the reference's io.o otherwise", 8802);
+  if(NTask > 1 || All.NumFilesPerSnapshot > 1 || All.SnapFormat < 1 || All.SnapFormat > 3)
+    gl_io_fail("savepositions", "the library writes formats 1, 2 and 3, one file, on a single rank; link the reference's io.o otherwise", 8802);
   gl_fill_layout();
   gl_io_setup(&io, &par);
   par.format = All.SnapFormat;

@@ -226,7 +226,9 @@ def test_reader_fails_where_the_reference_would_endrun(tmp_path):
         rd(fn2, format=1)
     with pytest.raises(snapshot.SnapshotError, match="Not enough space"):                 # endrun(173)
         rd(fn1, n=10, format=1)
-    with pytest.raises(snapshot.SnapshotError, match="not 1 or 2"):
+    with pytest.raises(snapshot.SnapshotError, match="not 1, 2 or 3"):
+        rd(fn1, format=4)
+    with pytest.raises(snapshot.SnapshotError, match="not an HDF5 file"):
         rd(fn1, format=3)
     # a format-2 record with the wrong label: endrun(1890)
     bad = bytearray(data2)
