@@ -1421,6 +1421,179 @@ extern "C" int gl_gadget_costfactors(const gl_gadget_layout *lay, const void *Pv
   return 0;
 }
 
+// ---- the multi-rank half of domain_decompose() (domain.c:470-487) ------------------------------------------------------
+// These run identically on every rank of the reference, on leaf tables domain_sumCost has summed over the ranks
+// (domain.c:1950-1960) - so they are plain functions of those tables and of NTask, restated with the reference's
+// statements in the reference's order.  qsort() is the C library's, as in the reference: equal loads fall the same way.
+namespace
+{
+struct LoadOrigin
+{
+  double load;
+  int origin;
+};
+struct Segment
+{
+  int task, start, end;
+};
+int cmp_loadorigin(const void *a, const void *b)
+{
+  const double x = ((const LoadOrigin *) a)->load, y = ((const LoadOrigin *) b)->load;
+  return x < y ? -1 : (x > y ? +1 : 0);
+}
+int cmp_segments(const void *a, const void *b)
+{
+  const int x = ((const Segment *) a)->task, y = ((const Segment *) b)->task;
+  return x < y ? -1 : (x > y ? +1 : 0);
+}
+// domain_findSplit_work_balanced (domain.c:1075) / domain_findSplit_load_balanced (:1225): ncpu stretches of leaves of
+// about equal sum
+template <class T> void find_split(const T *v, int ncpu, int ndomain, int *start_list, int *end_list)
+{
+  double sum = 0;
+  for(int i = 0; i < ndomain; i++) sum += v[i];
+  const double avg = sum / ncpu;
+  double before = 0, avg_before = 0;
+  int start = 0;
+  for(int i = 0; i < ncpu; i++)
+    {
+      double w = 0;
+      int end = start;
+      w += v[end];
+      while((w + before < avg + avg_before) || (i == ncpu - 1 && end < ndomain - 1))
+	{
+	  if((ndomain - end) > (ncpu - i))
+	    end++;
+	  else
+	    break;
+	  w += v[end];
+	}
+      start_list[i] = start;
+      end_list[i] = end;
+      before += w;
+      avg_before += avg;
+      start = end + 1;
+    }
+}
+// domain_assign_load_or_work_balanced (domain.c:1153): the MULTIPLEDOMAINS * NTask stretches are paired, heaviest with
+// lightest, until NTask groups are left
+void assign_balanced(int mode, int NTask, int md, const float *work, const int *count, int *start_list, int *end_list, int *domain_task)
+{
+  const int nseg = md * NTask;
+  std::vector<Segment> seg((size_t) nseg);
+  std::vector<LoadOrigin> dom((size_t) nseg);
+  std::vector<int> target((size_t) nseg);
+  for(int n = 0; n < nseg; n++) seg[(size_t) n].task = n;
+  int ndomains = nseg;
+  while(ndomains > NTask)
+    {
+      for(int i = 0; i < ndomains; i++)
+	{
+	  dom[(size_t) i].load = 0;
+	  dom[(size_t) i].origin = i;
+	}
+      for(int n = 0; n < nseg; n++)
+	for(int i = start_list[n]; i <= end_list[n]; i++)
+	  {
+	    if(mode == 1)
+	      dom[(size_t) seg[(size_t) n].task].load += count[i];
+	    else
+	      dom[(size_t) seg[(size_t) n].task].load += work[i];
+	  }
+      qsort(dom.data(), (size_t) ndomains, sizeof(LoadOrigin), cmp_loadorigin);
+      for(int i = 0; i < ndomains / 2; i++)
+	{
+	  target[(size_t) dom[(size_t) i].origin] = i;
+	  target[(size_t) dom[(size_t) (ndomains - 1 - i)].origin] = i;
+	}
+      for(int n = 0; n < nseg; n++) seg[(size_t) n].task = target[(size_t) seg[(size_t) n].task];
+      ndomains /= 2;
+    }
+  for(int n = 0; n < nseg; n++)
+    {
+      seg[(size_t) n].start = start_list[n];
+      seg[(size_t) n].end = end_list[n];
+    }
+  qsort(seg.data(), (size_t) nseg, sizeof(Segment), cmp_segments);
+  for(int n = 0; n < nseg; n++)
+    {
+      start_list[n] = seg[(size_t) n].start;
+      end_list[n] = seg[(size_t) n].end;
+      for(int i = start_list[n]; i <= end_list[n]; i++) domain_task[i] = seg[(size_t) n].task;
+    }
+}
+// domain_check_memory_bound (domain.c:595)
+int memory_bound(int NTask, int md, const float *work, const int *count, const int *countsph, const int *start_list, const int *end_list,
+		 long long max_load, long long max_load_sph, int *list_load, int *list_loadsph, double *list_work)
+{
+  int max_l = 0, max_s = 0;
+  for(int ta = 0; ta < NTask; ta++)
+    {
+      int load = 0, sphload = 0;
+      double w = 0;
+      for(int m = 0; m < md; m++)
+	for(int i = start_list[ta * md + m]; i <= end_list[ta * md + m]; i++)
+	  {
+	    load += count[i];
+	    sphload += countsph ? countsph[i] : 0;
+	    w += work[i];
+	  }
+      if(list_load) list_load[ta] = load;
+      if(list_loadsph) list_loadsph[ta] = sphload;
+      if(list_work) list_work[ta] = w;
+      if(load > max_l) max_l = load;
+      if(sphload > max_s) max_s = sphload;
+    }
+  return (max_l > max_load || max_s > max_load_sph) ? 1 : 0;
+}
+}	// namespace
+
+extern "C" int gl_domain_assign(int NTask, int multipledomains, int ntopleaves, const float *leaf_work, const int *leaf_count,
+				const int *leaf_count_sph, long long max_load, long long max_load_sph, int *domain_task, int *start_list,
+				int *end_list, int *list_load, int *list_loadsph, double *list_work)
+{
+  const int md = multipledomains, nseg = md * NTask;
+  // the pairing halves the number of groups: it ends at NTask only when md is a power of two (the reference's
+  // MULTIPLEDOMAINS = 16); fewer leaves than stretches is endrun(112) (domain.c:1912)
+  if(NTask < 1 || md < 1 || (md & (md - 1)) || ntopleaves < nseg || !leaf_work || !leaf_count || !domain_task || !start_list || !end_list) return 3;
+  find_split(leaf_work, nseg, ntopleaves, start_list, end_list);
+  assign_balanced(1, NTask, md, leaf_work, leaf_count, start_list, end_list, domain_task);
+  if(!memory_bound(NTask, md, leaf_work, leaf_count, leaf_count_sph, start_list, end_list, max_load, max_load_sph, list_load, list_loadsph, list_work))
+    return 0;
+  // "the optimum balanced solution violates memory constraint, let's try something different" (domain.c:476-480)
+  find_split(leaf_count, nseg, ntopleaves, start_list, end_list);
+  assign_balanced(0, NTask, md, leaf_work, leaf_count, start_list, end_list, domain_task);
+  return memory_bound(NTask, md, leaf_work, leaf_count, leaf_count_sph, start_list, end_list, max_load, max_load_sph, list_load, list_loadsph, list_work) ? 2 : 1;
+}
+
+// domain_countToGo (domain.c:1274-1305, the part in front of the memory-limited iteration): where every local particle
+// goes under DomainTask[], and how many leave for each rank
+extern "C" int gl_domain_count_to_go(const gl_topnode *T, const gl_peanokey *Key, const int *type, long long NumPart, const int *domain_task,
+				     int ThisTask, int NTask, int *to_go, int *to_go_sph, int *dest)
+{
+  if(!T || !Key || !domain_task || !to_go || NTask < 1 || ThisTask < 0 || ThisTask >= NTask) return 3;
+  for(int n = 0; n < NTask; n++)
+    {
+      to_go[n] = 0;
+      if(to_go_sph) to_go_sph[n] = 0;
+    }
+  for(long long n = 0; n < NumPart; n++)
+    {
+      int no = 0;
+      while(T[no].Daughter >= 0) no = T[no].Daughter + (int) ((Key[n] - T[no].StartKey) / (T[no].Size >> 3));
+      no = T[no].Leaf;
+      const int ta = domain_task[no];
+      if(ta < 0 || ta >= NTask) return 3;
+      if(dest) dest[n] = ta;
+      if(ta != ThisTask)
+	{
+	  to_go[ta] += 1;
+	  if(to_go_sph && type && type[n] == 0) to_go_sph[ta] += 1;
+	}
+    }
+  return 0;
+}
+
 // domain_sumCost (domain.c:1920-1966: work and count of every top-level leaf; the work is a 4-byte float accumulated in
 // P[] order) followed by domain_findSplit_work_balanced (domain.c:1075-1113, all speed factors 1): ncpu consecutive
 // stretches of leaves of about equal work.

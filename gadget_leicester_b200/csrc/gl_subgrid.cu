@@ -931,6 +931,14 @@ extern "C" int gl_blackhole_accretion(gl_ctx *c, const int *active, long long na
   long long ns = 0;
   if(sg_targets(c, active, nactive, 5, &ns)) return 1;
   if(n_swallowed) n_swallowed[0] = n_swallowed[1] = n_swallowed[2] = 0;
+  if(ns == 0)
+    {
+      // no active sink: nothing is read or written (the caller's arrays are not even copied to the device)
+      if(st->mass)
+	GL_CUDA(c, cudaMemcpyAsync(st->mass, c->in_mass.p, n * sizeof(double), where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      return 0;
+    }
   Staged<double> vel, bhm, bhd, acd, dum, tom, rho, inj;
   Staged<int> id, swl;
   if(vel.bind(c, st->vel, 3 * n, where, true, true) || id.bind(c, st->id, n, where, true, false) || swl.bind(c, st->swallow_id, n, where, true, true) ||

@@ -140,6 +140,7 @@ EXPORTS = [
     "gl_comm_finalize", "gl_comm_set_options", "gl_get_let_stats",
     "gl_set_subgrid_params", "gl_blackhole_accretion", "gl_dust_density", "gl_dust_drag",
     "gl_gadget_blackhole_accretion", "gl_gadget_dust_density", "gl_gadget_dust_drag", "gl_hdf5_read_f64",
+    "gl_domain_assign", "gl_domain_count_to_go",
 ]
 
 _lib = None

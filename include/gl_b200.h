@@ -271,6 +271,24 @@ int gl_gadget_domain_keys(const gl_gadget_layout * lay, const void *P, long long
 int gl_gadget_costfactors(const gl_gadget_layout * lay, const void *P, long long NumPart, double *costfactor);
 int gl_domain_split(const gl_topnode * nodes, int ntopleaves, const gl_peanokey * Key, const double *costfactor, long long NumPart,
 		    int ncpu, int *start_list, int *end_list, float *leaf_work, int *leaf_count);
+/* The multi-rank half of domain_decompose() (domain.c:470-487).  In the reference these functions run
+ * identically on every rank, on leaf tables that domain_sumCost has summed over the ranks (the caller's MPI_Allreduce of
+ * the leaf_work / leaf_count tables gl_domain_split returns, domain.c:1950-1960), so they are plain functions of those
+ * tables and of NTask: the split into multipledomains * NTask stretches of about equal work (domain_findSplit_work_balanced
+ * :1075), dealt to the ranks so that the particle numbers are even (domain_assign_load_or_work_balanced(1) :1153); if a rank
+ * would then hold more than max_load particles or max_load_sph gas particles (domain_check_memory_bound :595) the split by
+ * particle number (:1225) dealt by work (mode 0) instead.  Out: domain_task[ntopleaves] = DomainTask[], start_list /
+ * end_list[multipledomains * NTask] = DomainStartList / DomainEndList (ordered by rank), list_load / list_loadsph /
+ * list_work[NTask] (may be NULL).  Returns 0 (first variant), 1 (second), 2 (neither fits: endrun(0), domain.c:483-487),
+ * 3 (bad arguments: multipledomains must be a power of two, ntopleaves >= multipledomains * NTask).  Host code only. */
+int gl_domain_assign(int NTask, int multipledomains, int ntopleaves, const float *leaf_work, const int *leaf_count,
+		     const int *leaf_count_sph, long long max_load, long long max_load_sph, int *domain_task, int *start_list,
+		     int *end_list, int *list_load, int *list_loadsph, double *list_work);
+/* domain_countToGo (domain.c:1274-1305, in front of its memory-limited iteration): dest[NumPart] (may be NULL) = the new
+ * owner of every local particle, to_go / to_go_sph[NTask] = how many (gas) particles leave for each rank.  The struct
+ * exchange itself (domain_exchange :665) stays with the caller's MPI. */
+int gl_domain_count_to_go(const gl_topnode * nodes, const gl_peanokey * Key, const int *type, long long NumPart, const int *domain_task,
+			  int ThisTask, int NTask, int *to_go, int *to_go_sph, int *dest);
 /* Individual time steps: the per-particle part of advance_and_find_timesteps() (timestep.c:29) for
  * the particles of the active list - get_timestep (timestep.c:607: acceleration, Courant, dust, sink-accretion and
  * feedback criteria of the shipped -D list), the power-of-two bin with the "only onto a synchronised bin" rule
