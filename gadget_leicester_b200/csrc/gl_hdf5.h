@@ -224,9 +224,13 @@ class Writer
 public:
   explicit Writer(std::vector<char> &meta) : m(meta) {}
   // meta <- every byte of the file in front of the raw data; groups[].dsets[].data_off / bytes <- where the raw data go;
-  // returns the length of the file
+  // returns the length of the file (0: more members in a group than one symbol-table node holds)
   u64 layout(std::vector<Group> &groups)
   {
+    // one symbol-table node per group (2 * LEAF_K entries); a snapshot has at most 7 groups and 22 datasets per group
+    if(groups.size() > 2 * (size_t) LEAF_K) return 0;
+    for(const Group &g : groups)
+      if(g.dsets.size() > 2 * (size_t) LEAF_K) return 0;
     m.assign(96, 0);		// superblock, filled in at the end
     // raw data sizes first: the dataset headers hold the addresses, and those lie behind all metadata - whose size does
     // not depend on the addresses.  So: build everything with addresses relative to the start of the data area, then

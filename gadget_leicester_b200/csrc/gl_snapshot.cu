@@ -380,6 +380,7 @@ extern "C" int gl_snapshot_write(const char *fname, const gl_gadget_layout *lay,
 	}
       glh5::Writer w(h5meta);
       off = (long long) w.layout(groups);
+      if(off <= 0) return c.fail("gl_snapshot_write: more datasets in one group than the HDF5 writer lays out");
       for(const Where &q : where)
 	{
 	  const long long at = (long long) groups[(size_t) q.group].dsets[(size_t) q.dset].data_off;
