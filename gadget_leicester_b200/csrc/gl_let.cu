@@ -888,3 +888,185 @@ extern "C" int gl_get_let_stats(gl_ctx *c, gl_let_stats *out)
   out->violations = c->let_violations;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Collective partition (SURVEY.md 8(e) "Partition"; domain.c:1075 domain_findSplit_work_balanced with ONE stretch per rank):
+// the global Peano-Hilbert order is cut into `world` stretches of equal cost and every rank learns where each of its
+// particles belongs.  No rank ever sees all keys: each sorts its own, describes its cost distribution by DS_SAMPLES keys at
+// equal steps of its cumulative cost, the samples are all-gathered and every rank derives the same world-1 splitter keys
+// from them (error per splitter <= total cost / DS_SAMPLES, 0.4 % of a stretch at 8 ranks).  The struct migration itself
+// (domain_exchange, domain.c:665) stays with the caller, who owns the structs.
+#define DS_SAMPLES 2048
+namespace
+{
+__global__ void k_ds_iota(long long n, int *idx)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i < n) idx[i] = (int) i;
+}
+__global__ void k_ds_gather_cost(long long n, const int *__restrict__ idx, const double *__restrict__ cost, double *__restrict__ out)
+{
+  const long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(k < n) out[k] = cost ? cost[idx[k]] : 1.0;
+}
+// sample s = the key at which the rank's cumulative cost reaches (s + 1/2) / DS_SAMPLES of its total
+__global__ void k_ds_samples(long long n, const unsigned long long *__restrict__ key_sorted, const double *__restrict__ cum, unsigned long long *__restrict__ out)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if(s >= DS_SAMPLES) return;
+  const double want = cum[n - 1] * ((s + 0.5) / DS_SAMPLES);
+  long long lo = 0, hi = n - 1;
+  while(lo < hi)
+    {
+      const long long mid = (lo + hi) >> 1;
+      if(cum[mid] < want)
+	lo = mid + 1;
+      else
+	hi = mid;
+    }
+  out[s] = key_sorted[lo];
+}
+__global__ void k_ds_dest(long long n, const unsigned long long *__restrict__ key, const unsigned long long *__restrict__ split, int nsplit,
+			  int *__restrict__ dest, unsigned long long *__restrict__ count)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const unsigned long long k = key[i];
+  int lo = 0, hi = nsplit;	// number of splitters <= k
+  while(lo < hi)
+    {
+      const int mid = (lo + hi) >> 1;
+      if(split[mid] <= k)
+	lo = mid + 1;
+      else
+	hi = mid;
+    }
+  dest[i] = lo;
+  atomicAdd(&count[lo], 1ull);
+}
+}	// namespace
+
+extern "C" int gl_domain_split_collective(gl_ctx *c, const double *cost, int cost_where, int *dest, int dest_where, long long *to_go,
+					   unsigned long long *splitters)
+{
+  cudaSetDevice(c->device);
+  gl_comm *cm = c->comm;
+  if(!cm) return c->fail("gl_domain_split_collective: no communicator (gl_comm_init)");
+  const int W = cm->world, me = cm->rank;
+  if(W > GL_LET_MAXRANKS) return c->fail("gl_domain_split_collective: more than 64 ranks");
+  const long long n = c->n_own > 0 ? c->n_own : c->n;
+  if(n <= 0) return c->fail("gl_domain_split_collective: no particles loaded");
+  if(!dest || !to_go) return c->fail("gl_domain_split_collective: dest and to_go are required");
+  c->n = n;			// (imports of an earlier build are not particles of this rank)
+  c->ncell = 0;
+  c->nit = n;
+  // ---- the global cube: MPI_Allreduce of the extent (domain.c:1996-1997) ----
+  {
+    GL_CUDA(c, c->dom_dev.ensure((size_t) 148 * 4 * 6 + 16 + 6 * (size_t) W));
+    if(glk_local_minmax(c, c->dom_dev.p)) return 1;
+    double *all = c->dom_dev.p + 148 * 4 * 6 + 16;
+    GL_COMM(c, cm->allgather(c->dom_dev.p, all, 6 * sizeof(double), c->stream));
+    std::vector<double> h(6 * (size_t) W);
+    GL_CUDA(c, cudaMemcpyAsync(h.data(), all, sizeof(double) * 6 * W, cudaMemcpyDeviceToHost, c->stream));
+    GL_CUDA(c, cudaStreamSynchronize(c->stream));
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for(int r = 0; r < W; r++)
+      for(int k = 0; k < 3; k++)
+	{
+	  lo[k] = std::min(lo[k], h[6 * r + k]);
+	  hi[k] = std::max(hi[k], h[6 * r + 3 + k]);
+	}
+    if(!c->domain_imposed) glk_set_domain_minmax(c, lo, hi);
+  }
+  // ---- Peano-Hilbert keys of the own particles, sorted with the cost riding along ----
+  if(glk_export_keys(c, nullptr, nullptr, 1)) return 1;	// -> c->key_ph (P[] order)
+  DBuf<unsigned long long> ksort, samples, split_dev, count;
+  DBuf<int> idx, idx_sorted, dest_dev;
+  DBuf<double> cost_dev, cs, cum;
+  struct Release
+  {
+    std::function<void()> f;
+    ~Release() { f(); }
+  } rel{ [&] { ksort.release(); samples.release(); split_dev.release(); count.release(); idx.release(); idx_sorted.release(); dest_dev.release();
+	       cost_dev.release(); cs.release(); cum.release(); } };
+  GL_CUDA(c, ksort.ensure((size_t) n)); GL_CUDA(c, idx.ensure((size_t) n)); GL_CUDA(c, idx_sorted.ensure((size_t) n));
+  GL_CUDA(c, cs.ensure((size_t) n)); GL_CUDA(c, cum.ensure((size_t) n));
+  GL_CUDA(c, samples.ensure((size_t) DS_SAMPLES * (W + 1))); GL_CUDA(c, split_dev.ensure((size_t) W)); GL_CUDA(c, count.ensure((size_t) W + 1));
+  const double *cost_p = nullptr;
+  if(cost)
+    {
+      if(cost_where)
+	cost_p = cost;
+      else
+	{
+	  GL_CUDA(c, cost_dev.ensure((size_t) n));
+	  GL_CUDA(c, cudaMemcpyAsync(cost_dev.p, cost, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	  cost_p = cost_dev.p;
+	}
+    }
+  k_ds_iota<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, idx.p);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->key_ph.p, ksort.p, idx.p, idx_sorted.p, (int) n, 0, 63, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->key_ph.p, ksort.p, idx.p, idx_sorted.p, (int) n, 0, 63, c->stream));
+  k_ds_gather_cost<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, idx_sorted.p, cost_p, cs.p);
+  tmp = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tmp, cs.p, cum.p, (int) n, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp, cs.p, cum.p, (int) n, c->stream));
+  // ---- samples + the rank's total, all-gathered ----
+  unsigned long long *mine = samples.p + (size_t) DS_SAMPLES * W;
+  k_ds_samples<<<gl_grid(DS_SAMPLES, 256), 256, 0, c->stream>>>(n, ksort.p, cum.p, mine);
+  c->kernel_launches += 6;
+  GL_COMM(c, cm->allgather(mine, samples.p, DS_SAMPLES * sizeof(unsigned long long), c->stream));
+  double *tot_all = c->dom_dev.p;	// reuse: W doubles
+  GL_COMM(c, cm->allgather(cum.p + (n - 1), tot_all, sizeof(double), c->stream));
+  std::vector<unsigned long long> hs((size_t) DS_SAMPLES * W);
+  std::vector<double> ht((size_t) W);
+  GL_CUDA(c, cudaMemcpyAsync(hs.data(), samples.p, hs.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaMemcpyAsync(ht.data(), tot_all, (size_t) W * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  // ---- the same splitters on every rank: weighted samples in key order, cut at k / world of the total ----
+  std::vector<std::pair<unsigned long long, double> > ws;
+  ws.reserve(hs.size());
+  double total = 0;
+  for(int r = 0; r < W; r++)
+    {
+      total += ht[(size_t) r];
+      for(int s = 0; s < DS_SAMPLES; s++) ws.push_back({ hs[(size_t) r * DS_SAMPLES + s], ht[(size_t) r] / DS_SAMPLES });
+    }
+  std::stable_sort(ws.begin(), ws.end(), [](const std::pair<unsigned long long, double> &a, const std::pair<unsigned long long, double> &b) { return a.first < b.first; });
+  std::vector<unsigned long long> split((size_t) W > 1 ? (size_t) W - 1 : 0);
+  {
+    double run = 0;
+    size_t k = 0;
+    for(int j = 1; j < W; j++)
+      {
+	const double want = total * j / W;
+	while(k < ws.size() && run + ws[k].second <= want)
+	  {
+	    run += ws[k].second;
+	    k++;
+	  }
+	// particles with a key >= the splitter go to rank j or beyond
+	split[(size_t) j - 1] = k < ws.size() ? ws[k].first : ~0ull;
+	if(j > 1 && split[(size_t) j - 1] < split[(size_t) j - 2]) split[(size_t) j - 1] = split[(size_t) j - 2];
+      }
+  }
+  if(splitters)
+    for(int j = 0; j + 1 < W; j++) splitters[j] = split[(size_t) j];
+  // ---- destination of every own particle (P[] order) and the to-go counts ----
+  GL_CUDA(c, dest_dev.ensure((size_t) n));
+  if(W > 1) GL_CUDA(c, cudaMemcpyAsync(split_dev.p, split.data(), (size_t) (W - 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  GL_CUDA(c, cudaMemsetAsync(count.p, 0, ((size_t) W + 1) * sizeof(unsigned long long), c->stream));
+  k_ds_dest<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->key_ph.p, split_dev.p, W - 1, dest_dev.p, count.p);
+  GL_LAUNCH_COUNT(c);
+  std::vector<unsigned long long> hc((size_t) W);
+  GL_CUDA(c, cudaMemcpyAsync(hc.data(), count.p, (size_t) W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaMemcpyAsync(dest, dest_dev.p, (size_t) n * sizeof(int), dest_where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  for(int r = 0; r < W; r++) to_go[r] = r == me ? 0 : (long long) hc[(size_t) r];
+  c->tree_valid = false;
+  c->tree_flag = true;
+  return 0;
+}

@@ -294,16 +294,35 @@ class ForcePath:
         """NCCL communicator inside the library; unique_id = the 128 bytes of gl_comm_unique_id(), broadcast by the caller."""
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._chk(self._lib.gl_comm_init(self._ctx, int(rank), int(world), C.cast(buf, C.c_void_p)))
+        self._world = int(world)
 
-    def comm_init_local(self, rank, group):
+    def comm_init_local(self, rank, group, world=None):
         """Attach to an in-process group (gl_comm_local_group_create): several contexts of one process as ranks."""
         self._chk(self._lib.gl_comm_init_local(self._ctx, int(rank), group))
+        if world is not None:
+            self._world = int(world)
 
     def comm_set_options(self, want_gravity=True, search_padding=1.25):
         self._chk(self._lib.gl_comm_set_options(self._ctx, 1 if want_gravity else 0, float(search_padding)))
 
     def comm_finalize(self):
         self._chk(self._lib.gl_comm_finalize(self._ctx))
+
+    def domain_split_collective(self, cost=None):
+        """SURVEY 8(e) partition: where each loaded particle belongs when the global Peano-Hilbert order is cut into
+        `world` stretches of equal cost.  Returns (dest[n], to_go[world], splitters[world-1]); collective."""
+        n = self.N
+        dest = np.zeros(n, dtype=np.int32)
+        world = self._world if hasattr(self, "_world") else 1
+        togo = (C.c_longlong * max(world, 1))()
+        spl = np.zeros(max(world - 1, 1), dtype=np.uint64)
+        cp = None
+        if cost is not None:
+            cost = np.ascontiguousarray(cost, dtype=np.float64)
+            assert cost.size == n
+            cp = L._ptr(cost)
+        self._chk(self._lib.gl_domain_split_collective(self._ctx, cp, 0, L._ptr(dest), 0, togo, L._ptr(spl)))
+        return dest, np.array(list(togo), dtype=np.int64), spl[: max(world - 1, 0)]
 
     def let_stats(self):
         st = L.GLLetStats()

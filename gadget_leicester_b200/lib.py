@@ -140,7 +140,7 @@ EXPORTS = [
     "gl_comm_finalize", "gl_comm_set_options", "gl_get_let_stats",
     "gl_set_subgrid_params", "gl_blackhole_accretion", "gl_dust_density", "gl_dust_drag",
     "gl_gadget_blackhole_accretion", "gl_gadget_dust_density", "gl_gadget_dust_drag", "gl_hdf5_read_f64",
-    "gl_domain_assign", "gl_domain_count_to_go",
+    "gl_domain_assign", "gl_domain_count_to_go", "gl_domain_split_collective",
 ]
 
 _lib = None
@@ -207,6 +207,7 @@ def load_library():
     lib.gl_comm_finalize.argtypes = [vp]
     lib.gl_comm_set_options.argtypes = [vp, C.c_int, C.c_double]
     lib.gl_reset_launch_count.argtypes = [vp]
+    lib.gl_domain_split_collective.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.POINTER(C.c_longlong), vp]
     lib.gl_set_subgrid_params.argtypes = [vp, C.POINTER(GLSubgridParams)]
     lib.gl_blackhole_accretion.argtypes = [vp, vp, C.c_longlong, C.POINTER(GLSinkState), C.c_int, C.POINTER(C.c_longlong)]
     lib.gl_dust_density.argtypes = [vp, vp, C.c_longlong, vp, C.c_int]

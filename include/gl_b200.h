@@ -193,6 +193,16 @@ int gl_comm_finalize(gl_ctx * ctx);
 /* want_gravity = 0: the export test leaves out the gravity opening criteria (a run that only calls density / hydro);
  * search_padding (>= 1, default 1.3): factor on the search radii in the export test (room for Hsml to grow) */
 int gl_comm_set_options(gl_ctx * ctx, int want_gravity, double search_padding);
+/* Collective partition (domain.c:1075 domain_findSplit_work_balanced with one stretch per rank): the global
+ * Peano-Hilbert order of ALL ranks' particles is cut into `world` stretches of equal cost, and every rank learns where each
+ * of its loaded particles belongs: dest[n] (where = 0 host / 1 device), to_go[world] (host; 0 for the rank itself) - the
+ * toGo row of domain_countToGo (domain.c:1274).  cost[n]: the reference's (1 + GravCost) / 2^TimeBin (domain.c:378), NULL =
+ * equal costs.  splitters[world-1] (may be NULL) <- the first Peano-Hilbert key of ranks 1 .. world-1, the same on every
+ * rank.  No rank sees all keys: each describes its cost distribution by 2048 sample keys, which are all-gathered (balance
+ * within world / 2048 of a stretch).  The struct migration (domain_exchange, domain.c:665) stays with the caller.  Every
+ * rank must call it; the tree is invalidated. */
+int gl_domain_split_collective(gl_ctx * ctx, const double *cost, int cost_where, int *dest, int dest_where, long long *to_go,
+			       unsigned long long *splitters);
 typedef struct gl_let_stats
 {
   long long own_particles, exported_cells, exported_particles, imported_cells, imported_particles;

@@ -162,3 +162,63 @@ def test_dropin_call_on_every_ranks_own_arrays():
             num = np.abs(a - b) if a.ndim == 1 else np.linalg.norm(a - b, axis=-1)
             den = np.abs(b) if a.ndim == 1 else np.linalg.norm(b, axis=-1)
             assert (num / np.maximum(den, 1e-300)).max() <= 1e-11, k
+
+
+def test_collective_partition_cuts_the_global_peano_hilbert_order_by_cost():
+    """SURVEY 8(e) partition (gl_domain_split_collective): four ranks holding an ARBITRARY quarter of a disc each (every
+    fourth particle) agree on three splitter keys; every particle is sent to the rank whose stretch of the global
+    Peano-Hilbert order holds its key, and the stretches carry equal cost (costs spread over 2^6 here) to within the
+    sampling error - against the exact cut computed from all keys at once."""
+    import threading
+    from gadget_leicester_b200 import ics, lib as L
+    from gadget_leicester_b200.gadget import ForcePath
+    world = 4
+    par = ics.default_params()
+    ps = ics.disc(119999, seed=31)                       # + 2 sinks: 120 001 particles, not a multiple of the rank count
+    n = ps["pos"].shape[0]
+    g = np.random.default_rng(3)
+    cost = 2.0 ** (-g.integers(0, 7, n).astype(np.float64))
+    lib = L.load_library()
+    group = lib.gl_comm_local_group_create(world)
+    res, err = [None] * world, [None] * world
+
+    def worker(r):
+        try:
+            mine = np.arange(r, n, world)
+            psr = {k: (np.ascontiguousarray(v[mine]) if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+            fp = ForcePath(par)
+            fp.comm_init_local(r, group, world)
+            fp.load(psr)
+            dest, togo, spl = fp.domain_split_collective(cost[mine])
+            keys = fp.peano_and_morton_keys()[0]
+            res[r] = (mine, dest, togo, spl, keys)
+            fp.close()
+        except Exception as ex:   # noqa: BLE001
+            err[r] = ex
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    lib.gl_comm_local_group_destroy(group)
+    for e in err:
+        if e is not None:
+            raise e
+    spl = res[0][3]
+    assert spl.size == world - 1 and (np.diff(spl.astype(np.float64)) >= 0).all()
+    dest = np.zeros(n, np.int32)
+    keys = np.zeros(n, np.uint64)
+    for r in range(world):
+        mine, d, togo, s, k = res[r]
+        assert np.array_equal(s, spl)                                   # the same splitters everywhere
+        dest[mine], keys[mine] = d, k
+        assert togo[r] == 0 and all(togo[q] == (d == q).sum() for q in range(world) if q != r)
+    assert np.array_equal(dest, np.searchsorted(spl, keys, side="right"))       # a key decides the owner, monotonically
+    share = np.array([cost[dest == r].sum() for r in range(world)]) / cost.sum()
+    assert np.abs(share - 1.0 / world).max() < 2.0 * world / 2048 / world + 1e-3, share
+    # against the exact cut of the global order
+    order = np.argsort(keys, kind="stable")
+    cum = np.cumsum(cost[order])
+    exact = np.zeros(n, np.int32)
+    exact[order] = np.minimum((cum - cost[order] * 0.5) / cum[-1] * world, world - 1).astype(np.int32)
+    assert (exact != dest).mean() < 0.01
