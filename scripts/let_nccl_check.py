@@ -52,7 +52,20 @@ def main():
     own = ref[d.lo:d.hi]
     bad = torch.stack([(mine["gravcost"].double() != own[:, 0]).sum(), (mine["acc"] != own[:, 1:4]).any(dim=1).sum()]).double()
     dist.all_reduce(bad)
+    # the collective partition over the same communicator: every rank must arrive at the same splitter keys, and the
+    # stretches must carry equal numbers of particles (equal costs)
+    dest, togo, spl = d.fp.domain_split_collective()
+    sp = torch.from_numpy(spl.astype(np.int64)).cuda()
+    allsp = [torch.zeros_like(sp) for _ in range(world)]
+    dist.all_gather(allsp, sp)
+    cnt = torch.from_numpy(np.bincount(dest, minlength=world).astype(np.float64)).cuda()
+    dist.all_reduce(cnt)
+    same = all(bool((q == sp).all()) for q in allsp)
+    share = (cnt / cnt.sum()).cpu().numpy()
+    part_ok = same and float(np.abs(share - 1.0 / world).max()) < 0.005
+    bad = torch.cat([bad, torch.tensor([0.0 if part_ok else 1.0], dtype=torch.float64, device="cuda")])
     if rank == 0:
+        print("collective partition: splitters agree %s, shares %s" % (same, np.round(share, 4)))
         st = d.fp.let_stats()
         print("rank 0 imported %d particles + %d cells of %d foreign particles; violations %d" % (
             st["imported_particles"], st["imported_cells"], n - st["own_particles"], st["violations"]))
