@@ -47,10 +47,16 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define GL_GAMMA (7. / 5.)	// allvars.h:64
 #define GL_GAMMA_MINUS1 (GL_GAMMA - 1)
 #define BOX_SLACK 1.0000000001
+#ifndef CAND_CAP
 #define CAND_CAP 192		// staged candidates per warp
+#endif
+#ifndef QCAP
 #define QCAP 32			// lane = target mode: entries of every lane's private hit queue (power of two)
+#endif
 #define SPH_WARPS 2		// warps per block: 64-thread blocks (3.48 / 3.70 ms density / hydro; 128 threads 3.57 / 3.75, 32 threads 3.52 / 3.74)
+#ifndef STK_CAP
 #define STK_CAP 512
+#endif
 #define LT_MIN_ACTIVE 12	// with at least this many active targets a warp runs lane = target (see density_chunk_lt)
 #define FAT_THRESH 4096	// neighbours above which a target leaves the warp path
 #define FAT_MAX 64
