@@ -302,6 +302,46 @@ def big_config(args):
         dist.destroy_process_group()
 
 
+def resident_loop(ForcePath, par, ps, n, ksteps):
+    """run.c:63-110 on the device-resident state (gl_run_begin / gl_run_steps): every step = TimeBinCount histogram ->
+    next sync point -> drift of all particles -> tree rebuild + gravity + density + hmax + hydro for the active ones ->
+    advance_and_find_timesteps.  MaxSizeTimestep is two ticks of the integer time line, so every particle stays on bin 1
+    and every step is a full step (all particles active) - the same force work as `value`, plus drift and kick."""
+    import time
+    import numpy as np
+    import torch
+    tbi = par["Timebase_interval"]
+    ps = dict(ps)
+    ps["timebin"] = np.ones(n, dtype=np.int32)
+    ps["ti_begstep"] = np.zeros(n, dtype=np.int32)
+    fp = ForcePath(dict(par, ErrTolTheta=0.0, Ti_Current=2))
+    fp.load(ps)
+    fp.compute_accelerations()
+    fp.run_begin(2)
+    t = fp.timestep_params(2, [1, 1] + [0] * 27, Timebase_interval=tbi, ErrTolIntAccuracy=0.025, CourantFac=0.15, MaxSizeTimestep=2 * tbi,
+                           MinSizeTimestep=0.0, MinEgySpec=0.0, SofteningTable=par["Softening"], OuterBoundary=1.4e10,
+                           UnitVelocity_in_cm_per_s=2.98e6, FeedBackVelocity=1.0, SMBHmass=0.5, InnerBoundary=2.0e-2, SinkBoundary=1.0e-4,
+                           AccDtBlackHole=0.007)
+    fp.advance_and_find_timesteps(t)
+    fp.run(t, 3)                                          # warm-up
+    torch.cuda.synchronize()
+    fp.reset_launch_count()
+    t0 = time.perf_counter()
+    info = fp.run(t, ksteps)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / ksteps
+    launches = fp.stats()["kernel_launches"]
+    st = fp.run_state(int((ps["type"] == 0).sum()))
+    out = dict(value=info["interactions"] / ksteps / wall, unit=UNIT, ms_per_step=wall * 1e3, device_ms_per_step=info["ms_total"] / ksteps,
+               steps=ksteps, active_per_step=info["active_total"] / ksteps, particles=n, Ti_Current=int(t.Ti_Current),
+               bins_in_use=sorted(int(b) for b in np.unique(st["TimeBin"])), gpu_launches=int(launches),
+               h2d_bytes_per_step=0, d2h_bytes_per_step=128 + 3 * 24 + 8 + 8,
+               api="gl_run_steps: find_next_sync_point_and_drift + compute_accelerations + advance_and_find_timesteps per step on the "
+                   "state in HBM; per step only TimeBinCount[32] and the phases' counters come back (wall clock, host loop included)")
+    fp.close()
+    return out
+
+
 def identity_check(dfp, ps, par, n, rank, world, dist):
     """One more step on N ranks and the same step on ONE GPU (rank 0) from the same state (Hsml and OldAcc gathered from
     the ranks): interaction counts, pair counts and accelerations of every rank's own particles must be those of the
@@ -719,6 +759,14 @@ def main():
                    steps=ksteps, api="gl_gadget_compute_accelerations on pinned host P[]/SphP[] (pack + H2D, force path, pipelined D2H + scatter)")
         fp.close()
 
+    # ---- run()'s loop with the state resident in HBM: drift + force path + kick per step, nothing but TimeBinCount[] crosses PCIe ----
+    resident = None
+    if not args.no_e2e and world == 1:
+        try:
+            resident = resident_loop(ForcePath, par, ps2, n, max(2, min(args.steps, 10)))
+        except Exception as ex:  # an extra record, never a reason to lose the bench line
+            resident = dict(error=str(ex)[:300])
+
     # ---- strong scaling on the 2^27-particle sets (north_star: >= 70 % at 8 GPUs), part of the N > 1 line ----
     strong = None
     if dist is not None and use_let and not args.no_strong and args.config == 0:
@@ -768,6 +816,8 @@ def main():
                 wall_phase_ms={k: round(v, 3) for k, v in wall.items()}, rank_phase_ms=rank_phase)
     if e2e is not None:
         line["e2e"] = e2e
+    if resident is not None:
+        line["resident_loop"] = resident
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     if parity is not None:

@@ -48,6 +48,9 @@ extern "C" void gl_destroy(gl_ctx *c)
   gll_release(c);
   c->c_key.release(); c->c_level.release(); c->c_sm.release(); c->c_aux.release(); c->s_lev.release(); c->let_hsml_backup.release();
   c->in_velpred.release();
+  c->run_err.release();
+  c->run_hist.release();
+  c->run_list.release();
   c->dma_rows.release();
   if(c->ev_blk) cudaEventDestroy(c->ev_blk);
   for(int i = 0; i < 4; i++)
@@ -154,6 +157,7 @@ extern "C" int gl_load_particles(gl_ctx *c, long long n, const double *pos, cons
   c->tree_flag = true;
   c->tgt_dirty = true;
   c->have_velpred = false;
+  c->run_ready = false;
   if(!c->domain_imposed) c->have_domain = false;
   return 0;
 }
@@ -295,6 +299,7 @@ extern "C" int gl_load_particles_gathered(gl_ctx *c, long long n, int world, lon
   c->tree_flag = true;
   c->tgt_dirty = true;
   c->have_velpred = false;
+  c->run_ready = false;
   if(!c->domain_imposed) c->have_domain = false;
   return 0;
 }

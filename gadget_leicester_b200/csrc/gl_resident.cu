@@ -1,0 +1,517 @@
+// gl_resident.cu - run()'s loop (run.c:63-110) with the particle state resident in HBM (device side).
+//
+// The reference alternates find_next_sync_point_and_drift (run.c:190) -> domain_Decomposition -> compute_accelerations
+// (accel.c:27) -> advance_and_find_timesteps (timestep.c:29) on P[] / SphP[] in host memory.  The drop-in call
+// gl_gadget_compute_accelerations moves those structs through the host's DRAM twice per step, which costs more than
+// the force computation.  Here the state the loop carries from one step to the next stays in the
+// context's input-order arrays (in_pos, in_vel, in_velpred, in_hsml, in_entropy, in_dtentropy, in_timebin,
+// in_tibegstep, in_oldacc, o_acc, o_hacc, o_maxsig, o_density, o_pressure, o_dhsml, o_divvel, o_curlvel) and three
+// kernels restate the per-particle statements of the host-side pieces on it:
+//   k_run_drift   drift_particle (predict.c:129-260) for every particle to the new All.Ti_Current - the reference
+//                 drifts the active ones at the sync point (run.c:325) and all others in domain_Decomposition
+//                 (domain.c:122) or lazily from the walks (forcetree.c:1912, ngb.c:58); with a new decomposition
+//                 and tree in every step (how this path runs) that is one drift of everything per step;
+//   k_run_kick    get_timestep (timestep.c:607) -> power-of-two bin with the "only onto a synchronised bin" rule
+//                 (timestep.c:136-154) -> do_the_kick (timestep.c:364) for the particles on active bins;
+//   k_run_bins    TimeBinCount[] (timestep.c:170-233 keeps it by relinking lists; a histogram is all the next sync
+//                 point needs, run.c:199-216).
+// The statements and their order are those of gl_gadget_drift / gl_gadget_advance_and_find_timesteps (host, bit-
+// identical to the reference); on the device exp() / pow() / sqrt() are CUDA's (<= 2 ulp from glibc's), so the
+// floating-point state agrees to rounding and the integer time line agrees except for a step that falls within an
+// ulp of a power-of-two boundary.  Checked against eight iterations of the reference's own loop (harness op L) by
+// tests/test_gpu_resident.py.  Non-comoving integration, no dynamic tree update (the tree is rebuilt every step).
+#include "gl_internal.h"
+#include <cub/cub.cuh>
+
+namespace
+{
+const int TIMEBASE = 1 << 29;	// allvars.h:39-41 (TIMEBINS 29)
+
+struct RunPar
+{
+  int ti_current;
+  unsigned active_mask;		// bit b: TimeBinActive[b]
+  double tbi, errtolint, courant, maxstep, minstep, minegyspec, gm1;
+  double softtab[6];
+  double outer, unitvel, feedvel, smbh, inner, sinkb, accdt;
+};
+
+RunPar make_runpar(const gl_timestep_params *T)
+{
+  RunPar r{};
+  r.ti_current = T->Ti_Current;
+  for(int b = 0; b < 32; b++)
+    if(T->TimeBinActive[b]) r.active_mask |= (1u << b);
+  r.tbi = T->Timebase_interval; r.errtolint = T->ErrTolIntAccuracy; r.courant = T->CourantFac;
+  r.maxstep = T->MaxSizeTimestep; r.minstep = T->MinSizeTimestep; r.minegyspec = T->MinEgySpec; r.gm1 = T->GammaMinus1;
+  for(int i = 0; i < 6; i++) r.softtab[i] = T->SofteningTable[i];
+  r.outer = T->OuterBoundary; r.unitvel = T->UnitVelocity_in_cm_per_s; r.feedvel = T->FeedBackVelocity;
+  r.smbh = T->SMBHmass; r.inner = T->InnerBoundary; r.sinkb = T->SinkBoundary; r.accdt = T->AccDtBlackHole;
+  return r;
+}
+
+__device__ __forceinline__ void run_fail(int *err, int code, long long p)
+{
+  if(atomicCAS(&err[0], 0, code) == 0) err[1] = (int) p;	// keep the first
+}
+
+// predict.c:129-260 for particle i, from time0 to time1 (every particle sits at time0: the loop drifts all of them)
+__global__ void k_run_drift(long long n, long long ngas, int time0, int time1, double tbi, double mingashsml, const int *__restrict__ type,
+			    double *__restrict__ pos, const double *__restrict__ vel, double *__restrict__ velpred,
+			    const double *__restrict__ gacc, const double *__restrict__ hacc, double *__restrict__ density,
+			    double *__restrict__ hsml, double *__restrict__ pressure, const double *__restrict__ divvel,
+			    const double *__restrict__ entropy, const double *__restrict__ dtentropy, const int *__restrict__ timebin,
+			    const int *__restrict__ tibegstep)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const int ty = type[i];
+  if(ty == 3) return;		// predict.c:134 (-DVIRTUAL)
+  const double dt = (time1 - time0) * tbi;	// predict.c:165: dt_drift = dt_gravkick = dt_hydrokick
+#pragma unroll
+  for(int j = 0; j < 3; j++) pos[3 * i + j] = __dadd_rn(pos[3 * i + j], __dmul_rn(vel[3 * i + j], dt));	// predict.c:169-170
+  if(ty == 0 && i < ngas)
+    {
+#pragma unroll
+      for(int j = 0; j < 3; j++)	// predict.c:185-186 (DragAccel stays 0 here: the dust loops are not part of this loop)
+	velpred[3 * i + j] = __dadd_rn(velpred[3 * i + j], __dadd_rn(__dmul_rn(gacc[3 * i + j], dt), __dmul_rn(hacc[3 * i + j], dt)));
+      const double divv = divvel[i];
+      const double rho = __dmul_rn(density[i], exp(__dmul_rn(-divv, dt)));	// predict.c:204
+      double h = __dmul_rn(hsml[i], exp(__dmul_rn(__dmul_rn(0.333333333333, divv), dt)));	// predict.c:205
+      if(h < mingashsml) h = mingashsml;
+      density[i] = rho;
+      hsml[i] = h;
+      const int tb = timebin[i];
+      const int dt_step = tb ? (1 << tb) : 0;
+      const double dt_entr = (time1 - (tibegstep[i] + dt_step / 2)) * tbi;	// predict.c:213
+      pressure[i] = __dmul_rn(__dadd_rn(entropy[i], __dmul_rn(dtentropy[i], dt_entr)), pow(rho, 7.0 / 5));	// predict.c:217
+    }
+}
+
+// get_timestep(p, &aphys, 0), timestep.c:607-1122, on the SoA state; < 0 after a failure
+__device__ int run_get_timestep(const RunPar &T, long long p, int type, double mass, double hsml, double ax, double ay, double az,
+				double maxsig, int *err)
+{
+  double ac = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
+  if(ac == 0) ac = 1.0e-30;
+  // TypeOfTimestepCriterion 0, timestep.c:676-708 (DeltaDustMomentum is zero without the dust loops: timestep.c:681-701
+  // then re-forms the same ac and dt)
+  double dt = sqrt(2 * T.errtolint * 1.0 * T.softtab[type] / ac);
+  if(type == 2) dt = dt / 2;
+  if(type == 0) dt = sqrt(2 * T.errtolint * 1.0 * hsml / 2.8 / ac);
+  if(type == 0)
+    {
+      const double dt_courant = 2 * T.courant * hsml / maxsig;	// timestep.c:853-866
+      if(dt_courant < dt) dt = dt_courant;
+    }
+  if(type == 3)
+    {
+      // timestep.c:889-900 (NewDensity is zero for every particle this loop can hold; see gl_run_begin)
+      double dt_abs = 0.03 * T.outer / 2.9979e10 * T.unitvel * T.feedvel;
+      const double dt_ff = 1.;
+      if(dt_abs > dt_ff) dt_abs = dt_ff;
+      if(dt > dt_abs) dt = dt_abs;
+    }
+  if(type == 5)
+    {
+      // sink particles, timestep.c:909-950
+      double dt_accr = 0.03 * (T.outer / 100.), dt_a = 1.e10;
+      if(mass >= 0.45 * T.smbh && T.inner > 0) dt_a = T.accdt * pow((T.inner + 0.5 * hsml), 1.5) / pow(mass, 0.5);
+      if(mass < 0.45 * T.smbh && T.sinkb > 0) dt_a = T.accdt * pow((T.sinkb + 0.5 * hsml), 1.5) / pow(mass, 0.5);
+      if(dt_accr > dt_a) dt_accr = dt_a;
+      if(dt_accr < dt) dt = dt_accr;
+    }
+  if(dt >= T.maxstep) dt = T.maxstep;	// timestep.c:1042-1122 (hubble_a = 1, dt_displacement = MaxSizeTimestep)
+  if(dt < T.minstep)
+    {
+      run_fail(err, 888, p);
+      return -1;
+    }
+  const int ti_step = (int) (dt / T.tbi);
+  if(!(ti_step > 0 && ti_step < TIMEBASE))
+    {
+      run_fail(err, 818, p);
+      return -1;
+    }
+  return ti_step;
+}
+
+// the per-particle body of advance_and_find_timesteps (timestep.c:127-168, :236-260) + do_the_kick (timestep.c:364-601)
+__global__ void k_run_kick(long long n, long long ngas, RunPar T, const int *__restrict__ type, const double *__restrict__ mass,
+			   const double *__restrict__ hsml, const double *__restrict__ gacc, const double *__restrict__ hacc,
+			   const double *__restrict__ maxsig, const double *__restrict__ density, double *__restrict__ vel,
+			   double *__restrict__ velpred, double *__restrict__ entropy, double *__restrict__ dtentropy,
+			   const double *__restrict__ dtentr_new, int *__restrict__ timebin, int *__restrict__ tibegstep, int *__restrict__ err)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const int binold = timebin[i];
+  if(binold < 0 || binold > 31 || !((T.active_mask >> binold) & 1u)) return;
+  const int ty = type[i];
+  const bool gas = ty == 0 && i < ngas;
+  const double g0 = gacc[3 * i], g1 = gacc[3 * i + 1], g2 = gacc[3 * i + 2];
+  double h0 = 0, h1 = 0, h2 = 0;
+  if(gas)
+    {
+      h0 = hacc[3 * i]; h1 = hacc[3 * i + 1]; h2 = hacc[3 * i + 2];
+      // the hydro force of this step belongs to this particle: SphP.e.DtEntropy <- hydra.c:785-813
+      if(dtentr_new) dtentropy[i] = dtentr_new[i];
+    }
+  // timestep.c:636-650 (fac1 = 1; DragAccel = 0)
+  const double ax = gas ? __dadd_rn(g0, h0) : g0, ay = gas ? __dadd_rn(g1, h1) : g1, az = gas ? __dadd_rn(g2, h2) : g2;
+  int ti_step = run_get_timestep(T, i, ty, mass[i], hsml[i], ax, ay, az, gas ? maxsig[i] : 1.0, err);
+  if(ti_step < 0) return;
+  int ti_min = TIMEBASE;	// timestep.c:141-144
+  while(ti_min > ti_step) ti_min >>= 1;
+  ti_step = ti_min;
+  if(ti_step == 1)
+    {
+      run_fail(err, 112313, i);	// get_timestep_bin, timestep.c:1226-1246
+      return;
+    }
+  int bin = -1;
+  for(int t = ti_step; t; t >>= 1) bin++;
+  if(ti_step == 0) bin = 0;
+  if(bin > binold && !((T.active_mask >> bin) & 1u))	// timestep.c:147-154
+    {
+      bin = binold;
+      ti_step = bin ? (1 << bin) : 0;
+    }
+  if(T.ti_current >= TIMEBASE)
+    {
+      ti_step = 0;
+      bin = 0;
+    }
+  if((TIMEBASE - T.ti_current) < ti_step)
+    {
+      run_fail(err, 889, i);
+      return;
+    }
+  if(bin != binold) timebin[i] = bin;
+  const int ti_step_old = binold ? (1 << binold) : 0;
+  const int beg = tibegstep[i];
+  const int tstart = beg + ti_step_old / 2, tend = beg + ti_step_old + ti_step / 2, tcur = beg + ti_step_old;
+  tibegstep[i] = tcur;
+  // ---- do_the_kick(i, tstart, tend, tcur) ----
+  if(ty == 3) return;		// -DVIRTUAL, timestep.c:379
+  const double dt_kick = (tend - tstart) * T.tbi, dt_kick2 = (tend - tcur) * T.tbi;
+  double v0 = vel[3 * i], v1 = vel[3 * i + 1], v2 = vel[3 * i + 2];
+  if(ty != 2)			// dust is moved by the drag module (timestep.c:478-485): dv = 0
+    {
+      v0 = __dadd_rn(v0, __dmul_rn(g0, dt_kick));
+      v1 = __dadd_rn(v1, __dmul_rn(g1, dt_kick));
+      v2 = __dadd_rn(v2, __dmul_rn(g2, dt_kick));
+    }
+  if(gas)
+    {
+      v0 = __dadd_rn(v0, __dmul_rn(h0, dt_kick));
+      v1 = __dadd_rn(v1, __dmul_rn(h1, dt_kick));
+      v2 = __dadd_rn(v2, __dmul_rn(h2, dt_kick));
+      velpred[3 * i] = __dsub_rn(__dsub_rn(v0, __dmul_rn(dt_kick2, g0)), __dmul_rn(dt_kick2, h0));
+      velpred[3 * i + 1] = __dsub_rn(__dsub_rn(v1, __dmul_rn(dt_kick2, g1)), __dmul_rn(dt_kick2, h1));
+      velpred[3 * i + 2] = __dsub_rn(__dsub_rn(v2, __dmul_rn(dt_kick2, g2)), __dmul_rn(dt_kick2, h2));
+      double A = entropy[i], dA = dtentropy[i];
+      if(__dmul_rn(dA, dt_kick) > __dmul_rn(-0.5, A))	// timestep.c:546-551
+	A = __dadd_rn(A, __dmul_rn(dA, dt_kick));
+      else
+	A = __dmul_rn(A, 0.5);
+      if(T.minegyspec != 0)
+	{
+	  const double minentropy = T.minegyspec * T.gm1 / pow(density[i], T.gm1);
+	  if(A < minentropy)
+	    {
+	      A = minentropy;
+	      dA = 0;
+	    }
+	}
+      // the same limit for the predicted entropy at the middle of the NEW step (timestep.c:577-583)
+      const double dt_entr = (bin ? (1 << bin) : 0) / 2 * T.tbi;
+      if(__dadd_rn(A, __dmul_rn(dA, dt_entr)) < __dmul_rn(0.5, A)) dA = __dmul_rn(-0.5, A) / dt_entr;
+      entropy[i] = A;
+      dtentropy[i] = dA;
+    }
+  vel[3 * i] = v0; vel[3 * i + 1] = v1; vel[3 * i + 2] = v2;
+}
+
+__global__ void k_run_bins(long long n, const int *__restrict__ timebin, int *__restrict__ hist)
+{
+  __shared__ int sh[32];
+  if(threadIdx.x < 32) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for(long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x)
+    {
+      const int b = timebin[i];
+      if(b >= 0 && b < 32) atomicAdd(&sh[b], 1);
+    }
+  __syncthreads();
+  if(threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void k_run_active_flags(long long n, unsigned mask, const int *__restrict__ timebin, int *__restrict__ flag)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const int b = timebin[i];
+  flag[i] = (b >= 0 && b < 32 && ((mask >> b) & 1u)) ? 1 : 0;
+}
+
+// the gas block leads (allvars.h: SphP[i] belongs to P[i], i < N_gas): count it and check that nothing else is gas
+__global__ void k_run_count_gas(long long n, const int *__restrict__ type, int *__restrict__ out)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  if(type[i] == 0)
+    {
+      atomicAdd(&out[0], 1);
+      atomicMax(&out[1], (int) i);
+    }
+}
+
+__global__ void k_run_copy_gas_vel(long long ngas, const double *__restrict__ vel, double *__restrict__ velpred)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i < 3 * ngas) velpred[i] = vel[i];
+}
+
+int run_check_err(gl_ctx *c, const char *where)
+{
+  int h[2] = { 0, 0 };
+  GL_CUDA(c, cudaMemcpyAsync(h, c->run_err.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, cudaGetLastError());
+  if(h[0] == 0) return 0;
+  const char *what = h[0] == 888 ? "timestep below MinSizeTimestep (endrun 888)"
+    : h[0] == 818 ? "a timestep of size zero was assigned on the integer timeline (endrun 818)"
+    : h[0] == 112313 ? "time-step of integer size 1 not allowed (endrun 112313)" : "step beyond the end of the time line (endrun 888)";
+  return c->fail(std::string(where) + ": " + what + ", particle " + std::to_string(h[1]));
+}
+
+int run_kick(gl_ctx *c, const gl_timestep_params *tp, bool commit_dtentropy)
+{
+  const long long n = c->n;
+  const RunPar T = make_runpar(tp);
+  GL_CUDA(c, cudaMemsetAsync(c->run_err.p, 0, 2 * sizeof(int), c->stream));
+  k_run_kick<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->run_ngas, T, c->in_type.p, c->in_mass.p, c->in_hsml.p, c->o_acc.p, c->o_hacc.p,
+						       c->o_maxsig.p, c->o_density.p, c->in_vel.p, c->in_velpred.p, c->in_entropy.p,
+						       c->in_dtentropy.p, commit_dtentropy ? c->o_dtentr.p : nullptr, c->in_timebin.p,
+						       c->in_tibegstep.p, c->run_err.p);
+  GL_LAUNCH_COUNT(c);
+  return run_check_err(c, "advance_and_find_timesteps");
+}
+}				// namespace
+
+// ---------------------------------------------------------------- C ABI ----
+extern "C" int gl_set_velpred(gl_ctx *c, const double *velpred3, long long n_gas, int where)
+{
+  cudaSetDevice(c->device);
+  if(c->n <= 0) return c->fail("gl_set_velpred: no particles");
+  if(n_gas < 0 || n_gas > c->n || (n_gas > 0 && !velpred3)) return c->fail("gl_set_velpred: bad arguments");
+  GL_CUDA(c, c->in_velpred.ensure(3 * (size_t) std::max<long long>(n_gas, 1)));
+  if(n_gas > 0)
+    GL_CUDA(c, cudaMemcpyAsync(c->in_velpred.p, velpred3, 3 * n_gas * sizeof(double), where ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+			       c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_velpred = n_gas;
+  c->have_velpred = n_gas > 0;
+  if(c->tree_valid && glk_apply_velpred(c)) return 1;
+  return 0;
+}
+
+extern "C" int gl_set_accelerations(gl_ctx *c, const double *gravaccel3, const double *hydroaccel3, const double *maxsignalvel, int where)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n;
+  if(n <= 0) return c->fail("gl_set_accelerations: no particles");
+  const cudaMemcpyKind k = where ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if(gravaccel3)
+    {
+      GL_CUDA(c, c->o_acc.ensure(3 * (size_t) n));
+      GL_CUDA(c, cudaMemcpyAsync(c->o_acc.p, gravaccel3, 3 * n * sizeof(double), k, c->stream));
+    }
+  if(hydroaccel3)
+    {
+      GL_CUDA(c, c->o_hacc.ensure(3 * (size_t) n));
+      GL_CUDA(c, cudaMemcpyAsync(c->o_hacc.p, hydroaccel3, 3 * n * sizeof(double), k, c->stream));
+    }
+  if(maxsignalvel)
+    {
+      GL_CUDA(c, c->o_maxsig.ensure((size_t) n));
+      GL_CUDA(c, cudaMemcpyAsync(c->o_maxsig.p, maxsignalvel, n * sizeof(double), k, c->stream));
+    }
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// The state the loop needs must be in the context: the particle set (gl_load_particles), the SphP state
+// (gl_set_sph_state or a density() of all gas particles) and the accelerations (gl_set_accelerations or a force
+// computation of all particles).  Sizes are checked here; VelPred defaults to the velocities that were loaded.
+extern "C" int gl_run_begin(gl_ctx *c, int Ti_Current)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n;
+  if(n <= 0) return c->fail("gl_run_begin: no particles loaded");
+  if(!c->have_par) return c->fail("gl_run_begin: gl_set_params not called");
+  if(c->comm && c->comm->world > 1) return c->fail("gl_run_begin: single rank only");
+  GL_CUDA(c, c->run_err.ensure(8));
+  GL_CUDA(c, c->run_hist.ensure(32));
+  GL_CUDA(c, cudaMemsetAsync(c->run_err.p, 0, 8 * sizeof(int), c->stream));
+  k_run_count_gas<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->in_type.p, c->run_err.p + 4);
+  GL_LAUNCH_COUNT(c);
+  int h[2] = { 0, 0 };
+  GL_CUDA(c, cudaMemcpyAsync(h, c->run_err.p + 4, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  const long long ngas = h[0];
+  if(ngas > 0 && h[1] != ngas - 1) return c->fail("gl_run_begin: the gas particles must form the leading block (SphP[i] belongs to P[i], i < N_gas)");
+  c->run_ngas = ngas;
+  if(c->o_acc.cap < 3 * (size_t) n) return c->fail("gl_run_begin: no gravitational accelerations in the context (force computation or gl_set_accelerations)");
+  if(ngas > 0)
+    {
+      if(c->o_hacc.cap < 3 * (size_t) n || c->o_maxsig.cap < (size_t) n || c->o_dtentr.cap < (size_t) n)
+	{
+	  if(c->o_hacc.cap < 3 * (size_t) n || c->o_maxsig.cap < (size_t) n)
+	    return c->fail("gl_run_begin: no hydro accelerations / signal velocities in the context (hydro_force or gl_set_accelerations)");
+	  GL_CUDA(c, c->o_dtentr.ensure((size_t) n));
+	}
+      if(c->o_density.cap < (size_t) n || c->o_pressure.cap < (size_t) n || c->o_divvel.cap < (size_t) n || c->o_dhsml.cap < (size_t) n ||
+	 c->o_curlvel.cap < (size_t) n)
+	return c->fail("gl_run_begin: no SphP state in the context (density or gl_set_sph_state)");
+      if(!c->have_velpred || c->n_velpred != ngas)
+	{
+	  GL_CUDA(c, c->in_velpred.ensure(3 * (size_t) ngas));
+	  k_run_copy_gas_vel<<<gl_grid(3 * ngas, 256), 256, 0, c->stream>>>(ngas, c->in_vel.p, c->in_velpred.p);
+	  GL_LAUNCH_COUNT(c);
+	  c->n_velpred = ngas;
+	  c->have_velpred = true;
+	}
+    }
+  c->run_ti = Ti_Current;
+  c->run_ready = true;
+  return 0;
+}
+
+extern "C" int gl_run_kick(gl_ctx *c, const gl_timestep_params *tp, int commit_dtentropy)
+{
+  cudaSetDevice(c->device);
+  if(!c->run_ready) return c->fail("gl_run_kick: gl_run_begin not called");
+  if(tp->Ti_Current != c->run_ti) return c->fail("gl_run_kick: Ti_Current differs from the time the particles are drifted to");
+  return run_kick(c, tp, commit_dtentropy != 0);
+}
+
+extern "C" int gl_run_steps(gl_ctx *c, gl_timestep_params *tp, int nsteps, gl_run_info *info)
+{
+  cudaSetDevice(c->device);
+  if(!c->run_ready) return c->fail("gl_run_steps: gl_run_begin not called");
+  if(tp->Ti_Current != c->run_ti) return c->fail("gl_run_steps: Ti_Current differs from the time the particles are drifted to");
+  const long long n = c->n;
+  gl_run_info I{};
+  GL_CUDA(c, c->tgt_flag.ensure(4 * (size_t) n + 4));
+  GL_CUDA(c, c->run_list.ensure((size_t) n + 1));
+  GL_CUDA(c, c->scan_tmp_i.ensure(64));
+  cudaEventRecord(c->ev[12], c->stream);
+  for(int step = 0; step < nsteps; step++)
+    {
+      // ---- find_next_sync_point_and_drift, run.c:190-330 ----
+      int hist[32];
+      GL_CUDA(c, cudaMemsetAsync(c->run_hist.p, 0, 32 * sizeof(int), c->stream));
+      k_run_bins<<<148 * 4, 256, 0, c->stream>>>(n, c->in_timebin.p, c->run_hist.p);
+      GL_LAUNCH_COUNT(c);
+      GL_CUDA(c, cudaMemcpyAsync(hist, c->run_hist.p, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      int ti_next_kick = TIMEBASE;
+      for(int b = 0; b < 29; b++)	// run.c:199-216
+	if(hist[b])
+	  {
+	    const int ti_next_for_bin = b > 0 ? (tp->Ti_Current / (1 << b)) * (1 << b) + (1 << b) : tp->Ti_Current;
+	    if(ti_next_for_bin < ti_next_kick) ti_next_kick = ti_next_for_bin;
+	  }
+      if(ti_next_kick >= TIMEBASE && tp->Ti_Current >= TIMEBASE) break;	// the end of the time line has been reached
+      const int time0 = tp->Ti_Current;
+      tp->Ti_Current = ti_next_kick;
+      long long nactive = hist[0];
+      tp->TimeBinActive[0] = 1;	// run.c:276-288
+      for(int b = 1; b < 29; b++)
+	{
+	  tp->TimeBinActive[b] = (ti_next_kick % (1 << b)) == 0;
+	  if(tp->TimeBinActive[b]) nactive += hist[b];
+	}
+      for(int b = 29; b < 32; b++) tp->TimeBinActive[b] = 0;
+      const RunPar T = make_runpar(tp);
+      // drift everything to the sync point (see the header of this file)
+      if(ti_next_kick != time0)
+	{
+	  k_run_drift<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->run_ngas, time0, ti_next_kick, tp->Timebase_interval, c->par.MinGasHsml,
+							      c->in_type.p, c->in_pos.p, c->in_vel.p, c->in_velpred.p, c->o_acc.p, c->o_hacc.p,
+							      c->o_density.p, c->in_hsml.p, c->o_pressure.p, c->o_divvel.p, c->in_entropy.p,
+							      c->in_dtentropy.p, c->in_timebin.p, c->in_tibegstep.p);
+	  GL_LAUNCH_COUNT(c);
+	}
+      c->run_ti = ti_next_kick;
+      // ---- domain_Decomposition: new extent, new tree (TreeReconstructFlag, domain.c:135) ----
+      c->par.Ti_Current = ti_next_kick;
+      c->tree_valid = false;
+      c->tree_flag = true;
+      if(!c->domain_imposed) c->have_domain = false;
+      // ---- the active list (run.c:296-320): particles on active bins, as targets of the force path ----
+      if(nactive >= n)
+	{
+	  if(gl_set_targets(c, nullptr, -1, 0)) return 1;
+	}
+      else
+	{
+	  int *flag = c->tgt_flag.p + 3 * n;	// the "mark" quarter: free until gl_prepare_targets runs
+	  k_run_active_flags<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, T.active_mask, c->in_timebin.p, flag);
+	  GL_LAUNCH_COUNT(c);
+	  size_t tmp = 0;
+	  int *dcount = c->scan_tmp_i.p + 59;
+	  cub::CountingInputIterator<int> iota(0);
+	  cub::DeviceSelect::Flagged(nullptr, tmp, iota, flag, c->run_list.p, dcount, (int) n, c->stream);
+	  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+	  GL_CUDA(c, cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, flag, c->run_list.p, dcount, (int) n, c->stream));
+	  c->kernel_launches += 2;
+	  int hcount = 0;
+	  GL_CUDA(c, cudaMemcpyAsync(&hcount, dcount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+	  if(hcount != nactive) return c->fail("gl_run_steps: active list and TimeBinCount disagree (\"terrible\", run.c:333)");
+	  if(gl_set_targets(c, c->run_list.p, hcount, 1)) return 1;
+	}
+      // ---- compute_accelerations, accel.c:27-106 ----
+      if(nactive > 0 && gl_compute_accelerations(c, 0)) return 1;
+      I.interactions += c->st.interactions;
+      // ---- advance_and_find_timesteps, timestep.c:29 ----
+      if(nactive > 0 && run_kick(c, tp, c->n_tgt_gas > 0)) return 1;
+      I.steps_done++;
+      I.active_total += nactive;
+      I.active_last = nactive;
+    }
+  cudaEventRecord(c->ev[13], c->stream);
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[12], c->ev[13]);
+  I.ms_total = ms;
+  I.Ti_Current = tp->Ti_Current;
+  if(info) *info = I;
+  return 0;
+}
+
+extern "C" int gl_get_run_state(gl_ctx *c, double *pos3, double *vel3, double *velpred3, double *hsml, double *entropy, double *dtentropy,
+				int *timebin, int *ti_begstep, int where)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n;
+  if(n <= 0) return c->fail("gl_get_run_state: no particles");
+  const cudaMemcpyKind k = where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if(pos3) GL_CUDA(c, cudaMemcpyAsync(pos3, c->in_pos.p, 3 * n * sizeof(double), k, c->stream));
+  if(vel3) GL_CUDA(c, cudaMemcpyAsync(vel3, c->in_vel.p, 3 * n * sizeof(double), k, c->stream));
+  if(velpred3)
+    {
+      if(!c->have_velpred) return c->fail("gl_get_run_state: no VelPred in the context");
+      GL_CUDA(c, cudaMemcpyAsync(velpred3, c->in_velpred.p, 3 * c->n_velpred * sizeof(double), k, c->stream));
+    }
+  if(hsml) GL_CUDA(c, cudaMemcpyAsync(hsml, c->in_hsml.p, n * sizeof(double), k, c->stream));
+  if(entropy) GL_CUDA(c, cudaMemcpyAsync(entropy, c->in_entropy.p, n * sizeof(double), k, c->stream));
+  if(dtentropy) GL_CUDA(c, cudaMemcpyAsync(dtentropy, c->in_dtentropy.p, n * sizeof(double), k, c->stream));
+  if(timebin) GL_CUDA(c, cudaMemcpyAsync(timebin, c->in_timebin.p, n * sizeof(int), k, c->stream));
+  if(ti_begstep) GL_CUDA(c, cudaMemcpyAsync(ti_begstep, c->in_tibegstep.p, n * sizeof(int), k, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}

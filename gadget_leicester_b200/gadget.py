@@ -278,6 +278,80 @@ class ForcePath:
         ap, na, ak = self._active(active)
         self._chk(self._lib.gl_dust_drag(self._ctx, ap, na, C.byref(st), 0))
 
+    # -- run()'s loop on the device-resident state (run.c:63-110; include/gl_b200.h "run()'s loop") -----------------------
+    def set_sph_state(self, Density, Pressure, DhsmlDensityFactor, DivVel, CurlVel):
+        """SphP[] state a density() leaves behind, P[]-indexed float64[n] (rows of non-gas particles are ignored)."""
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (Density, Pressure, DhsmlDensityFactor, DivVel, CurlVel)]
+        assert all(a.size == self.N for a in keep)
+        self._chk(self._lib.gl_set_sph_state(self._ctx, *[L._ptr(a) for a in keep], 0))
+
+    def set_VelPred(self, velpred):
+        """SphP[].VelPred of the leading gas block (n_gas x 3)."""
+        a = np.ascontiguousarray(velpred, dtype=np.float64)
+        self._chk(self._lib.gl_set_velpred(self._ctx, L._ptr(a), a.shape[0], 0))
+
+    def set_accelerations(self, GravAccel=None, HydroAccel=None, MaxSignalVel=None):
+        """P[].g.GravAccel, SphP[].a.HydroAccel (n x 3), SphP[].MaxSignalVel (n), all P[]-indexed."""
+        f = lambda a, w: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(self.N, w) if w > 1 else \
+            np.ascontiguousarray(a, dtype=np.float64).reshape(self.N)
+        keep = [f(GravAccel, 3), f(HydroAccel, 3), f(MaxSignalVel, 1)]
+        self._chk(self._lib.gl_set_accelerations(self._ctx, *[L._ptr(a) for a in keep], 0))
+
+    @staticmethod
+    def timestep_params(Ti_Current, TimeBinActive, **kw):
+        """gl_timestep_params from All.* values (names as in allvars.h); TimeBinActive: iterable of 0/1 per bin."""
+        t = L.GLTimestepParams()
+        t.Ti_Current = int(Ti_Current)
+        for b, v in enumerate(TimeBinActive):
+            t.TimeBinActive[b] = int(v)
+        t.GammaMinus1 = 7. / 5. - 1
+        t.p_DeltaDustMomentum = t.p_NewDensity = -1
+        for k, v in kw.items():
+            if k == "SofteningTable":
+                for i in range(6):
+                    t.SofteningTable[i] = float(v[i])
+            else:
+                setattr(t, k, float(v))
+        return t
+
+    def run_begin(self, Ti_Current):
+        self._chk(self._lib.gl_run_begin(self._ctx, int(Ti_Current)))
+
+    def advance_and_find_timesteps(self, tpar, commit_dtentropy=True):
+        """timestep.c:29 on the resident state, for the particles on the bins tpar.TimeBinActive marks."""
+        self._chk(self._lib.gl_run_kick(self._ctx, C.byref(tpar), 1 if commit_dtentropy else 0))
+
+    def run(self, tpar, nsteps):
+        """nsteps iterations of run.c:63-110 on the device; tpar.Ti_Current / TimeBinActive advance in place."""
+        info = L.GLRunInfo()
+        self._chk(self._lib.gl_run_steps(self._ctx, C.byref(tpar), int(nsteps), C.byref(info)))
+        self.params["Ti_Current"] = int(tpar.Ti_Current)
+        self._gp.Ti_Current = int(tpar.Ti_Current)
+        self._relative_criterion_engaged()
+        return {k: getattr(info, k) for k, _ in L.GLRunInfo._fields_}
+
+    def run_state(self, n_gas):
+        n = self.N
+        out = dict(Pos=np.zeros((n, 3)), Vel=np.zeros((n, 3)), VelPred=np.zeros((int(n_gas), 3)), Hsml=np.zeros(n), Entropy=np.zeros(n),
+                   DtEntropy=np.zeros(n), TimeBin=np.zeros(n, np.int32), Ti_begstep=np.zeros(n, np.int32))
+        self._chk(self._lib.gl_get_run_state(self._ctx, *[L._ptr(out[k]) for k in ("Pos", "Vel", "VelPred", "Hsml", "Entropy", "DtEntropy",
+                                                                                     "TimeBin", "Ti_begstep")], 0))
+        return out
+
+    def results(self):
+        """P[]-indexed results of the last force computations, without running anything."""
+        n = self.N
+        g = dict(GravAccel=np.zeros((n, 3)), OldAcc=np.zeros(n), GravCost=np.zeros(n, np.float32))
+        self._chk(self._lib.gl_get_gravity(self._ctx, L._ptr(g["GravAccel"]), L._ptr(g["OldAcc"]), L._ptr(g["GravCost"]), 0))
+        names = ["Hsml", "NumNgb", "Density", "DhsmlDensityFactor", "DivVel", "CurlVel", "Pressure"]
+        d = {k: np.zeros(n) for k in names}
+        self._chk(self._lib.gl_get_density(self._ctx, *[L._ptr(d[k]) for k in names], None, None, None, 0))
+        h = dict(HydroAccel=np.zeros((n, 3)), DtEntropy=np.zeros(n), MaxSignalVel=np.zeros(n))
+        self._chk(self._lib.gl_get_hydro(self._ctx, L._ptr(h["HydroAccel"]), L._ptr(h["DtEntropy"]), L._ptr(h["MaxSignalVel"]), 0))
+        g.update(d)
+        g.update({"HydroAccel": h["HydroAccel"], "HydroDtEntropy": h["DtEntropy"], "MaxSignalVel": h["MaxSignalVel"]})
+        return g
+
     # device-resident variants used by bench.py's `value` leg (no result download)
     def gravity_tree_nocopy(self):
         self._chk(self._lib.gl_gravity_tree(self._ctx))

@@ -94,6 +94,11 @@ class GLTimestepParams(C.Structure):
                 ("p_NewDensity", C.c_int)]
 
 
+class GLRunInfo(C.Structure):
+    _fields_ = [("steps_done", C.c_int), ("Ti_Current", C.c_int), ("active_total", C.c_longlong), ("active_last", C.c_longlong),
+                ("interactions", C.c_longlong), ("ms_total", C.c_double)]
+
+
 class GLTopNode(C.Structure):
     """struct local_topnode_data (domain.c:48)."""
     _fields_ = [("Size", C.c_ulonglong), ("StartKey", C.c_ulonglong), ("Count", C.c_longlong), ("Cost", C.c_double),
@@ -141,6 +146,7 @@ EXPORTS = [
     "gl_set_subgrid_params", "gl_blackhole_accretion", "gl_dust_density", "gl_dust_drag",
     "gl_gadget_blackhole_accretion", "gl_gadget_dust_density", "gl_gadget_dust_drag", "gl_hdf5_read_f64",
     "gl_domain_assign", "gl_domain_count_to_go", "gl_domain_split_collective",
+    "gl_set_velpred", "gl_set_accelerations", "gl_run_begin", "gl_run_kick", "gl_run_steps", "gl_get_run_state",
 ]
 
 _lib = None
@@ -241,6 +247,12 @@ def load_library():
                                      C.POINTER(GLIOHeader), C.c_char_p, C.c_int]
     lib.gl_export_tree.argtypes = [vp, C.POINTER(GLTreeLayout), vp, vp, vp, vp, C.c_longlong, C.c_longlong, C.c_int,
                                    C.POINTER(C.c_longlong)]
+    lib.gl_set_velpred.argtypes = [vp, vp, C.c_longlong, C.c_int]
+    lib.gl_set_accelerations.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.gl_run_begin.argtypes = [vp, C.c_int]
+    lib.gl_run_kick.argtypes = [vp, C.POINTER(GLTimestepParams), C.c_int]
+    lib.gl_run_steps.argtypes = [vp, C.POINTER(GLTimestepParams), C.c_int, C.POINTER(GLRunInfo)]
+    lib.gl_get_run_state.argtypes = [vp] + [vp] * 8 + [C.c_int]
     _lib = lib
     return lib
 

@@ -329,6 +329,42 @@ int gl_gadget_advance_and_find_timesteps(const gl_gadget_layout * lay, const gl_
 /* scatter results back in place; what = bit mask: 1 gravity, 2 density, 4 hydro */
 int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
 
+/* ---- run()'s loop with the state resident on the device (device side) -------------------------
+ * run.c:63-110 alternates find_next_sync_point_and_drift (run.c:190), domain_Decomposition, compute_accelerations
+ * (accel.c:27) and advance_and_find_timesteps (timestep.c:29) on P[] / SphP[] in host memory.  These entry points run
+ * the same loop on the SoA state the context already holds: drift_particle (predict.c:129) for every particle to the
+ * next synchronisation point, the force path for the particles on active time bins, get_timestep (timestep.c:607) +
+ * the bin rule (timestep.c:136-154) + do_the_kick (timestep.c:364) for them - nothing crosses PCIe but the 32
+ * TimeBinCount[] values per step.  Same restrictions as the host-side pieces above (non-comoving, tree rebuilt every
+ * step = TreeDomainUpdateFrequency 0, no sub-grid loops inside the loop: DragAccel and DeltaDustMomentum are zero).
+ * Single rank.  The gas particles must form the leading block of the particle set, as in P[]. */
+/* SphP[].VelPred of the gas block (n_gas x 3); without it gl_run_begin starts from the loaded velocities */
+int gl_set_velpred(gl_ctx * ctx, const double *velpred3, long long n_gas, int where);
+/* P[].g.GravAccel, SphP[].a.HydroAccel (3n each), SphP[].MaxSignalVel (n), indexed like P[] (non-gas rows of the
+ * last two are ignored); NULL = keep what the last force computation in this context left.  */
+int gl_set_accelerations(gl_ctx * ctx, const double *gravaccel3, const double *hydroaccel3, const double *maxsignalvel, int where);
+/* checks that the context holds the whole state (particles, SphP state, accelerations); every particle is taken to
+ * be drifted to Ti_Current (P[].Ti_current == All.Ti_Current) */
+int gl_run_begin(gl_ctx * ctx, int Ti_Current);
+/* advance_and_find_timesteps() for the particles on the bins par->TimeBinActive[] marks, at par->Ti_Current.
+ * commit_dtentropy != 0: SphP.e.DtEntropy of those gas particles is first taken from the last hydro_force() of this
+ * context (hydra.c:785-813 writes it for the active particles). Errors as gl_gadget_advance_and_find_timesteps. */
+int gl_run_kick(gl_ctx * ctx, const gl_timestep_params * par, int commit_dtentropy);
+typedef struct gl_run_info
+{
+  int steps_done, Ti_Current;	/* iterations executed (fewer than asked for only at the end of the time line) */
+  long long active_total, active_last;	/* force updates summed over the steps (NumForceUpdate), and of the last step */
+  long long interactions;	/* gravity interactions summed over the steps */
+  double ms_total;		/* device time of the whole call */
+} gl_run_info;
+/* nsteps iterations of the loop; par->Ti_Current and par->TimeBinActive[] are advanced in place (the caller's
+ * All.Ti_Current / TimeBinActive[]) */
+int gl_run_steps(gl_ctx * ctx, gl_timestep_params * par, int nsteps, gl_run_info * info);
+/* the state the loop integrates, indexed like P[] (velpred3: the n_gas leading rows); NULL = not wanted.  Forces,
+ * densities and the other results come from gl_get_gravity / gl_get_density / gl_get_hydro as usual */
+int gl_get_run_state(gl_ctx * ctx, double *pos3, double *vel3, double *velpred3, double *hsml, double *entropy, double *dtentropy,
+		     int *timebin, int *ti_begstep, int where);
+
 /* ---- the tree, in the reference's own storage (SURVEY.md 8(b) "Tree (if CPU consumers are kept)") ---------------
  * The sub-grid loops that follow the force path in the reference (sink accretion blackhole.c:794,1201,1351, dust
  * dust.c:60,263,748, setup_smoothinglengths init.c:719, its own force_update_hmax) walk Nodes[] / Nextnode[] with

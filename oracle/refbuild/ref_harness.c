@@ -201,6 +201,27 @@ static void dump_kick_state(const char *prefix, const char *tag)
 }
 
 
+/* what a force evaluation leaves behind beyond dump_kick_state's fields: the rest of the state run()'s loop carries
+   from one step to the next (drift: DivVel; hydro sources: DhsmlDensityFactor, CurlVel; relative criterion: OldAcc) */
+static void dump_loop_extra(const char *prefix, const char *tag)
+{
+  long long n = NumPart, ng = N_gas, i;
+  double *d1 = malloc(sizeof(double) * (n + 1));
+  char nm[40];
+  double q[8];
+#define PUT1(field, expr, cnt) do { for(i = 0; i < (cnt); i++) d1[i] = expr; snprintf(nm, sizeof(nm), "%s_%s", tag, field); put(prefix, nm, 'd', (cnt), 1, d1); } while(0)
+  PUT1("OldAcc", P[i].OldAcc, n); PUT1("NumNgb", P[i].n.NumNgb, n);
+  PUT1("DivVel", SphP[i].v.DivVel, ng); PUT1("CurlVel", SphP[i].r.CurlVel, ng);
+  PUT1("DhsmlDensityFactor", SphP[i].h.DhsmlDensityFactor, ng);
+#undef PUT1
+  q[0] = All.Ti_Current; q[1] = All.Timebase_interval; q[2] = All.ErrTolTheta; q[3] = All.ErrTolForceAcc; q[4] = All.MinGasHsml;
+  q[5] = All.MinEgySpec; q[6] = All.MaxSizeTimestep; q[7] = All.G;
+  snprintf(nm, sizeof(nm), "%s_%s", tag, "globals");
+  put(prefix, nm, 'd', 8, 1, q);
+  free(d1);
+}
+
+
 /* ---- sub-grid neighbour loops: blackhole.c, dust.c ---- */
 /* run-time parameters of the shipped run (Pd_N16e5_*.txt:76,86-88,126,138,167-171) unless the input overrides them */
 static int subgrid_ready;
@@ -682,6 +703,10 @@ int main(int argc, char **argv)
 		for(i = 0; i < TIMEBINS; i++) TimeBinActive[i] = (i <= 6);
 		reconstruct_timebins();
 		Flag_FullStep = 1;
+		/* the state the loop starts from, complete enough to start the same loop elsewhere (the device-resident
+		   loop gl_run_steps, tests/test_gpu_resident.py) */
+		dump_kick_state(prefix, "begin");
+		dump_loop_extra(prefix, "begin");
 		advance_and_find_timesteps();
 		for(step = 0; step < 8; step++)
 		  {
@@ -695,6 +720,7 @@ int main(int argc, char **argv)
 		q[0] = All.Ti_Current; q[1] = All.Time; q[2] = k; q[3] = step;
 		put(prefix, "loop", 'd', 4, 1, q);
 		dump_kick_state(prefix, "end");
+		dump_loop_extra(prefix, "end");
 	      }
 	      break;
 	    case 'B':
