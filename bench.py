@@ -331,7 +331,7 @@ def resident_loop(ForcePath, par, ps, n, ksteps):
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / ksteps
     launches = fp.stats()["kernel_launches"]
-    st = fp.run_state(int((ps["type"] == 0).sum()))
+    st = fp.run_state()
     out = dict(value=info["interactions"] / ksteps / wall, unit=UNIT, ms_per_step=wall * 1e3, device_ms_per_step=info["ms_total"] / ksteps,
                steps=ksteps, active_per_step=info["active_total"] / ksteps, particles=n, Ti_Current=int(t.Ti_Current),
                bins_in_use=sorted(int(b) for b in np.unique(st["TimeBin"])), gpu_launches=int(launches),
@@ -340,6 +340,48 @@ def resident_loop(ForcePath, par, ps, n, ksteps):
                    "state in HBM; per step only TimeBinCount[32] and the phases' counters come back (wall clock, host loop included)")
     fp.close()
     return out
+
+
+def resident_loop_ranks(dfp, par, dist, world, ksteps):
+    """resident_loop() at N ranks: every rank integrates its own Peano-Hilbert segment inside libgl_b200 (gl_run_steps in
+    multi-rank mode: TimeBinCount all-gather, locally-essential exchange and force path, kick), max over ranks."""
+    import time
+    import torch
+    k = dfp.hi - dfp.lo
+    r = dfp.fetch()
+    if "hsml" in r:
+        dfp.own["hsml"][:k] = r["hsml"]
+    dfp.own["oldacc"][:k] = r["oldacc"]
+    dfp.own["timebin"][:k] = 1
+    dfp.own["ti_begstep"][:k] = 0
+    fp = dfp.fp
+    fp.set_params(Ti_Current=2)
+    dfp._load_own()
+    fp.set_TreeReconstructFlag(1)
+    dfp.compute_accelerations()
+    tbi = par["Timebase_interval"]
+    fp.run_begin(2)
+    t = fp.timestep_params(2, [1, 1] + [0] * 27, Timebase_interval=tbi, ErrTolIntAccuracy=0.025, CourantFac=0.15, MaxSizeTimestep=2 * tbi,
+                           MinSizeTimestep=0.0, MinEgySpec=0.0, SofteningTable=par["Softening"], OuterBoundary=1.4e10,
+                           UnitVelocity_in_cm_per_s=2.98e6, FeedBackVelocity=1.0, SMBHmass=0.5, InnerBoundary=2.0e-2, SinkBoundary=1.0e-4,
+                           AccDtBlackHole=0.007)
+    fp.advance_and_find_timesteps(t)
+    fp.run(t, 3)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    info = fp.run(t, ksteps)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / ksteps
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    ii = torch.tensor([float(info["interactions"]) / ksteps, float(info["active_total"]) / ksteps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ii, op=dist.ReduceOp.SUM)
+    return dict(value=float(ii[0].item()) / float(tt.item()), unit=UNIT, ms_per_step=float(tt.item()) * 1e3, steps=ksteps,
+                active_per_step=float(ii[1].item()), Ti_Current=int(t.Ti_Current), h2d_bytes_per_step=0,
+                d2h_bytes_per_step=world * (128 * world + 3 * 24 + 8 + 8 + 8 * world),
+                api="gl_run_steps in multi-rank mode: every rank's own Peano-Hilbert segment stays in HBM; per step the "
+                    "TimeBinCount[] all-gather, drift, locally-essential exchange over NCCL + force path, kick; max over ranks (wall clock)")
 
 
 def identity_check(dfp, ps, par, n, rank, world, dist):
@@ -663,6 +705,14 @@ def main():
     dom = max(cand, key=cand.get)
     roof = dict(roofs[dom], others={k: v for k, v in roofs.items() if k != dom})
 
+    # ---- run()'s loop with every rank's state resident in HBM (the N-rank form of resident_loop below) ----
+    resident = None
+    if dist is not None and use_let and not args.no_e2e:
+        try:
+            resident = resident_loop_ranks(dfp, par, dist, world, max(2, min(args.steps, 10)))
+        except Exception as ex:  # collective: a failure here is a failure on every rank
+            resident = dict(error=str(ex)[:300])
+
     # ---- e2e: the same step through the drop-in boundary with host P[]/SphP[] (rank-local set) ----
     e2e = None
     if not args.no_e2e and world > 1 and use_let:
@@ -760,7 +810,6 @@ def main():
         fp.close()
 
     # ---- run()'s loop with the state resident in HBM: drift + force path + kick per step, nothing but TimeBinCount[] crosses PCIe ----
-    resident = None
     if not args.no_e2e and world == 1:
         try:
             resident = resident_loop(ForcePath, par, ps2, n, max(2, min(args.steps, 10)))

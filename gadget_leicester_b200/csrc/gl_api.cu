@@ -51,6 +51,7 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->run_err.release();
   c->run_hist.release();
   c->run_list.release();
+  c->run_flag.release();
   c->dma_rows.release();
   if(c->ev_blk) cudaEventDestroy(c->ev_blk);
   for(int i = 0; i < 4; i++)
@@ -799,6 +800,14 @@ extern "C" int gl_compute_accelerations(gl_ctx *c, int mode)
   long long have_sph = 0;
   if(gl_prepare_targets(c)) return 1;
   have_sph = c->n_tgt_sph;
+  if(c->comm && c->comm->world > 1)
+    {
+      // the SPH phases are collective: a rank whose active list holds no SPH particle in this step (individual time
+      // steps) still has to serve the others' neighbour searches
+      int any = 0;
+      if(gll_agree_violation(c, have_sph > 0 ? 1 : 0, &any)) return 1;
+      have_sph = any;
+    }
   if(have_sph > 0)
     {
       if(gl_density(c)) return 1;	// accel.c:84

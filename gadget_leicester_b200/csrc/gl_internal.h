@@ -216,8 +216,7 @@ struct gl_ctx
   DBuf<long long> sg_off;
   long long sg_pairs_seen = 0;	// (grain, gas) pairs of the last gl_dust_drag: sizes the next call's list
   // ---- device-resident integration loop (gl_resident.cu) ----
-  DBuf<int> run_err, run_hist, run_list;
-  long long run_ngas = 0;
+  DBuf<int> run_err, run_hist, run_list, run_flag;
   int run_ti = 0;		// the time every particle is drifted to
   bool run_ready = false;
   // ---- gadget AoS layer ----

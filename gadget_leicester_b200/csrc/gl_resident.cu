@@ -56,7 +56,7 @@ __device__ __forceinline__ void run_fail(int *err, int code, long long p)
 }
 
 // predict.c:129-260 for particle i, from time0 to time1 (every particle sits at time0: the loop drifts all of them)
-__global__ void k_run_drift(long long n, long long ngas, int time0, int time1, double tbi, double mingashsml, const int *__restrict__ type,
+__global__ void k_run_drift(long long n, int time0, int time1, double tbi, double mingashsml, const int *__restrict__ type,
 			    double *__restrict__ pos, const double *__restrict__ vel, double *__restrict__ velpred,
 			    const double *__restrict__ gacc, const double *__restrict__ hacc, double *__restrict__ density,
 			    double *__restrict__ hsml, double *__restrict__ pressure, const double *__restrict__ divvel,
@@ -70,7 +70,7 @@ __global__ void k_run_drift(long long n, long long ngas, int time0, int time1, d
   const double dt = (time1 - time0) * tbi;	// predict.c:165: dt_drift = dt_gravkick = dt_hydrokick
 #pragma unroll
   for(int j = 0; j < 3; j++) pos[3 * i + j] = __dadd_rn(pos[3 * i + j], __dmul_rn(vel[3 * i + j], dt));	// predict.c:169-170
-  if(ty == 0 && i < ngas)
+  if(ty == 0)
     {
 #pragma unroll
       for(int j = 0; j < 3; j++)	// predict.c:185-186 (DragAccel stays 0 here: the dust loops are not part of this loop)
@@ -137,7 +137,7 @@ __device__ int run_get_timestep(const RunPar &T, long long p, int type, double m
 }
 
 // the per-particle body of advance_and_find_timesteps (timestep.c:127-168, :236-260) + do_the_kick (timestep.c:364-601)
-__global__ void k_run_kick(long long n, long long ngas, RunPar T, const int *__restrict__ type, const double *__restrict__ mass,
+__global__ void k_run_kick(long long n, RunPar T, const int *__restrict__ type, const double *__restrict__ mass,
 			   const double *__restrict__ hsml, const double *__restrict__ gacc, const double *__restrict__ hacc,
 			   const double *__restrict__ maxsig, const double *__restrict__ density, double *__restrict__ vel,
 			   double *__restrict__ velpred, double *__restrict__ entropy, double *__restrict__ dtentropy,
@@ -148,7 +148,7 @@ __global__ void k_run_kick(long long n, long long ngas, RunPar T, const int *__r
   const int binold = timebin[i];
   if(binold < 0 || binold > 31 || !((T.active_mask >> binold) & 1u)) return;
   const int ty = type[i];
-  const bool gas = ty == 0 && i < ngas;
+  const bool gas = ty == 0;
   const double g0 = gacc[3 * i], g1 = gacc[3 * i + 1], g2 = gacc[3 * i + 2];
   double h0 = 0, h1 = 0, h2 = 0;
   if(gas)
@@ -255,22 +255,12 @@ __global__ void k_run_active_flags(long long n, unsigned mask, const int *__rest
   flag[i] = (b >= 0 && b < 32 && ((mask >> b) & 1u)) ? 1 : 0;
 }
 
-// the gas block leads (allvars.h: SphP[i] belongs to P[i], i < N_gas): count it and check that nothing else is gas
-__global__ void k_run_count_gas(long long n, const int *__restrict__ type, int *__restrict__ out)
+// VelPred gets a row per particle: rows the caller supplied (the leading n_have, SphP[i] belongs to P[i]) are kept, the
+// others start from the velocities (they are only read where the type is 0)
+__global__ void k_run_fill_velpred(long long n, long long n_have, const double *__restrict__ vel, double *__restrict__ velpred)
 {
   const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(i >= n) return;
-  if(type[i] == 0)
-    {
-      atomicAdd(&out[0], 1);
-      atomicMax(&out[1], (int) i);
-    }
-}
-
-__global__ void k_run_copy_gas_vel(long long ngas, const double *__restrict__ vel, double *__restrict__ velpred)
-{
-  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
-  if(i < 3 * ngas) velpred[i] = vel[i];
+  if(i < 3 * n && i >= 3 * n_have) velpred[i] = vel[i];
 }
 
 int run_check_err(gl_ctx *c, const char *where)
@@ -279,6 +269,13 @@ int run_check_err(gl_ctx *c, const char *where)
   GL_CUDA(c, cudaMemcpyAsync(h, c->run_err.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   GL_CUDA(c, cudaGetLastError());
+  if(c->comm && c->comm->world > 1)
+    {
+      // the reference aborts all ranks (endrun): every rank has to learn that one of them failed
+      int any = 0;
+      if(gll_agree_violation(c, h[0] != 0, &any)) return 1;
+      if(any && h[0] == 0) return c->fail(std::string(where) + ": another rank stopped (endrun)");
+    }
   if(h[0] == 0) return 0;
   const char *what = h[0] == 888 ? "timestep below MinSizeTimestep (endrun 888)"
     : h[0] == 818 ? "a timestep of size zero was assigned on the integer timeline (endrun 818)"
@@ -288,10 +285,10 @@ int run_check_err(gl_ctx *c, const char *where)
 
 int run_kick(gl_ctx *c, const gl_timestep_params *tp, bool commit_dtentropy)
 {
-  const long long n = c->n;
+  const long long n = c->n_own;
   const RunPar T = make_runpar(tp);
   GL_CUDA(c, cudaMemsetAsync(c->run_err.p, 0, 2 * sizeof(int), c->stream));
-  k_run_kick<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->run_ngas, T, c->in_type.p, c->in_mass.p, c->in_hsml.p, c->o_acc.p, c->o_hacc.p,
+  k_run_kick<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, T, c->in_type.p, c->in_mass.p, c->in_hsml.p, c->o_acc.p, c->o_hacc.p,
 						       c->o_maxsig.p, c->o_density.p, c->in_vel.p, c->in_velpred.p, c->in_entropy.p,
 						       c->in_dtentropy.p, commit_dtentropy ? c->o_dtentr.p : nullptr, c->in_timebin.p,
 						       c->in_tibegstep.p, c->run_err.p);
@@ -313,6 +310,7 @@ extern "C" int gl_set_velpred(gl_ctx *c, const double *velpred3, long long n_gas
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->n_velpred = n_gas;
   c->have_velpred = n_gas > 0;
+  c->run_ready = false;		// gl_run_begin gives VelPred a row per particle again
   if(c->tree_valid && glk_apply_velpred(c)) return 1;
   return 0;
 }
@@ -345,44 +343,50 @@ extern "C" int gl_set_accelerations(gl_ctx *c, const double *gravaccel3, const d
 // The state the loop needs must be in the context: the particle set (gl_load_particles), the SphP state
 // (gl_set_sph_state or a density() of all gas particles) and the accelerations (gl_set_accelerations or a force
 // computation of all particles).  Sizes are checked here; VelPred defaults to the velocities that were loaded.
+// Multi-rank mode: every rank holds its own particles [0, n_own); the imports of a locally-essential tree lie behind
+// them and are never drifted or kicked here - they come again with every rebuild.
 extern "C" int gl_run_begin(gl_ctx *c, int Ti_Current)
 {
   cudaSetDevice(c->device);
-  const long long n = c->n;
-  if(n <= 0) return c->fail("gl_run_begin: no particles loaded");
+  const long long n = c->n_own;
+  if(c->n <= 0 || n <= 0) return c->fail("gl_run_begin: no particles loaded");
   if(!c->have_par) return c->fail("gl_run_begin: gl_set_params not called");
-  if(c->comm && c->comm->world > 1) return c->fail("gl_run_begin: single rank only");
-  GL_CUDA(c, c->run_err.ensure(8));
-  GL_CUDA(c, c->run_hist.ensure(32));
-  GL_CUDA(c, cudaMemsetAsync(c->run_err.p, 0, 8 * sizeof(int), c->stream));
-  k_run_count_gas<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->in_type.p, c->run_err.p + 4);
-  GL_LAUNCH_COUNT(c);
-  int h[2] = { 0, 0 };
-  GL_CUDA(c, cudaMemcpyAsync(h, c->run_err.p + 4, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  GL_CUDA(c, cudaStreamSynchronize(c->stream));
-  const long long ngas = h[0];
-  if(ngas > 0 && h[1] != ngas - 1) return c->fail("gl_run_begin: the gas particles must form the leading block (SphP[i] belongs to P[i], i < N_gas)");
-  c->run_ngas = ngas;
+  const int W = c->comm ? c->comm->world : 1;
+  GL_CUDA(c, c->run_err.ensure(48));
+  GL_CUDA(c, c->run_hist.ensure(32 * (size_t) (W + 1)));
   if(c->o_acc.cap < 3 * (size_t) n) return c->fail("gl_run_begin: no gravitational accelerations in the context (force computation or gl_set_accelerations)");
-  if(ngas > 0)
+  // (a set without gas never allocates the SphP arrays; the kernels only read them where the type is 0)
+  const bool sph = c->o_density.cap >= (size_t) n;
+  if(sph)
     {
-      if(c->o_hacc.cap < 3 * (size_t) n || c->o_maxsig.cap < (size_t) n || c->o_dtentr.cap < (size_t) n)
-	{
-	  if(c->o_hacc.cap < 3 * (size_t) n || c->o_maxsig.cap < (size_t) n)
-	    return c->fail("gl_run_begin: no hydro accelerations / signal velocities in the context (hydro_force or gl_set_accelerations)");
-	  GL_CUDA(c, c->o_dtentr.ensure((size_t) n));
-	}
-      if(c->o_density.cap < (size_t) n || c->o_pressure.cap < (size_t) n || c->o_divvel.cap < (size_t) n || c->o_dhsml.cap < (size_t) n ||
-	 c->o_curlvel.cap < (size_t) n)
-	return c->fail("gl_run_begin: no SphP state in the context (density or gl_set_sph_state)");
-      if(!c->have_velpred || c->n_velpred != ngas)
-	{
-	  GL_CUDA(c, c->in_velpred.ensure(3 * (size_t) ngas));
-	  k_run_copy_gas_vel<<<gl_grid(3 * ngas, 256), 256, 0, c->stream>>>(ngas, c->in_vel.p, c->in_velpred.p);
-	  GL_LAUNCH_COUNT(c);
-	  c->n_velpred = ngas;
-	  c->have_velpred = true;
-	}
+      if(c->o_hacc.cap < 3 * (size_t) n || c->o_maxsig.cap < (size_t) n)
+	return c->fail("gl_run_begin: no hydro accelerations / signal velocities in the context (hydro_force or gl_set_accelerations)");
+      GL_CUDA(c, c->o_dtentr.ensure_keep((size_t) n));
+      if(c->o_pressure.cap < (size_t) n || c->o_divvel.cap < (size_t) n || c->o_dhsml.cap < (size_t) n || c->o_curlvel.cap < (size_t) n)
+	return c->fail("gl_run_begin: incomplete SphP state in the context (density or gl_set_sph_state)");
+    }
+  else
+    {
+      // no SphP state: fine as long as there is no gas (checked on the device below)
+      GL_CUDA(c, cudaMemsetAsync(c->run_err.p, 0, 48 * sizeof(int), c->stream));
+    }
+  const long long have = c->have_velpred ? std::min(c->n_velpred, n) : 0;
+  GL_CUDA(c, c->in_velpred.ensure_keep(3 * (size_t) n));
+  k_run_fill_velpred<<<gl_grid(3 * n, 256), 256, 0, c->stream>>>(n, have, c->in_vel.p, c->in_velpred.p);
+  GL_LAUNCH_COUNT(c);
+  c->n_velpred = n;
+  c->have_velpred = true;
+  if(!sph)
+    {
+      k_run_bins<<<148 * 4, 256, 0, c->stream>>>(n, c->in_type.p, c->run_err.p + 8);	// histogram of the types: slot 8 = type 0
+      GL_LAUNCH_COUNT(c);
+      int ngas = 0;
+      GL_CUDA(c, cudaMemcpyAsync(&ngas, c->run_err.p + 8, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      if(ngas > 0) return c->fail("gl_run_begin: no SphP state in the context (density or gl_set_sph_state)");
+      // the kernels are handed these pointers whatever the types are
+      GL_CUDA(c, c->o_hacc.ensure(8)); GL_CUDA(c, c->o_maxsig.ensure(8)); GL_CUDA(c, c->o_density.ensure(8));
+      GL_CUDA(c, c->o_pressure.ensure(8)); GL_CUDA(c, c->o_divvel.ensure(8)); GL_CUDA(c, c->o_dtentr.ensure(8));
     }
   c->run_ti = Ti_Current;
   c->run_ready = true;
@@ -402,24 +406,44 @@ extern "C" int gl_run_steps(gl_ctx *c, gl_timestep_params *tp, int nsteps, gl_ru
   cudaSetDevice(c->device);
   if(!c->run_ready) return c->fail("gl_run_steps: gl_run_begin not called");
   if(tp->Ti_Current != c->run_ti) return c->fail("gl_run_steps: Ti_Current differs from the time the particles are drifted to");
-  const long long n = c->n;
+  const long long n = c->n_own;
+  const int W = (c->comm && c->comm->world > 1) ? c->comm->world : 1;
   gl_run_info I{};
-  GL_CUDA(c, c->tgt_flag.ensure(4 * (size_t) n + 4));
   GL_CUDA(c, c->run_list.ensure((size_t) n + 1));
+  GL_CUDA(c, c->run_flag.ensure((size_t) n + 1));
   GL_CUDA(c, c->scan_tmp_i.ensure(64));
   cudaEventRecord(c->ev[12], c->stream);
   for(int step = 0; step < nsteps; step++)
     {
       // ---- find_next_sync_point_and_drift, run.c:190-330 ----
-      int hist[32];
+      std::vector<int> hall(32 * (size_t) W);
+      int *hist = hall.data();	// own counts first; slot 31 carries the number of own particles
       GL_CUDA(c, cudaMemsetAsync(c->run_hist.p, 0, 32 * sizeof(int), c->stream));
       k_run_bins<<<148 * 4, 256, 0, c->stream>>>(n, c->in_timebin.p, c->run_hist.p);
       GL_LAUNCH_COUNT(c);
-      GL_CUDA(c, cudaMemcpyAsync(hist, c->run_hist.p, sizeof(hist), cudaMemcpyDeviceToHost, c->stream));
+      const int n_int = (int) n;
+      GL_CUDA(c, cudaMemcpyAsync(c->run_hist.p + 31, &n_int, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      if(W > 1)
+	{
+	  // TimeBinCount[] of all ranks: the reference takes MPI_Allreduce(MPI_MIN) of the ranks' next kick times
+	  // (run.c:218) and sums the force updates (run.c:290); the counts give both
+	  if(c->comm->allgather(c->run_hist.p, c->run_hist.p + 32, 32 * sizeof(int), c->stream))
+	    return c->fail("gl_run_steps: all-gather of TimeBinCount failed: " + c->comm->err);
+	  GL_CUDA(c, cudaMemcpyAsync(hist, c->run_hist.p + 32, 32 * sizeof(int) * W, cudaMemcpyDeviceToHost, c->stream));
+	}
+      else
+	GL_CUDA(c, cudaMemcpyAsync(hist, c->run_hist.p, 32 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      long long glob[32], own[32];
+      for(int b = 0; b < 32; b++)
+	{
+	  glob[b] = 0;
+	  for(int r = 0; r < W; r++) glob[b] += hist[32 * r + b];
+	  own[b] = hist[32 * (W > 1 ? c->comm->rank : 0) + b];
+	}
       int ti_next_kick = TIMEBASE;
       for(int b = 0; b < 29; b++)	// run.c:199-216
-	if(hist[b])
+	if(glob[b])
 	  {
 	    const int ti_next_for_bin = b > 0 ? (tp->Ti_Current / (1 << b)) * (1 << b) + (1 << b) : tp->Ti_Current;
 	    if(ti_next_for_bin < ti_next_kick) ti_next_kick = ti_next_for_bin;
@@ -427,58 +451,67 @@ extern "C" int gl_run_steps(gl_ctx *c, gl_timestep_params *tp, int nsteps, gl_ru
       if(ti_next_kick >= TIMEBASE && tp->Ti_Current >= TIMEBASE) break;	// the end of the time line has been reached
       const int time0 = tp->Ti_Current;
       tp->Ti_Current = ti_next_kick;
-      long long nactive = hist[0];
+      long long nactive = own[0], nactive_glob = glob[0];
       tp->TimeBinActive[0] = 1;	// run.c:276-288
       for(int b = 1; b < 29; b++)
 	{
 	  tp->TimeBinActive[b] = (ti_next_kick % (1 << b)) == 0;
-	  if(tp->TimeBinActive[b]) nactive += hist[b];
+	  if(tp->TimeBinActive[b])
+	    {
+	      nactive += own[b];
+	      nactive_glob += glob[b];
+	    }
 	}
       for(int b = 29; b < 32; b++) tp->TimeBinActive[b] = 0;
       const RunPar T = make_runpar(tp);
       // drift everything to the sync point (see the header of this file)
       if(ti_next_kick != time0)
 	{
-	  k_run_drift<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->run_ngas, time0, ti_next_kick, tp->Timebase_interval, c->par.MinGasHsml,
-							      c->in_type.p, c->in_pos.p, c->in_vel.p, c->in_velpred.p, c->o_acc.p, c->o_hacc.p,
-							      c->o_density.p, c->in_hsml.p, c->o_pressure.p, c->o_divvel.p, c->in_entropy.p,
-							      c->in_dtentropy.p, c->in_timebin.p, c->in_tibegstep.p);
+	  k_run_drift<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, time0, ti_next_kick, tp->Timebase_interval, c->par.MinGasHsml, c->in_type.p,
+							      c->in_pos.p, c->in_vel.p, c->in_velpred.p, c->o_acc.p, c->o_hacc.p, c->o_density.p,
+							      c->in_hsml.p, c->o_pressure.p, c->o_divvel.p, c->in_entropy.p, c->in_dtentropy.p,
+							      c->in_timebin.p, c->in_tibegstep.p);
 	  GL_LAUNCH_COUNT(c);
 	}
       c->run_ti = ti_next_kick;
-      // ---- domain_Decomposition: new extent, new tree (TreeReconstructFlag, domain.c:135) ----
+      // ---- domain_Decomposition: new extent, new tree (TreeReconstructFlag, domain.c:135).  The ranks keep the
+      // particles they have: any assignment gives the same results, a stale one only prunes less ----
       c->par.Ti_Current = ti_next_kick;
+      gl_set_tree_reconstruct_flag(c, 1);	// (multi-rank mode: the imports of the last tree are dropped, the next build fetches them again)
       c->tree_valid = false;
-      c->tree_flag = true;
+      c->tgt_dirty = true;
       if(!c->domain_imposed) c->have_domain = false;
       // ---- the active list (run.c:296-320): particles on active bins, as targets of the force path ----
-      if(nactive >= n)
+      long long total = 0;
+      for(int r = 0; r < W; r++) total += hist[32 * r + 31];
+      if(nactive_glob >= total)
 	{
 	  if(gl_set_targets(c, nullptr, -1, 0)) return 1;
 	}
       else
 	{
-	  int *flag = c->tgt_flag.p + 3 * n;	// the "mark" quarter: free until gl_prepare_targets runs
-	  k_run_active_flags<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, T.active_mask, c->in_timebin.p, flag);
+	  k_run_active_flags<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, T.active_mask, c->in_timebin.p, c->run_flag.p);
 	  GL_LAUNCH_COUNT(c);
 	  size_t tmp = 0;
 	  int *dcount = c->scan_tmp_i.p + 59;
 	  cub::CountingInputIterator<int> iota(0);
-	  cub::DeviceSelect::Flagged(nullptr, tmp, iota, flag, c->run_list.p, dcount, (int) n, c->stream);
+	  cub::DeviceSelect::Flagged(nullptr, tmp, iota, c->run_flag.p, c->run_list.p, dcount, (int) n, c->stream);
 	  GL_CUDA(c, c->cub_tmp.ensure(tmp));
-	  GL_CUDA(c, cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, flag, c->run_list.p, dcount, (int) n, c->stream));
+	  GL_CUDA(c, cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, c->run_flag.p, c->run_list.p, dcount, (int) n, c->stream));
 	  c->kernel_launches += 2;
 	  int hcount = 0;
 	  GL_CUDA(c, cudaMemcpyAsync(&hcount, dcount, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	  GL_CUDA(c, cudaStreamSynchronize(c->stream));
 	  if(hcount != nactive) return c->fail("gl_run_steps: active list and TimeBinCount disagree (\"terrible\", run.c:333)");
-	  if(gl_set_targets(c, c->run_list.p, hcount, 1)) return 1;
+	  // multi-rank mode orders its own targets (a rank's particles are its stretch of the Peano-Hilbert curve, in order)
+	  if(W > 1 ? gl_set_targets_ordered(c, c->run_list.p, hcount, 1) : gl_set_targets(c, c->run_list.p, hcount, 1)) return 1;
 	}
-      // ---- compute_accelerations, accel.c:27-106 ----
-      if(nactive > 0 && gl_compute_accelerations(c, 0)) return 1;
+      // ---- compute_accelerations, accel.c:27-106 (collective in multi-rank mode: a rank without active particles
+      // still serves the others) ----
+      if(nactive_glob > 0 && gl_compute_accelerations(c, 0)) return 1;
       I.interactions += c->st.interactions;
       // ---- advance_and_find_timesteps, timestep.c:29 ----
-      if(nactive > 0 && run_kick(c, tp, c->n_tgt_gas > 0)) return 1;
+      if(nactive_glob > 0 && run_kick(c, tp, true)) return 1;
       I.steps_done++;
       I.active_total += nactive;
       I.active_last = nactive;
@@ -497,15 +530,15 @@ extern "C" int gl_get_run_state(gl_ctx *c, double *pos3, double *vel3, double *v
 				int *timebin, int *ti_begstep, int where)
 {
   cudaSetDevice(c->device);
-  const long long n = c->n;
-  if(n <= 0) return c->fail("gl_get_run_state: no particles");
+  const long long n = c->n_own;
+  if(c->n <= 0 || n <= 0) return c->fail("gl_get_run_state: no particles");
   const cudaMemcpyKind k = where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if(pos3) GL_CUDA(c, cudaMemcpyAsync(pos3, c->in_pos.p, 3 * n * sizeof(double), k, c->stream));
   if(vel3) GL_CUDA(c, cudaMemcpyAsync(vel3, c->in_vel.p, 3 * n * sizeof(double), k, c->stream));
   if(velpred3)
     {
-      if(!c->have_velpred) return c->fail("gl_get_run_state: no VelPred in the context");
-      GL_CUDA(c, cudaMemcpyAsync(velpred3, c->in_velpred.p, 3 * c->n_velpred * sizeof(double), k, c->stream));
+      if(!c->run_ready) return c->fail("gl_get_run_state: VelPred has a row per particle only after gl_run_begin");
+      GL_CUDA(c, cudaMemcpyAsync(velpred3, c->in_velpred.p, 3 * n * sizeof(double), k, c->stream));
     }
   if(hsml) GL_CUDA(c, cudaMemcpyAsync(hsml, c->in_hsml.p, n * sizeof(double), k, c->stream));
   if(entropy) GL_CUDA(c, cudaMemcpyAsync(entropy, c->in_entropy.p, n * sizeof(double), k, c->stream));

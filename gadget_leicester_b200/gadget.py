@@ -330,9 +330,10 @@ class ForcePath:
         self._relative_criterion_engaged()
         return {k: getattr(info, k) for k, _ in L.GLRunInfo._fields_}
 
-    def run_state(self, n_gas):
+    def run_state(self):
+        """P[]-indexed state of the resident loop (VelPred: a row per particle, meaningful for gas)."""
         n = self.N
-        out = dict(Pos=np.zeros((n, 3)), Vel=np.zeros((n, 3)), VelPred=np.zeros((int(n_gas), 3)), Hsml=np.zeros(n), Entropy=np.zeros(n),
+        out = dict(Pos=np.zeros((n, 3)), Vel=np.zeros((n, 3)), VelPred=np.zeros((n, 3)), Hsml=np.zeros(n), Entropy=np.zeros(n),
                    DtEntropy=np.zeros(n), TimeBin=np.zeros(n, np.int32), Ti_begstep=np.zeros(n, np.int32))
         self._chk(self._lib.gl_get_run_state(self._ctx, *[L._ptr(out[k]) for k in ("Pos", "Vel", "VelPred", "Hsml", "Entropy", "DtEntropy",
                                                                                      "TimeBin", "Ti_begstep")], 0))

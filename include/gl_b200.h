@@ -337,8 +337,12 @@ int gl_gadget_push(gl_ctx * ctx, void *P, void *SphP, int what);
  * the bin rule (timestep.c:136-154) + do_the_kick (timestep.c:364) for them - nothing crosses PCIe but the 32
  * TimeBinCount[] values per step.  Same restrictions as the host-side pieces above (non-comoving, tree rebuilt every
  * step = TreeDomainUpdateFrequency 0, no sub-grid loops inside the loop: DragAccel and DeltaDustMomentum are zero).
- * Single rank.  The gas particles must form the leading block of the particle set, as in P[]. */
-/* SphP[].VelPred of the gas block (n_gas x 3); without it gl_run_begin starts from the loaded velocities */
+ * Multi-rank mode (a communicator attached): every rank integrates its own particles, gl_run_steps is collective -
+ * the ranks' TimeBinCount[] are all-gathered (the MPI_Allreduce of run.c:218 / :290), the force path imports its
+ * locally-essential set in every step, an endrun() on one rank stops all.  The ranks keep the particles they have
+ * (any assignment gives the same results; re-balancing is gl_domain_split_collective + the caller's exchange). */
+/* SphP[].VelPred of the leading n_gas particles (SphP[i] belongs to P[i]); gas particles without a row start from the
+ * loaded velocities in gl_run_begin */
 int gl_set_velpred(gl_ctx * ctx, const double *velpred3, long long n_gas, int where);
 /* P[].g.GravAccel, SphP[].a.HydroAccel (3n each), SphP[].MaxSignalVel (n), indexed like P[] (non-gas rows of the
  * last two are ignored); NULL = keep what the last force computation in this context left.  */
@@ -360,7 +364,8 @@ typedef struct gl_run_info
 /* nsteps iterations of the loop; par->Ti_Current and par->TimeBinActive[] are advanced in place (the caller's
  * All.Ti_Current / TimeBinActive[]) */
 int gl_run_steps(gl_ctx * ctx, gl_timestep_params * par, int nsteps, gl_run_info * info);
-/* the state the loop integrates, indexed like P[] (velpred3: the n_gas leading rows); NULL = not wanted.  Forces,
+/* the state the loop integrates, indexed like P[] (velpred3: a row per particle, meaningful where the type is 0); NULL
+ * = not wanted.  Forces,
  * densities and the other results come from gl_get_gravity / gl_get_density / gl_get_hydro as usual */
 int gl_get_run_state(gl_ctx * ctx, double *pos3, double *vel3, double *velpred3, double *hsml, double *entropy, double *dtentropy,
 		     int *timebin, int *ti_begstep, int where);

@@ -93,7 +93,7 @@ def test_resident_loop_equals_the_reference_loop():
     info = fp.run(t, 8)
     assert info["steps_done"] == 8
     assert t.Ti_Current == int(loop[0]) == 80
-    st = fp.run_state(ng)
+    st = fp.run_state()
     res = fp.results()
 
     def mine(a):                                         # my arrays are in begin order: bring them to id order
@@ -140,7 +140,7 @@ def test_resident_kick_equals_host_kick():
     fp, n, ng = _start(par, b)
     t = _tpar(fp, par, 64, 6)
     fp.advance_and_find_timesteps(t, commit_dtentropy=False)
-    st = fp.run_state(ng)
+    st = fp.run_state()
     # every particle is on an active bin at Ti = 64: all step starts move to 64, velocities change
     assert np.all(st["Ti_begstep"] == 64)
     assert np.all((st["TimeBin"] >= 1) & (st["TimeBin"] <= 6))
@@ -168,3 +168,103 @@ def test_run_begin_needs_the_whole_state():
     fp.compute_accelerations()
     fp.run_begin(0)
     fp.close()
+
+
+def _loop_state(fp):
+    st = fp.run_state()
+    st.update(fp.results())
+    return st
+
+
+def ranks_vs_one(world, nsteps=8, n_gas=24000):
+    """the loop on `world` in-process ranks and in one context from the same start; returns (errors, info of the one
+    context, time-line mismatches)"""
+    import threading
+    from gadget_leicester_b200 import lib as L
+    from gadget_leicester_b200.gadget import ForcePath
+    ps = ics.disc(n_gas, seed=11)
+    par = ics.default_params()
+    par["Timebase_interval"] = 1.0e-4
+    ps["hsml"] = ics.guess_hsml(ps, par["DesNumNgb"])
+    ps["hsml"][ps["type"] == 5] = par["Softening"][5]
+    n = ps["pos"].shape[0]
+    ngas = int((ps["type"] == 0).sum())
+    g = np.random.Generator(np.random.Philox(key=77))
+    ps["timebin"] = g.integers(1, 7, size=n).astype(np.int32)
+    ps["ti_begstep"] = (64 - (1 << ps["timebin"])).astype(np.int32)
+    one = ForcePath(par)
+    one.load(ps)
+    order = one.peano_hilbert_order(ngas)
+    pso = {k: (np.ascontiguousarray(v[order]) if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in ps.items()}
+
+    def tpar(fp):
+        # (the accretion time-step criterion of the sinks is switched off: it wants steps far below this time line's tick)
+        return fp.timestep_params(64, [1 if b <= 6 else 0 for b in range(29)], Timebase_interval=par["Timebase_interval"],
+                                  ErrTolIntAccuracy=0.025, CourantFac=0.15, MaxSizeTimestep=64 * par["Timebase_interval"], MinSizeTimestep=0.0,
+                                  MinEgySpec=0.0, SofteningTable=par["Softening"], OuterBoundary=1.4e10, UnitVelocity_in_cm_per_s=2.98e6,
+                                  FeedBackVelocity=1.0, SMBHmass=0.5, InnerBoundary=0.0, SinkBoundary=0.0, AccDtBlackHole=0.007)
+
+    def drive(fp, p):
+        fp.set_params(Ti_Current=64)
+        fp.load(p)
+        fp.compute_accelerations()          # Barnes-Hut pass + cold-start density: the state the loop starts from
+        fp.set_TreeReconstructFlag(1)       # a new step: new tree (node maxsoft / hmax from the settled Hsml on ranks and in one context alike)
+        fp.compute_accelerations()          # relative criterion
+        fp.run_begin(64)
+        t = tpar(fp)
+        fp.advance_and_find_timesteps(t)
+        info = fp.run(t, nsteps)
+        return _loop_state(fp), info, int(t.Ti_Current)
+
+    ref, info1, ti1 = drive(one, pso)
+    one.close()
+    lib = L.load_library()
+    group = lib.gl_comm_local_group_create(world)
+    m = -(-n // world)
+    res, err = [None] * world, [None] * world
+
+    def worker(r):
+        try:
+            lo, hi = r * m, min(n, (r + 1) * m)
+            psr = {k: (np.ascontiguousarray(v[lo:hi]) if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in pso.items()}
+            fp = ForcePath(par)
+            fp.comm_init_local(r, group, world)
+            res[r] = drive(fp, psr)
+            fp.close()
+        except Exception as ex:   # noqa: BLE001
+            err[r] = ex
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    lib.gl_comm_local_group_destroy(group)
+    for e in err:
+        if e is not None:
+            raise e
+    cat = lambda k: np.concatenate([r[0][k] for r in res])       # noqa: E731
+    line = dict(Ti_Current=[r[2] != ti1 for r in res].count(True), TimeBin=int((cat("TimeBin") != ref["TimeBin"]).sum()),
+                Ti_begstep=int((cat("Ti_begstep") != ref["Ti_begstep"]).sum()),
+                active_total=int(sum(r[1]["active_total"] for r in res) - info1["active_total"]))
+    gas = pso["type"] == 0
+    errs = {}
+    for k in ("Pos", "Vel", "GravAccel", "Hsml"):
+        errs[k] = util.rel_err_vec(cat(k), ref[k])
+    for k in ("VelPred", "Entropy", "Density", "HydroAccel", "Pressure", "MaxSignalVel"):
+        errs[k] = util.rel_err_vec(cat(k)[gas], ref[k][gas])
+    return errs, info1, line, n
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_resident_loop_on_ranks_equals_one_context(world):
+    """The same loop in multi-rank mode (several contexts of this process as ranks, in-process transport): every rank
+    integrates its own stretch of the Peano-Hilbert order, the TimeBinCount[] are all-gathered, the force path imports
+    its locally-essential set in every step - also in steps where a rank has few or no active particles.  After eight
+    steps on individual time bins the ranks hold what one context holds: time line exact, the floating-point state to
+    the 1e-12 per evaluation of FP64 sums formed in another order."""
+    errs, info1, line, n = ranks_vs_one(world)
+    assert info1["steps_done"] == 8 and 0 < info1["active_total"] < 8 * n
+    assert all(v == 0 for v in line.values()), line
+    for k, tol in (("Pos", 1e-13), ("Vel", 1e-10), ("GravAccel", 1e-10), ("Hsml", 1e-10), ("VelPred", 1e-10), ("Entropy", 1e-10),
+                   ("Density", 1e-10), ("HydroAccel", 1e-8), ("Pressure", 1e-10), ("MaxSignalVel", 1e-10)):
+        assert errs[k].max() < tol, util.summarize(k, errs[k])
