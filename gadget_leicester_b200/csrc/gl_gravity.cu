@@ -283,9 +283,11 @@ int glg_gravity(gl_ctx *c)
     if(glt_build(c)) return 1;
   if(gl_prepare_targets(c)) return 1;
   long long n = c->n, nt = c->n_tgt;
-  GL_CUDA(c, c->o_acc.ensure(3 * n));
-  GL_CUDA(c, c->o_oldacc.ensure(n));
-  GL_CUDA(c, c->o_gravcost.ensure(n));
+  // (ensure_keep: with an active SUBSET the results of the other particles are state - the resident loop integrates
+  //  them - and must survive a build that imported more particles than the last one)
+  GL_CUDA(c, c->o_acc.ensure_keep(3 * n));
+  GL_CUDA(c, c->o_oldacc.ensure_keep(n));
+  GL_CUDA(c, c->o_gravcost.ensure_keep(n));
   GL_CUDA(c, c->d_counter.ensure(8));
   GL_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 8 * sizeof(unsigned long long), c->stream));
   // non-targets keep their OldAcc (only the active list is updated, gravtree.c:381-392)

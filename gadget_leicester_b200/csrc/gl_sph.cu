@@ -1103,15 +1103,15 @@ int gls_density(gl_ctx *c)
   if(c->par.ComovingIntegrationOn) return c->fail("density: ComovingIntegrationOn != 0 is not implemented");
   if(gl_prepare_targets(c)) return 1;
   long long n = c->n, nt = c->n_tgt_sph;
-  GL_CUDA(c, c->o_numngb.ensure(n));
-  GL_CUDA(c, c->o_density.ensure(n));
-  GL_CUDA(c, c->o_dhsml.ensure(n));
-  GL_CUDA(c, c->o_divvel.ensure(n));
-  GL_CUDA(c, c->o_curlvel.ensure(n));
-  GL_CUDA(c, c->o_pressure.ensure(n));
-  GL_CUDA(c, c->o_sinkrho.ensure(n));
-  GL_CUDA(c, c->o_sinkentr.ensure(n));
-  GL_CUDA(c, c->o_sinkvel.ensure(3 * n));
+  GL_CUDA(c, c->o_numngb.ensure_keep(n));
+  GL_CUDA(c, c->o_density.ensure_keep(n));
+  GL_CUDA(c, c->o_dhsml.ensure_keep(n));
+  GL_CUDA(c, c->o_divvel.ensure_keep(n));
+  GL_CUDA(c, c->o_curlvel.ensure_keep(n));
+  GL_CUDA(c, c->o_pressure.ensure_keep(n));
+  GL_CUDA(c, c->o_sinkrho.ensure_keep(n));
+  GL_CUDA(c, c->o_sinkentr.ensure_keep(n));
+  GL_CUDA(c, c->o_sinkvel.ensure_keep(3 * n));
   if(c->o_denspairs.cap < (size_t) n)
     {
       GL_CUDA(c, c->o_denspairs.ensure(n));
@@ -1386,10 +1386,10 @@ int gls_hydro_begin(gl_ctx *c)
   if(c->o_density.cap < (size_t) c->n) return c->fail("hydro_force: density() has not been run (SphP.Density unknown)");
   if(gl_prepare_targets(c)) return 1;
   long long n = c->n;
-  GL_CUDA(c, c->o_hacc.ensure(3 * n));
-  GL_CUDA(c, c->o_dtentr.ensure(n));
-  GL_CUDA(c, c->o_maxsig.ensure(n));
-  GL_CUDA(c, c->o_hydropairs.ensure(n));
+  GL_CUDA(c, c->o_hacc.ensure_keep(3 * n));
+  GL_CUDA(c, c->o_dtentr.ensure_keep(n));
+  GL_CUDA(c, c->o_maxsig.ensure_keep(n));
+  GL_CUDA(c, c->o_hydropairs.ensure_keep(n));
   GL_CUDA(c, c->h_q.ensure(c->nit + 1));
   GL_CUDA(c, c->h_r.ensure(c->nit + 1));
   GL_CUDA(c, c->d_counter.ensure(16));

@@ -255,7 +255,7 @@ def ranks_vs_one(world, nsteps=8, n_gas=24000):
     return errs, info1, line, n
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_resident_loop_on_ranks_equals_one_context(world):
     """The same loop in multi-rank mode (several contexts of this process as ranks, in-process transport): every rank
     integrates its own stretch of the Peano-Hilbert order, the TimeBinCount[] are all-gathered, the force path imports
