@@ -548,3 +548,156 @@ extern "C" int gl_get_run_state(gl_ctx *c, double *pos3, double *vel3, double *v
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
+
+// ---------------------------------------------------------------- the loop on the reference's own P[] / SphP[] ----
+// What a reference-side binding calls instead of run.c's loop body for `nsteps` iterations: the structs are read ONCE,
+// the loop runs on the device, the structs are written ONCE - where the per-step drop-in call moves them through the
+// host's memory twice per step.  Not a pipeline like gl_gadget_compute_accelerations: one pass of the host pool each way.
+#include "gl_host.h"
+
+namespace
+{
+template <class T> inline T &fld(char *base, long long off) { return *reinterpret_cast<T *>(base + off); }
+template <class T> inline const T &fld(const char *base, long long off) { return *reinterpret_cast<const T *>(base + off); }
+}
+
+extern "C" int gl_gadget_run_steps(gl_ctx *c, void *Pv, void *SphPv, long long NumPart, long long N_gas, gl_timestep_params *tp, int nsteps,
+				   gl_run_info *info)
+{
+  cudaSetDevice(c->device);
+  if(!c->have_lay) return c->fail("gl_gadget_run_steps: gl_gadget_bind not called");
+  const gl_gadget_layout L = c->lay;
+  const long long n = NumPart, ng = std::min(N_gas, NumPart);
+  if(n <= 0) return c->fail("gl_gadget_run_steps: NumPart <= 0");
+  if(L.p_Ti_current < 0) return c->fail("gl_gadget_run_steps: the layout has no P.Ti_current");
+  char *P = (char *) Pv, *S = (char *) SphPv;
+  // ---- gather: everything run()'s loop carries from one step to the next ----
+  std::vector<double> f((size_t) n * 29);
+  std::vector<int> q((size_t) n * 3);
+  double *pos = f.data(), *vel = pos + 3 * n, *mass = vel + 3 * n, *hsml = mass + n, *oldacc = hsml + n, *entropy = oldacc + n,
+    *dtentropy = entropy + n, *velpred = dtentropy + n, *gacc = velpred + 3 * n, *hacc = gacc + 3 * n, *maxsig = hacc + 3 * n,
+    *density = maxsig + n, *pressure = density + n, *dhsml = pressure + n, *divvel = dhsml + n, *curlvel = divvel + n,
+    *numngb = curlvel + n, *gcost = numngb + n;
+  int *type = q.data(), *timebin = type + n, *tibeg = timebin + n;
+  std::atomic<long long> behind{0}, badgas{0};
+  const int ti = tp->Ti_Current;
+  HostPool::get().run(n, 8192, [&](long long, long long a, long long b) {
+    long long nb = 0, bg = 0;
+    for(long long i = a; i < b; i++)
+      {
+	const char *pi = P + i * L.p_stride;
+	const int ty = fld<short>(pi, L.p_Type);
+	for(int k = 0; k < 3; k++)
+	  {
+	    pos[3 * i + k] = (&fld<double>(pi, L.p_Pos))[k];
+	    vel[3 * i + k] = (&fld<double>(pi, L.p_Vel))[k];
+	    gacc[3 * i + k] = (&fld<double>(pi, L.p_GravAccel))[k];
+	  }
+	mass[i] = fld<double>(pi, L.p_Mass);
+	hsml[i] = fld<double>(pi, L.p_Hsml);
+	oldacc[i] = fld<double>(pi, L.p_OldAcc);
+	type[i] = ty;
+	timebin[i] = fld<short>(pi, L.p_TimeBin);
+	tibeg[i] = fld<int>(pi, L.p_Ti_begstep);
+	if(ty != 3 && fld<int>(pi, L.p_Ti_current) != ti) nb++;
+	if((ty == 0) != (i < ng)) bg++;
+	if(i < ng)
+	  {
+	    const char *si = S + i * L.sph_stride;
+	    for(int k = 0; k < 3; k++)
+	      {
+		velpred[3 * i + k] = (&fld<double>(si, L.s_VelPred))[k];
+		hacc[3 * i + k] = (&fld<double>(si, L.s_HydroAccel))[k];
+	      }
+	    entropy[i] = fld<double>(si, L.s_Entropy);
+	    dtentropy[i] = fld<double>(si, L.s_DtEntropy);
+	    maxsig[i] = fld<double>(si, L.s_MaxSignalVel);
+	    density[i] = fld<double>(si, L.s_Density);
+	    pressure[i] = fld<double>(si, L.s_Pressure);
+	    dhsml[i] = fld<double>(si, L.s_DhsmlDensityFactor);
+	    divvel[i] = fld<double>(si, L.s_DivVel);
+	    curlvel[i] = fld<double>(si, L.s_CurlVel);
+	  }
+	else
+	  {
+	    for(int k = 0; k < 3; k++) velpred[3 * i + k] = hacc[3 * i + k] = 0;
+	    entropy[i] = dtentropy[i] = maxsig[i] = density[i] = pressure[i] = dhsml[i] = divvel[i] = curlvel[i] = 0;
+	  }
+      }
+    if(nb) behind.fetch_add(nb);
+    if(bg) badgas.fetch_add(bg);
+  });
+  if(badgas.load()) return c->fail("gl_gadget_run_steps: the gas particles (Type 0) must be exactly P[0..N_gas)");
+  if(behind.load())
+    return c->fail("gl_gadget_run_steps: " + std::to_string(behind.load()) + " particles are not drifted to Ti_Current (P.Ti_current != All.Ti_Current): "
+		   "call move_particles() / gl_gadget_drift first");
+  if(gl_load_particles(c, n, pos, vel, mass, type, hsml, oldacc, timebin, tibeg, entropy, dtentropy, 0)) return 1;
+  c->par.Ti_Current = ti;
+  if(ng > 0)
+    {
+      if(gl_set_velpred(c, velpred, ng, 0)) return 1;
+      if(gl_set_sph_state(c, density, pressure, dhsml, divvel, curlvel, 0)) return 1;
+    }
+  if(gl_set_accelerations(c, gacc, ng > 0 ? hacc : nullptr, ng > 0 ? maxsig : nullptr, 0)) return 1;
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if(gl_run_begin(c, ti)) return 1;
+  // ---- the loop ----
+  gl_run_info I{};
+  if(gl_run_steps(c, tp, nsteps, &I)) return 1;
+  if(info) *info = I;
+  // ---- scatter: the state and the results of the last force computation of every particle ----
+  std::vector<float> gc((size_t) n);
+  if(gl_get_run_state(c, pos, vel, velpred, hsml, entropy, dtentropy, timebin, tibeg, 0)) return 1;
+  const long long keep_first = c->res_first, keep_count = c->res_count;
+  c->res_first = 0;
+  c->res_count = n;		// the own particles (the arrays may be longer in multi-rank mode)
+  int rc = gl_get_gravity(c, gacc, oldacc, gc.data(), 0);
+  if(!rc && ng > 0) rc = gl_get_density(c, nullptr, numngb, density, dhsml, divvel, curlvel, pressure, nullptr, nullptr, nullptr, 0);
+  if(!rc && ng > 0) rc = gl_get_hydro(c, hacc, nullptr, maxsig, 0);
+  c->res_first = keep_first;
+  c->res_count = keep_count;
+  if(rc) return 1;
+  (void) gcost;
+  const int ti_end = tp->Ti_Current;
+  const bool stepped = I.steps_done > 0;
+  HostPool::get().run(n, 8192, [&](long long, long long a, long long b) {
+    for(long long i = a; i < b; i++)
+      {
+	char *pi = P + i * L.p_stride;
+	const int ty = type[i];
+	for(int k = 0; k < 3; k++)
+	  {
+	    (&fld<double>(pi, L.p_Pos))[k] = pos[3 * i + k];
+	    (&fld<double>(pi, L.p_Vel))[k] = vel[3 * i + k];
+	    (&fld<double>(pi, L.p_GravAccel))[k] = gacc[3 * i + k];
+	  }
+	fld<double>(pi, L.p_Hsml) = hsml[i];
+	fld<double>(pi, L.p_OldAcc) = oldacc[i];
+	if(stepped) fld<float>(pi, L.p_GravCost) = gc[(size_t) i];
+	fld<short>(pi, L.p_TimeBin) = (short) timebin[i];
+	fld<int>(pi, L.p_Ti_begstep) = tibeg[i];
+	if(ty != 3) fld<int>(pi, L.p_Ti_current) = ti_end;	// predict.c:134: virtual particles are never drifted
+	if(i < ng)
+	  {
+	    char *si = S + i * L.sph_stride;
+	    if(stepped) fld<double>(pi, L.p_NumNgb) = numngb[i];
+	    for(int k = 0; k < 3; k++)
+	      {
+		(&fld<double>(si, L.s_VelPred))[k] = velpred[3 * i + k];
+		(&fld<double>(si, L.s_HydroAccel))[k] = hacc[3 * i + k];
+	      }
+	    fld<double>(si, L.s_Entropy) = entropy[i];
+	    fld<double>(si, L.s_DtEntropy) = dtentropy[i];
+	    fld<double>(si, L.s_MaxSignalVel) = maxsig[i];
+	    fld<double>(si, L.s_Density) = density[i];
+	    fld<double>(si, L.s_Pressure) = pressure[i];
+	    fld<double>(si, L.s_DhsmlDensityFactor) = dhsml[i];
+	    fld<double>(si, L.s_DivVel) = divvel[i];
+	    fld<double>(si, L.s_CurlVel) = curlvel[i];
+	    if(L.s_DragAccel >= 0 && stepped)
+	      for(int k = 0; k < 3; k++) (&fld<double>(si, L.s_DragAccel))[k] = 0;	// do_the_kick, timestep.c:503-505
+	  }
+      }
+  });
+  return 0;
+}

@@ -369,6 +369,15 @@ int gl_run_steps(gl_ctx * ctx, gl_timestep_params * par, int nsteps, gl_run_info
  * densities and the other results come from gl_get_gravity / gl_get_density / gl_get_hydro as usual */
 int gl_get_run_state(gl_ctx * ctx, double *pos3, double *vel3, double *velpred3, double *hsml, double *entropy, double *dtentropy,
 		     int *timebin, int *ti_begstep, int where);
+/* The same loop on the reference's own arrays: P[0..NumPart) / SphP[0..N_gas) are read once (everything the loop
+ * carries: positions, velocities, VelPred, Hsml, entropies, time bins, the accelerations and SphP state of the last
+ * force computation), nsteps iterations run on the device, and the structs are written once - where
+ * gl_gadget_compute_accelerations moves them through host memory twice PER STEP.  Every particle must be drifted to
+ * par->Ti_Current on entry (P.Ti_current, as after move_particles(); Type 3 excepted, predict.c:134); on return all
+ * are drifted to the new par->Ti_Current, and P.TimeBin / P.Ti_begstep are current: the caller rebuilds its time-bin
+ * lists from them (reconstruct_timebins(), timestep.c) before it touches them.  gl_gadget_bind first. */
+int gl_gadget_run_steps(gl_ctx * ctx, void *P, void *SphP, long long NumPart, long long N_gas, gl_timestep_params * par, int nsteps,
+			gl_run_info * info);
 
 /* ---- the tree, in the reference's own storage (SURVEY.md 8(b) "Tree (if CPU consumers are kept)") ---------------
  * The sub-grid loops that follow the force path in the reference (sink accretion blackhole.c:794,1201,1351, dust

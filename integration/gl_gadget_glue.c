@@ -656,6 +656,87 @@ void savepositions(int num)
 }
 #endif /* GL_SNAPSHOT_IO */
 
+#if defined(GL_TIMESTEP) || defined(GL_RESIDENT_RUN)
+/* All.* -> gl_timestep_params (timestep.c:607-1122 reads these) */
+static void gl_fill_timestep_params(gl_timestep_params * t)
+{
+  int i;
+  t->Ti_Current = All.Ti_Current;
+  for(i = 0; i < 32; i++)
+    t->TimeBinActive[i] = i < TIMEBINS ? TimeBinActive[i] : 0;
+  t->Timebase_interval = All.Timebase_interval;
+  t->ErrTolIntAccuracy = All.ErrTolIntAccuracy;
+  t->CourantFac = All.CourantFac;
+  t->MaxSizeTimestep = All.MaxSizeTimestep;
+  t->MinSizeTimestep = All.MinSizeTimestep;
+  t->MinEgySpec = All.MinEgySpec;
+  t->GammaMinus1 = GAMMA_MINUS1;
+  for(i = 0; i < 6; i++)
+    t->SofteningTable[i] = All.SofteningTable[i];
+  t->OuterBoundary = All.OuterBoundary;
+  t->UnitVelocity_in_cm_per_s = All.UnitVelocity_in_cm_per_s;
+  t->FeedBackVelocity = All.FeedBackVelocity;
+  t->SMBHmass = All.SMBHmass;
+  t->InnerBoundary = All.InnerBoundary;
+  t->SinkBoundary = All.SinkBoundary;
+  t->AccDtBlackHole = All.AccDtBlackHole;
+#ifdef DUST
+  t->p_DeltaDustMomentum = offsetof(struct particle_data, DeltaDustMomentum);
+#else
+  t->p_DeltaDustMomentum = -1;
+#endif
+#ifdef VIRTUAL
+  t->p_NewDensity = offsetof(struct particle_data, NewDensity);
+#else
+  t->p_NewDensity = -1;
+#endif
+}
+#endif
+
+#ifdef GL_RESIDENT_RUN
+/* ---- run.c:63-110 for nsteps iterations with the particle state resident on the GPU ----------------------------------
+ * run()'s loop body is  find_next_sync_point_and_drift(); domain_Decomposition(); compute_accelerations(0);
+ * advance_and_find_timesteps();  on P[] / SphP[] in host memory.  A maintainer who does not need the structs between
+ * two outputs replaces `nsteps` iterations by ONE call of this function (between outputs: nsteps = until
+ * All.Ti_nextoutput; the statistics / restart-file hooks of run.c:66-110 then run once per call): the structs are read
+ * once, the loop runs in the library (gl_run_steps: drift, tree + gravity + density + hydro for the active particles,
+ * kick), the structs are written once, and the time line of the host is brought up to date - All.Ti_Current, All.Time,
+ * TimeBinActive[], the time-bin lists (reconstruct_timebins(), the reference's own function for exactly this).
+ * Restrictions: include/gl_b200.h "run()'s loop".  Returns the iterations executed. */
+int gl_glue_run_steps(int nsteps)
+{
+  gl_timestep_params t;
+  gl_run_info info;
+  int i;
+  if(All.ComovingIntegrationOn)
+    gl_fail("gl_glue_run_steps: comoving integration");
+  if(NTask != 1)
+    gl_fail("gl_glue_run_steps: the struct-level entry point handles NTask == 1 (at NTask > 1 keep the state in the library: gl_run_steps)");
+  gl_attach();
+  gl_sync_params();
+  /* everybody to All.Ti_Current first (the loop drifts all particles from ONE time) */
+  if(gl_gadget_drift(&GL_Layout, P, SphP, NumPart, N_gas, All.Ti_Current, All.Timebase_interval, All.MinGasHsml, NULL))
+    endrun(12);
+  gl_fill_timestep_params(&t);
+  if(gl_gadget_run_steps(GL, P, SphP, NumPart, N_gas, &t, nsteps, &info))
+    gl_fail("gl_gadget_run_steps");
+  All.Ti_Current = t.Ti_Current;
+  All.Time = All.TimeBegin + All.Ti_Current * All.Timebase_interval;	/* run.c:262-265 */
+  for(i = 0; i < TIMEBINS; i++)
+    TimeBinActive[i] = t.TimeBinActive[i];
+  All.NumCurrentTiStep += info.steps_done;
+  if(All.TypeOfOpeningCriterion == 1 && info.steps_done > 0)
+    All.ErrTolTheta = 0;	/* gravtree.c:396-397 */
+  /* reconstruct_timebins() checks its active list against NumForceUpdate (predict.c:104-123): the particles of the
+   * last step's active bins are still on active bins after their kick (a bin only grows onto a synchronised bin) */
+  NumForceUpdate = (int) info.active_last;
+  reconstruct_timebins();
+  TreeReconstructFlag = 1;
+  gl_loaded_for = -1;
+  return info.steps_done;
+}
+#endif
+
 #ifdef GL_TIMESTEP
 /* ---- advance_and_find_timesteps() (proto.h; timestep.c:29) --------------------------------------------------------
  * The per-particle work - get_timestep, the bin decision, do_the_kick - runs in the library on all host cores
@@ -674,35 +755,7 @@ void advance_and_find_timesteps(void)
     gl_fail("advance_and_find_timesteps: comoving integration");
   gl_fill_layout();
   All.DoDynamicUpdate = 0;
-  t.Ti_Current = All.Ti_Current;
-  for(i = 0; i < 32; i++)
-    t.TimeBinActive[i] = i < TIMEBINS ? TimeBinActive[i] : 0;
-  t.Timebase_interval = All.Timebase_interval;
-  t.ErrTolIntAccuracy = All.ErrTolIntAccuracy;
-  t.CourantFac = All.CourantFac;
-  t.MaxSizeTimestep = All.MaxSizeTimestep;
-  t.MinSizeTimestep = All.MinSizeTimestep;
-  t.MinEgySpec = All.MinEgySpec;
-  t.GammaMinus1 = GAMMA_MINUS1;
-  for(i = 0; i < 6; i++)
-    t.SofteningTable[i] = All.SofteningTable[i];
-  t.OuterBoundary = All.OuterBoundary;
-  t.UnitVelocity_in_cm_per_s = All.UnitVelocity_in_cm_per_s;
-  t.FeedBackVelocity = All.FeedBackVelocity;
-  t.SMBHmass = All.SMBHmass;
-  t.InnerBoundary = All.InnerBoundary;
-  t.SinkBoundary = All.SinkBoundary;
-  t.AccDtBlackHole = All.AccDtBlackHole;
-#ifdef DUST
-  t.p_DeltaDustMomentum = offsetof(struct particle_data, DeltaDustMomentum);
-#else
-  t.p_DeltaDustMomentum = -1;
-#endif
-#ifdef VIRTUAL
-  t.p_NewDensity = offsetof(struct particle_data, NewDensity);
-#else
-  t.p_NewDensity = -1;
-#endif
+  gl_fill_timestep_params(&t);
   for(i = FirstActiveParticle, n = 0; i >= 0; i = NextActiveParticle[i]) n++;
   act = (int *) malloc(sizeof(int) * (n > 0 ? n : 1));	/* private scratch: the mymalloc stack stays as found */
   old = (int *) malloc(sizeof(int) * (n > 0 ? n : 1));

@@ -25,6 +25,7 @@
  *     K  Peano-Hilbert and Morton key of every particle (peano_and_morton_key, peano.c:335)
  *     A  compute_accelerations-order block:  R G D U H   (accel.c:61-106 without sub-grid physics)
  *     L  eight iterations of run()'s loop: find_next_sync_point_and_drift, domain_Decomposition, force path, kick
+ *     M  op L with its eight iterations run by the glue's gl_glue_run_steps() (drop-in builds: the device-resident loop)
  *     B  blackhole_accretion()               (accel.c:189, blackhole.c:70: sink accretion loops blackhole_evaluate :794 and
  *        blackhole_evaluate_swallow :1201 over ngb_treefind_blackhole :1351) on the current tree; sink state is derived
  *        from the input (see set_subgrid_state), everything read and written is dumped (pre / post)
@@ -325,6 +326,7 @@ void compute_accelerations(int mode)
 }
 
 void ref_density(void) __attribute__((weak));
+int gl_glue_run_steps(int nsteps) __attribute__((weak));	/* integration/gl_gadget_glue.c -DGL_RESIDENT_RUN (drop-in builds) */
 void ref_hydro_force(void) __attribute__((weak));
 
 static void dump_nodes(const char *prefix)
@@ -716,6 +718,46 @@ int main(int argc, char **argv)
 		    advance_and_find_timesteps();
 		    All.NumCurrentTiStep++;
 		  }
+		for(i = 0, k = 0; i < NumPart; i++) k += (P[i].Ti_current == All.Ti_Current);
+		q[0] = All.Ti_Current; q[1] = All.Time; q[2] = k; q[3] = step;
+		put(prefix, "loop", 'd', 4, 1, q);
+		dump_kick_state(prefix, "end");
+		dump_loop_extra(prefix, "end");
+	      }
+	      break;
+	    case 'M':
+	      /* op L with the eight iterations handed to the glue's gl_glue_run_steps() (device-resident loop); the same dumps.
+	         several iterations of run()'s loop (run.c:63-110) on individual time steps, starting at the synchronisation
+	         point of op V: find_next_sync_point_and_drift (run.c:190), domain_Decomposition, the force path for the
+	         active particles, advance_and_find_timesteps.  TreeDomainUpdateFrequency = 0: a new decomposition and a new
+	         tree in every step (no dynamic tree update), which is how the GPU path runs. */
+	      {
+		int k, step;
+		double q[4];
+		All.Ti_Current = 64;
+		All.ErrTolIntAccuracy = 0.025; All.CourantFac = 0.15; All.TypeOfTimestepCriterion = 0;
+		All.MaxSizeTimestep = 200 * All.Timebase_interval; All.MinSizeTimestep = 0;
+		All.MinEgySpec = par[P_MINEGYSPEC];
+		All.OuterBoundary = 1.4e10; All.UnitVelocity_in_cm_per_s = 2.98e6; All.FeedBackVelocity = 1.0;
+		All.SMBHmass = 0.5; All.InnerBoundary = 2.0e-2; All.SinkBoundary = 1.0e-4; All.AccDtBlackHole = 0.007;
+		All.TreeDomainUpdateFrequency = 0; All.Ti_nextoutput = -1; All.TimeBegin = 0;
+		for(i = 0; i < NumPart; i++)
+		  {
+		    int b = P[i].TimeBin < 1 ? 1 : (P[i].TimeBin > 6 ? 6 : P[i].TimeBin);
+		    P[i].TimeBin = b;
+		    P[i].Ti_begstep = All.Ti_Current - (1 << b);
+		    P[i].Ti_current = All.Ti_Current;
+		  }
+		for(i = 0; i < TIMEBINS; i++) TimeBinActive[i] = (i <= 6);
+		reconstruct_timebins();
+		Flag_FullStep = 1;
+		/* the state the loop starts from, complete enough to start the same loop elsewhere (the device-resident
+		   loop gl_run_steps, tests/test_gpu_resident.py) */
+		dump_kick_state(prefix, "begin");
+		dump_loop_extra(prefix, "begin");
+		advance_and_find_timesteps();
+		if(!gl_glue_run_steps) { fprintf(stderr, "op M needs a drop-in build with -DGL_RESIDENT_RUN\n"); return 2; }
+		step = gl_glue_run_steps(8);	/* the same eight iterations, in the library, on the device-resident state */
 		for(i = 0, k = 0; i < NumPart; i++) k += (P[i].Ti_current == All.Ti_Current);
 		q[0] = All.Ti_Current; q[1] = All.Time; q[2] = k; q[3] = step;
 		put(prefix, "loop", 'd', 4, 1, q);

@@ -268,3 +268,114 @@ def test_resident_loop_on_ranks_equals_one_context(world):
     for k, tol in (("Pos", 1e-13), ("Vel", 1e-10), ("GravAccel", 1e-10), ("Hsml", 1e-10), ("VelPred", 1e-10), ("Entropy", 1e-10),
                    ("Density", 1e-10), ("HydroAccel", 1e-8), ("Pressure", 1e-10), ("MaxSignalVel", 1e-10)):
         assert errs[k].max() < tol, util.summarize(k, errs[k])
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/ref_harness not built (needs /root/reference)")
+def test_loop_on_the_reference_structs():
+    """gl_gadget_run_steps: the same eight iterations, called the way a reference-side binding calls them - on P[] /
+    SphP[] byte buffers laid out like the reference's structs (read once, written once).  The first kick of op L is
+    taken with the host-side gl_gadget_advance_and_find_timesteps (bit-identical to the reference, tests/test_timestep.py);
+    afterwards the structs must hold the reference's end state."""
+    import ctypes as C
+    import test_timestep as TT
+    from gadget_leicester_b200 import aos, lib as L
+    from gadget_leicester_b200.gadget import ForcePath
+    par, b, e, loop = _reference_loop()
+    n, ng = b["Pos"].shape[0], b["VelPred"].shape[0]
+    z = {"pre_" + k: v for k, v in b.items()}
+    a = TT._arrays(z, "pre")
+    a.pview("p_OldAcc", np.float64)[:] = b["OldAcc"]
+    a.pview("p_Ti_current", np.int32)[:] = 64
+    a.sview("s_DhsmlDensityFactor", np.float64)[:] = b["DhsmlDensityFactor"]
+    a.sview("s_DivVel", np.float64)[:] = b["DivVel"]
+    a.sview("s_CurlVel", np.float64)[:] = b["CurlVel"]
+    q = dict(par)
+    q["ErrTolTheta"] = float(b["globals"][2])
+    q["Ti_Current"] = 64
+    fp = ForcePath(q)
+    t = _tpar(fp, par, 64, 6)
+    lay = aos.layout()
+    t.p_DeltaDustMomentum, t.p_NewDensity = lay["ts_p_DeltaDustMomentum"], lay["io_p_NewDensity"]
+    rc, msg = TT._call(a, t, np.arange(n, dtype=np.int32))
+    assert rc == 0, msg
+    lib = fp._lib
+    ls = aos.layout_struct()
+    fp._chk(lib.gl_gadget_bind(fp.ctx, C.byref(ls)))
+    info = L.GLRunInfo()
+    fp._chk(lib.gl_gadget_run_steps(fp.ctx, L._ptr(a.P), L._ptr(a.SphP), n, ng, C.byref(t), 8, C.byref(info)))
+    assert info.steps_done == 8 and t.Ti_Current == 80
+    ids = b["id"]
+
+    def mine(x):
+        out = np.zeros_like(x)
+        out[ids[: x.shape[0]] - 1] = x
+        return out
+
+    gas = np.zeros(n, bool)
+    gas[ids[:ng] - 1] = True
+    assert np.array_equal(mine(a.pview("p_TimeBin", np.int16).astype(np.int32)), _by_id(e, "TimeBin", n))
+    assert np.array_equal(mine(a.pview("p_Ti_begstep", np.int32).copy()), _by_id(e, "Ti_begstep", n))
+    ty = b["Type"]
+    assert np.all(a.pview("p_Ti_current", np.int32)[ty != 3] == 80)
+    for key, f, c, tol in (("Pos", "p_Pos", 3, 1e-9), ("Vel", "p_Vel", 3, 1e-6), ("GravAccel", "p_GravAccel", 3, 1e-5), ("Hsml", "p_Hsml", 1, 1e-9)):
+        err = util.rel_err_vec(mine(a.pview(f, np.float64, c).copy()), _by_id(e, key, n))
+        assert np.percentile(err, 99) < tol and err.max() < 30 * tol, util.summarize(key, err)
+    for key, f, c, tol in (("VelPred", "s_VelPred", 3, 1e-6), ("Entropy", "s_Entropy", 1, 1e-9), ("DtEntropy", "s_DtEntropy", 1, 1e-6),
+                           ("Density", "s_Density", 1, 1e-9), ("Pressure", "s_Pressure", 1, 1e-9), ("HydroAccel", "s_HydroAccel", 3, 1e-6),
+                           ("MaxSignalVel", "s_MaxSignalVel", 1, 1e-9)):
+        ref = _by_id(e, key, n)[gas]
+        got = mine(_pad(a.sview(f, np.float64, c).copy(), n))[gas]
+        if ref.ndim == 1:
+            err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6 * np.abs(ref).max())
+        else:
+            err = util.rel_err_vec(got, ref)
+        assert np.percentile(err, 99) < tol and err.max() < 100 * tol, util.summarize(key, err)
+    # a particle that is not at Ti_Current is refused (the loop drifts everybody from ONE time)
+    a.pview("p_Ti_current", np.int32)[5] = 79
+    assert lib.gl_gadget_run_steps(fp.ctx, L._ptr(a.P), L._ptr(a.SphP), n, ng, C.byref(t), 1, C.byref(info)) != 0
+    assert "not drifted" in lib.gl_last_error(fp.ctx).decode()
+    fp.close()
+
+
+REF_DROPIN = os.path.join(util.ROOT, "oracle", "_ref", "ref_dropin")
+
+
+@pytest.mark.skipif(not (util.have_ref() and os.path.exists(REF_DROPIN)), reason="oracle/_ref binaries not built (needs /root/reference)")
+def test_reference_harness_with_the_glue_resident_loop():
+    """The drop-in proof for the loop: the reference harness and the reference's own objects, linked with
+    integration/gl_gadget_glue.c (-DGL_RESIDENT_RUN).  Op M is op L with the eight iterations handed to
+    gl_glue_run_steps() - P[] / SphP[] read once, the loop in the library on the GPU, the structs written once, the host's
+    time line (All.Ti_Current, TimeBinActive[], the time-bin lists via the reference's reconstruct_timebins()) brought up
+    to date.  The all-reference binary's op L is the checker."""
+    mg = _golden_module()
+    ps = mg._kick_set()
+    par = ics.default_params(Ti_Current=16, MinEgySpec=1.8)
+    par["Timebase_interval"] = TBI
+    par["PartAllocFactor"] = 20.0
+    ref = util.run_oracle(util.REF_HARNESS, ps, par, "T S D R G D U H L")
+    got = util.run_oracle(REF_DROPIN, ps, par, "T S D R G D U H M")
+    r = {k[len("8_L_end_"):]: v for k, v in ref.items() if k.startswith("8_L_end_")}
+    g = {k[len("8_M_end_"):]: v for k, v in got.items() if k.startswith("8_M_end_")}
+    assert set(r) == set(g) and len(r) > 25
+    n = r["Pos"].shape[0]
+    assert np.array_equal(ref["8_L_loop"], got["8_M_loop"])                  # Ti_Current 80, All.Time, everybody current, 8 steps
+    for k in ("TimeBin", "Ti_begstep", "Type"):
+        assert np.array_equal(_by_id(r, k, n), _by_id(g, k, n)), k
+    for k in ("TimeBinCount", "TimeBinCountSph", "TimeBinActive"):           # the host's time line after reconstruct_timebins()
+        assert np.array_equal(r[k], g[k]), k
+    ng = r["VelPred"].shape[0]
+    gas = np.zeros(n, bool)
+    gas[r["id"][:ng] - 1] = True
+    for k, tol in (("Pos", 1e-9), ("Vel", 1e-6), ("GravAccel", 1e-5), ("Hsml", 1e-9), ("Mass", 1e-15)):
+        err = util.rel_err_vec(_by_id(g, k, n), _by_id(r, k, n))
+        assert np.percentile(err, 99) < tol and err.max() < 30 * tol, util.summarize(k, err)
+    # (here the state the loop STARTS from is the CUDA path's as well - ops G D U H of the drop-in binary - so the
+    #  velocities carry the 1e-7 of its FP32 force magnitudes into every SPH quantity that reads them)
+    for k, tol in (("VelPred", 1e-6), ("Entropy", 1e-8), ("DtEntropy", 1e-6), ("Density", 1e-8), ("Pressure", 1e-8), ("HydroAccel", 1e-6),
+                   ("MaxSignalVel", 1e-7), ("DivVel", 1e-5), ("CurlVel", 1e-5), ("DhsmlDensityFactor", 1e-8)):
+        a, b_ = _by_id(g, k, n)[gas], _by_id(r, k, n)[gas]
+        if a.ndim == 1:
+            err = np.abs(a - b_) / np.maximum(np.abs(b_), 1e-6 * np.abs(b_).max())
+        else:
+            err = util.rel_err_vec(a, b_)
+        assert np.percentile(err, 99) < tol and err.max() < 100 * tol, util.summarize(k, err)
