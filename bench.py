@@ -342,6 +342,51 @@ def resident_loop(ForcePath, par, ps, n, ksteps):
     return out
 
 
+def resident_block(ForcePath, par, ps, n, ksteps):
+    """The resident loop through the reference-facing struct call (gl_gadget_run_steps): host P[] / SphP[] (pinned) are
+    read once, ksteps iterations of run()'s loop run on the device, the structs are written once - gather, H2D, D2H and
+    scatter are inside the timed region, paid once per call instead of twice per step."""
+    import ctypes as C
+    import time
+    import numpy as np
+    import torch
+    from gadget_leicester_b200 import aos, lib as L
+    tbi = par["Timebase_interval"]
+    ps = dict(ps)
+    ps["timebin"] = np.ones(n, dtype=np.int32)
+    ps["ti_begstep"] = np.zeros(n, dtype=np.int32)
+    fp = ForcePath(dict(par, ErrTolTheta=0.0, Ti_Current=2))
+    arr = aos.GadgetArrays(ps, pinned=True)
+    drop = aos.GadgetDropIn(fp, arr)
+    drop.compute_accelerations()                          # the structs now hold a complete, settled state
+    arr.pview("p_Ti_current", np.int32)[:] = 2
+    t = fp.timestep_params(2, [1, 1] + [0] * 27, Timebase_interval=tbi, ErrTolIntAccuracy=0.025, CourantFac=0.15, MaxSizeTimestep=2 * tbi,
+                           MinSizeTimestep=0.0, MinEgySpec=0.0, SofteningTable=par["Softening"], OuterBoundary=1.4e10,
+                           UnitVelocity_in_cm_per_s=2.98e6, FeedBackVelocity=1.0, SMBHmass=0.5, InnerBoundary=2.0e-2, SinkBoundary=1.0e-4,
+                           AccDtBlackHole=0.007)
+    lib, lay = fp._lib, aos.layout_struct()
+    act = np.arange(n, dtype=np.int32)
+    err = C.create_string_buffer(512)
+    if lib.gl_gadget_advance_and_find_timesteps(C.byref(lay), C.byref(t), L._ptr(arr.P), L._ptr(arr.SphP), L._ptr(act), n, None, err, len(err)):
+        raise RuntimeError(err.value.decode())
+    info = L.GLRunInfo()
+    ng = arr.N_gas
+    fp._chk(lib.gl_gadget_run_steps(fp.ctx, L._ptr(arr.P), L._ptr(arr.SphP), n, ng, C.byref(t), 2, C.byref(info)))      # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fp._chk(lib.gl_gadget_run_steps(fp.ctx, L._ptr(arr.P), L._ptr(arr.SphP), n, ng, C.byref(t), ksteps, C.byref(info)))
+    wall = time.perf_counter() - t0
+    h2d = n * (16 * 8 + 3 * 4) + ng * 16 * 8
+    d2h = n * (14 * 8 + 4 + 2 * 4) + ng * 16 * 8
+    out = dict(value=info.interactions / wall, unit=UNIT, ms_per_step=wall * 1e3 / ksteps, ms_per_call=wall * 1e3, steps_per_call=ksteps,
+               device_ms_per_step=info.ms_total / ksteps, active_per_step=info.active_total / ksteps,
+               h2d_bytes_per_step=h2d // ksteps, d2h_bytes_per_step=d2h // ksteps, h2d_bytes_per_call=h2d, d2h_bytes_per_call=d2h,
+               api="gl_gadget_run_steps on pinned host P[]/SphP[]: structs gathered + H2D once, %d iterations of run()'s loop on the device, "
+                   "D2H + scatter once (all inside the timed region)" % ksteps)
+    fp.close()
+    return out
+
+
 def resident_loop_ranks(dfp, par, dist, world, ksteps):
     """resident_loop() at N ranks: every rank integrates its own Peano-Hilbert segment inside libgl_b200 (gl_run_steps in
     multi-rank mode: TimeBinCount all-gather, locally-essential exchange and force path, kick), max over ranks."""
@@ -815,6 +860,10 @@ def main():
             resident = resident_loop(ForcePath, par, ps2, n, max(2, min(args.steps, 10)))
         except Exception as ex:  # an extra record, never a reason to lose the bench line
             resident = dict(error=str(ex)[:300])
+        try:
+            resident["through_structs"] = resident_block(ForcePath, par, ps2, n, 10)
+        except Exception as ex:
+            resident["through_structs"] = dict(error=str(ex)[:300])
 
     # ---- strong scaling on the 2^27-particle sets (north_star: >= 70 % at 8 GPUs), part of the N > 1 line ----
     strong = None

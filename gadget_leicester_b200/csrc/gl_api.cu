@@ -52,6 +52,7 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->run_hist.release();
   c->run_list.release();
   c->run_flag.release();
+  if(c->run_pin) cudaFreeHost(c->run_pin);
   c->dma_rows.release();
   if(c->ev_blk) cudaEventDestroy(c->ev_blk);
   for(int i = 0; i < 4; i++)

@@ -219,6 +219,8 @@ struct gl_ctx
   DBuf<int> run_err, run_hist, run_list, run_flag;
   int run_ti = 0;		// the time every particle is drifted to
   bool run_ready = false;
+  void *run_pin = nullptr;	// page-locked staging of gl_gadget_run_steps
+  size_t run_pin_cap = 0;
   // ---- gadget AoS layer ----
   gl_gadget_layout lay{};
   bool have_lay = false;

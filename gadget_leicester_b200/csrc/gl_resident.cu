@@ -554,6 +554,7 @@ extern "C" int gl_get_run_state(gl_ctx *c, double *pos3, double *vel3, double *v
 // the loop runs on the device, the structs are written ONCE - where the per-step drop-in call moves them through the
 // host's memory twice per step.  Not a pipeline like gl_gadget_compute_accelerations: one pass of the host pool each way.
 #include "gl_host.h"
+#include <chrono>
 
 namespace
 {
@@ -572,15 +573,36 @@ extern "C" int gl_gadget_run_steps(gl_ctx *c, void *Pv, void *SphPv, long long N
   if(L.p_Ti_current < 0) return c->fail("gl_gadget_run_steps: the layout has no P.Ti_current");
   char *P = (char *) Pv, *S = (char *) SphPv;
   // ---- gather: everything run()'s loop carries from one step to the next ----
-  std::vector<double> f((size_t) n * 29);
-  std::vector<int> q((size_t) n * 3);
-  double *pos = f.data(), *vel = pos + 3 * n, *mass = vel + 3 * n, *hsml = mass + n, *oldacc = hsml + n, *entropy = oldacc + n,
+  // staging in page-locked memory, kept by the context: pageable vectors cost more in first-touch faults and bounce
+  // copies than the loop itself (measured: 217 ms per call for 1.6 M particles, 1.6 M x 500 B each way)
+  const size_t need = (size_t) n * (29 * sizeof(double) + 3 * sizeof(int) + sizeof(float)) + 64;
+  if(c->run_pin_cap < need)
+    {
+      if(c->run_pin) cudaFreeHost(c->run_pin);
+      c->run_pin = nullptr;
+      c->run_pin_cap = 0;
+      GL_CUDA(c, cudaMallocHost(&c->run_pin, need + need / 8));
+      c->run_pin_cap = need + need / 8;
+    }
+  double *fbase = (double *) c->run_pin;
+  int *qbase = (int *) (fbase + (size_t) n * 29);
+  float *gcbase = (float *) (qbase + (size_t) n * 3);
+  double *pos = fbase, *vel = pos + 3 * n, *mass = vel + 3 * n, *hsml = mass + n, *oldacc = hsml + n, *entropy = oldacc + n,
     *dtentropy = entropy + n, *velpred = dtentropy + n, *gacc = velpred + 3 * n, *hacc = gacc + 3 * n, *maxsig = hacc + 3 * n,
     *density = maxsig + n, *pressure = density + n, *dhsml = pressure + n, *divvel = dhsml + n, *curlvel = divvel + n,
     *numngb = curlvel + n, *gcost = numngb + n;
-  int *type = q.data(), *timebin = type + n, *tibeg = timebin + n;
+  int *type = qbase, *timebin = type + n, *tibeg = timebin + n;
   std::atomic<long long> behind{0}, badgas{0};
   const int ti = tp->Ti_Current;
+  static const bool dbg = getenv("GL_DEBUG_E2E") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tl = now();
+  auto stamp = [&](const char *what) {
+    if(!dbg) return;
+    const double t = now();
+    fprintf(stderr, "[gl run_steps] %-10s %8.2f ms\n", what, t - tl);
+    tl = t;
+  };
   HostPool::get().run(n, 8192, [&](long long, long long a, long long b) {
     long long nb = 0, bg = 0;
     for(long long i = a; i < b; i++)
@@ -627,6 +649,7 @@ extern "C" int gl_gadget_run_steps(gl_ctx *c, void *Pv, void *SphPv, long long N
     if(nb) behind.fetch_add(nb);
     if(bg) badgas.fetch_add(bg);
   });
+  stamp("gather");
   if(badgas.load()) return c->fail("gl_gadget_run_steps: the gas particles (Type 0) must be exactly P[0..N_gas)");
   if(behind.load())
     return c->fail("gl_gadget_run_steps: " + std::to_string(behind.load()) + " particles are not drifted to Ti_Current (P.Ti_current != All.Ti_Current): "
@@ -641,22 +664,25 @@ extern "C" int gl_gadget_run_steps(gl_ctx *c, void *Pv, void *SphPv, long long N
   if(gl_set_accelerations(c, gacc, ng > 0 ? hacc : nullptr, ng > 0 ? maxsig : nullptr, 0)) return 1;
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
   if(gl_run_begin(c, ti)) return 1;
+  stamp("upload");
   // ---- the loop ----
   gl_run_info I{};
   if(gl_run_steps(c, tp, nsteps, &I)) return 1;
   if(info) *info = I;
+  stamp("loop");
   // ---- scatter: the state and the results of the last force computation of every particle ----
-  std::vector<float> gc((size_t) n);
+  float *gc = gcbase;
   if(gl_get_run_state(c, pos, vel, velpred, hsml, entropy, dtentropy, timebin, tibeg, 0)) return 1;
   const long long keep_first = c->res_first, keep_count = c->res_count;
   c->res_first = 0;
   c->res_count = n;		// the own particles (the arrays may be longer in multi-rank mode)
-  int rc = gl_get_gravity(c, gacc, oldacc, gc.data(), 0);
+  int rc = gl_get_gravity(c, gacc, oldacc, gc, 0);
   if(!rc && ng > 0) rc = gl_get_density(c, nullptr, numngb, density, dhsml, divvel, curlvel, pressure, nullptr, nullptr, nullptr, 0);
   if(!rc && ng > 0) rc = gl_get_hydro(c, hacc, nullptr, maxsig, 0);
   c->res_first = keep_first;
   c->res_count = keep_count;
   if(rc) return 1;
+  stamp("download");
   (void) gcost;
   const int ti_end = tp->Ti_Current;
   const bool stepped = I.steps_done > 0;
@@ -673,7 +699,7 @@ extern "C" int gl_gadget_run_steps(gl_ctx *c, void *Pv, void *SphPv, long long N
 	  }
 	fld<double>(pi, L.p_Hsml) = hsml[i];
 	fld<double>(pi, L.p_OldAcc) = oldacc[i];
-	if(stepped) fld<float>(pi, L.p_GravCost) = gc[(size_t) i];
+	if(stepped) fld<float>(pi, L.p_GravCost) = gc[i];
 	fld<short>(pi, L.p_TimeBin) = (short) timebin[i];
 	fld<int>(pi, L.p_Ti_begstep) = tibeg[i];
 	if(ty != 3) fld<int>(pi, L.p_Ti_current) = ti_end;	// predict.c:134: virtual particles are never drifted
@@ -699,5 +725,6 @@ extern "C" int gl_gadget_run_steps(gl_ctx *c, void *Pv, void *SphPv, long long N
 	  }
       }
   });
+  stamp("scatter");
   return 0;
 }
