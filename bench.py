@@ -342,23 +342,18 @@ def resident_loop(ForcePath, par, ps, n, ksteps):
     return out
 
 
-def resident_block(ForcePath, par, ps, n, ksteps):
-    """The resident loop through the reference-facing struct call (gl_gadget_run_steps): host P[] / SphP[] (pinned) are
-    read once, ksteps iterations of run()'s loop run on the device, the structs are written once - gather, H2D, D2H and
-    scatter are inside the timed region, paid once per call instead of twice per step."""
+def _block_on(fp, arr, par, ksteps, dist=None, world=1):
+    """gl_gadget_run_steps on structs that hold a complete, settled state (all ranks together when dist is given)."""
     import ctypes as C
     import time
     import numpy as np
     import torch
     from gadget_leicester_b200 import aos, lib as L
     tbi = par["Timebase_interval"]
-    ps = dict(ps)
-    ps["timebin"] = np.ones(n, dtype=np.int32)
-    ps["ti_begstep"] = np.zeros(n, dtype=np.int32)
-    fp = ForcePath(dict(par, ErrTolTheta=0.0, Ti_Current=2))
-    arr = aos.GadgetArrays(ps, pinned=True)
-    drop = aos.GadgetDropIn(fp, arr)
-    drop.compute_accelerations()                          # the structs now hold a complete, settled state
+    n, ng = arr.NumPart, arr.N_gas
+    fp.set_params(Ti_Current=2)
+    arr.pview("p_TimeBin", np.int16)[:] = 1
+    arr.pview("p_Ti_begstep", np.int32)[:] = 0
     arr.pview("p_Ti_current", np.int32)[:] = 2
     t = fp.timestep_params(2, [1, 1] + [0] * 27, Timebase_interval=tbi, ErrTolIntAccuracy=0.025, CourantFac=0.15, MaxSizeTimestep=2 * tbi,
                            MinSizeTimestep=0.0, MinEgySpec=0.0, SofteningTable=par["Softening"], OuterBoundary=1.4e10,
@@ -370,19 +365,44 @@ def resident_block(ForcePath, par, ps, n, ksteps):
     if lib.gl_gadget_advance_and_find_timesteps(C.byref(lay), C.byref(t), L._ptr(arr.P), L._ptr(arr.SphP), L._ptr(act), n, None, err, len(err)):
         raise RuntimeError(err.value.decode())
     info = L.GLRunInfo()
-    ng = arr.N_gas
     fp._chk(lib.gl_gadget_run_steps(fp.ctx, L._ptr(arr.P), L._ptr(arr.SphP), n, ng, C.byref(t), 2, C.byref(info)))      # warm-up
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     fp._chk(lib.gl_gadget_run_steps(fp.ctx, L._ptr(arr.P), L._ptr(arr.SphP), n, ng, C.byref(t), ksteps, C.byref(info)))
     wall = time.perf_counter() - t0
     h2d = n * (16 * 8 + 3 * 4) + ng * 16 * 8
     d2h = n * (14 * 8 + 4 + 2 * 4) + ng * 16 * 8
-    out = dict(value=info.interactions / wall, unit=UNIT, ms_per_step=wall * 1e3 / ksteps, ms_per_call=wall * 1e3, steps_per_call=ksteps,
-               device_ms_per_step=info.ms_total / ksteps, active_per_step=info.active_total / ksteps,
-               h2d_bytes_per_step=h2d // ksteps, d2h_bytes_per_step=d2h // ksteps, h2d_bytes_per_call=h2d, d2h_bytes_per_call=d2h,
-               api="gl_gadget_run_steps on pinned host P[]/SphP[]: structs gathered + H2D once, %d iterations of run()'s loop on the device, "
-                   "D2H + scatter once (all inside the timed region)" % ksteps)
+    inter, active = float(info.interactions), float(info.active_total)
+    if dist is not None:
+        tt = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        ii = torch.tensor([inter, active, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ii, op=dist.ReduceOp.SUM)
+        wall, (inter, active, h2d, d2h) = float(tt.item()), [float(x) for x in ii.tolist()]
+    return dict(value=inter / wall, unit=UNIT, ms_per_step=wall * 1e3 / ksteps, ms_per_call=wall * 1e3, steps_per_call=ksteps,
+                device_ms_per_step=info.ms_total / ksteps, active_per_step=active / ksteps,
+                h2d_bytes_per_step=int(h2d) // ksteps, d2h_bytes_per_step=int(d2h) // ksteps, h2d_bytes_per_call=int(h2d), d2h_bytes_per_call=int(d2h),
+                api="gl_gadget_run_steps on %s pinned host P[]/SphP[]: structs gathered + H2D once, %d iterations of run()'s loop on the "
+                    "device, D2H + scatter once (all inside the timed region%s)"
+                    % ("every rank's own" if world > 1 else "the", ksteps, "; max over ranks" if world > 1 else ""))
+
+
+def resident_block(ForcePath, par, ps, n, ksteps):
+    """The resident loop through the reference-facing struct call (gl_gadget_run_steps): host P[] / SphP[] (pinned) are
+    read once, ksteps iterations of run()'s loop run on the device, the structs are written once - gather, H2D, D2H and
+    scatter are inside the timed region, paid once per call instead of twice per step."""
+    import numpy as np
+    from gadget_leicester_b200 import aos
+    ps = dict(ps)
+    ps["timebin"] = np.ones(n, dtype=np.int32)
+    ps["ti_begstep"] = np.zeros(n, dtype=np.int32)
+    fp = ForcePath(dict(par, ErrTolTheta=0.0, Ti_Current=2))
+    arr = aos.GadgetArrays(ps, pinned=True)
+    drop = aos.GadgetDropIn(fp, arr)
+    drop.compute_accelerations()                          # the structs now hold a complete, settled state
+    out = _block_on(fp, arr, par, ksteps)
     fp.close()
     return out
 
@@ -792,6 +812,11 @@ def main():
                    ms_per_step=float(tt.item()) * 1e3, steps=ksteps,
                    api="gl_gadget_compute_accelerations on every rank's own pinned host P[]/SphP[] segment (pack + H2D, "
                        "locally-essential exchange over NCCL, force path, D2H + scatter); max over ranks")
+        if resident is not None and "error" not in resident:
+            try:
+                resident["through_structs"] = _block_on(dfp.fp, arr, par, 10, dist=dist, world=world)
+            except Exception as ex:  # collective: a failure here is a failure on every rank
+                resident["through_structs"] = dict(error=str(ex)[:300])
     if not args.no_e2e and world > 1 and not use_let:
         # every rank owns the host P[]/SphP[] of its Peano-Hilbert segment, like every MPI rank of the reference
         from gadget_leicester_b200.multigpu import DistributedDropIn
