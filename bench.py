@@ -434,16 +434,25 @@ def resident_loop_ranks(dfp, par, dist, world, ksteps):
     fp.run(t, 3)
     torch.cuda.synchronize()
     dist.barrier()
+    ls0 = fp.let_stats()
     t0 = time.perf_counter()
     info = fp.run(t, ksteps)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / ksteps
+    ls1 = fp.let_stats()
+    st1 = fp.stats()
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     ii = torch.tensor([float(info["interactions"]) / ksteps, float(info["active_total"]) / ksteps], dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dist.all_reduce(ii, op=dist.ReduceOp.SUM)
     return dict(value=float(ii[0].item()) / float(tt.item()), unit=UNIT, ms_per_step=float(tt.item()) * 1e3, steps=ksteps,
-                active_per_step=float(ii[1].item()), Ti_Current=int(t.Ti_Current), h2d_bytes_per_step=0,
+                active_per_step=float(ii[1].item()), Ti_Current=int(t.Ti_Current),
+                rank0=dict(let_builds=ls1["builds"] - ls0["builds"], let_violations=ls1["violations"] - ls0["violations"],
+                           imported_particles=ls1["imported_particles"], ms_own_tree=ls1["ms_own_tree"], ms_select=ls1["ms_select"],
+                           ms_exchange=ls1["ms_exchange"], ms_sph_exchange=ls1["ms_sph_exchange"],
+                           phase_ms={k: round(st1[k], 3) for k in ("ms_keys_sort", "ms_treebuild", "ms_moments", "ms_gravity_walk", "ms_density",
+                                                                   "ms_hmax", "ms_hydro")}),
+                h2d_bytes_per_step=0,
                 d2h_bytes_per_step=world * (128 * world + 3 * 24 + 8 + 8 + 8 * world),
                 api="gl_run_steps in multi-rank mode: every rank's own Peano-Hilbert segment stays in HBM; per step the "
                     "TimeBinCount[] all-gather, drift, locally-essential exchange over NCCL + force path, kick; max over ranks (wall clock)")

@@ -52,6 +52,8 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->run_hist.release();
   c->run_list.release();
   c->run_flag.release();
+  c->hull_u64.release();
+  c->hull_i32.release();
   if(c->run_pin) cudaFreeHost(c->run_pin);
   c->dma_rows.release();
   if(c->ev_blk) cudaEventDestroy(c->ev_blk);
@@ -101,6 +103,7 @@ extern "C" int gl_set_params(gl_ctx *c, const gl_params *p)
 // installed by itself goes with the old set
 void gl_fresh_particle_set(gl_ctx *c)
 {
+  c->let_gap_hulls = false;	// a new set comes in the caller's order again
   c->n_own = c->n;
   c->ncell = 0;
   c->nit = c->n;

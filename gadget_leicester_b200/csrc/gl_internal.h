@@ -217,6 +217,9 @@ struct gl_ctx
   long long sg_pairs_seen = 0;	// (grain, gas) pairs of the last gl_dust_drag: sizes the next call's list
   // ---- device-resident integration loop (gl_resident.cu) ----
   DBuf<int> run_err, run_hist, run_list, run_flag;
+  DBuf<unsigned long long> hull_u64;	// multi-rank resident loop: order-independent key hulls (glk_ph_gap_hulls)
+  DBuf<int> hull_i32;
+  bool let_gap_hulls = false;
   int run_ti = 0;		// the time every particle is drifted to
   bool run_ready = false;
   void *run_pin = nullptr;	// page-locked staging of gl_gadget_run_steps
@@ -282,6 +285,8 @@ int glk_local_minmax(gl_ctx *c, double *dev6);	// min[3], max[3] of the loaded p
 void glk_set_domain_minmax(gl_ctx *c, const double lo[3], const double hi[3]);
 // Peano-Hilbert key hull {min, max} of each of nchunks stretches [bounds[b], bounds[b+1]) of the own particles (input order)
 int glk_ph_chunk_hulls(gl_ctx *c, const long long *bounds_dev, int nchunks, unsigned long long *out);
+// the same cover from the SORTED own keys, cut at the largest gaps: independent of the caller's order (resident loop)
+int glk_ph_gap_hulls(gl_ctx *c, int nchunks, unsigned long long *out);
 // per node of the current tree: 1 if no other rank has a particle inside the cell (its Peano-Hilbert key range
 // misses every key hull of every other rank); rank r's nhull hulls start at ranges + r * stride (device)
 int glk_node_complete(gl_ctx *c, const unsigned long long *ranges, int world, int nhull, long long stride, int me, unsigned char *complete);

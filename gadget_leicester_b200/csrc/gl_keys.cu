@@ -582,6 +582,101 @@ int glk_ph_chunk_hulls(gl_ctx *c, const long long *bounds_dev, int nchunks, unsi
   return 0;
 }
 
+// ---- key hulls that do not depend on the caller's order -----------------------------------------------------------
+// The stretch hulls above are tight while the caller's particles are in Peano-Hilbert order of the CURRENT grid.  When a
+// rank keeps its particles over several steps (the resident loop, gl_resident.cu), the cube moves with the outermost
+// particles, the grid shifts, and a few particles of every stretch land across a high-level cell boundary: their keys
+// jump far away and the [min, max] hull of the stretch covers half the curve - nothing is missed (the hulls only have to
+// COVER the rank's keys), but cells stop being "complete" and are exported particle by particle (measured: +18 ... +330 %
+// imports).  Here the own keys are sorted and cut at the nchunks - 1 LARGEST GAPS: the smallest cover by nchunks
+// intervals whatever the order of the particles - a stray particle becomes an interval of its own.
+__global__ void k_ph_keys_of(long long n, const unsigned long long *__restrict__ mkey_in, unsigned long long *__restrict__ ph)
+{
+  __shared__ unsigned char s_sub[192], s_next[192];
+  for(int t = threadIdx.x; t < 192; t += blockDim.x)
+    {
+      s_sub[t] = c_hsub[t];
+      s_next[t] = c_hnext[t];
+    }
+  __syncthreads();
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i < n) ph[i] = ph_from_morton_dev(mkey_in[i], s_sub, s_next);
+}
+
+__global__ void k_key_gaps(long long n, const unsigned long long *__restrict__ sorted, unsigned long long *__restrict__ gap, int *__restrict__ idx)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n - 1) return;
+  gap[i] = sorted[i + 1] - sorted[i];
+  idx[i] = (int) i;
+}
+
+// one block: cut[] = the positions of the ncut largest gaps (any order) -> ncut + 1 intervals of the sorted keys
+__global__ void k_gap_hulls(long long n, int ncut, int nchunks, const unsigned long long *__restrict__ sorted, const int *__restrict__ cut,
+			    unsigned long long *__restrict__ out)
+{
+  __shared__ int s_cut[256];
+  const int t = threadIdx.x;
+  if(t < ncut)
+    {
+      // rank of my cut among all cuts (ncut <= 255: a quadratic count is nothing)
+      const int mine = cut[t];
+      int r = 0;
+      for(int k = 0; k < ncut; k++)
+	{
+	  const int o = cut[k];
+	  r += (o < mine || (o == mine && k < t)) ? 1 : 0;
+	}
+      s_cut[r] = mine;
+    }
+  __syncthreads();
+  if(t < nchunks)
+    {
+      if(t <= ncut)
+	{
+	  const long long a = t == 0 ? 0 : (long long) s_cut[t - 1] + 1, b = t == ncut ? n - 1 : (long long) s_cut[t];
+	  out[2 * t] = sorted[a];
+	  out[2 * t + 1] = sorted[b];
+	}
+      else
+	{
+	  out[2 * t] = ~0ull;	// unused hull: lo > hi
+	  out[2 * t + 1] = 0;
+	}
+    }
+}
+
+int glk_ph_gap_hulls(gl_ctx *c, int nchunks, unsigned long long *out)
+{
+  const long long n = c->n_own;
+  if(nchunks > 256 || n <= 0) return c->fail("key hulls: bad arguments");
+  if(upload_tables(c)) return 1;
+  GL_CUDA(c, c->hull_u64.ensure(3 * (size_t) n + 4));
+  GL_CUDA(c, c->hull_i32.ensure(2 * (size_t) n + 4));
+  unsigned long long *ph = c->hull_u64.p, *sorted = ph + n, *gap = sorted + n;
+  int *idx = c->hull_i32.p, *idx_sorted = idx + n;
+  k_ph_keys_of<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->key_m.p, ph);
+  GL_LAUNCH_COUNT(c);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp, ph, sorted, (int) n, 0, 63, c->stream);
+  GL_CUDA(c, c->cub_tmp.ensure(tmp));
+  GL_CUDA(c, cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp, ph, sorted, (int) n, 0, 63, c->stream));
+  int ncut = (int) std::min<long long>(nchunks - 1, n - 1);
+  if(ncut > 0)
+    {
+      k_key_gaps<<<gl_grid(n - 1, 256), 256, 0, c->stream>>>(n, sorted, gap, idx);
+      GL_LAUNCH_COUNT(c);
+      // (ph is free again: the sorted gaps go there)
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, gap, ph, idx, idx_sorted, (int) (n - 1), 0, 64, c->stream);
+      GL_CUDA(c, c->cub_tmp.ensure(tmp));
+      GL_CUDA(c, cub::DeviceRadixSort::SortPairsDescending(c->cub_tmp.p, tmp, gap, ph, idx, idx_sorted, (int) (n - 1), 0, 64, c->stream));
+    }
+  c->kernel_launches += 10;
+  k_gap_hulls<<<1, 256, 0, c->stream>>>(n, ncut, nchunks, sorted, idx_sorted, out);
+  GL_LAUNCH_COUNT(c);
+  return 0;
+}
+
 // A cell of level L is a contiguous stretch of the Peano-Hilbert curve: all keys that share its leading 3 L bits.
 __global__ void k_node_complete(long long m, const int *__restrict__ n_first, const signed char *__restrict__ n_level,
 				const unsigned long long *__restrict__ mkey, const unsigned long long *__restrict__ ranges, int world,

@@ -562,7 +562,11 @@ int gll_distributed_build(gl_ctx *c)
     for(int b = 1; b <= nb_rest; b++) hbnd[nb_gas + b] = ngas + (long long) b * nrest / nb_rest;
     hbnd[GL_LET_BOXES] = n;
     GL_CUDA(c, cudaMemcpyAsync(bdev, hbnd, sizeof(hbnd), cudaMemcpyHostToDevice, c->stream));
-    if(glk_ph_chunk_hulls(c, bdev, GL_LET_BOXES, (unsigned long long *) L->box_own.p)) return 1;
+    // key hulls: per stretch of the caller's order (tight while that order is the Peano-Hilbert order of this step's grid),
+    // or from the sorted keys when the rank has kept its particles over several steps (gl_run_steps)
+    if(c->let_gap_hulls ? glk_ph_gap_hulls(c, GL_LET_BOXES, (unsigned long long *) L->box_own.p)
+       : glk_ph_chunk_hulls(c, bdev, GL_LET_BOXES, (unsigned long long *) L->box_own.p))
+      return 1;
     k_let_boxes<<<GL_LET_LEAVES, 128, 0, c->stream>>>(n, bdev, c->in_pos.p, c->in_oldacc.p, c->in_hsml.p, c->in_type.p,
 						       c->par.ErrTolForceAcc, L->fs, L->box_own.p);
     k_let_box_union<<<GL_LET_BOXES, 32, 0, c->stream>>>(L->box_own.p, 0);

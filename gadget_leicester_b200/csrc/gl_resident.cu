@@ -477,6 +477,7 @@ extern "C" int gl_run_steps(gl_ctx *c, gl_timestep_params *tp, int nsteps, gl_ru
       // ---- domain_Decomposition: new extent, new tree (TreeReconstructFlag, domain.c:135).  The ranks keep the
       // particles they have: any assignment gives the same results, a stale one only prunes less ----
       c->par.Ti_Current = ti_next_kick;
+      if(W > 1 && !getenv("GL_NO_GAP_HULLS")) c->let_gap_hulls = true;	// the caller's order is no longer this grid's Peano-Hilbert order
       gl_set_tree_reconstruct_flag(c, 1);	// (multi-rank mode: the imports of the last tree are dropped, the next build fetches them again)
       c->tree_valid = false;
       c->tgt_dirty = true;
