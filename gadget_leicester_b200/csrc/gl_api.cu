@@ -54,6 +54,7 @@ extern "C" void gl_destroy(gl_ctx *c)
   c->run_flag.release();
   c->hull_u64.release();
   c->hull_i32.release();
+  c->run_id.release();
   if(c->run_pin) cudaFreeHost(c->run_pin);
   c->dma_rows.release();
   if(c->ev_blk) cudaEventDestroy(c->ev_blk);
@@ -163,6 +164,7 @@ extern "C" int gl_load_particles(gl_ctx *c, long long n, const double *pos, cons
   c->tgt_dirty = true;
   c->have_velpred = false;
   c->run_ready = false;
+  c->run_have_id = false;
   if(!c->domain_imposed) c->have_domain = false;
   return 0;
 }
@@ -305,6 +307,7 @@ extern "C" int gl_load_particles_gathered(gl_ctx *c, long long n, int world, lon
   c->tgt_dirty = true;
   c->have_velpred = false;
   c->run_ready = false;
+  c->run_have_id = false;
   if(!c->domain_imposed) c->have_domain = false;
   return 0;
 }

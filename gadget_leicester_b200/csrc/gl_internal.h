@@ -220,6 +220,8 @@ struct gl_ctx
   DBuf<unsigned long long> hull_u64;	// multi-rank resident loop: order-independent key hulls (glk_ph_gap_hulls)
   DBuf<int> hull_i32;
   bool let_gap_hulls = false;
+  DBuf<int> run_id;		// particle ids travelling with gl_domain_exchange
+  bool run_have_id = false;
   int run_ti = 0;		// the time every particle is drifted to
   bool run_ready = false;
   void *run_pin = nullptr;	// page-locked staging of gl_gadget_run_steps

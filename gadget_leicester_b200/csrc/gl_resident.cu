@@ -729,3 +729,271 @@ extern "C" int gl_gadget_run_steps(gl_ctx *c, void *Pv, void *SphPv, long long N
   stamp("scatter");
   return 0;
 }
+
+// ---------------------------------------------------------------- domain_exchange for the resident state ----
+// domain_Decomposition() ends with domain_exchange (domain.c:665): every particle struct travels to the rank its key now
+// belongs to.  With the state resident in the library the same move happens between the GPUs: the new owners come from
+// gl_domain_split_collective (equal-cost stretches of the global Peano-Hilbert order, domain.c:1075 / :378), every
+// particle's state is packed into one 256-byte record, the records cross NVLink in ONE all-to-all, and the receiver
+// stores them in Peano-Hilbert order of the current grid (so a warp's 32 targets are neighbours again and the stretch
+// key hulls are tight).  Results do not depend on who owns what: this only restores the balance and the
+// pruning of the locally-essential exchange after the particles have moved.
+namespace
+{
+#define XR 32			// doubles per record
+// [0..2] pos [3..5] vel [6..8] velpred [9..11] gravaccel [12..14] hydroaccel [15] mass [16] hsml [17] oldacc [18] entropy
+// [19] dtentropy [20] maxsignalvel [21] density [22] pressure [23] dhsml [24] divvel [25] curlvel [26] gravcost [27] numngb
+// [28] key (bits) [29] type | timebin [30] ti_begstep | id [31] -
+struct XArrays
+{
+  double *pos, *vel, *velpred, *acc, *hacc, *mass, *hsml, *oldacc, *entropy, *dtentropy, *maxsig, *density, *pressure, *dhsml, *divvel,
+    *curlvel, *numngb;
+  float *gravcost;
+  int *type, *timebin, *tibeg, *id;
+};
+
+__global__ void k_x_cost(long long n, const float *__restrict__ gravcost, const int *__restrict__ timebin, double *__restrict__ cost)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const int tb = timebin[i];
+  cost[i] = (1.0 + (double) gravcost[i]) / (double) (1ll << (tb > 0 && tb < 40 ? tb : 0));	// domain.c:378-384
+}
+
+__global__ void k_x_pack(long long n, const int *__restrict__ order, const unsigned long long *__restrict__ key, XArrays A, int sph,
+			 double *__restrict__ rec)
+{
+  const long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(k >= n) return;
+  const long long i = order[k];
+  double *r = rec + XR * k;
+  for(int j = 0; j < 3; j++)
+    {
+      r[j] = A.pos[3 * i + j];
+      r[3 + j] = A.vel[3 * i + j];
+      r[6 + j] = A.velpred[3 * i + j];
+      r[9 + j] = A.acc[3 * i + j];
+      r[12 + j] = sph ? A.hacc[3 * i + j] : 0.0;
+    }
+  r[15] = A.mass[i]; r[16] = A.hsml[i]; r[17] = A.oldacc[i]; r[18] = A.entropy[i]; r[19] = A.dtentropy[i];
+  r[20] = sph ? A.maxsig[i] : 0.0; r[21] = sph ? A.density[i] : 0.0; r[22] = sph ? A.pressure[i] : 0.0; r[23] = sph ? A.dhsml[i] : 0.0;
+  r[24] = sph ? A.divvel[i] : 0.0; r[25] = sph ? A.curlvel[i] : 0.0;
+  r[26] = (double) A.gravcost[i];
+  r[27] = sph ? A.numngb[i] : 0.0;
+  r[28] = __longlong_as_double((long long) key[i]);
+  r[29] = __hiloint2double(A.type[i], A.timebin[i]);
+  r[30] = __hiloint2double(A.tibeg[i], A.id[i]);
+  r[31] = 0;
+}
+
+__global__ void k_x_keys(long long n, const double *__restrict__ rec, unsigned long long *__restrict__ key, int *__restrict__ idx)
+{
+  const long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(k >= n) return;
+  key[k] = (unsigned long long) __double_as_longlong(rec[XR * k + 28]);
+  idx[k] = (int) k;
+}
+
+__global__ void k_x_unpack(long long n, const int *__restrict__ order, const double *__restrict__ rec, XArrays A, int sph)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const double *r = rec + XR * (long long) order[i];
+  for(int j = 0; j < 3; j++)
+    {
+      A.pos[3 * i + j] = r[j];
+      A.vel[3 * i + j] = r[3 + j];
+      A.velpred[3 * i + j] = r[6 + j];
+      A.acc[3 * i + j] = r[9 + j];
+      if(sph) A.hacc[3 * i + j] = r[12 + j];
+    }
+  A.mass[i] = r[15]; A.hsml[i] = r[16]; A.oldacc[i] = r[17]; A.entropy[i] = r[18]; A.dtentropy[i] = r[19];
+  if(sph)
+    {
+      A.maxsig[i] = r[20]; A.density[i] = r[21]; A.pressure[i] = r[22]; A.dhsml[i] = r[23]; A.divvel[i] = r[24]; A.curlvel[i] = r[25];
+      A.numngb[i] = r[27];
+    }
+  A.gravcost[i] = (float) r[26];
+  A.type[i] = __double2hiint(r[29]); A.timebin[i] = __double2loint(r[29]);
+  A.tibeg[i] = __double2hiint(r[30]); A.id[i] = __double2loint(r[30]);
+}
+
+__global__ void k_x_default_ids(long long n, int base, int *__restrict__ id)
+{
+  const long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(i < n) id[i] = base + (int) i;
+}
+
+XArrays x_arrays(gl_ctx *c)
+{
+  return XArrays{ c->in_pos.p, c->in_vel.p, c->in_velpred.p, c->o_acc.p, c->o_hacc.p, c->in_mass.p, c->in_hsml.p, c->in_oldacc.p, c->in_entropy.p,
+		  c->in_dtentropy.p, c->o_maxsig.p, c->o_density.p, c->o_pressure.p, c->o_dhsml.p, c->o_divvel.p, c->o_curlvel.p, c->o_numngb.p,
+		  c->o_gravcost.p, c->in_type.p, c->in_timebin.p, c->in_tibegstep.p, c->run_id.p };
+}
+}				// namespace
+
+extern "C" int gl_run_set_ids(gl_ctx *c, const int *ids, int where)
+{
+  cudaSetDevice(c->device);
+  const long long n = c->n_own;
+  if(c->n <= 0 || n <= 0 || !ids) return c->fail("gl_run_set_ids: no particles / no ids");
+  GL_CUDA(c, c->run_id.ensure((size_t) n));
+  GL_CUDA(c, cudaMemcpyAsync(c->run_id.p, ids, n * sizeof(int), where ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->run_have_id = true;
+  return 0;
+}
+
+extern "C" int gl_get_run_ids(gl_ctx *c, int *ids, int where)
+{
+  cudaSetDevice(c->device);
+  if(!c->run_have_id) return c->fail("gl_get_run_ids: no ids in the context (gl_run_set_ids, or a gl_domain_exchange that numbered the particles)");
+  GL_CUDA(c, cudaMemcpyAsync(ids, c->run_id.p, c->n_own * sizeof(int), where ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gl_domain_exchange(gl_ctx *c, int by_cost, long long *n_new, long long *n_sent)
+{
+  cudaSetDevice(c->device);
+  if(!c->run_ready) return c->fail("gl_domain_exchange: the resident state is not set up (gl_run_begin)");
+  gl_comm *cm = c->comm;
+  if(!cm || cm->world < 2)
+    {
+      if(n_new) *n_new = c->n_own;
+      if(n_sent) *n_sent = 0;
+      return 0;
+    }
+  const int W = cm->world, me = cm->rank;
+  const long long n = c->n_own;
+  const bool sph = c->o_density.cap >= (size_t) n && c->o_hacc.cap >= 3 * (size_t) n;
+  if(c->o_gravcost.cap < (size_t) n)
+    {
+      GL_CUDA(c, c->o_gravcost.ensure((size_t) n));
+      GL_CUDA(c, cudaMemsetAsync(c->o_gravcost.p, 0, n * sizeof(float), c->stream));
+    }
+  if(sph) GL_CUDA(c, c->o_numngb.ensure_keep((size_t) n));
+  // ---- ids: whoever holds a particle afterwards can say which one it is ----
+  if(!c->run_have_id)
+    {
+      long long *cnt = (long long *) c->run_hist.p;	// 32 (W + 1) ints: room for W + 1 long longs
+      GL_CUDA(c, cudaMemcpyAsync(cnt, &n, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+      if(cm->allgather(cnt, cnt + 1, sizeof(long long), c->stream)) return c->fail("gl_domain_exchange: all-gather failed: " + cm->err);
+      std::vector<long long> hn((size_t) W);
+      GL_CUDA(c, cudaMemcpyAsync(hn.data(), cnt + 1, W * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+      GL_CUDA(c, cudaStreamSynchronize(c->stream));
+      long long base = 0;
+      for(int r = 0; r < me; r++) base += hn[(size_t) r];
+      GL_CUDA(c, c->run_id.ensure((size_t) n));
+      k_x_default_ids<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, (int) base, c->run_id.p);
+      GL_LAUNCH_COUNT(c);
+      c->run_have_id = true;
+    }
+  // ---- who goes where: equal-cost stretches of the global Peano-Hilbert order ----
+  DBuf<double> cost, rec, rec2;
+  DBuf<int> dest, idx, order;
+  DBuf<unsigned long long> ksorted, cntdev;
+  struct Release
+  {
+    std::function<void()> f;
+    ~Release() { f(); }
+  } rel{ [&] { cost.release(); rec.release(); rec2.release(); dest.release(); idx.release(); order.release(); ksorted.release(); cntdev.release(); } };
+  GL_CUDA(c, dest.ensure((size_t) n));
+  if(by_cost)
+    {
+      GL_CUDA(c, cost.ensure((size_t) n));
+      k_x_cost<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->o_gravcost.p, c->in_timebin.p, cost.p);
+      GL_LAUNCH_COUNT(c);
+    }
+  std::vector<long long> to_go((size_t) W);
+  if(gl_domain_split_collective(c, by_cost ? cost.p : nullptr, 1, dest.p, 1, to_go.data(), nullptr)) return 1;
+  // the owner is a monotone function of the key: sorted by key, the particles of every destination are one stretch
+  GL_CUDA(c, idx.ensure((size_t) n)); GL_CUDA(c, order.ensure((size_t) n)); GL_CUDA(c, ksorted.ensure((size_t) n));
+  GL_CUDA(c, rec.ensure((size_t) n * XR));
+  {
+    // iota
+    k_x_default_ids<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, 0, idx.p);
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->key_ph.p, ksorted.p, idx.p, order.p, (int) n, 0, 63, c->stream);
+    GL_CUDA(c, c->cub_tmp.ensure(tmp));
+    GL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->key_ph.p, ksorted.p, idx.p, order.p, (int) n, 0, 63, c->stream));
+    c->kernel_launches += 6;
+  }
+  k_x_pack<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, order.p, c->key_ph.p, x_arrays(c), sph ? 1 : 0, rec.p);
+  GL_LAUNCH_COUNT(c);
+  // ---- counts: my row of toGo, everybody's rows all-gathered (domain.c:1274 + the MPI_Allgather of :700) ----
+  long long sent = 0;
+  for(int r = 0; r < W; r++) sent += to_go[(size_t) r];
+  to_go[(size_t) me] = n - sent;
+  GL_CUDA(c, cntdev.ensure((size_t) W * (W + 1)));
+  GL_CUDA(c, cudaMemcpyAsync(cntdev.p, to_go.data(), W * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  if(cm->allgather(cntdev.p, cntdev.p + W, W * sizeof(long long), c->stream)) return c->fail("gl_domain_exchange: all-gather failed: " + cm->err);
+  std::vector<long long> all((size_t) W * W);
+  GL_CUDA(c, cudaMemcpyAsync(all.data(), cntdev.p + W, (size_t) W * W * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<size_t> soff((size_t) W), scnt((size_t) W), roff((size_t) W), rcnt((size_t) W);
+  long long nn = 0;
+  size_t so = 0;
+  for(int r = 0; r < W; r++)
+    {
+      scnt[(size_t) r] = (size_t) to_go[(size_t) r] * XR * sizeof(double);
+      soff[(size_t) r] = so;
+      so += scnt[(size_t) r];
+      const long long from_r = all[(size_t) r * W + me];
+      rcnt[(size_t) r] = (size_t) from_r * XR * sizeof(double);
+      roff[(size_t) r] = (size_t) nn * XR * sizeof(double);
+      nn += from_r;
+    }
+  if(nn <= 0) return c->fail("gl_domain_exchange: this rank would be left without particles");
+  if(nn >= (1ll << 27)) return c->fail("gl_domain_exchange: more than 2^27 particles on one rank");
+  GL_CUDA(c, rec2.ensure((size_t) nn * XR));
+  if(cm->alltoallv(rec.p, soff.data(), scnt.data(), rec2.p, roff.data(), rcnt.data(), c->stream))
+    return c->fail("gl_domain_exchange: all-to-all failed: " + cm->err);
+  // ---- store in Peano-Hilbert order of the current grid ----
+  GL_CUDA(c, idx.ensure((size_t) nn)); GL_CUDA(c, order.ensure((size_t) nn)); GL_CUDA(c, ksorted.ensure((size_t) nn));
+  GL_CUDA(c, c->key_ph.ensure((size_t) nn));
+  k_x_keys<<<gl_grid(nn, 256), 256, 0, c->stream>>>(nn, rec2.p, c->key_ph.p, idx.p);
+  GL_LAUNCH_COUNT(c);
+  {
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->key_ph.p, ksorted.p, idx.p, order.p, (int) nn, 0, 63, c->stream);
+    GL_CUDA(c, c->cub_tmp.ensure(tmp));
+    GL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->key_ph.p, ksorted.p, idx.p, order.p, (int) nn, 0, 63, c->stream));
+    c->kernel_launches += 6;
+  }
+  const size_t N = (size_t) nn;
+  GL_CUDA(c, c->in_pos.ensure(3 * N)); GL_CUDA(c, c->in_vel.ensure(3 * N)); GL_CUDA(c, c->in_velpred.ensure(3 * N));
+  GL_CUDA(c, c->o_acc.ensure(3 * N)); GL_CUDA(c, c->in_mass.ensure(N)); GL_CUDA(c, c->in_hsml.ensure(N)); GL_CUDA(c, c->in_oldacc.ensure(N));
+  GL_CUDA(c, c->in_entropy.ensure(N)); GL_CUDA(c, c->in_dtentropy.ensure(N)); GL_CUDA(c, c->o_gravcost.ensure(N));
+  GL_CUDA(c, c->in_type.ensure(N)); GL_CUDA(c, c->in_timebin.ensure(N)); GL_CUDA(c, c->in_tibegstep.ensure(N)); GL_CUDA(c, c->run_id.ensure(N));
+  GL_CUDA(c, c->o_oldacc.ensure(N));
+  if(sph)
+    {
+      GL_CUDA(c, c->o_hacc.ensure(3 * N)); GL_CUDA(c, c->o_maxsig.ensure(N)); GL_CUDA(c, c->o_density.ensure(N)); GL_CUDA(c, c->o_pressure.ensure(N));
+      GL_CUDA(c, c->o_dhsml.ensure(N)); GL_CUDA(c, c->o_divvel.ensure(N)); GL_CUDA(c, c->o_curlvel.ensure(N)); GL_CUDA(c, c->o_numngb.ensure(N));
+      GL_CUDA(c, c->o_dtentr.ensure(N));
+      GL_CUDA(c, c->o_denspairs.ensure(N));
+      GL_CUDA(c, cudaMemsetAsync(c->o_denspairs.p, 0, c->o_denspairs.cap * sizeof(int), c->stream));	// no history for the new set
+    }
+  k_x_unpack<<<gl_grid(nn, 256), 256, 0, c->stream>>>(nn, order.p, rec2.p, x_arrays(c), sph ? 1 : 0);
+  GL_LAUNCH_COUNT(c);
+  GL_CUDA(c, cudaMemcpyAsync(c->o_oldacc.p, c->in_oldacc.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  GL_CUDA(c, cudaGetLastError());
+  // ---- a new particle set on this rank ----
+  c->n = nn;
+  gl_fresh_particle_set(c);
+  c->n_velpred = nn;
+  c->have_velpred = true;
+  c->n_tgt_in = -1;
+  c->tgt_ordered = false;
+  c->tgt_dirty = true;
+  c->res_first = 0;
+  c->res_count = -1;
+  c->tree_valid = false;
+  c->tree_flag = true;
+  if(!c->domain_imposed) c->have_domain = false;
+  if(n_new) *n_new = nn;
+  if(n_sent) *n_sent = sent;
+  return 0;
+}

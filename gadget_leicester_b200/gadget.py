@@ -330,6 +330,23 @@ class ForcePath:
         self._relative_criterion_engaged()
         return {k: getattr(info, k) for k, _ in L.GLRunInfo._fields_}
 
+    def run_set_ids(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        assert a.size == self.N
+        self._chk(self._lib.gl_run_set_ids(self._ctx, L._ptr(a), 0))
+
+    def run_ids(self):
+        a = np.zeros(self.N, dtype=np.int32)
+        self._chk(self._lib.gl_get_run_ids(self._ctx, L._ptr(a), 0))
+        return a
+
+    def domain_exchange(self, by_cost=True):
+        """domain_exchange (domain.c:665) of the resident state; collective.  Returns (particles held now, particles sent)."""
+        nn, ns = C.c_longlong(0), C.c_longlong(0)
+        self._chk(self._lib.gl_domain_exchange(self._ctx, 1 if by_cost else 0, C.byref(nn), C.byref(ns)))
+        self.N = int(nn.value)
+        return int(nn.value), int(ns.value)
+
     def run_state(self):
         """P[]-indexed state of the resident loop (VelPred: a row per particle, meaningful for gas)."""
         n = self.N

@@ -369,6 +369,16 @@ int gl_run_steps(gl_ctx * ctx, gl_timestep_params * par, int nsteps, gl_run_info
  * densities and the other results come from gl_get_gravity / gl_get_density / gl_get_hydro as usual */
 int gl_get_run_state(gl_ctx * ctx, double *pos3, double *vel3, double *velpred3, double *hsml, double *entropy, double *dtentropy,
 		     int *timebin, int *ti_begstep, int where);
+/* domain_exchange (domain.c:665) for the resident state, collective: the new owners come from
+ * gl_domain_split_collective (by_cost != 0: the reference's cost (1 + GravCost) / 2^TimeBin, domain.c:378; 0: equal
+ * counts), every particle's state crosses to its owner in one all-to-all of 256-byte records, and every rank stores what
+ * it now holds in Peano-Hilbert order.  Results do not depend on the assignment; this restores the balance and the
+ * pruning of the exchange after the particles have moved.  *n_new <- the particles this rank holds afterwards, *n_sent
+ * <- how many left it.  Particle ids (gl_run_set_ids; default: the global index before the first exchange) travel with
+ * the particles: gl_get_run_ids says which particle each row of gl_get_run_state / gl_get_* now is. */
+int gl_run_set_ids(gl_ctx * ctx, const int *ids, int where);
+int gl_get_run_ids(gl_ctx * ctx, int *ids, int where);
+int gl_domain_exchange(gl_ctx * ctx, int by_cost, long long *n_new, long long *n_sent);
 /* The same loop on the reference's own arrays: P[0..NumPart) / SphP[0..N_gas) are read once (everything the loop
  * carries: positions, velocities, VelPred, Hsml, entropies, time bins, the accelerations and SphP state of the last
  * force computation), nsteps iterations run on the device, and the structs are written once - where

@@ -176,7 +176,7 @@ def _loop_state(fp):
     return st
 
 
-def ranks_vs_one(world, nsteps=8, n_gas=24000):
+def ranks_vs_one(world, nsteps=8, n_gas=24000, exchange_after=None, skew=False, by_cost=True):
     """the loop on `world` in-process ranks and in one context from the same start; returns (errors, info of the one
     context, time-line mismatches)"""
     import threading
@@ -204,7 +204,9 @@ def ranks_vs_one(world, nsteps=8, n_gas=24000):
                                   MinEgySpec=0.0, SofteningTable=par["Softening"], OuterBoundary=1.4e10, UnitVelocity_in_cm_per_s=2.98e6,
                                   FeedBackVelocity=1.0, SMBHmass=0.5, InnerBoundary=0.0, SinkBoundary=0.0, AccDtBlackHole=0.007)
 
-    def drive(fp, p):
+    moved = {}
+
+    def drive(fp, p, ids=None, rank=None):
         fp.set_params(Ti_Current=64)
         fp.load(p)
         fp.compute_accelerations()          # Barnes-Hut pass + cold-start density: the state the loop starts from
@@ -213,23 +215,38 @@ def ranks_vs_one(world, nsteps=8, n_gas=24000):
         fp.run_begin(64)
         t = tpar(fp)
         fp.advance_and_find_timesteps(t)
-        info = fp.run(t, nsteps)
-        return _loop_state(fp), info, int(t.Ti_Current)
+        if exchange_after is None or ids is None:
+            info = fp.run(t, nsteps)
+        else:
+            fp.run_set_ids(ids)
+            info = fp.run(t, exchange_after)
+            moved[rank] = fp.domain_exchange(by_cost=by_cost) + (len(ids),)
+            info2 = fp.run(t, nsteps - exchange_after)
+            for k in ("steps_done", "active_total", "interactions"):
+                info[k] += info2[k]
+        st = _loop_state(fp)
+        if ids is not None and exchange_after is not None:
+            st["ids"] = fp.run_ids()
+        return st, info, int(t.Ti_Current)
 
     ref, info1, ti1 = drive(one, pso)
     one.close()
     lib = L.load_library()
     group = lib.gl_comm_local_group_create(world)
     m = -(-n // world)
+    # skew: a deliberately bad first assignment (rank 0 holds half of everything) for the exchange to repair
+    cuts = [0] + [min(n, (r + 1) * m) for r in range(world)]
+    if skew:
+        cuts = [0, n // 2] + [n // 2 + (n - n // 2) * (r + 1) // (world - 1) for r in range(world - 1)]
     res, err = [None] * world, [None] * world
 
     def worker(r):
         try:
-            lo, hi = r * m, min(n, (r + 1) * m)
+            lo, hi = cuts[r], cuts[r + 1]
             psr = {k: (np.ascontiguousarray(v[lo:hi]) if hasattr(v, "shape") and v.shape[0] == n else v) for k, v in pso.items()}
             fp = ForcePath(par)
             fp.comm_init_local(r, group, world)
-            res[r] = drive(fp, psr)
+            res[r] = drive(fp, psr, ids=np.arange(lo, hi, dtype=np.int32), rank=r)
             fp.close()
         except Exception as ex:   # noqa: BLE001
             err[r] = ex
@@ -242,7 +259,13 @@ def ranks_vs_one(world, nsteps=8, n_gas=24000):
     for e in err:
         if e is not None:
             raise e
-    cat = lambda k: np.concatenate([r[0][k] for r in res])       # noqa: E731
+    if exchange_after is not None:
+        ids = np.concatenate([r[0]["ids"] for r in res])
+        assert np.array_equal(np.sort(ids), np.arange(n)), "every particle is held by exactly one rank"
+        back = np.argsort(ids)                                     # rows of the concatenated ranks -> the order of the one context
+        cat = lambda k: np.concatenate([r[0][k] for r in res])[back]       # noqa: E731
+    else:
+        cat = lambda k: np.concatenate([r[0][k] for r in res])       # noqa: E731
     line = dict(Ti_Current=[r[2] != ti1 for r in res].count(True), TimeBin=int((cat("TimeBin") != ref["TimeBin"]).sum()),
                 Ti_begstep=int((cat("Ti_begstep") != ref["Ti_begstep"]).sum()),
                 active_total=int(sum(r[1]["active_total"] for r in res) - info1["active_total"]))
@@ -252,6 +275,8 @@ def ranks_vs_one(world, nsteps=8, n_gas=24000):
         errs[k] = util.rel_err_vec(cat(k), ref[k])
     for k in ("VelPred", "Entropy", "Density", "HydroAccel", "Pressure", "MaxSignalVel"):
         errs[k] = util.rel_err_vec(cat(k)[gas], ref[k][gas])
+    if exchange_after is not None:
+        return errs, info1, line, n, moved
     return errs, info1, line, n
 
 
@@ -379,3 +404,24 @@ def test_reference_harness_with_the_glue_resident_loop():
         else:
             err = util.rel_err_vec(a, b_)
         assert np.percentile(err, 99) < tol and err.max() < 100 * tol, util.summarize(k, err)
+
+
+@pytest.mark.parametrize("by_cost", [False, True])
+def test_domain_exchange_of_the_resident_state(by_cost):
+    """gl_domain_exchange (domain_exchange, domain.c:665, for the state in HBM): three ranks start from a deliberately
+    bad assignment (rank 0 holds half of all particles), run three steps, exchange - by equal counts, or by the reference's
+    cost (1 + GravCost) / 2^TimeBin - and run five more.  Every particle ends on exactly one rank, the loads are balanced,
+    and - because results do not depend on who owns what - the eight steps still end in the state of one context: time
+    line exact, gravity bitwise, the rest to FP64 summation order."""
+    errs, info1, line, n, moved = ranks_vs_one(3, nsteps=8, exchange_after=3, skew=True, by_cost=by_cost)
+    assert all(v == 0 for v in line.values()), line
+    for k, tol in (("Pos", 1e-13), ("Vel", 1e-10), ("GravAccel", 1e-10), ("Hsml", 1e-10), ("VelPred", 1e-10), ("Entropy", 1e-10),
+                   ("Density", 1e-10), ("HydroAccel", 1e-8), ("Pressure", 1e-10), ("MaxSignalVel", 1e-10)):
+        assert errs[k].max() < tol, util.summarize(k, errs[k])
+    held = [moved[r][0] for r in range(3)]
+    sent = [moved[r][1] for r in range(3)]
+    before = [moved[r][2] for r in range(3)]
+    assert sum(held) == n and before[0] == n // 2 and sum(sent) > 0
+    if not by_cost:
+        assert max(abs(h - n / 3) for h in held) < 0.02 * n, held      # equal counts (within the 2048-sample resolution)
+        assert sent[0] > 0.15 * n                                        # rank 0 gave a third of its half away
