@@ -986,6 +986,7 @@ extern "C" int gl_domain_exchange(gl_ctx *c, int by_cost, long long *n_new, long
   c->n_velpred = nn;
   c->have_velpred = true;
   c->n_tgt_in = -1;
+  c->tgt_host.clear();
   c->tgt_ordered = false;
   c->tgt_dirty = true;
   c->res_first = 0;
