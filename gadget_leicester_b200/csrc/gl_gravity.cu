@@ -31,6 +31,8 @@ gl_dparams gl_make_dparams(const gl_ctx *c);
 #define GW_ABS 3.4694469519536142e-18f	// 2^-58
 #define GW_ONE_LO (1.0f - GW_REL)
 #define GW_ONE_HI (1.0f + GW_REL)
+#define GW_TWO_LO (1.0f - 2.0f * GW_REL)
+#define GW_TWO_HI (1.0f + 2.0f * GW_REL)
 
 // The reference's opening decision for node entry e and ONE target, in FP64, statement by statement
 // (forcetree.c:2009-2011, :2074-2137).  Returns -1 = open, else the softening length to use for the accepted node.
@@ -87,16 +89,18 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
   if(last_first) warp = ((nt + 31) >> 5) - 1 - warp;
   const long long t = warp * 32 + lane;
   const bool live = t >= 0 && t < nt;
-  const double S = scale[0], Ms = scale[1];
-  int p = 0, ptype = 0, pin = 0;
+  // (p, its type, its input index and the two scales are only needed in the rare FP64 branch and in the epilogue: they are
+  //  fetched again there instead of living in registers through the march - at 48 registers the compiler otherwise spills
+  //  four of the six split coordinates and re-loads them from local memory in EVERY iteration)
   float thx = 0, thy = 0, thz = 0, tlx = 0, tly = 0, tlz = 0;	// split target position
-  float hif = 0, a_lo = 0, a_hi = 0;
+  float hif = 0, af = 0;
   if(live)
     {
-      p = tgt[t];
+      const double S = scale[0], Ms = scale[1];
+      const int p = tgt[t];
       const double4 pm = s_pm[p];
-      ptype = s_type[p];
-      pin = perm[p];
+      const int ptype = s_type[p];
+      const int pin = perm[p];
       gl_split(pm.x, dom.center[0], S, thx, tlx);
       gl_split(pm.y, dom.center[1], S, thy, tly);
       gl_split(pm.z, dom.center[2], S, thz, tlz);
@@ -104,9 +108,7 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
       hif = (float) (hi * S);
       // aold = ErrTolForceAcc * OldAcc (forcetree.c:1850), in the scaled units: x Ms / S^2
       const double aold = __dmul_rn(par.errtolforceacc, in_oldacc[pin]) * (Ms / (S * S));
-      const float af = (float) aold;
-      a_lo = af * GW_ONE_LO;
-      a_hi = af * GW_ONE_HI;
+      af = (float) aold;
     }
   const float thetaf = (float) par.theta;
   double ax = 0, ay = 0, az = 0;
@@ -151,10 +153,11 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 		{
 		  // forcetree.c:2085  mass*len*len > r2*r2*aold
 		  lhs = (F0.w * F1.w) * F1.w;
-		  t_hi = (r2hi * r2hi) * a_hi;
-		  t_lo = (r2lo * r2lo) * a_lo;
+		  t_hi = (r2hi * r2hi) * af;
+		  t_lo = (r2lo * r2lo) * af;
 		}
-	      const bool mac_open = lhs * GW_ONE_LO > t_hi, mac_closed = lhs * GW_ONE_HI < t_lo;
+	      // both margin factors sit on the node side: (1 - 2^-20) / (1 + 2^-20) > 1 - 2^-19 (one register for aold, not two)
+	      const bool mac_open = lhs * GW_TWO_LO > t_hi, mac_closed = lhs * GW_TWO_HI < t_lo;
 	      // forcetree.c:2094-2105  inside the 0.6*len box around the geometric centre (relative criterion only)
 	      const float cmax = fmaxf(fmaxf(fabsf(dx + F2.x), fabsf(dy + F2.y)), fabsf(dz + F2.z));
 	      const bool box_in = !BH && cmax < F1.w * (0.6f - GW_REL), box_out = BH || cmax > F1.w * (0.6f + GW_REL);
@@ -171,6 +174,9 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
 	      if(!sure)
 		{
 		  // the uncertain shell: the reference's own FP64 statements
+		  const int p = tgt[t];
+		  const int ptype = s_type[p], pin = perm[p];
+		  const double S = scale[0];
 		  const double4 pm = s_pm[p];
 		  const double hi = (ptype == 0) ? s_vh[p].w : par.soft[ptype];
 		  const double aold = __dmul_rn(par.errtolforceacc, in_oldacc[pin]);
@@ -249,6 +255,9 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
   if(live && POT)
     {
       // potential.c:169-184: remove the self term with All.SofteningTable, then x G (the Lambda term of :235 is 0 here)
+      const double S = scale[0], Ms = scale[1];
+      const int p = tgt[t];
+      const int ptype = s_type[p], pin = perm[p];
       const double m_i = s_pm[p].w;
       ax *= S / Ms;		// back from the scaled units: m'/r' = m/r * Ms / S
       o_pot[pin] = __dmul_rn(__dadd_rn(ax, __ddiv_rn(m_i, par.softtab[ptype])), par.G);
@@ -256,6 +265,9 @@ k_gravity_walk(const int *__restrict__ tgt, long long nt, int nentries, const in
   if(live && !POT)
     {
       // gravtree.c:388-403: OldAcc from the un-scaled acceleration, then x G (+ the Lambda term, :405-411)
+      const double S = scale[0], Ms = scale[1];
+      const int p = tgt[t];
+      const int pin = perm[p];
       const double un = (S * S) / Ms;	// d' m'/r'^3 = d m/r^3 * Ms / S^2
       ax *= un; ay *= un; az *= un;
       const double4 pm = s_pm[p];
