@@ -401,6 +401,45 @@ extern "C" int gl_run_kick(gl_ctx *c, const gl_timestep_params *tp, int commit_d
   return run_kick(c, tp, commit_dtentropy != 0);
 }
 
+// The time-line part of find_next_sync_point_and_drift (run.c:199-216, :276-290), as a plain host function of the ranks'
+// TimeBinCount[] rows (hist[32 r + b]: particles of rank r on bin b; slot 31 of a row = the particles the rank holds):
+// the next kick time - the reference takes MPI_Allreduce(MPI_MIN) of the ranks' own answers (run.c:218), which is the
+// answer for the summed counts -, the bins that are synchronised there, and the force updates of this rank and of all.
+extern "C" int gl_next_sync_point(const int *hist, int world, int rank, int Ti_Current, int *TimeBinActive, long long *nactive_own,
+				  long long *nactive_all, long long *particles_all)
+{
+  long long glob[32], own[32];
+  for(int b = 0; b < 32; b++)
+    {
+      glob[b] = 0;
+      for(int r = 0; r < world; r++) glob[b] += hist[32 * r + b];
+      own[b] = hist[32 * rank + b];
+    }
+  int ti_next_kick = TIMEBASE;
+  for(int b = 0; b < 29; b++)	// run.c:199-216
+    if(glob[b])
+      {
+	const int ti_next_for_bin = b > 0 ? (Ti_Current / (1 << b)) * (1 << b) + (1 << b) : Ti_Current;
+	if(ti_next_for_bin < ti_next_kick) ti_next_kick = ti_next_for_bin;
+      }
+  long long na = own[0], ng = glob[0];
+  TimeBinActive[0] = 1;	// run.c:276-288
+  for(int b = 1; b < 29; b++)
+    {
+      TimeBinActive[b] = (ti_next_kick % (1 << b)) == 0;
+      if(TimeBinActive[b])
+	{
+	  na += own[b];
+	  ng += glob[b];
+	}
+    }
+  for(int b = 29; b < 32; b++) TimeBinActive[b] = 0;
+  if(nactive_own) *nactive_own = na;
+  if(nactive_all) *nactive_all = ng;
+  if(particles_all) *particles_all = glob[31];
+  return ti_next_kick;
+}
+
 extern "C" int gl_run_steps(gl_ctx *c, gl_timestep_params *tp, int nsteps, gl_run_info *info)
 {
   cudaSetDevice(c->device);
@@ -434,35 +473,11 @@ extern "C" int gl_run_steps(gl_ctx *c, gl_timestep_params *tp, int nsteps, gl_ru
       else
 	GL_CUDA(c, cudaMemcpyAsync(hist, c->run_hist.p, 32 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       GL_CUDA(c, cudaStreamSynchronize(c->stream));
-      long long glob[32], own[32];
-      for(int b = 0; b < 32; b++)
-	{
-	  glob[b] = 0;
-	  for(int r = 0; r < W; r++) glob[b] += hist[32 * r + b];
-	  own[b] = hist[32 * (W > 1 ? c->comm->rank : 0) + b];
-	}
-      int ti_next_kick = TIMEBASE;
-      for(int b = 0; b < 29; b++)	// run.c:199-216
-	if(glob[b])
-	  {
-	    const int ti_next_for_bin = b > 0 ? (tp->Ti_Current / (1 << b)) * (1 << b) + (1 << b) : tp->Ti_Current;
-	    if(ti_next_for_bin < ti_next_kick) ti_next_kick = ti_next_for_bin;
-	  }
-      if(ti_next_kick >= TIMEBASE && tp->Ti_Current >= TIMEBASE) break;	// the end of the time line has been reached
       const int time0 = tp->Ti_Current;
+      long long nactive = 0, nactive_glob = 0, total = 0;
+      const int ti_next_kick = gl_next_sync_point(hist, W, W > 1 ? c->comm->rank : 0, time0, tp->TimeBinActive, &nactive, &nactive_glob, &total);
+      if(ti_next_kick >= TIMEBASE && time0 >= TIMEBASE) break;	// the end of the time line has been reached
       tp->Ti_Current = ti_next_kick;
-      long long nactive = own[0], nactive_glob = glob[0];
-      tp->TimeBinActive[0] = 1;	// run.c:276-288
-      for(int b = 1; b < 29; b++)
-	{
-	  tp->TimeBinActive[b] = (ti_next_kick % (1 << b)) == 0;
-	  if(tp->TimeBinActive[b])
-	    {
-	      nactive += own[b];
-	      nactive_glob += glob[b];
-	    }
-	}
-      for(int b = 29; b < 32; b++) tp->TimeBinActive[b] = 0;
       const RunPar T = make_runpar(tp);
       // drift everything to the sync point (see the header of this file)
       if(ti_next_kick != time0)
@@ -483,8 +498,6 @@ extern "C" int gl_run_steps(gl_ctx *c, gl_timestep_params *tp, int nsteps, gl_ru
       c->tgt_dirty = true;
       if(!c->domain_imposed) c->have_domain = false;
       // ---- the active list (run.c:296-320): particles on active bins, as targets of the force path ----
-      long long total = 0;
-      for(int r = 0; r < W; r++) total += hist[32 * r + 31];
       if(nactive_glob >= total)
 	{
 	  if(gl_set_targets(c, nullptr, -1, 0)) return 1;

@@ -146,7 +146,7 @@ EXPORTS = [
     "gl_set_subgrid_params", "gl_blackhole_accretion", "gl_dust_density", "gl_dust_drag",
     "gl_gadget_blackhole_accretion", "gl_gadget_dust_density", "gl_gadget_dust_drag", "gl_hdf5_read_f64",
     "gl_domain_assign", "gl_domain_count_to_go", "gl_domain_split_collective",
-    "gl_set_velpred", "gl_set_accelerations", "gl_run_begin", "gl_run_kick", "gl_run_steps", "gl_get_run_state", "gl_gadget_run_steps", "gl_run_set_ids", "gl_get_run_ids", "gl_domain_exchange",
+    "gl_set_velpred", "gl_set_accelerations", "gl_run_begin", "gl_run_kick", "gl_run_steps", "gl_get_run_state", "gl_gadget_run_steps", "gl_next_sync_point", "gl_run_set_ids", "gl_get_run_ids", "gl_domain_exchange",
 ]
 
 _lib = None
@@ -254,6 +254,7 @@ def load_library():
     lib.gl_run_steps.argtypes = [vp, C.POINTER(GLTimestepParams), C.c_int, C.POINTER(GLRunInfo)]
     lib.gl_get_run_state.argtypes = [vp] + [vp] * 8 + [C.c_int]
     lib.gl_gadget_run_steps.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, C.POINTER(GLTimestepParams), C.c_int, C.POINTER(GLRunInfo)]
+    lib.gl_next_sync_point.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.gl_run_set_ids.argtypes = [vp, vp, C.c_int]
     lib.gl_get_run_ids.argtypes = [vp, vp, C.c_int]
     lib.gl_domain_exchange.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]

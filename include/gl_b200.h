@@ -361,6 +361,12 @@ typedef struct gl_run_info
   long long interactions;	/* gravity interactions summed over the steps */
   double ms_total;		/* device time of the whole call */
 } gl_run_info;
+/* The time-line arithmetic of find_next_sync_point_and_drift (run.c:199-216, :276-290) on the ranks' TimeBinCount[] rows -
+ * hist[32 r + b] = particles of rank r on time bin b (b < 29), hist[32 r + 31] = particles rank r holds.  Returns the next
+ * kick time (the reference's MPI_Allreduce(MPI_MIN) over the ranks, run.c:218), fills TimeBinActive[32] for it and
+ * counts the force updates of `rank` and of all ranks.  Host code only - gl_run_steps calls it with the all-gathered rows. */
+int gl_next_sync_point(const int *hist, int world, int rank, int Ti_Current, int *TimeBinActive, long long *nactive_own,
+		       long long *nactive_all, long long *particles_all);
 /* nsteps iterations of the loop; par->Ti_Current and par->TimeBinActive[] are advanced in place (the caller's
  * All.Ti_Current / TimeBinActive[]) */
 int gl_run_steps(gl_ctx * ctx, gl_timestep_params * par, int nsteps, gl_run_info * info);
