@@ -301,8 +301,9 @@ int run_kick(gl_ctx *c, const gl_timestep_params *tp, bool commit_dtentropy)
 extern "C" int gl_set_velpred(gl_ctx *c, const double *velpred3, long long n_gas, int where)
 {
   cudaSetDevice(c->device);
+  const long long n_all = c->n_own > 0 ? c->n_own : c->n;	// (multi-rank mode: imports of a tree are not the caller's particles)
   if(c->n <= 0) return c->fail("gl_set_velpred: no particles");
-  if(n_gas < 0 || n_gas > c->n || (n_gas > 0 && !velpred3)) return c->fail("gl_set_velpred: bad arguments");
+  if(n_gas < 0 || n_gas > n_all || (n_gas > 0 && !velpred3)) return c->fail("gl_set_velpred: bad arguments");
   GL_CUDA(c, c->in_velpred.ensure(3 * (size_t) std::max<long long>(n_gas, 1)));
   if(n_gas > 0)
     GL_CUDA(c, cudaMemcpyAsync(c->in_velpred.p, velpred3, 3 * n_gas * sizeof(double), where ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
@@ -318,22 +319,22 @@ extern "C" int gl_set_velpred(gl_ctx *c, const double *velpred3, long long n_gas
 extern "C" int gl_set_accelerations(gl_ctx *c, const double *gravaccel3, const double *hydroaccel3, const double *maxsignalvel, int where)
 {
   cudaSetDevice(c->device);
-  const long long n = c->n;
+  const long long n = c->n_own > 0 ? c->n_own : c->n;	// (multi-rank mode: imports of a tree are not the caller's particles)
   if(n <= 0) return c->fail("gl_set_accelerations: no particles");
   const cudaMemcpyKind k = where ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if(gravaccel3)
     {
-      GL_CUDA(c, c->o_acc.ensure(3 * (size_t) n));
+      GL_CUDA(c, c->o_acc.ensure_keep(3 * (size_t) n));
       GL_CUDA(c, cudaMemcpyAsync(c->o_acc.p, gravaccel3, 3 * n * sizeof(double), k, c->stream));
     }
   if(hydroaccel3)
     {
-      GL_CUDA(c, c->o_hacc.ensure(3 * (size_t) n));
+      GL_CUDA(c, c->o_hacc.ensure_keep(3 * (size_t) n));
       GL_CUDA(c, cudaMemcpyAsync(c->o_hacc.p, hydroaccel3, 3 * n * sizeof(double), k, c->stream));
     }
   if(maxsignalvel)
     {
-      GL_CUDA(c, c->o_maxsig.ensure((size_t) n));
+      GL_CUDA(c, c->o_maxsig.ensure_keep((size_t) n));
       GL_CUDA(c, cudaMemcpyAsync(c->o_maxsig.p, maxsignalvel, n * sizeof(double), k, c->stream));
     }
   GL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -355,20 +356,27 @@ extern "C" int gl_run_begin(gl_ctx *c, int Ti_Current)
   GL_CUDA(c, c->run_err.ensure(48));
   GL_CUDA(c, c->run_hist.ensure(32 * (size_t) (W + 1)));
   if(c->o_acc.cap < 3 * (size_t) n) return c->fail("gl_run_begin: no gravitational accelerations in the context (force computation or gl_set_accelerations)");
-  // (a set without gas never allocates the SphP arrays; the kernels only read them where the type is 0)
-  const bool sph = c->o_density.cap >= (size_t) n;
-  if(sph)
+  // how many gas particles: a set without gas never allocates the SphP arrays (the kernels only read them where the type is 0)
+  GL_CUDA(c, cudaMemsetAsync(c->run_err.p, 0, 48 * sizeof(int), c->stream));
+  k_run_bins<<<148 * 4, 256, 0, c->stream>>>(n, c->in_type.p, c->run_err.p + 8);	// histogram of the types: slot 8 = type 0
+  GL_LAUNCH_COUNT(c);
+  int ngas = 0;
+  GL_CUDA(c, cudaMemcpyAsync(&ngas, c->run_err.p + 8, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if(ngas > 0)
     {
+      if(c->o_density.cap < (size_t) n || c->o_pressure.cap < (size_t) n || c->o_divvel.cap < (size_t) n || c->o_dhsml.cap < (size_t) n ||
+	 c->o_curlvel.cap < (size_t) n)
+	return c->fail("gl_run_begin: no SphP state in the context (density or gl_set_sph_state)");
       if(c->o_hacc.cap < 3 * (size_t) n || c->o_maxsig.cap < (size_t) n)
 	return c->fail("gl_run_begin: no hydro accelerations / signal velocities in the context (hydro_force or gl_set_accelerations)");
       GL_CUDA(c, c->o_dtentr.ensure_keep((size_t) n));
-      if(c->o_pressure.cap < (size_t) n || c->o_divvel.cap < (size_t) n || c->o_dhsml.cap < (size_t) n || c->o_curlvel.cap < (size_t) n)
-	return c->fail("gl_run_begin: incomplete SphP state in the context (density or gl_set_sph_state)");
     }
   else
     {
-      // no SphP state: fine as long as there is no gas (checked on the device below)
-      GL_CUDA(c, cudaMemsetAsync(c->run_err.p, 0, 48 * sizeof(int), c->stream));
+      // the kernels are handed these pointers whatever the types are
+      GL_CUDA(c, c->o_hacc.ensure_keep(8)); GL_CUDA(c, c->o_maxsig.ensure_keep(8)); GL_CUDA(c, c->o_density.ensure_keep(8));
+      GL_CUDA(c, c->o_pressure.ensure_keep(8)); GL_CUDA(c, c->o_divvel.ensure_keep(8)); GL_CUDA(c, c->o_dtentr.ensure_keep(8));
     }
   const long long have = c->have_velpred ? std::min(c->n_velpred, n) : 0;
   GL_CUDA(c, c->in_velpred.ensure_keep(3 * (size_t) n));
@@ -376,18 +384,6 @@ extern "C" int gl_run_begin(gl_ctx *c, int Ti_Current)
   GL_LAUNCH_COUNT(c);
   c->n_velpred = n;
   c->have_velpred = true;
-  if(!sph)
-    {
-      k_run_bins<<<148 * 4, 256, 0, c->stream>>>(n, c->in_type.p, c->run_err.p + 8);	// histogram of the types: slot 8 = type 0
-      GL_LAUNCH_COUNT(c);
-      int ngas = 0;
-      GL_CUDA(c, cudaMemcpyAsync(&ngas, c->run_err.p + 8, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      GL_CUDA(c, cudaStreamSynchronize(c->stream));
-      if(ngas > 0) return c->fail("gl_run_begin: no SphP state in the context (density or gl_set_sph_state)");
-      // the kernels are handed these pointers whatever the types are
-      GL_CUDA(c, c->o_hacc.ensure(8)); GL_CUDA(c, c->o_maxsig.ensure(8)); GL_CUDA(c, c->o_density.ensure(8));
-      GL_CUDA(c, c->o_pressure.ensure(8)); GL_CUDA(c, c->o_divvel.ensure(8)); GL_CUDA(c, c->o_dtentr.ensure(8));
-    }
   c->run_ti = Ti_Current;
   c->run_ready = true;
   return 0;
