@@ -839,10 +839,77 @@ __global__ void k_export_nodes(long long m, long long nentries, gl_tree_layout L
   *(int *) (nd + L.n_sibling) = ref_index(e_next[e], nentries, e_next, e_rng, perm, maxpart);
   *(int *) (nd + L.n_father) = (n_parent[id] >= 0) ? maxpart + n_parent[id] : -1;
   *(int *) (nd + L.n_Ti_current) = ti_current;
-  // extNODE: vs / divVmax / dp only feed the dynamic tree update (force_drift_node), which a per-step rebuild never runs
+  // extNODE: vs / divVmax follow from k_export_velocity_moments; dp starts at zero (forcetree.c:742-744)
   *(double *) (ex + L.e_vmax) = ax.z;
   *(double *) (ex + L.e_hmax) = e_hmax[e];
   *(int *) (ex + L.e_Ti_lastkicked) = ti_current;
+}
+
+// extNODE.vs / .divVmax (forcetree.c:522-545 initial values, :571-573 / :609-610 child cells, :650-652 / :679-681
+// particles, :704-706 division by the mass): the mass-weighted velocity of the cell in child-slot order, and the largest
+// SphP.v.DivVel below it.  Only force_drift_node / force_kick_node read them (the dynamic tree update), so this pass runs
+// in the export and not in the build: one launch per level, bottom-up, over the child table the moment pass left.
+__global__ void k_export_velocity_moments(int count, const int *__restrict__ lev_list, const int *__restrict__ n_child,
+					  const int *__restrict__ n_first, const int *__restrict__ n_end, const int2 *__restrict__ e_rng,
+					  const double4 *__restrict__ n_sm, const double4 *__restrict__ s_pm, const int *__restrict__ s_type,
+					  const int *__restrict__ perm, const double *__restrict__ in_vel, const double *__restrict__ divvel,
+					  double4 *__restrict__ vsd)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= count) return;
+  const int id = lev_list[t];
+  const int *tab = n_child + 8ll * id;
+  double v0 = 0, v1 = 0, v2 = 0, dmax = 0;
+  auto particle = [&](int p) {
+    const int i = perm[p];
+    const double m = s_pm[p].w;
+    v0 = __dadd_rn(v0, __dmul_rn(m, in_vel[3ll * i]));
+    v1 = __dadd_rn(v1, __dmul_rn(m, in_vel[3ll * i + 1]));
+    v2 = __dadd_rn(v2, __dmul_rn(m, in_vel[3ll * i + 2]));
+    if(s_type[p] == 0 && divvel && divvel[i] > dmax) dmax = divvel[i];
+  };
+  if(tab[0] == INT_MIN)
+    for(int p = n_first[id]; p < n_end[id]; p++) particle(p);	// finest-level cell with coincident keys: every particle hangs directly below
+  else
+    for(int k = 0; k < 8; k++)
+      {
+	const int code = tab[k];
+	if(code == -1) break;
+	if(code <= -2)
+	  particle(-(code + 2));
+	else
+	  {
+	    const int child = code - e_rng[code].x;	// DFS entry -> cell index
+	    const double m = n_sm[child].w;
+	    const double4 cv = vsd[child];
+	    v0 = __dadd_rn(v0, __dmul_rn(m, cv.x));
+	    v1 = __dadd_rn(v1, __dmul_rn(m, cv.y));
+	    v2 = __dadd_rn(v2, __dmul_rn(m, cv.z));
+	    if(cv.w > dmax) dmax = cv.w;
+	  }
+      }
+  const double mass = n_sm[id].w;
+  if(mass != 0)
+    {
+      v0 = __ddiv_rn(v0, mass); v1 = __ddiv_rn(v1, mass); v2 = __ddiv_rn(v2, mass);
+    }
+  else
+    v0 = v1 = v2 = 0;
+  vsd[id] = make_double4(v0, v1, v2, dmax);
+}
+
+__global__ void k_export_vs_store(long long m, gl_tree_layout L, const double4 *__restrict__ vsd, char *__restrict__ ext)
+{
+  const long long id = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if(id >= m) return;
+  char *ex = ext + id * L.ext_stride;
+  const double4 v = vsd[id];
+  if(L.e_vs >= 0)
+    {
+      double *o = (double *) (ex + L.e_vs);
+      o[0] = v.x; o[1] = v.y; o[2] = v.z;
+    }
+  if(L.e_divVmax >= 0) *(double *) (ex + L.e_divVmax) = v.w;
 }
 
 __global__ void k_export_particles(long long n, long long nentries, int maxpart, const int *__restrict__ noff,
@@ -882,6 +949,23 @@ extern "C" int gl_export_tree(gl_ctx *c, const gl_tree_layout *lay, void *nodes_
 							    c->perm.p, dn.p, de.p);
       GL_LAUNCH_COUNT(c);
     }
+  DBuf<double4> vsd;
+  if(m > 0 && (lay->e_vs >= 0 || lay->e_divVmax >= 0))
+    {
+      GL_CUDA(c, vsd.ensure((size_t) m));
+      const double *divv = c->o_divvel.cap >= (size_t) n ? c->o_divvel.p : nullptr;	// SphP.v.DivVel as the last density() left it
+      for(int L = GL_BITS; L >= 0; L--)
+	{
+	  const int cnt = c->lev_start[L + 1] - c->lev_start[L];
+	  if(cnt <= 0) continue;
+	  k_export_velocity_moments<<<gl_grid(cnt, 128), 128, 0, c->stream>>>(cnt, c->lev_list.p + c->lev_start[L], c->n_child.p, c->n_first.p,
+									      c->n_end.p, c->e_rng.p, c->n_sm.p, c->s_pm.p, c->s_type.p, c->perm.p,
+									      c->in_vel.p, divv, vsd.p);
+	  GL_LAUNCH_COUNT(c);
+	}
+      k_export_vs_store<<<gl_grid(m, 256), 256, 0, c->stream>>>(m, *lay, vsd.p, de.p);
+      GL_LAUNCH_COUNT(c);
+    }
   k_export_particles<<<gl_grid(n, 256), 256, 0, c->stream>>>(n, c->nentries, (int) MaxPart, c->noff.p, c->p_father.p, c->e_next.p,
 							      c->e_rng.p, c->perm.p, dx.p, dx.p + n);
   GL_LAUNCH_COUNT(c);
@@ -894,6 +978,7 @@ extern "C" int gl_export_tree(gl_ctx *c, const gl_tree_layout *lay, void *nodes_
   dn.release();
   de.release();
   dx.release();
+  vsd.release();
   if(numnodes) *numnodes = m;
   return 0;
 }

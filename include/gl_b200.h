@@ -403,7 +403,9 @@ int gl_gadget_run_steps(gl_ctx * ctx, void *P, void *SphP, long long NumPart, lo
  * :1887) with the threading of force_update_node_recursive (forcetree.c:468-872): nextnode = first daughter,
  * sibling = next entry behind the subtree, Nextnode[i] = entry behind particle i, Father[i] = its parent cell;
  * node k of the library is Nodes[MaxPart + k], the root is Nodes[MaxPart] (density.c:804).  Offsets come from the
- * reference side via offsetof(), like gl_gadget_layout.  Single rank only: no pseudo-particles are inserted. */
+ * reference side via offsetof(), like gl_gadget_layout.  extNODE.vs / .divVmax (forcetree.c:684-706, what force_drift_node
+ * / force_kick_node read) are formed here - a bottom-up pass in child-slot order from P.Vel and the SphP.v.DivVel of the
+ * last density() - when their offsets are >= 0; dp = 0.  Single rank only: no pseudo-particles are inserted. */
 typedef struct gl_tree_layout
 {
   long long node_stride, ext_stride;	/* sizeof(struct NODE), sizeof(struct extNODE) */

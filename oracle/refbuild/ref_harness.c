@@ -353,6 +353,16 @@ static void dump_nodes(const char *prefix)
     }
   put(prefix, "nodes", 'd', nn, 11, buf);
   put(prefix, "nodeflags", 'i', nn, 1, fl);
+  /* the velocity moments of extNODE (forcetree.c:684-706): what the dynamic tree update reads */
+  for(k = 0; k < nn; k++)
+    {
+      int no = All.MaxPart + (int) k;
+      buf[4 * k + 0] = Extnodes[no].vs[0];
+      buf[4 * k + 1] = Extnodes[no].vs[1];
+      buf[4 * k + 2] = Extnodes[no].vs[2];
+      buf[4 * k + 3] = Extnodes[no].divVmax;
+    }
+  put(prefix, "nodes_vel", 'd', nn, 4, buf);
   dom[0] = DomainLen; dom[1] = DomainFac;
   dom[2] = DomainCorner[0]; dom[3] = DomainCorner[1]; dom[4] = DomainCorner[2];
   dom[5] = DomainCenter[0]; dom[6] = DomainCenter[1]; dom[7] = DomainCenter[2];

@@ -676,3 +676,36 @@ def test_library_has_no_oracle_dependency():
         if os.path.exists(p):
             src = open(p).read()
             assert "oracle" not in src.replace("Nothing under oracle/ is imported here", "")
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/ref_harness not built (needs /root/reference)")
+def test_exported_velocity_moments_equal_the_reference():
+    """extNODE.vs and .divVmax (forcetree.c:684-706; read by the dynamic tree update force_drift_node / force_kick_node)
+    as gl_export_tree writes them, against the tree the reference builds after a density(): vs - mass-weighted P.Vel in
+    child-slot order - bit for bit, divVmax to the 1e-12 of the DivVel sums it is the maximum of."""
+    from gadget_leicester_b200 import aos
+    from gadget_leicester_b200.gadget import ForcePath
+    ps, par = ics.disc(6000, seed=19), ics.default_params()
+    n = ps["pos"].shape[0]
+    ngas = int((ps["type"] == 0).sum())
+    ref = util.run_oracle(util.REF_HARNESS, ps, par, "T S D R G N")
+    rn, rv, rf = ref["5_N_nodes"], ref["5_N_nodes_vel"], ref["5_N_nodeflags"]
+    keep = (rf & 128) != 0
+    rn, rv = rn[keep], rv[keep]
+    ps2 = dict(ps, hsml=util.by_id(ref, "2_D_", "Hsml", n))
+    fp = ForcePath(par)
+    fp.load(ps2)
+    d = fp.density()                      # leaves SphP.v.DivVel in the context, like the reference's D before its rebuild
+    assert d["Hsml"].shape[0] == n
+    fp.set_TreeReconstructFlag(1)
+    fp.gravity_tree()
+    T = aos.ReferenceTree(fp, max_part=n + 10)
+    ctr, ln = T.nfield("n_center", np.float64, 3), T.nfield("n_len", np.float64)
+    vs, dv = T.efield("e_vs", np.float64, 3), T.efield("e_divVmax", np.float64)
+    mine = {(ln[k], ctr[k, 0], ctr[k, 1], ctr[k, 2]): k for k in range(T.Numnodestree)}
+    assert len(mine) == rn.shape[0]
+    idx = np.array([mine[tuple(r[0:4])] for r in rn])
+    assert np.array_equal(vs[idx], rv[:, 0:3]), "vs differs: max %g" % np.abs(vs[idx] - rv[:, 0:3]).max()
+    assert (rv[:, 3] >= 0).all() and rv[:, 3].max() > 0
+    assert np.abs(dv[idx] - rv[:, 3]).max() <= 1e-10 * rv[:, 3].max()
+    fp.close()
