@@ -159,3 +159,17 @@ def test_host_worker_pool_native(tmp_path, sanitizer):
     assert cc.returncode == 0, cc.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, GL_HOST_THREADS="6"))
     assert r.returncode == 0 and "HOSTPOOL OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_timestep_params_mirror_of_the_reference_globals():
+    """ForcePath.timestep_params (host mirror of gl_timestep_params): All.* names in, the struct the resident loop and the
+    host kick read out - no GPU involved."""
+    from gadget_leicester_b200.gadget import ForcePath
+    t = ForcePath.timestep_params(64, [1 if b <= 6 else 0 for b in range(29)], Timebase_interval=4.0e-5, ErrTolIntAccuracy=0.025,
+                                  CourantFac=0.15, MaxSizeTimestep=8.0e-3, MinSizeTimestep=0.0, MinEgySpec=1.8,
+                                  SofteningTable=[1e-5, 0.01, 5e-5, 1e-7, 0.01, 5e-5], SMBHmass=0.5)
+    assert t.Ti_Current == 64 and list(t.TimeBinActive)[:8] == [1] * 7 + [0] and sum(t.TimeBinActive) == 7
+    assert t.Timebase_interval == 4.0e-5 and t.MaxSizeTimestep == 8.0e-3 and t.MinEgySpec == 1.8
+    assert abs(t.GammaMinus1 - 0.4) < 1e-15                                   # GAMMA = 7/5 (allvars.h:64)
+    assert t.SofteningTable[5] == 5e-5 and t.SMBHmass == 0.5
+    assert t.p_DeltaDustMomentum == -1 and t.p_NewDensity == -1              # SoA state: no struct offsets
